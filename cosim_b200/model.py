@@ -1,0 +1,420 @@
+"""Model builder: (config dict, baked assets) -> flat model blob.
+
+Replaces, for the batched engine, what the reference does by rewriting the MJCF and
+letting MuJoCo recompile it per env instance:
+  * XMLManager.get_model_path  (/root/reference/envs/flamingo_p_v3/manager/xml_manager.py:16-121):
+    terrain select, precision (timestep / iterations), which bodies get mass noise and load,
+    which geoms / dofs receive the random friction / frictionloss  -> *flags and ranges*
+    in the blob; the per-env draws themselves happen on the device (counter-based RNG).
+  * MjModel.from_xml_path (gymnasium MujocoEnv.__init__, flamingo_p_v3.py:94-100):
+    hfield PNG normalisation + row flip [upstream MuJoCo, SURVEY.md A.4], qpos0, connect anchors.
+  * the per-robot constants of envs/<robot>/<robot>.py (tables in cosim_b200/robots.py).
+
+Blob layout ("CSB1"): u32 magic, u32 nsections, then nsections directory entries
+{char name[24]; u32 dtype (0=i32,1=f32,2=f64); u32 pad; u64 count; u64 offset}, then 16-byte
+aligned payloads.  `include/cosim_blob.h` is the C view of the same contract.
+"""
+import math
+import os
+import struct
+
+import numpy as np
+
+from .robots import ROBOTS, OBS_DIMS, POS, VEL
+
+_ASSETS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "assets")
+
+# ---- dims / opts indices (keep in sync with include/cosim_blob.h) ----
+DIMS = ["nq", "nv", "nu", "nbody", "njnt", "ngeom", "nhullvert", "neq", "ground_type", "hf_nrow", "hf_ncol",
+        "frame_skip", "iterations", "ls_iterations", "ccd_iterations", "ncon_max", "hm_res_x", "hm_res_y",
+        "state_dim", "stack_size", "stacked_dim", "nonstacked_dim", "command_dim", "n_term_body", "n_dofpos",
+        "n_dofvel", "n_initnoise", "max_episode_steps", "lin_vel_f32", "n_sobs", "n_nobs", "cache_dim",
+        "n_state_pos", "n_state_vel", "position_command", "nefc_max", "imu_body", "n_massnoise", "base_body",
+        "zero_noise", "auto_reset", "nfl", "nlimit_max"]
+OPTS = ["timestep", "gx", "gy", "gz", "tolerance", "ls_tolerance", "ccd_tolerance", "hf_sx", "hf_sy", "hf_sz",
+        "hf_base", "z0", "hm_size_x", "hm_size_y", "hm_zmin", "term_threshold", "init_noise",
+        "solref0", "solref1", "solimp0", "solimp1", "solimp2", "solimp3", "solimp4",
+        "slide_lo", "slide_hi", "tors_lo", "tors_hi", "roll_lo", "roll_hi", "floss_lo", "floss_hi",
+        "delay_lo", "delay_hi", "mass_noise", "load_lo", "load_hi", "kp_lo", "kp_hi", "kd_lo", "kd_hi",
+        "plane_sx", "plane_sy"]
+DIM = {k: i for i, k in enumerate(DIMS)}
+OPT = {k: i for i, k in enumerate(OPTS)}
+
+OBS_KINDS = {"dof_pos": 0, "dof_vel": 1, "ang_vel": 2, "lin_vel": 3, "projected_gravity": 4,
+             "last_action": 5, "height_map": 6, "command": 7}
+NOISE_ORDER = ["dof_pos", "dof_vel", "ang_vel", "lin_vel", "projected_gravity", "height_map"]
+
+
+def load_robot(robot_id):
+    z = np.load(os.path.join(_ASSETS, f"robot_{robot_id}.npz"), allow_pickle=False)
+    return {k: z[k] for k in z.files}
+
+
+def load_terrain_raster(name):
+    z = np.load(os.path.join(_ASSETS, f"terrain_{name}.npz"), allow_pickle=False)
+    if "alias" in z.files:
+        z = np.load(os.path.join(_ASSETS, f"terrain_{str(z['alias'])}.npz"), allow_pickle=False)
+    return z["raster"]
+
+
+def hfield_from_raster(raster_u8):
+    """PNG raster -> MuJoCo hfield_data (float32, row 0 = -y edge, normalised to [0,1]).
+
+    [upstream MuJoCo 3.2.7 user_objects: LoadPNG flips rows so image-top is +y; Compile subtracts
+    the minimum and divides by the range]  (confidence M)."""
+    data = raster_u8[::-1, :].astype(np.float32)
+    emin, emax = float(data.min()), float(data.max())
+    data = data - np.float32(emin)
+    if emax - emin > 1e-15:
+        data = data / np.float32(emax - emin)
+    return np.ascontiguousarray(data, dtype=np.float32)
+
+
+# ------------------------------------------------------------------ small numpy FK (qpos0 only)
+def _quat_mul(a, b):
+    return np.array([a[0] * b[0] - a[1] * b[1] - a[2] * b[2] - a[3] * b[3],
+                     a[0] * b[1] + a[1] * b[0] + a[2] * b[3] - a[3] * b[2],
+                     a[0] * b[2] - a[1] * b[3] + a[2] * b[0] + a[3] * b[1],
+                     a[0] * b[3] + a[1] * b[2] - a[2] * b[1] + a[3] * b[0]])
+
+
+def _quat_mat(q):
+    w, x, y, z = q
+    return np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                     [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                     [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+
+
+def fk_qpos0(rb, base_pos=None):
+    """World pose of every body at the reference pose (joints at 0). Returns (xpos[nb,3], xquat[nb,4])."""
+    nb = len(rb["body_mass"])
+    xpos = np.zeros((nb + 1, 3))
+    xquat = np.zeros((nb + 1, 4))
+    xquat[0, 0] = 1
+    for i in range(nb):
+        p = int(rb["body_parent"][i])
+        R = _quat_mat(xquat[p])
+        xpos[i + 1] = xpos[p] + R @ rb["body_pos"][i]
+        xquat[i + 1] = _quat_mul(xquat[p], rb["body_quat"][i])
+        if i == 0 and base_pos is not None:
+            xpos[1] = base_pos
+    return xpos, xquat
+
+
+def _ncdf(x):
+    return 0.5 * math.erfc(-x / math.sqrt(2.0))
+
+
+def _rng_pair(v):
+    if isinstance(v, (list, tuple)):
+        return float(v[0]), float(v[1])
+    return float(v), float(v)
+
+
+class Model:
+    """Holds the named sections and the packed blob."""
+
+    def __init__(self, sections, meta):
+        self.sections = sections
+        self.meta = meta
+        self.blob = pack_blob(sections)
+
+    def dim(self, name):
+        return int(self.sections["dims"][DIM[name]])
+
+    def opt(self, name):
+        return float(self.sections["opts"][OPT[name]])
+
+
+def pack_blob(sections):
+    names = list(sections)
+    hdr = 8 + 48 * len(names)
+    off = (hdr + 15) // 16 * 16
+    entries, payload = [], []
+    for n in names:
+        a = np.ascontiguousarray(sections[n])
+        dt = {np.dtype(np.int32): 0, np.dtype(np.float32): 1, np.dtype(np.float64): 2}[a.dtype]
+        raw = a.tobytes()
+        entries.append(struct.pack("<24sIIQQ", n.encode()[:23], dt, 0, a.size, off))
+        pad = (-len(raw)) % 16
+        payload.append(raw + b"\0" * pad)
+        off += len(raw) + pad
+    head = struct.pack("<4sI", b"CSB1", len(names)) + b"".join(entries)
+    head += b"\0" * ((-len(head)) % 16)
+    return head + b"".join(payload)
+
+
+def build_model(config, ncon_max=None, auto_reset=False):
+    env_id = config["env"]["id"]
+    if env_id not in ROBOTS:
+        raise NameError(f"Please select a valid environment id. Received '{env_id}'.")
+    spec = ROBOTS[env_id]
+    rb = load_robot(env_id)
+    obs_cfg = config["observation"]
+    rnd = config["random"]
+    hw = config["hardware"]
+    rtab = config["random_table"]
+    eng = config.get("engine", {}) or {}
+
+    nb = len(rb["body_mass"]) + 1           # incl. world
+    njnt = len(rb["jnt_type"])
+    nv = len(rb["dof_body"])
+    nq = int(sum(7 if t == 0 else 1 for t in rb["jnt_type"]))
+    nu = len(rb["act_joint"])
+    ngeom = len(rb["geom_type"])
+    jname = {str(n): i for i, n in enumerate(rb["jnt_names"])}
+    bname = {str(n): i + 1 for i, n in enumerate(rb["body_names"])}
+
+    # ---- precision (xml_manager.py:34-41, flamingo_p_v3.py:48-55)
+    prec = rtab["precision"][rnd["precision"]]
+    timestep, iterations, frame_skip = float(prec["timestep"]), int(prec["iterations"]), int(prec["frame_skip"])
+    control_freq = 1.0 / (timestep * frame_skip)
+    assert control_freq == 50, "Currently, only control frequency of 50 is supported."
+
+    # ---- terrain (xml_manager.py:21-32)
+    terrain = config["env"]["terrain"]
+    if terrain == "flat":
+        ground_type, hf = 0, np.zeros((1, 1), np.float32)
+        hf_size = np.zeros(4)
+    else:
+        names = [str(n) for n in rb["hfield_names"]]
+        if terrain not in names:
+            raise ValueError(f"unknown terrain '{terrain}' for {env_id}")
+        ground_type = 1
+        hf = hfield_from_raster(load_terrain_raster(terrain))
+        hf_size = rb["hfield_size"][names.index(terrain)].astype(np.float64)
+
+    # ---- height map
+    hm = obs_cfg.get("height_map")
+    if hm is not None and ground_type == 0:
+        raise ValueError("height_map needs an hfield terrain: mj_rayHfield on a plane geom is a fatal error "
+                         "in the reference (SURVEY.md B.11)")
+    res_x, res_y = (int(hm["res_x"]), int(hm["res_y"])) if hm is not None else (0, 0)
+
+    # ---- observation layout (wrappers.py:93-121,160-202)
+    n_dofpos, n_dofvel = OBS_DIMS[env_id]
+    command_dim = int(obs_cfg["command_dim"])
+    obs_to_dim = {"dof_pos": n_dofpos, "dof_vel": n_dofvel, "ang_vel": 3, "lin_vel": 3, "projected_gravity": 3,
+                  "last_action": nu, "height_map": res_x * res_y, "command": command_dim}
+    cache_off, cache_dim = {}, 0
+
+    def items(order):
+        nonlocal cache_dim
+        kinds, dims, scales, intervals, offs = [], [], [], [], []
+        for n in order:
+            if n not in obs_to_dim:
+                raise KeyError(n)
+            kinds.append(OBS_KINDS[n])
+            dims.append(obs_to_dim[n])
+            if n == "command":
+                scales.append(1.0)
+                intervals.append(1)
+                offs.append(-1)
+                continue
+            ncfg = obs_cfg[n]
+            freq = float(ncfg["freq"])
+            if freq <= 0:
+                raise ValueError(f"Invalid observation update frequency for '{n}': {freq}. Must be > 0.")
+            scales.append(float(ncfg["scale"]))
+            intervals.append(max(1, int(round(control_freq / freq))))
+            if n not in cache_off:
+                cache_off[n] = cache_dim
+                cache_dim += obs_to_dim[n]
+            offs.append(cache_off[n])
+        return (np.array(kinds, np.int32), np.array(dims, np.int32), np.array(scales, np.float64),
+                np.array(intervals, np.int32), np.array(offs, np.int32))
+
+    s_kind, s_dim, s_scale, s_int, s_off = items(list(obs_cfg["stacked_obs_order"]))
+    n_kind, n_dim, n_scale, n_int, n_off = items(list(obs_cfg["non_stacked_obs_order"]))
+    stack_size = int(obs_cfg["stack_size"])
+    stacked_dim, nonstacked_dim = int(s_dim.sum()), int(n_dim.sum())
+    state_dim = stack_size * stacked_dim + nonstacked_dim
+
+    # ---- actuators / PD tables
+    act_dof = np.array([rb["jnt_dofadr"][j] for j in rb["act_joint"]], np.int32)
+    act_qadr = np.array([rb["jnt_qposadr"][j] for j in rb["act_joint"]], np.int32)
+    act_jnt_name = [str(rb["jnt_names"][j]) for j in rb["act_joint"]]
+    kp = np.zeros(nu); kd = np.zeros(nu); sc = np.zeros(nu); posfac = np.ones(nu); gam = np.ones(nu)
+    clip = np.zeros(nu); mode = np.zeros(nu, np.int32)
+    k = 0
+    for g in spec.groups:
+        for jn in g.joints:
+            assert act_jnt_name[k] == jn, f"actuator order mismatch {act_jnt_name[k]} vs {jn}"
+            mode[k] = g.mode
+            kp[k] = float(hw[g.kp]) if g.mode == POS else 0.0
+            kd[k] = float(hw[g.kd])
+            sc[k] = float(hw["action_scales"][g.scale])
+            clip[k] = float(hw[g.clip])
+            if g.geared:
+                posfac[k] = float(hw["gear_ratio"])
+                gam[k] = float(hw["gamma"])
+            k += 1
+    assert k == nu
+    gear_of = {jn: float(hw["gear_ratio"]) for jn in spec.geared_joints}
+
+    dofpos_qadr = np.array([rb["jnt_qposadr"][jname[j]] for j in spec.dof_pos_joints], np.int32)
+    dofpos_fac = np.array([gear_of.get(j, 1.0) for j in spec.dof_pos_joints])
+    dofvel_dadr = np.array([rb["jnt_dofadr"][jname[j]] for j in spec.dof_vel_joints], np.int32)
+    dofvel_fac = np.array([gear_of.get(j, 1.0) for j in spec.dof_vel_joints])
+    if spec.init_noise_joints:
+        initnoise_qadr = np.array([rb["jnt_qposadr"][jname[j]] for j in spec.init_noise_joints], np.int32)
+    else:
+        initnoise_qadr = np.arange(7, nq, dtype=np.int32)
+    state_pos_qadr = np.array([rb["jnt_qposadr"][jname[j]] for j in spec.state_pos_joints], np.int32)
+    state_vel_dadr = np.array([rb["jnt_dofadr"][jname[j]] for j in spec.state_vel_joints], np.int32)
+    term_body = np.array([bname[b] for b in spec.term_bodies], np.int32)
+    massnoise_body = np.array(sorted(bname[b] for b in spec.mass_noise_bodies), np.int32)  # document order
+
+    # ---- randomisation flags (xml_manager.py:57-87)
+    wheel_ids = {bname[b] for b in spec.wheel_bodies}
+    geom_fr_random = np.array([int(rb["geom_body"][g] in wheel_ids and rb["geom_has_friction_attr"][g])
+                               for g in range(ngeom)], np.int32)
+    dof_fl_random = np.array([int(str(rb["jnt_class"][rb["dof_jnt"][d]]) in ("joints", "wheels"))
+                              for d in range(nv)], np.int32)
+    nfl_upper = int(np.sum((rb["dof_frictionloss"] > 0) | (dof_fl_random > 0)))
+    nlimit_max = int(np.sum(rb["jnt_limited"]))
+
+    # ---- sensor noise table (random_table.yaml; "zero" = true-zero extension)
+    level = rnd["sensor_noise"]
+    zero_noise = int(level == "zero")
+    noise = np.zeros((6, 6))
+    if not zero_noise:
+        nm = rtab["sensor_noise"][level]
+        for i, n in enumerate(NOISE_ORDER):
+            mean, std, lo, hi = (float(nm[n][q]) for q in ("mean", "std", "lower", "upper"))
+            a, b = (lo - mean) / std, (hi - mean) / std
+            noise[i] = [mean, std, lo, hi, _ncdf(a), _ncdf(b)]
+
+    # ---- qpos0 and connect anchors
+    qpos0 = np.zeros(nq)
+    qpos0[0:3] = rb["body_pos"][0]
+    qpos0[3:7] = rb["body_quat"][0]
+    xpos0, xquat0 = fk_qpos0(rb)
+    neq = len(rb["eq_body1"])
+    eq_anchor2 = np.zeros((neq, 3))
+    for e in range(neq):
+        b1, b2 = int(rb["eq_body1"][e]), int(rb["eq_body2"][e])
+        pw = xpos0[b1] + _quat_mat(xquat0[b1]) @ rb["eq_anchor"][e]
+        eq_anchor2[e] = _quat_mat(xquat0[b2]).T @ (pw - xpos0[b2])
+
+    if ncon_max is None:
+        ncon_max = int(eng.get("ncon_max", 24))
+    nefc_max = 3 * neq + nfl_upper + nlimit_max + 4 * ncon_max
+
+    dims = np.zeros(64, np.int32)
+    opts = np.zeros(64, np.float64)
+
+    def setd(**kw):
+        for a, b in kw.items():
+            dims[DIM[a]] = int(b)
+
+    def seto(**kw):
+        for a, b in kw.items():
+            opts[OPT[a]] = float(b)
+
+    max_steps = int(config["env"]["max_duration"] * control_freq)
+    setd(nq=nq, nv=nv, nu=nu, nbody=nb, njnt=njnt, ngeom=ngeom, nhullvert=len(rb["hull_verts"]), neq=neq,
+         ground_type=ground_type, hf_nrow=hf.shape[0], hf_ncol=hf.shape[1], frame_skip=frame_skip,
+         iterations=iterations, ls_iterations=50, ccd_iterations=50, ncon_max=ncon_max, hm_res_x=res_x,
+         hm_res_y=res_y, state_dim=state_dim, stack_size=stack_size, stacked_dim=stacked_dim,
+         nonstacked_dim=nonstacked_dim, command_dim=command_dim, n_term_body=len(term_body), n_dofpos=n_dofpos,
+         n_dofvel=n_dofvel, n_initnoise=len(initnoise_qadr), max_episode_steps=max_steps,
+         lin_vel_f32=int(spec.lin_vel_f32), n_sobs=len(s_kind), n_nobs=len(n_kind), cache_dim=cache_dim,
+         n_state_pos=len(state_pos_qadr), n_state_vel=len(state_vel_dadr),
+         position_command=int(bool(config["env"]["position_command"])), nefc_max=nefc_max,
+         imu_body=int(rb["imu_body"]), n_massnoise=len(massnoise_body), base_body=bname[spec.base_body],
+         zero_noise=zero_noise, auto_reset=int(bool(eng.get("auto_reset", auto_reset))), nfl=nfl_upper,
+         nlimit_max=nlimit_max)
+    g = rb["gravity"]
+    sl, tl, rl = _rng_pair(rnd["sliding_friction"]), _rng_pair(rnd["torsional_friction"]), _rng_pair(rnd["rolling_friction"])
+    fl, dl, ld = _rng_pair(rnd["friction_loss"]), _rng_pair(rnd["action_delay_prob"]), _rng_pair(rnd["load"])
+    kpr, kdr = _rng_pair(rnd.get("kp_scale", 1.0)), _rng_pair(rnd.get("kd_scale", 1.0))
+    seto(timestep=timestep, gx=g[0], gy=g[1], gz=g[2], tolerance=1e-8, ls_tolerance=0.01, ccd_tolerance=1e-6,
+         hf_sx=hf_size[0], hf_sy=hf_size[1], hf_sz=hf_size[2], hf_base=hf_size[3], z0=spec.z0,
+         hm_size_x=(hm["size_x"] if hm else 0.0), hm_size_y=(hm["size_y"] if hm else 0.0), hm_zmin=spec.hm_zmin,
+         term_threshold=spec.term_threshold, init_noise=float(rnd["init_noise"]),
+         solref0=0.02, solref1=1.0, solimp0=0.9, solimp1=0.95, solimp2=0.001, solimp3=0.5, solimp4=2.0,
+         slide_lo=sl[0], slide_hi=sl[1], tors_lo=tl[0], tors_hi=tl[1], roll_lo=rl[0], roll_hi=rl[1],
+         floss_lo=fl[0], floss_hi=fl[1], delay_lo=dl[0], delay_hi=dl[1], mass_noise=float(rnd["mass_noise"]),
+         load_lo=ld[0], load_hi=ld[1], kp_lo=kpr[0], kp_hi=kpr[1], kd_lo=kdr[0], kd_hi=kdr[1],
+         plane_sx=100.0, plane_sy=100.0)
+
+    def w0(a, fill=0.0):  # prepend the world body row
+        a = np.asarray(a)
+        z = np.full((1,) + a.shape[1:], fill, dtype=a.dtype)
+        return np.concatenate([z, a])
+
+    wq = np.zeros((1, 4)); wq[0, 0] = 1.0
+    S = {}
+    S["dims"], S["opts"] = dims, opts
+    S["body_parent"] = w0(rb["body_parent"]).astype(np.int32)
+    S["body_pos"] = w0(rb["body_pos"]).astype(np.float64)
+    S["body_quat"] = np.concatenate([wq, rb["body_quat"]]).astype(np.float64)
+    S["body_mass"] = w0(rb["body_mass"]).astype(np.float64)
+    S["body_ipos"] = w0(rb["body_ipos"]).astype(np.float64)
+    S["body_inertia"] = w0(rb["body_inertia"]).astype(np.float64)
+    S["body_jntadr"] = w0(rb["body_jntadr"]).astype(np.int32)
+    S["body_jntnum"] = w0(rb["body_jntnum"]).astype(np.int32)
+    S["body_dofadr"] = w0(rb["body_dofadr"]).astype(np.int32)
+    S["body_dofnum"] = w0(rb["body_dofnum"]).astype(np.int32)
+    for key in ("jnt_type", "jnt_body", "jnt_qposadr", "jnt_dofadr", "jnt_limited", "jnt_actfrclimited",
+                "dof_body", "dof_jnt", "dof_parent", "act_ctrllimited", "geom_type", "geom_body", "geom_vadr",
+                "geom_vnum"):
+        S[key] = rb[key].astype(np.int32)
+    for key in ("jnt_pos", "jnt_axis", "jnt_range", "jnt_actfrcrange", "dof_armature", "dof_damping",
+                "dof_frictionloss", "act_gear", "act_ctrlrange", "geom_size", "geom_pos", "geom_quat",
+                "geom_friction", "geom_center", "geom_rbound"):
+        S[key] = rb[key].astype(np.float64)
+    S["dof_fl_random"], S["geom_fr_random"] = dof_fl_random, geom_fr_random
+    S["qpos0"] = qpos0
+    S["act_dof"], S["act_qadr"], S["act_mode"] = act_dof, act_qadr, mode
+    S["act_kp"], S["act_kd"], S["act_scale"], S["act_posfac"], S["act_gamma"], S["act_clip"] = kp, kd, sc, posfac, gam, clip
+    S["hull_verts"] = rb["hull_verts"].astype(np.float32).reshape(-1)
+    gf = np.concatenate([rb["ground_friction"].astype(np.float64), [float(rb["ground_has_friction_attr"])]])
+    S["ground_friction"] = gf
+    S["hfield_data"] = hf.reshape(-1)
+    S["eq_body1"], S["eq_body2"] = rb["eq_body1"].astype(np.int32), rb["eq_body2"].astype(np.int32)
+    S["eq_anchor1"], S["eq_anchor2"] = rb["eq_anchor"].astype(np.float64), eq_anchor2
+    S["eq_solref"], S["eq_solimp"] = rb["eq_solref"].astype(np.float64), rb["eq_solimp"].astype(np.float64)
+    S["imu_pos"], S["imu_quat"] = rb["imu_pos"].astype(np.float64), rb["imu_quat"].astype(np.float64)
+    S["dofpos_qadr"], S["dofpos_fac"] = dofpos_qadr, dofpos_fac
+    S["dofvel_dadr"], S["dofvel_fac"] = dofvel_dadr, dofvel_fac
+    S["initnoise_qadr"], S["term_body"] = initnoise_qadr, term_body
+    S["state_pos_qadr"], S["state_vel_dadr"], S["massnoise_body"] = state_pos_qadr, state_vel_dadr, massnoise_body
+    S["sobs_kind"], S["sobs_dim"], S["sobs_scale"], S["sobs_interval"], S["sobs_off"] = s_kind, s_dim, s_scale, s_int, s_off
+    S["nobs_kind"], S["nobs_dim"], S["nobs_scale"], S["nobs_interval"], S["nobs_off"] = n_kind, n_dim, n_scale, n_int, n_off
+    S["noise"] = noise.reshape(-1)
+    S["command_scales"] = np.array([float(obs_cfg["command_scales"][str(i)]) for i in range(command_dim)], np.float64)
+    # empty arrays still need a dtype the packer knows
+    for k_, v_ in list(S.items()):
+        if v_.dtype not in (np.int32, np.float32, np.float64):
+            S[k_] = v_.astype(np.float64)
+
+    meta = dict(robot=env_id, terrain=terrain, nq=nq, nv=nv, nu=nu, nbody=nb, ngeom=ngeom, state_dim=state_dim,
+                command_dim=command_dim, control_freq=control_freq, dt=timestep * frame_skip,
+                frame_skip=frame_skip, max_episode_steps=max_steps, body_names=["world"] + [str(n) for n in rb["body_names"]],
+                jnt_names=[str(n) for n in rb["jnt_names"]], geom_names=[str(n) for n in rb["geom_names"]],
+                obs_to_dim=obs_to_dim, action_scaler=sc.copy(), notes=[str(n) for n in rb["notes"]],
+                cmd_slices=_cmd_slices(obs_cfg, obs_to_dim, stack_size, stacked_dim, command_dim))
+    return Model(S, meta)
+
+
+def _cmd_slices(obs_cfg, obs_to_dim, stack_size, stacked_dim, command_dim):
+    """StateBuildWrapper._get_cmd_index_cache, /root/reference/envs/wrappers.py:123-158."""
+    out = []
+    if command_dim <= 0:
+        return out
+    off, starts = 0, []
+    for n in obs_cfg["stacked_obs_order"]:
+        if n == "command":
+            starts.append(off)
+        off += obs_to_dim[n]
+    for k in range(stack_size):
+        for s in starts:
+            out.append(slice(k * stacked_dim + s, k * stacked_dim + s + command_dim))
+    base, off = stack_size * stacked_dim, 0
+    for n in obs_cfg["non_stacked_obs_order"]:
+        if n == "command":
+            out.append(slice(base + off, base + off + command_dim))
+        off += obs_to_dim[n]
+    return out
