@@ -1,0 +1,1342 @@
+// engine_core.h -- warp-per-env rigid-body step for sm_100a (B200).
+//
+// One warp owns one environment: its whole working set (poses, spatial inertias, mass matrix,
+// contact Jacobians, solver vectors) lives in that warp's slice of shared memory; lanes split the
+// per-body / per-dof / per-row / per-vertex loops and meet at __syncwarp().  No tensor cores here:
+// this is small dense fp32 linear algebra and branchy collision, bound by the FP32 pipe and
+// shared-memory latency.
+//
+// The same source compiles in a single-lane host mode (COSIM_HOST_EMU, LANES = 1) used ONLY by
+// tests/hostsim to debug kernel logic on machines without a GPU.  The product library is built
+// from engine.cu with nvcc and has no CPU path.
+//
+// What each stage replaces (MuJoCo 3.2.7 is an un-vendored dependency of the reference; semantics
+// per SURVEY.md Appendix B; reference call site: gymnasium do_simulation from
+// /root/reference/envs/flamingo_p_v3/flamingo_p_v3.py:189):
+//   kinematics/com_pos/crb  <- mj_kinematics, mj_comPos, mj_crb       (K1 fk_crb)
+//   chol_factor/chol_solve  <- mj_factorM / mj_solveM (dense here)     (K2 ldl_smem)
+//   collide_*               <- mj_collision: hfield|plane x convex     (K3 collide)
+//   make_constraint         <- mj_makeConstraint/Impedance/reference   (K4 constraints)
+//   newton_solve            <- mj_fwdConstraint, Newton + exact LS     (K5 newton)
+//   rne_bias/actuation/integrate <- mj_rne, mj_fwdActuation, mj_implicit(fast), mj_advance (K6)
+//   pd_delay                <- <Robot>.step PD + ControlManager.delay_filter (K7)
+//   sensors/observe         <- mj_sensor*, _get_obs, StateBuildWrapper (K8)
+//   height_map              <- get_height_map + mj_rayHfield           (K9)
+#pragma once
+#include <stdint.h>
+#include <math.h>
+#include <float.h>
+#include "../../include/cosim_blob.h"
+
+#ifdef COSIM_HOST_EMU
+#define DEV static inline
+#define LANES 1
+#define SYNC() ((void)0)
+#define LDG(p) (*(p))
+static inline float wsum(float v) { return v; }
+static inline float wmaxf(float v) { return v; }
+static inline int wor(int v) { return v; }
+static inline void wargmax(float& v, int& i) {}
+static inline float fast_ndtri(float p);
+#else
+#define DEV __device__ __forceinline__
+#define LANES 32
+#define SYNC() __syncwarp()
+#define LDG(p) __ldg(p)
+DEV float wsum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+DEV float wmaxf(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+DEV int wor(int v) { return __any_sync(0xffffffffu, v); }
+// arg-max with lowest-index tie break; result broadcast to all lanes
+DEV void wargmax(float& v, int& i) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    float ov = __shfl_xor_sync(0xffffffffu, v, o);
+    int oi = __shfl_xor_sync(0xffffffffu, i, o);
+    if (ov > v || (ov == v && oi < i)) { v = ov; i = oi; }
+  }
+}
+#endif
+
+DEV int imax(int a, int b) { return a > b ? a : b; }
+DEV int imin(int a, int b) { return a < b ? a : b; }
+#define FOR_LANE(i, n) for (int i = lane; i < (n); i += LANES)
+#define MINVALF 1e-15f
+
+// ------------------------------------------------------------------------------------------ model
+// Read-only model shared by every env (device pointers; f64 blob sections are converted to f32 once
+// at create time).  Passed to kernels by value (constant bank).
+struct ModelDev {
+  int dims[48];
+  float opts[48];
+  // bodies (index 0 = world)
+  const int *body_parent, *body_jnt, *body_dofadr, *body_dofnum, *body_subsize, *body_dofmask;
+  const float *body_pos, *body_quat, *body_ipos, *body_inertia, *body_mass;
+  const int *level_start, *level_body; int nlevels;
+  // joints / dofs
+  const int *jnt_type, *jnt_body, *jnt_qposadr, *jnt_dofadr, *jnt_limited, *jnt_actfrclimited;
+  const float *jnt_pos, *jnt_axis, *jnt_range, *jnt_actfrcrange;
+  const int *dof_body, *dof_jnt, *dof_parent, *dof_fl_random;
+  const float *dof_armature, *dof_damping, *dof_frictionloss;
+  const int *mpair_i, *mpair_j; int nmpair;
+  const float *qpos0;
+  // actuators + PD tables
+  const int *act_dof, *act_qadr, *act_mode, *act_ctrllimited;
+  const float *act_gear, *act_ctrlrange, *act_kp, *act_kd, *act_scale, *act_posfac, *act_gamma, *act_clip;
+  // geoms
+  const int *geom_type, *geom_body, *geom_vadr, *geom_vnum, *geom_fr_random;
+  const float *geom_size, *geom_pos, *geom_quat, *geom_friction, *geom_center, *geom_rbound;
+  const float *hull_verts, *hfield_data;
+  float ground_friction[4];
+  // equality
+  const int *eq_body1, *eq_body2;
+  const float *eq_anchor1, *eq_anchor2, *eq_solref, *eq_solimp;
+  float imu_pos[3], imu_quat[4];
+  // env layer tables
+  const int *dofpos_qadr, *dofvel_dadr, *initnoise_qadr, *term_body, *massnoise_body;
+  const float *dofpos_fac, *dofvel_fac;
+  const int *sobs_kind, *sobs_dim, *sobs_interval, *sobs_off, *nobs_kind, *nobs_dim, *nobs_interval, *nobs_off;
+  const float *sobs_scale, *nobs_scale, *noise;
+  // randomisation ranges pre-reduced on the host in double: lo and (hi - lo)
+  float rnd_lo[8], rnd_span[8];
+  // workspace layout (float offsets into the per-warp shared slice)
+  int off[80]; int ws_floats;
+  uint32_t seed_lo, seed_hi, env_offset;
+};
+#define MD(name) (m.dims[CD_##name])
+#define MO(name) (m.opts[CO_##name])
+
+enum WsField {
+  W_QPOS, W_QVEL, W_CTRL, W_WARM, W_QACC, W_XPOS, W_XQUAT, W_XMAT, W_XIPOS, W_XANCHOR, W_XAXIS, W_GXPOS, W_GXMAT,
+  W_SCOM, W_CINERT, W_CRB, W_CDOF, W_CDOFDOT, W_CVEL, W_CACC, W_CFRC, W_BUF, W_M, W_A, W_INVD,
+  W_FSMOOTH, W_ASMOOTH, W_FCON, W_GRAD, W_SEARCH, W_MV, W_MA, W_TMPV, W_TMPW,
+  W_BMASS, W_INVWD, W_INVWB, W_FLOSS, W_GMU, W_SCAL,
+  W_FR_D, W_FR_AREF, W_LM_SIGN, W_LM_D, W_LM_AREF,
+  W_CN_POS, W_CN_FRAME, W_CN_DIST, W_CN_MU, W_CN_BODY, W_CN_GEOM, W_CN_CELL, W_CN_D, W_CN_AREF, W_CN_J, W_CN_F, W_CN_X, W_CN_V,
+  W_EQ_J, W_EQ_D, W_EQ_AREF, W_EQ_X, W_EQ_V, W_EQ_F, W_SENS, W_RAW, W_ACT, W_FILT, W_KP, W_KD, W__COUNT   // keep <= 80 (ModelDev::off)
+};
+static_assert(W__COUNT <= 80, "ModelDev::off too small");
+#define WS(f) (ws + m.off[f])
+#define WSI(f) ((int*)(ws + m.off[f]))
+// W_SCAL: [0] ground mu, [1] meaninertia, [2] delay_prob, [3] unused
+
+// Per-env arrays in HBM: one row per env, rows contiguous (a warp reads its env's row coalesced).
+struct EnvArrays {
+  int N;
+  float *qpos, *qvel, *warm;
+  float *body_mass, *invw_dof, *invw_body, *floss, *gmu, *scal, *kp, *kd;
+  float *prev_action, *delay_prev, *obs_buffer, *freq_cache, *torque, *info, *last_action;
+  int *counters;     // [N][8]: sim_step, has_delay_prev, n_reset, n_obs, n_step, nan_count, need_reset, ncon
+  // episode statistics (reporter): [N][NSTAT]
+  float *stats;
+  // optional debug dumps (NULL when disabled)
+  float *dbg_contacts, *dbg_heightmap, *dbg_cfrc, *dbg_sens, *dbg_qacc; int *dbg_hmcell, *dbg_iters;
+};
+enum { CT_SIM_STEP = 0, CT_HAS_DELAY = 1, CT_NRESET = 2, CT_NOBS = 3, CT_NSTEP = 4, CT_NAN = 5, CT_NEED_RESET = 6, CT_NCON = 7 };
+// per-env episode statistics accumulated on device (reporter semantics)
+enum { ST_STEPS = 0, ST_EPISODES, ST_SUCCESS, ST_TERMINATED, ST_ERR_VX, ST_ERR_VY, ST_ERR_WZ, ST_RMSE, ST_ABS_TORQUE, ST_SQ_TORQUE, ST_MAX_TORQUE, ST_NCON, ST_ITERS, ST_DROPPED, ST_NAN, ST__COUNT = 16 };
+
+// ------------------------------------------------------------------------------------------ small math
+DEV void v3copy(float* r, const float* a) { r[0] = a[0]; r[1] = a[1]; r[2] = a[2]; }
+DEV void v3add(float* r, const float* a, const float* b) { r[0] = a[0] + b[0]; r[1] = a[1] + b[1]; r[2] = a[2] + b[2]; }
+DEV void v3sub(float* r, const float* a, const float* b) { r[0] = a[0] - b[0]; r[1] = a[1] - b[1]; r[2] = a[2] - b[2]; }
+DEV void v3scl(float* r, const float* a, float s) { r[0] = a[0] * s; r[1] = a[1] * s; r[2] = a[2] * s; }
+DEV void v3addscl(float* r, const float* a, const float* b, float s) { r[0] = a[0] + b[0] * s; r[1] = a[1] + b[1] * s; r[2] = a[2] + b[2] * s; }
+DEV float v3dot(const float* a, const float* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+DEV void v3cross(float* r, const float* a, const float* b) {
+  float x = a[1] * b[2] - a[2] * b[1], y = a[2] * b[0] - a[0] * b[2], z = a[0] * b[1] - a[1] * b[0];
+  r[0] = x; r[1] = y; r[2] = z;
+}
+DEV float v3norm(const float* a) { return sqrtf(v3dot(a, a)); }
+DEV float v3normalize(float* a) {
+  float n = v3norm(a);
+  if (n < MINVALF) { a[0] = 1.f; a[1] = a[2] = 0.f; return n; }
+  float s = 1.f / n; a[0] *= s; a[1] *= s; a[2] *= s; return n;
+}
+DEV void m3mulv(float* r, const float* M, const float* v) {
+  float x = M[0] * v[0] + M[1] * v[1] + M[2] * v[2], y = M[3] * v[0] + M[4] * v[1] + M[5] * v[2], z = M[6] * v[0] + M[7] * v[1] + M[8] * v[2];
+  r[0] = x; r[1] = y; r[2] = z;
+}
+DEV void m3tmulv(float* r, const float* M, const float* v) {
+  float x = M[0] * v[0] + M[3] * v[1] + M[6] * v[2], y = M[1] * v[0] + M[4] * v[1] + M[7] * v[2], z = M[2] * v[0] + M[5] * v[1] + M[8] * v[2];
+  r[0] = x; r[1] = y; r[2] = z;
+}
+DEV void quat_mul(float* r, const float* a, const float* b) {
+  float w = a[0] * b[0] - a[1] * b[1] - a[2] * b[2] - a[3] * b[3];
+  float x = a[0] * b[1] + a[1] * b[0] + a[2] * b[3] - a[3] * b[2];
+  float y = a[0] * b[2] - a[1] * b[3] + a[2] * b[0] + a[3] * b[1];
+  float z = a[0] * b[3] + a[1] * b[2] - a[2] * b[1] + a[3] * b[0];
+  r[0] = w; r[1] = x; r[2] = y; r[3] = z;
+}
+DEV void quat_normalize(float* q) {
+  float n = sqrtf(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+  if (n < MINVALF) { q[0] = 1.f; q[1] = q[2] = q[3] = 0.f; return; }
+  float s = 1.f / n; q[0] *= s; q[1] *= s; q[2] *= s; q[3] *= s;
+}
+DEV void quat_to_mat(float* M, const float* q) {
+  float w = q[0], x = q[1], y = q[2], z = q[3];
+  M[0] = 1.f - 2.f * (y * y + z * z); M[1] = 2.f * (x * y - z * w); M[2] = 2.f * (x * z + y * w);
+  M[3] = 2.f * (x * y + z * w); M[4] = 1.f - 2.f * (x * x + z * z); M[5] = 2.f * (y * z - x * w);
+  M[6] = 2.f * (x * z - y * w); M[7] = 2.f * (y * z + x * w); M[8] = 1.f - 2.f * (x * x + y * y);
+}
+DEV void quat_rot(float* r, const float* q, const float* v) { float M[9]; quat_to_mat(M, q); m3mulv(r, M, v); }
+DEV void inert_mul(float* r, const float* I, const float* v) {
+  const float* w = v; const float* l = v + 3; const float* mh = I + 6; float ms = I[9];
+  float c1[3], c2[3]; v3cross(c1, mh, l); v3cross(c2, mh, w);
+  r[0] = I[0] * w[0] + I[3] * w[1] + I[4] * w[2] + c1[0];
+  r[1] = I[3] * w[0] + I[1] * w[1] + I[5] * w[2] + c1[1];
+  r[2] = I[4] * w[0] + I[5] * w[1] + I[2] * w[2] + c1[2];
+  r[3] = ms * l[0] - c2[0]; r[4] = ms * l[1] - c2[1]; r[5] = ms * l[2] - c2[2];
+}
+DEV void cross_motion(float* r, const float* v, const float* s) {
+  float a[3], b[3], c[3]; v3cross(a, v, s); v3cross(b, v, s + 3); v3cross(c, v + 3, s);
+  r[0] = a[0]; r[1] = a[1]; r[2] = a[2]; r[3] = b[0] + c[0]; r[4] = b[1] + c[1]; r[5] = b[2] + c[2];
+}
+DEV void cross_force(float* r, const float* v, const float* f) {
+  float a[3], b[3], c[3]; v3cross(a, v, f); v3cross(b, v + 3, f + 3); v3cross(c, v, f + 3);
+  r[0] = a[0] + b[0]; r[1] = a[1] + b[1]; r[2] = a[2] + b[2]; r[3] = c[0]; r[4] = c[1]; r[5] = c[2];
+}
+
+// ------------------------------------------------------------------------------------------ RNG
+// Philox4x32-10, counter = (global env id, stream, step, block), key = seed
+DEV uint32_t mulhi32(uint32_t a, uint32_t b) {
+#ifdef COSIM_HOST_EMU
+  return (uint32_t)(((uint64_t)a * b) >> 32);
+#else
+  return __umulhi(a, b);
+#endif
+}
+DEV uint32_t philox_draw(const ModelDev& m, uint32_t env, uint32_t stream, uint32_t step, uint32_t idx) {
+  uint32_t c0 = env + m.env_offset, c1 = stream, c2 = step, c3 = idx >> 2, k0 = m.seed_lo, k1 = m.seed_hi;
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    uint32_t h0 = mulhi32(0xD2511F53u, c0), l0 = 0xD2511F53u * c0, h1 = mulhi32(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+    uint32_t n0 = h1 ^ c1 ^ k0, n2 = h0 ^ c3 ^ k1;
+    c0 = n0; c1 = l1; c2 = n2; c3 = l0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  uint32_t o[4] = {c0, c1, c2, c3};
+  return o[idx & 3];
+}
+DEV float u01(uint32_t x) { return (float)(x >> 8) * (1.0f / 16777216.0f); }
+DEV float uni(const ModelDev& m, int env, uint32_t stream, uint32_t step, uint32_t idx) { return u01(philox_draw(m, (uint32_t)env, stream, step, idx)); }
+
+DEV float ndtri(float p) {
+#ifdef COSIM_HOST_EMU
+  return fast_ndtri(p);
+#else
+  return normcdfinvf(p);
+#endif
+}
+
+// ------------------------------------------------------------------------------------------ kinematics
+DEV void kinematics(const ModelDev& m, float* ws, int lane) {
+  float* qpos = WS(W_QPOS); float* xpos = WS(W_XPOS); float* xquat = WS(W_XQUAT); float* xmat = WS(W_XMAT);
+  float* xipos = WS(W_XIPOS); float* xanchor = WS(W_XANCHOR); float* xaxis = WS(W_XAXIS);
+  if (lane == 0) {
+    xpos[0] = xpos[1] = xpos[2] = 0.f; xquat[0] = 1.f; xquat[1] = xquat[2] = xquat[3] = 0.f;
+    xmat[0] = xmat[4] = xmat[8] = 1.f; xmat[1] = xmat[2] = xmat[3] = xmat[5] = xmat[6] = xmat[7] = 0.f;
+    xipos[0] = xipos[1] = xipos[2] = 0.f;
+  }
+  SYNC();
+  for (int l = 1; l < m.nlevels; ++l) {
+    for (int idx = m.level_start[l] + lane; idx < m.level_start[l + 1]; idx += LANES) {
+      const int b = m.level_body[idx], j = m.body_jnt[b];
+      float xp[3], xq[4];
+      if (j >= 0 && m.jnt_type[j] == 0) {
+        const int qa = m.jnt_qposadr[j];
+        quat_normalize(qpos + qa + 3);
+        v3copy(xp, qpos + qa);
+        xq[0] = qpos[qa + 3]; xq[1] = qpos[qa + 4]; xq[2] = qpos[qa + 5]; xq[3] = qpos[qa + 6];
+        v3copy(xanchor + 3 * j, xp);
+        float ax[3] = {LDG(m.jnt_axis + 3 * j), LDG(m.jnt_axis + 3 * j + 1), LDG(m.jnt_axis + 3 * j + 2)};
+        quat_rot(xaxis + 3 * j, xq, ax);
+      } else {
+        const int p = m.body_parent[b];
+        float bp[3] = {LDG(m.body_pos + 3 * b), LDG(m.body_pos + 3 * b + 1), LDG(m.body_pos + 3 * b + 2)};
+        float bq[4] = {LDG(m.body_quat + 4 * b), LDG(m.body_quat + 4 * b + 1), LDG(m.body_quat + 4 * b + 2), LDG(m.body_quat + 4 * b + 3)};
+        float r[3]; m3mulv(r, xmat + 9 * p, bp); v3add(xp, xpos + 3 * p, r);
+        quat_mul(xq, xquat + 4 * p, bq);
+        if (j >= 0) {
+          float jp[3] = {LDG(m.jnt_pos + 3 * j), LDG(m.jnt_pos + 3 * j + 1), LDG(m.jnt_pos + 3 * j + 2)};
+          float ax[3] = {LDG(m.jnt_axis + 3 * j), LDG(m.jnt_axis + 3 * j + 1), LDG(m.jnt_axis + 3 * j + 2)};
+          float v[3]; quat_rot(v, xq, jp); v3add(xanchor + 3 * j, xp, v);
+          quat_rot(xaxis + 3 * j, xq, ax);
+          const int qa = m.jnt_qposadr[j];
+          float ang = (qpos[qa] - LDG(m.qpos0 + qa)) * 0.5f, s, c;
+          sincosf(ang, &s, &c);
+          float ql[4] = {c, ax[0] * s, ax[1] * s, ax[2] * s};
+          quat_mul(xq, xq, ql);
+          quat_rot(v, xq, jp); v3sub(xp, xanchor + 3 * j, v);
+        }
+      }
+      quat_normalize(xq);
+      v3copy(xpos + 3 * b, xp);
+      xquat[4 * b] = xq[0]; xquat[4 * b + 1] = xq[1]; xquat[4 * b + 2] = xq[2]; xquat[4 * b + 3] = xq[3];
+      quat_to_mat(xmat + 9 * b, xq);
+      float ip[3] = {LDG(m.body_ipos + 3 * b), LDG(m.body_ipos + 3 * b + 1), LDG(m.body_ipos + 3 * b + 2)}, r[3];
+      m3mulv(r, xmat + 9 * b, ip); v3add(xipos + 3 * b, xp, r);
+    }
+    SYNC();
+  }
+  float* gxpos = WS(W_GXPOS); float* gxmat = WS(W_GXMAT);
+  FOR_LANE(g, MD(ngeom)) {
+    const int b = m.geom_body[g];
+    float gp[3] = {LDG(m.geom_pos + 3 * g), LDG(m.geom_pos + 3 * g + 1), LDG(m.geom_pos + 3 * g + 2)};
+    float gq[4] = {LDG(m.geom_quat + 4 * g), LDG(m.geom_quat + 4 * g + 1), LDG(m.geom_quat + 4 * g + 2), LDG(m.geom_quat + 4 * g + 3)};
+    float r[3], q[4]; m3mulv(r, xmat + 9 * b, gp); v3add(gxpos + 3 * g, xpos + 3 * b, r);
+    quat_mul(q, xquat + 4 * b, gq); quat_to_mat(gxmat + 9 * g, q);
+  }
+  SYNC();
+}
+
+// subtree COM of the (single) tree, spatial inertias about it, motion axes
+DEV void com_pos(const ModelDev& m, float* ws, int lane) {
+  const int nb = MD(nbody), nv = MD(nv);
+  const float* xipos = WS(W_XIPOS); const float* xmat = WS(W_XMAT); const float* bmass = WS(W_BMASS);
+  float sx = 0.f, sy = 0.f, sz = 0.f, sm = 0.f;
+  for (int b = 1 + lane; b < nb; b += LANES) { float ms = bmass[b]; sx += ms * xipos[3 * b]; sy += ms * xipos[3 * b + 1]; sz += ms * xipos[3 * b + 2]; sm += ms; }
+  sx = wsum(sx); sy = wsum(sy); sz = wsum(sz); sm = wsum(sm);
+  const float inv = 1.f / sm;
+  const float com[3] = {sx * inv, sy * inv, sz * inv};
+  float* scom = WS(W_SCOM);
+  if (lane == 0) { scom[0] = com[0]; scom[1] = com[1]; scom[2] = com[2]; scom[3] = sm; }
+  float* cinert = WS(W_CINERT);
+  for (int b = 1 + lane; b < nb; b += LANES) {
+    const float* Ib = m.body_inertia + 6 * b;
+    const float I[9] = {LDG(Ib), LDG(Ib + 3), LDG(Ib + 4), LDG(Ib + 3), LDG(Ib + 1), LDG(Ib + 5), LDG(Ib + 4), LDG(Ib + 5), LDG(Ib + 2)};
+    const float* R = xmat + 9 * b;
+    float RI[9], Iw[9];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) RI[3 * i + j] = R[3 * i] * I[j] + R[3 * i + 1] * I[3 + j] + R[3 * i + 2] * I[6 + j];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) Iw[3 * i + j] = RI[3 * i] * R[3 * j] + RI[3 * i + 1] * R[3 * j + 1] + RI[3 * i + 2] * R[3 * j + 2];
+    float h[3]; v3sub(h, xipos + 3 * b, com);
+    const float ms = bmass[b], hh = v3dot(h, h);
+    float* ci = cinert + 10 * b;
+    ci[0] = Iw[0] + ms * (hh - h[0] * h[0]); ci[1] = Iw[4] + ms * (hh - h[1] * h[1]); ci[2] = Iw[8] + ms * (hh - h[2] * h[2]);
+    ci[3] = Iw[1] - ms * h[0] * h[1]; ci[4] = Iw[2] - ms * h[0] * h[2]; ci[5] = Iw[5] - ms * h[1] * h[2];
+    ci[6] = ms * h[0]; ci[7] = ms * h[1]; ci[8] = ms * h[2]; ci[9] = ms;
+  }
+  float* cdof = WS(W_CDOF); const float* xanchor = WS(W_XANCHOR); const float* xaxis = WS(W_XAXIS);
+  FOR_LANE(k, nv) {
+    const int j = m.dof_jnt[k], b = m.dof_body[k];
+    float off[3]; v3sub(off, com, xanchor + 3 * j);
+    float* cd = cdof + 6 * k;
+    if (m.jnt_type[j] == 0) {
+      const int r = k - m.jnt_dofadr[j];
+      if (r < 3) { cd[0] = cd[1] = cd[2] = 0.f; cd[3] = (r == 0); cd[4] = (r == 1); cd[5] = (r == 2); }
+      else { float ax[3] = {xmat[9 * b + r - 3], xmat[9 * b + 3 + r - 3], xmat[9 * b + 6 + r - 3]}; v3copy(cd, ax); v3cross(cd + 3, ax, off); }
+    } else { v3copy(cd, xaxis + 3 * j); v3cross(cd + 3, xaxis + 3 * j, off); }
+  }
+  SYNC();
+}
+
+DEV void crb(const ModelDev& m, float* ws, int lane) {
+  const int nb = MD(nbody), nv = MD(nv);
+  const float* cinert = WS(W_CINERT); float* crbI = WS(W_CRB); const float* cdof = WS(W_CDOF);
+  float* buf = WS(W_BUF); float* M = WS(W_M);
+  for (int b = 1 + lane; b < nb; b += LANES) {   // composite = sum over the contiguous DFS subtree, fixed order
+    float acc[10];
+#pragma unroll
+    for (int i = 0; i < 10; ++i) acc[i] = cinert[10 * b + i];
+    const int end = b + m.body_subsize[b];
+    for (int c = b + 1; c < end; ++c)
+#pragma unroll
+      for (int i = 0; i < 10; ++i) acc[i] += cinert[10 * c + i];
+#pragma unroll
+    for (int i = 0; i < 10; ++i) crbI[10 * b + i] = acc[i];
+  }
+  FOR_LANE(i, nv * nv) M[i] = 0.f;
+  SYNC();
+  FOR_LANE(i, nv) inert_mul(buf + 6 * i, crbI + 10 * m.dof_body[i], cdof + 6 * i);
+  SYNC();
+  FOR_LANE(p, m.nmpair) {
+    const int i = m.mpair_i[p], j = m.mpair_j[p];
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) s += cdof[6 * j + k] * buf[6 * i + k];
+    if (i == j) s += LDG(m.dof_armature + i);
+    M[i * nv + j] = s; M[j * nv + i] = s;
+  }
+  SYNC();
+}
+
+// dense Cholesky of the n x n SPD matrix in A (lower triangle used, overwritten by L below the
+// diagonal; the diagonal keeps L_jj^2 and 1/L_jj goes to invd)
+DEV void chol_factor(float* A, float* invd, int n, int lane) {
+  for (int j = 0; j < n; ++j) {
+    const float inv = 1.f / sqrtf(fmaxf(A[j * n + j], 1e-30f));
+    if (lane == 0) invd[j] = inv;
+    for (int i = j + 1 + lane; i < n; i += LANES) A[i * n + j] *= inv;
+    SYNC();
+    for (int i = j + 1 + lane; i < n; i += LANES) {
+      const float lij = A[i * n + j];
+      for (int k = j + 1; k <= i; ++k) A[i * n + k] -= lij * A[k * n + j];
+    }
+    SYNC();
+  }
+}
+// solves L L^T x = b.  b is destroyed, tmp is scratch, result in out (all length n, distinct)
+DEV void chol_solve(const float* A, const float* invd, float* b, float* tmp, float* out, int n, int lane) {
+  for (int i = 0; i < n; ++i) {
+    const float xi = b[i] * invd[i];
+    for (int k = i + 1 + lane; k < n; k += LANES) b[k] -= A[k * n + i] * xi;
+    if (lane == 0) tmp[i] = xi;
+    SYNC();
+  }
+  for (int i = n - 1; i >= 0; --i) {
+    const float xi = tmp[i] * invd[i];
+    for (int k = lane; k < i; k += LANES) tmp[k] -= A[i * n + k] * xi;
+    if (lane == 0) out[i] = xi;
+    SYNC();
+  }
+}
+
+// ------------------------------------------------------------------------------------------ velocity / bias
+DEV void com_vel(const ModelDev& m, float* ws, int lane) {
+  const int nv = MD(nv);
+  const float* cdof = WS(W_CDOF); float* cdd = WS(W_CDOFDOT); float* cvel = WS(W_CVEL); const float* qvel = WS(W_QVEL);
+  FOR_LANE(i, 6) cvel[i] = 0.f;
+  SYNC();
+  for (int l = 1; l < m.nlevels; ++l) {
+    for (int idx = m.level_start[l] + lane; idx < m.level_start[l + 1]; idx += LANES) {
+      const int b = m.level_body[idx], p = m.body_parent[b], j = m.body_jnt[b];
+      float v[6];
+#pragma unroll
+      for (int i = 0; i < 6; ++i) v[i] = cvel[6 * p + i];
+      if (j >= 0) {
+        const int da = m.jnt_dofadr[j];
+        if (m.jnt_type[j] == 0) {
+          for (int k = 0; k < 3; ++k) {
+#pragma unroll
+            for (int i = 0; i < 6; ++i) { cdd[6 * (da + k) + i] = 0.f; v[i] += cdof[6 * (da + k) + i] * qvel[da + k]; }
+          }
+          for (int k = 3; k < 6; ++k) cross_motion(cdd + 6 * (da + k), v, cdof + 6 * (da + k));
+          for (int k = 3; k < 6; ++k)
+#pragma unroll
+            for (int i = 0; i < 6; ++i) v[i] += cdof[6 * (da + k) + i] * qvel[da + k];
+        } else {
+          cross_motion(cdd + 6 * da, v, cdof + 6 * da);
+#pragma unroll
+          for (int i = 0; i < 6; ++i) v[i] += cdof[6 * da + i] * qvel[da];
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 6; ++i) cvel[6 * b + i] = v[i];
+    }
+    SYNC();
+  }
+  (void)nv;
+}
+
+// qfrc_bias into `out` (length nv)
+DEV void rne_bias(const ModelDev& m, float* ws, float* out, int lane) {
+  const int nb = MD(nbody), nv = MD(nv);
+  const float* cdof = WS(W_CDOF); const float* cdd = WS(W_CDOFDOT); const float* cvel = WS(W_CVEL);
+  float* cacc = WS(W_CACC); float* cfrc = WS(W_CFRC); const float* cinert = WS(W_CINERT); const float* qvel = WS(W_QVEL);
+  if (lane == 0) { cacc[0] = cacc[1] = cacc[2] = 0.f; cacc[3] = -MO(gx); cacc[4] = -MO(gy); cacc[5] = -MO(gz); }
+  SYNC();
+  for (int l = 1; l < m.nlevels; ++l) {
+    for (int idx = m.level_start[l] + lane; idx < m.level_start[l + 1]; idx += LANES) {
+      const int b = m.level_body[idx], p = m.body_parent[b];
+      float a[6];
+#pragma unroll
+      for (int i = 0; i < 6; ++i) a[i] = cacc[6 * p + i];
+      const int d0 = m.body_dofadr[b], d1 = d0 + m.body_dofnum[b];
+      for (int k = d0; k < d1; ++k)
+#pragma unroll
+        for (int i = 0; i < 6; ++i) a[i] += cdd[6 * k + i] * qvel[k];
+#pragma unroll
+      for (int i = 0; i < 6; ++i) cacc[6 * b + i] = a[i];
+      float Iv[6], t1[6], Ia[6];
+      inert_mul(Iv, cinert + 10 * b, cvel + 6 * b);
+      cross_force(t1, cvel + 6 * b, Iv);
+      inert_mul(Ia, cinert + 10 * b, a);
+#pragma unroll
+      for (int i = 0; i < 6; ++i) cfrc[6 * b + i] = Ia[i] + t1[i];
+    }
+    SYNC();
+  }
+  // subtree sums (deterministic order) folded directly into the dof projection
+  FOR_LANE(k, nv) {
+    const int b = m.dof_body[k], end = b + m.body_subsize[b];
+    float f[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int c = b; c < end; ++c)
+#pragma unroll
+      for (int i = 0; i < 6; ++i) f[i] += cfrc[6 * c + i];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) s += cdof[6 * k + i] * f[i];
+    out[k] = s;
+  }
+  SYNC();
+  (void)nb;
+}
+
+// ------------------------------------------------------------------------------------------ collision
+struct GeomW { int type; const float* pos; const float* mat; float size[3]; const float* verts; int nvert; float center[3]; };
+
+DEV GeomW make_geom(const ModelDev& m, const float* ws, int g) {
+  GeomW G; G.type = m.geom_type[g]; G.pos = WS(W_GXPOS) + 3 * g; G.mat = WS(W_GXMAT) + 9 * g;
+  G.size[0] = LDG(m.geom_size + 3 * g); G.size[1] = LDG(m.geom_size + 3 * g + 1); G.size[2] = LDG(m.geom_size + 3 * g + 2);
+  G.verts = m.hull_verts + 3 * m.geom_vadr[g]; G.nvert = m.geom_vnum[g];
+  float c[3] = {LDG(m.geom_center + 3 * g), LDG(m.geom_center + 3 * g + 1), LDG(m.geom_center + 3 * g + 2)}, r[3];
+  m3mulv(r, G.mat, c); v3add(G.center, G.pos, r);
+  return G;
+}
+// support point in world direction dir; warp-cooperative for meshes (all lanes return the same point)
+DEV void support(const GeomW& G, const float* dir, float* out, int lane) {
+  float ld[3]; m3tmulv(ld, G.mat, dir);
+  float lp[3] = {0.f, 0.f, 0.f};
+  if (G.type == GEOM_SPHERE) { v3scl(lp, ld, G.size[0]); }
+  else if (G.type == GEOM_CYLINDER) {
+    float n = sqrtf(ld[0] * ld[0] + ld[1] * ld[1]);
+    if (n > MINVALF) { lp[0] = ld[0] / n * G.size[0]; lp[1] = ld[1] / n * G.size[0]; }
+    lp[2] = (ld[2] > 0.f ? 1.f : (ld[2] < 0.f ? -1.f : 0.f)) * G.size[1];
+  } else if (G.type == GEOM_BOX) {
+    lp[0] = (ld[0] > 0.f ? 1.f : -1.f) * G.size[0]; lp[1] = (ld[1] > 0.f ? 1.f : -1.f) * G.size[1]; lp[2] = (ld[2] > 0.f ? 1.f : -1.f) * G.size[2];
+  } else {   // mesh: lanes stride the hull vertices
+    float bv = -INFINITY; int best = 0x7fffffff;
+    for (int i = lane; i < G.nvert; i += LANES) {
+      float v = LDG(G.verts + 3 * i) * ld[0] + LDG(G.verts + 3 * i + 1) * ld[1] + LDG(G.verts + 3 * i + 2) * ld[2];
+      if (v > bv) { bv = v; best = i; }
+    }
+    wargmax(bv, best);
+    lp[0] = LDG(G.verts + 3 * best); lp[1] = LDG(G.verts + 3 * best + 1); lp[2] = LDG(G.verts + 3 * best + 2);
+  }
+  float r[3]; m3mulv(r, G.mat, lp); v3add(out, G.pos, r);
+}
+
+struct Sup { float v[3], v1[3], v2[3]; };
+// libccd's degenerate-case guards use CCD_EPS = DBL_EPSILON (MuJoCo builds it in double).  They are
+// ABSOLUTE thresholds, so the fp32 engine keeps the double value: with FLT_EPSILON the guards fire on
+// ordinary millimetre-scale portal triangles and the contact normal degenerates.
+#define CCD_EPS 2.220446e-16f
+DEV bool f_is_zero(float x) { return fabsf(x) < CCD_EPS; }
+DEV bool f_eq(float a, float b) {
+  float ab = fabsf(a - b);
+  if (ab < CCD_EPS) return true;
+  float aa = fabsf(a), bb = fabsf(b);
+  return ab < CCD_EPS * (bb > aa ? bb : aa);
+}
+DEV bool v3eq0(const float* a) { return f_eq(a[0], 0.f) && f_eq(a[1], 0.f) && f_eq(a[2], 0.f); }
+DEV void mink_support(const float (*P)[3], const GeomW& G, const float* dir, Sup& s, int lane) {
+  int best = 0; float bv = v3dot(P[0], dir);
+#pragma unroll
+  for (int i = 1; i < 6; ++i) { float v = v3dot(P[i], dir); if (v > bv) { bv = v; best = i; } }
+  v3copy(s.v1, P[best]);
+  float nd[3] = {-dir[0], -dir[1], -dir[2]};
+  support(G, nd, s.v2, lane);
+  v3sub(s.v, s.v1, s.v2);
+}
+DEV void portal_dir(const Sup* p, float* dir) {
+  float a[3], b[3]; v3sub(a, p[2].v, p[1].v); v3sub(b, p[3].v, p[1].v); v3cross(dir, a, b); v3normalize(dir);
+}
+DEV void expand_portal(Sup* p, const Sup& v4) {
+  float v4v0[3]; v3cross(v4v0, v4.v, p[0].v);
+  float dot = v3dot(p[1].v, v4v0);
+  if (dot > 0.f) { dot = v3dot(p[2].v, v4v0); if (dot > 0.f) p[1] = v4; else p[3] = v4; }
+  else { dot = v3dot(p[3].v, v4v0); if (dot > 0.f) p[2] = v4; else p[1] = v4; }
+}
+DEV bool reach_tol(const Sup* p, const Sup& v4, const float* dir, float tol) {
+  float dv1 = v3dot(p[1].v, dir), dv2 = v3dot(p[2].v, dir), dv3 = v3dot(p[3].v, dir), dv4 = v3dot(v4.v, dir);
+  float dm = fminf(dv4 - dv1, fminf(dv4 - dv2, dv4 - dv3));
+  return f_eq(dm, tol) || dm < tol;
+}
+DEV float seg_dist2(const float* A, const float* B, float* wit) {
+  float dd[3]; v3sub(dd, B, A);
+  float tt = -v3dot(A, dd) / v3dot(dd, dd);
+  if (tt < 0.f || f_is_zero(tt)) { v3copy(wit, A); return v3dot(A, A); }
+  if (tt > 1.f || f_eq(tt, 1.f)) { v3copy(wit, B); return v3dot(B, B); }
+  float w3[3]; v3addscl(w3, A, dd, tt); v3copy(wit, w3); return v3dot(w3, w3);
+}
+DEV float point_tri_dist2(const float* x0, const float* B, const float* C, float* witness) {
+  float d1[3], d2[3]; v3sub(d1, B, x0); v3sub(d2, C, x0);
+  float v = v3dot(d1, d1), w = v3dot(d2, d2), p = v3dot(x0, d1), q = v3dot(x0, d2), r = v3dot(d1, d2);
+  float div = w * v - r * r, s, t = 0.f, dist;
+  if (f_is_zero(div)) s = -1.f; else { s = (q * r - w * p) / div; t = (-s * r - q) / w; }
+  if ((f_is_zero(s) || s > 0.f) && (f_eq(s, 1.f) || s < 1.f) && (f_is_zero(t) || t > 0.f) && (f_eq(t, 1.f) || t < 1.f) && (f_eq(t + s, 1.f) || t + s < 1.f)) {
+    float wv[3]; v3addscl(wv, x0, d1, s); v3addscl(wv, wv, d2, t); v3copy(witness, wv); dist = v3dot(wv, wv);
+  } else {
+    float w2[3]; dist = seg_dist2(x0, B, witness);
+    float d2v = seg_dist2(x0, C, w2); if (d2v < dist) { dist = d2v; v3copy(witness, w2); }
+    d2v = seg_dist2(B, C, w2); if (d2v < dist) { dist = d2v; v3copy(witness, w2); }
+  }
+  return dist;
+}
+DEV void find_pos(const Sup* p, float* pos) {
+  float dir[3]; portal_dir(p, dir);
+  float b[4], vec[3];
+  v3cross(vec, p[1].v, p[2].v); b[0] = v3dot(vec, p[3].v);
+  v3cross(vec, p[3].v, p[2].v); b[1] = v3dot(vec, p[0].v);
+  v3cross(vec, p[0].v, p[1].v); b[2] = v3dot(vec, p[3].v);
+  v3cross(vec, p[2].v, p[1].v); b[3] = v3dot(vec, p[0].v);
+  float sum = b[0] + b[1] + b[2] + b[3];
+  if (f_is_zero(sum) || sum < 0.f) {
+    b[0] = 0.f;
+    v3cross(vec, p[2].v, p[3].v); b[1] = v3dot(vec, dir);
+    v3cross(vec, p[3].v, p[1].v); b[2] = v3dot(vec, dir);
+    v3cross(vec, p[1].v, p[2].v); b[3] = v3dot(vec, dir);
+    sum = b[1] + b[2] + b[3];
+  }
+  float inv = 1.f / sum, p1[3] = {0.f, 0.f, 0.f}, p2[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { v3addscl(p1, p1, p[i].v1, b[i]); v3addscl(p2, p2, p[i].v2, b[i]); }
+#pragma unroll
+  for (int k = 0; k < 3; ++k) pos[k] = (p1[k] * inv + p2[k] * inv) * 0.5f;
+}
+// MPR penetration query (libccd ccdMPRPenetration as driven by mjc_ConvexHField); 0 = hit
+DEV int mpr_penetration(const ModelDev& m, const float (*P)[3], const GeomW& G, float* depth, float* dir_out, float* pos, int lane) {
+  const float tol = MO(ccd_tolerance); const int maxit = MD(ccd_iterations);
+  Sup p[4];
+  float c1[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+  for (int i = 0; i < 6; ++i) v3add(c1, c1, P[i]);
+  v3scl(c1, c1, 1.f / 6.f);
+  v3copy(p[0].v1, c1); v3copy(p[0].v2, G.center); v3sub(p[0].v, c1, G.center);
+  if (v3eq0(p[0].v)) p[0].v[0] += CCD_EPS * 10.f;
+  float dir[3] = {-p[0].v[0], -p[0].v[1], -p[0].v[2]}; v3normalize(dir);
+  mink_support(P, G, dir, p[1], lane);
+  float dot = v3dot(p[1].v, dir);
+  if (f_is_zero(dot) || dot < 0.f) return -1;
+  v3cross(dir, p[0].v, p[1].v);
+  if (f_is_zero(v3dot(dir, dir))) {
+    if (v3eq0(p[1].v)) { *depth = 0.f; dir_out[0] = dir_out[1] = dir_out[2] = 0.f; for (int k = 0; k < 3; ++k) pos[k] = (p[1].v1[k] + p[1].v2[k]) * 0.5f; return 0; }
+    for (int k = 0; k < 3; ++k) pos[k] = (p[1].v1[k] + p[1].v2[k]) * 0.5f;
+    *depth = v3norm(p[1].v); v3copy(dir_out, p[1].v); v3normalize(dir_out); return 0;
+  }
+  v3normalize(dir);
+  mink_support(P, G, dir, p[2], lane);
+  dot = v3dot(p[2].v, dir);
+  if (f_is_zero(dot) || dot < 0.f) return -1;
+  float va[3], vb[3];
+  v3sub(va, p[1].v, p[0].v); v3sub(vb, p[2].v, p[0].v); v3cross(dir, va, vb); v3normalize(dir);
+  dot = v3dot(dir, p[0].v);
+  if (dot > 0.f) { Sup t = p[1]; p[1] = p[2]; p[2] = t; v3scl(dir, dir, -1.f); }
+  int size = 3, guard = 0;
+  while (size < 4) {
+    if (++guard > 100) return -1;
+    mink_support(P, G, dir, p[3], lane);
+    dot = v3dot(p[3].v, dir);
+    if (f_is_zero(dot) || dot < 0.f) return -1;
+    int cont = 0;
+    v3cross(va, p[1].v, p[3].v); dot = v3dot(va, p[0].v);
+    if (dot < 0.f && !f_is_zero(dot)) { p[2] = p[3]; cont = 1; }
+    if (!cont) {
+      v3cross(va, p[3].v, p[2].v); dot = v3dot(va, p[0].v);
+      if (dot < 0.f && !f_is_zero(dot)) { p[1] = p[3]; cont = 1; }
+    }
+    if (cont) { v3sub(va, p[1].v, p[0].v); v3sub(vb, p[2].v, p[0].v); v3cross(dir, va, vb); v3normalize(dir); }
+    else size = 4;
+  }
+  guard = 0;
+  while (true) {
+    if (++guard > 1000) return -1;
+    portal_dir(p, dir);
+    dot = v3dot(dir, p[1].v);
+    if (f_is_zero(dot) || dot > 0.f) break;
+    Sup v4; mink_support(P, G, dir, v4, lane);
+    dot = v3dot(v4.v, dir);
+    if (!(f_is_zero(dot) || dot > 0.f) || reach_tol(p, v4, dir, tol)) return -1;
+    expand_portal(p, v4);
+  }
+  int it = 0;
+  while (true) {
+    portal_dir(p, dir);
+    Sup v4; mink_support(P, G, dir, v4, lane);
+    if (reach_tol(p, v4, dir, tol) || it > maxit) {
+      float wit[3];
+      float d2 = point_tri_dist2(p[1].v, p[2].v, p[3].v, wit);
+      *depth = sqrtf(d2);
+      if (f_is_zero(*depth)) { dir_out[0] = dir_out[1] = dir_out[2] = 0.f; } else { v3copy(dir_out, wit); v3normalize(dir_out); }
+      find_pos(p, pos);
+      return 0;
+    }
+    expand_portal(p, v4);
+    ++it;
+  }
+}
+
+DEV void make_frame(float* frame) {
+  float* n = frame; float* t1 = frame + 3; float* t2 = frame + 6;
+  v3normalize(n);
+  float tmp[3] = {0.f, 0.f, 0.f};
+  if (n[1] < 0.5f && n[1] > -0.5f) tmp[1] = 1.f; else tmp[2] = 1.f;
+  float dn = v3dot(n, tmp);
+  v3addscl(t1, tmp, n, -dn); v3normalize(t1);
+  v3cross(t2, n, t1);
+}
+// all lanes call with identical arguments; lane 0 writes.  ncon is warp-uniform (register) state
+DEV void add_contact(const ModelDev& m, float* ws, int& ncon, int& dropped, const float* pos, const float* normal, float dist, int g, int cell, int lane) {
+  if (ncon >= MD(ncon_max)) { ++dropped; return; }
+  if (lane == 0) {
+    float* cp = WS(W_CN_POS) + 3 * ncon; float* fr = WS(W_CN_FRAME) + 9 * ncon;
+    v3copy(cp, pos); v3copy(fr, normal); make_frame(fr);
+    WS(W_CN_DIST)[ncon] = dist;
+    WS(W_CN_MU)[ncon] = fmaxf(WS(W_SCAL)[0], WS(W_GMU)[g]);
+    WSI(W_CN_BODY)[ncon] = m.geom_body[g]; WSI(W_CN_GEOM)[ncon] = g; WSI(W_CN_CELL)[ncon] = cell;
+  }
+  ++ncon;
+}
+
+DEV void collide_hfield(const ModelDev& m, float* ws, int g, int& ncon, int& dropped, int lane) {
+  const GeomW G = make_geom(m, ws, g);
+  const int nrow = MD(hf_nrow), ncol = MD(hf_ncol);
+  const float sx = MO(hf_sx), sy = MO(hf_sy), sz = MO(hf_sz), base = MO(hf_base);
+  const float rb = LDG(m.geom_rbound + g);
+  const float* pos = G.center;
+  if (pos[0] - rb > sx || pos[0] + rb < -sx || pos[1] - rb > sy || pos[1] + rb < -sy) return;
+  if (pos[2] - rb > sz || pos[2] + rb < -base) return;
+  const float dx = 2.f * sx / (float)(ncol - 1), dy = 2.f * sy / (float)(nrow - 1);
+  {  // conservative early-out (does not change results): highest terrain vertex under the bounding sphere
+    int c0 = imax(0, (int)floorf((pos[0] - rb + sx) / dx)), c1 = imin(ncol - 1, (int)ceilf((pos[0] + rb + sx) / dx));
+    int r0 = imax(0, (int)floorf((pos[1] - rb + sy) / dy)), r1 = imin(nrow - 1, (int)ceilf((pos[1] + rb + sy) / dy));
+    const int w = c1 - c0 + 1, cnt = w * (r1 - r0 + 1);
+    if (cnt <= 256) {
+      float hmax = -INFINITY;
+      for (int t = lane; t < cnt; t += LANES) hmax = fmaxf(hmax, LDG(m.hfield_data + (size_t)(r0 + t / w) * ncol + c0 + t % w));
+      hmax = wmaxf(hmax) * sz;
+      if (pos[2] - rb > hmax) return;
+    }
+  }
+  float xmin[3], xmax[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    float dir[3] = {0.f, 0.f, 0.f}, s[3];
+    dir[i] = 1.f; support(G, dir, s, lane); xmax[i] = s[i];
+    dir[i] = -1.f; support(G, dir, s, lane); xmin[i] = s[i];
+  }
+  if (xmin[0] > sx || xmax[0] < -sx || xmin[1] > sy || xmax[1] < -sy || xmin[2] > sz || xmax[2] < -base) return;
+  int cmin = (int)floorf((xmin[0] + sx) / (2.f * sx) * (float)(ncol - 1));
+  int cmax = (int)ceilf((xmax[0] + sx) / (2.f * sx) * (float)(ncol - 1));
+  int rmin = (int)floorf((xmin[1] + sy) / (2.f * sy) * (float)(nrow - 1));
+  int rmax = (int)ceilf((xmax[1] + sy) / (2.f * sy) * (float)(nrow - 1));
+  cmin = imax(0, cmin); rmin = imax(0, rmin); cmax = imin(ncol - 1, cmax); rmax = imin(nrow - 1, rmax);
+  int cnt = 0;
+  float P[6][3];
+  for (int r = rmin; r < rmax; ++r) {
+    int nvert = 0;
+    for (int c = cmin; c <= cmax; ++c) {
+      for (int i = 0; i < 2; ++i) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { P[0][k] = P[1][k]; P[1][k] = P[2][k]; P[3][k] = P[4][k]; P[4][k] = P[5][k]; }
+        const float x = dx * (float)c - sx, y = dy * (float)(r + i) - sy;
+        P[2][0] = P[5][0] = x; P[2][1] = P[5][1] = y;
+        P[2][2] = -base; P[5][2] = LDG(m.hfield_data + (size_t)(r + i) * ncol + c) * sz;
+        ++nvert;
+        if (nvert > 2) {
+          if (P[3][2] < xmin[2] && P[4][2] < xmin[2] && P[5][2] < xmin[2]) continue;
+          float depth, dir[3], cp[3];
+          if (mpr_penetration(m, P, G, &depth, dir, cp, lane) == 0) {
+            if (dir[0] == 0.f && dir[1] == 0.f && dir[2] == 0.f) continue;
+            if (!(depth == depth)) continue;
+            add_contact(m, ws, ncon, dropped, cp, dir, -depth, g, ((r * ncol + (c - 1)) << 1) | i, lane);
+            if (++cnt >= 50) return;
+          }
+        }
+      }
+    }
+  }
+}
+
+DEV void collide_plane(const ModelDev& m, float* ws, int g, int& ncon, int& dropped, int lane) {
+  const GeomW G = make_geom(m, ws, g);
+  const float n[3] = {0.f, 0.f, 1.f};
+  if (G.type == GEOM_SPHERE) {
+    float dist = G.pos[2] - G.size[0];
+    if (dist > 0.f) return;
+    float p[3]; v3addscl(p, G.pos, n, -(G.size[0] + dist * 0.5f));
+    add_contact(m, ws, ncon, dropped, p, n, dist, g, -1, lane);
+  } else if (G.type == GEOM_CYLINDER) {
+    float axis[3] = {G.mat[2], G.mat[5], G.mat[8]};
+    float prjaxis = v3dot(n, axis);
+    if (prjaxis > 0.f) { v3scl(axis, axis, -1.f); prjaxis = -prjaxis; }
+    float dist0 = G.pos[2];
+    float vec[3]; v3scl(vec, axis, prjaxis); v3sub(vec, vec, n);
+    float len2 = v3dot(vec, vec);
+    if (len2 >= MINVALF * MINVALF) v3scl(vec, vec, G.size[0] / sqrtf(len2));
+    else { vec[0] = G.mat[0] * G.size[0]; vec[1] = G.mat[3] * G.size[0]; vec[2] = G.mat[6] * G.size[0]; }
+    float prjvec = v3dot(vec, n);
+    v3scl(axis, axis, G.size[1]); prjaxis *= G.size[1];
+    if (dist0 + prjaxis + prjvec > 0.f) return;
+    float dist = dist0 + prjaxis + prjvec, p[3];
+    for (int k = 0; k < 3; ++k) p[k] = G.pos[k] + vec[k] + axis[k] - n[k] * dist * 0.5f;
+    add_contact(m, ws, ncon, dropped, p, n, dist, g, -1, lane);
+    if (dist0 - prjaxis + prjvec <= 0.f) {
+      dist = dist0 - prjaxis + prjvec;
+      for (int k = 0; k < 3; ++k) p[k] = G.pos[k] + vec[k] - axis[k] - n[k] * dist * 0.5f;
+      add_contact(m, ws, ncon, dropped, p, n, dist, g, -1, lane);
+    }
+    float prjvec1 = -prjvec * 0.5f;
+    if (dist0 + prjaxis + prjvec1 <= 0.f) {
+      float vec1[3]; v3cross(vec1, vec, axis); v3normalize(vec1); v3scl(vec1, vec1, G.size[0] * sqrtf(3.f) * 0.5f);
+      dist = dist0 + prjaxis + prjvec1;
+      for (int k = 0; k < 3; ++k) p[k] = G.pos[k] + vec1[k] + axis[k] - vec[k] * 0.5f - n[k] * dist * 0.5f;
+      add_contact(m, ws, ncon, dropped, p, n, dist, g, -1, lane);
+      for (int k = 0; k < 3; ++k) p[k] = G.pos[k] - vec1[k] + axis[k] - vec[k] * 0.5f - n[k] * dist * 0.5f;
+      add_contact(m, ws, ncon, dropped, p, n, dist, g, -1, lane);
+    }
+  } else if (G.type == GEOM_BOX) {
+    int cnt = 0;
+    for (int i = 0; i < 8 && cnt < 4; ++i) {
+      float lc[3] = {(i & 1 ? G.size[0] : -G.size[0]), (i & 2 ? G.size[1] : -G.size[1]), (i & 4 ? G.size[2] : -G.size[2])}, w[3], p[3];
+      m3mulv(w, G.mat, lc);
+      float dist = G.pos[2] + w[2];
+      if (dist > 0.f) continue;
+      for (int k = 0; k < 3; ++k) p[k] = G.pos[k] + w[k] - n[k] * dist * 0.5f;
+      add_contact(m, ws, ncon, dropped, p, n, dist, g, -1, lane); ++cnt;
+    }
+  } else if (G.type == GEOM_MESH) {
+    // up to 4 deepest hull vertices below the plane (ties: lowest index): 4 rounds of warp arg-min with exclusion
+    int taken[4] = {-1, -1, -1, -1};
+    for (int c = 0; c < 4; ++c) {
+      float bv = -INFINITY; int best = 0x7fffffff;
+      for (int i = lane; i < G.nvert; i += LANES) {
+        if (i == taken[0] || i == taken[1] || i == taken[2]) continue;
+        float z = G.mat[6] * LDG(G.verts + 3 * i) + G.mat[7] * LDG(G.verts + 3 * i + 1) + G.mat[8] * LDG(G.verts + 3 * i + 2);
+        if (-z > bv) { bv = -z; best = i; }
+      }
+      wargmax(bv, best);
+      if (best == 0x7fffffff) break;
+      float lv[3] = {LDG(G.verts + 3 * best), LDG(G.verts + 3 * best + 1), LDG(G.verts + 3 * best + 2)}, w[3], p[3];
+      m3mulv(w, G.mat, lv);
+      float dist = G.pos[2] + w[2];
+      if (dist > 0.f) break;
+      taken[c] = best;
+      for (int k = 0; k < 3; ++k) p[k] = G.pos[k] + w[k] - n[k] * dist * 0.5f;
+      add_contact(m, ws, ncon, dropped, p, n, dist, g, -1, lane);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------ constraints
+DEV float impedance(const float* s_in, float pos) {
+  float s0 = fminf(0.9999f, fmaxf(1e-4f, s_in[0])), s1 = fminf(0.9999f, fmaxf(1e-4f, s_in[1]));
+  float s2 = fmaxf(0.f, s_in[2]), s3 = fminf(0.9999f, fmaxf(1e-4f, s_in[3])), s4 = fmaxf(1.f, s_in[4]);
+  if (s0 == s1 || s2 <= MINVALF) return 0.5f * (s0 + s1);
+  float x = fabsf(pos) / s2;
+  if (x >= 1.f) return s1;
+  if (x <= 0.f) return s0;
+  float y;
+  if (s4 == 1.f) y = x;
+  else if (x <= s3) { float a = 1.f / powf(s3, s4 - 1.f); y = a * powf(x, s4); }
+  else { float b = 1.f / powf(1.f - s3, s4 - 1.f); y = 1.f - b * powf(1.f - x, s4); }
+  return s0 + y * (s1 - s0);
+}
+// K, B of the reference acceleration for given solref/solimp (refsafe)
+DEV void kb_params(const ModelDev& m, const float* solref, const float* solimp, float* K, float* B) {
+  float dmax = fminf(0.9999f, fmaxf(1e-4f, solimp[1]));
+  float tc = fmaxf(solref[0], 2.f * MO(timestep)), dr = solref[1];
+  *K = 1.f / fmaxf(MINVALF, dmax * dmax * tc * tc * dr * dr);
+  *B = 2.f / fmaxf(MINVALF, dmax * tc);
+}
+// translational point Jacobian column for dof k at world point (offset from subtree COM), if dof k moves `body`
+DEV void jac_col(const ModelDev& m, const float* ws, int body, int k, const float* off, float* jp) {
+  if ((m.body_dofmask[body] >> k) & 1) {
+    const float* cd = WS(W_CDOF) + 6 * k; float c[3]; v3cross(c, cd, off);
+    jp[0] = cd[3] + c[0]; jp[1] = cd[4] + c[1]; jp[2] = cd[5] + c[2];
+  } else { jp[0] = jp[1] = jp[2] = 0.f; }
+}
+
+DEV void make_constraint(const ModelDev& m, float* ws, int ncon, int lane) {
+  const int nv = MD(nv), njnt = MD(njnt), neq = MD(neq);
+  const float solref[2] = {MO(solref0), MO(solref1)};
+  const float solimp[5] = {MO(solimp0), MO(solimp1), MO(solimp2), MO(solimp3), MO(solimp4)};
+  float K, B; kb_params(m, solref, solimp, &K, &B);
+  const float* qvel = WS(W_QVEL); const float* qpos = WS(W_QPOS); const float* scom = WS(W_SCOM);
+  // equality: connect
+  for (int e = 0; e < neq; ++e) {
+    const int b1 = m.eq_body1[e], b2 = m.eq_body2[e];
+    float a1[3] = {LDG(m.eq_anchor1 + 3 * e), LDG(m.eq_anchor1 + 3 * e + 1), LDG(m.eq_anchor1 + 3 * e + 2)};
+    float a2[3] = {LDG(m.eq_anchor2 + 3 * e), LDG(m.eq_anchor2 + 3 * e + 1), LDG(m.eq_anchor2 + 3 * e + 2)};
+    float p1[3], p2[3], r[3], o1[3], o2[3];
+    m3mulv(r, WS(W_XMAT) + 9 * b1, a1); v3add(p1, WS(W_XPOS) + 3 * b1, r);
+    m3mulv(r, WS(W_XMAT) + 9 * b2, a2); v3add(p2, WS(W_XPOS) + 3 * b2, r);
+    v3sub(o1, p1, scom); v3sub(o2, p2, scom);
+    float* J = WS(W_EQ_J) + (size_t)3 * e * nv;
+    float vel[3] = {0.f, 0.f, 0.f};
+    FOR_LANE(k, nv) {
+      float j1[3], j2[3]; jac_col(m, ws, b1, k, o1, j1); jac_col(m, ws, b2, k, o2, j2);
+      for (int r_ = 0; r_ < 3; ++r_) { float v = j1[r_] - j2[r_]; J[r_ * nv + k] = v; vel[r_] += v * qvel[k]; }
+    }
+    vel[0] = wsum(vel[0]); vel[1] = wsum(vel[1]); vel[2] = wsum(vel[2]);
+    float pe[3]; v3sub(pe, p1, p2);
+    float si[5]; for (int i = 0; i < 5; ++i) si[i] = LDG(m.eq_solimp + 5 * e + i);
+    float sr[2] = {LDG(m.eq_solref + 2 * e), LDG(m.eq_solref + 2 * e + 1)};
+    float imp = impedance(si, v3norm(pe)), Ke, Be; kb_params(m, sr, si, &Ke, &Be);
+    float diag = WS(W_INVWB)[b1] + WS(W_INVWB)[b2];
+    float R = fmaxf(MINVALF, (1.f - imp) * diag / imp);
+    FOR_LANE(i, 3) { WS(W_EQ_D)[3 * e + i] = 1.f / R; WS(W_EQ_AREF)[3 * e + i] = -Be * vel[i] - Ke * imp * pe[i]; }
+  }
+  // dof friction loss: D = 0 marks "no row"
+  FOR_LANE(k, nv) {
+    float fl = WS(W_FLOSS)[k];
+    if (fl > 0.f) {
+      float imp = impedance(solimp, 0.f);
+      float R = fmaxf(MINVALF, (1.f - imp) * WS(W_INVWD)[k] / imp);
+      WS(W_FR_D)[k] = 1.f / R; WS(W_FR_AREF)[k] = -B * qvel[k];
+    } else { WS(W_FR_D)[k] = 0.f; WS(W_FR_AREF)[k] = 0.f; }
+  }
+  // joint limits: at most one side active per joint (lo < hi); sign 0 marks "no row"
+  FOR_LANE(j, njnt) {
+    float sign = 0.f, D = 0.f, aref = 0.f;
+    if (m.jnt_limited[j]) {
+      const float q = qpos[m.jnt_qposadr[j]]; const int k = m.jnt_dofadr[j];
+      float dlo = q - LDG(m.jnt_range + 2 * j), dhi = LDG(m.jnt_range + 2 * j + 1) - q;
+      float dist = 0.f;
+      if (dlo < 0.f) { sign = 1.f; dist = dlo; } else if (dhi < 0.f) { sign = -1.f; dist = dhi; }
+      if (sign != 0.f) {
+        float imp = impedance(solimp, dist);
+        float R = fmaxf(MINVALF, (1.f - imp) * WS(W_INVWD)[k] / imp);
+        D = 1.f / R; aref = -B * (sign * qvel[k]) - K * imp * dist;
+      }
+    }
+    WS(W_LM_SIGN)[j] = sign; WS(W_LM_D)[j] = D; WS(W_LM_AREF)[j] = aref;
+  }
+  // contacts: 3 x nv frame Jacobian per contact; 4 pyramid edges share D = 1/(2 mu^2 R_first)
+  for (int idx = lane; idx < ncon * nv; idx += LANES) {
+    const int c = idx / nv, k = idx - c * nv;
+    const float* fr = WS(W_CN_FRAME) + 9 * c; float off[3], jp[3];
+    v3sub(off, WS(W_CN_POS) + 3 * c, scom);
+    jac_col(m, ws, WSI(W_CN_BODY)[c], k, off, jp);
+    float* J = WS(W_CN_J) + (size_t)3 * c * nv;
+    J[k] = v3dot(fr, jp); J[nv + k] = v3dot(fr + 3, jp); J[2 * nv + k] = v3dot(fr + 6, jp);
+  }
+  SYNC();
+  for (int idx = lane; idx < ncon * 4; idx += LANES) {
+    const int c = idx >> 2, e = idx & 3;
+    const float* J = WS(W_CN_J) + (size_t)3 * c * nv; const float* Jt = J + (1 + (e >> 1)) * nv;
+    const float mu = WS(W_CN_MU)[c], sg = (e & 1) ? -mu : mu, dist = WS(W_CN_DIST)[c];
+    float vel = 0.f;
+    for (int k = 0; k < nv; ++k) vel += (J[k] + sg * Jt[k]) * qvel[k];
+    float imp = impedance(solimp, dist);
+    WS(W_CN_AREF)[idx] = -B * vel - K * imp * dist;
+    if (e == 0) {
+      float tran = WS(W_INVWB)[WSI(W_CN_BODY)[c]];
+      float R = fmaxf(MINVALF, (1.f - imp) * (tran + mu * mu * tran) / imp);
+      WS(W_CN_D)[c] = 1.f / (2.f * mu * mu * R);
+    }
+  }
+  SYNC();
+}
+
+// ------------------------------------------------------------------------------------------ Newton solver
+// evaluates rows at x0 + alpha*dx; returns per-lane partial sums of (cost, d0, d1); writes nothing.
+// X arrays hold J*qacc - aref ("Jaref") per row, V arrays hold J*search.
+struct RowSum { float cost, d0, d1; };
+DEV void row_acc(RowSum& s, float x0, float jv, float a, float D, int kind, float Rf, float f) {
+  const float x = x0 + a * jv;
+  if (kind == 1) {           // friction loss (Huber)
+    if (x <= -Rf) { s.cost += f * (-0.5f * Rf - x); s.d0 -= f * jv; return; }
+    if (x >= Rf) { s.cost += f * (-0.5f * Rf + x); s.d0 += f * jv; return; }
+  } else if (kind == 2) {    // inequality (limit, pyramid edge)
+    if (x >= 0.f) return;
+  }
+  s.cost += 0.5f * D * x * x; s.d0 += D * x * jv; s.d1 += D * jv * jv;
+}
+DEV RowSum eval_rows(const ModelDev& m, const float* ws, int ncon, float a, bool use_v, int lane) {
+  const int nv = MD(nv), njnt = MD(njnt), neq3 = 3 * MD(neq);
+  RowSum s = {0.f, 0.f, 0.f};
+  FOR_LANE(i, neq3) row_acc(s, WS(W_EQ_X)[i], use_v ? WS(W_EQ_V)[i] : 0.f, a, WS(W_EQ_D)[i], 0, 0.f, 0.f);
+  FOR_LANE(k, nv) {
+    const float D = WS(W_FR_D)[k];
+    if (D > 0.f) { const float f = WS(W_FLOSS)[k]; row_acc(s, WS(W_TMPW)[k], use_v ? WS(W_SEARCH)[k] : 0.f, a, D, 1, f / D, f); }
+  }
+  FOR_LANE(j, njnt) {
+    const float sg = WS(W_LM_SIGN)[j];
+    if (sg != 0.f) { const int k = m.jnt_dofadr[j]; row_acc(s, sg * WS(W_QACC)[k] - WS(W_LM_AREF)[j], use_v ? sg * WS(W_SEARCH)[k] : 0.f, a, WS(W_LM_D)[j], 2, 0.f, 0.f); }
+  }
+  for (int idx = lane; idx < 4 * ncon; idx += LANES) row_acc(s, WS(W_CN_X)[idx], use_v ? WS(W_CN_V)[idx] : 0.f, a, WS(W_CN_D)[idx >> 2], 2, 0.f, 0.f);
+  return s;
+}
+// X = J*q - aref for every row class, given q (length nv).  friction rows' X go to W_TMPW.
+DEV void compute_jaref(const ModelDev& m, float* ws, int ncon, const float* q, int lane) {
+  const int nv = MD(nv), neq3 = 3 * MD(neq);
+  FOR_LANE(i, neq3) { const float* J = WS(W_EQ_J) + (size_t)i * nv; float s = 0.f; for (int k = 0; k < nv; ++k) s += J[k] * q[k]; WS(W_EQ_X)[i] = s - WS(W_EQ_AREF)[i]; }
+  FOR_LANE(k, nv) WS(W_TMPW)[k] = q[k] - WS(W_FR_AREF)[k];
+  for (int idx = lane; idx < 4 * ncon; idx += LANES) {
+    const int c = idx >> 2, e = idx & 3;
+    const float* J = WS(W_CN_J) + (size_t)3 * c * nv; const float* Jt = J + (1 + (e >> 1)) * nv;
+    const float mu = WS(W_CN_MU)[c], sg = (e & 1) ? -mu : mu;
+    float s = 0.f; for (int k = 0; k < nv; ++k) s += (J[k] + sg * Jt[k]) * q[k];
+    WS(W_CN_X)[idx] = s - WS(W_CN_AREF)[idx];
+  }
+  SYNC();
+}
+DEV void compute_jv(const ModelDev& m, float* ws, int ncon, const float* v, int lane) {
+  const int nv = MD(nv), neq3 = 3 * MD(neq);
+  FOR_LANE(i, neq3) { const float* J = WS(W_EQ_J) + (size_t)i * nv; float s = 0.f; for (int k = 0; k < nv; ++k) s += J[k] * v[k]; WS(W_EQ_V)[i] = s; }
+  for (int idx = lane; idx < 4 * ncon; idx += LANES) {
+    const int c = idx >> 2, e = idx & 3;
+    const float* J = WS(W_CN_J) + (size_t)3 * c * nv; const float* Jt = J + (1 + (e >> 1)) * nv;
+    const float mu = WS(W_CN_MU)[c], sg = (e & 1) ? -mu : mu;
+    float s = 0.f; for (int k = 0; k < nv; ++k) s += (J[k] + sg * Jt[k]) * v[k];
+    WS(W_CN_V)[idx] = s;
+  }
+  SYNC();
+}
+DEV void mat_vec(const float* M, const float* x, float* y, int n, int lane) {
+  FOR_LANE(i, n) { float s = 0.f; for (int k = 0; k < n; ++k) s += M[i * n + k] * x[k]; y[i] = s; }
+  SYNC();
+}
+// constraint forces from current X; qfrc_constraint -> W_FCON; contact frame forces -> W_CN_F; returns constraint cost
+DEV float update_forces(const ModelDev& m, float* ws, int ncon, int lane) {
+  const int nv = MD(nv), njnt = MD(njnt), neq = MD(neq);
+  float cost = 0.f;
+  FOR_LANE(i, 3 * neq) { const float x = WS(W_EQ_X)[i], D = WS(W_EQ_D)[i]; WS(W_EQ_F)[i] = -D * x; cost += 0.5f * D * x * x; }
+  for (int c = lane; c < ncon; c += LANES) {
+    const float D = WS(W_CN_D)[c], mu = WS(W_CN_MU)[c]; float f[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { const float x = WS(W_CN_X)[4 * c + e]; f[e] = x < 0.f ? -D * x : 0.f; if (x < 0.f) cost += 0.5f * D * x * x; }
+    WS(W_CN_F)[3 * c] = f[0] + f[1] + f[2] + f[3]; WS(W_CN_F)[3 * c + 1] = mu * (f[0] - f[1]); WS(W_CN_F)[3 * c + 2] = mu * (f[2] - f[3]);
+  }
+  SYNC();
+  FOR_LANE(k, nv) {
+    float q = 0.f;
+    const float D = WS(W_FR_D)[k];
+    if (D > 0.f) {
+      const float x = WS(W_TMPW)[k], f = WS(W_FLOSS)[k], Rf = f / D;
+      if (x <= -Rf) { q += f; cost += f * (-0.5f * Rf - x); }
+      else if (x >= Rf) { q -= f; cost += f * (-0.5f * Rf + x); }
+      else { q -= D * x; cost += 0.5f * D * x * x; }
+    }
+    const int j = m.dof_jnt[k];
+    const float sg = WS(W_LM_SIGN)[j];
+    if (sg != 0.f && m.jnt_dofadr[j] == k) {
+      const float x = sg * WS(W_QACC)[k] - WS(W_LM_AREF)[j], Dl = WS(W_LM_D)[j];
+      if (x < 0.f) { q += sg * (-Dl * x); cost += 0.5f * Dl * x * x; }
+    }
+    for (int c = 0; c < ncon; ++c) {
+      const float* J = WS(W_CN_J) + (size_t)3 * c * nv; const float* F = WS(W_CN_F) + 3 * c;
+      q += J[k] * F[0] + J[nv + k] * F[1] + J[2 * nv + k] * F[2];
+    }
+    for (int i = 0; i < 3 * neq; ++i) q += WS(W_EQ_J)[(size_t)i * nv + k] * WS(W_EQ_F)[i];
+    WS(W_FCON)[k] = q;
+  }
+  SYNC();
+  (void)njnt;
+  return wsum(cost);
+}
+// total cost at q (Gauss + constraints); leaves X / forces for q
+DEV float total_cost(const ModelDev& m, float* ws, int ncon, const float* q, float* Mq, int lane) {
+  const int nv = MD(nv);
+  mat_vec(WS(W_M), q, Mq, nv, lane);
+  if (q != WS(W_QACC)) { FOR_LANE(k, nv) WS(W_QACC)[k] = q[k]; SYNC(); }
+  compute_jaref(m, ws, ncon, q, lane);
+  float c = update_forces(m, ws, ncon, lane);
+  float g = 0.f;
+  FOR_LANE(k, nv) g += (Mq[k] - WS(W_FSMOOTH)[k]) * (q[k] - WS(W_ASMOOTH)[k]);
+  return c + 0.5f * wsum(g);
+}
+
+// Newton with exact line search on the primal cost [SURVEY.md B.8]; same control flow as the
+// oracle's solve()/linesearch() (oracle/oracle.hpp), lanes split the rows inside every evaluation.
+// fp32 note: the reference's line-search gradient tolerance (tolerance * ls_tolerance * |search| *
+// meaninertia * nv ~ 1e-10) sits far below fp32 round-off of the derivative, so it is floored at a
+// few ulps of the magnitude of the terms the derivative is summed from.
+struct LSPoint { float alpha, cost, d0, d1; };
+DEV LSPoint ls_eval(const ModelDev& m, const float* ws, int ncon, float a, float q0, float q1, float q2, int lane) {
+  RowSum s = eval_rows(m, ws, ncon, a, true, lane);
+  LSPoint p; p.alpha = a;
+  p.cost = a * a * q2 + a * q1 + q0 + wsum(s.cost);
+  p.d0 = 2.f * a * q2 + q1 + wsum(s.d0);
+  p.d1 = 2.f * q2 + wsum(s.d1);
+  if (p.d1 <= 0.f) p.d1 = MINVALF;
+  return p;
+}
+DEV int ls_update(LSPoint& p, const LSPoint* cand) {
+  int flag = 0;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    if (p.d0 < 0.f && cand[i].d0 < 0.f && p.d0 < cand[i].d0) { p = cand[i]; flag = 1; }
+    else if (p.d0 > 0.f && cand[i].d0 > 0.f && p.d0 > cand[i].d0) { p = cand[i]; flag = 2; }
+  }
+  return flag;
+}
+DEV float linesearch(const ModelDev& m, const float* ws, int ncon, float gauss, float q1, float q2, float snorm, float absterms, int lane) {
+  if (snorm < MINVALF) return 0.f;
+  const float gtol = fmaxf(MO(tolerance) * MO(ls_tolerance) * snorm * WS(W_SCAL)[1] * (float)imax(1, MD(nv)), 1e-6f * absterms);
+  const int maxit = MD(ls_iterations);
+  int iter = 0;
+#define LS_EVAL(a) (++iter, ls_eval(m, ws, ncon, (a), gauss, q1, q2, lane))
+  const LSPoint p0 = LS_EVAL(0.f);
+  LSPoint p1 = LS_EVAL(p0.alpha - p0.d0 / p0.d1);
+  if (p0.cost < p1.cost) p1 = p0;
+  if (fabsf(p1.d0) < gtol) return p1.alpha;
+  const float dir = p1.d0 < 0.f ? 1.f : -1.f;
+  LSPoint p2 = p1; bool p2upd = false;
+  while (p1.d0 * dir <= -gtol && iter < maxit) {
+    p2 = p1; p2upd = true;
+    p1 = LS_EVAL(p1.alpha - p1.d0 / p1.d1);
+    if (fabsf(p1.d0) < gtol) return p1.alpha;
+  }
+  if (iter >= maxit || !p2upd) return p1.alpha;
+  LSPoint p2next = p1, p1next = LS_EVAL(p1.alpha - p1.d0 / p1.d1);
+  while (iter < maxit) {
+    const LSPoint pmid = LS_EVAL(0.5f * (p1.alpha + p2.alpha));
+    const LSPoint cand[3] = {p1next, p2next, pmid};
+    int best = -1; float bc = 0.f;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) if (fabsf(cand[i].d0) < gtol && (best == -1 || cand[i].cost < bc)) { bc = cand[i].cost; best = i; }
+    if (best >= 0) return cand[best].alpha;
+    const int b1 = ls_update(p1, cand); if (b1) p1next = LS_EVAL(p1.alpha - p1.d0 / p1.d1);
+    const int b2 = ls_update(p2, cand); if (b2) p2next = LS_EVAL(p2.alpha - p2.d0 / p2.d1);
+    if (!b1 && !b2) return pmid.alpha;
+  }
+#undef LS_EVAL
+  if (p1.cost <= p2.cost && p1.cost < p0.cost) return p1.alpha;
+  if (p2.cost <= p1.cost && p2.cost < p0.cost) return p2.alpha;
+  return 0.f;
+}
+
+// grad = Ma - qfrc_smooth - qfrc_constraint; H = M + J' D_quad J; search = -H^-1 grad.  Returns |grad|.
+DEV float newton_direction(const ModelDev& m, float* ws, int ncon, int lane) {
+  const int nv = MD(nv), neq = MD(neq);
+  float* grad = WS(W_GRAD); float* H = WS(W_A); const float* M = WS(W_M); const float* qacc = WS(W_QACC); const float* Ma = WS(W_MA);
+  float gn = 0.f;
+  FOR_LANE(k, nv) { const float g = Ma[k] - WS(W_FSMOOTH)[k] - WS(W_FCON)[k]; grad[k] = g; gn += g * g; WS(W_TMPV)[k] = -g; }
+  gn = sqrtf(wsum(gn));
+  for (int idx = lane; idx < nv * nv; idx += LANES) {
+    const int i = idx / nv, j = idx - i * nv;
+    if (j > i) continue;
+    float h = M[idx];
+    for (int c = 0; c < ncon; ++c) {
+      const float* X = WS(W_CN_X) + 4 * c;
+      const float s0 = X[0] < 0.f, s1 = X[1] < 0.f, s2 = X[2] < 0.f, s3 = X[3] < 0.f;
+      if (s0 + s1 + s2 + s3 == 0.f) continue;
+      const float D = WS(W_CN_D)[c], mu = WS(W_CN_MU)[c];
+      const float* J = WS(W_CN_J) + (size_t)3 * c * nv;
+      const float gnn = D * (s0 + s1 + s2 + s3), gn1 = D * mu * (s0 - s1), gn2 = D * mu * (s2 - s3), g11 = D * mu * mu * (s0 + s1), g22 = D * mu * mu * (s2 + s3);
+      const float jn = J[j], j1 = J[nv + j], j2 = J[2 * nv + j];
+      h += J[i] * (gnn * jn + gn1 * j1 + gn2 * j2) + J[nv + i] * (gn1 * jn + g11 * j1) + J[2 * nv + i] * (gn2 * jn + g22 * j2);
+    }
+    for (int e = 0; e < 3 * neq; ++e) h += WS(W_EQ_D)[e] * WS(W_EQ_J)[(size_t)e * nv + i] * WS(W_EQ_J)[(size_t)e * nv + j];
+    if (i == j) {
+      const float D = WS(W_FR_D)[i];
+      if (D > 0.f) { const float x = WS(W_TMPW)[i], Rf = WS(W_FLOSS)[i] / D; if (x > -Rf && x < Rf) h += D; }
+      const int jn_ = m.dof_jnt[i]; const float sg = WS(W_LM_SIGN)[jn_];
+      if (sg != 0.f && m.jnt_dofadr[jn_] == i && (sg * qacc[i] - WS(W_LM_AREF)[jn_]) < 0.f) h += WS(W_LM_D)[jn_];
+    }
+    H[idx] = h;
+  }
+  SYNC();
+  chol_factor(H, WS(W_INVD), nv, lane);
+  chol_solve(H, WS(W_INVD), WS(W_TMPV), WS(W_BUF), WS(W_SEARCH), nv, lane);
+  return gn;
+}
+
+DEV int newton_solve(const ModelDev& m, float* ws, int ncon, int has_rows, int lane) {
+  const int nv = MD(nv), neq = MD(neq);
+  float* qacc = WS(W_QACC); float* Ma = WS(W_MA); float* Mv = WS(W_MV); float* search = WS(W_SEARCH);
+  const float* M = WS(W_M);
+  if (!has_rows) {
+    FOR_LANE(k, nv) { qacc[k] = WS(W_ASMOOTH)[k]; WS(W_WARM)[k] = WS(W_ASMOOTH)[k]; WS(W_FCON)[k] = 0.f; }
+    SYNC(); return 0;
+  }
+  // warm start: cheaper of qacc_warmstart and qacc_smooth [upstream mj_fwdConstraint]
+  const float cw = total_cost(m, ws, ncon, WS(W_WARM), Ma, lane);
+  float cost = total_cost(m, ws, ncon, WS(W_ASMOOTH), Ma, lane);
+  if (!(cw > cost)) cost = total_cost(m, ws, ncon, WS(W_WARM), Ma, lane);
+  const float scale = 1.f / (WS(W_SCAL)[1] * (float)imax(1, nv));
+  const float tol = MO(tolerance);
+  const int maxiter = MD(iterations);
+  (void)newton_direction(m, ws, ncon, lane);
+  int iter = 0;
+  while (iter < maxiter) {
+    mat_vec(M, search, Mv, nv, lane);
+    compute_jv(m, ws, ncon, search, lane);
+    float q1 = 0.f, q2 = 0.f, sn = 0.f, gauss = 0.f, absterms = 0.f;
+    FOR_LANE(k, nv) {
+      const float r = Ma[k] - WS(W_FSMOOTH)[k];
+      q1 += search[k] * r; q2 += 0.5f * search[k] * Mv[k]; sn += search[k] * search[k];
+      gauss += r * (qacc[k] - WS(W_ASMOOTH)[k]); absterms += fabsf(search[k] * r);
+      const float D = WS(W_FR_D)[k]; if (D > 0.f) absterms += fminf(fabsf(D * WS(W_TMPW)[k]), WS(W_FLOSS)[k]) * fabsf(search[k]);
+    }
+    FOR_LANE(i, 3 * neq) absterms += fabsf(WS(W_EQ_D)[i] * WS(W_EQ_X)[i] * WS(W_EQ_V)[i]);
+    for (int idx = lane; idx < 4 * ncon; idx += LANES) absterms += fabsf(WS(W_CN_D)[idx >> 2] * WS(W_CN_X)[idx] * WS(W_CN_V)[idx]);
+    q1 = wsum(q1); q2 = wsum(q2); sn = sqrtf(wsum(sn)); gauss = 0.5f * wsum(gauss); absterms = wsum(absterms);
+    const float alpha = linesearch(m, ws, ncon, gauss, q1, q2, sn, absterms, lane);
+    if (alpha == 0.f) break;
+    FOR_LANE(k, nv) { qacc[k] += alpha * search[k]; Ma[k] += alpha * Mv[k]; }
+    FOR_LANE(i, 3 * neq) WS(W_EQ_X)[i] += alpha * WS(W_EQ_V)[i];
+    for (int idx = lane; idx < 4 * ncon; idx += LANES) WS(W_CN_X)[idx] += alpha * WS(W_CN_V)[idx];
+    SYNC();
+    FOR_LANE(k, nv) WS(W_TMPW)[k] = qacc[k] - WS(W_FR_AREF)[k];
+    SYNC();
+    const float old = cost;
+    float g = 0.f;
+    FOR_LANE(k, nv) g += (Ma[k] - WS(W_FSMOOTH)[k]) * (qacc[k] - WS(W_ASMOOTH)[k]);
+    cost = update_forces(m, ws, ncon, lane) + 0.5f * wsum(g);
+    const float gn = newton_direction(m, ws, ncon, lane);
+    ++iter;
+    if (scale * (old - cost) < tol || scale * gn < tol) break;
+  }
+  FOR_LANE(k, nv) WS(W_WARM)[k] = qacc[k];
+  SYNC();
+  return iter;
+}
+
+// ------------------------------------------------------------------------------------------ sensors
+DEV void sensors(const ModelDev& m, float* ws, int lane) {
+  if (lane == 0) {
+    const int b = MD(imu_body);
+    float sq[4] = {m.imu_quat[0], m.imu_quat[1], m.imu_quat[2], m.imu_quat[3]};
+    quat_normalize(sq);
+    float* S = WS(W_SENS);
+    quat_mul(S, WS(W_XQUAT) + 4 * b, sq);
+    float smat[9]; quat_to_mat(smat, S);
+    float r[3], spos[3], off[3], c[3], lin[3];
+    m3mulv(r, WS(W_XMAT) + 9 * b, m.imu_pos); v3add(spos, WS(W_XPOS) + 3 * b, r);
+    const float* cv = WS(W_CVEL) + 6 * b;
+    v3sub(off, spos, WS(W_SCOM)); v3cross(c, cv, off); v3add(lin, cv + 3, c);
+    m3tmulv(S + 4, smat, cv); m3tmulv(S + 7, smat, lin);
+    for (int k = 0; k < 3; ++k) { S[4 + k] = fminf(34.9f, fmaxf(-34.9f, S[4 + k])); S[7 + k] = fminf(30.f, fmaxf(-30.f, S[7 + k])); }
+  }
+}
+
+// ------------------------------------------------------------------------------------------ forward + one sub-step
+// returns solver iterations; ncon_out / dropped_out = contacts of this forward pass
+DEV int forward(const ModelDev& m, float* ws, int& ncon_out, int& dropped_out, int lane) {
+  const int nv = MD(nv), nu = MD(nu), njnt = MD(njnt);
+  kinematics(m, ws, lane);
+  com_pos(m, ws, lane);
+  crb(m, ws, lane);
+  float* A = WS(W_A); const float* M = WS(W_M);
+  FOR_LANE(i, nv * nv) A[i] = M[i];
+  SYNC();
+  chol_factor(A, WS(W_INVD), nv, lane);
+  int ncon = 0, dropped = 0;
+  for (int g = 0; g < MD(ngeom); ++g) { if (MD(ground_type) == 1) collide_hfield(m, ws, g, ncon, dropped, lane); else collide_plane(m, ws, g, ncon, dropped, lane); }
+  SYNC();
+  com_vel(m, ws, lane);
+  make_constraint(m, ws, ncon, lane);
+  sensors(m, ws, lane);
+  // smooth forces: passive damping - bias + actuation (ctrl clamp, gear, actuatorfrcrange clamp)
+  rne_bias(m, ws, WS(W_TMPV), lane);
+  float* fs = WS(W_FSMOOTH);
+  FOR_LANE(k, nv) fs[k] = -LDG(m.dof_damping + k) * WS(W_QVEL)[k] - WS(W_TMPV)[k];
+  SYNC();
+  FOR_LANE(a, nu) {
+    float c = WS(W_CTRL)[a];
+    if (m.act_ctrllimited[a]) c = fminf(LDG(m.act_ctrlrange + 2 * a + 1), fmaxf(LDG(m.act_ctrlrange + 2 * a), c));
+    float f = LDG(m.act_gear + a) * c;
+    const int k = m.act_dof[a], j = m.dof_jnt[k];
+    if (m.jnt_actfrclimited[j]) f = fminf(LDG(m.jnt_actfrcrange + 2 * j + 1), fmaxf(LDG(m.jnt_actfrcrange + 2 * j), f));
+    fs[k] += f;     // one actuator per joint in all four robots
+  }
+  SYNC();
+  FOR_LANE(k, nv) WS(W_TMPV)[k] = fs[k];
+  SYNC();
+  chol_solve(A, WS(W_INVD), WS(W_TMPV), WS(W_BUF), WS(W_ASMOOTH), nv, lane);
+  // any constraint row?
+  int rows = (ncon > 0) || (MD(neq) > 0);
+  { int r = 0; FOR_LANE(k, nv) r |= (WS(W_FR_D)[k] > 0.f); FOR_LANE(j, njnt) r |= (WS(W_LM_SIGN)[j] != 0.f); rows |= wor(r); }
+  int iters = newton_solve(m, ws, ncon, rows, lane);
+  ncon_out = ncon; dropped_out = dropped;
+  return iters;
+}
+
+DEV int bad_state(const ModelDev& m, const float* ws, int lane) {
+  int bad = 0;
+  FOR_LANE(i, MD(nq)) { float x = WS(W_QPOS)[i]; bad |= !(x == x) || fabsf(x) > 1e10f; }
+  FOR_LANE(i, MD(nv)) { float x = WS(W_QVEL)[i]; bad |= !(x == x) || fabsf(x) > 1e10f; }
+  return wor(bad);
+}
+DEV void reset_data(const ModelDev& m, float* ws, int lane) {
+  FOR_LANE(i, MD(nq)) WS(W_QPOS)[i] = LDG(m.qpos0 + i);
+  FOR_LANE(i, MD(nv)) { WS(W_QVEL)[i] = 0.f; WS(W_WARM)[i] = 0.f; }
+  SYNC();
+}
+
+DEV int substep(const ModelDev& m, float* ws, int& ncon, int& dropped, int& nan_count, int lane) {
+  const int nv = MD(nv), njnt = MD(njnt);
+  if (bad_state(m, ws, lane)) { reset_data(m, ws, lane); ++nan_count; }
+  int iters = forward(m, ws, ncon, dropped, lane);
+  { int bad = 0; FOR_LANE(i, nv) { float x = WS(W_QACC)[i]; bad |= !(x == x) || fabsf(x) > 1e10f; }
+    if (wor(bad)) { reset_data(m, ws, lane); ++nan_count; iters = forward(m, ws, ncon, dropped, lane); } }
+  // implicitfast: (M + dt diag(damping)) a = qfrc_smooth + qfrc_constraint
+  const float dt = MO(timestep);
+  float* A = WS(W_A); const float* M = WS(W_M);
+  FOR_LANE(i, nv * nv) { const int r = i / nv, c = i - r * nv; A[i] = M[i] + (r == c ? dt * LDG(m.dof_damping + r) : 0.f); }
+  FOR_LANE(k, nv) WS(W_TMPV)[k] = WS(W_FSMOOTH)[k] + WS(W_FCON)[k];
+  SYNC();
+  chol_factor(A, WS(W_INVD), nv, lane);
+  chol_solve(A, WS(W_INVD), WS(W_TMPV), WS(W_BUF), WS(W_GRAD), nv, lane);
+  float* qvel = WS(W_QVEL); float* qpos = WS(W_QPOS);
+  FOR_LANE(k, nv) qvel[k] += dt * WS(W_GRAD)[k];
+  SYNC();
+  FOR_LANE(j, njnt) {
+    const int qa = m.jnt_qposadr[j], da = m.jnt_dofadr[j];
+    if (m.jnt_type[j] == 0) {
+      for (int k = 0; k < 3; ++k) qpos[qa + k] += dt * qvel[da + k];
+      float w[3] = {qvel[da + 3], qvel[da + 4], qvel[da + 5]};
+      float ang = v3norm(w) * dt;
+      if (ang > 0.f) {
+        v3normalize(w);
+        float s, c; sincosf(ang * 0.5f, &s, &c);
+        float dq[4] = {c, w[0] * s, w[1] * s, w[2] * s}, q[4];
+        quat_mul(q, qpos + qa + 3, dq); quat_normalize(q);
+        qpos[qa + 3] = q[0]; qpos[qa + 4] = q[1]; qpos[qa + 5] = q[2]; qpos[qa + 6] = q[3];
+      }
+    } else qpos[qa] += dt * qvel[da];
+  }
+  SYNC();
+  return iters;
+}
+
+// cfrc_ext of the bodies in contact / connected -> W_CACC region reused as [nbody][6]
+DEV void cfrc_ext(const ModelDev& m, float* ws, int ncon, int lane) {
+  const int nb = MD(nbody), neq = MD(neq);
+  float* out = WS(W_CACC); const float* scom = WS(W_SCOM);
+  FOR_LANE(i, 6 * nb) out[i] = 0.f;
+  SYNC();
+  if (lane == 0) {   // few contacts; sequential keeps the summation order fixed
+    for (int c = 0; c < ncon; ++c) {
+      const float* F = WS(W_CN_F) + 3 * c; float wf[3], arm[3], tq[3];
+      m3tmulv(wf, WS(W_CN_FRAME) + 9 * c, F);
+      v3sub(arm, WS(W_CN_POS) + 3 * c, scom); v3cross(tq, arm, wf);
+      float* o = out + 6 * WSI(W_CN_BODY)[c];
+      for (int k = 0; k < 3; ++k) { o[k] += tq[k]; o[3 + k] += wf[k]; }
+    }
+    for (int e = 0; e < neq; ++e) {
+      const int b1 = m.eq_body1[e], b2 = m.eq_body2[e];
+      float a1[3] = {m.eq_anchor1[3 * e], m.eq_anchor1[3 * e + 1], m.eq_anchor1[3 * e + 2]}, p1[3], r[3], arm[3], tq[3];
+      m3mulv(r, WS(W_XMAT) + 9 * b1, a1); v3add(p1, WS(W_XPOS) + 3 * b1, r);
+      const float* wf = WS(W_EQ_F) + 3 * e;
+      v3sub(arm, p1, scom); v3cross(tq, arm, wf);
+      for (int k = 0; k < 3; ++k) { out[6 * b1 + k] += tq[k]; out[6 * b1 + 3 + k] += wf[k]; out[6 * b2 + k] -= tq[k]; out[6 * b2 + 3 + k] -= wf[k]; }
+    }
+  }
+  SYNC();
+}
+
+// ------------------------------------------------------------------------------------------ height map (K9)
+DEV float hfield_height(const ModelDev& m, float x, float y, int* cell) {
+  const int nrow = MD(hf_nrow), ncol = MD(hf_ncol);
+  const float sx = MO(hf_sx), sy = MO(hf_sy), sz = MO(hf_sz);
+  *cell = -1;
+  if (x < -sx || x > sx || y < -sy || y > sy) return NAN;
+  const float dx = 2.f * sx / (float)(ncol - 1), dy = 2.f * sy / (float)(nrow - 1);
+  int c = (int)floorf((x + sx) / dx), r = (int)floorf((y + sy) / dy);
+  c = imin(imax(c, 0), ncol - 2); r = imin(imax(r, 0), nrow - 2);
+  const float u = (x - (dx * (float)c - sx)) / dx, v = (y - (dy * (float)r - sy)) / dy;
+  const float* h = m.hfield_data + (size_t)r * ncol + c;
+  const float z00 = LDG(h) * sz, z10 = LDG(h + 1) * sz, z01 = LDG(h + ncol) * sz, z11 = LDG(h + ncol + 1) * sz;
+  float z; int tri;
+  if (u >= v) { tri = 0; z = z00 + u * (z10 - z00) + v * (z11 - z10); }
+  else { tri = 1; z = z00 + v * (z01 - z00) + u * (z11 - z01); }
+  *cell = ((r * ncol + c) << 1) | tri;
+  return z;
+}

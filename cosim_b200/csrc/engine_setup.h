@@ -1,0 +1,208 @@
+// engine_setup.h -- host side of the engine: model blob -> ModelDev (read-only tables in device
+// memory) + the per-warp shared-memory workspace layout.  Plain C++; memory comes from the
+// `Uploader` the caller supplies (cudaMalloc+cudaMemcpy in engine.cu; malloc in tests/hostsim).
+//
+// Replaces, together with cosim_b200/model.py, what MjModel.from_xml_path hands to mj_step in the
+// reference (gymnasium MujocoEnv.__init__, /root/reference/envs/flamingo_p_v3/flamingo_p_v3.py:94-100).
+#pragma once
+#include <string>
+#include <vector>
+#include <stdexcept>
+#include "engine_core.h"
+
+struct Uploader {
+  void* (*up)(void* ctx, const void* host, size_t bytes);   // returns a device copy (never NULL for bytes > 0)
+  void* ctx;
+};
+
+namespace setup {
+
+template <class V> static std::vector<V> section(const void* blob, const char* name) {
+  const cosim_blob_entry* e = cosim_blob_find(blob, name);
+  if (!e) throw std::runtime_error(std::string("model blob: section '") + name + "' missing");
+  const uint8_t* p = (const uint8_t*)blob + e->offset;
+  std::vector<V> out(e->count);
+  for (uint64_t i = 0; i < e->count; ++i) {
+    if (e->dtype == 0) out[i] = (V)((const int32_t*)p)[i];
+    else if (e->dtype == 1) out[i] = (V)((const float*)p)[i];
+    else out[i] = (V)((const double*)p)[i];
+  }
+  return out;
+}
+template <class V> static const V* push(const Uploader& u, const std::vector<V>& v) {
+  static const V zero[4] = {0, 0, 0, 0};
+  if (v.empty()) return (const V*)u.up(u.ctx, zero, sizeof(zero));      // keep pointers valid
+  return (const V*)u.up(u.ctx, v.data(), v.size() * sizeof(V));
+}
+
+static inline void build_model(const void* blob, size_t nbytes, uint64_t seed, uint32_t env_offset, const Uploader& u, ModelDev& m) {
+  if (nbytes < 8 || memcmp(blob, "CSB1", 4) != 0) throw std::runtime_error("model blob: bad magic");
+  memset(&m, 0, sizeof(m));
+  std::vector<int> dims = section<int>(blob, "dims");
+  std::vector<double> opts = section<double>(blob, "opts");
+  if ((int)dims.size() < CD__count || (int)opts.size() < CO__count) throw std::runtime_error("model blob: dims/opts too short");
+  for (int i = 0; i < 48; ++i) { m.dims[i] = i < (int)dims.size() ? dims[i] : 0; m.opts[i] = i < (int)opts.size() ? (float)opts[i] : 0.f; }
+  const int nb = m.dims[CD_nbody], nv = m.dims[CD_nv], njnt = m.dims[CD_njnt];
+  if (nv > 31) throw std::runtime_error("engine supports nv <= 31 (dof masks are 32-bit)");
+
+#define FSEC(field, name) m.field = push(u, section<float>(blob, name))
+#define ISEC(field, name) m.field = push(u, section<int>(blob, name))
+  std::vector<int> body_parent = section<int>(blob, "body_parent"), body_jntadr = section<int>(blob, "body_jntadr"),
+                   body_jntnum = section<int>(blob, "body_jntnum"), body_dofadr = section<int>(blob, "body_dofadr"),
+                   body_dofnum = section<int>(blob, "body_dofnum"), dof_parent = section<int>(blob, "dof_parent"),
+                   dof_body = section<int>(blob, "dof_body");
+  std::vector<int> body_jnt(nb, -1), subsize(nb, 1), dofmask(nb, 0), depth(nb, 0);
+  for (int b = 1; b < nb; ++b) {
+    if (body_jntnum[b] > 1) throw std::runtime_error("engine supports at most one joint per body");
+    if (body_jntnum[b] == 1) body_jnt[b] = body_jntadr[b];
+    if (body_parent[b] >= b) throw std::runtime_error("bodies must be in depth-first order");
+    depth[b] = depth[body_parent[b]] + 1;
+  }
+  for (int b = nb - 1; b >= 1; --b) subsize[body_parent[b]] += subsize[b];
+  // contiguous-subtree check (depth-first numbering): every body in (b, b+subsize) descends from b
+  for (int b = 1; b < nb; ++b) for (int c = b + 1; c < b + subsize[b]; ++c) {
+    int a = c; while (a > b) a = body_parent[a];
+    if (a != b) throw std::runtime_error("body numbering is not depth-first");
+  }
+  for (int b = 1; b < nb; ++b) {
+    int mask = dofmask[body_parent[b]];
+    for (int k = body_dofadr[b]; k < body_dofadr[b] + body_dofnum[b]; ++k) mask |= (1 << k);
+    dofmask[b] = mask;
+  }
+  int maxd = 0; for (int b = 0; b < nb; ++b) maxd = depth[b] > maxd ? depth[b] : maxd;
+  std::vector<int> level_start(maxd + 2, 0), level_body;
+  for (int l = 0; l <= maxd; ++l) { level_start[l] = (int)level_body.size(); for (int b = 0; b < nb; ++b) if (depth[b] == l) level_body.push_back(b); }
+  level_start[maxd + 1] = (int)level_body.size();
+  m.nlevels = maxd + 1;
+  std::vector<int> mi, mj;
+  for (int i = 0; i < nv; ++i) for (int j = i; j >= 0; j = dof_parent[j]) { mi.push_back(i); mj.push_back(j); }
+  m.nmpair = (int)mi.size();
+
+  m.body_parent = push(u, body_parent); m.body_jnt = push(u, body_jnt); m.body_dofadr = push(u, body_dofadr); m.body_dofnum = push(u, body_dofnum);
+  m.body_subsize = push(u, subsize); m.body_dofmask = push(u, dofmask);
+  m.level_start = push(u, level_start); m.level_body = push(u, level_body);
+  m.mpair_i = push(u, mi); m.mpair_j = push(u, mj);
+  FSEC(body_pos, "body_pos"); FSEC(body_quat, "body_quat"); FSEC(body_ipos, "body_ipos"); FSEC(body_inertia, "body_inertia"); FSEC(body_mass, "body_mass");
+  ISEC(jnt_type, "jnt_type"); ISEC(jnt_body, "jnt_body"); ISEC(jnt_qposadr, "jnt_qposadr"); ISEC(jnt_dofadr, "jnt_dofadr");
+  ISEC(jnt_limited, "jnt_limited"); ISEC(jnt_actfrclimited, "jnt_actfrclimited");
+  FSEC(jnt_pos, "jnt_pos"); FSEC(jnt_axis, "jnt_axis"); FSEC(jnt_range, "jnt_range"); FSEC(jnt_actfrcrange, "jnt_actfrcrange");
+  m.dof_body = push(u, dof_body); ISEC(dof_jnt, "dof_jnt"); m.dof_parent = push(u, dof_parent); ISEC(dof_fl_random, "dof_fl_random");
+  FSEC(dof_armature, "dof_armature"); FSEC(dof_damping, "dof_damping"); FSEC(dof_frictionloss, "dof_frictionloss");
+  FSEC(qpos0, "qpos0");
+  ISEC(act_dof, "act_dof"); ISEC(act_qadr, "act_qadr"); ISEC(act_mode, "act_mode"); ISEC(act_ctrllimited, "act_ctrllimited");
+  FSEC(act_gear, "act_gear"); FSEC(act_ctrlrange, "act_ctrlrange"); FSEC(act_kp, "act_kp"); FSEC(act_kd, "act_kd");
+  FSEC(act_scale, "act_scale"); FSEC(act_posfac, "act_posfac"); FSEC(act_gamma, "act_gamma"); FSEC(act_clip, "act_clip");
+  ISEC(geom_type, "geom_type"); ISEC(geom_body, "geom_body"); ISEC(geom_vadr, "geom_vadr"); ISEC(geom_vnum, "geom_vnum"); ISEC(geom_fr_random, "geom_fr_random");
+  FSEC(geom_size, "geom_size"); FSEC(geom_pos, "geom_pos"); FSEC(geom_quat, "geom_quat"); FSEC(geom_friction, "geom_friction");
+  FSEC(geom_center, "geom_center"); FSEC(geom_rbound, "geom_rbound");
+  FSEC(hull_verts, "hull_verts"); FSEC(hfield_data, "hfield_data");
+  { std::vector<float> gf = section<float>(blob, "ground_friction"); for (int i = 0; i < 4; ++i) m.ground_friction[i] = i < (int)gf.size() ? gf[i] : 0.f; }
+  ISEC(eq_body1, "eq_body1"); ISEC(eq_body2, "eq_body2");
+  FSEC(eq_anchor1, "eq_anchor1"); FSEC(eq_anchor2, "eq_anchor2"); FSEC(eq_solref, "eq_solref"); FSEC(eq_solimp, "eq_solimp");
+  { std::vector<float> p = section<float>(blob, "imu_pos"), q = section<float>(blob, "imu_quat");
+    for (int i = 0; i < 3; ++i) m.imu_pos[i] = p[i];
+    for (int i = 0; i < 4; ++i) m.imu_quat[i] = q[i]; }
+  ISEC(dofpos_qadr, "dofpos_qadr"); ISEC(dofvel_dadr, "dofvel_dadr"); ISEC(initnoise_qadr, "initnoise_qadr"); ISEC(term_body, "term_body");
+  ISEC(massnoise_body, "massnoise_body"); FSEC(dofpos_fac, "dofpos_fac"); FSEC(dofvel_fac, "dofvel_fac");
+  ISEC(sobs_kind, "sobs_kind"); ISEC(sobs_dim, "sobs_dim"); ISEC(sobs_interval, "sobs_interval"); ISEC(sobs_off, "sobs_off");
+  ISEC(nobs_kind, "nobs_kind"); ISEC(nobs_dim, "nobs_dim"); ISEC(nobs_interval, "nobs_interval"); ISEC(nobs_off, "nobs_off");
+  FSEC(sobs_scale, "sobs_scale"); FSEC(nobs_scale, "nobs_scale"); FSEC(noise, "noise");
+#undef FSEC
+#undef ISEC
+  // randomisation ranges: [slide, torsional, rolling, frictionloss, delay, load, kp scale, kd scale]
+  const int lo_idx[8] = {CO_slide_lo, CO_tors_lo, CO_roll_lo, CO_floss_lo, CO_delay_lo, CO_load_lo, CO_kp_lo, CO_kd_lo};
+  for (int i = 0; i < 8; ++i) { m.rnd_lo[i] = (float)opts[lo_idx[i]]; m.rnd_span[i] = (float)(opts[lo_idx[i] + 1] - opts[lo_idx[i]]); }
+  m.seed_lo = (uint32_t)seed; m.seed_hi = (uint32_t)(seed >> 32); m.env_offset = env_offset;
+
+  // ---- workspace layout (floats), every field padded to 4 floats
+  const int nq = m.dims[CD_nq], nu = m.dims[CD_nu], ng = m.dims[CD_ngeom], neq = m.dims[CD_neq], nc = m.dims[CD_ncon_max];
+  const int nh = m.dims[CD_hm_res_x] * m.dims[CD_hm_res_y];
+  const int nraw = m.dims[CD_n_dofpos] + m.dims[CD_n_dofvel] + 9 + nu + nh;
+  int size[W__COUNT];
+  for (int i = 0; i < W__COUNT; ++i) size[i] = 0;
+  size[W_QPOS] = nq; size[W_QVEL] = nv; size[W_CTRL] = nu; size[W_WARM] = nv; size[W_QACC] = nv;
+  size[W_XPOS] = 3 * nb; size[W_XQUAT] = 4 * nb; size[W_XMAT] = 9 * nb; size[W_XIPOS] = 3 * nb;
+  size[W_XANCHOR] = 3 * njnt; size[W_XAXIS] = 3 * njnt; size[W_GXPOS] = 3 * ng; size[W_GXMAT] = 9 * ng; size[W_SCOM] = 4;
+  size[W_CINERT] = 10 * nb; size[W_CRB] = 10 * nb; size[W_CDOF] = 6 * nv; size[W_CDOFDOT] = 6 * nv;
+  size[W_CVEL] = 6 * nb; size[W_CACC] = 6 * nb; size[W_CFRC] = 6 * nb; size[W_BUF] = 6 * nv;
+  size[W_M] = nv * nv; size[W_A] = nv * nv; size[W_INVD] = nv;
+  size[W_FSMOOTH] = size[W_ASMOOTH] = size[W_FCON] = size[W_GRAD] = size[W_SEARCH] = size[W_MV] = size[W_MA] = size[W_TMPV] = size[W_TMPW] = nv;
+  size[W_BMASS] = nb; size[W_INVWD] = nv; size[W_INVWB] = nb; size[W_FLOSS] = nv; size[W_GMU] = ng; size[W_SCAL] = 4;
+  size[W_FR_D] = nv; size[W_FR_AREF] = nv; size[W_LM_SIGN] = njnt; size[W_LM_D] = njnt; size[W_LM_AREF] = njnt;
+  size[W_CN_POS] = 3 * nc; size[W_CN_FRAME] = 9 * nc; size[W_CN_DIST] = nc; size[W_CN_MU] = nc; size[W_CN_BODY] = nc; size[W_CN_GEOM] = nc;
+  size[W_CN_CELL] = nc; size[W_CN_D] = nc; size[W_CN_AREF] = 4 * nc; size[W_CN_J] = 3 * nc * nv; size[W_CN_F] = 3 * nc; size[W_CN_X] = 4 * nc; size[W_CN_V] = 4 * nc;
+  size[W_EQ_J] = 3 * neq * nv; size[W_EQ_D] = size[W_EQ_AREF] = size[W_EQ_X] = size[W_EQ_V] = size[W_EQ_F] = 3 * neq;
+  size[W_SENS] = 12; size[W_RAW] = nraw; size[W_ACT] = nu; size[W_FILT] = nu; size[W_KP] = nu; size[W_KD] = nu;
+  int o = 0;
+  for (int i = 0; i < W__COUNT; ++i) { m.off[i] = o; o += (size[i] + 3) & ~3; }
+  m.ws_floats = o;
+}
+
+// per-env arrays: sizes in elements per env
+struct EnvDims { int nq, nv, nu, nb, ng, obsbuf, cache, nh, ncon, cd, sd; };
+static inline EnvDims env_dims(const ModelDev& m) {
+  EnvDims d;
+  d.nq = m.dims[CD_nq]; d.nv = m.dims[CD_nv]; d.nu = m.dims[CD_nu]; d.nb = m.dims[CD_nbody]; d.ng = m.dims[CD_ngeom];
+  d.obsbuf = m.dims[CD_stack_size] * m.dims[CD_stacked_dim]; if (d.obsbuf < 1) d.obsbuf = 1;
+  d.cache = m.dims[CD_cache_dim] < 1 ? 1 : m.dims[CD_cache_dim];
+  d.nh = m.dims[CD_hm_res_x] * m.dims[CD_hm_res_y]; d.ncon = m.dims[CD_ncon_max];
+  d.cd = m.dims[CD_command_dim]; d.sd = m.dims[CD_state_dim];
+  return d;
+}
+
+
+// ---- per-env arrays: allocation + the name table behind cosim_get / cosim_set
+struct Field { const char* name; void* ptr; int dim; int is_int; };
+typedef void* (*ZAlloc)(void* ctx, size_t bytes);   // zero-initialised device memory
+
+static inline void alloc_env(const ModelDev& m, int N, EnvArrays& E, ZAlloc za, void* ctx) {
+  const EnvDims d = env_dims(m);
+  memset(&E, 0, sizeof(E));
+  E.N = N;
+  const size_t n = (size_t)N;
+#define FA(field, dim) E.field = (float*)za(ctx, n * (size_t)(dim) * sizeof(float))
+  FA(qpos, d.nq); FA(qvel, d.nv); FA(warm, d.nv);
+  FA(body_mass, d.nb); FA(invw_dof, d.nv); FA(invw_body, d.nb); FA(floss, d.nv); FA(gmu, d.ng); FA(scal, 4); FA(kp, d.nu); FA(kd, d.nu);
+  FA(prev_action, d.nu); FA(delay_prev, d.nu); FA(obs_buffer, d.obsbuf); FA(freq_cache, d.cache); FA(torque, d.nu); FA(info, 4); FA(last_action, d.nu);
+  FA(stats, ST__COUNT);
+#undef FA
+  E.counters = (int*)za(ctx, n * 8 * sizeof(int));
+}
+static inline void alloc_debug(const ModelDev& m, int N, EnvArrays& E, ZAlloc za, void* ctx) {
+  const EnvDims d = env_dims(m);
+  const size_t n = (size_t)N;
+  if (E.dbg_contacts) return;
+  E.dbg_contacts = (float*)za(ctx, n * (size_t)d.ncon * 10 * sizeof(float));
+  E.dbg_heightmap = (float*)za(ctx, n * (size_t)(d.nh < 1 ? 1 : d.nh) * sizeof(float));
+  E.dbg_hmcell = (int*)za(ctx, n * (size_t)(d.nh < 1 ? 1 : d.nh) * sizeof(int));
+  E.dbg_cfrc = (float*)za(ctx, n * (size_t)d.nb * 6 * sizeof(float));
+  E.dbg_sens = (float*)za(ctx, n * 10 * sizeof(float));
+  E.dbg_qacc = (float*)za(ctx, n * (size_t)d.nv * sizeof(float));
+  E.dbg_iters = (int*)za(ctx, n * sizeof(int));
+}
+static inline std::vector<Field> env_fields(const ModelDev& m, const EnvArrays& E) {
+  const EnvDims d = env_dims(m);
+  std::vector<Field> f = {
+    {"qpos", E.qpos, d.nq, 0}, {"qvel", E.qvel, d.nv, 0}, {"qacc_warmstart", E.warm, d.nv, 0},
+    {"body_mass", E.body_mass, d.nb, 0}, {"invweight_dof", E.invw_dof, d.nv, 0}, {"invweight_body", E.invw_body, d.nb, 0},
+    {"frictionloss", E.floss, d.nv, 0}, {"geom_mu", E.gmu, d.ng, 0}, {"scal", E.scal, 4, 0}, {"kp", E.kp, d.nu, 0}, {"kd", E.kd, d.nu, 0},
+    {"torque", E.torque, d.nu, 0}, {"info", E.info, 4, 0}, {"last_action", E.last_action, d.nu, 0}, {"prev_action", E.prev_action, d.nu, 0},
+    {"obs_buffer", E.obs_buffer, d.obsbuf, 0}, {"counters", E.counters, 8, 1}, {"stats", E.stats, ST__COUNT, 0},
+    {"contacts", E.dbg_contacts, d.ncon * 10, 0}, {"heightmap", E.dbg_heightmap, d.nh < 1 ? 1 : d.nh, 0},
+    {"hm_cell", E.dbg_hmcell, d.nh < 1 ? 1 : d.nh, 1}, {"cfrc_ext", E.dbg_cfrc, d.nb * 6, 0}, {"sens", E.dbg_sens, 10, 0},
+    {"qacc", E.dbg_qacc, d.nv, 0}, {"iters", E.dbg_iters, 1, 1},
+  };
+  return f;
+}
+static inline int dim_by_name(const ModelDev& m, const std::string& n) {
+  static const char* names[] = {"nq", "nv", "nu", "nbody", "njnt", "ngeom", "nhullvert", "neq", "ground_type", "hf_nrow", "hf_ncol",
+    "frame_skip", "iterations", "ls_iterations", "ccd_iterations", "ncon_max", "hm_res_x", "hm_res_y", "state_dim", "stack_size",
+    "stacked_dim", "nonstacked_dim", "command_dim", "n_term_body", "n_dofpos", "n_dofvel", "n_initnoise", "max_episode_steps",
+    "lin_vel_f32", "n_sobs", "n_nobs", "cache_dim", "n_state_pos", "n_state_vel", "position_command", "nefc_max", "imu_body",
+    "n_massnoise", "base_body", "zero_noise", "auto_reset", "nfl", "nlimit_max"};
+  if (n == "action_dim") return m.dims[CD_nu];
+  for (int i = 0; i < CD__count; ++i) if (n == names[i]) return m.dims[i];
+  return -1;
+}
+
+}  // namespace setup
