@@ -1,0 +1,265 @@
+// engine.cu -- kernels + C ABI of libcosim_b200.so (sm_100a).  See include/cosim_b200.h for the
+// reference interface each entry point replaces.  One warp owns one environment; its working set
+// lives in that warp's slice of dynamic shared memory (engine_core.h).  No CPU path.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+#include "engine_env.h"
+#include "engine_setup.h"
+#include "../../include/cosim_b200.h"
+
+// ------------------------------------------------------------------------------------------ kernels
+extern __shared__ __align__(16) float g_smem[];
+
+#define ENV_PROLOGUE()                                              \
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;       \
+  const int env = blockIdx.x * (blockDim.x >> 5) + warp;            \
+  if (env >= E.N) return;                                           \
+  float* ws = g_smem + (size_t)warp * m.ws_floats;
+
+__global__ void __launch_bounds__(256) k_init(const __grid_constant__ ModelDev m, const EnvArrays E) {
+  ENV_PROLOGUE();
+  init_env(m, E, env, ws, lane);
+}
+__global__ void __launch_bounds__(256) k_reset(const __grid_constant__ ModelDev m, const EnvArrays E, const StepArgs a) {
+  ENV_PROLOGUE();
+  if (a.mask && !a.mask[env]) return;
+  const int cd = MD(command_dim);
+  reset_env(m, E, env, ws, a.command ? a.command + (size_t)env * cd : nullptr, a.state_out + (size_t)env * MD(state_dim), lane);
+}
+__global__ void __launch_bounds__(256) k_step(const __grid_constant__ ModelDev m, const EnvArrays E, const StepArgs a) {
+  ENV_PROLOGUE();
+  step_env(m, E, env, ws, a, lane);
+}
+__global__ void k_push(const __grid_constant__ ModelDev m, const EnvArrays E, const uint8_t* mask, const float* vel) {
+  const int env = blockIdx.x * blockDim.x + threadIdx.x;
+  if (env >= E.N) return;
+  if (mask && !mask[env]) return;
+  push_env(m, E, env, vel + 3 * (size_t)env, 0);
+}
+// counter-based RNG probe: out[env][i] = i-th 32-bit draw of (env, stream, step)
+__global__ void k_rng_probe(const __grid_constant__ ModelDev m, int N, uint32_t stream, uint32_t step, int nidx, uint32_t* out) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= N * nidx) return;
+  const int env = t / nidx, i = t - env * nidx;
+  out[t] = philox_draw(m, (uint32_t)env, stream, step, (uint32_t)i);
+}
+// reporter statistics: out[k] = sum over envs (max for ST_MAX_TORQUE), fp64 accumulation
+__global__ void k_stats(const float* stats, int N, double* out) {
+  __shared__ double sh[8][ST__COUNT];
+  const int k = threadIdx.x & (ST__COUNT - 1), part = threadIdx.x / ST__COUNT, nparts = blockDim.x / ST__COUNT;
+  double acc = 0.0;
+  for (int e = blockIdx.x * nparts + part; e < N; e += gridDim.x * nparts) {
+    const double v = (double)stats[(size_t)e * ST__COUNT + k];
+    if (k == ST_MAX_TORQUE) acc = v > acc ? v : acc; else acc += v;
+  }
+  sh[part][k] = acc;
+  __syncthreads();
+  if (part == 0) {
+    for (int p = 1; p < nparts; ++p) { if (k == ST_MAX_TORQUE) acc = sh[p][k] > acc ? sh[p][k] : acc; else acc += sh[p][k]; }
+    if (k == ST_MAX_TORQUE) {
+      unsigned long long* addr = (unsigned long long*)(out + k); unsigned long long old = *addr, assumed;
+      do { assumed = old; if (__longlong_as_double((long long)assumed) >= acc) break; old = atomicCAS(addr, assumed, (unsigned long long)__double_as_longlong(acc)); } while (assumed != old);
+    } else atomicAdd(out + k, acc);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ handle
+struct cosim_handle {
+  ModelDev m; EnvArrays E; EnvArrays Edbg;   // Edbg keeps the debug pointers while dumps are switched off
+  int N = 0, device = 0, wpb = 1, launches = 0, debug = 0;
+  size_t smem = 0;
+  std::string err;
+  std::vector<void*> allocs;
+  cudaStream_t stream = nullptr;            // used by cosim_step_host
+  float *d_action = nullptr, *d_command = nullptr, *d_state = nullptr; uint8_t *d_term = nullptr, *d_trunc = nullptr;
+};
+
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { h->err = std::string(#call) + ": " + cudaGetErrorString(e_); return COSIM_ERR_CUDA; } } while (0)
+
+static void* dev_upload(void* ctx, const void* src, size_t bytes) {
+  cosim_handle* h = (cosim_handle*)ctx; void* p = nullptr;
+  if (cudaMalloc(&p, bytes ? bytes : 4) != cudaSuccess) throw std::runtime_error("cudaMalloc failed (model tables)");
+  if (cudaMemcpy(p, src, bytes, cudaMemcpyHostToDevice) != cudaSuccess) throw std::runtime_error("cudaMemcpy failed (model tables)");
+  h->allocs.push_back(p); return p;
+}
+static void* dev_zalloc(void* ctx, size_t bytes) {
+  cosim_handle* h = (cosim_handle*)ctx; void* p = nullptr;
+  if (cudaMalloc(&p, bytes ? bytes : 4) != cudaSuccess) throw std::runtime_error("cudaMalloc failed (env arrays)");
+  cudaMemset(p, 0, bytes ? bytes : 4);
+  h->allocs.push_back(p); return p;
+}
+static int grid_for(const cosim_handle* h) { return (h->N + h->wpb - 1) / h->wpb; }
+
+extern "C" {
+
+int cosim_create(const void* blob, size_t nbytes, int num_envs, int device, uint64_t seed, uint32_t env_offset, cosim_handle** out) {
+  if (!blob || !out || num_envs <= 0) return COSIM_ERR_ARG;
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { fprintf(stderr, "cosim_b200: no CUDA device -- this library has no CPU path\n"); return COSIM_ERR_CUDA; }
+  cosim_handle* h = new cosim_handle;
+  h->N = num_envs; h->device = device;
+  if (cudaSetDevice(device) != cudaSuccess) { delete h; return COSIM_ERR_CUDA; }
+  try {
+    Uploader u = {dev_upload, h};
+    setup::build_model(blob, nbytes, seed, env_offset, u, h->m);
+    setup::alloc_env(h->m, num_envs, h->E, dev_zalloc, h);
+  } catch (std::exception& e) {
+    fprintf(stderr, "cosim_create: %s\n", e.what());
+    for (void* p : h->allocs) cudaFree(p);
+    delete h; return COSIM_ERR_MODEL;
+  }
+  // launch geometry: as many env-warps per block as fit comfortably; blocks co-reside up to the 227 KB/SM limit
+  const size_t per = (size_t)h->m.ws_floats * sizeof(float);
+  int wpb = 4;
+  while (wpb > 1 && per * wpb > 100 * 1024) wpb >>= 1;
+  if (per * wpb > 227 * 1024) { fprintf(stderr, "cosim_create: workspace %zu B/env exceeds shared memory\n", per); for (void* p : h->allocs) cudaFree(p); delete h; return COSIM_ERR_MODEL; }
+  h->wpb = wpb; h->smem = per * wpb;
+  cudaError_t e1 = cudaFuncSetAttribute(k_init, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem);
+  cudaError_t e2 = cudaFuncSetAttribute(k_reset, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem);
+  cudaError_t e3 = cudaFuncSetAttribute(k_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem);
+  if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) { fprintf(stderr, "cosim_create: cudaFuncSetAttribute failed: %s\n", cudaGetErrorString(e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3))); for (void* p : h->allocs) cudaFree(p); delete h; return COSIM_ERR_CUDA; }
+  cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+  k_init<<<grid_for(h), 32 * h->wpb, h->smem, h->stream>>>(h->m, h->E);
+  h->launches++;
+  cudaError_t e = cudaStreamSynchronize(h->stream);
+  if (e == cudaSuccess) e = cudaGetLastError();
+  if (e != cudaSuccess) { fprintf(stderr, "cosim_create: init kernel failed: %s\n", cudaGetErrorString(e)); for (void* p : h->allocs) cudaFree(p); delete h; return COSIM_ERR_CUDA; }
+  *out = h;
+  return COSIM_OK;
+}
+
+void cosim_destroy(cosim_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  for (void* p : h->allocs) cudaFree(p);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+const char* cosim_last_error(const cosim_handle* h) { return h ? h->err.c_str() : "null handle"; }
+
+int cosim_reset(cosim_handle* h, const uint8_t* mask, const float* command, float* state_out, void* stream) {
+  if (!h || !state_out) return COSIM_ERR_ARG;
+  StepArgs a = {nullptr, command, nullptr, state_out, nullptr, nullptr, mask};
+  k_reset<<<grid_for(h), 32 * h->wpb, h->smem, (cudaStream_t)stream>>>(h->m, h->E, a);
+  h->launches++;
+  CK(cudaGetLastError());
+  return COSIM_OK;
+}
+
+int cosim_step(cosim_handle* h, const float* action, const float* command, const float* user_command, float* state_out,
+               uint8_t* terminated, uint8_t* truncated, void* stream) {
+  if (!h || !action || !state_out || !terminated || !truncated) return COSIM_ERR_ARG;
+  StepArgs a = {action, command, user_command, state_out, terminated, truncated, nullptr};
+  k_step<<<grid_for(h), 32 * h->wpb, h->smem, (cudaStream_t)stream>>>(h->m, h->E, a);
+  h->launches++;
+  CK(cudaGetLastError());
+  return COSIM_OK;
+}
+
+int cosim_step_host(cosim_handle* h, const float* action_host, const float* command_host, float* state_out_host,
+                    uint8_t* terminated_host, uint8_t* truncated_host) {
+  if (!h || !action_host || !state_out_host || !terminated_host || !truncated_host) return COSIM_ERR_ARG;
+  const setup::EnvDims d = setup::env_dims(h->m);
+  const size_t n = (size_t)h->N;
+  if (!h->d_action) {
+    try {
+      h->d_action = (float*)dev_zalloc(h, n * d.nu * 4); h->d_command = (float*)dev_zalloc(h, n * (d.cd > 0 ? d.cd : 1) * 4);
+      h->d_state = (float*)dev_zalloc(h, n * d.sd * 4); h->d_term = (uint8_t*)dev_zalloc(h, n); h->d_trunc = (uint8_t*)dev_zalloc(h, n);
+    } catch (std::exception& e) { h->err = e.what(); return COSIM_ERR_CUDA; }
+  }
+  CK(cudaMemcpyAsync(h->d_action, action_host, n * d.nu * 4, cudaMemcpyHostToDevice, h->stream));
+  if (command_host && d.cd > 0) CK(cudaMemcpyAsync(h->d_command, command_host, n * d.cd * 4, cudaMemcpyHostToDevice, h->stream));
+  int rc = cosim_step(h, h->d_action, (command_host && d.cd > 0) ? h->d_command : nullptr, nullptr, h->d_state, h->d_term, h->d_trunc, h->stream);
+  if (rc != COSIM_OK) return rc;
+  CK(cudaMemcpyAsync(state_out_host, h->d_state, n * d.sd * 4, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(terminated_host, h->d_term, n, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(truncated_host, h->d_trunc, n, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return COSIM_OK;
+}
+
+int cosim_push(cosim_handle* h, const uint8_t* mask, const float* vel_world, void* stream) {
+  if (!h || !vel_world) return COSIM_ERR_ARG;
+  k_push<<<(h->N + 127) / 128, 128, 0, (cudaStream_t)stream>>>(h->m, h->E, mask, vel_world);
+  h->launches++;
+  CK(cudaGetLastError());
+  return COSIM_OK;
+}
+
+int cosim_field_dim(const cosim_handle* h, const char* field) {
+  if (!h || !field) return COSIM_ERR_ARG;
+  for (auto& f : setup::env_fields(h->m, h->E)) if (!strcmp(f.name, field)) return f.ptr ? f.dim : COSIM_ERR_FIELD;
+  return COSIM_ERR_FIELD;
+}
+int cosim_field_is_int(const cosim_handle* h, const char* field) {
+  if (!h || !field) return COSIM_ERR_ARG;
+  for (auto& f : setup::env_fields(h->m, h->E)) if (!strcmp(f.name, field)) return f.is_int;
+  return COSIM_ERR_FIELD;
+}
+int cosim_get(cosim_handle* h, const char* field, void* dst, void* stream) {
+  if (!h || !field || !dst) return COSIM_ERR_ARG;
+  for (auto& f : setup::env_fields(h->m, h->E)) if (!strcmp(f.name, field)) {
+    if (!f.ptr) { h->err = std::string("field '") + field + "' needs cosim_set_debug(h, 1)"; return COSIM_ERR_FIELD; }
+    CK(cudaMemcpyAsync(dst, f.ptr, (size_t)h->N * f.dim * 4, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return COSIM_OK;
+  }
+  h->err = std::string("unknown field '") + field + "'";
+  return COSIM_ERR_FIELD;
+}
+int cosim_set(cosim_handle* h, const char* field, const void* src, void* stream) {
+  if (!h || !field || !src) return COSIM_ERR_ARG;
+  const std::string n(field);
+  if (n != "qpos" && n != "qvel" && n != "qacc_warmstart") { h->err = "cosim_set: only qpos, qvel, qacc_warmstart are writable"; return COSIM_ERR_FIELD; }
+  for (auto& f : setup::env_fields(h->m, h->E)) if (n == f.name) {
+    CK(cudaMemcpyAsync(f.ptr, src, (size_t)h->N * f.dim * 4, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return COSIM_OK;
+  }
+  return COSIM_ERR_FIELD;
+}
+int cosim_set_debug(cosim_handle* h, int enable) {
+  if (!h) return COSIM_ERR_ARG;
+  if (enable) {
+    if (h->debug == 2) h->E = h->Edbg;      // re-enable: restore the saved pointers
+    else if (!h->E.dbg_contacts) { try { setup::alloc_debug(h->m, h->N, h->E, dev_zalloc, h); } catch (std::exception& e) { h->err = e.what(); return COSIM_ERR_CUDA; } }
+    h->debug = 1;
+  } else if (h->debug == 1) {
+    h->Edbg = h->E;
+    h->E.dbg_contacts = h->E.dbg_heightmap = h->E.dbg_cfrc = h->E.dbg_sens = h->E.dbg_qacc = nullptr; h->E.dbg_hmcell = h->E.dbg_iters = nullptr;
+    h->debug = 2;
+  }
+  return COSIM_OK;
+}
+
+int cosim_stats_reduce(cosim_handle* h, double* out, void* stream) {
+  if (!h || !out) return COSIM_ERR_ARG;
+  CK(cudaMemsetAsync(out, 0, COSIM_NSTAT * sizeof(double), (cudaStream_t)stream));
+  int blocks = (h->N + 1023) / 1024; if (blocks > 148) blocks = 148; if (blocks < 1) blocks = 1;
+  k_stats<<<blocks, 8 * ST__COUNT, 0, (cudaStream_t)stream>>>(h->E.stats, h->N, out);
+  h->launches++;
+  CK(cudaGetLastError());
+  return COSIM_OK;
+}
+int cosim_stats_clear(cosim_handle* h, void* stream) {
+  if (!h) return COSIM_ERR_ARG;
+  CK(cudaMemsetAsync(h->E.stats, 0, (size_t)h->N * ST__COUNT * sizeof(float), (cudaStream_t)stream));
+  return COSIM_OK;
+}
+int cosim_rng_probe(cosim_handle* h, uint32_t rng_stream, uint32_t step, int nidx, uint32_t* out, void* stream) {
+  if (!h || !out || nidx <= 0) return COSIM_ERR_ARG;
+  const int n = h->N * nidx;
+  k_rng_probe<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(h->m, h->N, rng_stream, step, nidx, out);
+  h->launches++;
+  CK(cudaGetLastError());
+  return COSIM_OK;
+}
+
+int cosim_num_envs(const cosim_handle* h) { return h ? h->N : COSIM_ERR_ARG; }
+int cosim_dim(const cosim_handle* h, const char* name) { return (h && name) ? setup::dim_by_name(h->m, name) : COSIM_ERR_ARG; }
+int cosim_launch_count(const cosim_handle* h) { return h ? h->launches : COSIM_ERR_ARG; }
+int cosim_smem_bytes_per_env(const cosim_handle* h) { return h ? h->m.ws_floats * 4 : COSIM_ERR_ARG; }
+int cosim_warps_per_block(const cosim_handle* h) { return h ? h->wpb : COSIM_ERR_ARG; }
+
+}  // extern "C"

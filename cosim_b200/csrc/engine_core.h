@@ -30,6 +30,7 @@
 
 #ifdef COSIM_HOST_EMU
 #define DEV static inline
+#define DEV_NOINLINE static
 #define LANES 1
 #define SYNC() ((void)0)
 #define LDG(p) (*(p))
@@ -40,6 +41,7 @@ static inline void wargmax(float& v, int& i) {}
 static inline float fast_ndtri(float p);
 #else
 #define DEV __device__ __forceinline__
+#define DEV_NOINLINE __device__ __noinline__
 #define LANES 32
 #define SYNC() __syncwarp()
 #define LDG(p) __ldg(p)
@@ -1208,7 +1210,7 @@ DEV void sensors(const ModelDev& m, float* ws, int lane) {
 
 // ------------------------------------------------------------------------------------------ forward + one sub-step
 // returns solver iterations; ncon_out / dropped_out = contacts of this forward pass
-DEV int forward(const ModelDev& m, float* ws, int& ncon_out, int& dropped_out, int lane) {
+DEV_NOINLINE int forward(const ModelDev& m, float* ws, int& ncon_out, int& dropped_out, int lane) {
   const int nv = MD(nv), nu = MD(nu), njnt = MD(njnt);
   kinematics(m, ws, lane);
   com_pos(m, ws, lane);

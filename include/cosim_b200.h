@@ -62,6 +62,11 @@ int cosim_field_dim(const cosim_handle* h, const char* field);
 int cosim_get(cosim_handle* h, const char* field, void* dst, void* stream);
 int cosim_set(cosim_handle* h, const char* field, const void* src, void* stream);   /* qpos qvel qacc_warmstart */
 int cosim_set_debug(cosim_handle* h, int enable);   /* allocate + fill the debug dumps */
+int cosim_field_is_int(const cosim_handle* h, const char* field);   /* 1 = int32 rows, 0 = float32 rows */
+/* Counter-based RNG probe (replaces the reference's unseeded random / numpy / scipy draws,
+ * manager/control_manager.py:18, manager/xml_manager.py:50, utils/noise_generator_utils.py:13,25-27):
+ * out[N][nidx] (uint32, device) = Philox4x32-10 draws of (global env id, rng_stream, step, idx). */
+int cosim_rng_probe(cosim_handle* h, uint32_t rng_stream, uint32_t step, int nidx, uint32_t* out, void* stream);
 
 /* Reporter statistics (core/reporter.py:210-218 accumulates info; SURVEY.md C-17 defines the
  * reductions): sums the per-env accumulators into out[COSIM_NSTAT] (device, float64). */
@@ -74,6 +79,7 @@ int cosim_num_envs(const cosim_handle* h);
 int cosim_dim(const cosim_handle* h, const char* name);      /* "state_dim", "action_dim", "command_dim", "nq", "nv", ... */
 int cosim_launch_count(const cosim_handle* h);               /* kernels launched so far */
 int cosim_smem_bytes_per_env(const cosim_handle* h);
+int cosim_warps_per_block(const cosim_handle* h);
 
 /* ---- policy MLP (core/policy.py:11-21 MLPPolicy.get_action: clip(MLP(state), -1, 1)) ---- */
 typedef struct cosim_policy cosim_policy;
