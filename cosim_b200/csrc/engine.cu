@@ -32,6 +32,10 @@ __global__ void __launch_bounds__(256) k_step(const __grid_constant__ ModelDev m
   ENV_PROLOGUE();
   step_env(m, E, env, ws, a, lane);
 }
+__global__ void __launch_bounds__(256) k_substep(const __grid_constant__ ModelDev m, const EnvArrays E) {
+  ENV_PROLOGUE();
+  substep_env(m, E, env, ws, lane);
+}
 __global__ void k_push(const __grid_constant__ ModelDev m, const EnvArrays E, const uint8_t* mask, const float* vel) {
   const int env = blockIdx.x * blockDim.x + threadIdx.x;
   if (env >= E.N) return;
@@ -106,6 +110,7 @@ int cosim_create(const void* blob, size_t nbytes, int num_envs, int device, uint
     Uploader u = {dev_upload, h};
     setup::build_model(blob, nbytes, seed, env_offset, u, h->m);
     setup::alloc_env(h->m, num_envs, h->E, dev_zalloc, h);
+    h->m.phase = (unsigned long long*)dev_zalloc(h, PH__COUNT * sizeof(unsigned long long));
   } catch (std::exception& e) {
     fprintf(stderr, "cosim_create: %s\n", e.what());
     for (void* p : h->allocs) cudaFree(p);
@@ -120,6 +125,7 @@ int cosim_create(const void* blob, size_t nbytes, int num_envs, int device, uint
   cudaError_t e1 = cudaFuncSetAttribute(k_init, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem);
   cudaError_t e2 = cudaFuncSetAttribute(k_reset, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem);
   cudaError_t e3 = cudaFuncSetAttribute(k_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem);
+  if (e3 == cudaSuccess) e3 = cudaFuncSetAttribute(k_substep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem);
   if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) { fprintf(stderr, "cosim_create: cudaFuncSetAttribute failed: %s\n", cudaGetErrorString(e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3))); for (void* p : h->allocs) cudaFree(p); delete h; return COSIM_ERR_CUDA; }
   cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
   k_init<<<grid_for(h), 32 * h->wpb, h->smem, h->stream>>>(h->m, h->E);
@@ -181,6 +187,14 @@ int cosim_step_host(cosim_handle* h, const float* action_host, const float* comm
   return COSIM_OK;
 }
 
+int cosim_substep(cosim_handle* h, void* stream) {
+  if (!h) return COSIM_ERR_ARG;
+  k_substep<<<grid_for(h), 32 * h->wpb, h->smem, (cudaStream_t)stream>>>(h->m, h->E);
+  h->launches++;
+  CK(cudaGetLastError());
+  return COSIM_OK;
+}
+
 int cosim_push(cosim_handle* h, const uint8_t* mask, const float* vel_world, void* stream) {
   if (!h || !vel_world) return COSIM_ERR_ARG;
   k_push<<<(h->N + 127) / 128, 128, 0, (cudaStream_t)stream>>>(h->m, h->E, mask, vel_world);
@@ -212,7 +226,7 @@ int cosim_get(cosim_handle* h, const char* field, void* dst, void* stream) {
 int cosim_set(cosim_handle* h, const char* field, const void* src, void* stream) {
   if (!h || !field || !src) return COSIM_ERR_ARG;
   const std::string n(field);
-  if (n != "qpos" && n != "qvel" && n != "qacc_warmstart") { h->err = "cosim_set: only qpos, qvel, qacc_warmstart are writable"; return COSIM_ERR_FIELD; }
+  if (n != "qpos" && n != "qvel" && n != "qacc_warmstart" && n != "torque") { h->err = "cosim_set: only qpos, qvel, qacc_warmstart, torque are writable"; return COSIM_ERR_FIELD; }
   for (auto& f : setup::env_fields(h->m, h->E)) if (n == f.name) {
     CK(cudaMemcpyAsync(f.ptr, src, (size_t)h->N * f.dim * 4, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
     return COSIM_OK;
@@ -256,6 +270,20 @@ int cosim_rng_probe(cosim_handle* h, uint32_t rng_stream, uint32_t step, int nid
   return COSIM_OK;
 }
 
+/* profiling builds (-DCOSIM_PHASE_TIMING): cycle counters per phase, summed over env-warps; zeros otherwise */
+int cosim_phase_cycles(cosim_handle* h, unsigned long long* out_host, int reset) {
+  if (!h || !out_host) return COSIM_ERR_ARG;
+  for (int i = 0; i < PH__COUNT; ++i) out_host[i] = 0;
+#ifdef COSIM_PHASE_TIMING
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpy(out_host, h->m.phase, PH__COUNT * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  unsigned long long v = 0;
+  CK(cudaMemcpyFromSymbol(&v, g_support_calls, sizeof(v))); out_host[PH_SUPPORT_CALLS] = v;
+  CK(cudaMemcpyFromSymbol(&v, g_mpr_calls, sizeof(v))); out_host[PH_MPR_CALLS] = v;
+  if (reset) { CK(cudaMemset(h->m.phase, 0, PH__COUNT * sizeof(unsigned long long))); v = 0; CK(cudaMemcpyToSymbol(g_support_calls, &v, sizeof(v))); CK(cudaMemcpyToSymbol(g_mpr_calls, &v, sizeof(v))); }
+#endif
+  return COSIM_OK;
+}
 int cosim_num_envs(const cosim_handle* h) { return h ? h->N : COSIM_ERR_ARG; }
 int cosim_dim(const cosim_handle* h, const char* name) { return (h && name) ? setup::dim_by_name(h->m, name) : COSIM_ERR_ARG; }
 int cosim_launch_count(const cosim_handle* h) { return h ? h->launches : COSIM_ERR_ARG; }

@@ -67,6 +67,18 @@ DEV void wargmax(float& v, int& i) {
 }
 #endif
 
+// optional per-phase cycle counters (profiling builds only: -DCOSIM_PHASE_TIMING)
+enum { PH_KIN = 0, PH_COLLIDE, PH_CONSTRAINT, PH_SMOOTH, PH_NEWTON, PH_INTEGRATE, PH_OBS, PH_IO, PH_NEWTON_ITERS, PH_LS_EVALS, PH_SUPPORT_CALLS, PH_MPR_CALLS, PH__COUNT = 16 };
+#if defined(COSIM_PHASE_TIMING) && !defined(COSIM_HOST_EMU)
+#define PH_DECL long long ph_t0_ = clock64()
+#define PH_MARK(k) do { long long t_ = clock64(); if (lane == 0) atomicAdd((unsigned long long*)m.phase + (k), (unsigned long long)(t_ - ph_t0_)); ph_t0_ = clock64(); } while (0)
+#define PH_COUNT(k, n) do { if (lane == 0) atomicAdd((unsigned long long*)m.phase + (k), (unsigned long long)(n)); } while (0)
+#else
+#define PH_DECL ((void)0)
+#define PH_MARK(k) ((void)0)
+#define PH_COUNT(k, n) ((void)0)
+#endif
+
 DEV int imax(int a, int b) { return a > b ? a : b; }
 DEV int imin(int a, int b) { return a < b ? a : b; }
 #define FOR_LANE(i, n) for (int i = lane; i < (n); i += LANES)
@@ -111,6 +123,7 @@ struct ModelDev {
   // workspace layout (float offsets into the per-warp shared slice)
   int off[80]; int ws_floats;
   uint32_t seed_lo, seed_hi, env_offset;
+  unsigned long long* phase;      // [PH__COUNT] cycle counters, profiling builds only (else NULL)
 };
 #define MD(name) (m.dims[CD_##name])
 #define MO(name) (m.opts[CO_##name])
@@ -522,6 +535,9 @@ DEV void support(const GeomW& G, const float* dir, float* out, int lane) {
 }
 
 struct Sup { float v[3], v1[3], v2[3]; };
+#if defined(COSIM_PHASE_TIMING) && !defined(COSIM_HOST_EMU)
+__device__ unsigned long long g_support_calls = 0, g_mpr_calls = 0;
+#endif
 // libccd's degenerate-case guards use CCD_EPS = DBL_EPSILON (MuJoCo builds it in double).  They are
 // ABSOLUTE thresholds, so the fp32 engine keeps the double value: with FLT_EPSILON the guards fire on
 // ordinary millimetre-scale portal triangles and the contact normal degenerates.
@@ -535,6 +551,9 @@ DEV bool f_eq(float a, float b) {
 }
 DEV bool v3eq0(const float* a) { return f_eq(a[0], 0.f) && f_eq(a[1], 0.f) && f_eq(a[2], 0.f); }
 DEV void mink_support(const float (*P)[3], const GeomW& G, const float* dir, Sup& s, int lane) {
+#if defined(COSIM_PHASE_TIMING) && !defined(COSIM_HOST_EMU)
+  if (lane == 0) atomicAdd(&g_support_calls, 1ull);
+#endif
   int best = 0; float bv = v3dot(P[0], dir);
 #pragma unroll
   for (int i = 1; i < 6; ++i) { float v = v3dot(P[i], dir); if (v > bv) { bv = v; best = i; } }
@@ -602,6 +621,9 @@ DEV void find_pos(const Sup* p, float* pos) {
 // MPR penetration query (libccd ccdMPRPenetration as driven by mjc_ConvexHField); 0 = hit
 DEV int mpr_penetration(const ModelDev& m, const float (*P)[3], const GeomW& G, float* depth, float* dir_out, float* pos, int lane) {
   const float tol = MO(ccd_tolerance); const int maxit = MD(ccd_iterations);
+#if defined(COSIM_PHASE_TIMING) && !defined(COSIM_HOST_EMU)
+  if (lane == 0) atomicAdd(&g_mpr_calls, 1ull);
+#endif
   Sup p[4];
   float c1[3] = {0.f, 0.f, 0.f};
 #pragma unroll
@@ -1051,6 +1073,7 @@ DEV float total_cost(const ModelDev& m, float* ws, int ncon, const float* q, flo
 struct LSPoint { float alpha, cost, d0, d1; };
 DEV LSPoint ls_eval(const ModelDev& m, const float* ws, int ncon, float a, float q0, float q1, float q2, int lane) {
   RowSum s = eval_rows(m, ws, ncon, a, true, lane);
+  PH_COUNT(PH_LS_EVALS, 1);
   LSPoint p; p.alpha = a;
   p.cost = a * a * q2 + a * q1 + q0 + wsum(s.cost);
   p.d0 = 2.f * a * q2 + q1 + wsum(s.d0);
@@ -1212,6 +1235,7 @@ DEV void sensors(const ModelDev& m, float* ws, int lane) {
 // returns solver iterations; ncon_out / dropped_out = contacts of this forward pass
 DEV_NOINLINE int forward(const ModelDev& m, float* ws, int& ncon_out, int& dropped_out, int lane) {
   const int nv = MD(nv), nu = MD(nu), njnt = MD(njnt);
+  PH_DECL;
   kinematics(m, ws, lane);
   com_pos(m, ws, lane);
   crb(m, ws, lane);
@@ -1219,12 +1243,15 @@ DEV_NOINLINE int forward(const ModelDev& m, float* ws, int& ncon_out, int& dropp
   FOR_LANE(i, nv * nv) A[i] = M[i];
   SYNC();
   chol_factor(A, WS(W_INVD), nv, lane);
+  PH_MARK(PH_KIN);
   int ncon = 0, dropped = 0;
   for (int g = 0; g < MD(ngeom); ++g) { if (MD(ground_type) == 1) collide_hfield(m, ws, g, ncon, dropped, lane); else collide_plane(m, ws, g, ncon, dropped, lane); }
   SYNC();
+  PH_MARK(PH_COLLIDE);
   com_vel(m, ws, lane);
   make_constraint(m, ws, ncon, lane);
   sensors(m, ws, lane);
+  PH_MARK(PH_CONSTRAINT);
   // smooth forces: passive damping - bias + actuation (ctrl clamp, gear, actuatorfrcrange clamp)
   rne_bias(m, ws, WS(W_TMPV), lane);
   float* fs = WS(W_FSMOOTH);
@@ -1245,7 +1272,10 @@ DEV_NOINLINE int forward(const ModelDev& m, float* ws, int& ncon_out, int& dropp
   // any constraint row?
   int rows = (ncon > 0) || (MD(neq) > 0);
   { int r = 0; FOR_LANE(k, nv) r |= (WS(W_FR_D)[k] > 0.f); FOR_LANE(j, njnt) r |= (WS(W_LM_SIGN)[j] != 0.f); rows |= wor(r); }
+  PH_MARK(PH_SMOOTH);
   int iters = newton_solve(m, ws, ncon, rows, lane);
+  PH_MARK(PH_NEWTON);
+  PH_COUNT(PH_NEWTON_ITERS, iters);
   ncon_out = ncon; dropped_out = dropped;
   return iters;
 }
@@ -1269,6 +1299,7 @@ DEV int substep(const ModelDev& m, float* ws, int& ncon, int& dropped, int& nan_
   { int bad = 0; FOR_LANE(i, nv) { float x = WS(W_QACC)[i]; bad |= !(x == x) || fabsf(x) > 1e10f; }
     if (wor(bad)) { reset_data(m, ws, lane); ++nan_count; iters = forward(m, ws, ncon, dropped, lane); } }
   // implicitfast: (M + dt diag(damping)) a = qfrc_smooth + qfrc_constraint
+  PH_DECL;
   const float dt = MO(timestep);
   float* A = WS(W_A); const float* M = WS(W_M);
   FOR_LANE(i, nv * nv) { const int r = i / nv, c = i - r * nv; A[i] = M[i] + (r == c ? dt * LDG(m.dof_damping + r) : 0.f); }
@@ -1295,6 +1326,7 @@ DEV int substep(const ModelDev& m, float* ws, int& ncon, int& dropped, int& nan_
     } else qpos[qa] += dt * qvel[da];
   }
   SYNC();
+  PH_MARK(PH_INTEGRATE);
   return iters;
 }
 

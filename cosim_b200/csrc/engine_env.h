@@ -300,6 +300,7 @@ DEV void step_env(const ModelDev& m, const EnvArrays& E, int env, float* ws, con
   int ncon = 0, dropped = 0, nan_count = 0, iters = 0, dropped_total = 0;
   const int fs = MD(frame_skip);
   for (int s = 0; s < fs; ++s) { iters += substep(m, ws, ncon, dropped, nan_count, lane); dropped_total += dropped; }
+  PH_DECL;
   cfrc_ext(m, ws, ncon, lane);
   // termination: signed cfrc_ext component above threshold on the listed bodies
   int term = 0;
@@ -312,6 +313,7 @@ DEV void step_env(const ModelDev& m, const EnvArrays& E, int env, float* ws, con
   build_state(m, E, env, ws, sim_step, false, cmd, state, lane);
   store_state(m, E, env, ws, lane);
   const int trunc = (sim_step == MD(max_episode_steps));
+  PH_MARK(PH_OBS);
   if (E.dbg_sens) FOR_LANE(i, 10) E.dbg_sens[(size_t)env * 10 + i] = WS(W_SENS)[i];
   if (E.dbg_qacc) FOR_LANE(i, nv) E.dbg_qacc[(size_t)env * nv + i] = WS(W_QACC)[i];
   if (lane == 0) {
@@ -331,6 +333,26 @@ DEV void step_env(const ModelDev& m, const EnvArrays& E, int env, float* ws, con
     st[ST_NCON] += (float)ncon; st[ST_ITERS] += (float)iters; st[ST_DROPPED] += (float)dropped_total; st[ST_NAN] += (float)nan_count;
     if (term || trunc) { st[ST_EPISODES] += 1.f; st[ST_TERMINATED] += (float)term; st[ST_SUCCESS] += (float)(trunc && !term); }
   }
+  SYNC();
+}
+
+// one raw physics sub-step (mj_step) from the stored state with ctrl = the last applied torque; debug / parity aid
+// mirroring the oracle's orc_substep
+DEV void substep_env(const ModelDev& m, const EnvArrays& E, int env, float* ws, int lane) {
+  const int nv = MD(nv), nu = MD(nu), nb = MD(nbody);
+  load_params(m, E, env, ws, lane);
+  load_state(m, E, env, ws, lane);
+  FOR_LANE(k, nu) WS(W_CTRL)[k] = E.torque[(size_t)env * nu + k];
+  SYNC();
+  int ncon = 0, dropped = 0, nan_count = 0;
+  const int iters = substep(m, ws, ncon, dropped, nan_count, lane);
+  cfrc_ext(m, ws, ncon, lane);
+  if (E.dbg_cfrc) FOR_LANE(i, 6 * nb) E.dbg_cfrc[(size_t)env * 6 * nb + i] = WS(W_CACC)[i];
+  dump_contacts(m, E, env, ws, ncon, lane);
+  store_state(m, E, env, ws, lane);
+  if (E.dbg_sens) FOR_LANE(i, 10) E.dbg_sens[(size_t)env * 10 + i] = WS(W_SENS)[i];
+  if (E.dbg_qacc) FOR_LANE(i, nv) E.dbg_qacc[(size_t)env * nv + i] = WS(W_QACC)[i];
+  if (lane == 0) { E.counters[(size_t)env * 8 + CT_NCON] = ncon; if (E.dbg_iters) E.dbg_iters[env] = iters; }
   SYNC();
 }
 

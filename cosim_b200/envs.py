@@ -227,6 +227,10 @@ class BatchedEnv:
         p = lambda a: None if a is None else a.ctypes.data_as(ctypes.c_void_p)
         self._check(self._L.cosim_step_host(self._h, p(action), p(command), p(state_out), p(terminated_out), p(truncated_out)), "cosim_step_host")
 
+    def substep(self):
+        """One raw physics sub-step with ctrl = last applied torque (parity aid, see cosim_substep)."""
+        self._check(self._L.cosim_substep(self._h, self._stream()), "cosim_substep")
+
     def event(self, event, value, mask=None):
         if event == "push":
             v = self._as(value, 3)
@@ -260,14 +264,30 @@ class BatchedEnv:
         429-581): success = truncated without termination; tracking error = mean |lin_vel_x - cmd0| etc."""
         self._check(self._L.cosim_stats_reduce(self._h, self._ptr(self._stats), self._stream()), "cosim_stats_reduce")
         s = self._stats.clone()
-        if all_reduce and torch.distributed.is_available() and torch.distributed.is_initialized():
-            mx = s[_ST_MAX].clone()
-            torch.distributed.all_reduce(s, op=torch.distributed.ReduceOp.SUM)
-            torch.distributed.all_reduce(mx, op=torch.distributed.ReduceOp.MAX)
-            s[_ST_MAX] = mx
+        if all_reduce:
+            s = all_reduce_stats(s)
         if clear:
             self._check(self._L.cosim_stats_clear(self._h, self._stream()), "cosim_stats_clear")
         return derive_stats(s.cpu().numpy(), self.action_dim)
+
+
+def all_reduce_stats(s):
+    """Sum the raw statistics vector over ranks (max for the max-torque slot).  The only collective of the
+    path: NCCL on GPU tensors, gloo on CPU tensors (tests); no-op without a process group."""
+    if torch.distributed.is_available() and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1:
+        mx = s[_ST_MAX].clone()
+        torch.distributed.all_reduce(s, op=torch.distributed.ReduceOp.SUM)
+        torch.distributed.all_reduce(mx, op=torch.distributed.ReduceOp.MAX)
+        s[_ST_MAX] = mx
+    return s
+
+
+def shard_envs(total_envs, world_size, rank):
+    """Contiguous env ranges per rank: (num_envs, env_offset).  Global env id = offset + local id = RNG substream."""
+    base, rem = divmod(int(total_envs), int(world_size))
+    n = base + (1 if rank < rem else 0)
+    off = rank * base + min(rank, rem)
+    return n, off
 
 
 def derive_stats(raw, action_dim):

@@ -48,7 +48,7 @@ def build(force=False, verbose=False):
     for cmd, p in procs:
         if p.wait() != 0:
             raise RuntimeError("nvcc failed: " + " ".join(cmd))
-    subprocess.check_call([nvcc, "-shared", "-o", LIB_PATH] + objs + ["-lcuda"])
+    subprocess.check_call([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB_PATH] + objs)
     return LIB_PATH
 
 
@@ -73,6 +73,7 @@ def lib():
     L.cosim_step.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp]
     L.cosim_step_host.argtypes = [vp, vp, vp, vp, vp, vp]
     L.cosim_push.argtypes = [vp, vp, vp, vp]
+    L.cosim_substep.argtypes = [vp, vp]
     L.cosim_field_dim.argtypes = [vp, cp]
     L.cosim_field_is_int.argtypes = [vp, cp]
     L.cosim_get.argtypes = [vp, cp, vp, vp]
@@ -97,7 +98,7 @@ def lib():
 
 
 EXPORTS = ["cosim_create", "cosim_destroy", "cosim_last_error", "cosim_reset", "cosim_step", "cosim_step_host",
-           "cosim_push", "cosim_field_dim", "cosim_field_is_int", "cosim_get", "cosim_set", "cosim_set_debug",
+           "cosim_push", "cosim_substep", "cosim_field_dim", "cosim_field_is_int", "cosim_get", "cosim_set", "cosim_set_debug",
            "cosim_stats_reduce", "cosim_stats_clear", "cosim_rng_probe", "cosim_num_envs", "cosim_dim",
            "cosim_launch_count", "cosim_smem_bytes_per_env", "cosim_warps_per_block",
            "cosim_policy_create", "cosim_policy_destroy", "cosim_policy_forward", "cosim_policy_launch_count"]

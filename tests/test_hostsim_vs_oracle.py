@@ -1,0 +1,81 @@
+"""CPU tests of the CUDA engine's per-env LOGIC: tests/hostsim compiles cosim_b200/csrc/engine_core.h +
+engine_env.h in a single-lane host emulation (LANES = 1) and is compared with the fp64 oracle.  This checks
+layouts, indexing, solver control flow and the env layer without a GPU; the real kernels are tested by
+tests/test_gpu_parity.py on the B200 (-m gpu).  hostsim is test infrastructure, never a product path."""
+import numpy as np
+import pytest
+
+from cosim_b200.config import make_config, load_tables, RANDOM_NONE, RANDOM_FULL
+from cosim_b200.model import build_model
+from oracle.oracle import Oracle
+from tests.hostsim.hostsim import HostSim
+
+CASES = [("flamingo_p_v3", "rocky_hard"), ("flamingo_light_v1", "flat"), ("w4_p_v2", "stairs_up_hard"), ("humanoid_p_v0", "slope_hard")]
+
+
+@pytest.mark.parametrize("robot,terrain", CASES)
+def test_reset_and_substeps(robot, terrain):
+    m = build_model(make_config(robot, terrain, random=RANDOM_NONE))
+    N = 4
+    o, h = Oracle(m, N, seed=1), HostSim(m, N, seed=1)
+    np.testing.assert_allclose(h.reset(), o.reset(), atol=1e-6)
+    rng = np.random.default_rng(0)
+    errs = []
+    for i in range(5):
+        a = rng.uniform(-1, 1, (N, m.dim("nu")))
+        o.step(a)
+        for s in range(2):
+            for k in ("qpos", "qvel", "qacc_warmstart", "torque"):
+                h.set(k, o.get(k))
+            o.substep(); h.substep()
+            assert (o.get("ncon")[:, 0].astype(int) == h.get("counters")[:, 7]).all()
+            errs.append(np.abs(o.get("qvel") - h.get("qvel")).max(axis=1))
+    errs = np.concatenate(errs)
+    assert np.median(errs) < 2e-4 and (errs > 1e-2).mean() <= 0.15
+
+
+def test_env_layer_state_and_flags():
+    """Whole control steps incl. PD, delay, obs build, frequency gating, stack, command slots, truncation."""
+    et, _ = load_tables()
+    cfg = make_config("flamingo_p_v3", "rocky_hard", random=dict(RANDOM_NONE, action_delay_prob=0.3, init_noise=0.05),
+                      non_stacked_obs_order=list(et["flamingo_p_v3"]["non_stacked_obs_order"]) + ["height_map"], max_duration=0.2)
+    cfg["observation"]["dof_vel"]["freq"] = 25          # refresh every 2nd control step
+    m = build_model(cfg)
+    N = 3
+    o, h = Oracle(m, N, seed=4), HostSim(m, N, seed=4)
+    cmd = np.array([[0.5, 0.1, -0.2, 0.0]] * N)
+    np.testing.assert_allclose(h.reset(command=cmd), o.reset(command=cmd), atol=1e-6)
+    rng = np.random.default_rng(2)
+    for i in range(10):
+        a = rng.uniform(-1, 1, (N, 8))
+        for k in ("qpos", "qvel", "qacc_warmstart"):
+            h.set(k, o.get(k))
+        so, to, tro = o.step(a, cmd)
+        sh, th, trh = h.step(a, cmd)
+        np.testing.assert_allclose(h.get("torque"), o.get("torque"), atol=2e-4)
+        assert (tro == trh).all() and tro.all() == (i == 9)
+        ok = np.abs(o.get("qvel") - h.get("qvel")).max(axis=1) < 1e-3
+        np.testing.assert_allclose(sh[ok], so[ok], atol=2e-3)
+        assert (sh[:, 84:88] == cmd.astype(np.float32)).all()          # command slots carry the applied command
+
+
+def test_randomization_draws_match_fp32_oracle():
+    m = build_model(make_config("humanoid_p_v0", "slope_hard", random=RANDOM_FULL))
+    N = 6
+    f, h = Oracle(m, N, seed=0xC051, use_float=True), HostSim(m, N, seed=0xC051)
+    for g, k in [("body_mass", "body_mass"), ("frictionloss", "dof_frictionloss"), ("kp", "kp"), ("kd", "kd")]:
+        assert (h.get(g) == f.get(k).astype(np.float32)).all(), g
+    np.testing.assert_allclose(h.get("invweight_dof"), f.get("dof_invweight0"), rtol=5e-4)
+    from oracle.oracle import philox
+    assert h.philox(3, 2, 17, 5) == philox(0xC051, 3, 2, 17, 5)
+
+
+def test_push_event():
+    m = build_model(make_config("flamingo_p_v3", "flat", random=RANDOM_NONE))
+    h = HostSim(m, 2, seed=1)
+    h.reset()
+    q = h.get("qpos"); q[:, 3:7] = [np.cos(0.4), 0, 0, np.sin(0.4)]     # yaw 0.8 rad
+    h.set("qpos", q)
+    h.push([1.0, 0.0, 0.3])
+    v = h.get("qvel")[0, :3]
+    np.testing.assert_allclose(v, [np.cos(0.8), -np.sin(0.8), 0.3], atol=1e-6)   # robot-frame xy, world z (quirk C-12)
