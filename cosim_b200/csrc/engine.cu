@@ -12,27 +12,48 @@
 // ------------------------------------------------------------------------------------------ kernels
 extern __shared__ __align__(16) float g_smem[];
 
-#define ENV_PROLOGUE()                                              \
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;       \
-  const int env = blockIdx.x * (blockDim.x >> 5) + warp;            \
-  if (env >= E.N) return;                                           \
-  float* ws = g_smem + (size_t)warp * m.ws_floats;
+// The model header (dims, opts, table pointers, workspace offsets: ~1.8 KB) is copied to shared memory once per
+// CTA so that the out-of-line device functions read it with LDS instead of generic loads from the param bank.
+#define MODEL_FLOATS ((int)((sizeof(ModelDev) + 15) / 16 * 4))
+#define ENV_PROLOGUE()                                                                   \
+  {                                                                                      \
+    const uint32_t* src_ = (const uint32_t*)&mp;                                         \
+    uint32_t* dst_ = (uint32_t*)g_smem;                                                  \
+    for (int i = threadIdx.x; i < (int)(sizeof(ModelDev) / 4); i += blockDim.x) dst_[i] = src_[i]; \
+    __syncthreads();                                                                     \
+  }                                                                                      \
+  const ModelDev& m = *(const ModelDev*)g_smem;                                          \
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;                            \
+  const int env = blockIdx.x * (blockDim.x >> 5) + warp;                                 \
+  if (env >= E.N) return;                                                                \
+  float* ws = g_smem + MODEL_FLOATS + (size_t)warp * m.ws_floats;
 
-__global__ void __launch_bounds__(256) k_init(const __grid_constant__ ModelDev m, const EnvArrays E) {
+__global__ void __launch_bounds__(512, 1) k_init(const __grid_constant__ ModelDev mp, const EnvArrays E) {
   ENV_PROLOGUE();
   init_env(m, E, env, ws, lane);
 }
-__global__ void __launch_bounds__(256) k_reset(const __grid_constant__ ModelDev m, const EnvArrays E, const StepArgs a) {
+__global__ void __launch_bounds__(512, 1) k_reset(const __grid_constant__ ModelDev mp, const EnvArrays E, const StepArgs a) {
   ENV_PROLOGUE();
   if (a.mask && !a.mask[env]) return;
   const int cd = MD(command_dim);
   reset_env(m, E, env, ws, a.command ? a.command + (size_t)env * cd : nullptr, a.state_out + (size_t)env * MD(state_dim), lane);
 }
-__global__ void __launch_bounds__(256) k_step(const __grid_constant__ ModelDev m, const EnvArrays E, const StepArgs a) {
-  ENV_PROLOGUE();
-  step_env(m, E, env, ws, a, lane);
+// k_step: every warp of the CTA (also the padding warps of the last CTA) walks through the phase barriers
+__global__ void __launch_bounds__(512, 1) k_step(const __grid_constant__ ModelDev mp, const EnvArrays E, const StepArgs a) {
+  {
+    const uint32_t* src_ = (const uint32_t*)&mp;
+    uint32_t* dst_ = (uint32_t*)g_smem;
+    for (int i = threadIdx.x; i < (int)(sizeof(ModelDev) / 4); i += blockDim.x) dst_[i] = src_[i];
+    __syncthreads();
+  }
+  const ModelDev& m = *(const ModelDev*)g_smem;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int env = blockIdx.x * (blockDim.x >> 5) + warp;
+  float* ws = g_smem + MODEL_FLOATS + (size_t)warp * m.ws_floats;
+  const int have_env = env < E.N;
+  step_env(m, E, have_env ? env : 0, ws, a, lane, have_env, 1);
 }
-__global__ void __launch_bounds__(256) k_substep(const __grid_constant__ ModelDev m, const EnvArrays E) {
+__global__ void __launch_bounds__(512, 1) k_substep(const __grid_constant__ ModelDev mp, const EnvArrays E) {
   ENV_PROLOGUE();
   substep_env(m, E, env, ws, lane);
 }
@@ -118,16 +139,19 @@ int cosim_create(const void* blob, size_t nbytes, int num_envs, int device, uint
   }
   // launch geometry: as many env-warps per block as fit comfortably; blocks co-reside up to the 227 KB/SM limit
   const size_t per = (size_t)h->m.ws_floats * sizeof(float);
-  int wpb = 4;
-  while (wpb > 1 && per * wpb > 100 * 1024) wpb >>= 1;
+  // one CTA per SM with as many env-warps as its shared memory holds (<= 16): the warps of a CTA move through the
+  // phases of a sub-step together (block barriers in k_step), which keeps the instruction working set per SM small
+  int wpb = 16;
+  while (wpb > 1 && per * wpb + MODEL_FLOATS * sizeof(float) > 200 * 1024) --wpb;
+  if (num_envs < wpb * 148) { wpb = (num_envs + 147) / 148; if (wpb < 1) wpb = 1; }      // small batches: spread over the SMs
   if (per * wpb > 227 * 1024) { fprintf(stderr, "cosim_create: workspace %zu B/env exceeds shared memory\n", per); for (void* p : h->allocs) cudaFree(p); delete h; return COSIM_ERR_MODEL; }
-  h->wpb = wpb; h->smem = per * wpb;
+  h->wpb = wpb; h->smem = per * wpb + MODEL_FLOATS * sizeof(float);
   cudaError_t e1 = cudaFuncSetAttribute(k_init, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem);
   cudaError_t e2 = cudaFuncSetAttribute(k_reset, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem);
   cudaError_t e3 = cudaFuncSetAttribute(k_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem);
   if (e3 == cudaSuccess) e3 = cudaFuncSetAttribute(k_substep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem);
   if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) { fprintf(stderr, "cosim_create: cudaFuncSetAttribute failed: %s\n", cudaGetErrorString(e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3))); for (void* p : h->allocs) cudaFree(p); delete h; return COSIM_ERR_CUDA; }
-  cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+  cudaStreamCreate(&h->stream);     // blocking stream: ordered after work the caller queued on the legacy default stream (reset, set)
   k_init<<<grid_for(h), 32 * h->wpb, h->smem, h->stream>>>(h->m, h->E);
   h->launches++;
   cudaError_t e = cudaStreamSynchronize(h->stream);

@@ -21,7 +21,7 @@ struct StepArgs {
   const uint8_t* mask;         // reset: [N] or NULL (all)
 };
 
-DEV void load_params(const ModelDev& m, const EnvArrays& E, int env, float* ws, int lane) {
+DEV_NOINLINE void load_params(const ModelDev& m, const EnvArrays& E, int env, float* ws, int lane) {
   const int nb = MD(nbody), nv = MD(nv), ng = MD(ngeom), nu = MD(nu);
   FOR_LANE(i, nb) { WS(W_BMASS)[i] = E.body_mass[(size_t)env * nb + i]; WS(W_INVWB)[i] = E.invw_body[(size_t)env * nb + i]; }
   FOR_LANE(i, nv) { WS(W_INVWD)[i] = E.invw_dof[(size_t)env * nv + i]; WS(W_FLOSS)[i] = E.floss[(size_t)env * nv + i]; }
@@ -29,19 +29,19 @@ DEV void load_params(const ModelDev& m, const EnvArrays& E, int env, float* ws, 
   FOR_LANE(i, nu) { WS(W_KP)[i] = E.kp[(size_t)env * nu + i]; WS(W_KD)[i] = E.kd[(size_t)env * nu + i]; }
   FOR_LANE(i, 4) WS(W_SCAL)[i] = E.scal[(size_t)env * 4 + i];
 }
-DEV void load_state(const ModelDev& m, const EnvArrays& E, int env, float* ws, int lane) {
+DEV_NOINLINE void load_state(const ModelDev& m, const EnvArrays& E, int env, float* ws, int lane) {
   const int nq = MD(nq), nv = MD(nv);
   FOR_LANE(i, nq) WS(W_QPOS)[i] = E.qpos[(size_t)env * nq + i];
   FOR_LANE(i, nv) { WS(W_QVEL)[i] = E.qvel[(size_t)env * nv + i]; WS(W_WARM)[i] = E.warm[(size_t)env * nv + i]; }
 }
-DEV void store_state(const ModelDev& m, const EnvArrays& E, int env, const float* ws, int lane) {
+DEV_NOINLINE void store_state(const ModelDev& m, const EnvArrays& E, int env, const float* ws, int lane) {
   const int nq = MD(nq), nv = MD(nv);
   FOR_LANE(i, nq) E.qpos[(size_t)env * nq + i] = WS(W_QPOS)[i];
   FOR_LANE(i, nv) { E.qvel[(size_t)env * nv + i] = WS(W_QVEL)[i]; E.warm[(size_t)env * nv + i] = WS(W_WARM)[i]; }
 }
 
 // ------------------------------------------------------------------------------------------ init: randomise + setConst
-DEV void init_env(const ModelDev& m, const EnvArrays& E, int env, float* ws, int lane) {
+DEV_NOINLINE void init_env(const ModelDev& m, const EnvArrays& E, int env, float* ws, int lane) {
   const int nb = MD(nbody), nv = MD(nv), ng = MD(ngeom), nu = MD(nu), njnt = MD(njnt);
   float draw[8];
 #pragma unroll
@@ -70,7 +70,7 @@ DEV void init_env(const ModelDev& m, const EnvArrays& E, int env, float* ws, int
   FOR_LANE(i, nv * nv) A[i] = M[i];
   SYNC();
   chol_factor(A, WS(W_INVD), nv, lane);
-  for (int c = 0; c < nv; ++c) {           // column c of M^-1 overwrites M
+  NOUNROLL for (int c = 0; c < nv; ++c) {           // column c of M^-1 overwrites M
     FOR_LANE(k, nv) WS(W_TMPV)[k] = (k == c) ? 1.f : 0.f;
     SYNC();
     chol_solve(A, WS(W_INVD), WS(W_TMPV), WS(W_BUF), WS(W_GRAD), nv, lane);
@@ -82,18 +82,18 @@ DEV void init_env(const ModelDev& m, const EnvArrays& E, int env, float* ws, int
     if (m.jnt_type[j] == 0) {
       const float t = (M[a * nv + a] + M[(a + 1) * nv + a + 1] + M[(a + 2) * nv + a + 2]) / 3.f;
       const float r = (M[(a + 3) * nv + a + 3] + M[(a + 4) * nv + a + 4] + M[(a + 5) * nv + a + 5]) / 3.f;
-      for (int k = 0; k < 3; ++k) { WS(W_INVWD)[a + k] = t; WS(W_INVWD)[a + 3 + k] = r; }
+      NOUNROLL for (int k = 0; k < 3; ++k) { WS(W_INVWD)[a + k] = t; WS(W_INVWD)[a + 3 + k] = r; }
     } else WS(W_INVWD)[a] = M[a * nv + a];
   }
   if (lane == 0) WS(W_INVWB)[0] = 0.f;
-  for (int b = 1; b < nb; ++b) {
+  NOUNROLL for (int b = 1; b < nb; ++b) {
     float off[3]; v3sub(off, WS(W_XIPOS) + 3 * b, WS(W_SCOM));
     float tran = 0.f;
-    for (int r = 0; r < 3; ++r) {
+    NOUNROLL for (int r = 0; r < 3; ++r) {
       FOR_LANE(k, nv) { float jp[3]; jac_col(m, ws, b, k, off, jp); WS(W_TMPV)[k] = jp[r]; }
       SYNC();
       float acc = 0.f;
-      FOR_LANE(i, nv) { float s = 0.f; for (int k = 0; k < nv; ++k) s += M[i * nv + k] * WS(W_TMPV)[k]; acc += WS(W_TMPV)[i] * s; }
+      FOR_LANE(i, nv) { float s = 0.f; NOUNROLL for (int k = 0; k < nv; ++k) s += M[i * nv + k] * WS(W_TMPV)[k]; acc += WS(W_TMPV)[i] * s; }
       tran += wsum(acc);
       SYNC();
     }
@@ -107,14 +107,14 @@ DEV void init_env(const ModelDev& m, const EnvArrays& E, int env, float* ws, int
     float* sc = E.scal + (size_t)env * 4;
     sc[0] = m.ground_friction[3] != 0.f ? slide : m.ground_friction[0]; sc[1] = meaninertia; sc[2] = delay; sc[3] = 0.f;
     int* ct = E.counters + (size_t)env * 8;
-    for (int i = 0; i < 8; ++i) ct[i] = 0;
+    NOUNROLL for (int i = 0; i < 8; ++i) ct[i] = 0;
     ct[CT_NEED_RESET] = 1;
   }
   FOR_LANE(i, ST__COUNT) E.stats[(size_t)env * ST__COUNT + i] = 0.f;
 }
 
 // ------------------------------------------------------------------------------------------ observation build
-DEV float trunc_noise(const ModelDev& m, int env, uint32_t nobs, int which, uint32_t idx) {
+DEV_NOINLINE float trunc_noise(const ModelDev& m, int env, uint32_t nobs, int which, uint32_t idx) {
   if (MD(zero_noise)) return 0.f;
   const float* nz = m.noise + 6 * which;
   const float u = uni(m, env, RNG_NOISE, nobs, idx);
@@ -128,7 +128,7 @@ DEV int raw_offset(const ModelDev& m, int kind) {
   return 0;
 }
 // raw noisy observations -> W_RAW: [dof_pos | dof_vel | ang_vel | lin_vel | projected_gravity | last_action | height_map]
-DEV void get_obs(const ModelDev& m, const EnvArrays& E, int env, float* ws, uint32_t nobs, int lane) {
+DEV_NOINLINE void get_obs(const ModelDev& m, const EnvArrays& E, int env, float* ws, uint32_t nobs, int lane) {
   const int np = MD(n_dofpos), nvl = MD(n_dofvel), nu = MD(nu), rx = MD(hm_res_x), ry = MD(hm_res_y), nh = rx * ry;
   float* raw = WS(W_RAW); const float* qpos = WS(W_QPOS); const float* qvel = WS(W_QVEL); const float* S = WS(W_SENS);
   FOR_LANE(i, np) raw[i] = qpos[m.dofpos_qadr[i]] * LDG(m.dofpos_fac + i) + trunc_noise(m, env, nobs, 0, i);
@@ -165,13 +165,13 @@ DEV void get_obs(const ModelDev& m, const EnvArrays& E, int env, float* ws, uint
 }
 // noise draw index convention: position in [dof_pos | dof_vel | ang_vel | lin_vel | proj_grav | height_map]
 
-DEV void concat_obs(const ModelDev& m, const EnvArrays& E, int env, const float* ws, int sim_step, bool stacked, const float* cmd, float* out, int lane) {
+DEV_NOINLINE void concat_obs(const ModelDev& m, const EnvArrays& E, int env, const float* ws, int sim_step, bool stacked, const float* cmd, float* out, int lane) {
   const int* kind = stacked ? m.sobs_kind : m.nobs_kind; const int* dim = stacked ? m.sobs_dim : m.nobs_dim;
   const float* scale = stacked ? m.sobs_scale : m.nobs_scale; const int* itv = stacked ? m.sobs_interval : m.nobs_interval;
   const int* off = stacked ? m.sobs_off : m.nobs_off; const int n = stacked ? MD(n_sobs) : MD(n_nobs);
   float* cache = E.freq_cache + (size_t)env * imax(1, MD(cache_dim));
   int o = 0;
-  for (int k = 0; k < n; ++k) {
+  NOUNROLL for (int k = 0; k < n; ++k) {
     const int d = dim[k];
     if (kind[k] == OBS_COMMAND) { FOR_LANE(i, d) out[o + i] = cmd ? cmd[i] : 0.f; o += d; continue; }
     const bool upd = (sim_step == 0) || (sim_step % itv[k] == 0);
@@ -185,7 +185,7 @@ DEV void concat_obs(const ModelDev& m, const EnvArrays& E, int env, const float*
   }
 }
 // StateBuildWrapper._build_state + CommandWrapper._apply_command_inplace
-DEV void build_state(const ModelDev& m, const EnvArrays& E, int env, float* ws, int sim_step, bool reset, const float* cmd, float* state, int lane) {
+DEV_NOINLINE void build_state(const ModelDev& m, const EnvArrays& E, int env, float* ws, int sim_step, bool reset, const float* cmd, float* state, int lane) {
   const int ss = MD(stack_size), sd = MD(stacked_dim);
   float* buf = E.obs_buffer + (size_t)env * ss * sd;
   // newest frame straight into state[0:sd]; older frames shift by one (or copy on reset)
@@ -195,21 +195,21 @@ DEV void build_state(const ModelDev& m, const EnvArrays& E, int env, float* ws, 
     const float v = state[i];
     if (reset) { for (int k = 0; k < ss; ++k) { buf[k * sd + i] = v; state[k * sd + i] = v; } }
     else {
-      for (int k = ss - 1; k > 0; --k) { const float o = buf[(k - 1) * sd + i]; buf[k * sd + i] = o; state[k * sd + i] = o; }
+      NOUNROLL for (int k = ss - 1; k > 0; --k) { const float o = buf[(k - 1) * sd + i]; buf[k * sd + i] = o; state[k * sd + i] = o; }
       buf[i] = v;
     }
   }
   concat_obs(m, E, env, ws, sim_step, false, cmd, state + ss * sd, lane);
   // command slots inside stacked frames carry the current command in every frame
   int o = 0;
-  for (int k = 0; k < MD(n_sobs); ++k) {
+  NOUNROLL for (int k = 0; k < MD(n_sobs); ++k) {
     if (m.sobs_kind[k] == OBS_COMMAND) for (int f = 1; f < ss; ++f) FOR_LANE(i, m.sobs_dim[k]) state[f * sd + o + i] = cmd ? cmd[i] : 0.f;
     o += m.sobs_dim[k];
   }
 }
 
 // ------------------------------------------------------------------------------------------ reset
-DEV void reset_env(const ModelDev& m, const EnvArrays& E, int env, float* ws, const float* cmd, float* state, int lane) {
+DEV_NOINLINE void reset_env(const ModelDev& m, const EnvArrays& E, int env, float* ws, const float* cmd, float* state, int lane) {
   const int nq = MD(nq), nv = MD(nv), nu = MD(nu);
   int* ct = E.counters + (size_t)env * 8;
   const uint32_t nreset = (uint32_t)ct[CT_NRESET], nobs = (uint32_t)ct[CT_NOBS];
@@ -237,31 +237,36 @@ DEV void reset_env(const ModelDev& m, const EnvArrays& E, int env, float* ws, co
   SYNC();
 }
 
-DEV void dump_contacts(const ModelDev& m, const EnvArrays& E, int env, const float* ws, int ncon, int lane) {
+DEV_NOINLINE void dump_contacts(const ModelDev& m, const EnvArrays& E, int env, const float* ws, int ncon, int lane) {
   if (!E.dbg_contacts) return;
   const int cap = MD(ncon_max);
   float* out = E.dbg_contacts + (size_t)env * cap * 10;
   FOR_LANE(c, ncon) {
     float* o = out + 10 * c;
     o[0] = WS(W_CN_DIST)[c];
-    for (int k = 0; k < 3; ++k) { o[1 + k] = WS(W_CN_POS)[3 * c + k]; o[4 + k] = WS(W_CN_FRAME)[9 * c + k]; }
+    NOUNROLL for (int k = 0; k < 3; ++k) { o[1 + k] = WS(W_CN_POS)[3 * c + k]; o[4 + k] = WS(W_CN_FRAME)[9 * c + k]; }
     o[7] = (float)WSI(W_CN_GEOM)[c]; o[8] = (float)WSI(W_CN_CELL)[c]; o[9] = WS(W_CN_MU)[c];
   }
 }
 
 // ------------------------------------------------------------------------------------------ step
-DEV void step_env(const ModelDev& m, const EnvArrays& E, int env, float* ws, const StepArgs& a, int lane) {
+// `have_env` = this warp owns an env (false for the padding warps of the last CTA); `bsync` = CTA-wide phase barriers
+DEV_NOINLINE void step_env(const ModelDev& m, const EnvArrays& E, int env, float* ws, const StepArgs& a, int lane, int have_env = 1, int bsync = 0) {
   const int nv = MD(nv), nu = MD(nu), cd = MD(command_dim), sdim = MD(state_dim), nb = MD(nbody);
   int* ct = E.counters + (size_t)env * 8;
   const float* cmd = a.command ? a.command + (size_t)env * cd : nullptr;
   float* state = a.state_out + (size_t)env * sdim;
-  if (ct[CT_NEED_RESET]) {     // reference asserts reset-before-step; the batched engine resets the env instead
+  int active = have_env;
+  if (have_env && ct[CT_NEED_RESET]) {     // reference asserts reset-before-step; the batched engine resets the env instead
     if (MD(auto_reset)) { reset_env(m, E, env, ws, cmd, state, lane); if (lane == 0) { a.terminated[env] = 0; a.truncated[env] = 0; } }
-    return;
+    active = 0;
   }
-  const int sim_step = ct[CT_SIM_STEP] + 1;
-  const uint32_t nstep = (uint32_t)ct[CT_NSTEP], nobs = (uint32_t)ct[CT_NOBS];
-  const int has_prev = ct[CT_HAS_DELAY];
+  int sim_step = 0, has_prev = 0; uint32_t nstep = 0, nobs = 0;
+  float rm = 0.f, tabs = 0.f, tsq = 0.f, tmax = 0.f;
+  if (active) {
+  sim_step = ct[CT_SIM_STEP] + 1;
+  nstep = (uint32_t)ct[CT_NSTEP]; nobs = (uint32_t)ct[CT_NOBS];
+  has_prev = ct[CT_HAS_DELAY];
   load_params(m, E, env, ws, lane);
   load_state(m, E, env, ws, lane);
   const float* act = a.action + (size_t)env * nu;
@@ -269,7 +274,6 @@ DEV void step_env(const ModelDev& m, const EnvArrays& E, int env, float* ws, con
   const float v = uni(m, env, RNG_DELAY, nstep, 0);
   SYNC();
   const bool delay = (WS(W_SCAL)[2] > v) && has_prev;
-  float rm = 0.f, tabs = 0.f, tsq = 0.f, tmax = 0.f;
   FOR_LANE(k, nu) {
     const float ak = act[k];
     const float f = delay ? E.delay_prev[(size_t)env * nu + k] : ak;
@@ -297,9 +301,12 @@ DEV void step_env(const ModelDev& m, const EnvArrays& E, int env, float* ws, con
   }
   rm = sqrtf(wsum(rm) / (float)nu); tabs = wsum(tabs); tsq = wsum(tsq); tmax = wmaxf(tmax);
   SYNC();
+  }
+  BSYNC(bsync);
   int ncon = 0, dropped = 0, nan_count = 0, iters = 0, dropped_total = 0;
   const int fs = MD(frame_skip);
-  for (int s = 0; s < fs; ++s) { iters += substep(m, ws, ncon, dropped, nan_count, lane); dropped_total += dropped; }
+  NOUNROLL for (int s = 0; s < fs; ++s) { iters += substep(m, ws, ncon, dropped, nan_count, lane, active, bsync); dropped_total += dropped; }
+  if (!active) return;
   PH_DECL;
   cfrc_ext(m, ws, ncon, lane);
   // termination: signed cfrc_ext component above threshold on the listed bodies
@@ -338,7 +345,7 @@ DEV void step_env(const ModelDev& m, const EnvArrays& E, int env, float* ws, con
 
 // one raw physics sub-step (mj_step) from the stored state with ctrl = the last applied torque; debug / parity aid
 // mirroring the oracle's orc_substep
-DEV void substep_env(const ModelDev& m, const EnvArrays& E, int env, float* ws, int lane) {
+DEV_NOINLINE void substep_env(const ModelDev& m, const EnvArrays& E, int env, float* ws, int lane) {
   const int nv = MD(nv), nu = MD(nu), nb = MD(nbody);
   load_params(m, E, env, ws, lane);
   load_state(m, E, env, ws, lane);

@@ -70,6 +70,97 @@ def hfield_from_raster(raster_u8):
     return np.ascontiguousarray(data, dtype=np.float32)
 
 
+# ------------------------------------------------------------------ support maps for convex hulls
+SUP_G = 8          # cube-map grid per face: 6 * G * G direction buckets per mesh
+
+
+def support_bucket(d, G=SUP_G):
+    """Direction -> bucket id (cube map).  Must match `support_bucket` in csrc/engine_core.h bit for bit."""
+    d = np.asarray(d, dtype=np.float32)
+    a = np.abs(d)
+    ax = 0 if (a[0] >= a[1] and a[0] >= a[2]) else (1 if a[1] >= a[2] else 2)
+    face = 2 * ax + (1 if d[ax] < 0 else 0)
+    inv = np.float32(1.0) / np.maximum(a[ax], np.float32(1e-30))
+    u = d[(ax + 1) % 3] * inv
+    v = d[(ax + 2) % 3] * inv
+    iu = int(min(G - 1, max(0, np.floor((u + np.float32(1.0)) * np.float32(0.5 * G)))))
+    iv = int(min(G - 1, max(0, np.floor((v + np.float32(1.0)) * np.float32(0.5 * G)))))
+    return (face * G + iu) * G + iv
+
+
+def support_buckets(D, G=SUP_G):
+    """Vectorised `support_bucket` for an array of directions [n, 3] (float32 arithmetic, same result)."""
+    D = np.asarray(D, dtype=np.float32)
+    a = np.abs(D)
+    ax = np.where((a[:, 0] >= a[:, 1]) & (a[:, 0] >= a[:, 2]), 0, np.where(a[:, 1] >= a[:, 2], 1, 2))
+    r = np.arange(len(D))
+    major = D[r, ax]
+    face = 2 * ax + (major < 0)
+    inv = np.float32(1.0) / np.maximum(a[r, ax], np.float32(1e-30))
+    u = D[r, (ax + 1) % 3] * inv
+    v = D[r, (ax + 2) % 3] * inv
+    iu = np.clip(np.floor((u + np.float32(1.0)) * np.float32(0.5 * G)), 0, G - 1).astype(np.int64)
+    iv = np.clip(np.floor((v + np.float32(1.0)) * np.float32(0.5 * G)), 0, G - 1).astype(np.int64)
+    return (face * G + iu) * G + iv
+
+
+def build_support_map(verts, G=SUP_G, samples=9, checks=20000, seed=0):
+    """Per direction bucket, the hull vertices that can be the support point for a direction in that bucket.
+
+    The engine's hull support (`support()` in csrc/engine_core.h) scans only the bucket's candidates instead of
+    all vertices (696 for a wheel).  Candidates = arg-max vertices of a dense direction sample of the bucket
+    (borders included) + their hull neighbours; then verified against brute force on random directions and
+    patched until clean.  Returns (offsets[6*G*G + 1], indices)."""
+    from scipy.spatial import ConvexHull
+    V = np.asarray(verts, dtype=np.float64)
+    n = len(V)
+    nb = 6 * G * G
+    if n <= 32:                                   # tiny hulls (proxy boxes): every bucket lists every vertex
+        return np.arange(nb + 1, dtype=np.int32) * n, np.tile(np.arange(n, dtype=np.int32), nb)
+    hull = ConvexHull(V)
+    nbr = [set() for _ in range(n)]
+    for tri in hull.simplices:
+        for a in tri:
+            nbr[a].update(int(b) for b in tri if b != a)
+    cand = [set() for _ in range(nb)]
+    t = np.linspace(0.0, 1.0, samples)
+    for face in range(6):
+        ax, sgn = face // 2, (-1.0 if face % 2 else 1.0)
+        for iu in range(G):
+            for iv in range(G):
+                u = -1.0 + 2.0 * (iu + t) / G
+                v = -1.0 + 2.0 * (iv + t) / G
+                uu, vv = np.meshgrid(u, v, indexing="ij")
+                D = np.zeros((samples * samples, 3))
+                D[:, ax] = sgn
+                D[:, (ax + 1) % 3] = uu.ravel()
+                D[:, (ax + 2) % 3] = vv.ravel()
+                P = D @ V.T
+                mx = P.max(axis=1, keepdims=True)
+                hit = np.unique(np.nonzero(P >= mx - 1e-9 * (1.0 + np.abs(mx)))[1])
+                c = cand[(face * G + iu) * G + iv]
+                for h in hit:
+                    c.add(int(h))
+                    c.update(nbr[int(h)])
+    rng = np.random.default_rng(seed)
+    for _ in range(8):                            # verify + patch
+        D = rng.standard_normal((checks, 3)).astype(np.float32)
+        best = np.argmax(D.astype(np.float64) @ V.T, axis=1)
+        bad = 0
+        for k, b in zip(support_buckets(D, G), best):
+            if int(b) not in cand[int(k)]:
+                cand[int(k)].add(int(b)); cand[int(k)].update(nbr[int(b)]); bad += 1
+        if bad == 0:
+            break
+    off = np.zeros(nb + 1, dtype=np.int32)
+    idx = []
+    for k in range(nb):
+        lst = sorted(cand[k])
+        idx.extend(lst)
+        off[k + 1] = len(idx)
+    return off, np.array(idx, dtype=np.int32)
+
+
 # ------------------------------------------------------------------ small numpy FK (qpos0 only)
 def _quat_mul(a, b):
     return np.array([a[0] * b[0] - a[1] * b[1] - a[2] * b[2] - a[3] * b[3],
@@ -109,6 +200,16 @@ def _rng_pair(v):
     if isinstance(v, (list, tuple)):
         return float(v[0]), float(v[1])
     return float(v), float(v)
+
+
+_SUP_CACHE = {}
+
+
+def _support_map_cached(verts):
+    key = verts.tobytes()
+    if key not in _SUP_CACHE:
+        _SUP_CACHE[key] = build_support_map(verts)
+    return _SUP_CACHE[key]
 
 
 class Model:
@@ -370,6 +471,25 @@ def build_model(config, ncon_max=None, auto_reset=False):
     S["act_dof"], S["act_qadr"], S["act_mode"] = act_dof, act_qadr, mode
     S["act_kp"], S["act_kd"], S["act_scale"], S["act_posfac"], S["act_gamma"], S["act_clip"] = kp, kd, sc, posfac, gam, clip
     S["hull_verts"] = rb["hull_verts"].astype(np.float32).reshape(-1)
+    # support maps (engine only; the oracle scans all hull vertices): per mesh geom, base of its bucket table
+    hv = rb["hull_verts"].astype(np.float32).reshape(-1, 3)
+    sup_adr = np.full(ngeom, -1, np.int32)
+    sup_off, sup_idx, cache = [np.zeros(1, np.int32)], [], {}
+    nidx = 0
+    for g in range(ngeom):
+        if int(rb["geom_type"][g]) != 7:
+            continue
+        key = (int(rb["geom_vadr"][g]), int(rb["geom_vnum"][g]))
+        if key not in cache:
+            off, idx = _support_map_cached(hv[key[0]:key[0] + key[1]])
+            cache[key] = sum(len(o) for o in sup_off) - 1
+            sup_off.append(off[1:] + nidx)
+            sup_idx.append(idx)
+            nidx += len(idx)
+        sup_adr[g] = cache[key]
+    S["geom_supadr"] = sup_adr
+    S["sup_off"] = np.concatenate(sup_off).astype(np.int32)
+    S["sup_idx"] = (np.concatenate(sup_idx) if sup_idx else np.zeros(1)).astype(np.int32)
     gf = np.concatenate([rb["ground_friction"].astype(np.float64), [float(rb["ground_has_friction_attr"])]])
     S["ground_friction"] = gf
     S["hfield_data"] = hf.reshape(-1)
