@@ -15,18 +15,25 @@ extern __shared__ __align__(16) float g_smem[];
 // The model header (dims, opts, table pointers, workspace offsets: ~1.8 KB) is copied to shared memory once per
 // CTA so that the out-of-line device functions read it with LDS instead of generic loads from the param bank.
 #define MODEL_FLOATS ((int)((sizeof(ModelDev) + 15) / 16 * 4))
-#define ENV_PROLOGUE()                                                                   \
-  {                                                                                      \
-    const uint32_t* src_ = (const uint32_t*)&mp;                                         \
-    uint32_t* dst_ = (uint32_t*)g_smem;                                                  \
-    for (int i = threadIdx.x; i < (int)(sizeof(ModelDev) / 4); i += blockDim.x) dst_[i] = src_[i]; \
-    __syncthreads();                                                                     \
-  }                                                                                      \
-  const ModelDev& m = *(const ModelDev*)g_smem;                                          \
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;                            \
-  const int env = blockIdx.x * (blockDim.x >> 5) + warp;                                 \
-  if (env >= E.N) return;                                                                \
-  float* ws = g_smem + MODEL_FLOATS + (size_t)warp * m.ws_floats;
+// CTA prologue: copy the model header and the table arena to shared memory, re-point the table pointers at the copy
+#define CTA_PROLOGUE()                                                                                   \
+  {                                                                                                      \
+    const uint32_t* src_ = (const uint32_t*)&mp;                                                         \
+    uint32_t* dst_ = (uint32_t*)g_smem;                                                                  \
+    for (int i = threadIdx.x; i < (int)(sizeof(ModelDev) / 4); i += blockDim.x) dst_[i] = src_[i];       \
+    const uint4* asrc_ = (const uint4*)mp.arena_g;                                                       \
+    uint4* adst_ = (uint4*)(g_smem + MODEL_FLOATS);                                                      \
+    for (int i = threadIdx.x; i < mp.arena_bytes / 16; i += blockDim.x) adst_[i] = __ldg(asrc_ + i);     \
+    __syncthreads();                                                                                     \
+    for (int i = threadIdx.x; i < mp.nslots; i += blockDim.x)                                            \
+      *(const uint8_t**)((char*)g_smem + mp.slot_field[i]) = (const uint8_t*)adst_ + 16 * (size_t)mp.slot_off16[i]; \
+    __syncthreads();                                                                                     \
+  }                                                                                                      \
+  const ModelDev& m = *(const ModelDev*)g_smem;                                                          \
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;                                            \
+  const int env = blockIdx.x * (blockDim.x >> 5) + warp;                                                 \
+  float* ws = g_smem + m.shared_floats + (size_t)warp * m.ws_floats;
+#define ENV_PROLOGUE() CTA_PROLOGUE() if (env >= E.N) return;
 
 __global__ void __launch_bounds__(512, 1) k_init(const __grid_constant__ ModelDev mp, const EnvArrays E) {
   ENV_PROLOGUE();
@@ -40,16 +47,7 @@ __global__ void __launch_bounds__(512, 1) k_reset(const __grid_constant__ ModelD
 }
 // k_step: every warp of the CTA (also the padding warps of the last CTA) walks through the phase barriers
 __global__ void __launch_bounds__(512, 1) k_step(const __grid_constant__ ModelDev mp, const EnvArrays E, const StepArgs a) {
-  {
-    const uint32_t* src_ = (const uint32_t*)&mp;
-    uint32_t* dst_ = (uint32_t*)g_smem;
-    for (int i = threadIdx.x; i < (int)(sizeof(ModelDev) / 4); i += blockDim.x) dst_[i] = src_[i];
-    __syncthreads();
-  }
-  const ModelDev& m = *(const ModelDev*)g_smem;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int env = blockIdx.x * (blockDim.x >> 5) + warp;
-  float* ws = g_smem + MODEL_FLOATS + (size_t)warp * m.ws_floats;
+  CTA_PROLOGUE();
   const int have_env = env < E.N;
   step_env(m, E, have_env ? env : 0, ws, a, lane, have_env, 1);
 }
@@ -142,10 +140,10 @@ int cosim_create(const void* blob, size_t nbytes, int num_envs, int device, uint
   // one CTA per SM with as many env-warps as its shared memory holds (<= 16): the warps of a CTA move through the
   // phases of a sub-step together (block barriers in k_step), which keeps the instruction working set per SM small
   int wpb = 16;
-  while (wpb > 1 && per * wpb + MODEL_FLOATS * sizeof(float) > 200 * 1024) --wpb;
+  while (wpb > 1 && per * wpb + h->m.shared_floats * sizeof(float) > 200 * 1024) --wpb;
   if (num_envs < wpb * 148) { wpb = (num_envs + 147) / 148; if (wpb < 1) wpb = 1; }      // small batches: spread over the SMs
   if (per * wpb > 227 * 1024) { fprintf(stderr, "cosim_create: workspace %zu B/env exceeds shared memory\n", per); for (void* p : h->allocs) cudaFree(p); delete h; return COSIM_ERR_MODEL; }
-  h->wpb = wpb; h->smem = per * wpb + MODEL_FLOATS * sizeof(float);
+  h->wpb = wpb; h->smem = per * wpb + h->m.shared_floats * sizeof(float);
   cudaError_t e1 = cudaFuncSetAttribute(k_init, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem);
   cudaError_t e2 = cudaFuncSetAttribute(k_reset, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem);
   cudaError_t e3 = cudaFuncSetAttribute(k_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem);

@@ -27,6 +27,9 @@
 #include <math.h>
 #include <float.h>
 #include "../../include/cosim_blob.h"
+#ifdef COSIM_HOST_EMU
+struct float4 { float x, y, z, w; };
+#endif
 
 #ifdef COSIM_HOST_EMU
 #define DEV static inline
@@ -34,6 +37,7 @@
 #define LANES 1
 #define SYNC() ((void)0)
 #define LDG(p) (*(p))
+#define LDGB(p) (*(p))
 static inline float wsum(float v) { return v; }
 static inline float wmaxf(float v) { return v; }
 static inline int wor(int v) { return v; }
@@ -44,7 +48,8 @@ static inline float fast_ndtri(float p);
 #define DEV_NOINLINE __device__ __noinline__
 #define LANES 32
 #define SYNC() __syncwarp()
-#define LDG(p) __ldg(p)
+#define LDG(p) (*(p))          // small model tables: shared-memory copy of the arena (plain load; __ldg would fault)
+#define LDGB(p) __ldg(p)       // big read-only tables in global memory: hull vertices, support maps, height field
 DEV float wsum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -123,6 +128,14 @@ struct ModelDev {
   const int *geom_type, *geom_body, *geom_vadr, *geom_vnum, *geom_fr_random;
   const float *geom_size, *geom_pos, *geom_quat, *geom_friction, *geom_center, *geom_rbound;
   const float *hull_verts, *hfield_data;
+  // hull support maps (cosim_b200/model.py:build_support_map): per mesh geom a table of 6*8*8 direction buckets;
+  // sup_cand[k] = (x, y, z, vertex index) of the k-th candidate, so one 16-byte load per candidate
+  const int *geom_supadr, *sup_off; const float4* sup_cand;
+  // lower-triangle (i, k) pairs of an nv x nv matrix sorted by k descending, packed (i << 8) | k: the trailing
+  // sub-matrix update of Cholesky column j is the prefix of length (nv-j-1)(nv-j)/2
+  const int* tri; int shared_floats;
+  // table arena (engine_setup.h): global copy + which pointer fields of this struct point into it
+  const uint8_t* arena_g; int arena_bytes, nslots; uint16_t slot_field[112], slot_off16[112];
   float ground_friction[4];
   // equality
   const int *eq_body1, *eq_body2;
@@ -150,7 +163,7 @@ enum WsField {
   W_BMASS, W_INVWD, W_INVWB, W_FLOSS, W_GMU, W_SCAL,
   W_FR_D, W_FR_AREF, W_LM_SIGN, W_LM_D, W_LM_AREF,
   W_CN_POS, W_CN_FRAME, W_CN_DIST, W_CN_MU, W_CN_BODY, W_CN_GEOM, W_CN_CELL, W_CN_D, W_CN_AREF, W_CN_J, W_CN_F, W_CN_X, W_CN_V,
-  W_EQ_J, W_EQ_D, W_EQ_AREF, W_EQ_X, W_EQ_V, W_EQ_F, W_SENS, W_RAW, W_ACT, W_FILT, W_KP, W_KD, W__COUNT   // keep <= 80 (ModelDev::off)
+  W_EQ_J, W_EQ_D, W_EQ_AREF, W_EQ_X, W_EQ_V, W_EQ_F, W_SENS, W_RAW, W_ACT, W_FILT, W_KP, W_KD, W_GTASK, W__COUNT   // keep <= 80 (ModelDev::off)
 };
 static_assert(W__COUNT <= 80, "ModelDev::off too small");
 #define WS(f) (ws + m.off[f])
@@ -404,34 +417,54 @@ DEV_NOINLINE void crb(const ModelDev& m, float* ws, int lane) {
 }
 
 // dense Cholesky of the n x n SPD matrix in A (lower triangle used, overwritten by L below the
-// diagonal; the diagonal keeps L_jj^2 and 1/L_jj goes to invd)
-DEV_NOINLINE void chol_factor(float* A, float* invd, int n, int lane) {
+// diagonal; the diagonal keeps L_jj^2 and 1/L_jj goes to invd).  The trailing update of column j runs over the
+// flat list of (i, k) pairs `tri` (n must be the nv the table was built for), 32 pairs per pass.
+DEV_NOINLINE void chol_factor(float* A, float* invd, int n, int lane, const int* tri) {
   NOUNROLL for (int j = 0; j < n; ++j) {
     const float inv = 1.f / sqrtf(fmaxf(A[j * n + j], 1e-30f));
     if (lane == 0) invd[j] = inv;
     NOUNROLL for (int i = j + 1 + lane; i < n; i += LANES) A[i * n + j] *= inv;
     SYNC();
-    NOUNROLL for (int i = j + 1 + lane; i < n; i += LANES) {
-      const float lij = A[i * n + j];
-      NOUNROLL for (int k = j + 1; k <= i; ++k) A[i * n + k] -= lij * A[k * n + j];
+    const int T = ((n - j - 1) * (n - j)) >> 1;
+    NOUNROLL for (int idx = lane; idx < T; idx += LANES) {
+      const int t = tri[idx], i = t >> 8, k = t & 255;
+      A[i * n + k] -= A[i * n + j] * A[k * n + j];
     }
     SYNC();
   }
 }
 // solves L L^T x = b.  b is destroyed, tmp is scratch, result in out (all length n, distinct)
 DEV_NOINLINE void chol_solve(const float* A, const float* invd, float* b, float* tmp, float* out, int n, int lane) {
-  NOUNROLL for (int i = 0; i < n; ++i) {
+#ifdef COSIM_HOST_EMU
+  for (int i = 0; i < n; ++i) {
     const float xi = b[i] * invd[i];
-    NOUNROLL for (int k = i + 1 + lane; k < n; k += LANES) b[k] -= A[k * n + i] * xi;
+    for (int k = i + 1 + lane; k < n; k += LANES) b[k] -= A[k * n + i] * xi;
     if (lane == 0) tmp[i] = xi;
     SYNC();
   }
-  NOUNROLL for (int i = n - 1; i >= 0; --i) {
+  for (int i = n - 1; i >= 0; --i) {
     const float xi = tmp[i] * invd[i];
-    NOUNROLL for (int k = lane; k < i; k += LANES) tmp[k] -= A[i * n + k] * xi;
+    for (int k = lane; k < i; k += LANES) tmp[k] -= A[i * n + k] * xi;
     if (lane == 0) out[i] = xi;
     SYNC();
   }
+#else
+  // n <= 32: lane k keeps element k in a register, the pivot travels by shuffle (same arithmetic as above)
+  float bk = lane < n ? b[lane] : 0.f;
+  NOUNROLL for (int i = 0; i < n; ++i) {
+    const float xi = __shfl_sync(0xffffffffu, bk, i) * invd[i];
+    if (lane > i && lane < n) bk -= A[lane * n + i] * xi;
+    if (lane == i) bk = xi;
+  }
+  NOUNROLL for (int i = n - 1; i >= 0; --i) {
+    const float xi = __shfl_sync(0xffffffffu, bk, i) * invd[i];
+    if (lane < i) bk -= A[i * n + lane] * xi;
+    if (lane == i) bk = xi;
+  }
+  if (lane < n) out[lane] = bk;
+  SYNC();
+  (void)tmp;
+#endif
 }
 
 // ------------------------------------------------------------------------------------------ velocity / bias
@@ -516,12 +549,31 @@ DEV_NOINLINE void rne_bias(const ModelDev& m, float* ws, float* out, int lane) {
 }
 
 // ------------------------------------------------------------------------------------------ collision
-struct GeomW { int type; const float* pos; const float* mat; float size[3]; const float* verts; int nvert; float center[3]; };
+#ifdef COSIM_HOST_EMU
+static inline int __float_as_int(float f) { int i; memcpy(&i, &f, 4); return i; }
+#endif
+// direction -> cube-map bucket; must match cosim_b200/model.py:support_bucket (float32 arithmetic)
+DEV int support_bucket(const float* d) {
+  const int G = 8;
+  const float a0 = fabsf(d[0]), a1 = fabsf(d[1]), a2 = fabsf(d[2]);
+  const int ax = (a0 >= a1 && a0 >= a2) ? 0 : (a1 >= a2 ? 1 : 2);
+  const float dm = ax == 0 ? d[0] : (ax == 1 ? d[1] : d[2]);
+  const float du = ax == 0 ? d[1] : (ax == 1 ? d[2] : d[0]);
+  const float dv = ax == 0 ? d[2] : (ax == 1 ? d[0] : d[1]);
+  const int face = 2 * ax + (dm < 0.f ? 1 : 0);
+  const float inv = 1.0f / fmaxf(fabsf(dm), 1e-30f);
+  const float u = du * inv, v = dv * inv;
+  const int iu = imin(G - 1, imax(0, (int)floorf((u + 1.0f) * (0.5f * G))));
+  const int iv = imin(G - 1, imax(0, (int)floorf((v + 1.0f) * (0.5f * G))));
+  return (face * G + iu) * G + iv;
+}
+struct GeomW { int type; const float* pos; const float* mat; float size[3]; const float* verts; int nvert; float center[3]; const int* sup_off; const float4* sup_cand; };
 
 DEV GeomW make_geom(const ModelDev& m, const float* ws, int g) {
   GeomW G; G.type = m.geom_type[g]; G.pos = WS(W_GXPOS) + 3 * g; G.mat = WS(W_GXMAT) + 9 * g;
   G.size[0] = LDG(m.geom_size + 3 * g); G.size[1] = LDG(m.geom_size + 3 * g + 1); G.size[2] = LDG(m.geom_size + 3 * g + 2);
   G.verts = m.hull_verts + 3 * m.geom_vadr[g]; G.nvert = m.geom_vnum[g];
+  { const int sa = m.geom_supadr[g]; G.sup_off = sa >= 0 ? m.sup_off + sa : nullptr; G.sup_cand = m.sup_cand; }
   float c[3] = {LDG(m.geom_center + 3 * g), LDG(m.geom_center + 3 * g + 1), LDG(m.geom_center + 3 * g + 2)}, r[3];
   m3mulv(r, G.mat, c); v3add(G.center, G.pos, r);
   return G;
@@ -537,14 +589,33 @@ DEV_NOINLINE void support(const GeomW& G, const float* dir, float* out, int lane
     lp[2] = (ld[2] > 0.f ? 1.f : (ld[2] < 0.f ? -1.f : 0.f)) * G.size[1];
   } else if (G.type == GEOM_BOX) {
     lp[0] = (ld[0] > 0.f ? 1.f : -1.f) * G.size[0]; lp[1] = (ld[1] > 0.f ? 1.f : -1.f) * G.size[1]; lp[2] = (ld[2] > 0.f ? 1.f : -1.f) * G.size[2];
-  } else {   // mesh: lanes stride the hull vertices
+  } else if (G.sup_off) {   // mesh with a support map: scan only the candidates of the direction's bucket
+    const int bk = support_bucket(ld);
+    const int o0 = LDGB(G.sup_off + bk), o1 = LDGB(G.sup_off + bk + 1);
+    float bv = -INFINITY; int best = 0x7fffffff; float bx = 0.f, by = 0.f, bz = 0.f;
+    NOUNROLL for (int k = o0 + lane; k < o1; k += LANES) {
+#ifdef COSIM_HOST_EMU
+      const float4 c = G.sup_cand[k];
+#else
+      const float4 c = __ldg(G.sup_cand + k);
+#endif
+      const float v = c.x * ld[0] + c.y * ld[1] + c.z * ld[2];
+      if (v > bv) { bv = v; best = __float_as_int(c.w); bx = c.x; by = c.y; bz = c.z; }     // candidates are sorted by vertex index
+    }
+#ifndef COSIM_HOST_EMU
+    { const int mine = best; wargmax(bv, best);
+      const int src = __ffs(__ballot_sync(0xffffffffu, mine == best)) - 1;
+      bx = __shfl_sync(0xffffffffu, bx, src); by = __shfl_sync(0xffffffffu, by, src); bz = __shfl_sync(0xffffffffu, bz, src); }
+#endif
+    lp[0] = bx; lp[1] = by; lp[2] = bz;
+  } else {   // mesh without a map: lanes stride all hull vertices
     float bv = -INFINITY; int best = 0x7fffffff;
     NOUNROLL for (int i = lane; i < G.nvert; i += LANES) {
-      float v = LDG(G.verts + 3 * i) * ld[0] + LDG(G.verts + 3 * i + 1) * ld[1] + LDG(G.verts + 3 * i + 2) * ld[2];
+      float v = LDGB(G.verts + 3 * i) * ld[0] + LDGB(G.verts + 3 * i + 1) * ld[1] + LDGB(G.verts + 3 * i + 2) * ld[2];
       if (v > bv) { bv = v; best = i; }
     }
     wargmax(bv, best);
-    lp[0] = LDG(G.verts + 3 * best); lp[1] = LDG(G.verts + 3 * best + 1); lp[2] = LDG(G.verts + 3 * best + 2);
+    lp[0] = LDGB(G.verts + 3 * best); lp[1] = LDGB(G.verts + 3 * best + 1); lp[2] = LDGB(G.verts + 3 * best + 2);
   }
   float r[3]; m3mulv(r, G.mat, lp); v3add(out, G.pos, r);
 }
@@ -745,7 +816,7 @@ DEV_NOINLINE void collide_hfield(const ModelDev& m, float* ws, int g, int& ncon,
     const int w = c1 - c0 + 1, cnt = w * (r1 - r0 + 1);
     if (cnt <= 256) {
       float hmax = -INFINITY;
-      NOUNROLL for (int t = lane; t < cnt; t += LANES) hmax = fmaxf(hmax, LDG(m.hfield_data + (size_t)(r0 + t / w) * ncol + c0 + t % w));
+      NOUNROLL for (int t = lane; t < cnt; t += LANES) hmax = fmaxf(hmax, LDGB(m.hfield_data + (size_t)(r0 + t / w) * ncol + c0 + t % w));
       hmax = wmaxf(hmax) * sz;
       if (pos[2] - rb > hmax) return;
     }
@@ -773,7 +844,7 @@ DEV_NOINLINE void collide_hfield(const ModelDev& m, float* ws, int g, int& ncon,
         for (int k = 0; k < 3; ++k) { P[0][k] = P[1][k]; P[1][k] = P[2][k]; P[3][k] = P[4][k]; P[4][k] = P[5][k]; }
         const float x = dx * (float)c - sx, y = dy * (float)(r + i) - sy;
         P[2][0] = P[5][0] = x; P[2][1] = P[5][1] = y;
-        P[2][2] = -base; P[5][2] = LDG(m.hfield_data + (size_t)(r + i) * ncol + c) * sz;
+        P[2][2] = -base; P[5][2] = LDGB(m.hfield_data + (size_t)(r + i) * ncol + c) * sz;
         ++nvert;
         if (nvert > 2) {
           if (P[3][2] < xmin[2] && P[4][2] < xmin[2] && P[5][2] < xmin[2]) continue;
@@ -788,6 +859,301 @@ DEV_NOINLINE void collide_hfield(const ModelDev& m, float* ws, int g, int& ncon,
       }
     }
   }
+}
+
+// ------------------------------------------------------------------------------------------ lane-parallel hfield collision
+// Same results as collide_hfield above (mjc_ConvexHField restated), different schedule: stage 1 gives every geom a lane
+// (bounding tests, AABB from 6 support queries, sub-grid), stage 2 enumerates the (geom, row, col, triangle) prisms of
+// the whole env in the reference order and gives every prism a lane; each lane runs its own scalar MPR query.  Contacts
+// are appended in task order (ballot prefix), so order, the 50-per-geom cap and the ncon_max cap match the serial loop.
+struct PV { float x, y, z; int pi; };     // Minkowski-difference vertex + index of the prism vertex it came from
+struct GeomL { int type; const float* pos; const float* mat; float sx, sy, sz; const float* verts; int nvert; const int* sup_off; const float4* sup_cand; };
+
+DEV GeomL make_geom_lane(const ModelDev& m, const float* ws, int g) {
+  GeomL G; G.type = m.geom_type[g]; G.pos = WS(W_GXPOS) + 3 * g; G.mat = WS(W_GXMAT) + 9 * g;
+  G.sx = LDG(m.geom_size + 3 * g); G.sy = LDG(m.geom_size + 3 * g + 1); G.sz = LDG(m.geom_size + 3 * g + 2);
+  G.verts = m.hull_verts + 3 * m.geom_vadr[g]; G.nvert = m.geom_vnum[g];
+  const int sa = m.geom_supadr[g]; G.sup_off = sa >= 0 ? m.sup_off + sa : nullptr; G.sup_cand = m.sup_cand;
+  return G;
+}
+// scalar support query (one lane): same arithmetic and tie-breaks as support()
+DEV_NOINLINE void support_lane(const GeomL& G, float dx, float dy, float dz, float* out) {
+  const float* M = G.mat;
+  const float l0 = M[0] * dx + M[3] * dy + M[6] * dz, l1 = M[1] * dx + M[4] * dy + M[7] * dz, l2 = M[2] * dx + M[5] * dy + M[8] * dz;
+  float px = 0.f, py = 0.f, pz = 0.f;
+  if (G.type == GEOM_SPHERE) { px = l0 * G.sx; py = l1 * G.sx; pz = l2 * G.sx; }
+  else if (G.type == GEOM_CYLINDER) {
+    const float n = sqrtf(l0 * l0 + l1 * l1);
+    if (n > MINVALF) { px = l0 / n * G.sx; py = l1 / n * G.sx; }
+    pz = (l2 > 0.f ? 1.f : (l2 < 0.f ? -1.f : 0.f)) * G.sy;
+  } else if (G.type == GEOM_BOX) {
+    px = (l0 > 0.f ? 1.f : -1.f) * G.sx; py = (l1 > 0.f ? 1.f : -1.f) * G.sy; pz = (l2 > 0.f ? 1.f : -1.f) * G.sz;
+  } else if (G.sup_off) {
+    const float ld[3] = {l0, l1, l2};
+    const int bk = support_bucket(ld);
+    const int o0 = LDGB(G.sup_off + bk), o1 = LDGB(G.sup_off + bk + 1);
+    float bv = -INFINITY;
+    NOUNROLL for (int k = o0; k < o1; ++k) {
+#ifdef COSIM_HOST_EMU
+      const float4 c = G.sup_cand[k];
+#else
+      const float4 c = __ldg(G.sup_cand + k);
+#endif
+      const float v = c.x * l0 + c.y * l1 + c.z * l2;
+      if (v > bv) { bv = v; px = c.x; py = c.y; pz = c.z; }
+    }
+  } else {
+    float bv = -INFINITY;
+    NOUNROLL for (int i = 0; i < G.nvert; ++i) {
+      const float vx = LDGB(G.verts + 3 * i), vy = LDGB(G.verts + 3 * i + 1), vz = LDGB(G.verts + 3 * i + 2);
+      const float v = vx * l0 + vy * l1 + vz * l2;
+      if (v > bv) { bv = v; px = vx; py = vy; pz = vz; }
+    }
+  }
+  out[0] = G.pos[0] + (M[0] * px + M[1] * py + M[2] * pz);
+  out[1] = G.pos[1] + (M[3] * px + M[4] * py + M[5] * pz);
+  out[2] = G.pos[2] + (M[6] * px + M[7] * py + M[8] * pz);
+}
+// prism in registers: three columns (x, y, top z), bottoms at -base.  Vertex order as in the strip walk: 0..2 bottoms, 3..5 tops
+struct PrismL { float x[3], y[3], z[3], base; };
+DEV void prism_vertex(const PrismL& P, int i, float* v) {
+  const int c = i >= 3 ? i - 3 : i;
+  v[0] = c == 0 ? P.x[0] : (c == 1 ? P.x[1] : P.x[2]);
+  v[1] = c == 0 ? P.y[0] : (c == 1 ? P.y[1] : P.y[2]);
+  v[2] = i >= 3 ? (c == 0 ? P.z[0] : (c == 1 ? P.z[1] : P.z[2])) : -P.base;
+}
+DEV PV mink_lane(const PrismL& P, const GeomL& G, float dx, float dy, float dz) {
+  int best = 0; float bv = 0.f, bx = 0.f, by = 0.f, bz = 0.f;
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    const int c = i >= 3 ? i - 3 : i;
+    const float vx = P.x[c], vy = P.y[c], vz = i >= 3 ? P.z[c] : -P.base;
+    const float v = vx * dx + vy * dy + vz * dz;
+    if (i == 0 || v > bv) { bv = v; best = i; bx = vx; by = vy; bz = vz; }
+  }
+  float s2[3]; support_lane(G, -dx, -dy, -dz, s2);
+  PV r; r.x = bx - s2[0]; r.y = by - s2[1]; r.z = bz - s2[2]; r.pi = best;
+  return r;
+}
+DEV float pv_dot(const PV& a, float x, float y, float z) { return a.x * x + a.y * y + a.z * z; }
+DEV void pv_portal_dir(const PV& p1, const PV& p2, const PV& p3, float* dir) {
+  float a[3] = {p2.x - p1.x, p2.y - p1.y, p2.z - p1.z}, b[3] = {p3.x - p1.x, p3.y - p1.y, p3.z - p1.z};
+  v3cross(dir, a, b); v3normalize(dir);
+}
+DEV bool pv_reach_tol(const PV& p1, const PV& p2, const PV& p3, const PV& v4, const float* dir, float tol) {
+  const float dv1 = pv_dot(p1, dir[0], dir[1], dir[2]), dv2 = pv_dot(p2, dir[0], dir[1], dir[2]), dv3 = pv_dot(p3, dir[0], dir[1], dir[2]), dv4 = pv_dot(v4, dir[0], dir[1], dir[2]);
+  const float dm = fminf(dv4 - dv1, fminf(dv4 - dv2, dv4 - dv3));
+  return f_eq(dm, tol) || dm < tol;
+}
+DEV void pv_expand(const PV& p0, PV& p1, PV& p2, PV& p3, const PV& v4) {
+  const float a[3] = {v4.x, v4.y, v4.z}, b[3] = {p0.x, p0.y, p0.z};
+  float c[3]; v3cross(c, a, b);
+  float dot = pv_dot(p1, c[0], c[1], c[2]);
+  if (dot > 0.f) { dot = pv_dot(p2, c[0], c[1], c[2]); if (dot > 0.f) p1 = v4; else p3 = v4; }
+  else { dot = pv_dot(p3, c[0], c[1], c[2]); if (dot > 0.f) p2 = v4; else p1 = v4; }
+}
+// witness points of a portal vertex: v1 on the prism (exact), v2 = v1 - v on the geom
+DEV void pv_witness(const PrismL& P, const PV& p, const float* c1, float* v1) { if (p.pi < 0) v3copy(v1, c1); else prism_vertex(P, p.pi, v1); }
+// scalar MPR penetration query (one lane); 0 = hit.  Control flow identical to mpr_penetration().
+DEV_NOINLINE int mpr_lane(const ModelDev& m, const PrismL& P, const GeomL& G, const float* gcenter, float* depth, float* dir_out, float* pos) {
+  const float tol = MO(ccd_tolerance); const int maxit = MD(ccd_iterations);
+  float c1[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+  for (int i = 0; i < 6; ++i) { float v[3]; prism_vertex(P, i, v); v3add(c1, c1, v); }
+  v3scl(c1, c1, 1.f / 6.f);
+  PV p0, p1, p2, p3;
+  p0.x = c1[0] - gcenter[0]; p0.y = c1[1] - gcenter[1]; p0.z = c1[2] - gcenter[2]; p0.pi = -1;
+  if (f_eq(p0.x, 0.f) && f_eq(p0.y, 0.f) && f_eq(p0.z, 0.f)) p0.x += CCD_EPS * 10.f;
+  float dir[3] = {-p0.x, -p0.y, -p0.z}; v3normalize(dir);
+  p1 = mink_lane(P, G, dir[0], dir[1], dir[2]);
+  float dot = pv_dot(p1, dir[0], dir[1], dir[2]);
+  if (f_is_zero(dot) || dot < 0.f) return -1;
+  { const float a[3] = {p0.x, p0.y, p0.z}, b[3] = {p1.x, p1.y, p1.z}; v3cross(dir, a, b); }
+  if (f_is_zero(v3dot(dir, dir))) {
+    float v1[3]; pv_witness(P, p1, c1, v1);
+    for (int k = 0; k < 3; ++k) { const float pk = k == 0 ? p1.x : (k == 1 ? p1.y : p1.z); pos[k] = (v1[k] + (v1[k] - pk)) * 0.5f; }
+    if (f_eq(p1.x, 0.f) && f_eq(p1.y, 0.f) && f_eq(p1.z, 0.f)) { *depth = 0.f; dir_out[0] = dir_out[1] = dir_out[2] = 0.f; return 0; }
+    float pv[3] = {p1.x, p1.y, p1.z};
+    *depth = v3norm(pv); v3copy(dir_out, pv); v3normalize(dir_out); return 0;
+  }
+  v3normalize(dir);
+  p2 = mink_lane(P, G, dir[0], dir[1], dir[2]);
+  dot = pv_dot(p2, dir[0], dir[1], dir[2]);
+  if (f_is_zero(dot) || dot < 0.f) return -1;
+  { float va[3] = {p1.x - p0.x, p1.y - p0.y, p1.z - p0.z}, vb[3] = {p2.x - p0.x, p2.y - p0.y, p2.z - p0.z}; v3cross(dir, va, vb); v3normalize(dir); }
+  dot = pv_dot(p0, dir[0], dir[1], dir[2]);
+  if (dot > 0.f) { const PV t = p1; p1 = p2; p2 = t; dir[0] = -dir[0]; dir[1] = -dir[1]; dir[2] = -dir[2]; }
+  int guard = 0;
+  while (true) {       // portal discovery
+    if (++guard > 100) return -1;
+    p3 = mink_lane(P, G, dir[0], dir[1], dir[2]);
+    dot = pv_dot(p3, dir[0], dir[1], dir[2]);
+    if (f_is_zero(dot) || dot < 0.f) return -1;
+    int cont = 0;
+    { const float a[3] = {p1.x, p1.y, p1.z}, b[3] = {p3.x, p3.y, p3.z}; float va[3]; v3cross(va, a, b); dot = pv_dot(p0, va[0], va[1], va[2]); }
+    if (dot < 0.f && !f_is_zero(dot)) { p2 = p3; cont = 1; }
+    if (!cont) {
+      const float a[3] = {p3.x, p3.y, p3.z}, b[3] = {p2.x, p2.y, p2.z}; float va[3]; v3cross(va, a, b); dot = pv_dot(p0, va[0], va[1], va[2]);
+      if (dot < 0.f && !f_is_zero(dot)) { p1 = p3; cont = 1; }
+    }
+    if (!cont) break;
+    float va[3] = {p1.x - p0.x, p1.y - p0.y, p1.z - p0.z}, vb[3] = {p2.x - p0.x, p2.y - p0.y, p2.z - p0.z}; v3cross(dir, va, vb); v3normalize(dir);
+  }
+  guard = 0;
+  while (true) {       // portal refinement
+    if (++guard > 1000) return -1;
+    pv_portal_dir(p1, p2, p3, dir);
+    dot = pv_dot(p1, dir[0], dir[1], dir[2]);
+    if (f_is_zero(dot) || dot > 0.f) break;
+    const PV v4 = mink_lane(P, G, dir[0], dir[1], dir[2]);
+    dot = pv_dot(v4, dir[0], dir[1], dir[2]);
+    if (!(f_is_zero(dot) || dot > 0.f) || pv_reach_tol(p1, p2, p3, v4, dir, tol)) return -1;
+    pv_expand(p0, p1, p2, p3, v4);
+  }
+  int it = 0;
+  while (true) {       // penetration depth
+    pv_portal_dir(p1, p2, p3, dir);
+    const PV v4 = mink_lane(P, G, dir[0], dir[1], dir[2]);
+    if (pv_reach_tol(p1, p2, p3, v4, dir, tol) || it > maxit) {
+      const float a[3] = {p1.x, p1.y, p1.z}, b[3] = {p2.x, p2.y, p2.z}, c[3] = {p3.x, p3.y, p3.z};
+      float wit[3];
+      const float d2 = point_tri_dist2(a, b, c, wit);
+      *depth = sqrtf(d2);
+      if (f_is_zero(*depth)) { dir_out[0] = dir_out[1] = dir_out[2] = 0.f; } else { v3copy(dir_out, wit); v3normalize(dir_out); }
+      // find_pos: barycentric blend of the witness points
+      const float z0[3] = {p0.x, p0.y, p0.z};
+      float bw[4], vec[3];
+      v3cross(vec, a, b); bw[0] = v3dot(vec, c);
+      v3cross(vec, c, b); bw[1] = v3dot(vec, z0);
+      v3cross(vec, z0, a); bw[2] = v3dot(vec, c);
+      v3cross(vec, b, a); bw[3] = v3dot(vec, z0);
+      float sum = bw[0] + bw[1] + bw[2] + bw[3];
+      if (f_is_zero(sum) || sum < 0.f) {
+        bw[0] = 0.f;
+        v3cross(vec, b, c); bw[1] = v3dot(vec, dir);
+        v3cross(vec, c, a); bw[2] = v3dot(vec, dir);
+        v3cross(vec, a, b); bw[3] = v3dot(vec, dir);
+        sum = bw[1] + bw[2] + bw[3];
+      }
+      const float inv = 1.f / sum;
+      float s1[3] = {0.f, 0.f, 0.f}, s2[3] = {0.f, 0.f, 0.f}, v1[3];
+      pv_witness(P, p0, c1, v1); v3addscl(s1, s1, v1, bw[0]); { const float v2[3] = {v1[0] - p0.x, v1[1] - p0.y, v1[2] - p0.z}; v3addscl(s2, s2, v2, bw[0]); }
+      pv_witness(P, p1, c1, v1); v3addscl(s1, s1, v1, bw[1]); { const float v2[3] = {v1[0] - p1.x, v1[1] - p1.y, v1[2] - p1.z}; v3addscl(s2, s2, v2, bw[1]); }
+      pv_witness(P, p2, c1, v1); v3addscl(s1, s1, v1, bw[2]); { const float v2[3] = {v1[0] - p2.x, v1[1] - p2.y, v1[2] - p2.z}; v3addscl(s2, s2, v2, bw[2]); }
+      pv_witness(P, p3, c1, v1); v3addscl(s1, s1, v1, bw[3]); { const float v2[3] = {v1[0] - p3.x, v1[1] - p3.y, v1[2] - p3.z}; v3addscl(s2, s2, v2, bw[3]); }
+      for (int k = 0; k < 3; ++k) pos[k] = (s1[k] * inv + s2[k] * inv) * 0.5f;
+      return 0;
+    }
+    pv_expand(p0, p1, p2, p3, v4);
+    ++it;
+  }
+}
+
+// per-geom task record in W_GTASK: [cmin, rmin, ncols, nrows, first task, contacts so far, zmin (float), unused]
+DEV_NOINLINE void collide_hfield_all(const ModelDev& m, float* ws, int& ncon, int& dropped, int lane) {
+  const int ng = MD(ngeom), nrow = MD(hf_nrow), ncol = MD(hf_ncol);
+  const float sx = MO(hf_sx), sy = MO(hf_sy), sz = MO(hf_sz), base = MO(hf_base);
+  const float dx = 2.f * sx / (float)(ncol - 1), dy = 2.f * sy / (float)(nrow - 1);
+  int* task = WSI(W_GTASK);
+  // ---- stage 1: one lane per geom
+  FOR_LANE(g, ng) {
+    int* tk = task + 8 * g;
+    tk[0] = tk[1] = tk[2] = tk[3] = tk[4] = tk[5] = 0;
+    const GeomL G = make_geom_lane(m, ws, g);
+    const float cl[3] = {LDG(m.geom_center + 3 * g), LDG(m.geom_center + 3 * g + 1), LDG(m.geom_center + 3 * g + 2)};
+    float pos[3]; m3mulv(pos, G.mat, cl); v3add(pos, G.pos, pos);
+    const float rb = LDG(m.geom_rbound + g);
+    if (pos[0] - rb > sx || pos[0] + rb < -sx || pos[1] - rb > sy || pos[1] + rb < -sy) continue;
+    if (pos[2] - rb > sz || pos[2] + rb < -base) continue;
+    {  // conservative early-out (does not change results): highest terrain vertex under the bounding sphere
+      const int c0 = imax(0, (int)floorf((pos[0] - rb + sx) / dx)), c1 = imin(ncol - 1, (int)ceilf((pos[0] + rb + sx) / dx));
+      const int r0 = imax(0, (int)floorf((pos[1] - rb + sy) / dy)), r1 = imin(nrow - 1, (int)ceilf((pos[1] + rb + sy) / dy));
+      const int w = c1 - c0 + 1, cnt = w * (r1 - r0 + 1);
+      if (cnt <= 64) {
+        float hmax = -INFINITY;
+        NOUNROLL for (int t = 0; t < cnt; ++t) hmax = fmaxf(hmax, LDGB(m.hfield_data + (size_t)(r0 + t / w) * ncol + c0 + t % w));
+        if (pos[2] - rb > hmax * sz) continue;
+      }
+    }
+    float xmin[3], xmax[3], s[3];
+    support_lane(G, 1.f, 0.f, 0.f, s); xmax[0] = s[0]; support_lane(G, -1.f, 0.f, 0.f, s); xmin[0] = s[0];
+    support_lane(G, 0.f, 1.f, 0.f, s); xmax[1] = s[1]; support_lane(G, 0.f, -1.f, 0.f, s); xmin[1] = s[1];
+    support_lane(G, 0.f, 0.f, 1.f, s); xmax[2] = s[2]; support_lane(G, 0.f, 0.f, -1.f, s); xmin[2] = s[2];
+    if (xmin[0] > sx || xmax[0] < -sx || xmin[1] > sy || xmax[1] < -sy || xmin[2] > sz || xmax[2] < -base) continue;
+    int cmin = (int)floorf((xmin[0] + sx) / (2.f * sx) * (float)(ncol - 1));
+    int cmax = (int)ceilf((xmax[0] + sx) / (2.f * sx) * (float)(ncol - 1));
+    int rmin = (int)floorf((xmin[1] + sy) / (2.f * sy) * (float)(nrow - 1));
+    int rmax = (int)ceilf((xmax[1] + sy) / (2.f * sy) * (float)(nrow - 1));
+    cmin = imax(0, cmin); rmin = imax(0, rmin); cmax = imin(ncol - 1, cmax); rmax = imin(nrow - 1, rmax);
+    if (cmax <= cmin || rmax <= rmin) continue;
+    tk[0] = cmin; tk[1] = rmin; tk[2] = cmax - cmin; tk[3] = rmax - rmin;
+    ((float*)tk)[6] = xmin[2];
+  }
+  SYNC();
+  // ---- prefix of task counts (ngeom <= 32 is not required: serial scan by every lane over <= ngeom entries)
+  int T = 0;
+  NOUNROLL for (int g = 0; g < ng; ++g) { const int n = 2 * task[8 * g + 2] * task[8 * g + 3]; if (lane == 0) task[8 * g + 4] = T; T += n; }
+  SYNC();
+  // ---- stage 2: one lane per prism, chunks of LANES tasks in reference order
+  NOUNROLL for (int t0 = 0; t0 < T; t0 += LANES) {
+    const int t = t0 + lane;
+    int hit = 0, g = 0, cell = -1; float depth = 0.f, nrm[3] = {0.f, 0.f, 0.f}, cp[3] = {0.f, 0.f, 0.f};
+    if (t < T) {
+      NOUNROLL for (int k = 1; k < ng; ++k) if (task[8 * k + 4] <= t && task[8 * k + 2] * task[8 * k + 3] > 0) g = k;
+      // (the scan keeps the LAST geom whose first task is <= t and that has tasks; geoms without tasks never own t)
+      const int* tk = task + 8 * g;
+      if (tk[2] * tk[3] > 0 && t >= tk[4] && tk[5] < 50) {
+        const int local = t - tk[4], per_row = 2 * tk[2];
+        const int r = tk[1] + local / per_row, rem = local % per_row, c = tk[0] + 1 + (rem >> 1), i = rem & 1;
+        // strip walk of the reference: triangle i of cell (r, c-1): i = 0 -> (c-1,r) (c-1,r+1) (c,r); i = 1 -> (c-1,r+1) (c,r) (c,r+1)
+        const int ca = c - 1, ra = r + i, cb = i ? c : c - 1, rbb = i ? r : r + 1, cc = c, rc = r + i;
+        PrismL P; P.base = base;
+        P.x[0] = dx * (float)ca - sx; P.y[0] = dy * (float)ra - sy; P.z[0] = LDGB(m.hfield_data + (size_t)ra * ncol + ca) * sz;
+        P.x[1] = dx * (float)cb - sx; P.y[1] = dy * (float)rbb - sy; P.z[1] = LDGB(m.hfield_data + (size_t)rbb * ncol + cb) * sz;
+        P.x[2] = dx * (float)cc - sx; P.y[2] = dy * (float)rc - sy; P.z[2] = LDGB(m.hfield_data + (size_t)rc * ncol + cc) * sz;
+        const float zmin = ((const float*)tk)[6];
+        if (!(P.z[0] < zmin && P.z[1] < zmin && P.z[2] < zmin)) {
+          const GeomL G = make_geom_lane(m, ws, g);
+          const float cl[3] = {LDG(m.geom_center + 3 * g), LDG(m.geom_center + 3 * g + 1), LDG(m.geom_center + 3 * g + 2)};
+          float gc[3]; m3mulv(gc, G.mat, cl); v3add(gc, G.pos, gc);
+          PH_COUNT(PH_MPR_CALLS, 0);
+          if (mpr_lane(m, P, G, gc, &depth, nrm, cp) == 0 && !(nrm[0] == 0.f && nrm[1] == 0.f && nrm[2] == 0.f) && depth == depth) {
+            hit = 1; cell = ((r * ncol + (c - 1)) << 1) | i;
+          }
+        }
+      }
+    }
+    // ---- append the hits of this chunk in task order, honouring the per-geom cap (50) and ncon_max
+#ifdef COSIM_HOST_EMU
+    if (hit && task[8 * g + 5] < 50) { add_contact(m, ws, ncon, dropped, cp, nrm, -depth, g, cell, lane); task[8 * g + 5]++; }
+#else
+    unsigned hits = __ballot_sync(0xffffffffu, hit);
+    while (hits) {
+      const int src = __ffs(hits) - 1;
+      const int gs = __shfl_sync(0xffffffffu, g, src);
+      const unsigned same = __ballot_sync(0xffffffffu, hit && g == gs);      // hits of this geom, in task order
+      const int have = task[8 * gs + 5];
+      const int rank = __popc(same & ((1u << lane) - 1u));
+      const int keep = hit && g == gs && (have + rank) < 50;
+      const unsigned keepm = __ballot_sync(0xffffffffu, keep);
+      const int slot = ncon + __popc(keepm & ((1u << lane) - 1u));
+      if (keep && slot < MD(ncon_max)) {
+        float* cpp = WS(W_CN_POS) + 3 * slot; float* fr = WS(W_CN_FRAME) + 9 * slot;
+        v3copy(cpp, cp); v3copy(fr, nrm); make_frame(fr);
+        WS(W_CN_DIST)[slot] = -depth;
+        WS(W_CN_MU)[slot] = fmaxf(WS(W_SCAL)[0], WS(W_GMU)[g]);
+        WSI(W_CN_BODY)[slot] = m.geom_body[g]; WSI(W_CN_GEOM)[slot] = g; WSI(W_CN_CELL)[slot] = cell;
+      }
+      const int nkeep = __popc(keepm), room = imax(0, MD(ncon_max) - ncon);
+      dropped += imax(0, nkeep - room); ncon += imin(nkeep, room);
+      SYNC();
+      if (lane == 0) task[8 * gs + 5] = have + nkeep;
+      SYNC();
+      hits &= ~same;
+    }
+#endif
+  }
+  SYNC();
 }
 
 DEV_NOINLINE void collide_plane(const ModelDev& m, float* ws, int g, int& ncon, int& dropped, int lane) {
@@ -844,12 +1210,12 @@ DEV_NOINLINE void collide_plane(const ModelDev& m, float* ws, int g, int& ncon, 
       float bv = -INFINITY; int best = 0x7fffffff;
       NOUNROLL for (int i = lane; i < G.nvert; i += LANES) {
         if (i == taken[0] || i == taken[1] || i == taken[2]) continue;
-        float z = G.mat[6] * LDG(G.verts + 3 * i) + G.mat[7] * LDG(G.verts + 3 * i + 1) + G.mat[8] * LDG(G.verts + 3 * i + 2);
+        float z = G.mat[6] * LDGB(G.verts + 3 * i) + G.mat[7] * LDGB(G.verts + 3 * i + 1) + G.mat[8] * LDGB(G.verts + 3 * i + 2);
         if (-z > bv) { bv = -z; best = i; }
       }
       wargmax(bv, best);
       if (best == 0x7fffffff) break;
-      float lv[3] = {LDG(G.verts + 3 * best), LDG(G.verts + 3 * best + 1), LDG(G.verts + 3 * best + 2)}, w[3], p[3];
+      float lv[3] = {LDGB(G.verts + 3 * best), LDGB(G.verts + 3 * best + 1), LDGB(G.verts + 3 * best + 2)}, w[3], p[3];
       m3mulv(w, G.mat, lv);
       float dist = G.pos[2] + w[2];
       if (dist > 0.f) break;
@@ -1173,7 +1539,7 @@ DEV_NOINLINE float newton_direction(const ModelDev& m, float* ws, int ncon, int 
     H[idx] = h;
   }
   SYNC();
-  chol_factor(H, WS(W_INVD), nv, lane);
+  chol_factor(H, WS(W_INVD), nv, lane, m.tri);
   chol_solve(H, WS(W_INVD), WS(W_TMPV), WS(W_BUF), WS(W_SEARCH), nv, lane);
   return gn;
 }
@@ -1262,12 +1628,13 @@ DEV_NOINLINE int forward(const ModelDev& m, float* ws, int& ncon_out, int& dropp
     const float* M = WS(W_M);
     FOR_LANE(i, nv * nv) A[i] = M[i];
     SYNC();
-    chol_factor(A, WS(W_INVD), nv, lane);
+    chol_factor(A, WS(W_INVD), nv, lane, m.tri);
   }
   PH_MARK(PH_KIN);
   BSYNC(bsync);
   if (active) {           // ---- phase 2: collision
-    NOUNROLL for (int g = 0; g < MD(ngeom); ++g) { if (MD(ground_type) == 1) collide_hfield(m, ws, g, ncon, dropped, lane); else collide_plane(m, ws, g, ncon, dropped, lane); }
+    if (MD(ground_type) == 1) collide_hfield_all(m, ws, ncon, dropped, lane);
+    else { NOUNROLL for (int g = 0; g < MD(ngeom); ++g) collide_plane(m, ws, g, ncon, dropped, lane); }
     SYNC();
   }
   PH_MARK(PH_COLLIDE);
@@ -1336,7 +1703,7 @@ DEV_NOINLINE int substep(const ModelDev& m, float* ws, int& ncon, int& dropped, 
     FOR_LANE(i, nv * nv) { const int r = i / nv, c = i - r * nv; A[i] = M[i] + (r == c ? dt * LDG(m.dof_damping + r) : 0.f); }
     FOR_LANE(k, nv) WS(W_TMPV)[k] = WS(W_FSMOOTH)[k] + WS(W_FCON)[k];
     SYNC();
-    chol_factor(A, WS(W_INVD), nv, lane);
+    chol_factor(A, WS(W_INVD), nv, lane, m.tri);
     chol_solve(A, WS(W_INVD), WS(W_TMPV), WS(W_BUF), WS(W_GRAD), nv, lane);
     float* qvel = WS(W_QVEL); float* qpos = WS(W_QPOS);
     FOR_LANE(k, nv) qvel[k] += dt * WS(W_GRAD)[k];
@@ -1400,7 +1767,7 @@ DEV_NOINLINE float hfield_height(const ModelDev& m, float x, float y, int* cell)
   c = imin(imax(c, 0), ncol - 2); r = imin(imax(r, 0), nrow - 2);
   const float u = (x - (dx * (float)c - sx)) / dx, v = (y - (dy * (float)r - sy)) / dy;
   const float* h = m.hfield_data + (size_t)r * ncol + c;
-  const float z00 = LDG(h) * sz, z10 = LDG(h + 1) * sz, z01 = LDG(h + ncol) * sz, z11 = LDG(h + ncol + 1) * sz;
+  const float z00 = LDGB(h) * sz, z10 = LDGB(h + 1) * sz, z01 = LDGB(h + ncol) * sz, z11 = LDGB(h + ncol + 1) * sz;
   float z; int tri;
   if (u >= v) { tri = 0; z = z00 + u * (z10 - z00) + v * (z11 - z10); }
   else { tri = 1; z = z00 + v * (z01 - z00) + u * (z11 - z01); }

@@ -35,7 +35,22 @@ template <class V> static const V* push(const Uploader& u, const std::vector<V>&
   return (const V*)u.up(u.ctx, v.data(), v.size() * sizeof(V));
 }
 
+// Small read-only tables (body tree, joints, dofs, actuators, geoms, observation layout ...) are packed into ONE arena:
+// a CUDA kernel copies it to shared memory in its prologue and re-points the ModelDev fields listed in `slot_*`
+// at the copy, so table look-ups are shared-memory reads instead of dependent L2 round trips.
+struct Arena {
+  std::vector<uint8_t> bytes;
+  std::vector<std::pair<size_t, size_t>> slots;       // (byte offset of the pointer field in ModelDev, byte offset in the arena)
+  template <class V> void add(ModelDev& m, const V*& field, const std::vector<V>& v) {
+    const size_t off = (bytes.size() + 15) & ~(size_t)15, n = v.size() * sizeof(V);
+    bytes.resize(off + (n < 16 ? 16 : n), 0);
+    if (n) memcpy(bytes.data() + off, v.data(), n);
+    slots.push_back({(size_t)((const char*)&field - (const char*)&m), off});
+  }
+};
+
 static inline void build_model(const void* blob, size_t nbytes, uint64_t seed, uint32_t env_offset, const Uploader& u, ModelDev& m) {
+  Arena arena;
   if (nbytes < 8 || memcmp(blob, "CSB1", 4) != 0) throw std::runtime_error("model blob: bad magic");
   memset(&m, 0, sizeof(m));
   std::vector<int> dims = section<int>(blob, "dims");
@@ -45,8 +60,8 @@ static inline void build_model(const void* blob, size_t nbytes, uint64_t seed, u
   const int nb = m.dims[CD_nbody], nv = m.dims[CD_nv], njnt = m.dims[CD_njnt];
   if (nv > 31) throw std::runtime_error("engine supports nv <= 31 (dof masks are 32-bit)");
 
-#define FSEC(field, name) m.field = push(u, section<float>(blob, name))
-#define ISEC(field, name) m.field = push(u, section<int>(blob, name))
+#define FSEC(field, name) arena.add(m, m.field, section<float>(blob, name))
+#define ISEC(field, name) arena.add(m, m.field, section<int>(blob, name))
   std::vector<int> body_parent = section<int>(blob, "body_parent"), body_jntadr = section<int>(blob, "body_jntadr"),
                    body_jntnum = section<int>(blob, "body_jntnum"), body_dofadr = section<int>(blob, "body_dofadr"),
                    body_dofnum = section<int>(blob, "body_dofnum"), dof_parent = section<int>(blob, "dof_parent"),
@@ -78,15 +93,15 @@ static inline void build_model(const void* blob, size_t nbytes, uint64_t seed, u
   for (int i = 0; i < nv; ++i) for (int j = i; j >= 0; j = dof_parent[j]) { mi.push_back(i); mj.push_back(j); }
   m.nmpair = (int)mi.size();
 
-  m.body_parent = push(u, body_parent); m.body_jnt = push(u, body_jnt); m.body_dofadr = push(u, body_dofadr); m.body_dofnum = push(u, body_dofnum);
-  m.body_subsize = push(u, subsize); m.body_dofmask = push(u, dofmask);
-  m.level_start = push(u, level_start); m.level_body = push(u, level_body);
-  m.mpair_i = push(u, mi); m.mpair_j = push(u, mj);
+  arena.add(m, m.body_parent, body_parent); arena.add(m, m.body_jnt, body_jnt); arena.add(m, m.body_dofadr, body_dofadr); arena.add(m, m.body_dofnum, body_dofnum);
+  arena.add(m, m.body_subsize, subsize); arena.add(m, m.body_dofmask, dofmask);
+  arena.add(m, m.level_start, level_start); arena.add(m, m.level_body, level_body);
+  arena.add(m, m.mpair_i, mi); arena.add(m, m.mpair_j, mj);
   FSEC(body_pos, "body_pos"); FSEC(body_quat, "body_quat"); FSEC(body_ipos, "body_ipos"); FSEC(body_inertia, "body_inertia"); FSEC(body_mass, "body_mass");
   ISEC(jnt_type, "jnt_type"); ISEC(jnt_body, "jnt_body"); ISEC(jnt_qposadr, "jnt_qposadr"); ISEC(jnt_dofadr, "jnt_dofadr");
   ISEC(jnt_limited, "jnt_limited"); ISEC(jnt_actfrclimited, "jnt_actfrclimited");
   FSEC(jnt_pos, "jnt_pos"); FSEC(jnt_axis, "jnt_axis"); FSEC(jnt_range, "jnt_range"); FSEC(jnt_actfrcrange, "jnt_actfrcrange");
-  m.dof_body = push(u, dof_body); ISEC(dof_jnt, "dof_jnt"); m.dof_parent = push(u, dof_parent); ISEC(dof_fl_random, "dof_fl_random");
+  arena.add(m, m.dof_body, dof_body); ISEC(dof_jnt, "dof_jnt"); arena.add(m, m.dof_parent, dof_parent); ISEC(dof_fl_random, "dof_fl_random");
   FSEC(dof_armature, "dof_armature"); FSEC(dof_damping, "dof_damping"); FSEC(dof_frictionloss, "dof_frictionloss");
   FSEC(qpos0, "qpos0");
   ISEC(act_dof, "act_dof"); ISEC(act_qadr, "act_qadr"); ISEC(act_mode, "act_mode"); ISEC(act_ctrllimited, "act_ctrllimited");
@@ -95,7 +110,27 @@ static inline void build_model(const void* blob, size_t nbytes, uint64_t seed, u
   ISEC(geom_type, "geom_type"); ISEC(geom_body, "geom_body"); ISEC(geom_vadr, "geom_vadr"); ISEC(geom_vnum, "geom_vnum"); ISEC(geom_fr_random, "geom_fr_random");
   FSEC(geom_size, "geom_size"); FSEC(geom_pos, "geom_pos"); FSEC(geom_quat, "geom_quat"); FSEC(geom_friction, "geom_friction");
   FSEC(geom_center, "geom_center"); FSEC(geom_rbound, "geom_rbound");
-  FSEC(hull_verts, "hull_verts"); FSEC(hfield_data, "hfield_data");
+  m.hull_verts = push(u, section<float>(blob, "hull_verts")); m.hfield_data = push(u, section<float>(blob, "hfield_data"));     // big: stay in global memory
+  { // support maps: candidate (x, y, z, index) quadruples per direction bucket
+    std::vector<int> supadr = section<int>(blob, "geom_supadr"), sup_off = section<int>(blob, "sup_off"), sup_idx = section<int>(blob, "sup_idx");
+    std::vector<int> gtype = section<int>(blob, "geom_type"), vadr = section<int>(blob, "geom_vadr");
+    std::vector<float> hv = section<float>(blob, "hull_verts");
+    std::vector<float> cand(4 * (sup_idx.size() > 0 ? sup_idx.size() : 1), 0.f);
+    for (size_t g = 0; g < supadr.size(); ++g) {
+      if (supadr[g] < 0) continue;
+      for (int k = sup_off[supadr[g]]; k < sup_off[supadr[g] + 6 * 8 * 8]; ++k) {
+        const int vi = sup_idx[k];
+        for (int c = 0; c < 3; ++c) cand[4 * (size_t)k + c] = hv[3 * (size_t)(vadr[g] + vi) + c];
+        memcpy(&cand[4 * (size_t)k + 3], &vi, 4);
+      }
+    }
+    arena.add(m, m.geom_supadr, supadr); m.sup_off = push(u, sup_off); m.sup_cand = (const float4*)push(u, cand);
+  }
+  { // Cholesky pair table
+    std::vector<int> tri;
+    for (int k = nv - 1; k >= 0; --k) for (int i = k; i < nv; ++i) tri.push_back((i << 8) | k);
+    arena.add(m, m.tri, tri);
+  }
   { std::vector<float> gf = section<float>(blob, "ground_friction"); for (int i = 0; i < 4; ++i) m.ground_friction[i] = i < (int)gf.size() ? gf[i] : 0.f; }
   ISEC(eq_body1, "eq_body1"); ISEC(eq_body2, "eq_body2");
   FSEC(eq_anchor1, "eq_anchor1"); FSEC(eq_anchor2, "eq_anchor2"); FSEC(eq_solref, "eq_solref"); FSEC(eq_solimp, "eq_solimp");
@@ -132,10 +167,21 @@ static inline void build_model(const void* blob, size_t nbytes, uint64_t seed, u
   size[W_CN_POS] = 3 * nc; size[W_CN_FRAME] = 9 * nc; size[W_CN_DIST] = nc; size[W_CN_MU] = nc; size[W_CN_BODY] = nc; size[W_CN_GEOM] = nc;
   size[W_CN_CELL] = nc; size[W_CN_D] = nc; size[W_CN_AREF] = 4 * nc; size[W_CN_J] = 3 * nc * nv; size[W_CN_F] = 3 * nc; size[W_CN_X] = 4 * nc; size[W_CN_V] = 4 * nc;
   size[W_EQ_J] = 3 * neq * nv; size[W_EQ_D] = size[W_EQ_AREF] = size[W_EQ_X] = size[W_EQ_V] = size[W_EQ_F] = 3 * neq;
-  size[W_SENS] = 12; size[W_RAW] = nraw; size[W_ACT] = nu; size[W_FILT] = nu; size[W_KP] = nu; size[W_KD] = nu;
+  size[W_SENS] = 12; size[W_RAW] = nraw; size[W_ACT] = nu; size[W_FILT] = nu; size[W_KP] = nu; size[W_KD] = nu; size[W_GTASK] = 8 * ng;
   int o = 0;
   for (int i = 0; i < W__COUNT; ++i) { m.off[i] = o; o += (size[i] + 3) & ~3; }
   m.ws_floats = o;
+  // upload the arena and point the fields at it; CTA-shared area in front of the per-warp workspaces: [ModelDev copy | arena copy]
+  if (arena.slots.size() > sizeof(m.slot_field) / sizeof(m.slot_field[0])) throw std::runtime_error("too many model tables for ModelDev::slot_field");
+  arena.bytes.resize((arena.bytes.size() + 15) & ~(size_t)15, 0);
+  if (arena.bytes.size() / 16 > 65535) throw std::runtime_error("model table arena too large");
+  const uint8_t* dev = (const uint8_t*)u.up(u.ctx, arena.bytes.data(), arena.bytes.size());
+  m.arena_g = dev; m.arena_bytes = (int)arena.bytes.size(); m.nslots = (int)arena.slots.size();
+  for (size_t i = 0; i < arena.slots.size(); ++i) {
+    *(const uint8_t**)((char*)&m + arena.slots[i].first) = dev + arena.slots[i].second;
+    m.slot_field[i] = (uint16_t)arena.slots[i].first; m.slot_off16[i] = (uint16_t)(arena.slots[i].second / 16);
+  }
+  m.shared_floats = (int)((sizeof(ModelDev) + 15) / 16 * 4) + m.arena_bytes / 4;
 }
 
 // per-env arrays: sizes in elements per env
