@@ -306,3 +306,31 @@ def test_full_size_properties():
         outs.append(s.clone())
         env.close()
     assert torch.equal(outs[0], outs[1])
+
+
+@pytest.mark.parametrize("name", ["flamingo_p_v3__rocky_hard__hm", "flamingo_light_v1__flat__freq", "humanoid_p_v0__slope_hard__poscmd"])
+def test_engine_replays_reference_python_golden(name):
+    """tests/golden/*.npz were recorded by the reference's own Python env stack (tools/gen_golden.py).  Replay through the
+    CUDA engine, teacher-forced from the oracle (which reproduces the fixture exactly, tests/test_golden.py)."""
+    import json, os
+    from cosim_b200.envs import BatchedEnv
+    from oracle.oracle import Oracle
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", name + ".npz"), allow_pickle=False)
+    cfg = json.loads(str(z["config_json"])); cfg["random"]["sensor_noise"] = "zero"
+    env = BatchedEnv(cfg, 1, seed=0)
+    orc = Oracle(env.model, 1, seed=0)
+    orc.reset(); s, _ = env.reset()
+    np.testing.assert_allclose(s.cpu().numpy()[0], z["reset_state"], atol=1e-5)
+    worst = 0.0
+    for k in range(len(z["states"])):
+        for f in ("qpos", "qvel", "qacc_warmstart"):
+            env.set(f, orc.get(f))
+        env.applied_command = torch.tensor(z["applied"][k][None, :], dtype=torch.float32, device="cuda")
+        env.user_command = env.applied_command
+        s, term, trunc, info = env.step(z["actions"][k][None, :])
+        orc.step(z["actions"][k][None, :], z["applied"][k][None, :])
+        np.testing.assert_allclose(info["torque"].cpu().numpy()[0], z["torque"][k], atol=2e-3, rtol=1e-5)
+        assert bool(term[0]) == bool(z["terminated"][k]) and bool(trunc[0]) == bool(z["truncated"][k])
+        worst = max(worst, float(np.abs(s.cpu().numpy()[0] - z["states"][k]).max()))
+    assert worst < 2e-2, f"state differs from the reference-python golden by {worst:.2e}"
+    env.close()
