@@ -88,8 +88,10 @@ enum { PH_KIN = 0, PH_COLLIDE, PH_CONSTRAINT, PH_SMOOTH, PH_NEWTON, PH_INTEGRATE
 // SM's instruction caches hold ONE phase's code at a time instead of a dozen unrelated program counters (profiles/)
 #ifdef COSIM_HOST_EMU
 #define BSYNC(on) ((void)0)
+#define BSYNC_IF(on, bit) ((void)0)
 #else
 #define BSYNC(on) do { if (on) __syncthreads(); } while (0)
+#define BSYNC_IF(on, bit) do { if ((on) && ((m.bsync_mask >> (bit)) & 1)) __syncthreads(); } while (0)
 #endif
 
 DEV int imax(int a, int b) { return a > b ? a : b; }
@@ -152,6 +154,7 @@ struct ModelDev {
   int off[80]; int ws_floats;
   uint32_t seed_lo, seed_hi, env_offset;
   unsigned long long* phase;      // [PH__COUNT] cycle counters, profiling builds only (else NULL)
+  int bsync_mask;                 // which of the CTA-wide phase barriers of forward() are enabled (bit 0 .. 3)
 };
 #define MD(name) (m.dims[CD_##name])
 #define MO(name) (m.opts[CO_##name])
@@ -893,14 +896,19 @@ DEV_NOINLINE void support_lane(const GeomL& G, float dx, float dy, float dz, flo
     const int bk = support_bucket(ld);
     const int o0 = LDGB(G.sup_off + bk), o1 = LDGB(G.sup_off + bk + 1);
     float bv = -INFINITY;
-    NOUNROLL for (int k = o0; k < o1; ++k) {
+    NOUNROLL for (int k = o0; k < o1; k += 4) {       // four independent 16-byte loads in flight; a clamped duplicate never wins (strict >)
+      const int k1 = imin(k + 1, o1 - 1), k2 = imin(k + 2, o1 - 1), k3 = imin(k + 3, o1 - 1);
 #ifdef COSIM_HOST_EMU
-      const float4 c = G.sup_cand[k];
+      const float4 c0 = G.sup_cand[k], c1 = G.sup_cand[k1], c2 = G.sup_cand[k2], c3 = G.sup_cand[k3];
 #else
-      const float4 c = __ldg(G.sup_cand + k);
+      const float4 c0 = __ldg(G.sup_cand + k), c1 = __ldg(G.sup_cand + k1), c2 = __ldg(G.sup_cand + k2), c3 = __ldg(G.sup_cand + k3);
 #endif
-      const float v = c.x * l0 + c.y * l1 + c.z * l2;
-      if (v > bv) { bv = v; px = c.x; py = c.y; pz = c.z; }
+      const float v0 = c0.x * l0 + c0.y * l1 + c0.z * l2, v1 = c1.x * l0 + c1.y * l1 + c1.z * l2;
+      const float v2 = c2.x * l0 + c2.y * l1 + c2.z * l2, v3 = c3.x * l0 + c3.y * l1 + c3.z * l2;
+      if (v0 > bv) { bv = v0; px = c0.x; py = c0.y; pz = c0.z; }
+      if (v1 > bv) { bv = v1; px = c1.x; py = c1.y; pz = c1.z; }
+      if (v2 > bv) { bv = v2; px = c2.x; py = c2.y; pz = c2.z; }
+      if (v3 > bv) { bv = v3; px = c3.x; py = c3.y; pz = c3.z; }
     }
   } else {
     float bv = -INFINITY;
@@ -1509,12 +1517,44 @@ DEV_NOINLINE float linesearch(const ModelDev& m, const float* ws, int ncon, floa
 }
 
 // grad = Ma - qfrc_smooth - qfrc_constraint; H = M + J' D_quad J; search = -H^-1 grad.  Returns |grad|.
-DEV_NOINLINE float newton_direction(const ModelDev& m, float* ws, int ncon, int lane) {
+// signature of the set of rows in their quadratic zone (the only thing besides M the Hessian depends on)
+DEV uint32_t wxor(uint32_t v) {
+#ifndef COSIM_HOST_EMU
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v ^= __shfl_xor_sync(0xffffffffu, v, o);
+#endif
+  return v;
+}
+DEV uint32_t active_set_signature(const ModelDev& m, const float* ws, int ncon, int lane) {
+  const int nv = MD(nv), njnt = MD(njnt);
+  const float* qacc = WS(W_QACC);
+  uint32_t h = 0;
+  NOUNROLL for (int idx = lane; idx < 4 * ncon; idx += LANES) if (WS(W_CN_X)[idx] < 0.f) h ^= (uint32_t)(idx + 1) * 2654435761u;
+  FOR_LANE(k, nv) {
+    const float D = WS(W_FR_D)[k];
+    if (D > 0.f) { const float x = WS(W_TMPW)[k], Rf = WS(W_FLOSS)[k] / D; if (x > -Rf && x < Rf) h ^= (uint32_t)(k + 1001) * 2246822519u; }
+  }
+  FOR_LANE(j, njnt) {
+    const float sg = WS(W_LM_SIGN)[j];
+    if (sg != 0.f && (sg * qacc[m.jnt_dofadr[j]] - WS(W_LM_AREF)[j]) < 0.f) h ^= (uint32_t)(j + 2001) * 3266489917u;
+  }
+  return wxor(h) | 1u;       // never 0: 0 means "no factor yet"
+}
+// `sig` carries the signature of the factor currently held in W_A: when the active set did not change since the previous
+// iteration the Hessian is the same matrix and only the triangular solves are repeated
+DEV_NOINLINE float newton_direction(const ModelDev& m, float* ws, int ncon, int lane, uint32_t& sig) {
   const int nv = MD(nv), neq = MD(neq);
   float* grad = WS(W_GRAD); float* H = WS(W_A); const float* M = WS(W_M); const float* qacc = WS(W_QACC); const float* Ma = WS(W_MA);
   float gn = 0.f;
   FOR_LANE(k, nv) { const float g = Ma[k] - WS(W_FSMOOTH)[k] - WS(W_FCON)[k]; grad[k] = g; gn += g * g; WS(W_TMPV)[k] = -g; }
   gn = sqrtf(wsum(gn));
+  const uint32_t now = active_set_signature(m, ws, ncon, lane);
+  if (now == sig) {
+    SYNC();
+    chol_solve(H, WS(W_INVD), WS(W_TMPV), WS(W_BUF), WS(W_SEARCH), nv, lane);
+    return gn;
+  }
+  sig = now;
   NOUNROLL for (int idx = lane; idx < nv * nv; idx += LANES) {
     const int i = idx / nv, j = idx - i * nv;
     if (j > i) continue;
@@ -1559,7 +1599,8 @@ DEV_NOINLINE int newton_solve(const ModelDev& m, float* ws, int ncon, int has_ro
   const float scale = 1.f / (WS(W_SCAL)[1] * (float)imax(1, nv));
   const float tol = MO(tolerance);
   const int maxiter = MD(iterations);
-  (void)newton_direction(m, ws, ncon, lane);
+  uint32_t sig = 0;
+  (void)newton_direction(m, ws, ncon, lane, sig);
   int iter = 0;
   while (iter < maxiter) {
     mat_vec(M, search, Mv, nv, lane);
@@ -1586,7 +1627,7 @@ DEV_NOINLINE int newton_solve(const ModelDev& m, float* ws, int ncon, int has_ro
     float g = 0.f;
     FOR_LANE(k, nv) g += (Ma[k] - WS(W_FSMOOTH)[k]) * (qacc[k] - WS(W_ASMOOTH)[k]);
     cost = update_forces(m, ws, ncon, lane) + 0.5f * wsum(g);
-    const float gn = newton_direction(m, ws, ncon, lane);
+    const float gn = newton_direction(m, ws, ncon, lane, sig);
     ++iter;
     if (scale * (old - cost) < tol || scale * gn < tol) break;
   }
@@ -1631,14 +1672,14 @@ DEV_NOINLINE int forward(const ModelDev& m, float* ws, int& ncon_out, int& dropp
     chol_factor(A, WS(W_INVD), nv, lane, m.tri);
   }
   PH_MARK(PH_KIN);
-  BSYNC(bsync);
+  BSYNC_IF(bsync, 0);
   if (active) {           // ---- phase 2: collision
     if (MD(ground_type) == 1) collide_hfield_all(m, ws, ncon, dropped, lane);
     else { NOUNROLL for (int g = 0; g < MD(ngeom); ++g) collide_plane(m, ws, g, ncon, dropped, lane); }
     SYNC();
   }
   PH_MARK(PH_COLLIDE);
-  BSYNC(bsync);
+  BSYNC_IF(bsync, 1);
   if (active) {           // ---- phase 3: constraint rows, sensors, smooth forces and acceleration
     com_vel(m, ws, lane);
     make_constraint(m, ws, ncon, lane);
@@ -1666,13 +1707,13 @@ DEV_NOINLINE int forward(const ModelDev& m, float* ws, int& ncon_out, int& dropp
     { int r = 0; FOR_LANE(k, nv) r |= (WS(W_FR_D)[k] > 0.f); FOR_LANE(j, njnt) r |= (WS(W_LM_SIGN)[j] != 0.f); rows |= wor(r); }
   }
   PH_MARK(PH_SMOOTH);
-  BSYNC(bsync);
+  BSYNC_IF(bsync, 2);
   if (active) {           // ---- phase 4: constraint solve
     iters = newton_solve(m, ws, ncon, rows, lane);
     PH_COUNT(PH_NEWTON_ITERS, iters);
   }
   PH_MARK(PH_NEWTON);
-  BSYNC(bsync);
+  BSYNC_IF(bsync, 3);
   ncon_out = ncon; dropped_out = dropped;
   return iters;
 }
