@@ -36,7 +36,7 @@ def workload_config():
     et, _ = load_tables()
     non_stacked = list(et[ROBOT]["non_stacked_obs_order"]) + ["height_map"]
     return make_config(ROBOT, TERRAIN, random=RANDOM_FULL, non_stacked_obs_order=non_stacked,
-                       engine={"auto_reset": True, "seed": 0xC051})
+                       engine={"auto_reset": True, "seed": 0xC051, "ncon_max": 16})
 
 
 def measured_peaks():
@@ -239,7 +239,7 @@ def main():
                         "kernel": "k_step", "kernel_ms": kernel_ms, "bytes_per_env_step": B_ALG, "peak_source": peak_src,
                         "note": "the step is bound by the FP32 pipe / shared-memory latency, not HBM (DESIGN.md section 5)"},
            "reporter_stats": {k: stats[k] for k in ("steps", "episodes", "success_rate", "termination_rate", "mean_abs_err_lin_vel_x",
-                                                    "mean_abs_err_ang_vel_yaw", "mean_contacts", "mean_solver_iters_per_step", "nan_resets")}}
+                                                    "mean_abs_err_ang_vel_yaw", "mean_contacts", "mean_solver_iters_per_step", "nan_resets", "ncon_dropped")}}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         v, cores, dt = cpu_reference(cfg, args.cpu_envs, 3, 1)
         out["cpu_baseline"] = {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port",

@@ -35,23 +35,23 @@ extern __shared__ __align__(16) float g_smem[];
   float* ws = g_smem + m.shared_floats + (size_t)warp * m.ws_floats;
 #define ENV_PROLOGUE() CTA_PROLOGUE() if (env >= E.N) return;
 
-__global__ void __launch_bounds__(512, 1) k_init(const __grid_constant__ ModelDev mp, const EnvArrays E) {
+__global__ void __launch_bounds__(640, 1) k_init(const __grid_constant__ ModelDev mp, const EnvArrays E) {
   ENV_PROLOGUE();
   init_env(m, E, env, ws, lane);
 }
-__global__ void __launch_bounds__(512, 1) k_reset(const __grid_constant__ ModelDev mp, const EnvArrays E, const StepArgs a) {
+__global__ void __launch_bounds__(640, 1) k_reset(const __grid_constant__ ModelDev mp, const EnvArrays E, const StepArgs a) {
   ENV_PROLOGUE();
   if (a.mask && !a.mask[env]) return;
   const int cd = MD(command_dim);
   reset_env(m, E, env, ws, a.command ? a.command + (size_t)env * cd : nullptr, a.state_out + (size_t)env * MD(state_dim), lane);
 }
 // k_step: every warp of the CTA (also the padding warps of the last CTA) walks through the phase barriers
-__global__ void __launch_bounds__(512, 1) k_step(const __grid_constant__ ModelDev mp, const EnvArrays E, const StepArgs a) {
+__global__ void __launch_bounds__(640, 1) k_step(const __grid_constant__ ModelDev mp, const EnvArrays E, const StepArgs a) {
   CTA_PROLOGUE();
   const int have_env = env < E.N;
   step_env(m, E, have_env ? env : 0, ws, a, lane, have_env, 1);
 }
-__global__ void __launch_bounds__(512, 1) k_substep(const __grid_constant__ ModelDev mp, const EnvArrays E) {
+__global__ void __launch_bounds__(640, 1) k_substep(const __grid_constant__ ModelDev mp, const EnvArrays E) {
   ENV_PROLOGUE();
   substep_env(m, E, env, ws, lane);
 }
@@ -137,10 +137,12 @@ int cosim_create(const void* blob, size_t nbytes, int num_envs, int device, uint
   }
   // launch geometry: as many env-warps per block as fit comfortably; blocks co-reside up to the 227 KB/SM limit
   const size_t per = (size_t)h->m.ws_floats * sizeof(float);
-  // one CTA per SM with as many env-warps as its shared memory holds (<= 16): the warps of a CTA move through the
+  // one CTA per SM with as many env-warps as its shared memory holds (<= 20): the warps of a CTA move through the
   // phases of a sub-step together (block barriers in k_step), which keeps the instruction working set per SM small
-  int wpb = 16;
-  while (wpb > 1 && per * wpb + h->m.shared_floats * sizeof(float) > 200 * 1024) --wpb;
+  int wpb = 20; size_t budget = 200 * 1024;         // tuning overrides (experiments): COSIM_MAX_WPB, COSIM_SMEM_KB
+  { const char* e = getenv("COSIM_MAX_WPB"); if (e && atoi(e) >= 1 && atoi(e) <= 20) wpb = atoi(e); }
+  { const char* e = getenv("COSIM_SMEM_KB"); if (e && atoi(e) >= 16 && atoi(e) <= 227) budget = (size_t)atoi(e) * 1024; }
+  while (wpb > 1 && per * wpb + h->m.shared_floats * sizeof(float) > budget) --wpb;
   if (num_envs < wpb * 148) { wpb = (num_envs + 147) / 148; if (wpb < 1) wpb = 1; }      // small batches: spread over the SMs
   if (per * wpb > 227 * 1024) { fprintf(stderr, "cosim_create: workspace %zu B/env exceeds shared memory\n", per); for (void* p : h->allocs) cudaFree(p); delete h; return COSIM_ERR_MODEL; }
   h->wpb = wpb; h->smem = per * wpb + h->m.shared_floats * sizeof(float);

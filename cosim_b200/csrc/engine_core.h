@@ -419,49 +419,56 @@ DEV_NOINLINE void crb(const ModelDev& m, float* ws, int lane) {
   SYNC();
 }
 
-// dense Cholesky of the n x n SPD matrix in A (lower triangle used, overwritten by L below the
-// diagonal; the diagonal keeps L_jj^2 and 1/L_jj goes to invd).  The trailing update of column j runs over the
-// flat list of (i, k) pairs `tri` (n must be the nv the table was built for), 32 pairs per pass.
+// dense Cholesky of the n x n SPD matrix in A (lower triangle).  The factor is kept UNSCALED: after the call
+// A[i][j] (i > j) holds L_ij * L_jj and invd[j] = 1 / L_jj, so L_ij = A[i][j] * invd[j]; chol_solve folds the scaling
+// into its pivots.  That drops the column-scaling pass and one warp barrier per column.  The trailing update of
+// column j runs over the flat list of (i, k) pairs `tri` (n must be the nv the table was built for), 32 pairs per pass.
 DEV_NOINLINE void chol_factor(float* A, float* invd, int n, int lane, const int* tri) {
   NOUNROLL for (int j = 0; j < n; ++j) {
-    const float inv = 1.f / sqrtf(fmaxf(A[j * n + j], 1e-30f));
+    const float d = fmaxf(A[j * n + j], 1e-30f);
+#ifdef COSIM_HOST_EMU
+    const float inv = 1.f / sqrtf(d);
+#else
+    const float inv = rsqrtf(d);
+#endif
+    const float inv2 = inv * inv;
     if (lane == 0) invd[j] = inv;
-    NOUNROLL for (int i = j + 1 + lane; i < n; i += LANES) A[i * n + j] *= inv;
-    SYNC();
     const int T = ((n - j - 1) * (n - j)) >> 1;
     NOUNROLL for (int idx = lane; idx < T; idx += LANES) {
       const int t = tri[idx], i = t >> 8, k = t & 255;
-      A[i * n + k] -= A[i * n + j] * A[k * n + j];
+      A[i * n + k] -= A[i * n + j] * A[k * n + j] * inv2;
     }
     SYNC();
   }
 }
-// solves L L^T x = b.  b is destroyed, tmp is scratch, result in out (all length n, distinct)
+// solves L L^T x = b with the unscaled factor of chol_factor.  b is destroyed, tmp is scratch, result in out
 DEV_NOINLINE void chol_solve(const float* A, const float* invd, float* b, float* tmp, float* out, int n, int lane) {
 #ifdef COSIM_HOST_EMU
   for (int i = 0; i < n; ++i) {
-    const float xi = b[i] * invd[i];
-    for (int k = i + 1 + lane; k < n; k += LANES) b[k] -= A[k * n + i] * xi;
+    const float xi = b[i] * invd[i], yi = xi * invd[i];
+    for (int k = i + 1 + lane; k < n; k += LANES) b[k] -= A[k * n + i] * yi;
     if (lane == 0) tmp[i] = xi;
     SYNC();
   }
   for (int i = n - 1; i >= 0; --i) {
     const float xi = tmp[i] * invd[i];
-    for (int k = lane; k < i; k += LANES) tmp[k] -= A[i * n + k] * xi;
+    for (int k = lane; k < i; k += LANES) tmp[k] -= A[i * n + k] * invd[k] * xi;
     if (lane == 0) out[i] = xi;
     SYNC();
   }
 #else
   // n <= 32: lane k keeps element k in a register, the pivot travels by shuffle (same arithmetic as above)
   float bk = lane < n ? b[lane] : 0.f;
+  const float dk = lane < n ? invd[lane] : 0.f;
   NOUNROLL for (int i = 0; i < n; ++i) {
-    const float xi = __shfl_sync(0xffffffffu, bk, i) * invd[i];
-    if (lane > i && lane < n) bk -= A[lane * n + i] * xi;
+    const float di = __shfl_sync(0xffffffffu, dk, i);
+    const float xi = __shfl_sync(0xffffffffu, bk, i) * di;
+    if (lane > i && lane < n) bk -= A[lane * n + i] * (xi * di);
     if (lane == i) bk = xi;
   }
   NOUNROLL for (int i = n - 1; i >= 0; --i) {
-    const float xi = __shfl_sync(0xffffffffu, bk, i) * invd[i];
-    if (lane < i) bk -= A[i * n + lane] * xi;
+    const float xi = __shfl_sync(0xffffffffu, bk, i) * __shfl_sync(0xffffffffu, dk, i);
+    if (lane < i) bk -= A[i * n + lane] * dk * xi;
     if (lane == i) bk = xi;
   }
   if (lane < n) out[lane] = bk;
@@ -870,10 +877,11 @@ DEV_NOINLINE void collide_hfield(const ModelDev& m, float* ws, int g, int& ncon,
 // the whole env in the reference order and gives every prism a lane; each lane runs its own scalar MPR query.  Contacts
 // are appended in task order (ballot prefix), so order, the 50-per-geom cap and the ncon_max cap match the serial loop.
 struct PV { float x, y, z; int pi; };     // Minkowski-difference vertex + index of the prism vertex it came from
-struct GeomL { int type; const float* pos; const float* mat; float sx, sy, sz; const float* verts; int nvert; const int* sup_off; const float4* sup_cand; };
+// sub / gsize / gmask: the lanes [sub = 0 .. gsize) of one group work on the same query and split the candidate scan
+struct GeomL { int type; const float* pos; const float* mat; float sx, sy, sz; const float* verts; int nvert; const int* sup_off; const float4* sup_cand; int sub, gsize; unsigned gmask; };
 
-DEV GeomL make_geom_lane(const ModelDev& m, const float* ws, int g) {
-  GeomL G; G.type = m.geom_type[g]; G.pos = WS(W_GXPOS) + 3 * g; G.mat = WS(W_GXMAT) + 9 * g;
+DEV GeomL make_geom_lane(const ModelDev& m, const float* ws, int g, int sub = 0, int gsize = 1, unsigned gmask = 0xffffffffu) {
+  GeomL G; G.sub = sub; G.gsize = gsize; G.gmask = gmask; G.type = m.geom_type[g]; G.pos = WS(W_GXPOS) + 3 * g; G.mat = WS(W_GXMAT) + 9 * g;
   G.sx = LDG(m.geom_size + 3 * g); G.sy = LDG(m.geom_size + 3 * g + 1); G.sz = LDG(m.geom_size + 3 * g + 2);
   G.verts = m.hull_verts + 3 * m.geom_vadr[g]; G.nvert = m.geom_vnum[g];
   const int sa = m.geom_supadr[g]; G.sup_off = sa >= 0 ? m.sup_off + sa : nullptr; G.sup_cand = m.sup_cand;
@@ -893,11 +901,12 @@ DEV_NOINLINE void support_lane(const GeomL& G, float dx, float dy, float dz, flo
     px = (l0 > 0.f ? 1.f : -1.f) * G.sx; py = (l1 > 0.f ? 1.f : -1.f) * G.sy; pz = (l2 > 0.f ? 1.f : -1.f) * G.sz;
   } else if (G.sup_off) {
     const float ld[3] = {l0, l1, l2};
-    const int bk = support_bucket(ld);
-    const int o0 = LDGB(G.sup_off + bk), o1 = LDGB(G.sup_off + bk + 1);
-    float bv = -INFINITY;
-    NOUNROLL for (int k = o0; k < o1; k += 4) {       // four independent 16-byte loads in flight; a clamped duplicate never wins (strict >)
-      const int k1 = imin(k + 1, o1 - 1), k2 = imin(k + 2, o1 - 1), k3 = imin(k + 3, o1 - 1);
+    const int bucket = support_bucket(ld);
+    const int o0 = LDGB(G.sup_off + bucket), o1 = LDGB(G.sup_off + bucket + 1);
+    float bv = -INFINITY; int bk = 0x7fffffff;
+    const int gs = G.gsize;
+    NOUNROLL for (int k = o0 + G.sub; k < o1; k += 4 * gs) {    // four independent 16-byte loads in flight per lane
+      const int k1 = imin(k + gs, o1 - 1), k2 = imin(k + 2 * gs, o1 - 1), k3 = imin(k + 3 * gs, o1 - 1);
 #ifdef COSIM_HOST_EMU
       const float4 c0 = G.sup_cand[k], c1 = G.sup_cand[k1], c2 = G.sup_cand[k2], c3 = G.sup_cand[k3];
 #else
@@ -905,11 +914,23 @@ DEV_NOINLINE void support_lane(const GeomL& G, float dx, float dy, float dz, flo
 #endif
       const float v0 = c0.x * l0 + c0.y * l1 + c0.z * l2, v1 = c1.x * l0 + c1.y * l1 + c1.z * l2;
       const float v2 = c2.x * l0 + c2.y * l1 + c2.z * l2, v3 = c3.x * l0 + c3.y * l1 + c3.z * l2;
-      if (v0 > bv) { bv = v0; px = c0.x; py = c0.y; pz = c0.z; }
-      if (v1 > bv) { bv = v1; px = c1.x; py = c1.y; pz = c1.z; }
-      if (v2 > bv) { bv = v2; px = c2.x; py = c2.y; pz = c2.z; }
-      if (v3 > bv) { bv = v3; px = c3.x; py = c3.y; pz = c3.z; }
+      // candidates are sorted by vertex index: on equal support the earliest position wins, as in a serial scan
+      if (v0 > bv || (v0 == bv && k < bk)) { bv = v0; bk = k; px = c0.x; py = c0.y; pz = c0.z; }
+      if (v1 > bv || (v1 == bv && k1 < bk)) { bv = v1; bk = k1; px = c1.x; py = c1.y; pz = c1.z; }
+      if (v2 > bv || (v2 == bv && k2 < bk)) { bv = v2; bk = k2; px = c2.x; py = c2.y; pz = c2.z; }
+      if (v3 > bv || (v3 == bv && k3 < bk)) { bv = v3; bk = k3; px = c3.x; py = c3.y; pz = c3.z; }
     }
+#ifndef COSIM_HOST_EMU
+    if (gs > 1) {        // reduce over the lanes of the group, then fetch the winner's coordinates
+      const int mine = bk;
+      NOUNROLL for (int o = gs >> 1; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(G.gmask, bv, o); const int ok = __shfl_xor_sync(G.gmask, bk, o);
+        if (ov > bv || (ov == bv && ok < bk)) { bv = ov; bk = ok; }
+      }
+      const int src = __ffs(__ballot_sync(G.gmask, mine == bk)) - 1;
+      px = __shfl_sync(G.gmask, px, src); py = __shfl_sync(G.gmask, py, src); pz = __shfl_sync(G.gmask, pz, src);
+    }
+#endif
   } else {
     float bv = -INFINITY;
     NOUNROLL for (int i = 0; i < G.nvert; ++i) {
@@ -1063,30 +1084,40 @@ DEV_NOINLINE void collide_hfield_all(const ModelDev& m, float* ws, int& ncon, in
   const float sx = MO(hf_sx), sy = MO(hf_sy), sz = MO(hf_sz), base = MO(hf_base);
   const float dx = 2.f * sx / (float)(ncol - 1), dy = 2.f * sy / (float)(nrow - 1);
   int* task = WSI(W_GTASK);
-  // ---- stage 1: one lane per geom
-  FOR_LANE(g, ng) {
+  // ---- stage 1: one group of gs1 lanes per geom (gs1 = largest power of two with ng * gs1 <= LANES)
+  int gs1 = 1;
+#ifndef COSIM_HOST_EMU
+  while (gs1 < 8 && ng * gs1 * 2 <= LANES) gs1 <<= 1;
+#endif
+  const int sub1 = lane & (gs1 - 1);
+  const unsigned gmask1 = gs1 >= LANES ? 0xffffffffu : (((1u << gs1) - 1u) << (lane & ~(gs1 - 1)));
+  NOUNROLL for (int g = lane / gs1; g < ng; g += LANES / gs1) {
     int* tk = task + 8 * g;
-    tk[0] = tk[1] = tk[2] = tk[3] = tk[4] = tk[5] = 0;
-    const GeomL G = make_geom_lane(m, ws, g);
+    if (sub1 == 0) { tk[0] = tk[1] = tk[2] = tk[3] = tk[4] = tk[5] = 0; }
+    const GeomL G = make_geom_lane(m, ws, g, sub1, gs1, gmask1);
     const float cl[3] = {LDG(m.geom_center + 3 * g), LDG(m.geom_center + 3 * g + 1), LDG(m.geom_center + 3 * g + 2)};
     float pos[3]; m3mulv(pos, G.mat, cl); v3add(pos, G.pos, pos);
     const float rb = LDG(m.geom_rbound + g);
     if (pos[0] - rb > sx || pos[0] + rb < -sx || pos[1] - rb > sy || pos[1] + rb < -sy) continue;
     if (pos[2] - rb > sz || pos[2] + rb < -base) continue;
-    {  // conservative early-out (does not change results): highest terrain vertex under the bounding sphere
+    float hmax = INFINITY;
+    {  // conservative early-outs (do not change results): highest terrain vertex under the bounding sphere
       const int c0 = imax(0, (int)floorf((pos[0] - rb + sx) / dx)), c1 = imin(ncol - 1, (int)ceilf((pos[0] + rb + sx) / dx));
       const int r0 = imax(0, (int)floorf((pos[1] - rb + sy) / dy)), r1 = imin(nrow - 1, (int)ceilf((pos[1] + rb + sy) / dy));
       const int w = c1 - c0 + 1, cnt = w * (r1 - r0 + 1);
       if (cnt <= 64) {
-        float hmax = -INFINITY;
+        hmax = -INFINITY;
         NOUNROLL for (int t = 0; t < cnt; ++t) hmax = fmaxf(hmax, LDGB(m.hfield_data + (size_t)(r0 + t / w) * ncol + c0 + t % w));
-        if (pos[2] - rb > hmax * sz) continue;
+        hmax *= sz;
+        if (pos[2] - rb > hmax) continue;
       }
     }
     float xmin[3], xmax[3], s[3];
+    support_lane(G, 0.f, 0.f, -1.f, s); xmin[2] = s[2];
+    if (xmin[2] > hmax) continue;         // the geom's lowest point clears every terrain vertex it could reach: no contact
     support_lane(G, 1.f, 0.f, 0.f, s); xmax[0] = s[0]; support_lane(G, -1.f, 0.f, 0.f, s); xmin[0] = s[0];
     support_lane(G, 0.f, 1.f, 0.f, s); xmax[1] = s[1]; support_lane(G, 0.f, -1.f, 0.f, s); xmin[1] = s[1];
-    support_lane(G, 0.f, 0.f, 1.f, s); xmax[2] = s[2]; support_lane(G, 0.f, 0.f, -1.f, s); xmin[2] = s[2];
+    support_lane(G, 0.f, 0.f, 1.f, s); xmax[2] = s[2];
     if (xmin[0] > sx || xmax[0] < -sx || xmin[1] > sy || xmax[1] < -sy || xmin[2] > sz || xmax[2] < -base) continue;
     int cmin = (int)floorf((xmin[0] + sx) / (2.f * sx) * (float)(ncol - 1));
     int cmax = (int)ceilf((xmax[0] + sx) / (2.f * sx) * (float)(ncol - 1));
@@ -1094,17 +1125,23 @@ DEV_NOINLINE void collide_hfield_all(const ModelDev& m, float* ws, int& ncon, in
     int rmax = (int)ceilf((xmax[1] + sy) / (2.f * sy) * (float)(nrow - 1));
     cmin = imax(0, cmin); rmin = imax(0, rmin); cmax = imin(ncol - 1, cmax); rmax = imin(nrow - 1, rmax);
     if (cmax <= cmin || rmax <= rmin) continue;
-    tk[0] = cmin; tk[1] = rmin; tk[2] = cmax - cmin; tk[3] = rmax - rmin;
-    ((float*)tk)[6] = xmin[2];
+    if (sub1 == 0) { tk[0] = cmin; tk[1] = rmin; tk[2] = cmax - cmin; tk[3] = rmax - rmin; ((float*)tk)[6] = xmin[2]; }
   }
   SYNC();
   // ---- prefix of task counts (ngeom <= 32 is not required: serial scan by every lane over <= ngeom entries)
   int T = 0;
   NOUNROLL for (int g = 0; g < ng; ++g) { const int n = 2 * task[8 * g + 2] * task[8 * g + 3]; if (lane == 0) task[8 * g + 4] = T; T += n; }
   SYNC();
-  // ---- stage 2: one lane per prism, chunks of LANES tasks in reference order
-  NOUNROLL for (int t0 = 0; t0 < T; t0 += LANES) {
-    const int t = t0 + lane;
+  // ---- stage 2: one group of gs2 lanes per prism (few prisms: wide groups share the candidate scans), chunks of
+  //      LANES / gs2 tasks in reference order
+  int gs2 = 1;
+#ifndef COSIM_HOST_EMU
+  gs2 = T <= 4 ? 8 : (T <= 8 ? 4 : (T <= 16 ? 2 : 1));
+#endif
+  const int sub2 = lane & (gs2 - 1);
+  const unsigned gmask2 = ((gs2 >= 32 ? 0u : (1u << gs2)) - 1u) << (lane & ~(gs2 - 1));
+  NOUNROLL for (int t0 = 0; t0 < T; t0 += LANES / gs2) {
+    const int t = t0 + lane / gs2;
     int hit = 0, g = 0, cell = -1; float depth = 0.f, nrm[3] = {0.f, 0.f, 0.f}, cp[3] = {0.f, 0.f, 0.f};
     if (t < T) {
       NOUNROLL for (int k = 1; k < ng; ++k) if (task[8 * k + 4] <= t && task[8 * k + 2] * task[8 * k + 3] > 0) g = k;
@@ -1121,12 +1158,11 @@ DEV_NOINLINE void collide_hfield_all(const ModelDev& m, float* ws, int& ncon, in
         P.x[2] = dx * (float)cc - sx; P.y[2] = dy * (float)rc - sy; P.z[2] = LDGB(m.hfield_data + (size_t)rc * ncol + cc) * sz;
         const float zmin = ((const float*)tk)[6];
         if (!(P.z[0] < zmin && P.z[1] < zmin && P.z[2] < zmin)) {
-          const GeomL G = make_geom_lane(m, ws, g);
+          const GeomL G = make_geom_lane(m, ws, g, sub2, gs2, gmask2);
           const float cl[3] = {LDG(m.geom_center + 3 * g), LDG(m.geom_center + 3 * g + 1), LDG(m.geom_center + 3 * g + 2)};
           float gc[3]; m3mulv(gc, G.mat, cl); v3add(gc, G.pos, gc);
-          PH_COUNT(PH_MPR_CALLS, 0);
           if (mpr_lane(m, P, G, gc, &depth, nrm, cp) == 0 && !(nrm[0] == 0.f && nrm[1] == 0.f && nrm[2] == 0.f) && depth == depth) {
-            hit = 1; cell = ((r * ncol + (c - 1)) << 1) | i;
+            hit = (sub2 == 0); cell = ((r * ncol + (c - 1)) << 1) | i;       // one lane per group reports the contact
           }
         }
       }

@@ -9,6 +9,7 @@
 #include <vector>
 #include <stdexcept>
 #include <stdlib.h>
+#include <algorithm>
 #include "engine_core.h"
 
 struct Uploader {
@@ -169,9 +170,25 @@ static inline void build_model(const void* blob, size_t nbytes, uint64_t seed, u
   size[W_CN_POS] = 3 * nc; size[W_CN_FRAME] = 9 * nc; size[W_CN_DIST] = nc; size[W_CN_MU] = nc; size[W_CN_BODY] = nc; size[W_CN_GEOM] = nc;
   size[W_CN_CELL] = nc; size[W_CN_D] = nc; size[W_CN_AREF] = 4 * nc; size[W_CN_J] = 3 * nc * nv; size[W_CN_F] = 3 * nc; size[W_CN_X] = 4 * nc; size[W_CN_V] = 4 * nc;
   size[W_EQ_J] = 3 * neq * nv; size[W_EQ_D] = size[W_EQ_AREF] = size[W_EQ_X] = size[W_EQ_V] = size[W_EQ_F] = 3 * neq;
-  size[W_SENS] = 12; size[W_RAW] = nraw; size[W_ACT] = nu; size[W_FILT] = nu; size[W_KP] = nu; size[W_KD] = nu; size[W_GTASK] = 8 * ng;
+  size[W_SENS] = 12; size[W_RAW] = nraw; size[W_ACT] = nu; size[W_FILT] = 0; size[W_KP] = nu; size[W_KD] = nu; size[W_GTASK] = 8 * ng;
+  // Lay the fields out back to back, then overlay fields whose lifetimes never overlap (shared memory per env bounds
+  // how many env-warps an SM holds, and the step is latency-bound, so every KB counts):
+  //   W_CRB    (only inside crb(), phase 1)            over  W_CVEL + W_CACC   (written from com_vel on, phase 3)
+  //   W_BUF    (crb() scratch; host-emulation solves)  over  W_CDOFDOT         (com_vel .. rne_bias, phase 3)
+  //   W_RAW    (observation build, after the sub-steps) over  W_CN_J           (dead after the last solve)
+  //   W_GTASK  (collision task table, phase 2)         over  W_CN_X + W_CN_V   (written by the solver, phase 4)
+  auto pad4 = [](int n) { return (n + 3) & ~3; };
   int o = 0;
-  for (int i = 0; i < W__COUNT; ++i) { m.off[i] = o; o += (size[i] + 3) & ~3; }
+  bool placed[W__COUNT];
+  for (int i = 0; i < W__COUNT; ++i) placed[i] = false;
+  auto place = [&](int f, int at) { m.off[f] = at; placed[f] = true; };
+  { const int n = std::max(pad4(size[W_CRB]), pad4(size[W_CVEL]) + pad4(size[W_CACC]));
+    place(W_CRB, o); place(W_CVEL, o); place(W_CACC, o + pad4(size[W_CVEL])); o += n; }
+  { const int n = std::max(pad4(size[W_BUF]), pad4(size[W_CDOFDOT])); place(W_BUF, o); place(W_CDOFDOT, o); o += n; }
+  { const int n = std::max(pad4(size[W_RAW]), pad4(size[W_CN_J])); place(W_RAW, o); place(W_CN_J, o); o += n; }
+  { const int n = std::max(pad4(size[W_GTASK]), pad4(size[W_CN_X]) + pad4(size[W_CN_V]));
+    place(W_GTASK, o); place(W_CN_X, o); place(W_CN_V, o + pad4(size[W_CN_X])); o += n; }
+  for (int i = 0; i < W__COUNT; ++i) if (!placed[i]) { m.off[i] = o; o += pad4(size[i]); }
   m.ws_floats = o;
   // upload the arena and point the fields at it; CTA-shared area in front of the per-warp workspaces: [ModelDev copy | arena copy]
   if (arena.slots.size() > sizeof(m.slot_field) / sizeof(m.slot_field[0])) throw std::runtime_error("too many model tables for ModelDev::slot_field");
