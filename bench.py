@@ -131,7 +131,8 @@ def main():
     ap.add_argument("--envs", type=int, default=65536, help="environments per GPU")
     ap.add_argument("--impl", default="cosim_b200", choices=["cosim_b200", "reference"])
     ap.add_argument("--ref-envs", type=int, default=256)
-    ap.add_argument("--cpu-envs", type=int, default=128)
+    ap.add_argument("--cpu-envs", type=int, default=512)
+    ap.add_argument("--cpu-steps", type=int, default=20)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -241,9 +242,10 @@ def main():
            "reporter_stats": {k: stats[k] for k in ("steps", "episodes", "success_rate", "termination_rate", "mean_abs_err_lin_vel_x",
                                                     "mean_abs_err_ang_vel_yaw", "mean_contacts", "mean_solver_iters_per_step", "nan_resets", "ncon_dropped")}}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, cores, dt = cpu_reference(cfg, args.cpu_envs, 3, 1)
+        v, cores, dt = cpu_reference(cfg, args.cpu_envs, args.cpu_steps, 2)
         out["cpu_baseline"] = {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port",
-                               "sample": f"{args.cpu_envs} envs x 3 control steps of the same workload, {dt:.1f} s (fp64 C++ restatement, not MuJoCo)"}
+                               "sample": f"{args.cpu_envs} envs x {args.cpu_steps} control steps of the same workload after 2 warm-up steps, {dt:.1f} s wall on {cores} threads "
+                                         "(fp64 C++ restatement of the reference path, OpenMP over envs; not MuJoCo itself)"}
     if rank == 0:
         print(json.dumps(out), flush=True)
     env.close(); pol.close()

@@ -139,7 +139,7 @@ int cosim_create(const void* blob, size_t nbytes, int num_envs, int device, uint
   const size_t per = (size_t)h->m.ws_floats * sizeof(float);
   // one CTA per SM with as many env-warps as its shared memory holds (<= 20): the warps of a CTA move through the
   // phases of a sub-step together (block barriers in k_step), which keeps the instruction working set per SM small
-  int wpb = 20; size_t budget = 200 * 1024;         // tuning overrides (experiments): COSIM_MAX_WPB, COSIM_SMEM_KB
+  int wpb = 20; size_t budget = 224 * 1024;         // tuning overrides (experiments): COSIM_MAX_WPB, COSIM_SMEM_KB
   { const char* e = getenv("COSIM_MAX_WPB"); if (e && atoi(e) >= 1 && atoi(e) <= 20) wpb = atoi(e); }
   { const char* e = getenv("COSIM_SMEM_KB"); if (e && atoi(e) >= 16 && atoi(e) <= 227) budget = (size_t)atoi(e) * 1024; }
   while (wpb > 1 && per * wpb + h->m.shared_floats * sizeof(float) > budget) --wpb;
