@@ -1591,17 +1591,24 @@ DEV_NOINLINE float newton_direction(const ModelDev& m, float* ws, int ncon, int 
     return gn;
   }
   sig = now;
-  NOUNROLL for (int idx = lane; idx < nv * nv; idx += LANES) {
-    const int i = idx / nv, j = idx - i * nv;
-    if (j > i) continue;
-    float h = M[idx];
+  // per-contact 3x3 weight of the frame Jacobian (sum over the active pyramid edges), once per contact: W_CN_V is free here
+  float* cw = WS(W_CN_V);
+  NOUNROLL for (int c = lane; c < ncon; c += LANES) {
+    const float* X = WS(W_CN_X) + 4 * c;
+    const float s0 = X[0] < 0.f, s1 = X[1] < 0.f, s2 = X[2] < 0.f, s3 = X[3] < 0.f;
+    const float D = WS(W_CN_D)[c], mu = WS(W_CN_MU)[c];
+    cw[4 * c] = D * (s0 + s1 + s2 + s3); cw[4 * c + 1] = D * mu * (s0 - s1); cw[4 * c + 2] = D * mu * (s2 - s3); cw[4 * c + 3] = D * mu * mu * (s0 + s1);
+  }
+  SYNC();
+  const int npair = (nv * (nv + 1)) >> 1;
+  NOUNROLL for (int idx = lane; idx < npair; idx += LANES) {          // lower triangle only, one (i, j <= i) pair per lane
+    const int t = m.tri[idx], i = t >> 8, j = t & 255;
+    float h = M[i * nv + j];
     NOUNROLL for (int c = 0; c < ncon; ++c) {
-      const float* X = WS(W_CN_X) + 4 * c;
-      const float s0 = X[0] < 0.f, s1 = X[1] < 0.f, s2 = X[2] < 0.f, s3 = X[3] < 0.f;
-      if (s0 + s1 + s2 + s3 == 0.f) continue;
-      const float D = WS(W_CN_D)[c], mu = WS(W_CN_MU)[c];
+      const float gnn = cw[4 * c];
+      if (gnn == 0.f) continue;
+      const float gn1 = cw[4 * c + 1], gn2 = cw[4 * c + 2], g11 = cw[4 * c + 3], mu = WS(W_CN_MU)[c], g22 = mu * mu * gnn - g11;
       const float* J = WS(W_CN_J) + (size_t)3 * c * nv;
-      const float gnn = D * (s0 + s1 + s2 + s3), gn1 = D * mu * (s0 - s1), gn2 = D * mu * (s2 - s3), g11 = D * mu * mu * (s0 + s1), g22 = D * mu * mu * (s2 + s3);
       const float jn = J[j], j1 = J[nv + j], j2 = J[2 * nv + j];
       h += J[i] * (gnn * jn + gn1 * j1 + gn2 * j2) + J[nv + i] * (gn1 * jn + g11 * j1) + J[2 * nv + i] * (gn2 * jn + g22 * j2);
     }
@@ -1612,7 +1619,7 @@ DEV_NOINLINE float newton_direction(const ModelDev& m, float* ws, int ncon, int 
       const int jn_ = m.dof_jnt[i]; const float sg = WS(W_LM_SIGN)[jn_];
       if (sg != 0.f && m.jnt_dofadr[jn_] == i && (sg * qacc[i] - WS(W_LM_AREF)[jn_]) < 0.f) h += WS(W_LM_D)[jn_];
     }
-    H[idx] = h;
+    H[i * nv + j] = h;
   }
   SYNC();
   chol_factor(H, WS(W_INVD), nv, lane, m.tri);
