@@ -301,10 +301,7 @@ int cosim_phase_cycles(cosim_handle* h, unsigned long long* out_host, int reset)
 #ifdef COSIM_PHASE_TIMING
   CK(cudaDeviceSynchronize());
   CK(cudaMemcpy(out_host, h->m.phase, PH__COUNT * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
-  unsigned long long v = 0;
-  CK(cudaMemcpyFromSymbol(&v, g_support_calls, sizeof(v))); out_host[PH_SUPPORT_CALLS] = v;
-  CK(cudaMemcpyFromSymbol(&v, g_mpr_calls, sizeof(v))); out_host[PH_MPR_CALLS] = v;
-  if (reset) { CK(cudaMemset(h->m.phase, 0, PH__COUNT * sizeof(unsigned long long))); v = 0; CK(cudaMemcpyToSymbol(g_support_calls, &v, sizeof(v))); CK(cudaMemcpyToSymbol(g_mpr_calls, &v, sizeof(v))); }
+  if (reset) CK(cudaMemset(h->m.phase, 0, PH__COUNT * sizeof(unsigned long long)));
 #endif
   return COSIM_OK;
 }

@@ -588,52 +588,6 @@ DEV GeomW make_geom(const ModelDev& m, const float* ws, int g) {
   m3mulv(r, G.mat, c); v3add(G.center, G.pos, r);
   return G;
 }
-// support point in world direction dir; warp-cooperative for meshes (all lanes return the same point)
-DEV_NOINLINE void support(const GeomW& G, const float* dir, float* out, int lane) {
-  float ld[3]; m3tmulv(ld, G.mat, dir);
-  float lp[3] = {0.f, 0.f, 0.f};
-  if (G.type == GEOM_SPHERE) { v3scl(lp, ld, G.size[0]); }
-  else if (G.type == GEOM_CYLINDER) {
-    float n = sqrtf(ld[0] * ld[0] + ld[1] * ld[1]);
-    if (n > MINVALF) { lp[0] = ld[0] / n * G.size[0]; lp[1] = ld[1] / n * G.size[0]; }
-    lp[2] = (ld[2] > 0.f ? 1.f : (ld[2] < 0.f ? -1.f : 0.f)) * G.size[1];
-  } else if (G.type == GEOM_BOX) {
-    lp[0] = (ld[0] > 0.f ? 1.f : -1.f) * G.size[0]; lp[1] = (ld[1] > 0.f ? 1.f : -1.f) * G.size[1]; lp[2] = (ld[2] > 0.f ? 1.f : -1.f) * G.size[2];
-  } else if (G.sup_off) {   // mesh with a support map: scan only the candidates of the direction's bucket
-    const int bk = support_bucket(ld);
-    const int o0 = LDGB(G.sup_off + bk), o1 = LDGB(G.sup_off + bk + 1);
-    float bv = -INFINITY; int best = 0x7fffffff; float bx = 0.f, by = 0.f, bz = 0.f;
-    NOUNROLL for (int k = o0 + lane; k < o1; k += LANES) {
-#ifdef COSIM_HOST_EMU
-      const float4 c = G.sup_cand[k];
-#else
-      const float4 c = __ldg(G.sup_cand + k);
-#endif
-      const float v = c.x * ld[0] + c.y * ld[1] + c.z * ld[2];
-      if (v > bv) { bv = v; best = __float_as_int(c.w); bx = c.x; by = c.y; bz = c.z; }     // candidates are sorted by vertex index
-    }
-#ifndef COSIM_HOST_EMU
-    { const int mine = best; wargmax(bv, best);
-      const int src = __ffs(__ballot_sync(0xffffffffu, mine == best)) - 1;
-      bx = __shfl_sync(0xffffffffu, bx, src); by = __shfl_sync(0xffffffffu, by, src); bz = __shfl_sync(0xffffffffu, bz, src); }
-#endif
-    lp[0] = bx; lp[1] = by; lp[2] = bz;
-  } else {   // mesh without a map: lanes stride all hull vertices
-    float bv = -INFINITY; int best = 0x7fffffff;
-    NOUNROLL for (int i = lane; i < G.nvert; i += LANES) {
-      float v = LDGB(G.verts + 3 * i) * ld[0] + LDGB(G.verts + 3 * i + 1) * ld[1] + LDGB(G.verts + 3 * i + 2) * ld[2];
-      if (v > bv) { bv = v; best = i; }
-    }
-    wargmax(bv, best);
-    lp[0] = LDGB(G.verts + 3 * best); lp[1] = LDGB(G.verts + 3 * best + 1); lp[2] = LDGB(G.verts + 3 * best + 2);
-  }
-  float r[3]; m3mulv(r, G.mat, lp); v3add(out, G.pos, r);
-}
-
-struct Sup { float v[3], v1[3], v2[3]; };
-#if defined(COSIM_PHASE_TIMING) && !defined(COSIM_HOST_EMU)
-__device__ unsigned long long g_support_calls = 0, g_mpr_calls = 0;
-#endif
 // libccd's degenerate-case guards use CCD_EPS = DBL_EPSILON (MuJoCo builds it in double).  They are
 // ABSOLUTE thresholds, so the fp32 engine keeps the double value: with FLT_EPSILON the guards fire on
 // ordinary millimetre-scale portal triangles and the contact normal degenerates.
@@ -646,32 +600,6 @@ DEV bool f_eq(float a, float b) {
   return ab < CCD_EPS * (bb > aa ? bb : aa);
 }
 DEV bool v3eq0(const float* a) { return f_eq(a[0], 0.f) && f_eq(a[1], 0.f) && f_eq(a[2], 0.f); }
-DEV_NOINLINE void mink_support(const float (*P)[3], const GeomW& G, const float* dir, Sup& s, int lane) {
-#if defined(COSIM_PHASE_TIMING) && !defined(COSIM_HOST_EMU)
-  if (lane == 0) atomicAdd(&g_support_calls, 1ull);
-#endif
-  int best = 0; float bv = v3dot(P[0], dir);
-#pragma unroll
-  for (int i = 1; i < 6; ++i) { float v = v3dot(P[i], dir); if (v > bv) { bv = v; best = i; } }
-  v3copy(s.v1, P[best]);
-  float nd[3] = {-dir[0], -dir[1], -dir[2]};
-  support(G, nd, s.v2, lane);
-  v3sub(s.v, s.v1, s.v2);
-}
-DEV void portal_dir(const Sup* p, float* dir) {
-  float a[3], b[3]; v3sub(a, p[2].v, p[1].v); v3sub(b, p[3].v, p[1].v); v3cross(dir, a, b); v3normalize(dir);
-}
-DEV_NOINLINE void expand_portal(Sup* p, const Sup& v4) {
-  float v4v0[3]; v3cross(v4v0, v4.v, p[0].v);
-  float dot = v3dot(p[1].v, v4v0);
-  if (dot > 0.f) { dot = v3dot(p[2].v, v4v0); if (dot > 0.f) p[1] = v4; else p[3] = v4; }
-  else { dot = v3dot(p[3].v, v4v0); if (dot > 0.f) p[2] = v4; else p[1] = v4; }
-}
-DEV bool reach_tol(const Sup* p, const Sup& v4, const float* dir, float tol) {
-  float dv1 = v3dot(p[1].v, dir), dv2 = v3dot(p[2].v, dir), dv3 = v3dot(p[3].v, dir), dv4 = v3dot(v4.v, dir);
-  float dm = fminf(dv4 - dv1, fminf(dv4 - dv2, dv4 - dv3));
-  return f_eq(dm, tol) || dm < tol;
-}
 DEV float seg_dist2(const float* A, const float* B, float* wit) {
   float dd[3]; v3sub(dd, B, A);
   float tt = -v3dot(A, dd) / v3dot(dd, dd);
@@ -693,102 +621,6 @@ DEV_NOINLINE float point_tri_dist2(const float* x0, const float* B, const float*
   }
   return dist;
 }
-DEV_NOINLINE void find_pos(const Sup* p, float* pos) {
-  float dir[3]; portal_dir(p, dir);
-  float b[4], vec[3];
-  v3cross(vec, p[1].v, p[2].v); b[0] = v3dot(vec, p[3].v);
-  v3cross(vec, p[3].v, p[2].v); b[1] = v3dot(vec, p[0].v);
-  v3cross(vec, p[0].v, p[1].v); b[2] = v3dot(vec, p[3].v);
-  v3cross(vec, p[2].v, p[1].v); b[3] = v3dot(vec, p[0].v);
-  float sum = b[0] + b[1] + b[2] + b[3];
-  if (f_is_zero(sum) || sum < 0.f) {
-    b[0] = 0.f;
-    v3cross(vec, p[2].v, p[3].v); b[1] = v3dot(vec, dir);
-    v3cross(vec, p[3].v, p[1].v); b[2] = v3dot(vec, dir);
-    v3cross(vec, p[1].v, p[2].v); b[3] = v3dot(vec, dir);
-    sum = b[1] + b[2] + b[3];
-  }
-  float inv = 1.f / sum, p1[3] = {0.f, 0.f, 0.f}, p2[3] = {0.f, 0.f, 0.f};
-#pragma unroll
-  for (int i = 0; i < 4; ++i) { v3addscl(p1, p1, p[i].v1, b[i]); v3addscl(p2, p2, p[i].v2, b[i]); }
-#pragma unroll
-  for (int k = 0; k < 3; ++k) pos[k] = (p1[k] * inv + p2[k] * inv) * 0.5f;
-}
-// MPR penetration query (libccd ccdMPRPenetration as driven by mjc_ConvexHField); 0 = hit
-DEV_NOINLINE int mpr_penetration(const ModelDev& m, const float (*P)[3], const GeomW& G, float* depth, float* dir_out, float* pos, int lane) {
-  const float tol = MO(ccd_tolerance); const int maxit = MD(ccd_iterations);
-#if defined(COSIM_PHASE_TIMING) && !defined(COSIM_HOST_EMU)
-  if (lane == 0) atomicAdd(&g_mpr_calls, 1ull);
-#endif
-  Sup p[4];
-  float c1[3] = {0.f, 0.f, 0.f};
-#pragma unroll
-  for (int i = 0; i < 6; ++i) v3add(c1, c1, P[i]);
-  v3scl(c1, c1, 1.f / 6.f);
-  v3copy(p[0].v1, c1); v3copy(p[0].v2, G.center); v3sub(p[0].v, c1, G.center);
-  if (v3eq0(p[0].v)) p[0].v[0] += CCD_EPS * 10.f;
-  float dir[3] = {-p[0].v[0], -p[0].v[1], -p[0].v[2]}; v3normalize(dir);
-  mink_support(P, G, dir, p[1], lane);
-  float dot = v3dot(p[1].v, dir);
-  if (f_is_zero(dot) || dot < 0.f) return -1;
-  v3cross(dir, p[0].v, p[1].v);
-  if (f_is_zero(v3dot(dir, dir))) {
-    if (v3eq0(p[1].v)) { *depth = 0.f; dir_out[0] = dir_out[1] = dir_out[2] = 0.f; for (int k = 0; k < 3; ++k) pos[k] = (p[1].v1[k] + p[1].v2[k]) * 0.5f; return 0; }
-    for (int k = 0; k < 3; ++k) pos[k] = (p[1].v1[k] + p[1].v2[k]) * 0.5f;
-    *depth = v3norm(p[1].v); v3copy(dir_out, p[1].v); v3normalize(dir_out); return 0;
-  }
-  v3normalize(dir);
-  mink_support(P, G, dir, p[2], lane);
-  dot = v3dot(p[2].v, dir);
-  if (f_is_zero(dot) || dot < 0.f) return -1;
-  float va[3], vb[3];
-  v3sub(va, p[1].v, p[0].v); v3sub(vb, p[2].v, p[0].v); v3cross(dir, va, vb); v3normalize(dir);
-  dot = v3dot(dir, p[0].v);
-  if (dot > 0.f) { Sup t = p[1]; p[1] = p[2]; p[2] = t; v3scl(dir, dir, -1.f); }
-  int size = 3, guard = 0;
-  while (size < 4) {
-    if (++guard > 100) return -1;
-    mink_support(P, G, dir, p[3], lane);
-    dot = v3dot(p[3].v, dir);
-    if (f_is_zero(dot) || dot < 0.f) return -1;
-    int cont = 0;
-    v3cross(va, p[1].v, p[3].v); dot = v3dot(va, p[0].v);
-    if (dot < 0.f && !f_is_zero(dot)) { p[2] = p[3]; cont = 1; }
-    if (!cont) {
-      v3cross(va, p[3].v, p[2].v); dot = v3dot(va, p[0].v);
-      if (dot < 0.f && !f_is_zero(dot)) { p[1] = p[3]; cont = 1; }
-    }
-    if (cont) { v3sub(va, p[1].v, p[0].v); v3sub(vb, p[2].v, p[0].v); v3cross(dir, va, vb); v3normalize(dir); }
-    else size = 4;
-  }
-  guard = 0;
-  while (true) {
-    if (++guard > 1000) return -1;
-    portal_dir(p, dir);
-    dot = v3dot(dir, p[1].v);
-    if (f_is_zero(dot) || dot > 0.f) break;
-    Sup v4; mink_support(P, G, dir, v4, lane);
-    dot = v3dot(v4.v, dir);
-    if (!(f_is_zero(dot) || dot > 0.f) || reach_tol(p, v4, dir, tol)) return -1;
-    expand_portal(p, v4);
-  }
-  int it = 0;
-  while (true) {
-    portal_dir(p, dir);
-    Sup v4; mink_support(P, G, dir, v4, lane);
-    if (reach_tol(p, v4, dir, tol) || it > maxit) {
-      float wit[3];
-      float d2 = point_tri_dist2(p[1].v, p[2].v, p[3].v, wit);
-      *depth = sqrtf(d2);
-      if (f_is_zero(*depth)) { dir_out[0] = dir_out[1] = dir_out[2] = 0.f; } else { v3copy(dir_out, wit); v3normalize(dir_out); }
-      find_pos(p, pos);
-      return 0;
-    }
-    expand_portal(p, v4);
-    ++it;
-  }
-}
-
 DEV void make_frame(float* frame) {
   float* n = frame; float* t1 = frame + 3; float* t2 = frame + 6;
   v3normalize(n);
@@ -811,77 +643,17 @@ DEV_NOINLINE void add_contact(const ModelDev& m, float* ws, int& ncon, int& drop
   ++ncon;
 }
 
-DEV_NOINLINE void collide_hfield(const ModelDev& m, float* ws, int g, int& ncon, int& dropped, int lane) {
-  const GeomW G = make_geom(m, ws, g);
-  const int nrow = MD(hf_nrow), ncol = MD(hf_ncol);
-  const float sx = MO(hf_sx), sy = MO(hf_sy), sz = MO(hf_sz), base = MO(hf_base);
-  const float rb = LDG(m.geom_rbound + g);
-  const float* pos = G.center;
-  if (pos[0] - rb > sx || pos[0] + rb < -sx || pos[1] - rb > sy || pos[1] + rb < -sy) return;
-  if (pos[2] - rb > sz || pos[2] + rb < -base) return;
-  const float dx = 2.f * sx / (float)(ncol - 1), dy = 2.f * sy / (float)(nrow - 1);
-  {  // conservative early-out (does not change results): highest terrain vertex under the bounding sphere
-    int c0 = imax(0, (int)floorf((pos[0] - rb + sx) / dx)), c1 = imin(ncol - 1, (int)ceilf((pos[0] + rb + sx) / dx));
-    int r0 = imax(0, (int)floorf((pos[1] - rb + sy) / dy)), r1 = imin(nrow - 1, (int)ceilf((pos[1] + rb + sy) / dy));
-    const int w = c1 - c0 + 1, cnt = w * (r1 - r0 + 1);
-    if (cnt <= 256) {
-      float hmax = -INFINITY;
-      NOUNROLL for (int t = lane; t < cnt; t += LANES) hmax = fmaxf(hmax, LDGB(m.hfield_data + (size_t)(r0 + t / w) * ncol + c0 + t % w));
-      hmax = wmaxf(hmax) * sz;
-      if (pos[2] - rb > hmax) return;
-    }
-  }
-  float xmin[3], xmax[3];
-#pragma unroll
-  for (int i = 0; i < 3; ++i) {
-    float dir[3] = {0.f, 0.f, 0.f}, s[3];
-    dir[i] = 1.f; support(G, dir, s, lane); xmax[i] = s[i];
-    dir[i] = -1.f; support(G, dir, s, lane); xmin[i] = s[i];
-  }
-  if (xmin[0] > sx || xmax[0] < -sx || xmin[1] > sy || xmax[1] < -sy || xmin[2] > sz || xmax[2] < -base) return;
-  int cmin = (int)floorf((xmin[0] + sx) / (2.f * sx) * (float)(ncol - 1));
-  int cmax = (int)ceilf((xmax[0] + sx) / (2.f * sx) * (float)(ncol - 1));
-  int rmin = (int)floorf((xmin[1] + sy) / (2.f * sy) * (float)(nrow - 1));
-  int rmax = (int)ceilf((xmax[1] + sy) / (2.f * sy) * (float)(nrow - 1));
-  cmin = imax(0, cmin); rmin = imax(0, rmin); cmax = imin(ncol - 1, cmax); rmax = imin(nrow - 1, rmax);
-  int cnt = 0;
-  float P[6][3];
-  NOUNROLL for (int r = rmin; r < rmax; ++r) {
-    int nvert = 0;
-    NOUNROLL for (int c = cmin; c <= cmax; ++c) {
-      NOUNROLL for (int i = 0; i < 2; ++i) {
-#pragma unroll
-        for (int k = 0; k < 3; ++k) { P[0][k] = P[1][k]; P[1][k] = P[2][k]; P[3][k] = P[4][k]; P[4][k] = P[5][k]; }
-        const float x = dx * (float)c - sx, y = dy * (float)(r + i) - sy;
-        P[2][0] = P[5][0] = x; P[2][1] = P[5][1] = y;
-        P[2][2] = -base; P[5][2] = LDGB(m.hfield_data + (size_t)(r + i) * ncol + c) * sz;
-        ++nvert;
-        if (nvert > 2) {
-          if (P[3][2] < xmin[2] && P[4][2] < xmin[2] && P[5][2] < xmin[2]) continue;
-          float depth, dir[3], cp[3];
-          if (mpr_penetration(m, P, G, &depth, dir, cp, lane) == 0) {
-            if (dir[0] == 0.f && dir[1] == 0.f && dir[2] == 0.f) continue;
-            if (!(depth == depth)) continue;
-            add_contact(m, ws, ncon, dropped, cp, dir, -depth, g, ((r * ncol + (c - 1)) << 1) | i, lane);
-            if (++cnt >= 50) return;
-          }
-        }
-      }
-    }
-  }
-}
-
 // ------------------------------------------------------------------------------------------ lane-parallel hfield collision
-// Same results as collide_hfield above (mjc_ConvexHField restated), different schedule: stage 1 gives every geom a lane
+// mjc_ConvexHField restated (oracle/oracle.hpp collide_hfield is the serial version), different schedule: stage 1 gives every geom a lane
 // (bounding tests, AABB from 6 support queries, sub-grid), stage 2 enumerates the (geom, row, col, triangle) prisms of
 // the whole env in the reference order and gives every prism a lane; each lane runs its own scalar MPR query.  Contacts
 // are appended in task order (ballot prefix), so order, the 50-per-geom cap and the ncon_max cap match the serial loop.
 struct PV { float x, y, z; int pi; };     // Minkowski-difference vertex + index of the prism vertex it came from
 // sub / gsize / gmask: the lanes [sub = 0 .. gsize) of one group work on the same query and split the candidate scan
-struct GeomL { int type; const float* pos; const float* mat; float sx, sy, sz; const float* verts; int nvert; const int* sup_off; const float4* sup_cand; int sub, gsize; unsigned gmask; };
+struct GeomL { int type; const float* pos; const float* mat; float sx, sy, sz; const float* verts; int nvert; const int* sup_off; const float4* sup_cand; int sub, gsize; unsigned gmask; float ox, oy; };
 
 DEV GeomL make_geom_lane(const ModelDev& m, const float* ws, int g, int sub = 0, int gsize = 1, unsigned gmask = 0xffffffffu) {
-  GeomL G; G.sub = sub; G.gsize = gsize; G.gmask = gmask; G.type = m.geom_type[g]; G.pos = WS(W_GXPOS) + 3 * g; G.mat = WS(W_GXMAT) + 9 * g;
+  GeomL G; G.sub = sub; G.gsize = gsize; G.gmask = gmask; G.ox = 0.f; G.oy = 0.f; G.type = m.geom_type[g]; G.pos = WS(W_GXPOS) + 3 * g; G.mat = WS(W_GXMAT) + 9 * g;
   G.sx = LDG(m.geom_size + 3 * g); G.sy = LDG(m.geom_size + 3 * g + 1); G.sz = LDG(m.geom_size + 3 * g + 2);
   G.verts = m.hull_verts + 3 * m.geom_vadr[g]; G.nvert = m.geom_vnum[g];
   const int sa = m.geom_supadr[g]; G.sup_off = sa >= 0 ? m.sup_off + sa : nullptr; G.sup_cand = m.sup_cand;
@@ -939,8 +711,9 @@ DEV_NOINLINE void support_lane(const GeomL& G, float dx, float dy, float dz, flo
       if (v > bv) { bv = v; px = vx; py = vy; pz = vz; }
     }
   }
-  out[0] = G.pos[0] + (M[0] * px + M[1] * py + M[2] * pz);
-  out[1] = G.pos[1] + (M[3] * px + M[4] * py + M[5] * pz);
+  // (ox, oy): origin of the local frame the query runs in (exact subtraction of nearby numbers)
+  out[0] = (G.pos[0] - G.ox) + (M[0] * px + M[1] * py + M[2] * pz);
+  out[1] = (G.pos[1] - G.oy) + (M[3] * px + M[4] * py + M[5] * pz);
   out[2] = G.pos[2] + (M[6] * px + M[7] * py + M[8] * pz);
 }
 // prism in registers: three columns (x, y, top z), bottoms at -base.  Vertex order as in the strip walk: 0..2 bottoms, 3..5 tops
@@ -983,7 +756,9 @@ DEV void pv_expand(const PV& p0, PV& p1, PV& p2, PV& p3, const PV& v4) {
 }
 // witness points of a portal vertex: v1 on the prism (exact), v2 = v1 - v on the geom
 DEV void pv_witness(const PrismL& P, const PV& p, const float* c1, float* v1) { if (p.pi < 0) v3copy(v1, c1); else prism_vertex(P, p.pi, v1); }
-// scalar MPR penetration query (one lane); 0 = hit.  Control flow identical to mpr_penetration().
+// MPR (XenoCollide) penetration query, restating libccd ccdMPRPenetration as driven by mjc_ConvexHField (oracle/oracle.hpp
+// mpr_penetration is the readable fp64 version); 0 = hit.  Run by one lane, or by a group of lanes in lock step that
+// share the hull support scans (GeomL::gsize).
 DEV_NOINLINE int mpr_lane(const ModelDev& m, const PrismL& P, const GeomL& G, const float* gcenter, float* depth, float* dir_out, float* pos) {
   const float tol = MO(ccd_tolerance); const int maxit = MD(ccd_iterations);
   float c1[3] = {0.f, 0.f, 0.f};
@@ -1152,17 +927,28 @@ DEV_NOINLINE void collide_hfield_all(const ModelDev& m, float* ws, int& ncon, in
         const int r = tk[1] + local / per_row, rem = local % per_row, c = tk[0] + 1 + (rem >> 1), i = rem & 1;
         // strip walk of the reference: triangle i of cell (r, c-1): i = 0 -> (c-1,r) (c-1,r+1) (c,r); i = 1 -> (c-1,r+1) (c,r) (c,r+1)
         const int ca = c - 1, ra = r + i, cb = i ? c : c - 1, rbb = i ? r : r + 1, cc = c, rc = r + i;
+        // The query runs in a frame whose xy origin is the first grid vertex of this geom's sub-grid: far from the world
+        // origin (terrains span +-140 m) fp32 world coordinates resolve ~1e-5 m, ten times the MPR tolerance, while the
+        // local coordinates of prism and geom stay below a few metres.  Only the origin shift is rounded, and it is the
+        // same for both shapes.
+        const float ox = dx * (float)tk[0] - sx, oy = dy * (float)tk[1] - sy;
         PrismL P; P.base = base;
-        P.x[0] = dx * (float)ca - sx; P.y[0] = dy * (float)ra - sy; P.z[0] = LDGB(m.hfield_data + (size_t)ra * ncol + ca) * sz;
-        P.x[1] = dx * (float)cb - sx; P.y[1] = dy * (float)rbb - sy; P.z[1] = LDGB(m.hfield_data + (size_t)rbb * ncol + cb) * sz;
-        P.x[2] = dx * (float)cc - sx; P.y[2] = dy * (float)rc - sy; P.z[2] = LDGB(m.hfield_data + (size_t)rc * ncol + cc) * sz;
+        P.x[0] = dx * (float)(ca - tk[0]); P.y[0] = dy * (float)(ra - tk[1]); P.z[0] = LDGB(m.hfield_data + (size_t)ra * ncol + ca) * sz;
+        P.x[1] = dx * (float)(cb - tk[0]); P.y[1] = dy * (float)(rbb - tk[1]); P.z[1] = LDGB(m.hfield_data + (size_t)rbb * ncol + cb) * sz;
+        P.x[2] = dx * (float)(cc - tk[0]); P.y[2] = dy * (float)(rc - tk[1]); P.z[2] = LDGB(m.hfield_data + (size_t)rc * ncol + cc) * sz;
         const float zmin = ((const float*)tk)[6];
         if (!(P.z[0] < zmin && P.z[1] < zmin && P.z[2] < zmin)) {
-          const GeomL G = make_geom_lane(m, ws, g, sub2, gs2, gmask2);
+          GeomL G = make_geom_lane(m, ws, g, sub2, gs2, gmask2);
+          G.ox = ox; G.oy = oy;
+#if defined(COSIM_PHASE_TIMING) && !defined(COSIM_HOST_EMU)
+          if (sub2 == 0) atomicAdd(m.phase + PH_MPR_CALLS, 1ull);
+#endif
           const float cl[3] = {LDG(m.geom_center + 3 * g), LDG(m.geom_center + 3 * g + 1), LDG(m.geom_center + 3 * g + 2)};
-          float gc[3]; m3mulv(gc, G.mat, cl); v3add(gc, G.pos, gc);
+          float gc[3]; m3mulv(gc, G.mat, cl);
+          gc[0] += G.pos[0] - ox; gc[1] += G.pos[1] - oy; gc[2] += G.pos[2];
           if (mpr_lane(m, P, G, gc, &depth, nrm, cp) == 0 && !(nrm[0] == 0.f && nrm[1] == 0.f && nrm[2] == 0.f) && depth == depth) {
             hit = (sub2 == 0); cell = ((r * ncol + (c - 1)) << 1) | i;       // one lane per group reports the contact
+            cp[0] += ox; cp[1] += oy;
           }
         }
       }

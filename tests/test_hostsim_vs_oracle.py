@@ -79,3 +79,31 @@ def test_push_event():
     h.push([1.0, 0.0, 0.3])
     v = h.get("qvel")[0, :3]
     np.testing.assert_allclose(v, [np.cos(0.8), -np.sin(0.8), 0.3], atol=1e-6)   # robot-frame xy, world z (quirk C-12)
+
+
+def test_far_from_origin_contacts():
+    """+-130 m from the world origin fp32 world coordinates resolve ~1e-5 m; the engine runs hull / prism queries in a
+    local frame, so contact counts still match the fp64 oracle and depths agree to ~1e-6."""
+    m = build_model(make_config("flamingo_p_v3", "rocky_hard", random=RANDOM_NONE))
+    N = 8
+    o, h = Oracle(m, N, seed=1), HostSim(m, N, seed=1)
+    o.reset(); h.reset()
+    rng = np.random.default_rng(3)
+    q = o.get("qpos")
+    q[:, 0] = rng.uniform(-130, 130, N); q[:, 1] = rng.uniform(-130, 130, N); q[:, 2] += 0.3
+    o.set("qpos", q); h.set("qpos", q)
+    depth_err, ncontacts = [], 0
+    for i in range(25):
+        o.step(rng.uniform(-1, 1, (N, 8)))
+        for k in ("qpos", "qvel", "qacc_warmstart", "torque"):
+            h.set(k, o.get(k))
+        o.substep(); h.substep()
+        nco, nch = o.get("ncon")[:, 0].astype(int), h.get("counters")[:, 7]
+        assert (nco == nch).all()
+        for e in range(N):
+            if nco[e]:
+                co = o.contacts(e); ch = h.get("contacts")[e].reshape(-1, 10)[:len(co)]
+                assert (co[:, 8].astype(int) == ch[:, 8].astype(int)).all()
+                depth_err.append(np.abs(co[:, 0] - ch[:, 0])); ncontacts += len(co)
+    depth_err = np.concatenate(depth_err)
+    assert ncontacts > 50 and np.median(depth_err) < 5e-6 and (depth_err > 5e-5).mean() < 0.05
