@@ -649,40 +649,38 @@ DEV_NOINLINE void add_contact(const ModelDev& m, float* ws, int& ncon, int& drop
 // the whole env in the reference order and gives every prism a lane; each lane runs its own scalar MPR query.  Contacts
 // are appended in task order (ballot prefix), so order, the 50-per-geom cap and the ncon_max cap match the serial loop.
 struct PV { float x, y, z; int pi; };     // Minkowski-difference vertex + index of the prism vertex it came from
-// sub / gsize / gmask: the lanes [sub = 0 .. gsize) of one group work on the same query and split the candidate scan
-struct GeomL { int type; const float* pos; const float* mat; float sx, sy, sz; const float* verts; int nvert; const int* sup_off; const float4* sup_cand; int sub, gsize; unsigned gmask; float ox, oy; };
-
-DEV GeomL make_geom_lane(const ModelDev& m, const float* ws, int g, int sub = 0, int gsize = 1, unsigned gmask = 0xffffffffu) {
-  GeomL G; G.sub = sub; G.gsize = gsize; G.gmask = gmask; G.ox = 0.f; G.oy = 0.f; G.type = m.geom_type[g]; G.pos = WS(W_GXPOS) + 3 * g; G.mat = WS(W_GXMAT) + 9 * g;
-  G.sx = LDG(m.geom_size + 3 * g); G.sy = LDG(m.geom_size + 3 * g + 1); G.sz = LDG(m.geom_size + 3 * g + 2);
-  G.verts = m.hull_verts + 3 * m.geom_vadr[g]; G.nvert = m.geom_vnum[g];
-  const int sa = m.geom_supadr[g]; G.sup_off = sa >= 0 ? m.sup_off + sa : nullptr; G.sup_cand = m.sup_cand;
-  return G;
-}
-// scalar support query (one lane): same arithmetic and tie-breaks as support()
-DEV_NOINLINE void support_lane(const GeomL& G, float dx, float dy, float dz, float* out) {
-  const float* M = G.mat;
+struct F3 { float x, y, z; };
+// Hull support query.  Everything arrives in registers (scalars) and the geom's data is read from shared memory
+// (pose in the workspace, tables in the arena): no by-reference structs, hence no local-memory traffic on this hot path.
+// grp = sub | (gsize << 8): the lanes [sub = 0 .. gsize) of one group (mask gmask) work on the same query and split the
+// candidate scan.  (ox, oy) = origin of the local frame the query runs in.  Same arithmetic / tie-breaks as the oracle's
+// serial scan over all hull vertices.
+DEV_NOINLINE F3 support_lane(const ModelDev& m, const float* ws, int g, int grp, unsigned gmask, float ox, float oy, float dx, float dy, float dz) {
+  const float* M = WS(W_GXMAT) + 9 * g; const float* pos = WS(W_GXPOS) + 3 * g;
+  const int type = m.geom_type[g];
   const float l0 = M[0] * dx + M[3] * dy + M[6] * dz, l1 = M[1] * dx + M[4] * dy + M[7] * dz, l2 = M[2] * dx + M[5] * dy + M[8] * dz;
   float px = 0.f, py = 0.f, pz = 0.f;
-  if (G.type == GEOM_SPHERE) { px = l0 * G.sx; py = l1 * G.sx; pz = l2 * G.sx; }
-  else if (G.type == GEOM_CYLINDER) {
+  if (type == GEOM_SPHERE) { const float r = LDG(m.geom_size + 3 * g); px = l0 * r; py = l1 * r; pz = l2 * r; }
+  else if (type == GEOM_CYLINDER) {
+    const float r = LDG(m.geom_size + 3 * g), hh = LDG(m.geom_size + 3 * g + 1);
     const float n = sqrtf(l0 * l0 + l1 * l1);
-    if (n > MINVALF) { px = l0 / n * G.sx; py = l1 / n * G.sx; }
-    pz = (l2 > 0.f ? 1.f : (l2 < 0.f ? -1.f : 0.f)) * G.sy;
-  } else if (G.type == GEOM_BOX) {
-    px = (l0 > 0.f ? 1.f : -1.f) * G.sx; py = (l1 > 0.f ? 1.f : -1.f) * G.sy; pz = (l2 > 0.f ? 1.f : -1.f) * G.sz;
-  } else if (G.sup_off) {
+    if (n > MINVALF) { px = l0 / n * r; py = l1 / n * r; }
+    pz = (l2 > 0.f ? 1.f : (l2 < 0.f ? -1.f : 0.f)) * hh;
+  } else if (type == GEOM_BOX) {
+    px = (l0 > 0.f ? 1.f : -1.f) * LDG(m.geom_size + 3 * g); py = (l1 > 0.f ? 1.f : -1.f) * LDG(m.geom_size + 3 * g + 1); pz = (l2 > 0.f ? 1.f : -1.f) * LDG(m.geom_size + 3 * g + 2);
+  } else if (m.geom_supadr[g] >= 0) {
+    const int* sup_off = m.sup_off + m.geom_supadr[g];
     const float ld[3] = {l0, l1, l2};
     const int bucket = support_bucket(ld);
-    const int o0 = LDGB(G.sup_off + bucket), o1 = LDGB(G.sup_off + bucket + 1);
+    const int o0 = LDGB(sup_off + bucket), o1 = LDGB(sup_off + bucket + 1);
     float bv = -INFINITY; int bk = 0x7fffffff;
-    const int gs = G.gsize;
-    NOUNROLL for (int k = o0 + G.sub; k < o1; k += 4 * gs) {    // four independent 16-byte loads in flight per lane
+    const int gs = grp >> 8, sub = grp & 255;
+    NOUNROLL for (int k = o0 + sub; k < o1; k += 4 * gs) {    // four independent 16-byte loads in flight per lane
       const int k1 = imin(k + gs, o1 - 1), k2 = imin(k + 2 * gs, o1 - 1), k3 = imin(k + 3 * gs, o1 - 1);
 #ifdef COSIM_HOST_EMU
-      const float4 c0 = G.sup_cand[k], c1 = G.sup_cand[k1], c2 = G.sup_cand[k2], c3 = G.sup_cand[k3];
+      const float4 c0 = m.sup_cand[k], c1 = m.sup_cand[k1], c2 = m.sup_cand[k2], c3 = m.sup_cand[k3];
 #else
-      const float4 c0 = __ldg(G.sup_cand + k), c1 = __ldg(G.sup_cand + k1), c2 = __ldg(G.sup_cand + k2), c3 = __ldg(G.sup_cand + k3);
+      const float4 c0 = __ldg(m.sup_cand + k), c1 = __ldg(m.sup_cand + k1), c2 = __ldg(m.sup_cand + k2), c3 = __ldg(m.sup_cand + k3);
 #endif
       const float v0 = c0.x * l0 + c0.y * l1 + c0.z * l2, v1 = c1.x * l0 + c1.y * l1 + c1.z * l2;
       const float v2 = c2.x * l0 + c2.y * l1 + c2.z * l2, v3 = c3.x * l0 + c3.y * l1 + c3.z * l2;
@@ -696,25 +694,27 @@ DEV_NOINLINE void support_lane(const GeomL& G, float dx, float dy, float dz, flo
     if (gs > 1) {        // reduce over the lanes of the group, then fetch the winner's coordinates
       const int mine = bk;
       NOUNROLL for (int o = gs >> 1; o > 0; o >>= 1) {
-        const float ov = __shfl_xor_sync(G.gmask, bv, o); const int ok = __shfl_xor_sync(G.gmask, bk, o);
+        const float ov = __shfl_xor_sync(gmask, bv, o); const int ok = __shfl_xor_sync(gmask, bk, o);
         if (ov > bv || (ov == bv && ok < bk)) { bv = ov; bk = ok; }
       }
-      const int src = __ffs(__ballot_sync(G.gmask, mine == bk)) - 1;
-      px = __shfl_sync(G.gmask, px, src); py = __shfl_sync(G.gmask, py, src); pz = __shfl_sync(G.gmask, pz, src);
+      const int src = __ffs(__ballot_sync(gmask, mine == bk)) - 1;
+      px = __shfl_sync(gmask, px, src); py = __shfl_sync(gmask, py, src); pz = __shfl_sync(gmask, pz, src);
     }
 #endif
   } else {
+    const float* verts = m.hull_verts + 3 * m.geom_vadr[g]; const int nvert = m.geom_vnum[g];
     float bv = -INFINITY;
-    NOUNROLL for (int i = 0; i < G.nvert; ++i) {
-      const float vx = LDGB(G.verts + 3 * i), vy = LDGB(G.verts + 3 * i + 1), vz = LDGB(G.verts + 3 * i + 2);
+    NOUNROLL for (int i = 0; i < nvert; ++i) {
+      const float vx = LDGB(verts + 3 * i), vy = LDGB(verts + 3 * i + 1), vz = LDGB(verts + 3 * i + 2);
       const float v = vx * l0 + vy * l1 + vz * l2;
       if (v > bv) { bv = v; px = vx; py = vy; pz = vz; }
     }
   }
-  // (ox, oy): origin of the local frame the query runs in (exact subtraction of nearby numbers)
-  out[0] = (G.pos[0] - G.ox) + (M[0] * px + M[1] * py + M[2] * pz);
-  out[1] = (G.pos[1] - G.oy) + (M[3] * px + M[4] * py + M[5] * pz);
-  out[2] = G.pos[2] + (M[6] * px + M[7] * py + M[8] * pz);
+  F3 out;      // (pos - origin): exact subtraction of nearby numbers
+  out.x = (pos[0] - ox) + (M[0] * px + M[1] * py + M[2] * pz);
+  out.y = (pos[1] - oy) + (M[3] * px + M[4] * py + M[5] * pz);
+  out.z = pos[2] + (M[6] * px + M[7] * py + M[8] * pz);
+  return out;
 }
 // prism in registers: three columns (x, y, top z), bottoms at -base.  Vertex order as in the strip walk: 0..2 bottoms, 3..5 tops
 struct PrismL { float x[3], y[3], z[3], base; };
@@ -724,7 +724,9 @@ DEV void prism_vertex(const PrismL& P, int i, float* v) {
   v[1] = c == 0 ? P.y[0] : (c == 1 ? P.y[1] : P.y[2]);
   v[2] = i >= 3 ? (c == 0 ? P.z[0] : (c == 1 ? P.z[1] : P.z[2])) : -P.base;
 }
-DEV PV mink_lane(const PrismL& P, const GeomL& G, float dx, float dy, float dz) {
+#define GQ_PARAMS const ModelDev& m, const float* ws, int g, int grp, unsigned gmask, float ox, float oy
+#define GQ_ARGS m, ws, g, grp, gmask, ox, oy
+DEV PV mink_lane(const PrismL& P, GQ_PARAMS, float dx, float dy, float dz) {
   int best = 0; float bv = 0.f, bx = 0.f, by = 0.f, bz = 0.f;
 #pragma unroll
   for (int i = 0; i < 6; ++i) {
@@ -733,8 +735,8 @@ DEV PV mink_lane(const PrismL& P, const GeomL& G, float dx, float dy, float dz) 
     const float v = vx * dx + vy * dy + vz * dz;
     if (i == 0 || v > bv) { bv = v; best = i; bx = vx; by = vy; bz = vz; }
   }
-  float s2[3]; support_lane(G, -dx, -dy, -dz, s2);
-  PV r; r.x = bx - s2[0]; r.y = by - s2[1]; r.z = bz - s2[2]; r.pi = best;
+  const F3 s2 = support_lane(GQ_ARGS, -dx, -dy, -dz);
+  PV r; r.x = bx - s2.x; r.y = by - s2.y; r.z = bz - s2.z; r.pi = best;
   return r;
 }
 DEV float pv_dot(const PV& a, float x, float y, float z) { return a.x * x + a.y * y + a.z * z; }
@@ -758,8 +760,8 @@ DEV void pv_expand(const PV& p0, PV& p1, PV& p2, PV& p3, const PV& v4) {
 DEV void pv_witness(const PrismL& P, const PV& p, const float* c1, float* v1) { if (p.pi < 0) v3copy(v1, c1); else prism_vertex(P, p.pi, v1); }
 // MPR (XenoCollide) penetration query, restating libccd ccdMPRPenetration as driven by mjc_ConvexHField (oracle/oracle.hpp
 // mpr_penetration is the readable fp64 version); 0 = hit.  Run by one lane, or by a group of lanes in lock step that
-// share the hull support scans (GeomL::gsize).
-DEV_NOINLINE int mpr_lane(const ModelDev& m, const PrismL& P, const GeomL& G, const float* gcenter, float* depth, float* dir_out, float* pos) {
+// share the hull support scans (grp = sub | gsize << 8).
+DEV int mpr_lane(const PrismL& P, GQ_PARAMS, const float* gcenter, float* depth, float* dir_out, float* pos) {
   const float tol = MO(ccd_tolerance); const int maxit = MD(ccd_iterations);
   float c1[3] = {0.f, 0.f, 0.f};
 #pragma unroll
@@ -769,7 +771,7 @@ DEV_NOINLINE int mpr_lane(const ModelDev& m, const PrismL& P, const GeomL& G, co
   p0.x = c1[0] - gcenter[0]; p0.y = c1[1] - gcenter[1]; p0.z = c1[2] - gcenter[2]; p0.pi = -1;
   if (f_eq(p0.x, 0.f) && f_eq(p0.y, 0.f) && f_eq(p0.z, 0.f)) p0.x += CCD_EPS * 10.f;
   float dir[3] = {-p0.x, -p0.y, -p0.z}; v3normalize(dir);
-  p1 = mink_lane(P, G, dir[0], dir[1], dir[2]);
+  p1 = mink_lane(P, GQ_ARGS, dir[0], dir[1], dir[2]);
   float dot = pv_dot(p1, dir[0], dir[1], dir[2]);
   if (f_is_zero(dot) || dot < 0.f) return -1;
   { const float a[3] = {p0.x, p0.y, p0.z}, b[3] = {p1.x, p1.y, p1.z}; v3cross(dir, a, b); }
@@ -781,7 +783,7 @@ DEV_NOINLINE int mpr_lane(const ModelDev& m, const PrismL& P, const GeomL& G, co
     *depth = v3norm(pv); v3copy(dir_out, pv); v3normalize(dir_out); return 0;
   }
   v3normalize(dir);
-  p2 = mink_lane(P, G, dir[0], dir[1], dir[2]);
+  p2 = mink_lane(P, GQ_ARGS, dir[0], dir[1], dir[2]);
   dot = pv_dot(p2, dir[0], dir[1], dir[2]);
   if (f_is_zero(dot) || dot < 0.f) return -1;
   { float va[3] = {p1.x - p0.x, p1.y - p0.y, p1.z - p0.z}, vb[3] = {p2.x - p0.x, p2.y - p0.y, p2.z - p0.z}; v3cross(dir, va, vb); v3normalize(dir); }
@@ -790,7 +792,7 @@ DEV_NOINLINE int mpr_lane(const ModelDev& m, const PrismL& P, const GeomL& G, co
   int guard = 0;
   while (true) {       // portal discovery
     if (++guard > 100) return -1;
-    p3 = mink_lane(P, G, dir[0], dir[1], dir[2]);
+    p3 = mink_lane(P, GQ_ARGS, dir[0], dir[1], dir[2]);
     dot = pv_dot(p3, dir[0], dir[1], dir[2]);
     if (f_is_zero(dot) || dot < 0.f) return -1;
     int cont = 0;
@@ -809,7 +811,7 @@ DEV_NOINLINE int mpr_lane(const ModelDev& m, const PrismL& P, const GeomL& G, co
     pv_portal_dir(p1, p2, p3, dir);
     dot = pv_dot(p1, dir[0], dir[1], dir[2]);
     if (f_is_zero(dot) || dot > 0.f) break;
-    const PV v4 = mink_lane(P, G, dir[0], dir[1], dir[2]);
+    const PV v4 = mink_lane(P, GQ_ARGS, dir[0], dir[1], dir[2]);
     dot = pv_dot(v4, dir[0], dir[1], dir[2]);
     if (!(f_is_zero(dot) || dot > 0.f) || pv_reach_tol(p1, p2, p3, v4, dir, tol)) return -1;
     pv_expand(p0, p1, p2, p3, v4);
@@ -817,7 +819,7 @@ DEV_NOINLINE int mpr_lane(const ModelDev& m, const PrismL& P, const GeomL& G, co
   int it = 0;
   while (true) {       // penetration depth
     pv_portal_dir(p1, p2, p3, dir);
-    const PV v4 = mink_lane(P, G, dir[0], dir[1], dir[2]);
+    const PV v4 = mink_lane(P, GQ_ARGS, dir[0], dir[1], dir[2]);
     if (pv_reach_tol(p1, p2, p3, v4, dir, tol) || it > maxit) {
       const float a[3] = {p1.x, p1.y, p1.z}, b[3] = {p2.x, p2.y, p2.z}, c[3] = {p3.x, p3.y, p3.z};
       float wit[3];
@@ -869,9 +871,9 @@ DEV_NOINLINE void collide_hfield_all(const ModelDev& m, float* ws, int& ncon, in
   NOUNROLL for (int g = lane / gs1; g < ng; g += LANES / gs1) {
     int* tk = task + 8 * g;
     if (sub1 == 0) { tk[0] = tk[1] = tk[2] = tk[3] = tk[4] = tk[5] = 0; }
-    const GeomL G = make_geom_lane(m, ws, g, sub1, gs1, gmask1);
+    const int grp1 = sub1 | (gs1 << 8);
     const float cl[3] = {LDG(m.geom_center + 3 * g), LDG(m.geom_center + 3 * g + 1), LDG(m.geom_center + 3 * g + 2)};
-    float pos[3]; m3mulv(pos, G.mat, cl); v3add(pos, G.pos, pos);
+    float pos[3]; m3mulv(pos, WS(W_GXMAT) + 9 * g, cl); v3add(pos, WS(W_GXPOS) + 3 * g, pos);
     const float rb = LDG(m.geom_rbound + g);
     if (pos[0] - rb > sx || pos[0] + rb < -sx || pos[1] - rb > sy || pos[1] + rb < -sy) continue;
     if (pos[2] - rb > sz || pos[2] + rb < -base) continue;
@@ -882,17 +884,22 @@ DEV_NOINLINE void collide_hfield_all(const ModelDev& m, float* ws, int& ncon, in
       const int w = c1 - c0 + 1, cnt = w * (r1 - r0 + 1);
       if (cnt <= 64) {
         hmax = -INFINITY;
-        NOUNROLL for (int t = 0; t < cnt; ++t) hmax = fmaxf(hmax, LDGB(m.hfield_data + (size_t)(r0 + t / w) * ncol + c0 + t % w));
+        NOUNROLL for (int t = 0; t < cnt; t += 4) {          // four independent loads in flight
+          const int t1 = imin(t + 1, cnt - 1), t2 = imin(t + 2, cnt - 1), t3 = imin(t + 3, cnt - 1);
+          const float h0 = LDGB(m.hfield_data + (size_t)(r0 + t / w) * ncol + c0 + t % w), h1 = LDGB(m.hfield_data + (size_t)(r0 + t1 / w) * ncol + c0 + t1 % w);
+          const float h2 = LDGB(m.hfield_data + (size_t)(r0 + t2 / w) * ncol + c0 + t2 % w), h3 = LDGB(m.hfield_data + (size_t)(r0 + t3 / w) * ncol + c0 + t3 % w);
+          hmax = fmaxf(fmaxf(hmax, fmaxf(h0, h1)), fmaxf(h2, h3));
+        }
         hmax *= sz;
         if (pos[2] - rb > hmax) continue;
       }
     }
-    float xmin[3], xmax[3], s[3];
-    support_lane(G, 0.f, 0.f, -1.f, s); xmin[2] = s[2];
+    float xmin[3], xmax[3];
+    xmin[2] = support_lane(m, ws, g, grp1, gmask1, 0.f, 0.f, 0.f, 0.f, -1.f).z;
     if (xmin[2] > hmax) continue;         // the geom's lowest point clears every terrain vertex it could reach: no contact
-    support_lane(G, 1.f, 0.f, 0.f, s); xmax[0] = s[0]; support_lane(G, -1.f, 0.f, 0.f, s); xmin[0] = s[0];
-    support_lane(G, 0.f, 1.f, 0.f, s); xmax[1] = s[1]; support_lane(G, 0.f, -1.f, 0.f, s); xmin[1] = s[1];
-    support_lane(G, 0.f, 0.f, 1.f, s); xmax[2] = s[2];
+    xmax[0] = support_lane(m, ws, g, grp1, gmask1, 0.f, 0.f, 1.f, 0.f, 0.f).x; xmin[0] = support_lane(m, ws, g, grp1, gmask1, 0.f, 0.f, -1.f, 0.f, 0.f).x;
+    xmax[1] = support_lane(m, ws, g, grp1, gmask1, 0.f, 0.f, 0.f, 1.f, 0.f).y; xmin[1] = support_lane(m, ws, g, grp1, gmask1, 0.f, 0.f, 0.f, -1.f, 0.f).y;
+    xmax[2] = support_lane(m, ws, g, grp1, gmask1, 0.f, 0.f, 0.f, 0.f, 1.f).z;
     if (xmin[0] > sx || xmax[0] < -sx || xmin[1] > sy || xmax[1] < -sy || xmin[2] > sz || xmax[2] < -base) continue;
     int cmin = (int)floorf((xmin[0] + sx) / (2.f * sx) * (float)(ncol - 1));
     int cmax = (int)ceilf((xmax[0] + sx) / (2.f * sx) * (float)(ncol - 1));
@@ -938,15 +945,14 @@ DEV_NOINLINE void collide_hfield_all(const ModelDev& m, float* ws, int& ncon, in
         P.x[2] = dx * (float)(cc - tk[0]); P.y[2] = dy * (float)(rc - tk[1]); P.z[2] = LDGB(m.hfield_data + (size_t)rc * ncol + cc) * sz;
         const float zmin = ((const float*)tk)[6];
         if (!(P.z[0] < zmin && P.z[1] < zmin && P.z[2] < zmin)) {
-          GeomL G = make_geom_lane(m, ws, g, sub2, gs2, gmask2);
-          G.ox = ox; G.oy = oy;
 #if defined(COSIM_PHASE_TIMING) && !defined(COSIM_HOST_EMU)
           if (sub2 == 0) atomicAdd(m.phase + PH_MPR_CALLS, 1ull);
 #endif
           const float cl[3] = {LDG(m.geom_center + 3 * g), LDG(m.geom_center + 3 * g + 1), LDG(m.geom_center + 3 * g + 2)};
-          float gc[3]; m3mulv(gc, G.mat, cl);
-          gc[0] += G.pos[0] - ox; gc[1] += G.pos[1] - oy; gc[2] += G.pos[2];
-          if (mpr_lane(m, P, G, gc, &depth, nrm, cp) == 0 && !(nrm[0] == 0.f && nrm[1] == 0.f && nrm[2] == 0.f) && depth == depth) {
+          const float* gpos = WS(W_GXPOS) + 3 * g;
+          float gc[3]; m3mulv(gc, WS(W_GXMAT) + 9 * g, cl);
+          gc[0] += gpos[0] - ox; gc[1] += gpos[1] - oy; gc[2] += gpos[2];
+          if (mpr_lane(P, m, ws, g, sub2 | (gs2 << 8), gmask2, ox, oy, gc, &depth, nrm, cp) == 0 && !(nrm[0] == 0.f && nrm[1] == 0.f && nrm[2] == 0.f) && depth == depth) {
             hit = (sub2 == 0); cell = ((r * ncol + (c - 1)) << 1) | i;       // one lane per group reports the contact
             cp[0] += ox; cp[1] += oy;
           }
