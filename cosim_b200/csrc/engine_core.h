@@ -1427,10 +1427,11 @@ DEV_NOINLINE int newton_solve(const ModelDev& m, float* ws, int ncon, int has_ro
     FOR_LANE(k, nv) { qacc[k] = WS(W_ASMOOTH)[k]; WS(W_WARM)[k] = WS(W_ASMOOTH)[k]; WS(W_FCON)[k] = 0.f; }
     SYNC(); return 0;
   }
-  // warm start: cheaper of qacc_warmstart and qacc_smooth [upstream mj_fwdConstraint]
-  const float cw = total_cost(m, ws, ncon, WS(W_WARM), Ma, lane);
-  float cost = total_cost(m, ws, ncon, WS(W_ASMOOTH), Ma, lane);
-  if (!(cw > cost)) cost = total_cost(m, ws, ncon, WS(W_WARM), Ma, lane);
+  // warm start: cheaper of qacc_warmstart and qacc_smooth [upstream mj_fwdConstraint].  The warm start usually wins, so it
+  // is evaluated last: its row residuals / forces are then already in place and only a smooth-start win pays a third pass.
+  const float cs = total_cost(m, ws, ncon, WS(W_ASMOOTH), Ma, lane);
+  float cost = total_cost(m, ws, ncon, WS(W_WARM), Ma, lane);
+  if (cost > cs) cost = total_cost(m, ws, ncon, WS(W_ASMOOTH), Ma, lane);
   const float scale = 1.f / (WS(W_SCAL)[1] * (float)imax(1, nv));
   const float tol = MO(tolerance);
   const int maxiter = MD(iterations);
