@@ -39,6 +39,16 @@ def workload_config():
                        engine={"auto_reset": True, "seed": 0xC051, "ncon_max": 16})
 
 
+def measured_traffic(envs):
+    """DRAM bytes per k_step launch from the committed ncu capture (profiles/r01_traffic.json), if it matches this size."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            t = json.load(f)
+        return int(t["traffic_bytes_per_launch"]) if int(t["envs"]) == int(envs) else None
+    except Exception:
+        return None
+
+
 def measured_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -236,7 +246,7 @@ def main():
                       "l2": "per-env state, parameter and observation arrays total > 126 MB L2 at 65 536 envs (inputs larger than L2); no explicit flush"},
            "clocks": clk, "gpu_launches": launches,
            "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps},
-           "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+           "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": measured_traffic(N),
                         "kernel": "k_step", "kernel_ms": kernel_ms, "bytes_per_env_step": B_ALG, "peak_source": peak_src,
                         "note": "the step is bound by the FP32 pipe / shared-memory latency, not HBM (DESIGN.md section 5)"},
            "reporter_stats": {k: stats[k] for k in ("steps", "episodes", "success_rate", "termination_rate", "mean_abs_err_lin_vel_x",
