@@ -150,6 +150,7 @@ int cosim_create(const void* blob, size_t nbytes, int num_envs, int device, uint
   cudaError_t e2 = cudaFuncSetAttribute(k_reset, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem);
   cudaError_t e3 = cudaFuncSetAttribute(k_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem);
   if (e3 == cudaSuccess) e3 = cudaFuncSetAttribute(k_substep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem);
+  cudaFuncSetAttribute(k_step, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) { fprintf(stderr, "cosim_create: cudaFuncSetAttribute failed: %s\n", cudaGetErrorString(e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3))); for (void* p : h->allocs) cudaFree(p); delete h; return COSIM_ERR_CUDA; }
   cudaStreamCreate(&h->stream);     // blocking stream: ordered after work the caller queued on the legacy default stream (reset, set)
   k_init<<<grid_for(h), 32 * h->wpb, h->smem, h->stream>>>(h->m, h->E);

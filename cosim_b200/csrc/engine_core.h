@@ -1288,6 +1288,12 @@ DEV_NOINLINE float total_cost(const ModelDev& m, float* ws, int ncon, const floa
 // fp32 note: the reference's line-search gradient tolerance (tolerance * ls_tolerance * |search| *
 // meaninertia * nv ~ 1e-10) sits far below fp32 round-off of the derivative, so it is floored at a
 // few ulps of the magnitude of the terms the derivative is summed from.
+#ifndef COST_EPS
+#define COST_EPS 5e-7f
+#endif
+#ifndef GRAD_EPS
+#define GRAD_EPS 1e-6f
+#endif
 struct LSPoint { float alpha, cost, d0, d1; };
 DEV_NOINLINE LSPoint ls_eval(const ModelDev& m, const float* ws, int ncon, float a, float q0, float q1, float q2, int lane) {
   RowSum s = eval_rows(m, ws, ncon, a, true, lane);
@@ -1370,12 +1376,16 @@ DEV uint32_t active_set_signature(const ModelDev& m, const float* ws, int ncon, 
 }
 // `sig` carries the signature of the factor currently held in W_A: when the active set did not change since the previous
 // iteration the Hessian is the same matrix and only the triangular solves are repeated
-DEV_NOINLINE float newton_direction(const ModelDev& m, float* ws, int ncon, int lane, uint32_t& sig) {
+DEV_NOINLINE float newton_direction(const ModelDev& m, float* ws, int ncon, int lane, uint32_t& sig, float* termnorm = nullptr) {
   const int nv = MD(nv), neq = MD(neq);
   float* grad = WS(W_GRAD); float* H = WS(W_A); const float* M = WS(W_M); const float* qacc = WS(W_QACC); const float* Ma = WS(W_MA);
-  float gn = 0.f;
-  FOR_LANE(k, nv) { const float g = Ma[k] - WS(W_FSMOOTH)[k] - WS(W_FCON)[k]; grad[k] = g; gn += g * g; WS(W_TMPV)[k] = -g; }
+  float gn = 0.f, fn = 0.f;
+  FOR_LANE(k, nv) {
+    const float a = Ma[k], b = WS(W_FSMOOTH)[k], c = WS(W_FCON)[k], g = a - b - c;
+    grad[k] = g; gn += g * g; fn += a * a + b * b + c * c; WS(W_TMPV)[k] = -g;
+  }
   gn = sqrtf(wsum(gn));
+  if (termnorm) *termnorm = sqrtf(wsum(fn));
   const uint32_t now = active_set_signature(m, ws, ncon, lane);
   if (now == sig) {
     SYNC();
@@ -1463,9 +1473,14 @@ DEV_NOINLINE int newton_solve(const ModelDev& m, float* ws, int ncon, int has_ro
     float g = 0.f;
     FOR_LANE(k, nv) g += (Ma[k] - WS(W_FSMOOTH)[k]) * (qacc[k] - WS(W_ASMOOTH)[k]);
     cost = update_forces(m, ws, ncon, lane) + 0.5f * wsum(g);
-    const float gn = newton_direction(m, ws, ncon, lane, sig);
+    float fn;
+    const float gn = newton_direction(m, ws, ncon, lane, sig, &fn);
     ++iter;
-    if (scale * (old - cost) < tol || scale * gn < tol) break;
+    // reference criteria (scaled improvement / gradient below `tolerance` = 1e-8) with fp32 round-off floors: the cost is a
+    // sum of O(|cost|) terms, so an improvement below a few ulps of it is noise (without the floor the fp32 engine spends
+    // one more iteration per sub-step than the fp64 oracle just to see the improvement turn negative)
+    // ... and the gradient is a difference of three force vectors of norm fn, so it cannot be resolved below a few ulps of fn
+    if ((old - cost) < fmaxf(tol / scale, COST_EPS * fabsf(old)) || gn < fmaxf(tol / scale, GRAD_EPS * fn)) break;
   }
   FOR_LANE(k, nv) WS(W_WARM)[k] = qacc[k];
   SYNC();

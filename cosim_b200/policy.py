@@ -108,9 +108,12 @@ class MLPPolicy:
 
 
 def build_policy(config, policy_path=None, state_dim=None, action_dim=None, device="cuda:0"):
-    """core/policy.py:49-53.  ONNX loading is a 'next' row; without a file the synthetic MLP is used."""
+    """core/policy.py:49-53.  MLP policies are read from the user's ONNX file (cosim_b200/onnx_reader.py); without a file the
+    synthetic MLP of SURVEY.md section 8d is used.  LSTM policies are a 'next' row."""
     if config.get("policy", {}).get("use_lstm"):
         raise NotImplementedError("LSTM policies are not implemented yet (SURVEY.md section 8f, row 1)")
     if policy_path:
-        raise NotImplementedError("ONNX weight loading is not implemented yet (SURVEY.md section 8f, row 1)")
+        from .onnx_reader import load_mlp
+        layers, act = load_mlp(policy_path)          # the user's ONNX file, as in core/policy.py:7-9
+        return MLPPolicy(layers, act, device)
     return MLPPolicy(synthetic_mlp(state_dim, action_dim), "elu", device)
