@@ -94,7 +94,13 @@ def cpu_reference(cfg, n_envs, steps, warmup, threads=0):
     from cosim_b200.model import build_model
     from oracle.oracle import Oracle, lib as olib
     model = build_model(cfg)
-    cores = int(olib().orc_max_threads()) if threads <= 0 else threads
+    # all host threads this process may use; torchrun exports OMP_NUM_THREADS=1, which would silently make this a 1-core run
+    try:
+        avail = len(os.sched_getaffinity(0))
+    except AttributeError:
+        avail = os.cpu_count() or 1
+    cores = avail if threads <= 0 else threads
+    olib()
     orc = Oracle(model, n_envs, seed=0xC051)
     rng = np.random.default_rng(7)
     cmd = rng.uniform(-1.5, 1.5, (n_envs, model.dim("command_dim")))

@@ -1294,10 +1294,16 @@ DEV_NOINLINE float total_cost(const ModelDev& m, float* ws, int ncon, const floa
 #ifndef GRAD_EPS
 #define GRAD_EPS 1e-6f
 #endif
+#ifdef COSIM_HOST_EMU
+static long g_emu_ls_evals = 0;      // analysis aid of the host emulation (tests/hostsim)
+#endif
 struct LSPoint { float alpha, cost, d0, d1; };
 DEV_NOINLINE LSPoint ls_eval(const ModelDev& m, const float* ws, int ncon, float a, float q0, float q1, float q2, int lane) {
   RowSum s = eval_rows(m, ws, ncon, a, true, lane);
   PH_COUNT(PH_LS_EVALS, 1);
+#ifdef COSIM_HOST_EMU
+  ++g_emu_ls_evals;
+#endif
   LSPoint p; p.alpha = a;
   p.cost = a * a * q2 + a * q1 + q0 + wsum(s.cost);
   p.d0 = 2.f * a * q2 + q1 + wsum(s.d0);

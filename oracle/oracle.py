@@ -74,7 +74,7 @@ class Oracle:
             "hm_cell": max(1, model.dim("hm_res_x") * model.dim("hm_res_y")),
             "obs_buffer": model.dim("stack_size") * model.dim("stacked_dim"),
             "subtree_com": 3, "ground_friction": 3, "delay_prob": 1, "meaninertia": 1, "ncon": 1, "nefc": 1,
-            "solver_iter": 1, "ncon_dropped": 1, "sim_step": 1, "nan_count": 1, "sens_gyro": 3, "sens_vel": 3,
+            "solver_iter": 1, "ls_evals": 1, "ncon_dropped": 1, "sim_step": 1, "nan_count": 1, "sens_gyro": 3, "sens_vel": 3,
             "sens_quat": 4, "info": 4,
         }
 

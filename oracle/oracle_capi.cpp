@@ -72,6 +72,7 @@ template <class T> struct OracleT : IOracle {
       if (n == "ncon") { out[e] = (double)d.con.size(); continue; }
       if (n == "nefc") { out[e] = d.nefc; continue; }
       if (n == "solver_iter") { out[e] = d.solver_iter; continue; }
+      if (n == "ls_evals") { out[e] = (double)d.ls_evals; continue; }
       if (n == "ncon_dropped") { out[e] = d.ncon_dropped; continue; }
       if (n == "sim_step") { out[e] = d.sim_step; continue; }
       if (n == "nan_count") { out[e] = d.nan_count; continue; }

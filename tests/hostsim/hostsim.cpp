@@ -94,5 +94,6 @@ int hs_set(void* hp, const char* name, const void* src) {
   for (auto& f : setup::env_fields(h->m, h->E)) if (!strcmp(f.name, name)) { memcpy(f.ptr, src, (size_t)h->N * f.dim * 4); return 0; }
   return -1;
 }
+long hs_ls_evals() { return g_emu_ls_evals; }
 uint32_t hs_philox(void* hp, uint32_t env, uint32_t stream, uint32_t step, uint32_t idx) { return philox_draw(((HostSim*)hp)->m, env, stream, step, idx); }
 }
