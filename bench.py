@@ -146,7 +146,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--envs", type=int, default=65536, help="environments per GPU")
     ap.add_argument("--impl", default="cosim_b200", choices=["cosim_b200", "reference"])
-    ap.add_argument("--ref-envs", type=int, default=256)
+    ap.add_argument("--ref-envs", type=int, default=1024)
     ap.add_argument("--cpu-envs", type=int, default=512)
     ap.add_argument("--cpu-steps", type=int, default=20)
     ap.add_argument("--no-cpu-baseline", action="store_true")
