@@ -338,3 +338,23 @@ def test_engine_replays_reference_python_golden(name):
     assert np.median(diffs) < 2e-3 and (diffs > 2e-2).mean() <= 0.15 and diffs.max() < 0.5, \
         f"state vs reference-python golden: median {np.median(diffs):.1e}, {(diffs > 2e-2).mean():.0%} of steps above 2e-2, max {diffs.max():.1e}"
     env.close()
+
+
+@pytest.mark.parametrize("precision", ["low", "high"])
+def test_other_precision_presets(precision):
+    """random_table.yaml precision presets change timestep / iterations / frame_skip (2 and 8 sub-steps here)."""
+    N = 32
+    env = _env("flamingo_p_v3", "slope_easy", N, random=dict(RANDOM_NONE, precision=precision))
+    orc = _oracle(env, N)
+    orc.reset(); env.reset()
+    rng = np.random.default_rng(1)
+    errs = []
+    for i in range(6):
+        a = rng.uniform(-1, 1, (N, env.action_dim))
+        for k in ("qpos", "qvel", "qacc_warmstart"):
+            env.set(k, orc.get(k))
+        s_o, _, _ = orc.step(a); s_g, _, _, _ = env.step(a)
+        errs.append(np.abs(orc.get("qvel") - env.get("qvel").cpu().numpy()).max(axis=1))
+    errs = np.concatenate(errs)
+    assert np.median(errs) < 5e-4 and (errs > 5e-2).mean() <= 0.1
+    env.close()

@@ -169,3 +169,20 @@ def test_blob_header_in_sync():
     from cosim_b200.model import DIMS, OPTS
     src = open("include/cosim_blob.h").read()
     assert re.findall(r"CD_(\w+) = \d+", src) == DIMS and re.findall(r"CO_(\w+) = \d+", src) == OPTS
+
+
+def test_every_robot_terrain_and_precision_builds():
+    """All 4 robots x their terrains (xml_manager.py:21-32) x precision presets (random_table.yaml:2-22) build a model."""
+    from cosim_b200.config import load_tables
+    et, rt = load_tables()
+    from cosim_b200.model import load_robot
+    for robot in ROBOTS:
+        rb = load_robot(robot)
+        terrains = ["flat"] + [str(n) for n in rb["hfield_names"] if str(n) != "flat"]
+        assert len(terrains) >= 8
+        for t in terrains:
+            m = build_model(make_config(robot, t, random=RANDOM_NONE))
+            assert m.dim("ground_type") == (0 if t == "flat" else 1)
+    for prec, (dt, it, fs) in {"low": (0.01, 50, 2), "medium": (0.005, 50, 4), "high": (0.0025, 75, 8), "ultra": (0.00125, 75, 16), "extreme": (0.000625, 100, 32)}.items():
+        m = build_model(make_config("flamingo_p_v3", "rocky_easy", random=dict(RANDOM_NONE, precision=prec)))
+        assert (m.opt("timestep"), m.dim("iterations"), m.dim("frame_skip")) == (dt, it, fs)
