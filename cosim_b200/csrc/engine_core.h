@@ -166,12 +166,15 @@ enum WsField {
   W_BMASS, W_INVWD, W_INVWB, W_FLOSS, W_GMU, W_SCAL,
   W_FR_D, W_FR_AREF, W_LM_SIGN, W_LM_D, W_LM_AREF,
   W_CN_POS, W_CN_FRAME, W_CN_DIST, W_CN_MU, W_CN_BODY, W_CN_GEOM, W_CN_CELL, W_CN_D, W_CN_AREF, W_CN_J, W_CN_F, W_CN_X, W_CN_V,
-  W_EQ_J, W_EQ_D, W_EQ_AREF, W_EQ_X, W_EQ_V, W_EQ_F, W_SENS, W_RAW, W_ACT, W_FILT, W_KP, W_KD, W_GTASK, W__COUNT   // keep <= 80 (ModelDev::off)
+  W_EQ_J, W_EQ_D, W_EQ_AREF, W_EQ_X, W_EQ_V, W_EQ_F, W_SENS, W_RAW, W_ACT, W_FILT, W_KP, W_KD, W_GTASK, W_CNT, W__COUNT   // keep <= 80 (ModelDev::off)
 };
 static_assert(W__COUNT <= 80, "ModelDev::off too small");
 #define WS(f) (ws + m.off[f])
 #define WSI(f) ((int*)(ws + m.off[f]))
 // W_SCAL: [0] ground mu, [1] meaninertia, [2] delay_prob, [3] unused
+// W_CNT (ints, warp-uniform counters kept in shared memory so they need not travel by reference through the out-of-line
+// calls): [0] contacts of the last forward pass, [1] contacts dropped in it, [2] NaN resets, [3] dropped in this control step
+enum { CNT_NCON = 0, CNT_DROPPED = 1, CNT_NAN = 2, CNT_DROPPED_STEP = 3 };
 
 // Per-env arrays in HBM: one row per env, rows contiguous (a warp reads its env's row coalesced).
 struct EnvArrays {
@@ -856,7 +859,8 @@ DEV int mpr_lane(const PrismL& P, GQ_PARAMS, const float* gcenter, float* depth,
 }
 
 // per-geom task record in W_GTASK: [cmin, rmin, ncols, nrows, first task, contacts so far, zmin (float), unused]
-DEV_NOINLINE void collide_hfield_all(const ModelDev& m, float* ws, int& ncon, int& dropped, int lane) {
+DEV_NOINLINE void collide_hfield_all(const ModelDev& m, float* ws, int lane) {
+  int ncon = 0, dropped = 0;
   const int ng = MD(ngeom), nrow = MD(hf_nrow), ncol = MD(hf_ncol);
   const float sx = MO(hf_sx), sy = MO(hf_sy), sz = MO(hf_sz), base = MO(hf_base);
   const float dx = 2.f * sx / (float)(ncol - 1), dy = 2.f * sy / (float)(nrow - 1);
@@ -989,6 +993,7 @@ DEV_NOINLINE void collide_hfield_all(const ModelDev& m, float* ws, int& ncon, in
     }
 #endif
   }
+  if (lane == 0) { WSI(W_CNT)[CNT_NCON] = ncon; WSI(W_CNT)[CNT_DROPPED] = dropped; }
   SYNC();
 }
 
@@ -1512,9 +1517,9 @@ DEV_NOINLINE void sensors(const ModelDev& m, float* ws, int lane) {
 }
 
 // ------------------------------------------------------------------------------------------ forward + one sub-step
-// returns solver iterations; ncon_out / dropped_out = contacts of this forward pass
+// returns solver iterations; the contact count of this pass is left in W_CNT
 // `active` = this warp has an env to advance; `bsync` = CTA-wide phase barriers (must then be called by every warp)
-DEV_NOINLINE int forward(const ModelDev& m, float* ws, int& ncon_out, int& dropped_out, int lane, int active = 1, int bsync = 0) {
+DEV_NOINLINE int forward(const ModelDev& m, float* ws, int lane, int active = 1, int bsync = 0) {
   const int nv = MD(nv), nu = MD(nu), njnt = MD(njnt);
   PH_DECL;
   int ncon = 0, dropped = 0, rows = 0, iters = 0;
@@ -1531,13 +1536,17 @@ DEV_NOINLINE int forward(const ModelDev& m, float* ws, int& ncon_out, int& dropp
   PH_MARK(PH_KIN);
   BSYNC_IF(bsync, 0);
   if (active) {           // ---- phase 2: collision
-    if (MD(ground_type) == 1) collide_hfield_all(m, ws, ncon, dropped, lane);
-    else { NOUNROLL for (int g = 0; g < MD(ngeom); ++g) collide_plane(m, ws, g, ncon, dropped, lane); }
+    if (MD(ground_type) == 1) collide_hfield_all(m, ws, lane);
+    else {
+      NOUNROLL for (int g = 0; g < MD(ngeom); ++g) collide_plane(m, ws, g, ncon, dropped, lane);
+      if (lane == 0) { WSI(W_CNT)[CNT_NCON] = ncon; WSI(W_CNT)[CNT_DROPPED] = dropped; }
+    }
     SYNC();
   }
   PH_MARK(PH_COLLIDE);
   BSYNC_IF(bsync, 1);
   if (active) {           // ---- phase 3: constraint rows, sensors, smooth forces and acceleration
+    ncon = WSI(W_CNT)[CNT_NCON];
     com_vel(m, ws, lane);
     make_constraint(m, ws, ncon, lane);
     sensors(m, ws, lane);
@@ -1566,12 +1575,12 @@ DEV_NOINLINE int forward(const ModelDev& m, float* ws, int& ncon_out, int& dropp
   PH_MARK(PH_SMOOTH);
   BSYNC_IF(bsync, 2);
   if (active) {           // ---- phase 4: constraint solve
+    ncon = WSI(W_CNT)[CNT_NCON];
     iters = newton_solve(m, ws, ncon, rows, lane);
     PH_COUNT(PH_NEWTON_ITERS, iters);
   }
   PH_MARK(PH_NEWTON);
   BSYNC_IF(bsync, 3);
-  ncon_out = ncon; dropped_out = dropped;
   return iters;
 }
 
@@ -1587,13 +1596,13 @@ DEV_NOINLINE void reset_data(const ModelDev& m, float* ws, int lane) {
   SYNC();
 }
 
-DEV_NOINLINE int substep(const ModelDev& m, float* ws, int& ncon, int& dropped, int& nan_count, int lane, int active = 1, int bsync = 0) {
+DEV_NOINLINE int substep(const ModelDev& m, float* ws, int lane, int active = 1, int bsync = 0) {
   const int nv = MD(nv), njnt = MD(njnt);
-  if (active && bad_state(m, ws, lane)) { reset_data(m, ws, lane); ++nan_count; }
-  int iters = forward(m, ws, ncon, dropped, lane, active, bsync);
+  if (active && bad_state(m, ws, lane)) { reset_data(m, ws, lane); if (lane == 0) WSI(W_CNT)[CNT_NAN]++; }
+  int iters = forward(m, ws, lane, active, bsync);
   if (active) {
     { int bad = 0; FOR_LANE(i, nv) { float x = WS(W_QACC)[i]; bad |= !(x == x) || fabsf(x) > 1e10f; }
-      if (wor(bad)) { reset_data(m, ws, lane); ++nan_count; iters = forward(m, ws, ncon, dropped, lane, 1, 0); } }   // rare: no barriers inside
+      if (wor(bad)) { reset_data(m, ws, lane); if (lane == 0) WSI(W_CNT)[CNT_NAN]++; iters = forward(m, ws, lane, 1, 0); } }   // rare: no barriers inside
     // implicitfast: (M + dt diag(damping)) a = qfrc_smooth + qfrc_constraint
     PH_DECL;
     const float dt = MO(timestep);
@@ -1621,6 +1630,7 @@ DEV_NOINLINE int substep(const ModelDev& m, float* ws, int& ncon, int& dropped, 
         }
       } else qpos[qa] += dt * qvel[da];
     }
+    if (lane == 0) WSI(W_CNT)[CNT_DROPPED_STEP] += WSI(W_CNT)[CNT_DROPPED];
     SYNC();
     PH_MARK(PH_INTEGRATE);
   }

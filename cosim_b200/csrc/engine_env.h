@@ -221,8 +221,8 @@ DEV_NOINLINE void reset_env(const ModelDev& m, const EnvArrays& E, int env, floa
   FOR_LANE(i, nv) { WS(W_QVEL)[i] = 0.f; WS(W_WARM)[i] = 0.f; }
   FOR_LANE(i, nu) { WS(W_CTRL)[i] = 0.f; WS(W_ACT)[i] = 0.f; E.prev_action[(size_t)env * nu + i] = 0.f; E.delay_prev[(size_t)env * nu + i] = 0.f; E.torque[(size_t)env * nu + i] = 0.f; E.last_action[(size_t)env * nu + i] = 0.f; }
   SYNC();
-  int ncon, dropped;
-  int iters = forward(m, ws, ncon, dropped, lane);
+  int iters = forward(m, ws, lane);
+  const int ncon = WSI(W_CNT)[CNT_NCON];
   get_obs(m, E, env, ws, nobs, lane);
   build_state(m, E, env, ws, 0, true, cmd, state, lane);
   store_state(m, E, env, ws, lane);
@@ -303,10 +303,13 @@ DEV_NOINLINE void step_env(const ModelDev& m, const EnvArrays& E, int env, float
   SYNC();
   }
   BSYNC(bsync);
-  int ncon = 0, dropped = 0, nan_count = 0, iters = 0, dropped_total = 0;
+  int iters = 0;
   const int fs = MD(frame_skip);
-  NOUNROLL for (int s = 0; s < fs; ++s) { iters += substep(m, ws, ncon, dropped, nan_count, lane, active, bsync); dropped_total += dropped; }
+  if (lane == 0) { WSI(W_CNT)[CNT_NCON] = 0; WSI(W_CNT)[CNT_DROPPED] = 0; WSI(W_CNT)[CNT_NAN] = 0; WSI(W_CNT)[CNT_DROPPED_STEP] = 0; }
+  SYNC();
+  NOUNROLL for (int s = 0; s < fs; ++s) iters += substep(m, ws, lane, active, bsync);
   if (!active) return;
+  const int ncon = WSI(W_CNT)[CNT_NCON], nan_count = WSI(W_CNT)[CNT_NAN], dropped_total = WSI(W_CNT)[CNT_DROPPED_STEP];
   PH_DECL;
   cfrc_ext(m, ws, ncon, lane);
   // termination: signed cfrc_ext component above threshold on the listed bodies
@@ -351,8 +354,10 @@ DEV_NOINLINE void substep_env(const ModelDev& m, const EnvArrays& E, int env, fl
   load_state(m, E, env, ws, lane);
   FOR_LANE(k, nu) WS(W_CTRL)[k] = E.torque[(size_t)env * nu + k];
   SYNC();
-  int ncon = 0, dropped = 0, nan_count = 0;
-  const int iters = substep(m, ws, ncon, dropped, nan_count, lane);
+  if (lane == 0) { WSI(W_CNT)[CNT_NAN] = 0; WSI(W_CNT)[CNT_DROPPED_STEP] = 0; }
+  SYNC();
+  const int iters = substep(m, ws, lane);
+  const int ncon = WSI(W_CNT)[CNT_NCON];
   cfrc_ext(m, ws, ncon, lane);
   if (E.dbg_cfrc) FOR_LANE(i, 6 * nb) E.dbg_cfrc[(size_t)env * 6 * nb + i] = WS(W_CACC)[i];
   dump_contacts(m, E, env, ws, ncon, lane);

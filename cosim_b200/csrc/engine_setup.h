@@ -170,7 +170,7 @@ static inline void build_model(const void* blob, size_t nbytes, uint64_t seed, u
   size[W_CN_POS] = 3 * nc; size[W_CN_FRAME] = 9 * nc; size[W_CN_DIST] = nc; size[W_CN_MU] = nc; size[W_CN_BODY] = nc; size[W_CN_GEOM] = nc;
   size[W_CN_CELL] = nc; size[W_CN_D] = nc; size[W_CN_AREF] = 4 * nc; size[W_CN_J] = 3 * nc * nv; size[W_CN_F] = 3 * nc; size[W_CN_X] = 4 * nc; size[W_CN_V] = 4 * nc;
   size[W_EQ_J] = 3 * neq * nv; size[W_EQ_D] = size[W_EQ_AREF] = size[W_EQ_X] = size[W_EQ_V] = size[W_EQ_F] = 3 * neq;
-  size[W_SENS] = 12; size[W_RAW] = nraw; size[W_ACT] = nu; size[W_FILT] = 0; size[W_KP] = nu; size[W_KD] = nu; size[W_GTASK] = 8 * ng;
+  size[W_SENS] = 12; size[W_RAW] = nraw; size[W_ACT] = nu; size[W_FILT] = 0; size[W_KP] = nu; size[W_KD] = nu; size[W_GTASK] = 8 * ng; size[W_CNT] = 4;
   // Lay the fields out back to back, then overlay fields whose lifetimes never overlap (shared memory per env bounds
   // how many env-warps an SM holds, and the step is latency-bound, so every KB counts):
   //   W_CRB    (only inside crb(), phase 1)            over  W_CVEL + W_CACC   (written from com_vel on, phase 3)

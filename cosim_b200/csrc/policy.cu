@@ -3,7 +3,7 @@
 // Replaces MLPPolicy.get_action (/root/reference/core/policy.py:11-21): action = clip(MLP(state), -1, 1),
 // where the reference runs an ONNX graph through onnxruntime's CPU provider one state at a time.
 //
-// One CTA (128 threads) owns a tile of 128 environments = the 128 TMEM lanes:
+// One CTA (256 threads) owns a tile of 128 environments = the 128 TMEM lanes:
 //   * the activation tile [128 x K] lives in shared memory as bf16 in the UMMA "no-swizzle, K-major"
 //     canonical layout (8x8 core matrices of 128 B), and is overwritten in place layer after layer --
 //     the accumulators of a whole layer (<= 512 fp32 columns) sit in TMEM, so the input of a layer is
@@ -13,7 +13,7 @@
 //     2-stage ring, tracked by mbarriers;
 //   * thread 0 issues tcgen05.mma (M = 128, N = chunk width, K = 16 per instruction), tcgen05.commit
 //     releases the ring slot / publishes the accumulators;
-//   * all 4 warps run the epilogue: tcgen05.ld (32 lanes x 16 columns), + bias, ELU/tanh/ReLU, bf16
+//   * all 8 warps run the epilogue: tcgen05.ld (32 lanes x 16 columns), + bias, ELU/tanh/ReLU, bf16
 //     pack, store to the activation tile; the last layer clips to [-1, 1] and writes fp32 actions.
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
@@ -77,13 +77,13 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint
 __device__ __forceinline__ uint32_t umma_idesc(int n) { return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(POL_TILE_M >> 4) << 24); }
 
 __device__ __forceinline__ float activate(float x, int act) {
-  if (act == 0) return x > 0.f ? x : expm1f(x);      // ELU(alpha = 1)
+  if (act == 0) return x > 0.f ? x : __expf(x) - 1.f;   // ELU(alpha = 1); the result is rounded to bf16 (2^-8) right after
   if (act == 1) return tanhf(x);
   return fmaxf(x, 0.f);                               // ReLU
 }
 
 // ------------------------------------------------------------------------------------------ kernel
-__global__ void __launch_bounds__(128, 1) k_policy_mlp(const __grid_constant__ PolicyDev p, const float* __restrict__ state, int num_envs, float* __restrict__ action) {
+__global__ void __launch_bounds__(256, 1) k_policy_mlp(const __grid_constant__ PolicyDev p, const float* __restrict__ state, int num_envs, float* __restrict__ action) {
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* act_buf = smem;                                   // [k/8][row/8][row%8][k%8] bf16
   uint8_t* wbuf = smem + POL_ACT_BYTES;                      // 2 stages
@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(128, 1) k_policy_mlp(const __grid_constant__ P
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     // ---- stage the input tile: fp32 state rows -> bf16 canonical layout (one warp per row, lanes over 8-column groups)
     const int K0 = p.K[0];
-    for (int r = warp; r < POL_TILE_M; r += 4) {
+    for (int r = warp; r < POL_TILE_M; r += 8) {
       const int env = tile * POL_TILE_M + r;
       const float* src = state + (size_t)env * p.in_dim;
       for (int j = tid & 31; j < K0 / 8; j += 32) {
@@ -173,9 +173,11 @@ __global__ void __launch_bounds__(128, 1) k_policy_mlp(const __grid_constant__ P
       ++nacc;
       tc_fence_after();
       const bool last = (l == p.nlayers - 1);
-      const int row = tid, env = tile * POL_TILE_M + row;
-      const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
-      for (int c0 = 0; c0 < N; c0 += 16) {
+      // 8 warps: warp w reads TMEM lanes 32 (w % 4) .. +31 (a warp can only reach its own lane quarter); the two warps
+      // of a quarter alternate 16-column chunks
+      const int row = (warp & 3) * 32 + (tid & 31), env = tile * POL_TILE_M + row;
+      const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+      for (int c0 = (warp >> 2) * 16; c0 < N; c0 += 32) {
         uint32_t r[16];
         tc_ld16(lane_addr + (uint32_t)c0, r);
         if (!last) {
@@ -281,7 +283,7 @@ int cosim_policy_forward(cosim_policy* p, const float* state, int num_envs, floa
   if (!p || !state || !action_out || num_envs <= 0) return COSIM_ERR_ARG;
   const int ntiles = (num_envs + POL_TILE_M - 1) / POL_TILE_M;
   const int grid = ntiles < p->sms ? ntiles : p->sms;
-  k_policy_mlp<<<grid, 128, POL_SMEM_BYTES, (cudaStream_t)stream>>>(p->d, state, num_envs, action_out);
+  k_policy_mlp<<<grid, 256, POL_SMEM_BYTES, (cudaStream_t)stream>>>(p->d, state, num_envs, action_out);
   p->launches++;
   return cudaGetLastError() == cudaSuccess ? COSIM_OK : COSIM_ERR_CUDA;
 }
