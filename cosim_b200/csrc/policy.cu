@@ -34,7 +34,7 @@
 #define POL_SMEM_BYTES (POL_ACT_BYTES + 2 * POL_WSTAGE_BYTES + 64)
 
 struct PolicyDev {
-  int nlayers, act, in_dim, out_dim;
+  int nlayers, act, in_dim, out_dim, raw_out;      // raw_out: 0 = clip(-1, 1), 1 = plain linear output, 2 = hidden activation applied
   int K[POL_MAX_LAYERS], N[POL_MAX_LAYERS];        // padded: K % 64 == 0, N % 64 == 0 (hidden) or % 16 == 0 (last)
   const __nv_bfloat16* w[POL_MAX_LAYERS];          // packed blocks
   const float* b[POL_MAX_LAYERS];                  // padded biases
@@ -131,8 +131,14 @@ __global__ void __launch_bounds__(256, 1) k_policy_mlp(const __grid_constant__ P
     __syncthreads();
 
     for (int l = 0; l < p.nlayers; ++l) {
-      const int K = p.K[l], N = p.N[l];
-      const int nkc = K / POL_KC, nnc = (N + POL_NC - 1) / POL_NC;
+      const int K = p.K[l], Nl = p.N[l];
+      const bool last = (l == p.nlayers - 1);
+      const int nkc = K / POL_KC;
+      // hidden layers are at most 512 wide (one TMEM pass).  The LAST layer writes to global memory, so its input tile
+      // stays intact and wider outputs (LSTM gate pre-activations: 4 H columns) run as several 512-column passes.
+      for (int nbase = 0; nbase < Nl; nbase += POL_MAX_WIDTH) {
+      const int N = min(POL_MAX_WIDTH, Nl - nbase);
+      const int nnc = (N + POL_NC - 1) / POL_NC;
       if (tid == 0) {
         tc_fence_after();
         const int C = nkc * nnc;
@@ -140,7 +146,7 @@ __global__ void __launch_bounds__(256, 1) k_policy_mlp(const __grid_constant__ P
           const uint32_t gg = g + c, s = gg & 1, u = gg >> 1;
           if (u >= 1) mbar_wait(bar_empty + 8 * s, (u - 1) & 1);
           const int nc = c / nkc, kc = c - nc * nkc;
-          const int n0 = nc * POL_NC, Nc = min(POL_NC, N - n0);
+          const int n0 = nbase + nc * POL_NC, Nc = min(POL_NC, Nl - n0);
           const uint32_t bytes = (uint32_t)Nc * POL_KC * 2;
           const __nv_bfloat16* src = p.w[l] + ((size_t)n0 * K + (size_t)kc * Nc * POL_KC);
           mbar_expect_tx(bar_full + 8 * s, bytes);
@@ -153,7 +159,7 @@ __global__ void __launch_bounds__(256, 1) k_policy_mlp(const __grid_constant__ P
           mbar_wait(bar_full + 8 * s, u & 1);
           tc_fence_after();
           const int nc = c / nkc, kc = c - nc * nkc;
-          const int n0 = nc * POL_NC, Nc = min(POL_NC, N - n0);
+          const int n0 = nbase + nc * POL_NC, Nc = min(POL_NC, Nl - n0);
           const uint32_t idesc = umma_idesc(Nc);
           const uint32_t a_base = smem_u32(act_buf) + (uint32_t)(kc * (POL_KC / 8)) * 16 * 128;
           const uint32_t b_base = smem_u32(wbuf + s * POL_WSTAGE_BYTES);
@@ -161,18 +167,17 @@ __global__ void __launch_bounds__(256, 1) k_policy_mlp(const __grid_constant__ P
           for (int kk = 0; kk < POL_KC / 16; ++kk) {
             const uint64_t ad = umma_desc(a_base + (uint32_t)kk * 2 * 16 * 128, 16 * 128, 128);
             const uint64_t bd = umma_desc(b_base + (uint32_t)kk * 2 * (Nc / 8) * 128, (uint32_t)(Nc / 8) * 128, 128);
-            tc_mma_bf16(tmem_base + (uint32_t)n0, ad, bd, idesc, (kc > 0 || kk > 0) ? 1u : 0u);
+            tc_mma_bf16(tmem_base + (uint32_t)(n0 - nbase), ad, bd, idesc, (kc > 0 || kk > 0) ? 1u : 0u);
           }
           tc_commit(bar_empty + 8 * s);
         }
         tc_commit(bar_acc);
         g += C;
       }
-      // ---- epilogue (all threads): row = tid, TMEM lane = tid
+      // ---- epilogue (all threads)
       mbar_wait(bar_acc, nacc & 1);
       ++nacc;
       tc_fence_after();
-      const bool last = (l == p.nlayers - 1);
       // 8 warps: warp w reads TMEM lanes 32 (w % 4) .. +31 (a warp can only reach its own lane quarter); the two warps
       // of a quarter alternate 16-column chunks
       const int row = (warp & 3) * 32 + (tid & 31), env = tile * POL_TILE_M + row;
@@ -194,19 +199,36 @@ __global__ void __launch_bounds__(256, 1) k_policy_mlp(const __grid_constant__ P
         } else if (env < num_envs) {
 #pragma unroll
           for (int q = 0; q < 16; ++q) {
-            const int c = c0 + q;
-            if (c < p.out_dim) action[(size_t)env * p.out_dim + c] = fminf(1.f, fmaxf(-1.f, __uint_as_float(r[q]) + __ldg(p.b[l] + c)));
+            const int c = nbase + c0 + q;
+            if (c < p.out_dim) {
+              const float y = __uint_as_float(r[q]) + __ldg(p.b[l] + c);
+              action[(size_t)env * p.out_dim + c] = p.raw_out == 0 ? fminf(1.f, fmaxf(-1.f, y)) : (p.raw_out == 2 ? activate(y, p.act) : y);
+            }
           }
         }
       }
       tc_fence_before();
       proxy_fence_async();
       __syncthreads();
+      }
     }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
+}
+
+// LSTM cell update (ONNX LSTM op, gate order i, o, f, c; used by LSTMPolicy, core/policy.py:24-47): gates = W x + R h + b
+// come from k_policy_mlp with raw output; c and h are updated in place.
+__global__ void k_lstm_cell(const float* __restrict__ gates, float* __restrict__ c, float* __restrict__ h, int num_envs, int H) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)num_envs * H) return;
+  const int e = (int)(t / H), j = (int)(t - (long long)e * H);
+  const float* g = gates + (size_t)e * 4 * H;
+  const float gi = 1.f / (1.f + __expf(-g[j])), go = 1.f / (1.f + __expf(-g[H + j])), gf = 1.f / (1.f + __expf(-g[2 * H + j])), gc = tanhf(g[3 * H + j]);
+  const float cn = gf * c[t] + gi * gc;
+  c[t] = cn;
+  h[t] = go * tanhf(cn);
 }
 
 // ------------------------------------------------------------------------------------------ host side
@@ -227,16 +249,21 @@ extern "C" {
 
 int cosim_policy_create(int device, int nlayers, const int* dims, const float* const* weights_host, const float* const* biases_host,
                         int activation, cosim_policy** out) {
+  const int raw_out = (activation >> 8) & 3;       // 1 = COSIM_POLICY_RAW_OUTPUT, 2 = COSIM_POLICY_ACTIVATED_OUTPUT
+  activation &= 0xff;
   if (!out || !dims || !weights_host || !biases_host || nlayers < 1 || nlayers > POL_MAX_LAYERS || activation < 0 || activation > 2) return COSIM_ERR_ARG;
   *out = nullptr;
-  for (int l = 0; l <= nlayers; ++l) if (dims[l] < 1 || dims[l] > POL_MAX_WIDTH) { fprintf(stderr, "cosim_policy_create: layer width %d outside [1, %d]\n", dims[l], POL_MAX_WIDTH); return COSIM_ERR_ARG; }
+  for (int l = 0; l <= nlayers; ++l) {
+    const int lim = (l == nlayers) ? 4 * POL_MAX_WIDTH : POL_MAX_WIDTH;       // only the output may be wider than one TMEM pass
+    if (dims[l] < 1 || dims[l] > lim) { fprintf(stderr, "cosim_policy_create: layer width %d outside [1, %d]\n", dims[l], lim); return COSIM_ERR_ARG; }
+  }
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { fprintf(stderr, "cosim_b200: no CUDA device -- the policy has no CPU path\n"); return COSIM_ERR_CUDA; }
   if (cudaSetDevice(device) != cudaSuccess) return COSIM_ERR_CUDA;
   cosim_policy* p = new cosim_policy;
   p->device = device;
   memset(&p->d, 0, sizeof(p->d));
-  p->d.nlayers = nlayers; p->d.act = activation; p->d.in_dim = dims[0]; p->d.out_dim = dims[nlayers];
+  p->d.nlayers = nlayers; p->d.act = activation; p->d.in_dim = dims[0]; p->d.out_dim = dims[nlayers]; p->d.raw_out = raw_out;
   cudaDeviceProp prop; if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) p->sms = prop.multiProcessorCount;
   for (int l = 0; l < nlayers; ++l) {
     const int kin = dims[l], nout = dims[l + 1];
@@ -288,5 +315,12 @@ int cosim_policy_forward(cosim_policy* p, const float* state, int num_envs, floa
   return cudaGetLastError() == cudaSuccess ? COSIM_OK : COSIM_ERR_CUDA;
 }
 int cosim_policy_launch_count(const cosim_policy* p) { return p ? p->launches : COSIM_ERR_ARG; }
+
+int cosim_lstm_cell(const float* gates, float* c, float* h, int num_envs, int hidden, void* stream) {
+  if (!gates || !c || !h || num_envs <= 0 || hidden <= 0) return COSIM_ERR_ARG;
+  const long long n = (long long)num_envs * hidden;
+  k_lstm_cell<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(gates, c, h, num_envs, hidden);
+  return cudaGetLastError() == cudaSuccess ? COSIM_OK : COSIM_ERR_CUDA;
+}
 
 }  // extern "C"

@@ -227,6 +227,23 @@ class BatchedEnv:
         p = lambda a: None if a is None else a.ctypes.data_as(ctypes.c_void_p)
         self._check(self._L.cosim_step_host(self._h, p(action), p(command), p(state_out), p(terminated_out), p(truncated_out)), "cosim_step_host")
 
+    def step_policy_host(self, policy, user_command_host, state_out_host, terminated_out_host, truncated_out_host):
+        """One control step of the whole loop body of core/tester.py:66-97 with HOST I/O: the user commands of this step come
+        from (pinned) host memory, the policy runs on the device-resident state of the previous step, the new state and
+        the done flags are copied back to (pinned) host memory, and the call returns after a stream sync."""
+        assert self.reset_flag is True, "Call 'reset()' before calling 'step()'."
+        if self.command_dim > 0:
+            self._uc_stage = getattr(self, "_uc_stage", None)
+            if self._uc_stage is None:
+                self._uc_stage = torch.empty((self.num_envs, self.command_dim), dtype=torch.float32, device=self.device)
+            self._uc_stage.copy_(_as_cpu_tensor(user_command_host), non_blocking=True)          # H2D: this step's inputs
+            self.receive_user_command(self._uc_stage)
+        state, term, trunc, _ = self.step(policy.get_action(self._state))
+        _as_cpu_tensor(state_out_host).copy_(state, non_blocking=True)                        # D2H: this step's results
+        _as_cpu_tensor(terminated_out_host).copy_(self._term, non_blocking=True)
+        _as_cpu_tensor(truncated_out_host).copy_(self._trunc, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+
     def substep(self):
         """One raw physics sub-step with ctrl = last applied torque (parity aid, see cosim_substep)."""
         self._check(self._L.cosim_substep(self._h, self._stream()), "cosim_substep")
@@ -269,6 +286,11 @@ class BatchedEnv:
         if clear:
             self._check(self._L.cosim_stats_clear(self._h, self._stream()), "cosim_stats_clear")
         return derive_stats(s.cpu().numpy(), self.action_dim)
+
+
+def _as_cpu_tensor(x):
+    """numpy array or CPU tensor (ideally pinned) -> CPU tensor sharing the memory."""
+    return x if torch.is_tensor(x) else torch.from_numpy(x)
 
 
 def all_reduce_stats(s):

@@ -93,6 +93,7 @@ def lib():
         L.cosim_policy_destroy.restype = None
         L.cosim_policy_forward.argtypes = [vp, vp, i32, vp, vp]
         L.cosim_policy_launch_count.argtypes = [vp]
+        L.cosim_lstm_cell.argtypes = [vp, vp, vp, i32, i32, vp]
     _lib = L
     return L
 
@@ -101,4 +102,4 @@ EXPORTS = ["cosim_create", "cosim_destroy", "cosim_last_error", "cosim_reset", "
            "cosim_push", "cosim_substep", "cosim_field_dim", "cosim_field_is_int", "cosim_get", "cosim_set", "cosim_set_debug",
            "cosim_stats_reduce", "cosim_stats_clear", "cosim_rng_probe", "cosim_num_envs", "cosim_dim",
            "cosim_launch_count", "cosim_smem_bytes_per_env", "cosim_warps_per_block",
-           "cosim_policy_create", "cosim_policy_destroy", "cosim_policy_forward", "cosim_policy_launch_count"]
+           "cosim_policy_create", "cosim_policy_destroy", "cosim_policy_forward", "cosim_policy_launch_count", "cosim_lstm_cell"]

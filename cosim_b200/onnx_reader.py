@@ -116,14 +116,43 @@ def read_graph(path):
     return nodes, inits
 
 
-_PASS = {"Identity", "Flatten", "Reshape", "Squeeze", "Unsqueeze", "Cast", "Dropout"}
+_PASS = {"Identity", "Flatten", "Reshape", "Squeeze", "Unsqueeze", "Cast", "Dropout", "Transpose", "Concat", "Slice", "Gather", "Shape"}
 _ACT = {"Elu": "elu", "Tanh": "tanh", "Relu": "relu"}
 
 
-def load_mlp(path):
-    """-> (layers [(W[out, in], b[out]), ...], activation name).  The output clip to [-1, 1] is applied by the policy kernel
-    (core/policy.py:20), so a trailing Clip node is accepted and dropped."""
+def load_policy(path):
+    """-> {"kind": "mlp", "layers", "activation"} or {"kind": "lstm", "pre", "lstm": (W[4H,in], R[4H,H], B[8H]), "post", "activation"}.
+    An LSTM graph is a chain  [MLP encoder] -> LSTM (one direction, ONNX gate order i, o, f, c) -> [MLP head]."""
     nodes, inits = read_graph(path)
+    k = [i for i, n in enumerate(nodes) if n[0] == "LSTM"]
+    if not k:
+        layers, act = _chain(nodes, inits)
+        return {"kind": "mlp", "layers": layers, "activation": act or "elu"}
+    if len(k) > 1:
+        raise ValueError("more than one LSTM node is not supported")
+    op, ins, outs, attrs = nodes[k[0]]
+    W, R = inits[ins[1]], inits[ins[2]]
+    if W.shape[0] != 1 or attrs.get("direction", 0) not in (0, None):
+        raise ValueError("only single-direction LSTMs are supported")
+    H = R.shape[2]
+    B = inits[ins[3]][0] if len(ins) > 3 and ins[3] in inits else np.zeros(8 * H, np.float32)
+    pre, act1 = _chain(nodes[:k[0]], inits, allow_empty=True)
+    pre_ops = [n[0] for n in nodes[:k[0]] if n[0] in _ACT or n[0] in ("Gemm", "MatMul", "Add")]
+    pre_activated = bool(pre_ops) and pre_ops[-1] in _ACT          # is the encoder's last linear layer followed by the activation?
+    post, act2 = _chain(nodes[k[0] + 1:], inits, allow_empty=True)
+    return {"kind": "lstm", "pre": pre, "post": post, "lstm": (np.ascontiguousarray(W[0], np.float32), np.ascontiguousarray(R[0], np.float32),
+            np.ascontiguousarray(B, np.float32)), "activation": act1 or act2 or "elu", "pre_activated": pre_activated}
+
+
+def load_mlp(path):
+    nodes, inits = read_graph(path)
+    layers, act = _chain(nodes, inits)
+    return layers, act or "elu"
+
+
+def _chain(nodes, inits, allow_empty=False):
+    """-> (layers [(W[out, in], b[out]), ...], activation name or None).  The output clip to [-1, 1] is applied by the policy
+    kernel (core/policy.py:20), so a trailing Clip node is accepted and dropped."""
     layers, act, pending = [], None, None
     for op, ins, outs, attrs in nodes:
         if op == "Gemm":
@@ -149,9 +178,9 @@ def load_mlp(path):
             continue
         else:
             raise ValueError(f"unsupported ONNX op '{op}' in an MLP policy")
-    if not layers:
+    if not layers and not allow_empty:
         raise ValueError("no Gemm / MatMul layers found")
     for (w0, _), (w1, _) in zip(layers[:-1], layers[1:]):
         if w1.shape[1] != w0.shape[0]:
             raise ValueError("layer shapes do not chain")
-    return layers, act or "elu"
+    return layers, act

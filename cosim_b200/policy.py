@@ -28,7 +28,7 @@ def synthetic_mlp(state_dim, action_dim, hidden=(512, 256, 128), seed=1234):
 
 
 class MLPPolicy:
-    def __init__(self, layers, activation="elu", device="cuda:0"):
+    def __init__(self, layers, activation="elu", device="cuda:0", raw_output=False, activated_output=False):
         if not torch.cuda.is_available():
             raise RuntimeError("cosim_b200 policy needs a CUDA device (sm_100a); there is no CPU path")
         self.device = torch.device(device)
@@ -45,7 +45,10 @@ class MLPPolicy:
         bp = (ctypes.c_void_p * n)(*[b.ctypes.data for _, b in self.layers])
         self._h = ctypes.c_void_p()
         idx = self.device.index if self.device.index is not None else torch.cuda.current_device()
-        rc = self._L.cosim_policy_create(idx, n, d, wp, bp, ACTIVATIONS[activation], ctypes.byref(self._h))
+        self.raw_output = bool(raw_output)     # plain linear output of the last layer, no clip (LSTM gates / encoders)
+        self.activated_output = bool(activated_output)   # hidden activation on the output instead of the clip (encoders)
+        flags = 0x200 if activated_output else (0x100 if raw_output else 0)
+        rc = self._L.cosim_policy_create(idx, n, d, wp, bp, ACTIVATIONS[activation] | flags, ctypes.byref(self._h))
         if rc != 0:
             raise RuntimeError(f"cosim_policy_create failed with code {rc}")
         self._action = None
@@ -93,7 +96,9 @@ class MLPPolicy:
             x = rnd(x) @ wt.t() + torch.from_numpy(b).to(self.device)
             if i < len(self.layers) - 1:
                 x = f(x)
-        return x.clamp(-1, 1)
+        if self.activated_output:
+            return f(x)
+        return x if self.raw_output else x.clamp(-1, 1)
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h:
@@ -107,13 +112,88 @@ class MLPPolicy:
             pass
 
 
+class LSTMPolicy:
+    """Batched drop-in for core/policy.py:24-47 (LSTMPolicy): action = clip(head(LSTM(encoder(state), h, c))), h and c carried
+    from step to step per environment (zeros at start, as in the reference).  Every matrix product runs in the tcgen05
+    kernel: encoder (optional MLP), gate pre-activations [x | h] -> 4H (ONNX gate order i, o, f, c), head MLP; the cell
+    update is the elementwise kernel k_lstm_cell."""
+
+    def __init__(self, lstm, pre_layers=(), post_layers=(), activation="elu", device="cuda:0", num_envs=1, pre_activated=True):
+        W, R, B = (np.asarray(a, np.float32) for a in lstm)          # W [4H, in], R [4H, H], B [8H] = [Wb | Rb]
+        self.H = R.shape[1]
+        assert W.shape[0] == 4 * self.H and R.shape[0] == 4 * self.H and B.shape == (8 * self.H,)
+        self.device = torch.device(device)
+        self.pre = MLPPolicy(list(pre_layers), activation, device, raw_output=not pre_activated, activated_output=pre_activated) if len(pre_layers) else None
+        self.gates = MLPPolicy([(np.concatenate([W, R], axis=1), B[:4 * self.H] + B[4 * self.H:])], activation, device, raw_output=True)
+        self.post = MLPPolicy(list(post_layers), activation, device) if len(post_layers) else None
+        self.lstm = (W, R, B)
+        self.state_dim = self.pre.state_dim if self.pre else W.shape[1]
+        self.action_dim = self.post.action_dim if self.post else self.H
+        self._L = _libmod.lib()
+        self.reset(num_envs=num_envs)
+
+    def reset(self, mask=None, num_envs=None):
+        """Zero h / c (all environments, or the rows selected by `mask`)."""
+        if num_envs is not None:
+            self.h = torch.zeros((num_envs, self.H), dtype=torch.float32, device=self.device)
+            self.c = torch.zeros_like(self.h)
+        elif mask is None:
+            self.h.zero_(); self.c.zero_()
+        else:
+            m = torch.as_tensor(mask, device=self.device).bool()
+            self.h[m] = 0; self.c[m] = 0
+
+    def get_action(self, state):
+        state = torch.as_tensor(state, dtype=torch.float32, device=self.device)
+        squeeze = state.dim() == 1
+        if squeeze:
+            state = state.unsqueeze(0)
+        n = state.shape[0]
+        if self.h.shape[0] != n:
+            self.reset(num_envs=n)
+        x = self.pre.get_action(state) if self.pre else state
+        g = self.gates.get_action(torch.cat([x, self.h], dim=1))
+        stream = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        rc = self._L.cosim_lstm_cell(ctypes.c_void_p(g.data_ptr()), ctypes.c_void_p(self.c.data_ptr()), ctypes.c_void_p(self.h.data_ptr()), n, self.H, stream)
+        if rc != 0:
+            raise RuntimeError(f"cosim_lstm_cell failed with code {rc}")
+        a = self.post.get_action(self.h) if self.post else self.h.clamp(-1, 1)
+        return a[0] if squeeze else a
+
+    @property
+    def launch_count(self):
+        return sum(p.launch_count for p in (self.pre, self.gates, self.post) if p is not None)
+
+    def reference_forward(self, state, h, c, emulate_bf16=True):
+        """Plain PyTorch reference of one step: returns (action, h', c')."""
+        x = torch.as_tensor(state, dtype=torch.float32, device=self.device)
+        if self.pre:
+            x = self.pre.reference_forward(x, emulate_bf16)
+        g = self.gates.reference_forward(torch.cat([x, h], dim=1), emulate_bf16)
+        H = self.H
+        i, o, f, cc = torch.sigmoid(g[:, :H]), torch.sigmoid(g[:, H:2 * H]), torch.sigmoid(g[:, 2 * H:3 * H]), torch.tanh(g[:, 3 * H:])
+        c2 = f * c + i * cc
+        h2 = o * torch.tanh(c2)
+        a = self.post.reference_forward(h2, emulate_bf16) if self.post else h2.clamp(-1, 1)
+        return a, h2, c2
+
+    def close(self):
+        for p in (self.pre, self.gates, self.post):
+            if p is not None:
+                p.close()
+
+
 def build_policy(config, policy_path=None, state_dim=None, action_dim=None, device="cuda:0"):
     """core/policy.py:49-53.  MLP policies are read from the user's ONNX file (cosim_b200/onnx_reader.py); without a file the
-    synthetic MLP of SURVEY.md section 8d is used.  LSTM policies are a 'next' row."""
-    if config.get("policy", {}).get("use_lstm"):
-        raise NotImplementedError("LSTM policies are not implemented yet (SURVEY.md section 8f, row 1)")
+    synthetic MLP of SURVEY.md section 8d is used.  LSTM policies (core/policy.py:24-47) are read from ONNX too."""
     if policy_path:
-        from .onnx_reader import load_mlp
-        layers, act = load_mlp(policy_path)          # the user's ONNX file, as in core/policy.py:7-9
-        return MLPPolicy(layers, act, device)
+        from .onnx_reader import load_policy
+        spec = load_policy(policy_path)              # the user's ONNX file, as in core/policy.py:7-9 / 26-29
+        if bool(config.get("policy", {}).get("use_lstm")) != (spec["kind"] == "lstm"):
+            raise RuntimeError("config['policy']['use_lstm'] does not match the ONNX graph")
+        if spec["kind"] == "lstm":
+            return LSTMPolicy(spec["lstm"], spec["pre"], spec["post"], spec["activation"], device, pre_activated=spec["pre_activated"])
+        return MLPPolicy(spec["layers"], spec["activation"], device)
+    if config.get("policy", {}).get("use_lstm"):
+        raise RuntimeError("an LSTM policy needs an ONNX file")
     return MLPPolicy(synthetic_mlp(state_dim, action_dim), "elu", device)

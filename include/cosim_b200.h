@@ -94,6 +94,12 @@ int cosim_policy_create(int device, int nlayers, const int* dims, const float* c
 void cosim_policy_destroy(cosim_policy* p);
 int cosim_policy_forward(cosim_policy* p, const float* state, int num_envs, float* action_out, void* stream);
 int cosim_policy_launch_count(const cosim_policy* p);
+/* `activation | COSIM_POLICY_RAW_OUTPUT` in cosim_policy_create: the last layer writes its plain linear output (no clip) and
+ * may be up to 2048 wide -- used for the gate pre-activations of LSTMPolicy (core/policy.py:24-47). */
+#define COSIM_POLICY_RAW_OUTPUT 0x100
+#define COSIM_POLICY_ACTIVATED_OUTPUT 0x200   /* the output gets the hidden activation instead of the clip (encoders in front of an LSTM) */
+/* ONNX LSTM cell update, gate order i, o, f, c: gates [N][4H] -> c [N][H], h [N][H] updated in place (device pointers). */
+int cosim_lstm_cell(const float* gates, float* c, float* h, int num_envs, int hidden, void* stream);
 /* profiling builds only (-DCOSIM_PHASE_TIMING): per-phase cycle counters; zeros in the product build */
 int cosim_phase_cycles(cosim_handle* h, unsigned long long* out_host, int reset);
 

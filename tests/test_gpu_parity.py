@@ -358,3 +358,44 @@ def test_other_precision_presets(precision):
     errs = np.concatenate(errs)
     assert np.median(errs) < 5e-4 and (errs > 5e-2).mean() <= 0.1
     env.close()
+
+
+def test_step_policy_host_equals_device_loop():
+    """The e2e call (host commands in, host state out, policy on the device state) does the same as the device loop."""
+    from cosim_b200.policy import MLPPolicy, synthetic_mlp
+    N = 256
+    e1 = _env("flamingo_p_v3", "rocky_hard", N, random=RANDOM_DEFAULTS, debug=False, hm=True)
+    e2 = _env("flamingo_p_v3", "rocky_hard", N, random=RANDOM_DEFAULTS, debug=False, hm=True)
+    pol = MLPPolicy(synthetic_mlp(e1.state_dim, e1.action_dim), "elu")
+    cmd = np.random.default_rng(2).uniform(-1, 1, (N, e1.command_dim)).astype(np.float32)
+    s1, _ = e1.reset(); e2.reset()
+    pin = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory().numpy()
+    hs, hc, ht, hr = pin((N, e1.state_dim), torch.float32), pin((N, e1.command_dim), torch.float32), pin((N,), torch.uint8), pin((N,), torch.uint8)
+    hc[:] = cmd
+    for _ in range(4):
+        e1.receive_user_command(cmd)
+        s1, t1, r1, _ = e1.step(pol.get_action(s1).clone())
+        e2.step_policy_host(pol, hc, hs, ht, hr)
+        assert (s1.cpu().numpy() == hs).all() and (t1.cpu().numpy() == ht.astype(bool)).all()
+    e1.close(); e2.close(); pol.close()
+
+
+def test_lstm_policy_matches_torch_reference():
+    """LSTMPolicy (core/policy.py:24-47): encoder -> LSTM(H = 256, ONNX gate order iofc) -> head, h / c carried per env."""
+    from cosim_b200.policy import LSTMPolicy
+    rng = np.random.default_rng(4)
+    sd, E, H, nu, N = 88, 128, 256, 8, 300
+    g = lambda *s: (rng.standard_normal(s) / np.sqrt(s[-1])).astype(np.float32)
+    pol = LSTMPolicy((g(4 * H, E), g(4 * H, H), 0.1 * g(8 * H)), pre_layers=[(g(E, sd), 0.1 * g(E))], post_layers=[(g(64, H), 0.1 * g(64)), (g(nu, 64), 0.1 * g(nu))],
+                     activation="elu", num_envs=N)
+    h = torch.zeros((N, H), device="cuda"); c = torch.zeros((N, H), device="cuda")
+    for t in range(4):
+        x = torch.randn((N, sd), device="cuda")
+        ref, h, c = pol.reference_forward(x, h, c)
+        got = pol.get_action(x)
+        assert got.shape == (N, nu) and (got - ref).abs().max().item() < 3e-2
+        assert (pol.h - h).abs().max().item() < 3e-2 and (pol.c - c).abs().max().item() < 3e-2
+        h, c = pol.h.clone(), pol.c.clone()          # keep the reference on the engine's trajectory
+    pol.reset(mask=torch.arange(N) < 10)
+    assert pol.h[:10].abs().max() == 0 and pol.h[10:].abs().max() > 0
+    pol.close()

@@ -65,3 +65,22 @@ def test_rejects_unsupported_ops(tmp_path):
     path.write_bytes(_model([_node("LSTM", ["x"], ["y"])], []))
     with pytest.raises(ValueError):
         load_mlp(str(path))
+
+
+def test_lstm_graph(tmp_path):
+    from cosim_b200.onnx_reader import load_policy
+    rng = np.random.default_rng(1)
+    H, nin = 8, 6
+    we, be = rng.standard_normal((nin, 5)).astype(np.float32), rng.standard_normal(nin).astype(np.float32)
+    W, R, B = rng.standard_normal((1, 4 * H, nin)).astype(np.float32), rng.standard_normal((1, 4 * H, H)).astype(np.float32), rng.standard_normal((1, 8 * H)).astype(np.float32)
+    wh, bh = rng.standard_normal((3, H)).astype(np.float32), rng.standard_normal(3).astype(np.float32)
+    nodes = [_node("Gemm", ["state", "we", "be"], ["e"], {"transB": 1}), _node("Tanh", ["e"], ["ea"]), _node("Unsqueeze", ["ea"], ["x"]),
+             _node("LSTM", ["x", "W", "R", "B", "", "h_in", "c_in"], ["y", "h_out", "c_out"], {"hidden_size": H}),
+             _node("Squeeze", ["y"], ["ys"]), _node("Gemm", ["ys", "wh", "bh"], ["action"], {"transB": 1})]
+    inits = [_tensor("we", we), _tensor("be", be), _tensor("W", W), _tensor("R", R), _tensor("B", B), _tensor("wh", wh), _tensor("bh", bh)]
+    path = tmp_path / "lstm.onnx"
+    path.write_bytes(_model(nodes, inits))
+    spec = load_policy(str(path))
+    assert spec["kind"] == "lstm" and spec["activation"] == "tanh" and spec["pre_activated"]
+    np.testing.assert_array_equal(spec["pre"][0][0], we); np.testing.assert_array_equal(spec["post"][0][0], wh)
+    np.testing.assert_array_equal(spec["lstm"][0], W[0]); np.testing.assert_array_equal(spec["lstm"][1], R[0]); np.testing.assert_array_equal(spec["lstm"][2], B[0])
