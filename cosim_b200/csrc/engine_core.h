@@ -73,7 +73,8 @@ DEV void wargmax(float& v, int& i) {
 #endif
 
 // optional per-phase cycle counters (profiling builds only: -DCOSIM_PHASE_TIMING)
-enum { PH_KIN = 0, PH_COLLIDE, PH_CONSTRAINT, PH_SMOOTH, PH_NEWTON, PH_INTEGRATE, PH_OBS, PH_IO, PH_NEWTON_ITERS, PH_LS_EVALS, PH_SUPPORT_CALLS, PH_MPR_CALLS, PH__COUNT = 16 };
+enum { PH_KIN = 0, PH_COLLIDE, PH_CONSTRAINT, PH_SMOOTH, PH_NEWTON, PH_INTEGRATE, PH_OBS, PH_IO, PH_NEWTON_ITERS, PH_LS_EVALS, PH_SUPPORT_CALLS, PH_MPR_CALLS,
+       PH_WAIT_KIN, PH_WAIT_COLLIDE, PH_WAIT_SMOOTH, PH_WAIT_NEWTON, PH__COUNT = 16 };     // PH_WAIT_*: cycles spent at the barrier that ends the phase
 #if defined(COSIM_PHASE_TIMING) && !defined(COSIM_HOST_EMU)
 #define PH_DECL long long ph_t0_ = clock64()
 #define PH_MARK(k) do { long long t_ = clock64(); if (lane == 0) atomicAdd((unsigned long long*)m.phase + (k), (unsigned long long)(t_ - ph_t0_)); ph_t0_ = clock64(); } while (0)
@@ -1535,6 +1536,7 @@ DEV_NOINLINE int forward(const ModelDev& m, float* ws, int lane, int active = 1,
   }
   PH_MARK(PH_KIN);
   BSYNC_IF(bsync, 0);
+  PH_MARK(PH_WAIT_KIN);
   if (active) {           // ---- phase 2: collision
     if (MD(ground_type) == 1) collide_hfield_all(m, ws, lane);
     else {
@@ -1545,6 +1547,7 @@ DEV_NOINLINE int forward(const ModelDev& m, float* ws, int lane, int active = 1,
   }
   PH_MARK(PH_COLLIDE);
   BSYNC_IF(bsync, 1);
+  PH_MARK(PH_WAIT_COLLIDE);
   if (active) {           // ---- phase 3: constraint rows, sensors, smooth forces and acceleration
     ncon = WSI(W_CNT)[CNT_NCON];
     com_vel(m, ws, lane);
@@ -1574,6 +1577,7 @@ DEV_NOINLINE int forward(const ModelDev& m, float* ws, int lane, int active = 1,
   }
   PH_MARK(PH_SMOOTH);
   BSYNC_IF(bsync, 2);
+  PH_MARK(PH_WAIT_SMOOTH);
   if (active) {           // ---- phase 4: constraint solve
     ncon = WSI(W_CNT)[CNT_NCON];
     iters = newton_solve(m, ws, ncon, rows, lane);
@@ -1581,6 +1585,7 @@ DEV_NOINLINE int forward(const ModelDev& m, float* ws, int lane, int active = 1,
   }
   PH_MARK(PH_NEWTON);
   BSYNC_IF(bsync, 3);
+  PH_MARK(PH_WAIT_NEWTON);
   return iters;
 }
 

@@ -15,7 +15,8 @@ import torch
 from cosim_b200.config import make_config, RANDOM_FULL
 from cosim_b200.envs import BatchedEnv
 
-NAMES = ["kin+crb+chol", "collide", "constraint", "smooth", "newton", "integrate", "obs", "io", "newton_iters", "ls_evals", "support_calls", "mpr_calls"]
+NAMES = ["kin+crb+chol", "collide", "constraint", "smooth", "newton", "integrate", "obs", "io", "newton_iters", "ls_evals", "support_calls", "mpr_calls",
+         "wait after kin", "wait after collide", "wait after smooth", "wait after newton"]
 
 def run(robot, terrain, N, steps):
     cfg = make_config(robot, terrain, random=RANDOM_FULL, engine={"auto_reset": True})
@@ -33,11 +34,13 @@ def run(robot, terrain, N, steps):
     torch.cuda.synchronize(); dt = time.time() - t
     lib.cosim_phase_cycles(env._h, buf, 1)
     v = list(buf)
-    tot = sum(v[:8])
+    tot = sum(v[:8]) + sum(v[12:16])
     nsub = N * steps * 4
     print(f"{robot} {terrain} N={N}: {dt / steps * 1e3:.2f} ms/step, {N * steps / dt / 1e6:.3f} M env-steps/s; smem/env {lib.cosim_smem_bytes_per_env(env._h)} wpb {lib.cosim_warps_per_block(env._h)}")
     for i in range(8):
         print(f"  {NAMES[i]:14s} {100.0 * v[i] / max(tot, 1):5.1f} %   {v[i] / nsub:10.0f} cycles/sub-step")
+    for i in range(12, 16):
+        print(f"  {NAMES[i]:18s} {100.0 * v[i] / max(tot, 1):5.1f} %   {v[i] / nsub:10.0f} cycles/sub-step")
     for i in range(8, 12):
         print(f"  {NAMES[i]:14s} {v[i] / nsub:8.2f} per sub-step")
     print("  stats:", {k: round(x, 3) for k, x in env.stats().items() if k in ("mean_contacts", "mean_solver_iters_per_step", "termination_rate", "episodes")})
