@@ -33,6 +33,7 @@ struct float4 { float x, y, z, w; };
 
 #ifdef COSIM_HOST_EMU
 #define DEV static inline
+#define DEVM inline                      /* member functions */
 #define DEV_NOINLINE static
 #define LANES 1
 #define SYNC() ((void)0)
@@ -43,8 +44,17 @@ static inline float wmaxf(float v) { return v; }
 static inline int wor(int v) { return v; }
 static inline void wargmax(float& v, int& i) {}
 static inline float fast_ndtri(float p);
+static inline int popc32(unsigned x) { return __builtin_popcount(x); }
+static inline int __float_as_int_emu(float f) { int i; memcpy(&i, &f, 4); return i; }
+static inline float __int_as_float_emu(int i) { float f; memcpy(&f, &i, 4); return f; }
+static inline int ctz32(unsigned x) { return __builtin_ctz(x); }
 #else
 #define DEV __device__ __forceinline__
+#define DEVM __device__ __forceinline__
+__device__ __forceinline__ int popc32(unsigned x) { return __popc(x); }
+__device__ __forceinline__ int __float_as_int_emu(float f) { return __float_as_int(f); }
+__device__ __forceinline__ float __int_as_float_emu(int i) { return __int_as_float(i); }
+__device__ __forceinline__ int ctz32(unsigned x) { return __ffs(x) - 1; }
 #define DEV_NOINLINE __device__ __noinline__
 #define LANES 32
 #define SYNC() __syncwarp()
@@ -123,6 +133,8 @@ struct ModelDev {
   const int *dof_body, *dof_jnt, *dof_parent, *dof_fl_random;
   const float *dof_armature, *dof_damping, *dof_frictionloss;
   const int *mpair_i, *mpair_j; int nmpair;
+  const int* pair_geom;                        // [npair][2] geom-geom candidates (cosim_b200/model.py self_collision_pairs)
+  const float* geom_aabb;                      // [ngeom][6] geom-frame box: centre, half extents
   const float *qpos0;
   // actuators + PD tables
   const int *act_dof, *act_qadr, *act_mode, *act_ctrllimited;
@@ -167,7 +179,7 @@ enum WsField {
   W_BMASS, W_INVWD, W_INVWB, W_FLOSS, W_GMU, W_SCAL,
   W_FR_D, W_FR_AREF, W_LM_SIGN, W_LM_D, W_LM_AREF,
   W_CN_POS, W_CN_FRAME, W_CN_DIST, W_CN_MU, W_CN_BODY, W_CN_GEOM, W_CN_CELL, W_CN_D, W_CN_AREF, W_CN_J, W_CN_F, W_CN_X, W_CN_V,
-  W_EQ_J, W_EQ_D, W_EQ_AREF, W_EQ_X, W_EQ_V, W_EQ_F, W_SENS, W_RAW, W_ACT, W_FILT, W_KP, W_KD, W_GTASK, W_CNT, W__COUNT   // keep <= 80 (ModelDev::off)
+  W_EQ_J, W_EQ_D, W_EQ_AREF, W_EQ_X, W_EQ_V, W_EQ_F, W_SENS, W_RAW, W_ACT, W_FILT, W_KP, W_KD, W_GTASK, W_CNT, W_PAXIS, W__COUNT   // keep <= 80 (ModelDev::off)
 };
 static_assert(W__COUNT <= 80, "ModelDev::off too small");
 #define WS(f) (ws + m.off[f])
@@ -181,6 +193,7 @@ enum { CNT_NCON = 0, CNT_DROPPED = 1, CNT_NAN = 2, CNT_DROPPED_STEP = 3 };
 struct EnvArrays {
   int N;
   float *qpos, *qvel, *warm;
+  float *paxis;      // [N][4 * PAXIS_SLOTS] cached separating axes of geom-geom pairs (pair id + 1, axis in the first geom's frame)
   float *body_mass, *invw_dof, *invw_body, *floss, *gmu, *scal, *kp, *kd;
   float *prev_action, *delay_prev, *obs_buffer, *freq_cache, *torque, *info, *last_action;
   int *counters;     // [N][8]: sim_step, has_delay_prev, n_reset, n_obs, n_step, nan_count, need_reset, ncon
@@ -189,6 +202,7 @@ struct EnvArrays {
   // optional debug dumps (NULL when disabled)
   float *dbg_contacts, *dbg_heightmap, *dbg_cfrc, *dbg_sens, *dbg_qacc; int *dbg_hmcell, *dbg_iters;
 };
+enum { PAXIS_SLOTS = 8 };
 enum { CT_SIM_STEP = 0, CT_HAS_DELAY = 1, CT_NRESET = 2, CT_NOBS = 3, CT_NSTEP = 4, CT_NAN = 5, CT_NEED_RESET = 6, CT_NCON = 7 };
 // per-env episode statistics accumulated on device (reporter semantics)
 enum { ST_STEPS = 0, ST_EPISODES, ST_SUCCESS, ST_TERMINATED, ST_ERR_VX, ST_ERR_VY, ST_ERR_WZ, ST_RMSE, ST_ABS_TORQUE, ST_SQ_TORQUE, ST_MAX_TORQUE, ST_NCON, ST_ITERS, ST_DROPPED, ST_NAN, ST__COUNT = 16 };
@@ -730,75 +744,100 @@ DEV void prism_vertex(const PrismL& P, int i, float* v) {
 }
 #define GQ_PARAMS const ModelDev& m, const float* ws, int g, int grp, unsigned gmask, float ox, float oy
 #define GQ_ARGS m, ws, g, grp, gmask, ox, oy
-DEV PV mink_lane(const PrismL& P, GQ_PARAMS, float dx, float dy, float dz) {
-  int best = 0; float bv = 0.f, bx = 0.f, by = 0.f, bz = 0.f;
+// First MPR object ("shape A"): a terrain prism (mjc_ConvexHField) or a convex geom (mjc_Convex).  A shape provides its
+// portal-vertex type PV (Minkowski-difference point x, y, z + what it needs to recover the witness on A), the Minkowski
+// support, the interior-point vertex p0 and the witness lookup.  The second object is always geom g (GQ_PARAMS).
+struct PrismA {
+  typedef ::PV PV;
+  PrismL P;
+  DEVM PV mink(GQ_PARAMS, float dx, float dy, float dz) const {
+    int best = 0; float bv = 0.f, bx = 0.f, by = 0.f, bz = 0.f;
 #pragma unroll
-  for (int i = 0; i < 6; ++i) {
-    const int c = i >= 3 ? i - 3 : i;
-    const float vx = P.x[c], vy = P.y[c], vz = i >= 3 ? P.z[c] : -P.base;
-    const float v = vx * dx + vy * dy + vz * dz;
-    if (i == 0 || v > bv) { bv = v; best = i; bx = vx; by = vy; bz = vz; }
+    for (int i = 0; i < 6; ++i) {
+      const int c = i >= 3 ? i - 3 : i;
+      const float vx = P.x[c], vy = P.y[c], vz = i >= 3 ? P.z[c] : -P.base;
+      const float v = vx * dx + vy * dy + vz * dz;
+      if (i == 0 || v > bv) { bv = v; best = i; bx = vx; by = vy; bz = vz; }
+    }
+    const F3 s2 = support_lane(GQ_ARGS, -dx, -dy, -dz);
+    PV r; r.x = bx - s2.x; r.y = by - s2.y; r.z = bz - s2.z; r.pi = best;
+    return r;
   }
-  const F3 s2 = support_lane(GQ_ARGS, -dx, -dy, -dz);
-  PV r; r.x = bx - s2.x; r.y = by - s2.y; r.z = bz - s2.z; r.pi = best;
-  return r;
-}
-DEV float pv_dot(const PV& a, float x, float y, float z) { return a.x * x + a.y * y + a.z * z; }
-DEV void pv_portal_dir(const PV& p1, const PV& p2, const PV& p3, float* dir) {
+  DEVM void center(float* c1) const {
+    c1[0] = c1[1] = c1[2] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) { float v[3]; prism_vertex(P, i, v); v3add(c1, c1, v); }
+    v3scl(c1, c1, 1.f / 6.f);
+  }
+  DEVM PV make_p0(const float* c1, const float* gcenter) const { PV p; p.x = c1[0] - gcenter[0]; p.y = c1[1] - gcenter[1]; p.z = c1[2] - gcenter[2]; p.pi = -1; return p; }
+  // witness on the prism: exact vertex (or the centre for p0)
+  DEVM void witness(const PV& p, const float* c1, float* v1) const { if (p.pi < 0) v3copy(v1, c1); else prism_vertex(P, p.pi, v1); }
+};
+struct PVG { float x, y, z, wx, wy, wz; };     // Minkowski-difference vertex + its witness point on the first geom
+struct GeomA {
+  typedef PVG PV;
+  int g1; float c[3];                          // first geom and its centre in the local frame
+  DEVM PV mink(GQ_PARAMS, float dx, float dy, float dz) const {
+    const F3 s1 = support_lane(m, ws, g1, grp, gmask, ox, oy, dx, dy, dz);
+    const F3 s2 = support_lane(GQ_ARGS, -dx, -dy, -dz);
+    PV r; r.x = s1.x - s2.x; r.y = s1.y - s2.y; r.z = s1.z - s2.z; r.wx = s1.x; r.wy = s1.y; r.wz = s1.z;
+    return r;
+  }
+  DEVM void center(float* c1) const { v3copy(c1, c); }
+  DEVM PV make_p0(const float* c1, const float* gcenter) const { PV p; p.x = c1[0] - gcenter[0]; p.y = c1[1] - gcenter[1]; p.z = c1[2] - gcenter[2]; p.wx = c1[0]; p.wy = c1[1]; p.wz = c1[2]; return p; }
+  DEVM void witness(const PV& p, const float*, float* v1) const { v1[0] = p.wx; v1[1] = p.wy; v1[2] = p.wz; }
+};
+template <class V> DEV float pv_dot(const V& a, float x, float y, float z) { return a.x * x + a.y * y + a.z * z; }
+template <class V> DEV void pv_portal_dir(const V& p1, const V& p2, const V& p3, float* dir) {
   float a[3] = {p2.x - p1.x, p2.y - p1.y, p2.z - p1.z}, b[3] = {p3.x - p1.x, p3.y - p1.y, p3.z - p1.z};
   v3cross(dir, a, b); v3normalize(dir);
 }
-DEV bool pv_reach_tol(const PV& p1, const PV& p2, const PV& p3, const PV& v4, const float* dir, float tol) {
+template <class V> DEV bool pv_reach_tol(const V& p1, const V& p2, const V& p3, const V& v4, const float* dir, float tol) {
   const float dv1 = pv_dot(p1, dir[0], dir[1], dir[2]), dv2 = pv_dot(p2, dir[0], dir[1], dir[2]), dv3 = pv_dot(p3, dir[0], dir[1], dir[2]), dv4 = pv_dot(v4, dir[0], dir[1], dir[2]);
   const float dm = fminf(dv4 - dv1, fminf(dv4 - dv2, dv4 - dv3));
   return f_eq(dm, tol) || dm < tol;
 }
-DEV void pv_expand(const PV& p0, PV& p1, PV& p2, PV& p3, const PV& v4) {
+template <class V> DEV void pv_expand(const V& p0, V& p1, V& p2, V& p3, const V& v4) {
   const float a[3] = {v4.x, v4.y, v4.z}, b[3] = {p0.x, p0.y, p0.z};
   float c[3]; v3cross(c, a, b);
   float dot = pv_dot(p1, c[0], c[1], c[2]);
   if (dot > 0.f) { dot = pv_dot(p2, c[0], c[1], c[2]); if (dot > 0.f) p1 = v4; else p3 = v4; }
   else { dot = pv_dot(p3, c[0], c[1], c[2]); if (dot > 0.f) p2 = v4; else p1 = v4; }
 }
-// witness points of a portal vertex: v1 on the prism (exact), v2 = v1 - v on the geom
-DEV void pv_witness(const PrismL& P, const PV& p, const float* c1, float* v1) { if (p.pi < 0) v3copy(v1, c1); else prism_vertex(P, p.pi, v1); }
-// MPR (XenoCollide) penetration query, restating libccd ccdMPRPenetration as driven by mjc_ConvexHField (oracle/oracle.hpp
-// mpr_penetration is the readable fp64 version); 0 = hit.  Run by one lane, or by a group of lanes in lock step that
-// share the hull support scans (grp = sub | gsize << 8).
-DEV int mpr_lane(const PrismL& P, GQ_PARAMS, const float* gcenter, float* depth, float* dir_out, float* pos) {
+// MPR (XenoCollide) penetration query, restating libccd ccdMPRPenetration as driven by mjc_ConvexHField / mjc_Convex
+// (oracle/oracle.hpp mpr_core is the readable fp64 version); 0 = hit.  Run by one lane, or by a group of lanes in lock
+// step that share the hull support scans (grp = sub | gsize << 8).
+template <class A> DEV int mpr_lane(const A& P, GQ_PARAMS, const float* gcenter, float* depth, float* dir_out, float* pos) {
+  typedef typename A::PV PV;
   const float tol = MO(ccd_tolerance); const int maxit = MD(ccd_iterations);
-  float c1[3] = {0.f, 0.f, 0.f};
-#pragma unroll
-  for (int i = 0; i < 6; ++i) { float v[3]; prism_vertex(P, i, v); v3add(c1, c1, v); }
-  v3scl(c1, c1, 1.f / 6.f);
-  PV p0, p1, p2, p3;
-  p0.x = c1[0] - gcenter[0]; p0.y = c1[1] - gcenter[1]; p0.z = c1[2] - gcenter[2]; p0.pi = -1;
+  float c1[3]; P.center(c1);
+  PV p0 = P.make_p0(c1, gcenter), p1, p2, p3;
   if (f_eq(p0.x, 0.f) && f_eq(p0.y, 0.f) && f_eq(p0.z, 0.f)) p0.x += CCD_EPS * 10.f;
   float dir[3] = {-p0.x, -p0.y, -p0.z}; v3normalize(dir);
-  p1 = mink_lane(P, GQ_ARGS, dir[0], dir[1], dir[2]);
+  p1 = P.mink(GQ_ARGS, dir[0], dir[1], dir[2]);
   float dot = pv_dot(p1, dir[0], dir[1], dir[2]);
-  if (f_is_zero(dot) || dot < 0.f) return -1;
+  if (f_is_zero(dot) || dot < 0.f) { v3copy(dir_out, dir); return -1; }      // -1: `dir_out` separates the two objects
   { const float a[3] = {p0.x, p0.y, p0.z}, b[3] = {p1.x, p1.y, p1.z}; v3cross(dir, a, b); }
   if (f_is_zero(v3dot(dir, dir))) {
-    float v1[3]; pv_witness(P, p1, c1, v1);
+    float v1[3]; P.witness(p1, c1, v1);
     for (int k = 0; k < 3; ++k) { const float pk = k == 0 ? p1.x : (k == 1 ? p1.y : p1.z); pos[k] = (v1[k] + (v1[k] - pk)) * 0.5f; }
     if (f_eq(p1.x, 0.f) && f_eq(p1.y, 0.f) && f_eq(p1.z, 0.f)) { *depth = 0.f; dir_out[0] = dir_out[1] = dir_out[2] = 0.f; return 0; }
     float pv[3] = {p1.x, p1.y, p1.z};
     *depth = v3norm(pv); v3copy(dir_out, pv); v3normalize(dir_out); return 0;
   }
   v3normalize(dir);
-  p2 = mink_lane(P, GQ_ARGS, dir[0], dir[1], dir[2]);
+  p2 = P.mink(GQ_ARGS, dir[0], dir[1], dir[2]);
   dot = pv_dot(p2, dir[0], dir[1], dir[2]);
-  if (f_is_zero(dot) || dot < 0.f) return -1;
+  if (f_is_zero(dot) || dot < 0.f) { v3copy(dir_out, dir); return -1; }
   { float va[3] = {p1.x - p0.x, p1.y - p0.y, p1.z - p0.z}, vb[3] = {p2.x - p0.x, p2.y - p0.y, p2.z - p0.z}; v3cross(dir, va, vb); v3normalize(dir); }
   dot = pv_dot(p0, dir[0], dir[1], dir[2]);
   if (dot > 0.f) { const PV t = p1; p1 = p2; p2 = t; dir[0] = -dir[0]; dir[1] = -dir[1]; dir[2] = -dir[2]; }
   int guard = 0;
   while (true) {       // portal discovery
-    if (++guard > 100) return -1;
-    p3 = mink_lane(P, GQ_ARGS, dir[0], dir[1], dir[2]);
+    if (++guard > 100) return -2;
+    p3 = P.mink(GQ_ARGS, dir[0], dir[1], dir[2]);
     dot = pv_dot(p3, dir[0], dir[1], dir[2]);
-    if (f_is_zero(dot) || dot < 0.f) return -1;
+    if (f_is_zero(dot) || dot < 0.f) { v3copy(dir_out, dir); return -1; }
     int cont = 0;
     { const float a[3] = {p1.x, p1.y, p1.z}, b[3] = {p3.x, p3.y, p3.z}; float va[3]; v3cross(va, a, b); dot = pv_dot(p0, va[0], va[1], va[2]); }
     if (dot < 0.f && !f_is_zero(dot)) { p2 = p3; cont = 1; }
@@ -811,19 +850,20 @@ DEV int mpr_lane(const PrismL& P, GQ_PARAMS, const float* gcenter, float* depth,
   }
   guard = 0;
   while (true) {       // portal refinement
-    if (++guard > 1000) return -1;
+    if (++guard > 1000) return -2;
     pv_portal_dir(p1, p2, p3, dir);
     dot = pv_dot(p1, dir[0], dir[1], dir[2]);
     if (f_is_zero(dot) || dot > 0.f) break;
-    const PV v4 = mink_lane(P, GQ_ARGS, dir[0], dir[1], dir[2]);
+    const PV v4 = P.mink(GQ_ARGS, dir[0], dir[1], dir[2]);
     dot = pv_dot(v4, dir[0], dir[1], dir[2]);
-    if (!(f_is_zero(dot) || dot > 0.f) || pv_reach_tol(p1, p2, p3, v4, dir, tol)) return -1;
+    if (!(f_is_zero(dot) || dot > 0.f)) { v3copy(dir_out, dir); return -1; }
+    if (pv_reach_tol(p1, p2, p3, v4, dir, tol)) return -2;                      // no intersection, but `dir` is not a separating axis
     pv_expand(p0, p1, p2, p3, v4);
   }
   int it = 0;
   while (true) {       // penetration depth
     pv_portal_dir(p1, p2, p3, dir);
-    const PV v4 = mink_lane(P, GQ_ARGS, dir[0], dir[1], dir[2]);
+    const PV v4 = P.mink(GQ_ARGS, dir[0], dir[1], dir[2]);
     if (pv_reach_tol(p1, p2, p3, v4, dir, tol) || it > maxit) {
       const float a[3] = {p1.x, p1.y, p1.z}, b[3] = {p2.x, p2.y, p2.z}, c[3] = {p3.x, p3.y, p3.z};
       float wit[3];
@@ -847,10 +887,10 @@ DEV int mpr_lane(const PrismL& P, GQ_PARAMS, const float* gcenter, float* depth,
       }
       const float inv = 1.f / sum;
       float s1[3] = {0.f, 0.f, 0.f}, s2[3] = {0.f, 0.f, 0.f}, v1[3];
-      pv_witness(P, p0, c1, v1); v3addscl(s1, s1, v1, bw[0]); { const float v2[3] = {v1[0] - p0.x, v1[1] - p0.y, v1[2] - p0.z}; v3addscl(s2, s2, v2, bw[0]); }
-      pv_witness(P, p1, c1, v1); v3addscl(s1, s1, v1, bw[1]); { const float v2[3] = {v1[0] - p1.x, v1[1] - p1.y, v1[2] - p1.z}; v3addscl(s2, s2, v2, bw[1]); }
-      pv_witness(P, p2, c1, v1); v3addscl(s1, s1, v1, bw[2]); { const float v2[3] = {v1[0] - p2.x, v1[1] - p2.y, v1[2] - p2.z}; v3addscl(s2, s2, v2, bw[2]); }
-      pv_witness(P, p3, c1, v1); v3addscl(s1, s1, v1, bw[3]); { const float v2[3] = {v1[0] - p3.x, v1[1] - p3.y, v1[2] - p3.z}; v3addscl(s2, s2, v2, bw[3]); }
+      P.witness(p0, c1, v1); v3addscl(s1, s1, v1, bw[0]); { const float v2[3] = {v1[0] - p0.x, v1[1] - p0.y, v1[2] - p0.z}; v3addscl(s2, s2, v2, bw[0]); }
+      P.witness(p1, c1, v1); v3addscl(s1, s1, v1, bw[1]); { const float v2[3] = {v1[0] - p1.x, v1[1] - p1.y, v1[2] - p1.z}; v3addscl(s2, s2, v2, bw[1]); }
+      P.witness(p2, c1, v1); v3addscl(s1, s1, v1, bw[2]); { const float v2[3] = {v1[0] - p2.x, v1[1] - p2.y, v1[2] - p2.z}; v3addscl(s2, s2, v2, bw[2]); }
+      P.witness(p3, c1, v1); v3addscl(s1, s1, v1, bw[3]); { const float v2[3] = {v1[0] - p3.x, v1[1] - p3.y, v1[2] - p3.z}; v3addscl(s2, s2, v2, bw[3]); }
       for (int k = 0; k < 3; ++k) pos[k] = (s1[k] * inv + s2[k] * inv) * 0.5f;
       return 0;
     }
@@ -944,7 +984,7 @@ DEV_NOINLINE void collide_hfield_all(const ModelDev& m, float* ws, int lane) {
         // local coordinates of prism and geom stay below a few metres.  Only the origin shift is rounded, and it is the
         // same for both shapes.
         const float ox = dx * (float)tk[0] - sx, oy = dy * (float)tk[1] - sy;
-        PrismL P; P.base = base;
+        PrismA PA; PrismL& P = PA.P; P.base = base;
         P.x[0] = dx * (float)(ca - tk[0]); P.y[0] = dy * (float)(ra - tk[1]); P.z[0] = LDGB(m.hfield_data + (size_t)ra * ncol + ca) * sz;
         P.x[1] = dx * (float)(cb - tk[0]); P.y[1] = dy * (float)(rbb - tk[1]); P.z[1] = LDGB(m.hfield_data + (size_t)rbb * ncol + cb) * sz;
         P.x[2] = dx * (float)(cc - tk[0]); P.y[2] = dy * (float)(rc - tk[1]); P.z[2] = LDGB(m.hfield_data + (size_t)rc * ncol + cc) * sz;
@@ -957,7 +997,7 @@ DEV_NOINLINE void collide_hfield_all(const ModelDev& m, float* ws, int lane) {
           const float* gpos = WS(W_GXPOS) + 3 * g;
           float gc[3]; m3mulv(gc, WS(W_GXMAT) + 9 * g, cl);
           gc[0] += gpos[0] - ox; gc[1] += gpos[1] - oy; gc[2] += gpos[2];
-          if (mpr_lane(P, m, ws, g, sub2 | (gs2 << 8), gmask2, ox, oy, gc, &depth, nrm, cp) == 0 && !(nrm[0] == 0.f && nrm[1] == 0.f && nrm[2] == 0.f) && depth == depth) {
+          if (mpr_lane(PA, m, ws, g, sub2 | (gs2 << 8), gmask2, ox, oy, gc, &depth, nrm, cp) == 0 && !(nrm[0] == 0.f && nrm[1] == 0.f && nrm[2] == 0.f) && depth == depth) {
             hit = (sub2 == 0); cell = ((r * ncol + (c - 1)) << 1) | i;       // one lane per group reports the contact
             cp[0] += ox; cp[1] += oy;
           }
@@ -994,6 +1034,126 @@ DEV_NOINLINE void collide_hfield_all(const ModelDev& m, float* ws, int lane) {
     }
 #endif
   }
+  if (lane == 0) { WSI(W_CNT)[CNT_NCON] = ncon; WSI(W_CNT)[CNT_DROPPED] = dropped; }
+  SYNC();
+}
+
+// body of the first geom of a contact: 0 (world) for ground contacts; geom-geom contacts carry -2 - geom1 in W_CN_CELL
+DEV int contact_body1(const ModelDev& m, const float* ws, int c) { const int cell = WSI(W_CN_CELL)[c]; return cell <= -2 ? m.geom_body[-2 - cell] : 0; }
+
+// ------------------------------------------------------------------------------------------ geom-geom (self) collision
+// mj_collideGeoms -> mj_filterSphere -> mjc_Convex restated (oracle/oracle.hpp collide_pairs is the serial version), different
+// schedule: (1) a lane per candidate pair runs a separating-axis cull on the two geom-frame bounding boxes (conservative: it
+// only removes pairs MPR would report as separated; MuJoCo's mid-phase culls oriented boxes the same way) ahead of the
+// reference's bounding-sphere filter; (2) the survivors of each 32-pair chunk are handed to lane groups (8 / 4
+// / 2 / 1 lanes per pair, sharing the hull support scans) that run the MPR query in a frame centred on the first geom.
+// Hits are appended after the ground contacts in pair order.
+DEV_NOINLINE void collide_pairs(const ModelDev& m, float* ws, int lane) {
+  const int npair = MD(npair);
+  int ncon = WSI(W_CNT)[CNT_NCON], dropped = WSI(W_CNT)[CNT_DROPPED];
+  SYNC();
+  NOUNROLL for (int p0 = 0; p0 < npair; p0 += LANES) {
+    const int p = p0 + lane;
+    int cand = 0;
+    if (p < npair) {      // separating-axis test on the six face normals of the two geom-frame boxes
+      const int g1 = m.pair_geom[2 * p], g2 = m.pair_geom[2 * p + 1];
+      const float* R1 = WS(W_GXMAT) + 9 * g1; const float* R2 = WS(W_GXMAT) + 9 * g2;
+      const float* x1 = WS(W_GXPOS) + 3 * g1; const float* x2 = WS(W_GXPOS) + 3 * g2;
+      const float* a1 = m.geom_aabb + 6 * g1; const float* a2 = m.geom_aabb + 6 * g2;
+      const float c1[3] = {LDG(a1), LDG(a1 + 1), LDG(a1 + 2)}, c2[3] = {LDG(a2), LDG(a2 + 1), LDG(a2 + 2)};
+      const float h1[3] = {LDG(a1 + 3), LDG(a1 + 4), LDG(a1 + 5)}, h2[3] = {LDG(a2 + 3), LDG(a2 + 4), LDG(a2 + 5)};
+      float w1[3], w2[3], t[3]; m3mulv(w1, R1, c1); m3mulv(w2, R2, c2);
+      for (int k = 0; k < 3; ++k) t[k] = (x2[k] - x1[k]) + (w2[k] - w1[k]);
+      float C[3][3];        // |axis i of frame 1 . axis j of frame 2|
+      for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) C[i][j] = fabsf(R1[i] * R2[j] + R1[3 + i] * R2[3 + j] + R1[6 + i] * R2[6 + j]);
+      cand = 1;
+      for (int i = 0; i < 3; ++i) {
+        const float proj = fabsf(t[0] * R1[i] + t[1] * R1[3 + i] + t[2] * R1[6 + i]);
+        const float rad = h1[i] + C[i][0] * h2[0] + C[i][1] * h2[1] + C[i][2] * h2[2];
+        if (proj > rad * 1.0001f + 1e-5f) cand = 0;
+      }
+      for (int j = 0; j < 3; ++j) {
+        const float proj = fabsf(t[0] * R2[j] + t[1] * R2[3 + j] + t[2] * R2[6 + j]);
+        const float rad = h2[j] + C[0][j] * h1[0] + C[1][j] * h1[1] + C[2][j] * h1[2];
+        if (proj > rad * 1.0001f + 1e-5f) cand = 0;
+      }
+    }
+#ifdef COSIM_HOST_EMU
+    unsigned cmask = cand ? 1u : 0u;
+#else
+    unsigned cmask = __ballot_sync(0xffffffffu, cand);
+#endif
+    if (!cmask) continue;
+    const int nc = popc32(cmask);
+    int gs = 1;
+#ifndef COSIM_HOST_EMU
+    gs = nc <= 4 ? 8 : (nc <= 8 ? 4 : (nc <= 16 ? 2 : 1));
+#endif
+    const int sub = lane & (gs - 1);
+    const unsigned gmask = ((gs >= 32 ? 0u : (1u << gs)) - 1u) << (lane & ~(gs - 1));
+    NOUNROLL for (int k0 = 0; k0 < nc; k0 += LANES / gs) {
+      const int k = k0 + lane / gs;           // k-th surviving pair of this chunk (pair order)
+      int hit = 0, g1 = 0, g2 = 0; float depth = 0.f, nrm[3] = {0.f, 0.f, 0.f}, cp[3] = {0.f, 0.f, 0.f};
+      if (k < nc) {
+        unsigned mm = cmask; for (int i = 0; i < k; ++i) mm &= mm - 1;
+        const int pp = p0 + ctz32(mm);
+        g1 = m.pair_geom[2 * pp]; g2 = m.pair_geom[2 * pp + 1];
+        const float cl1[3] = {LDG(m.geom_center + 3 * g1), LDG(m.geom_center + 3 * g1 + 1), LDG(m.geom_center + 3 * g1 + 2)};
+        const float cl2[3] = {LDG(m.geom_center + 3 * g2), LDG(m.geom_center + 3 * g2 + 1), LDG(m.geom_center + 3 * g2 + 2)};
+        const float* x1 = WS(W_GXPOS) + 3 * g1; const float* x2 = WS(W_GXPOS) + 3 * g2;
+        float r1[3], r2[3]; m3mulv(r1, WS(W_GXMAT) + 9 * g1, cl1); m3mulv(r2, WS(W_GXMAT) + 9 * g2, cl2);
+        const float ox = x1[0], oy = x1[1];
+        GeomA A; A.g1 = g1; A.c[0] = r1[0]; A.c[1] = r1[1]; A.c[2] = x1[2] + r1[2];
+        const float gc[3] = {(x2[0] - ox) + r2[0], (x2[1] - oy) + r2[1], x2[2] + r2[2]};
+        const float dv[3] = {gc[0] - A.c[0], gc[1] - A.c[1], gc[2] - A.c[2]};
+        const float bound = LDG(m.geom_rbound + g1) + LDG(m.geom_rbound + g2);
+        if (v3dot(dv, dv) <= bound * bound) {      // mj_filterSphere, margin 0
+          // temporal coherence: the direction along which MPR last found this pair separated (kept in geom 1's frame, so
+          // it follows the robot).  If the two supports still leave a gap the pair cannot intersect and the query is
+          // skipped; a stale or useless axis only fails this test, so the cull is conservative like the ones above.
+          int res = 1;
+          {
+            const float* ax = WS(W_PAXIS) + 4 * (pp % PAXIS_SLOTS);
+            if (__float_as_int_emu(ax[0]) == pp + 1) {
+              const float* R1 = WS(W_GXMAT) + 9 * g1;
+              const float d[3] = {R1[0] * ax[1] + R1[1] * ax[2] + R1[2] * ax[3], R1[3] * ax[1] + R1[4] * ax[2] + R1[5] * ax[3], R1[6] * ax[1] + R1[7] * ax[2] + R1[8] * ax[3]};
+              const F3 s1 = support_lane(m, ws, g1, sub | (gs << 8), gmask, ox, oy, d[0], d[1], d[2]);
+              const F3 s2 = support_lane(m, ws, g2, sub | (gs << 8), gmask, ox, oy, -d[0], -d[1], -d[2]);
+              if ((s2.x - s1.x) * d[0] + (s2.y - s1.y) * d[1] + (s2.z - s1.z) * d[2] > 1e-5f) res = -2;
+            }
+          }
+#if defined(COSIM_PHASE_TIMING) && !defined(COSIM_HOST_EMU)
+          if (res == 1 && sub == 0) atomicAdd(m.phase + PH_SUPPORT_CALLS, 1ull);       // counter slot reused: geom-geom MPR queries
+#endif
+          if (res == 1) res = mpr_lane(A, m, ws, g2, sub | (gs << 8), gmask, ox, oy, gc, &depth, nrm, cp);
+          if (res == 0 && !(nrm[0] == 0.f && nrm[1] == 0.f && nrm[2] == 0.f) && depth == depth) {
+            hit = (sub == 0); cp[0] += ox; cp[1] += oy;
+          } else if (res == -1 && sub == 0) {          // remember the separating direction (in geom 1's frame)
+            const float* R1 = WS(W_GXMAT) + 9 * g1; float* ax = WS(W_PAXIS) + 4 * (pp % PAXIS_SLOTS);
+            ax[0] = __int_as_float_emu(pp + 1);
+            ax[1] = R1[0] * nrm[0] + R1[3] * nrm[1] + R1[6] * nrm[2]; ax[2] = R1[1] * nrm[0] + R1[4] * nrm[1] + R1[7] * nrm[2]; ax[3] = R1[2] * nrm[0] + R1[5] * nrm[1] + R1[8] * nrm[2];
+          }
+        }
+      }
+#ifdef COSIM_HOST_EMU
+      const int nhit = hit, slot = ncon;
+#else
+      const unsigned hits = __ballot_sync(0xffffffffu, hit);
+      const int nhit = __popc(hits), slot = ncon + __popc(hits & ((1u << lane) - 1u));
+#endif
+      if (hit && slot < MD(ncon_max)) {
+        float* cpp = WS(W_CN_POS) + 3 * slot; float* fr = WS(W_CN_FRAME) + 9 * slot;
+        v3copy(cpp, cp); v3copy(fr, nrm); make_frame(fr);
+        WS(W_CN_DIST)[slot] = -depth;
+        WS(W_CN_MU)[slot] = fmaxf(WS(W_GMU)[g1], WS(W_GMU)[g2]);
+        WSI(W_CN_BODY)[slot] = m.geom_body[g2]; WSI(W_CN_GEOM)[slot] = g2; WSI(W_CN_CELL)[slot] = -2 - g1;
+      }
+      const int room = imax(0, MD(ncon_max) - ncon);
+      dropped += imax(0, nhit - room); ncon += imin(nhit, room);
+      SYNC();       // cached axes written above are read by the next chunk's candidate test
+    }
+  }
+  SYNC();
   if (lane == 0) { WSI(W_CNT)[CNT_NCON] = ncon; WSI(W_CNT)[CNT_DROPPED] = dropped; }
   SYNC();
 }
@@ -1159,6 +1319,7 @@ DEV_NOINLINE void make_constraint(const ModelDev& m, float* ws, int ncon, int la
     const float* fr = WS(W_CN_FRAME) + 9 * c; float off[3], jp[3];
     v3sub(off, WS(W_CN_POS) + 3 * c, scom);
     jac_col(m, ws, WSI(W_CN_BODY)[c], k, off, jp);
+    { const int b1 = contact_body1(m, ws, c); if (b1 > 0) { float j1[3]; jac_col(m, ws, b1, k, off, j1); v3sub(jp, jp, j1); } }
     float* J = WS(W_CN_J) + (size_t)3 * c * nv;
     J[k] = v3dot(fr, jp); J[nv + k] = v3dot(fr + 3, jp); J[2 * nv + k] = v3dot(fr + 6, jp);
   }
@@ -1173,6 +1334,7 @@ DEV_NOINLINE void make_constraint(const ModelDev& m, float* ws, int ncon, int la
     WS(W_CN_AREF)[idx] = -B * vel - K * imp * dist;
     if (e == 0) {
       float tran = WS(W_INVWB)[WSI(W_CN_BODY)[c]];
+      { const int b1 = contact_body1(m, ws, c); if (b1 > 0) tran += WS(W_INVWB)[b1]; }
       float R = fmaxf(MINVALF, (1.f - imp) * (tran + mu * mu * tran) / imp);
       WS(W_CN_D)[c] = 1.f / (2.f * mu * mu * R);
     }
@@ -1544,6 +1706,7 @@ DEV_NOINLINE int forward(const ModelDev& m, float* ws, int lane, int active = 1,
       if (lane == 0) { WSI(W_CNT)[CNT_NCON] = ncon; WSI(W_CNT)[CNT_DROPPED] = dropped; }
     }
     SYNC();
+    if (MD(npair) > 0) collide_pairs(m, ws, lane);
   }
   PH_MARK(PH_COLLIDE);
   BSYNC_IF(bsync, 1);
@@ -1656,6 +1819,8 @@ DEV_NOINLINE void cfrc_ext(const ModelDev& m, float* ws, int ncon, int lane) {
       v3sub(arm, WS(W_CN_POS) + 3 * c, scom); v3cross(tq, arm, wf);
       float* o = out + 6 * WSI(W_CN_BODY)[c];
       for (int k = 0; k < 3; ++k) { o[k] += tq[k]; o[3 + k] += wf[k]; }
+      const int b1 = contact_body1(m, ws, c);
+      if (b1 > 0) { float* o1 = out + 6 * b1; for (int k = 0; k < 3; ++k) { o1[k] -= tq[k]; o1[3 + k] -= wf[k]; } }
     }
     NOUNROLL for (int e = 0; e < neq; ++e) {
       const int b1 = m.eq_body1[e], b2 = m.eq_body2[e];

@@ -33,11 +33,13 @@ DEV_NOINLINE void load_state(const ModelDev& m, const EnvArrays& E, int env, flo
   const int nq = MD(nq), nv = MD(nv);
   FOR_LANE(i, nq) WS(W_QPOS)[i] = E.qpos[(size_t)env * nq + i];
   FOR_LANE(i, nv) { WS(W_QVEL)[i] = E.qvel[(size_t)env * nv + i]; WS(W_WARM)[i] = E.warm[(size_t)env * nv + i]; }
+  if (MD(npair) > 0) FOR_LANE(i, 4 * PAXIS_SLOTS) WS(W_PAXIS)[i] = E.paxis[(size_t)env * 4 * PAXIS_SLOTS + i];
 }
 DEV_NOINLINE void store_state(const ModelDev& m, const EnvArrays& E, int env, const float* ws, int lane) {
   const int nq = MD(nq), nv = MD(nv);
   FOR_LANE(i, nq) E.qpos[(size_t)env * nq + i] = WS(W_QPOS)[i];
   FOR_LANE(i, nv) { E.qvel[(size_t)env * nv + i] = WS(W_QVEL)[i]; E.warm[(size_t)env * nv + i] = WS(W_WARM)[i]; }
+  if (MD(npair) > 0) FOR_LANE(i, 4 * PAXIS_SLOTS) E.paxis[(size_t)env * 4 * PAXIS_SLOTS + i] = WS(W_PAXIS)[i];
 }
 
 // ------------------------------------------------------------------------------------------ init: randomise + setConst

@@ -99,6 +99,8 @@ static inline void build_model(const void* blob, size_t nbytes, uint64_t seed, u
   arena.add(m, m.body_subsize, subsize); arena.add(m, m.body_dofmask, dofmask);
   arena.add(m, m.level_start, level_start); arena.add(m, m.level_body, level_body);
   arena.add(m, m.mpair_i, mi); arena.add(m, m.mpair_j, mj);
+  { std::vector<int> pg = section<int>(blob, "pair_geom"); arena.add(m, m.pair_geom, pg);
+    if (m.dims[CD_npair] > 32 * m.dims[CD_ngeom]) throw std::runtime_error("too many geom-geom candidate pairs for the task records (npair > 32 ngeom)"); }
   FSEC(body_pos, "body_pos"); FSEC(body_quat, "body_quat"); FSEC(body_ipos, "body_ipos"); FSEC(body_inertia, "body_inertia"); FSEC(body_mass, "body_mass");
   ISEC(jnt_type, "jnt_type"); ISEC(jnt_body, "jnt_body"); ISEC(jnt_qposadr, "jnt_qposadr"); ISEC(jnt_dofadr, "jnt_dofadr");
   ISEC(jnt_limited, "jnt_limited"); ISEC(jnt_actfrclimited, "jnt_actfrclimited");
@@ -127,6 +129,22 @@ static inline void build_model(const void* blob, size_t nbytes, uint64_t seed, u
       }
     }
     arena.add(m, m.geom_supadr, supadr); m.sup_off = push(u, sup_off); m.sup_cand = (const float4*)push(u, cand);
+  }
+  { // geom-frame bounding boxes [centre(3), half extents(3)]: conservative cull ahead of the geom-geom narrow phase
+    std::vector<int> gtype = section<int>(blob, "geom_type"), vadr = section<int>(blob, "geom_vadr"), vnum = section<int>(blob, "geom_vnum");
+    std::vector<float> hv = section<float>(blob, "hull_verts"), gsize = section<float>(blob, "geom_size");
+    std::vector<float> aabb(6 * gtype.size(), 0.f);
+    for (size_t g = 0; g < gtype.size(); ++g) {
+      float lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
+      if (gtype[g] == 7) {
+        for (int c = 0; c < 3; ++c) { lo[c] = 1e30f; hi[c] = -1e30f; }
+        for (int i = 0; i < vnum[g]; ++i) for (int c = 0; c < 3; ++c) { const float v = hv[3 * (size_t)(vadr[g] + i) + c]; lo[c] = std::min(lo[c], v); hi[c] = std::max(hi[c], v); }
+      } else if (gtype[g] == 2) { for (int c = 0; c < 3; ++c) { lo[c] = -gsize[3 * g]; hi[c] = gsize[3 * g]; } }
+      else if (gtype[g] == 5) { lo[0] = lo[1] = -gsize[3 * g]; hi[0] = hi[1] = gsize[3 * g]; lo[2] = -gsize[3 * g + 1]; hi[2] = gsize[3 * g + 1]; }
+      else { for (int c = 0; c < 3; ++c) { lo[c] = -gsize[3 * g + c]; hi[c] = gsize[3 * g + c]; } }
+      for (int c = 0; c < 3; ++c) { aabb[6 * g + c] = 0.5f * (lo[c] + hi[c]); aabb[6 * g + 3 + c] = 0.5f * (hi[c] - lo[c]) * 1.0001f + 1e-6f; }
+    }
+    arena.add(m, m.geom_aabb, aabb);
   }
   { // Cholesky pair table
     std::vector<int> tri;
@@ -170,7 +188,7 @@ static inline void build_model(const void* blob, size_t nbytes, uint64_t seed, u
   size[W_CN_POS] = 3 * nc; size[W_CN_FRAME] = 9 * nc; size[W_CN_DIST] = nc; size[W_CN_MU] = nc; size[W_CN_BODY] = nc; size[W_CN_GEOM] = nc;
   size[W_CN_CELL] = nc; size[W_CN_D] = nc; size[W_CN_AREF] = 4 * nc; size[W_CN_J] = 3 * nc * nv; size[W_CN_F] = 3 * nc; size[W_CN_X] = 4 * nc; size[W_CN_V] = 4 * nc;
   size[W_EQ_J] = 3 * neq * nv; size[W_EQ_D] = size[W_EQ_AREF] = size[W_EQ_X] = size[W_EQ_V] = size[W_EQ_F] = 3 * neq;
-  size[W_SENS] = 12; size[W_RAW] = nraw; size[W_ACT] = nu; size[W_FILT] = 0; size[W_KP] = nu; size[W_KD] = nu; size[W_GTASK] = 8 * ng; size[W_CNT] = 4;
+  size[W_SENS] = 12; size[W_RAW] = nraw; size[W_ACT] = nu; size[W_FILT] = 0; size[W_KP] = nu; size[W_KD] = nu; size[W_GTASK] = 8 * ng; size[W_CNT] = 4; size[W_PAXIS] = m.dims[CD_npair] > 0 ? 4 * PAXIS_SLOTS : 0;
   // Lay the fields out back to back, then overlay fields whose lifetimes never overlap (shared memory per env bounds
   // how many env-warps an SM holds, and the step is latency-bound, so every KB counts):
   //   W_CRB    (only inside crb(), phase 1)            over  W_CVEL + W_CACC   (written from com_vel on, phase 3)
@@ -226,7 +244,7 @@ static inline void alloc_env(const ModelDev& m, int N, EnvArrays& E, ZAlloc za, 
   E.N = N;
   const size_t n = (size_t)N;
 #define FA(field, dim) E.field = (float*)za(ctx, n * (size_t)(dim) * sizeof(float))
-  FA(qpos, d.nq); FA(qvel, d.nv); FA(warm, d.nv);
+  FA(qpos, d.nq); FA(qvel, d.nv); FA(warm, d.nv); FA(paxis, 4 * PAXIS_SLOTS);
   FA(body_mass, d.nb); FA(invw_dof, d.nv); FA(invw_body, d.nb); FA(floss, d.nv); FA(gmu, d.ng); FA(scal, 4); FA(kp, d.nu); FA(kd, d.nu);
   FA(prev_action, d.nu); FA(delay_prev, d.nu); FA(obs_buffer, d.obsbuf); FA(freq_cache, d.cache); FA(torque, d.nu); FA(info, 4); FA(last_action, d.nu);
   FA(stats, ST__COUNT);

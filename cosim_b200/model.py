@@ -30,7 +30,7 @@ DIMS = ["nq", "nv", "nu", "nbody", "njnt", "ngeom", "nhullvert", "neq", "ground_
         "state_dim", "stack_size", "stacked_dim", "nonstacked_dim", "command_dim", "n_term_body", "n_dofpos",
         "n_dofvel", "n_initnoise", "max_episode_steps", "lin_vel_f32", "n_sobs", "n_nobs", "cache_dim",
         "n_state_pos", "n_state_vel", "position_command", "nefc_max", "imu_body", "n_massnoise", "base_body",
-        "zero_noise", "auto_reset", "nfl", "nlimit_max"]
+        "zero_noise", "auto_reset", "nfl", "nlimit_max", "npair"]
 OPTS = ["timestep", "gx", "gy", "gz", "tolerance", "ls_tolerance", "ccd_tolerance", "hf_sx", "hf_sy", "hf_sz",
         "hf_base", "z0", "hm_size_x", "hm_size_y", "hm_zmin", "term_threshold", "init_noise",
         "solref0", "solref1", "solimp0", "solimp1", "solimp2", "solimp3", "solimp4",
@@ -43,6 +43,51 @@ OPT = {k: i for i, k in enumerate(OPTS)}
 OBS_KINDS = {"dof_pos": 0, "dof_vel": 1, "ang_vel": 2, "lin_vel": 3, "projected_gravity": 4,
              "last_action": 5, "height_map": 6, "command": 7}
 NOISE_ORDER = ["dof_pos", "dof_vel", "ang_vel", "lin_vel", "projected_gravity", "height_map"]
+
+
+def self_collision_pairs(rb):
+    """Geom pairs the broad phase of MuJoCo 3.2.7 hands to the narrow phase [upstream mj_collision / filterBodyPair /
+    mj_collideGeoms; SURVEY.md section 8f row 3]: geoms of different bodies, excluding (a) bodies welded together, (b)
+    parent-child weld pairs unless one of them is the world (filterparent), (c) <contact><exclude> body pairs, and (d)
+    pairs whose contype / conaffinity masks do not meet.  Body pairs are visited in (body1, body2) order, and the two geoms
+    of a pair are ordered by type as the narrow-phase function table requires.  Body ids are 1-based (0 = world).
+    Deviation: geoms that stand in for an STL missing from the reference checkout (inertia-box proxies, geom_proxy = 1) take
+    no part in self-collision: the proxy only approximates the link for ground contact, and neighbouring proxies overlap at
+    rest (flamingo_p_v3's two hip boxes by 27 mm), which the real meshes do not."""
+    gt, gb = rb["geom_type"], rb["geom_body"]
+    if "geom_contype" not in rb:
+        return np.zeros((0, 2), np.int32)
+    par = np.concatenate([[0], rb["body_parent"]]).astype(int)
+    dofnum = np.concatenate([[0], rb["body_dofnum"]]).astype(int)
+    nb = len(par)
+    weld = np.zeros(nb, int)
+    for b in range(1, nb):
+        weld[b] = b if dofnum[b] > 0 else weld[par[b]]
+    excl = {tuple(sorted(x)) for x in np.asarray(rb["exclude_body"]).reshape(-1, 2).tolist()}
+    ct, ca = rb["geom_contype"], rb["geom_conaffinity"]
+    out = []
+    for i in range(len(gt)):
+        for j in range(i + 1, len(gt)):
+            b1, b2 = int(gb[i]), int(gb[j])
+            if b1 == b2:
+                continue
+            w1, w2 = weld[b1], weld[b2]
+            if w1 == w2:
+                continue
+            if w1 != 0 and w2 != 0 and (w1 == weld[par[w2]] or w2 == weld[par[w1]]):
+                continue
+            if tuple(sorted((b1, b2))) in excl:
+                continue
+            if not ((int(ct[i]) & int(ca[j])) or (int(ct[j]) & int(ca[i]))):
+                continue
+            if int(rb["geom_proxy"][i]) or int(rb["geom_proxy"][j]):
+                continue
+            g1, g2 = (i, j) if b1 < b2 else (j, i)
+            if gt[g1] > gt[g2]:
+                g1, g2 = g2, g1
+            out.append((min(b1, b2), max(b1, b2), g1, g2))
+    out.sort(key=lambda t: (t[0], t[1]))
+    return np.array([(t[2], t[3]) for t in out], np.int32).reshape(-1, 2)
 
 
 def load_robot(robot_id):
@@ -398,6 +443,8 @@ def build_model(config, ncon_max=None, auto_reset=False):
         pw = xpos0[b1] + _quat_mat(xquat0[b1]) @ rb["eq_anchor"][e]
         eq_anchor2[e] = _quat_mat(xquat0[b2]).T @ (pw - xpos0[b2])
 
+    pair_geom = self_collision_pairs(rb) if eng.get("self_collision", True) else np.zeros((0, 2), np.int32)
+
     if ncon_max is None:
         ncon_max = int(eng.get("ncon_max", 24))
     nefc_max = 3 * neq + nfl_upper + nlimit_max + 4 * ncon_max
@@ -425,7 +472,7 @@ def build_model(config, ncon_max=None, auto_reset=False):
          position_command=int(bool(config["env"]["position_command"])), nefc_max=nefc_max,
          imu_body=int(rb["imu_body"]), n_massnoise=len(massnoise_body), base_body=bname[spec.base_body],
          zero_noise=zero_noise, auto_reset=int(bool(eng.get("auto_reset", auto_reset))), nfl=nfl_upper,
-         nlimit_max=nlimit_max)
+         nlimit_max=nlimit_max, npair=len(pair_geom))
     g = rb["gravity"]
     sl, tl, rl = _rng_pair(rnd["sliding_friction"]), _rng_pair(rnd["torsional_friction"]), _rng_pair(rnd["rolling_friction"])
     fl, dl, ld = _rng_pair(rnd["friction_loss"]), _rng_pair(rnd["action_delay_prob"]), _rng_pair(rnd["load"])
@@ -488,6 +535,7 @@ def build_model(config, ncon_max=None, auto_reset=False):
             nidx += len(idx)
         sup_adr[g] = cache[key]
     S["geom_supadr"] = sup_adr
+    S["pair_geom"] = (pair_geom if len(pair_geom) else np.zeros((1, 2), np.int32)).astype(np.int32).reshape(-1)
     S["sup_off"] = np.concatenate(sup_off).astype(np.int32)
     S["sup_idx"] = (np.concatenate(sup_idx) if sup_idx else np.zeros(1)).astype(np.int32)
     gf = np.concatenate([rb["ground_friction"].astype(np.float64), [float(rb["ground_has_friction_attr"])]])

@@ -41,6 +41,7 @@ def lib():
         L.orc_rne_post.argtypes = [ctypes.c_void_p]
         L.orc_ray_hfield.restype = ctypes.c_double
         L.orc_ray_hfield.argtypes = [ctypes.c_void_p, ctypes.c_double, ctypes.c_double]
+        L.orc_convex_pair.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
         L.orc_norm_ppf.restype = ctypes.c_double
         L.orc_norm_ppf.argtypes = [ctypes.c_double]
         _lib = L
@@ -134,6 +135,19 @@ class Oracle:
     def ray_hfield(self, x, y):
         """Terrain height under (x, y) as mj_rayHfield sees it for a vertical ray; NaN on a miss."""
         return float(lib().orc_ray_hfield(self.h, float(x), float(y)))
+
+    def convex_pair(self, g1, g2):
+        """MPR penetration query between two primitive geoms, each (type, size[3], pos[3], mat[3, 3]); -> (hit, depth, normal, pos).
+        The normal points from g1 to g2 (mjc_Convex convention)."""
+        buf = np.zeros(32)
+        for i, (t, size, pos, mat) in enumerate((g1, g2)):
+            buf[16 * i] = t
+            buf[16 * i + 1:16 * i + 4] = size
+            buf[16 * i + 4:16 * i + 7] = pos
+            buf[16 * i + 7:16 * i + 16] = np.asarray(mat, dtype=np.float64).reshape(9)
+        out = np.zeros(7)
+        r = lib().orc_convex_pair(self.h, _p(buf), _p(out))
+        return r == 0, float(out[0]), out[1:4].copy(), out[4:7].copy()
 
     def contacts(self, env=0, cap=256):
         out = np.zeros((cap, 10), dtype=np.float64)

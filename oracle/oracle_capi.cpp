@@ -20,6 +20,7 @@ struct IOracle {
   virtual int contacts(int env, double* out, int cap) = 0;
   virtual void rne_post_all() = 0;
   virtual double ray_hfield(double x, double y) = 0;
+  virtual int convex_pair(const double* geoms, double* out) = 0;
 };
 
 template <class T> struct OracleT : IOracle {
@@ -52,6 +53,22 @@ template <class T> struct OracleT : IOracle {
   void substep_all() override { for (auto& d : E.envs) E.substep(d); }
   void rne_post_all() override { for (auto& d : E.envs) E.cfrc_ext(d); }
   double ray_hfield(double x, double y) override { int cell; return (double)E.hfield_height((T)x, (T)y, &cell); }
+  // known-answer hook for the geom-geom narrow phase: geoms = 2 x [type, size(3), pos(3), mat(9)] of primitives;
+  // out = [depth, normal(3), pos(3)]; returns 0 on penetration, -1 otherwise
+  int convex_pair(const double* geoms, double* out) override {
+    typename orc::Engine<T>::Geom G[2]; T pos[2][3], mat[2][9];
+    for (int i = 0; i < 2; ++i) {
+      const double* g = geoms + 16 * i;
+      G[i].type = (int)g[0]; for (int k = 0; k < 3; ++k) { G[i].size[k] = (T)g[1 + k]; pos[i][k] = (T)g[4 + k]; G[i].center[k] = (T)g[4 + k]; }
+      for (int k = 0; k < 9; ++k) mat[i][k] = (T)g[7 + k];
+      G[i].pos = pos[i]; G[i].mat = mat[i]; G[i].verts = nullptr; G[i].nvert = 0;
+    }
+    typename orc::Engine<T>::ShapeA A{nullptr, &G[0]};
+    T depth = 0, dir[3] = {0, 0, 0}, cp[3] = {0, 0, 0};
+    int r = E.mpr_core(A, G[0].center, G[1], &depth, dir, cp);
+    out[0] = depth; for (int k = 0; k < 3; ++k) { out[1 + k] = dir[k]; out[4 + k] = cp[k]; }
+    return r;
+  }
   template <class V> static void put(double* out, const V& v, size_t stride, int e) { for (size_t i = 0; i < stride; ++i) out[(size_t)e * stride + i] = (double)v[i]; }
   int get(const char* name_, double* out) override {
     std::string n(name_);
@@ -134,6 +151,7 @@ void orc_rne_post(void* h);
 double orc_norm_ppf(double p) { return orc::norm_ppf(p); }
 void orc_rne_post(void* h) { ((IOracle*)h)->rne_post_all(); }
 double orc_ray_hfield(void* h, double x, double y) { return ((IOracle*)h)->ray_hfield(x, y); }
+int orc_convex_pair(void* h, const double* geoms, double* out) { return ((IOracle*)h)->convex_pair(geoms, out); }
 int orc_max_threads() {
 #ifdef _OPENMP
   return omp_get_max_threads();

@@ -52,14 +52,15 @@ def test_reset_state_bit_exact(robot, terrain):
 def test_contact_free_window_1e5():
     """flamingo_p_v3 dropped from z0 + 0.5 m: 13 control steps = 52 sub-steps without contact."""
     N = 32
-    env = _env("flamingo_p_v3", "rocky_hard", N)
+    nosc = {"engine": {"self_collision": False}}      # smooth dynamics only: the legs may touch each other under random actions
+    env = _env("flamingo_p_v3", "rocky_hard", N, **nosc)
     orc = _oracle(env, N)
     orc.reset(); env.reset()
     q = orc.get("qpos"); q[:, 2] += 0.5
     orc.set("qpos", q); env.set("qpos", q)
     rng = np.random.default_rng(7)
     # (a) teacher-forced per-step relative error, (b) free-running drift
-    free = _env("flamingo_p_v3", "rocky_hard", N); free.reset(); free.set("qpos", q)
+    free = _env("flamingo_p_v3", "rocky_hard", N, **nosc); free.reset(); free.set("qpos", q)
     worst = 0.0
     for i in range(13):
         a = rng.uniform(-1, 1, (N, env.action_dim))
@@ -130,6 +131,47 @@ def test_contact_parity_teacher_forced(robot, terrain):
     frac = CONTACT_OUTLIER_FRAC_CASE.get((robot, terrain), CONTACT_OUTLIER_FRAC)
     assert (sub_err > 1e-2).mean() <= frac, f"{(sub_err > 1e-2).mean():.1%} of sub-steps off by > 1e-2"
     assert np.median(step_err) < 50 * CONTACT_MEDIAN_TOL, f"median per-control-step qvel error {np.median(step_err):.2e}"
+    env.close()
+
+
+def test_self_collision_parity():
+    """Geom-geom contacts: humanoid limbs pressed into each other / into the torso by random joint
+    offsets.  Same pairs in the same order as the oracle; depths / normals statistically within fp32 of the fp64 oracle (MPR on
+    flat-faced primitives has tied supports, see tests/test_hostsim_vs_oracle.py); velocities against the oracle's fp32 build."""
+    N = 64
+    env = _env("humanoid_p_v0", "slope_hard", N)
+    o, f = _oracle(env, N), _oracle(env, N, use_float=True)
+    o.reset(); f.reset(); env.reset()
+    rng = np.random.default_rng(5)
+    q = o.get("qpos")
+    q[:, 7:] += rng.uniform(-0.45, 0.45, q[:, 7:].shape)
+    q[:, 2] += 0.05
+    for x in (o, f, env):
+        x.set("qpos", q)
+    nself, derr, nerr, verr, same, total = 0, [], [], [], 0, 0
+    for i in range(6):
+        o.substep(); f.substep(); env.substep()
+        nco, ncg = o.get("ncon")[:, 0].astype(int), env.get("counters")[:, 7].cpu().numpy()
+        same += int((nco == ncg).sum()); total += N
+        cg_all = env.get("contacts").cpu().numpy()
+        for e in np.nonzero(nco == ncg)[0]:
+            co = o.contacts(int(e)); cg = cg_all[e].reshape(-1, 10)[:len(co)]
+            if not len(co) or not (co[:, 8].astype(int) == cg[:, 8].astype(int)).all():
+                continue
+            assert (co[:, 7].astype(int) == cg[:, 7].astype(int)).all()
+            s = co[:, 8] <= -2
+            nself += int(s.sum())
+            if s.any():
+                derr.append(np.abs(cg[s, 0] - co[s, 0])); nerr.append(np.abs(cg[s, 4:7] - co[s, 4:7]).max(axis=1))
+        verr.append(np.abs(env.get("qvel").cpu().numpy() - f.get("qvel")).max(axis=1))
+        for k in ("qpos", "qvel", "qacc_warmstart"):
+            env.set(k, o.get(k)); f.set(k, o.get(k))
+    derr, nerr, verr = np.concatenate(derr), np.concatenate(nerr), np.concatenate(verr)
+    assert same / total >= 0.95, f"contact counts agree in only {same}/{total} cases"
+    assert nself >= 200, f"only {nself} self contacts exercised"
+    assert np.median(derr) < 5e-6 and (derr > 1e-4).mean() <= 0.20, f"depth: median {np.median(derr):.1e}, {(derr > 1e-4).mean():.1%} above 1e-4"
+    assert np.median(nerr) < 1e-4 and (nerr > 1e-2).mean() <= 0.20, f"normal: median {np.median(nerr):.1e}, {(nerr > 1e-2).mean():.1%} above 1e-2"
+    assert np.median(verr) < 2e-3 and (verr > 1e-2).mean() <= 0.25, f"qvel vs fp32 oracle: median {np.median(verr):.1e}, {(verr > 1e-2).mean():.1%} above 1e-2"
     env.close()
 
 

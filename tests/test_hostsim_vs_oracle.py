@@ -107,3 +107,40 @@ def test_far_from_origin_contacts():
                 depth_err.append(np.abs(co[:, 0] - ch[:, 0])); ncontacts += len(co)
     depth_err = np.concatenate(depth_err)
     assert ncontacts > 50 and np.median(depth_err) < 5e-6 and (depth_err > 5e-5).mean() < 0.05
+
+
+def test_self_collision_contacts_match_oracle():
+    """Geom-geom contacts (humanoid legs pressed into each other / arms into the torso): same pairs in the same order;
+    depths, normals and the accelerations from the two-body rows within fp32 of the oracle.
+
+    MPR on flat-faced primitives (cylinder caps, boxes) pressed centimetres into each other has tied supports: in fp32 the
+    portal may settle on a neighbouring face.  The oracle's own fp32 build shows the same outliers against its fp64 build,
+    so contact geometry is compared with fp64 statistically (as for terrain contacts in test_gpu_parity.py) and the
+    resulting velocities are compared with the fp32 build."""
+    m = build_model(make_config("humanoid_p_v0", "slope_hard", random=RANDOM_NONE))
+    N = 4
+    o, f, h = Oracle(m, N, seed=1), Oracle(m, N, seed=1, use_float=True), HostSim(m, N, seed=1)
+    o.reset(); f.reset(); h.reset()
+    q = o.get("qpos")
+    q[0, 19] -= 0.4; q[1, 25] += 0.4; q[2, 9] -= 0.4; q[3, 14] += 0.4
+    q[:, 2] += 0.05
+    for x in (o, f, h):
+        x.set("qpos", q)
+    nself, derr, nerr, verr = 0, [], [], []
+    for i in range(6):
+        o.substep(); f.substep(); h.substep()
+        nco, nch = o.get("ncon")[:, 0].astype(int), h.get("counters")[:, 7]
+        assert (nco == nch).all()
+        for e in range(N):
+            co = o.contacts(e); ch = h.get("contacts")[e].reshape(-1, 10)[:len(co)]
+            assert (co[:, 7].astype(int) == ch[:, 7].astype(int)).all() and (co[:, 8].astype(int) == ch[:, 8].astype(int)).all()
+            s = co[:, 8] <= -2
+            nself += int(s.sum())
+            derr.append(np.abs(ch[s, 0] - co[s, 0])); nerr.append(np.abs(ch[s, 4:7] - co[s, 4:7]).max(axis=1) if s.any() else np.zeros(0))
+        verr.append(np.abs(h.get("qvel") - f.get("qvel")).max(axis=1))
+        for k in ("qpos", "qvel", "qacc_warmstart"):
+            h.set(k, o.get(k)); f.set(k, o.get(k))
+    derr, nerr, verr = np.concatenate(derr), np.concatenate(nerr), np.concatenate(verr)
+    assert nself >= 12 and np.median(derr) < 5e-6 and (derr > 1e-4).mean() <= 0.20 and derr.max() < 3e-3
+    assert np.median(nerr) < 1e-4 and (nerr > 1e-2).mean() <= 0.20
+    assert np.median(verr) < 1e-3 and (verr > 1e-2).mean() <= 0.20

@@ -186,3 +186,73 @@ def test_every_robot_terrain_and_precision_builds():
     for prec, (dt, it, fs) in {"low": (0.01, 50, 2), "medium": (0.005, 50, 4), "high": (0.0025, 75, 8), "ultra": (0.00125, 75, 16), "extreme": (0.000625, 100, 32)}.items():
         m = build_model(make_config("flamingo_p_v3", "rocky_easy", random=dict(RANDOM_NONE, precision=prec)))
         assert (m.opt("timestep"), m.dim("iterations"), m.dim("frame_skip")) == (dt, it, fs)
+
+
+def test_self_collision_pair_table():
+    """Broad-phase candidates [upstream filterBodyPair + contype/conaffinity + <exclude>; SURVEY.md 8f row 3]."""
+    from cosim_b200.model import self_collision_pairs, load_robot
+    counts = {}
+    for robot in ("flamingo_light_v1", "flamingo_p_v3", "w4_p_v2", "humanoid_p_v0"):
+        rb = load_robot(robot)
+        pairs = self_collision_pairs(rb)
+        counts[robot] = len(pairs)
+        par = np.concatenate([[0], rb["body_parent"]])
+        excl = {tuple(sorted(x)) for x in rb["exclude_body"].tolist()}
+        seen = set()
+        for g1, g2 in pairs.tolist():
+            b1, b2 = int(rb["geom_body"][g1]), int(rb["geom_body"][g2])
+            assert b1 != b2 and par[b1] != b2 and par[b2] != b1            # one joint per body here: weld parent = parent
+            assert tuple(sorted((b1, b2))) not in excl
+            assert rb["geom_type"][g1] <= rb["geom_type"][g2]
+            assert not rb["geom_proxy"][g1] and not rb["geom_proxy"][g2]
+            assert (g1, g2) not in seen and (g2, g1) not in seen
+            seen.add((g1, g2))
+        bp = [tuple(sorted((int(rb["geom_body"][a]), int(rb["geom_body"][b])))) for a, b in pairs.tolist()]
+        assert bp == sorted(bp)                                            # (body1, body2) order of mj_collision
+    # flamingo_light: every robot geom is contype 1 / conaffinity 2 -> no robot-robot pair at all (flamingo_light_v1.xml:17)
+    assert counts == {"flamingo_light_v1": 0, "flamingo_p_v3": 4, "w4_p_v2": 39, "humanoid_p_v0": 212}
+    m = build_model(make_config("humanoid_p_v0", "flat", engine={"self_collision": False}))
+    assert m.dim("npair") == 0
+
+
+def test_convex_pair_known_answers():
+    """mjc_Convex restatement on primitives with closed-form penetration: normal from geom1 to geom2, pos = midpoint."""
+    o = Oracle(build_model(make_config("flamingo_p_v3", "flat")), 1)
+    I = np.eye(3)
+    hit, depth, n, p = o.convex_pair((2, [0.1, 0, 0], [0, 0, 0], I), (2, [0.2, 0, 0], [0.25, 0, 0], I))
+    assert hit and abs(depth - 0.05) < 1e-9
+    np.testing.assert_allclose(n, [1, 0, 0], atol=1e-9); np.testing.assert_allclose(p, [0.075, 0, 0], atol=1e-9)
+    hit, depth, n, p = o.convex_pair((6, [0.1, 0.1, 0.1], [0, 0, 0], I), (6, [0.1, 0.1, 0.1], [0.01, 0.02, 0.18], I))
+    assert hit and abs(depth - 0.02) < 1e-9 and abs(p[2] - 0.09) < 1e-9
+    np.testing.assert_allclose(n, [0, 0, 1], atol=1e-9)
+    # parallel cylinders side by side, rotated frame: depth = 2 r - gap along the line of centres
+    c, s = np.cos(0.7), np.sin(0.7)
+    R = np.array([[c, -s, 0], [s, c, 0], [0, 0, 1.0]])
+    d = np.array([0.06, 0.05, 0.0]); d = d / np.linalg.norm(d) * 0.08
+    hit, depth, n, p = o.convex_pair((5, [0.05, 0.2, 0], [1, 2, 3], R), (5, [0.05, 0.2, 0], np.array([1, 2, 3.01]) + d, R))
+    assert hit and abs(depth - 0.02) < 1e-5
+    np.testing.assert_allclose(n, d / 0.08, atol=5e-3)
+    hit, *_ = o.convex_pair((5, [0.05, 0.2, 0], [0, 0, 0], I), (5, [0.05, 0.2, 0], [0, 0.11, 0.01], I))
+    assert not hit
+
+
+def test_self_contact_is_action_reaction():
+    """A geom-geom contact pushes its two bodies with equal and opposite force: with the legs pressed into each other in
+    mid-air the humanoid's self-contact rows must leave the momentum balance of free fall untouched."""
+    m = build_model(make_config("humanoid_p_v0", "flat", random=RANDOM_NONE))
+    o = Oracle(m, 1, seed=1)
+    o.reset()
+    q = o.get("qpos"); q[:, 2] += 5.0          # lift off the ground: only self-contacts remain
+    q[:, 19] -= 0.4                            # swing one leg into the other
+    o.set("qpos", q); o.set("qvel", np.zeros_like(o.get("qvel")))
+    o.forward()
+    con = o.contacts(0)
+    assert len(con) >= 1 and (con[:, 8] <= -2).all()
+    o.rne_post()
+    cf = o.get("cfrc_ext").reshape(-1, 6)
+    assert np.abs(cf).max() > 1e-3
+    np.testing.assert_allclose(cf.sum(axis=0), 0, atol=1e-9)
+    # internal forces cannot move the centre of mass: no net generalized force on the floating base's translation
+    qc = o.get("qfrc_constraint")[0]
+    assert np.abs(qc).max() > 1e-3
+    np.testing.assert_allclose(qc[:3], 0, atol=1e-9)

@@ -293,7 +293,7 @@ def compile_robot(ref, robot, xml_name):
             geoms.append(dict(name=ga.get("name", ""), type=gtype, body=bid, size=size, pos=gpos, quat=gquat,
                               friction=fvec(ga["friction"], 3), has_friction_attr=int("friction" in g.attrib),
                               condim=int(ga["condim"]), vadr=vadr, vnum=vnum, center=center, rbound=rbound,
-                              proxy=proxy))
+                              proxy=proxy, contype=ct, conaffinity=ca))
         for child in elem.findall("body"):
             add_body(child, bid)
 
@@ -323,6 +323,12 @@ def compile_robot(ref, robot, xml_name):
             solref = fvec(c.attrib.get("solref", "0.02 1"))
             eqs.append(dict(body1=bname[c.attrib["body1"]], body2=bname[c.attrib["body2"]],
                             anchor=fvec(c.attrib["anchor"]), solref=solref, solimp=solimp))
+
+    # <contact><exclude body1 body2/>: body pairs whose geoms never collide
+    excl = []
+    for ct_root in root.findall("contact"):
+        for x in ct_root.findall("exclude"):
+            excl.append((bname[x.attrib["body1"]], bname[x.attrib["body2"]]))
 
     imu_name = "imu" if "imu" in sites else "imu_site"
     imu = sites[imu_name]
@@ -372,6 +378,9 @@ def compile_robot(ref, robot, xml_name):
         geom_center=np.stack([g["center"] for g in geoms]),
         geom_rbound=np.array([g["rbound"] for g in geoms]),
         geom_proxy=np.array([g["proxy"] for g in geoms], dtype=np.int32),
+        geom_contype=np.array([g["contype"] for g in geoms], dtype=np.int32),
+        geom_conaffinity=np.array([g["conaffinity"] for g in geoms], dtype=np.int32),
+        exclude_body=np.array(excl, dtype=np.int32).reshape(-1, 2),
         hull_verts=(np.concatenate(hull_verts) if hull_verts else np.zeros((0, 3), np.float32)),
         ground_friction=fvec(gnd["friction"], 3), ground_condim=np.array(int(gnd["condim"])),
         ground_has_friction_attr=np.array(int("friction" in ground.attrib)),

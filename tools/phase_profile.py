@@ -15,7 +15,7 @@ import torch
 from cosim_b200.config import make_config, RANDOM_FULL
 from cosim_b200.envs import BatchedEnv
 
-NAMES = ["kin+crb+chol", "collide", "constraint", "smooth", "newton", "integrate", "obs", "io", "newton_iters", "ls_evals", "support_calls", "mpr_calls",
+NAMES = ["kin+crb+chol", "collide", "constraint", "smooth", "newton", "integrate", "obs", "io", "newton_iters", "ls_evals", "pair_mpr_calls", "mpr_calls",
          "wait after kin", "wait after collide", "wait after smooth", "wait after newton"]
 
 def run(robot, terrain, N, steps):
