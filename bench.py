@@ -220,8 +220,12 @@ def main():
     h_term, h_trunc = pin((N,), torch.uint8), pin((N,), torch.uint8)
     h_cmd.copy_(cmd.cpu())
     assert h_state.is_pinned() and h_cmd.is_pinned()
-    e2e_steps = max(3, min(args.steps, 10))
-    env.step_policy_host(pol, h_cmd, h_state, h_term, h_trunc)
+    # Same simulated interval as the device-timed leg: reset, the same warm-up steps, then the same K steps (the cost of
+    # a step depends on what the robots are doing, so a leg timed later in the episodes would measure a different workload)
+    e2e_steps = args.steps
+    env.reset()
+    for _ in range(max(args.warmup, 3)):
+        env.step_policy_host(pol, h_cmd, h_state, h_term, h_trunc)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
