@@ -136,7 +136,10 @@ def run_reference(args):
            "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "kind": "port", "sample": sample},
            "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
-    print(json.dumps(out), flush=True)
+    _RESULT_OUT.write(json.dumps(out) + "\n"); _RESULT_OUT.flush()
+
+
+_RESULT_OUT = sys.stdout
 
 
 def main():
@@ -151,6 +154,12 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=20)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    # stdout carries exactly one JSON line: libraries that print to fd 1 (NCCL's version banner under torchrun) are sent to
+    # stderr, and the result is written to a private duplicate of the original stdout
+    global _RESULT_OUT
+    sys.stdout.flush()
+    _RESULT_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         return run_reference(args)
 
@@ -267,7 +276,7 @@ def main():
                                "sample": f"{args.cpu_envs} envs x {args.cpu_steps} control steps of the same workload after 2 warm-up steps, {dt:.1f} s wall on {cores} threads "
                                          "(fp64 C++ restatement of the reference path, OpenMP over envs; not MuJoCo itself)"}
     if rank == 0:
-        print(json.dumps(out), flush=True)
+        _RESULT_OUT.write(json.dumps(out) + "\n"); _RESULT_OUT.flush()
     env.close(); pol.close()
     if world > 1:
         dist.destroy_process_group()

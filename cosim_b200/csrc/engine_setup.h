@@ -206,6 +206,11 @@ static inline void build_model(const void* blob, size_t nbytes, uint64_t seed, u
   { const int n = std::max(pad4(size[W_RAW]), pad4(size[W_CN_J])); place(W_RAW, o); place(W_CN_J, o); o += n; }
   { const int n = std::max(pad4(size[W_GTASK]), pad4(size[W_CN_X]) + pad4(size[W_CN_V]));
     place(W_GTASK, o); place(W_CN_X, o); place(W_CN_V, o + pad4(size[W_CN_X])); o += n; }
+  { // composite inertias live from com_pos to rne_bias (phases 1-3); contact forces, gradient, search direction and
+    // M * search exist only from the Newton solve on (phase 4 .. cfrc_ext) and are rewritten before every use
+    const int n = std::max(pad4(size[W_CINERT]), pad4(size[W_CN_F]) + pad4(size[W_GRAD]) + pad4(size[W_SEARCH]) + pad4(size[W_MV]));
+    place(W_CINERT, o); place(W_CN_F, o); place(W_GRAD, o + pad4(size[W_CN_F])); place(W_SEARCH, o + pad4(size[W_CN_F]) + pad4(size[W_GRAD]));
+    place(W_MV, o + pad4(size[W_CN_F]) + pad4(size[W_GRAD]) + pad4(size[W_SEARCH])); o += n; }
   for (int i = 0; i < W__COUNT; ++i) if (!placed[i]) { m.off[i] = o; o += pad4(size[i]); }
   m.ws_floats = o;
   // upload the arena and point the fields at it; CTA-shared area in front of the per-warp workspaces: [ModelDev copy | arena copy]

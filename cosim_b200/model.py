@@ -102,6 +102,15 @@ def load_terrain_raster(name):
     return z["raster"]
 
 
+def load_png_raster(path):
+    """8-bit grey raster of a PNG, as MuJoCo reads hfield images [upstream mjCHField::LoadPNG: lodepng decode to LCT_GREY, 8 bit]."""
+    from PIL import Image
+    im = Image.open(path)
+    if im.mode in ("I;16", "I;16B", "I"):
+        return (np.asarray(im).astype(np.uint32) >> 8).astype(np.uint8)
+    return np.asarray(im.convert("L"), dtype=np.uint8)
+
+
 def hfield_from_raster(raster_u8):
     """PNG raster -> MuJoCo hfield_data (float32, row 0 = -y edge, normalised to [0,1]).
 
@@ -322,6 +331,18 @@ def build_model(config, ncon_max=None, auto_reset=False):
     if terrain == "flat":
         ground_type, hf = 0, np.zeros((1, 1), np.float32)
         hf_size = np.zeros(4)
+    elif isinstance(terrain, dict):
+        # terrain authoring: the user's own height image instead of a baked reference terrain --
+        # what adding an <hfield file=... size=.../> asset to the MJCF does in the reference
+        ground_type = 1
+        raster = load_png_raster(terrain["png"]) if "png" in terrain else np.asarray(terrain["raster"])
+        if raster.ndim != 2 or raster.dtype != np.uint8 or min(raster.shape) < 2:
+            raise ValueError("terrain raster must be a 2-D uint8 image of at least 2 x 2 pixels")
+        hf = hfield_from_raster(raster)
+        hf_size = np.asarray(terrain["size"], dtype=np.float64).reshape(4)      # MJCF hfield size: x, y half extents, z top, base
+        if not (hf_size > 0).all():
+            raise ValueError("terrain size = [radius_x, radius_y, elevation_z, base_z] must be positive")
+        terrain = str(terrain.get("name", "custom"))
     else:
         names = [str(n) for n in rb["hfield_names"]]
         if terrain not in names:

@@ -58,6 +58,8 @@ void* hs_create(const void* blob, uint64_t nbytes, int num_envs, uint64_t seed, 
   return h;
 }
 void hs_destroy(void* hp) { delete (HostSim*)hp; }
+// workspace layout (float offsets of every field, then ws_floats, shared_floats, arena_bytes): tools/ws_layout.py
+int hs_layout(void* hp, int* out, int cap) { HostSim* h = (HostSim*)hp; int n = 0; for (int i = 0; i < W__COUNT && n < cap; ++i) out[n++] = h->m.off[i]; if (n + 3 <= cap) { out[n++] = h->m.ws_floats; out[n++] = h->m.shared_floats; out[n++] = h->m.arena_bytes; } return n; }
 int hs_ws_floats(void* hp) { return ((HostSim*)hp)->m.ws_floats; }
 void hs_reset(void* hp, const uint8_t* mask, const float* command, float* state) {
   HostSim* h = (HostSim*)hp; const int cd = h->m.dims[CD_command_dim], sd = h->m.dims[CD_state_dim];

@@ -256,3 +256,34 @@ def test_self_contact_is_action_reaction():
     qc = o.get("qfrc_constraint")[0]
     assert np.abs(qc).max() > 1e-3
     np.testing.assert_allclose(qc[:3], 0, atol=1e-9)
+
+
+def test_terrain_authoring_from_png(tmp_path):
+    """A user's own height image: rows flipped, normalised to [0, 1], scaled by the MJCF size; the
+    robot comes to rest on the authored surface."""
+    from PIL import Image
+    yy, xx = np.mgrid[0:64, 0:96]
+    img = (40 + 60 * (xx / 95.0) + 20 * np.sin(yy / 6.0)).astype(np.uint8)         # ramp along x with ripples along y
+    path = str(tmp_path / "ramp.png")
+    Image.fromarray(img, mode="L").save(path)
+    size = [12.0, 8.0, 0.6, 0.1]
+    cfg = make_config("flamingo_p_v3", {"png": path, "size": size, "name": "ramp"}, random=RANDOM_NONE)
+    m = build_model(cfg)
+    assert (m.dim("hf_nrow"), m.dim("hf_ncol")) == (64, 96) and m.dim("ground_type") == 1
+    hf = m.sections["hfield_data"].reshape(64, 96)
+    ref = img[::-1].astype(np.float32); ref = (ref - ref.min()) / (ref.max() - ref.min())
+    np.testing.assert_array_equal(hf, ref)
+    o = Oracle(m, 1, seed=1)
+    o.reset()
+    # mj_rayHfield: height at the centre of the map = bilinear surface of the authored raster
+    z_mid = o.ray_hfield(0.0, 0.0)
+    assert abs(z_mid - size[2] * float(ref[31:33, 47:49].mean())) < 0.02
+    for _ in range(150):
+        o.step(np.zeros((1, m.dim("nu"))))
+    q = o.get("qpos")[0]
+    ground = o.ray_hfield(q[0], q[1])
+    assert 0.05 < q[2] - ground < 0.6 and o.get("ncon")[0, 0] >= 1            # resting on the authored terrain
+    same = build_model(make_config("flamingo_p_v3", {"raster": img, "size": size}, random=RANDOM_NONE))
+    np.testing.assert_array_equal(same.sections["hfield_data"], m.sections["hfield_data"])
+    with pytest.raises(ValueError):
+        build_model(make_config("flamingo_p_v3", {"raster": img.astype(np.float32), "size": size}))
