@@ -137,7 +137,7 @@ int cosim_create(const void* blob, size_t nbytes, int num_envs, int device, uint
   }
   // launch geometry: as many env-warps per block as fit comfortably; blocks co-reside up to the 227 KB/SM limit
   const size_t per = (size_t)h->m.ws_floats * sizeof(float);
-  // one CTA per SM with as many env-warps as its shared memory holds (<= 20): the warps of a CTA move through the
+  // one CTA per SM with as many env-warps as its shared memory holds (<= 20: five warps of 96 registers fill the 16 K registers of each SM sub-partition): the warps of a CTA move through the
   // phases of a sub-step together (block barriers in k_step), which keeps the instruction working set per SM small
   int wpb = 20; size_t budget = 224 * 1024;         // tuning overrides (experiments): COSIM_MAX_WPB, COSIM_SMEM_KB
   { const char* e = getenv("COSIM_MAX_WPB"); if (e && atoi(e) >= 1 && atoi(e) <= 20) wpb = atoi(e); }

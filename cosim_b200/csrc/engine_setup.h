@@ -211,6 +211,17 @@ static inline void build_model(const void* blob, size_t nbytes, uint64_t seed, u
     const int n = std::max(pad4(size[W_CINERT]), pad4(size[W_CN_F]) + pad4(size[W_GRAD]) + pad4(size[W_SEARCH]) + pad4(size[W_MV]));
     place(W_CINERT, o); place(W_CN_F, o); place(W_GRAD, o + pad4(size[W_CN_F])); place(W_SEARCH, o + pad4(size[W_CN_F]) + pad4(size[W_GRAD]));
     place(W_MV, o + pad4(size[W_CN_F]) + pad4(size[W_GRAD]) + pad4(size[W_SEARCH])); o += n; }
+  { // motion axes (cdof) serve the Jacobians and rne_bias (phases 1-3); M * qacc, the friction-row residuals and the
+    // constraint force are Newton-phase vectors (phase 4 .. integrate)
+    const int n = std::max(pad4(size[W_CDOF]), pad4(size[W_MA]) + pad4(size[W_TMPW]) + pad4(size[W_FCON]));
+    place(W_CDOF, o); place(W_MA, o); place(W_TMPW, o + pad4(size[W_MA])); place(W_FCON, o + pad4(size[W_MA]) + pad4(size[W_TMPW])); o += n; }
+  { // world joint anchors / axes are consumed by com_pos (phase 1); friction-loss and limit rows are built in phase 3
+    const int a = pad4(size[W_XANCHOR]) + pad4(size[W_XAXIS]);
+    const int b = pad4(size[W_FR_D]) + pad4(size[W_FR_AREF]) + pad4(size[W_LM_SIGN]) + pad4(size[W_LM_D]) + pad4(size[W_LM_AREF]);
+    place(W_XANCHOR, o); place(W_XAXIS, o + pad4(size[W_XANCHOR]));
+    int q = o; place(W_FR_D, q); q += pad4(size[W_FR_D]); place(W_FR_AREF, q); q += pad4(size[W_FR_AREF]);
+    place(W_LM_SIGN, q); q += pad4(size[W_LM_SIGN]); place(W_LM_D, q); q += pad4(size[W_LM_D]); place(W_LM_AREF, q);
+    o += std::max(a, b); }
   for (int i = 0; i < W__COUNT; ++i) if (!placed[i]) { m.off[i] = o; o += pad4(size[i]); }
   m.ws_floats = o;
   // upload the arena and point the fields at it; CTA-shared area in front of the per-warp workspaces: [ModelDev copy | arena copy]
