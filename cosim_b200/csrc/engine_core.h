@@ -146,6 +146,7 @@ struct ModelDev {
   // hull support maps (cosim_b200/model.py:build_support_map): per mesh geom a table of 6*8*8 direction buckets;
   // sup_cand[k] = (x, y, z, vertex index) of the k-th candidate, so one 16-byte load per candidate
   const int *geom_supadr, *sup_off; const float4* sup_cand;
+  const uint16_t* sup_off16; const int* geom_supbase;   // bucket offsets relative to the mesh's first candidate, in the shared-memory arena when they fit (else NULL)
   // lower-triangle (i, k) pairs of an nv x nv matrix sorted by k descending, packed (i << 8) | k: the trailing
   // sub-matrix update of Cholesky column j is the prefix of length (nv-j-1)(nv-j)/2
   const int* tri; int shared_floats;
@@ -690,7 +691,9 @@ DEV_NOINLINE F3 support_lane(const ModelDev& m, const float* ws, int g, int grp,
     const int* sup_off = m.sup_off + m.geom_supadr[g];
     const float ld[3] = {l0, l1, l2};
     const int bucket = support_bucket(ld);
-    const int o0 = LDGB(sup_off + bucket), o1 = LDGB(sup_off + bucket + 1);
+    int o0, o1;
+    if (m.sup_off16) { const uint16_t* t16 = m.sup_off16 + m.geom_supadr[g]; const int b0 = m.geom_supbase[g]; o0 = b0 + t16[bucket]; o1 = b0 + t16[bucket + 1]; }
+    else { o0 = LDGB(sup_off + bucket); o1 = LDGB(sup_off + bucket + 1); }
     float bv = -INFINITY; int bk = 0x7fffffff;
     const int gs = grp >> 8, sub = grp & 255;
     NOUNROLL for (int k = o0 + sub; k < o1; k += 4 * gs) {    // four independent 16-byte loads in flight per lane

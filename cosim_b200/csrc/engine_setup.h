@@ -53,6 +53,7 @@ struct Arena {
 
 static inline void build_model(const void* blob, size_t nbytes, uint64_t seed, uint32_t env_offset, const Uploader& u, ModelDev& m) {
   Arena arena;
+  std::vector<uint16_t> sup_off16;
   if (nbytes < 8 || memcmp(blob, "CSB1", 4) != 0) throw std::runtime_error("model blob: bad magic");
   memset(&m, 0, sizeof(m));
   std::vector<int> dims = section<int>(blob, "dims");
@@ -129,6 +130,19 @@ static inline void build_model(const void* blob, size_t nbytes, uint64_t seed, u
       }
     }
     arena.add(m, m.geom_supadr, supadr); m.sup_off = push(u, sup_off); m.sup_cand = (const float4*)push(u, cand);
+    // 16-bit copy of the bucket offsets, relative to each mesh's first candidate: goes into the shared-memory arena below
+    // if that does not cost an env-warp (saves one dependent L2 round trip per hull support query)
+    std::vector<int> supbase(supadr.size(), 0);
+    sup_off16.assign(sup_off.size(), 0);
+    bool ok16 = true;
+    for (size_t g = 0; g < supadr.size(); ++g) {
+      if (supadr[g] < 0) continue;
+      const int b0 = sup_off[supadr[g]];
+      supbase[g] = b0;
+      for (int k = 0; k <= 6 * 8 * 8; ++k) { const int rel = sup_off[supadr[g] + k] - b0; if (rel < 0 || rel > 65535) ok16 = false; else sup_off16[supadr[g] + k] = (uint16_t)rel; }
+    }
+    if (!ok16) sup_off16.clear();
+    arena.add(m, m.geom_supbase, supbase);
   }
   { // geom-frame bounding boxes [centre(3), half extents(3)]: conservative cull ahead of the geom-geom narrow phase
     std::vector<int> gtype = section<int>(blob, "geom_type"), vadr = section<int>(blob, "geom_vadr"), vnum = section<int>(blob, "geom_vnum");
@@ -224,6 +238,12 @@ static inline void build_model(const void* blob, size_t nbytes, uint64_t seed, u
     o += std::max(a, b); }
   for (int i = 0; i < W__COUNT; ++i) if (!placed[i]) { m.off[i] = o; o += pad4(size[i]); }
   m.ws_floats = o;
+  if (!sup_off16.empty()) {       // shared-memory budget as in cosim_create: 224 KB per CTA, at most 20 env-warps
+    const size_t per = (size_t)m.ws_floats * 4, budget = 224 * 1024, head = (sizeof(ModelDev) + 15) / 16 * 16;
+    const size_t a0 = (arena.bytes.size() + 15) & ~(size_t)15, a1 = ((a0 + sup_off16.size() * 2 + 15) & ~(size_t)15);
+    const size_t w0 = std::min<size_t>(20, (budget - head - a0) / per), w1 = std::min<size_t>(20, (budget - head - a1) / per);
+    if (w1 == w0 && w1 >= 1) arena.add(m, m.sup_off16, sup_off16);
+  }
   // upload the arena and point the fields at it; CTA-shared area in front of the per-warp workspaces: [ModelDev copy | arena copy]
   if (arena.slots.size() > sizeof(m.slot_field) / sizeof(m.slot_field[0])) throw std::runtime_error("too many model tables for ModelDev::slot_field");
   arena.bytes.resize((arena.bytes.size() + 15) & ~(size_t)15, 0);
