@@ -166,6 +166,21 @@ def test_self_collision_parity():
         verr.append(np.abs(env.get("qvel").cpu().numpy() - f.get("qvel")).max(axis=1))
         for k in ("qpos", "qvel", "qacc_warmstart"):
             env.set(k, o.get(k)); f.set(k, o.get(k))
+    # whole control steps (k_step: the geom-geom queries go through the CTA-wide task queue): same contact lists
+    same_step, nself_step = 0, 0
+    for i in range(3):
+        for k in ("qpos", "qvel", "qacc_warmstart", "torque"):
+            env.set(k, o.get(k))
+        a = rng.uniform(-1, 1, (N, env.action_dim))
+        o.step(a); env.step(a)
+        nco, ncg = o.get("ncon")[:, 0].astype(int), env.get("counters")[:, 7].cpu().numpy()
+        cg_all = env.get("contacts").cpu().numpy()
+        for e in range(N):
+            co = o.contacts(int(e)); cg = cg_all[e].reshape(-1, 10)[:len(co)]
+            ok = nco[e] == ncg[e] and (co[:, 7].astype(int) == cg[:, 7].astype(int)).all() and (co[:, 8].astype(int) == cg[:, 8].astype(int)).all()
+            same_step += int(ok); nself_step += int((co[:, 8] <= -2).sum())
+    assert same_step >= 0.80 * 3 * N, f"contact lists after whole steps agree in only {same_step}/{3 * N} cases"      # 4 free-running sub-steps
+    assert nself_step >= 50
     derr, nerr, verr = np.concatenate(derr), np.concatenate(nerr), np.concatenate(verr)
     assert same / total >= 0.95, f"contact counts agree in only {same}/{total} cases"
     assert nself >= 200, f"only {nself} self contacts exercised"

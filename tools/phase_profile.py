@@ -26,7 +26,7 @@ def run(robot, terrain, N, steps):
     a = torch.rand((N, env.action_dim), device="cuda") * 2 - 1
     for _ in range(3):
         env.step(a)
-    buf = (ctypes.c_ulonglong * 16)()
+    buf = (ctypes.c_ulonglong * 144)()
     lib.cosim_phase_cycles(env._h, buf, 1)
     torch.cuda.synchronize(); t = time.time()
     for _ in range(steps):
@@ -43,6 +43,12 @@ def run(robot, terrain, N, steps):
         print(f"  {NAMES[i]:18s} {100.0 * v[i] / max(tot, 1):5.1f} %   {v[i] / nsub:10.0f} cycles/sub-step")
     for i in range(8, 12):
         print(f"  {NAMES[i]:14s} {v[i] / nsub:8.2f} per sub-step")
+    for name, base in (("collide", 16), ("newton", 80)):
+        h = v[base:base + 64]; tot_h = max(sum(h), 1); acc = 0; line = []
+        for i, c in enumerate(h):
+            acc += c
+            if c: line.append(f"{8 * i}K:{100.0 * c / tot_h:.1f}%")
+        print(f"  {name} time histogram (8 K-cycle bins): " + " ".join(line))
     print("  stats:", {k: round(x, 3) for k, x in env.stats().items() if k in ("mean_contacts", "mean_solver_iters_per_step", "termination_rate", "episodes")})
     env.close()
 
