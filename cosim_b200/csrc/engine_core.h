@@ -84,10 +84,13 @@ DEV void wargmax(float& v, int& i) {
 
 // optional per-phase cycle counters (profiling builds only: -DCOSIM_PHASE_TIMING)
 enum { PH_KIN = 0, PH_COLLIDE, PH_CONSTRAINT, PH_SMOOTH, PH_NEWTON, PH_INTEGRATE, PH_OBS, PH_IO, PH_NEWTON_ITERS, PH_LS_EVALS, PH_SUPPORT_CALLS, PH_MPR_CALLS,
-       PH_WAIT_KIN, PH_WAIT_COLLIDE, PH_WAIT_SMOOTH, PH_WAIT_NEWTON, PH__COUNT = 16 };     // PH_WAIT_*: cycles spent at the barrier that ends the phase
+       PH_WAIT_KIN, PH_WAIT_COLLIDE, PH_WAIT_SMOOTH, PH_WAIT_NEWTON, PH_HIST = 16, PH_HIST_BINS = 64, PH__COUNT = PH_HIST + 2 * PH_HIST_BINS };     // PH_WAIT_*: cycles spent at the barrier that ends the phase
 #if defined(COSIM_PHASE_TIMING) && !defined(COSIM_HOST_EMU)
 #define PH_DECL long long ph_t0_ = clock64()
-#define PH_MARK(k) do { long long t_ = clock64(); if (lane == 0) atomicAdd((unsigned long long*)m.phase + (k), (unsigned long long)(t_ - ph_t0_)); ph_t0_ = clock64(); } while (0)
+#define PH_MARK(k) do { long long t_ = clock64(); if (lane == 0) { atomicAdd((unsigned long long*)m.phase + (k), (unsigned long long)(t_ - ph_t0_)); \
+    /* histograms (8 K-cycle bins) of the per-warp collision and Newton phase times */ \
+    if ((k) == PH_COLLIDE || (k) == PH_NEWTON) { long long b_ = (t_ - ph_t0_) >> 13; if (b_ >= PH_HIST_BINS) b_ = PH_HIST_BINS - 1; \
+      atomicAdd((unsigned long long*)m.phase + PH_HIST + ((k) == PH_NEWTON ? PH_HIST_BINS : 0) + b_, 1ull); } } ph_t0_ = clock64(); } while (0)
 #define PH_COUNT(k, n) do { if (lane == 0) atomicAdd((unsigned long long*)m.phase + (k), (unsigned long long)(n)); } while (0)
 #else
 #define PH_DECL ((void)0)
