@@ -100,7 +100,8 @@ int cosim_policy_launch_count(const cosim_policy* p);
 #define COSIM_POLICY_ACTIVATED_OUTPUT 0x200   /* the output gets the hidden activation instead of the clip (encoders in front of an LSTM) */
 /* ONNX LSTM cell update, gate order i, o, f, c: gates [N][4H] -> c [N][H], h [N][H] updated in place (device pointers). */
 int cosim_lstm_cell(const float* gates, float* c, float* h, int num_envs, int hidden, void* stream);
-/* profiling builds only (-DCOSIM_PHASE_TIMING): per-phase cycle counters; zeros in the product build */
+/* profiling builds only (-DCOSIM_PHASE_TIMING): out_host[144] = 16 per-phase cycle / event counters + two 64-bin histograms
+   (8 K-cycle bins) of the per-warp collision and Newton phase times; zeros in the product build (tools/phase_profile.py) */
 int cosim_phase_cycles(cosim_handle* h, unsigned long long* out_host, int reset);
 
 #ifdef __cplusplus
