@@ -309,6 +309,47 @@ def test_termination_truncation_autoreset_and_stats():
     env.close()
 
 
+def test_reporter_statistics_within_1pct_over_1k_episodes():
+    """north_star: "the reporter's success and tracking-error statistics must agree within 1% over 1k episodes".  1024
+    domain-randomised envs run one 1.2 s episode each (60 control steps, rocky_hard, per-env velocity commands, the same
+    open-loop action sequence) on the CUDA engine and on the fp64 oracle; the engine's on-device reporter accumulators are
+    compared with the same statistics computed from the oracle's per-step info."""
+    from cosim_b200.envs import BatchedEnv
+    N, T = 1024, 60
+    cfg = make_config("flamingo_p_v3", "rocky_hard", random=RANDOM_FULL, max_duration=T / 50.0)
+    env = BatchedEnv(cfg, N, seed=11)
+    orc = _oracle(env, N, seed=11)
+    rng = np.random.default_rng(11)
+    uc = rng.uniform(-1.0, 1.0, (N, env.command_dim)).astype(np.float32)
+    env.receive_user_command(uc)
+    applied = env.applied_command.cpu().numpy().astype(np.float64)
+    env.reset(); orc.reset(command=applied)
+    phase = rng.uniform(0, 2 * np.pi, (N, env.action_dim))
+    alive = np.ones(N, bool)
+    acc = dict(steps=0.0, vx=0.0, wz=0.0, rmse=0.0, success=0.0, terminated=0.0, episodes=0.0)
+    for t in range(T + 2):
+        a = 0.4 * np.sin(0.25 * t + phase)
+        _, term_o, trunc_o = orc.step(a, command=applied)
+        env.step(a)
+        info = orc.get("info")                       # action-diff RMSE, lin_vel_x, lin_vel_y, ang_vel_yaw (reference info dict)
+        acc["steps"] += alive.sum()
+        acc["vx"] += np.abs(info[alive, 1] - uc[alive, 0]).sum(); acc["wz"] += np.abs(info[alive, 3] - uc[alive, 2]).sum()
+        acc["rmse"] += info[alive, 0].sum()
+        done = alive & (term_o | trunc_o)
+        acc["episodes"] += done.sum(); acc["terminated"] += (done & term_o).sum(); acc["success"] += (done & trunc_o & ~term_o).sum()
+        alive &= ~done
+        if not alive.any():
+            break
+    st = env.stats()
+    assert acc["episodes"] == N and st["episodes"] == N, (acc["episodes"], st["episodes"])
+    assert abs(st["success_rate"] - acc["success"] / N) <= 0.01, (st["success_rate"], acc["success"] / N)
+    assert abs(st["steps"] - acc["steps"]) <= 0.01 * acc["steps"]
+    for key, ref in (("mean_abs_err_lin_vel_x", acc["vx"] / acc["steps"]), ("mean_abs_err_ang_vel_yaw", acc["wz"] / acc["steps"]),
+                     ("mean_action_diff_rmse", acc["rmse"] / acc["steps"])):
+        assert abs(st[key] - ref) <= 0.01 * abs(ref), f"{key}: engine {st[key]:.5f} vs oracle {ref:.5f}"
+    env.close()
+
+
 def test_single_env_reference_signature():
     from cosim_b200.envs import build_env
     cfg = make_config("flamingo_light_v1", "flat")
