@@ -351,7 +351,11 @@ class SingleEnv:
 
     def step(self, action):
         assert self.reset_flag is True, "Call 'reset()' before calling 'step()'."
-        state, term, trunc, info = self.env.step(np.asarray(action, dtype=np.float32)[None, :])
+        if torch.is_tensor(action):                 # the engine's policies return device tensors; the reference's return numpy
+            action = action.detach().reshape(1, -1)
+        else:
+            action = np.asarray(action, dtype=np.float32)[None, :]
+        state, term, trunc, info = self.env.step(action)
         out = {}
         for k in info:
             v = info[k]
