@@ -1,11 +1,15 @@
-"""The reference's evaluation driver on the batched engine: `core/tester.py:11-121` without the Qt plumbing.
+"""Evaluation driver with the reference's interface (`core/tester.py:11-121`) on top of the batched engine.
 
-Same methods and call order as the reference `Tester` (`load_config`, `load_policy`, `init_user_command`,
-`receive_user_command`, `update_command`, `activate_push_event`, `deactivate_push_event`, `test`, `stop`, `close`); the Qt
-signals `stepFinished` / `finished` become optional callbacks.  `num_envs=None` runs the reference's single-environment loop
-unchanged (numpy state, python bools, report from every step's `info`).  With `num_envs=N` the same loop advances N
-domain-randomised environments at once: it runs until every environment has finished an episode, traces environment
-`trace_env` into the report and adds the population statistics (all-reduced over ranks when torch.distributed is up).
+The public methods carry the reference's names so that its UI code can drive either implementation: `load_config`,
+`load_policy`, `init_user_command`, `receive_user_command`, `update_command`, `activate_push_event`,
+`deactivate_push_event`, `test`, `stop`, `close`.  Qt is not involved: the `stepFinished` / `finished` signals are plain
+callbacks (`on_step`, `on_finished`).
+
+Two modes:
+* `Tester()` -- one environment, numpy state, python bools, every step's `info` goes to the report (what the reference does);
+* `Tester(num_envs=N)` -- N domain-randomised environments advance together until each has completed an episode; environment
+  `trace_env` supplies the time series of the report and `BatchedEnv.stats()` (all-reduced over ranks when
+  torch.distributed is initialised) its population page.
 """
 import os
 
@@ -15,88 +19,92 @@ from .envs import build_env
 from .policy import build_policy
 from .reporter import Reporter
 
+_POLICY_ERROR = ("Failed to run inference with the selected ONNX policy: {path}.\n\nThe state has {n} entries; the policy may expect a "
+                 "different input length.\n")
+
 
 class Tester:
     def __init__(self, num_envs=None, device="cuda:0", seed=None, trace_env=0, on_step=None, on_finished=None):
-        self.user_command = None
-        self._push_event = False
-        self._stop = False
-        self._had_error = False
         self.num_envs, self.device, self.seed, self.trace_env = num_envs, device, seed, trace_env
         self.on_step, self.on_finished = on_step, on_finished
+        self.config, self.policy_path = None, None
         self.env = self.policy = self.reporter = None
-        self.policy_path = None
+        self.user_command = None          # [command_dim], or [num_envs, command_dim] for per-environment commands
+        self._push_vel = None             # world-frame velocity kick applied before every step while set
+        self._stop = self._had_error = False
 
+    # ---- configuration ------------------------------------------------------------------------------------------------
     def load_config(self, config):
         self.config = config
 
     def load_policy(self, policy_path):
         self.policy_path = policy_path
 
+    def _command_dim(self):
+        return int(self.config["observation"]["command_dim"])
+
     def init_user_command(self):
-        """Initialize the user command array before starting the test."""
-        self.user_command = np.zeros(self.config["observation"]["command_dim"])
+        self.user_command = np.zeros(self._command_dim())
+
+    def update_command(self, index, value):
+        """Set command slot `index` (a UI slider in the reference); out-of-range slots are ignored as there."""
+        if self.user_command is None:
+            self.init_user_command()
+        if 0 <= index < self._command_dim():
+            self.user_command[..., index] = value
 
     def receive_user_command(self):
-        """Send the current user command value to the environment."""
+        """Hand the current command to the environment (called once per step by `test`)."""
         if self.user_command is None:
             self.init_user_command()
         self.env.receive_user_command(self.user_command)
 
-    def update_command(self, index, value):
-        """Update one slot of the command (the UI sliders of the reference); a [num_envs, command_dim] array may be assigned to
-        `user_command` directly for per-environment commands."""
-        if self.user_command is None:
-            self.init_user_command()
-        if index < self.config["observation"]["command_dim"]:
-            self.user_command[..., index] = value
-
     def activate_push_event(self, push_vel):
-        self._push_event = True
         self._push_vel = push_vel
 
     def deactivate_push_event(self):
-        self._push_event = False
+        self._push_vel = None
+
+    # ---- the loop -----------------------------------------------------------------------------------------------------
+    def _act(self, state):
+        try:
+            return self.policy.get_action(state)
+        except Exception as err:
+            self._had_error = True
+            self.close()
+            raise RuntimeError(_POLICY_ERROR.format(path=self.policy_path, n=state.shape[-1])) from err
 
     def test(self, report_path=None):
         if report_path is None:
-            base = os.path.dirname(self.policy_path) if self.policy_path else os.getcwd()
-            report_path = os.path.join(base, "report.pdf")
+            report_path = os.path.join(os.path.dirname(self.policy_path) if self.policy_path else os.getcwd(), "report.pdf")
         self.reporter = Reporter(report_path=report_path, config=self.config)
         self.env = build_env(self.config, num_envs=self.num_envs, device=self.device, seed=self.seed)
         self.policy = build_policy(self.config, self.policy_path, state_dim=self.env.state_dim, action_dim=self.env.action_dim,
                                    device=self.device)
         batched = self.num_envs is not None
-        state, info = self.env.reset()
-        done = False
-        finished = None
-        while not done and not self._stop:
+        finished = None                                   # batched mode: which environments have completed their episode
+        state, _ = self.env.reset()
+        while not self._stop:
             self.receive_user_command()
-            try:
-                action = self.policy.get_action(state)
-            except Exception as e:
-                self.close()
-                self._had_error = True
-                raise RuntimeError(f"Failed to run inference with the selected ONNX policy: {self.policy_path}."
-                                   f"\n\nThe current state length (={state.shape[-1]}) may not match the input length expected by the "
-                                   "ONNX policy, which could have caused this error.\n") from e
-            if self._push_event:
+            action = self._act(state)
+            if self._push_vel is not None:
                 self.env.event(event="push", value=self._push_vel)
             self.env.render()
-            assert self.user_command is not None, "user_command must not be None."
-            next_state, terminated, truncated, info = self.env.step(action)
+            state, terminated, truncated, info = self.env.step(action)
             if batched:
-                ended = (terminated | truncated)
-                finished = ended.clone() if finished is None else (finished | ended)
-                if not bool(finished[self.trace_env]) or bool(ended[self.trace_env]):
-                    self.reporter.write_info(info, env_index=self.trace_env)      # the traced environment's own episode
-                done = bool(finished.all())
+                ended = terminated | truncated
+                traced_running = finished is None or not bool(finished[self.trace_env])
+                finished = ended.clone() if finished is None else finished | ended
+                if traced_running:
+                    self.reporter.write_info(info, env_index=self.trace_env)
+                over = bool(finished.all())
             else:
                 self.reporter.write_info(info)
-                done = terminated or truncated
+                over = bool(terminated or truncated)
             if self.on_step is not None:
                 self.on_step()
-            state = next_state
+            if over:
+                break
         if not self._had_error:
             if batched:
                 self.reporter.write_population(self.env.stats())
@@ -107,13 +115,12 @@ class Tester:
         return report_path
 
     def stop(self):
-        """Stop the test loop."""
         self._stop = True
 
     def close(self):
-        """Attempt to close the environment."""
-        if self.env is not None:
+        env, self.env = self.env, None
+        if env is not None:
             try:
-                self.env.close()
+                env.close()
             except Exception:
                 pass
