@@ -1047,6 +1047,36 @@ DEV_NOINLINE void collide_hfield_all(const ModelDev& m, float* ws, int lane) {
 // body of the first geom of a contact: 0 (world) for ground contacts; geom-geom contacts carry -2 - geom1 in W_CN_CELL
 DEV int contact_body1(const ModelDev& m, const float* ws, int c) { const int cell = WSI(W_CN_CELL)[c]; return cell <= -2 ? m.geom_body[-2 - cell] : 0; }
 
+// mjc_fixNormal restated (oracle/oracle.hpp fix_normal): for smooth primitives the contact normal is rebuilt from the contact
+// point -- sphere: centre to point; cylinder: radial direction of the wall unless the point sits on / near a cap.  A normal
+// from geom 2 is flipped, two normals are averaged.  pos is in world coordinates.
+DEV void fix_normal(const ModelDev& m, const float* ws, int g1, int g2, const float* pos, float* normal) {
+  float acc[3] = {0.f, 0.f, 0.f}; int n = 0;
+  for (int i = 0; i < 2; ++i) {
+    const int g = i ? g2 : g1, type = m.geom_type[g];
+    if (type != GEOM_SPHERE && type != GEOM_CYLINDER) continue;
+    const float* R = WS(W_GXMAT) + 9 * g; const float* x = WS(W_GXPOS) + 3 * g;
+    float rel[3], loc[3]; v3sub(rel, pos, x); m3tmulv(loc, R, rel);
+    if (type == GEOM_CYLINDER) {
+      const float rad = LDG(m.geom_size + 3 * g), hl = LDG(m.geom_size + 3 * g + 1);
+      if (fabsf(loc[2]) > 0.95f * hl) continue;
+      const float dflat = fabsf(hl - fabsf(loc[2])), dround = fabsf(rad - sqrtf(loc[0] * loc[0] + loc[1] * loc[1]));
+      if (!(dround < dflat)) continue;
+      loc[2] = 0.f;
+    }
+    const float nn = v3norm(loc);
+    if (nn < MINVALF) continue;
+    v3scl(loc, loc, 1.f / nn);
+    float w[3]; m3mulv(w, R, loc);
+    if (i == 1) v3scl(w, w, -1.f);
+    v3add(acc, acc, w); ++n;
+  }
+  if (!n) return;
+  const float nn = v3norm(acc);
+  if (nn < MINVALF) return;
+  v3scl(normal, acc, 1.f / nn);
+}
+
 // ------------------------------------------------------------------------------------------ geom-geom (self) collision
 // mj_collideGeoms -> mj_filterSphere -> mjc_Convex restated (oracle/oracle.hpp collide_pairs is the serial version), different
 // schedule: (1) a lane per candidate pair runs a separating-axis cull on the two geom-frame bounding boxes (conservative: it
@@ -1134,6 +1164,7 @@ DEV_NOINLINE void collide_pairs(const ModelDev& m, float* ws, int lane) {
           if (res == 1) res = mpr_lane(A, m, ws, g2, sub | (gs << 8), gmask, ox, oy, gc, &depth, nrm, cp);
           if (res == 0 && !(nrm[0] == 0.f && nrm[1] == 0.f && nrm[2] == 0.f) && depth == depth) {
             hit = (sub == 0); cp[0] += ox; cp[1] += oy;
+            fix_normal(m, ws, g1, g2, cp, nrm);
           } else if (res == -1 && sub == 0) {          // remember the separating direction (in geom 1's frame)
             const float* R1 = WS(W_GXMAT) + 9 * g1; float* ax = WS(W_PAXIS) + 4 * (pp % PAXIS_SLOTS);
             ax[0] = __int_as_float_emu(pp + 1);

@@ -66,6 +66,7 @@ template <class T> struct OracleT : IOracle {
     typename orc::Engine<T>::ShapeA A{nullptr, &G[0]};
     T depth = 0, dir[3] = {0, 0, 0}, cp[3] = {0, 0, 0};
     int r = E.mpr_core(A, G[0].center, G[1], &depth, dir, cp);
+    if (r == 0 && !(dir[0] == 0 && dir[1] == 0 && dir[2] == 0)) orc::Engine<T>::fix_normal(G[0], G[1], cp, dir);      // as mjc_Convex does
     out[0] = depth; for (int k = 0; k < 3; ++k) { out[1 + k] = dir[k]; out[4 + k] = cp[k]; }
     return r;
   }

@@ -231,7 +231,15 @@ def test_convex_pair_known_answers():
     d = np.array([0.06, 0.05, 0.0]); d = d / np.linalg.norm(d) * 0.08
     hit, depth, n, p = o.convex_pair((5, [0.05, 0.2, 0], [1, 2, 3], R), (5, [0.05, 0.2, 0], np.array([1, 2, 3.01]) + d, R))
     assert hit and abs(depth - 0.02) < 1e-5
-    np.testing.assert_allclose(n, d / 0.08, atol=5e-3)
+    np.testing.assert_allclose(n, d / 0.08, atol=1e-9)          # mjc_fixNormal: radial direction of the cylinder walls, exact
+    # a cylinder standing on a box: the point is on the cylinder's cap -> no normal from the cylinder, MPR's is kept
+    hit, depth, n, p = o.convex_pair((5, [0.05, 0.1, 0], [0, 0, 0.19], I), (6, [0.3, 0.3, 0.1], [0, 0, 0], I))
+    assert hit and abs(depth - 0.01) < 1e-6
+    np.testing.assert_allclose(n, [0, 0, -1], atol=1e-6)
+    # a sphere resting in a box corner region: normal = centre -> contact point
+    hit, depth, n, p = o.convex_pair((2, [0.1, 0, 0], [0, 0, 0.19], I), (6, [0.3, 0.3, 0.1], [0, 0, 0], I))
+    assert hit and abs(depth - 0.01) < 1e-6
+    np.testing.assert_allclose(n, [0, 0, -1], atol=1e-4)         # through MPR's contact point (accurate to the ccd tolerance)
     hit, *_ = o.convex_pair((5, [0.05, 0.2, 0], [0, 0, 0], I), (5, [0.05, 0.2, 0], [0, 0.11, 0.01], I))
     assert not hit
 
