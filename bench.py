@@ -39,14 +39,28 @@ def workload_config():
                        engine={"auto_reset": True, "seed": 0xC051, "ncon_max": 16})
 
 
-def measured_traffic(envs):
-    """DRAM bytes per k_step launch from the committed ncu capture (profiles/r01_traffic.json), if it matches this size."""
+def _ncu_capture(envs):
     try:
         with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
             t = json.load(f)
-        return int(t["traffic_bytes_per_launch"]) if int(t["envs"]) == int(envs) else None
+        return t if int(t["envs"]) == int(envs) else None
     except Exception:
         return None
+
+
+def measured_traffic(envs):
+    """DRAM bytes per k_step launch from the committed ncu capture (profiles/r01_traffic.json), if it matches this size."""
+    t = _ncu_capture(envs)
+    return int(t["traffic_bytes_per_launch"]) if t else None
+
+
+def issue_metrics(envs):
+    """What actually bounds k_step (same ncu capture): warp instructions per launch and the share of issue slots in use."""
+    t = _ncu_capture(envs)
+    if not t or "issue_slots_active_pct" not in t:
+        return None
+    return {"warp_instructions_per_env_step": t["warp_instructions_per_launch"] / float(envs), "issue_slots_active_pct": t["issue_slots_active_pct"],
+            "registers_per_thread": t.get("registers_per_thread"), "env_warps_per_sm": t.get("block_size", 0) // 32, "source": "profiles/r01_traffic.json (ncu --set full)"}
 
 
 def measured_peaks():
@@ -267,7 +281,8 @@ def main():
                            "state + done flags -> pinned host, stream sync (per step)"},
            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": measured_traffic(N),
                         "kernel": "k_step", "kernel_ms": kernel_ms, "bytes_per_env_step": B_ALG, "peak_source": peak_src,
-                        "note": "the step is bound by the FP32 pipe / shared-memory latency, not HBM (DESIGN.md section 5)"},
+                        "issue": issue_metrics(N),
+                        "note": "the step is bound by instruction issue / dependent-latency stalls of the warp-per-env solver and by phase-barrier waits, not by HBM (DESIGN.md section 3.2)"},
            "reporter_stats": {k: stats[k] for k in ("steps", "episodes", "success_rate", "termination_rate", "mean_abs_err_lin_vel_x",
                                                     "mean_abs_err_ang_vel_yaw", "mean_contacts", "mean_solver_iters_per_step", "nan_resets", "ncon_dropped")}}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
