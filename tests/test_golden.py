@@ -26,8 +26,20 @@ def _load(path):
     return z, cfg
 
 
+def push_oracle(o, vel):
+    """The reference's push event (<robot>.py event(): robot-frame xy, world-frame z -- quirk C-12) applied to the oracle state."""
+    q, v = o.get("qpos"), o.get("qvel")
+    w, x, y, z = q[0, 3:7]
+    R = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y)],
+                  [2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x)],
+                  [2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)]])
+    local = R.T @ np.asarray(vel, dtype=np.float64)
+    v[0, 0:2] = local[0:2]; v[0, 2] = vel[2]
+    o.set("qvel", v)
+
+
 def test_fixtures_present():
-    assert len(FIXTURES) >= 5
+    assert len(FIXTURES) >= 6
 
 
 @pytest.mark.parametrize("path", FIXTURES, ids=[os.path.basename(p)[:-4] for p in FIXTURES])
@@ -40,7 +52,10 @@ def test_oracle_env_layer_reproduces_reference_python(path):
     s0 = o.reset()
     np.testing.assert_allclose(s0[0], z["reset_state"], atol=1e-6)
     n = len(z["states"])
+    pushes = dict(zip(z["push_steps"].tolist(), z["push_vels"])) if "push_steps" in z.files else {}
     for k in range(n):
+        if k in pushes:
+            push_oracle(o, pushes[k])
         s, term, trunc = o.step(z["actions"][k][None, :], z["applied"][k][None, :])
         np.testing.assert_allclose(s[0], z["states"][k], atol=3e-6, err_msg=f"state at step {k}")
         np.testing.assert_allclose(o.get("torque")[0], z["torque"][k], atol=1e-9, rtol=1e-12, err_msg=f"torque at step {k}")

@@ -406,7 +406,7 @@ def test_full_size_properties():
     assert torch.equal(outs[0], outs[1])
 
 
-@pytest.mark.parametrize("name", ["flamingo_p_v3__rocky_hard__hm", "flamingo_light_v1__flat__freq", "humanoid_p_v0__slope_hard__poscmd"])
+@pytest.mark.parametrize("name", ["flamingo_p_v3__rocky_hard__hm", "flamingo_light_v1__flat__freq", "humanoid_p_v0__slope_hard__poscmd", "flamingo_p_v3__rocky_hard__push"])
 def test_engine_replays_reference_python_golden(name):
     """tests/golden/*.npz were recorded by the reference's own Python env stack (tools/gen_golden.py).  Replay through the
     CUDA engine, teacher-forced from the oracle (which reproduces the fixture exactly, tests/test_golden.py)."""
@@ -420,9 +420,14 @@ def test_engine_replays_reference_python_golden(name):
     orc.reset(); s, _ = env.reset()
     np.testing.assert_allclose(s.cpu().numpy()[0], z["reset_state"], atol=1e-5)
     diffs = []
+    pushes = dict(zip(z["push_steps"].tolist(), z["push_vels"])) if "push_steps" in z.files else {}
     for k in range(len(z["states"])):
         for f in ("qpos", "qvel", "qacc_warmstart"):
             env.set(f, orc.get(f))
+        if k in pushes:                              # the engine's push kernel against the reference's event code
+            from tests.test_golden import push_oracle
+            env.event("push", pushes[k]); push_oracle(orc, pushes[k])
+            np.testing.assert_allclose(env.get("qvel").cpu().numpy(), orc.get("qvel"), atol=1e-6)
         env.applied_command = torch.tensor(z["applied"][k][None, :], dtype=torch.float32, device="cuda")
         env.user_command = env.applied_command
         s, term, trunc, info = env.step(z["actions"][k][None, :])

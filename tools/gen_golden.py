@@ -201,7 +201,7 @@ def install_shims():
 
 
 # --------------------------------------------------------------------------------------- recording
-def record(robot, terrain, steps, seed, height_map=False, position_command=False, max_duration=120.0, freq_override=None):
+def record(robot, terrain, steps, seed, height_map=False, position_command=False, max_duration=120.0, freq_override=None, push=None):
     from envs.build import build_env          # the reference's factory, unmodified
     et, _ = load_tables()
     kw = {}
@@ -229,6 +229,8 @@ def record(robot, terrain, steps, seed, height_map=False, position_command=False
             if k % 7 == 0:
                 user_cmd = rng.uniform(-1.0, 1.0, cfg["observation"]["command_dim"]) * (3.0 if position_command else 1.0)
             env.receive_user_command(user_cmd.copy())
+            if push and k in push:                       # the reference's own event code (<robot>.py event())
+                env.event("push", push[k])
             action = np.clip(rng.normal(0.0, 0.6, nu), -1, 1)
             state, term, trunc, info = env.step(action)
             out["states"].append(np.array(state, dtype=np.float32)); out["actions"].append(action); out["commands"].append(user_cmd.copy())
@@ -243,6 +245,8 @@ def record(robot, terrain, steps, seed, height_map=False, position_command=False
     res["config_json"] = np.array(json.dumps(cfg))
     res["state_dim"] = np.array(env.state_dim)
     res["cmd_slices"] = np.array([[s.start, s.stop] for s in env.cmd_slices])
+    res["push_steps"] = np.array(sorted(push) if push else [], dtype=np.int64)
+    res["push_vels"] = np.array([push[k] for k in sorted(push)] if push else np.zeros((0, 3)), dtype=np.float64).reshape(-1, 3)
     return res
 
 
@@ -288,11 +292,12 @@ def main():
              ("flamingo_p_v3", "flat", 12, 2, dict(max_duration=0.2)),                      # truncation at 10 control steps
              ("flamingo_light_v1", "flat", 30, 3, dict(freq_override={"dof_vel": 25, "ang_vel": 10})),
              ("w4_p_v2", "stairs_up_hard", 16, 4, {}),
-             ("humanoid_p_v0", "slope_hard", 25, 5, dict(position_command=True))]
+             ("humanoid_p_v0", "slope_hard", 25, 5, dict(position_command=True)),
+             ("flamingo_p_v3", "rocky_hard", 24, 6, dict(push={4: [0.6, -0.4, 0.3], 15: [-0.5, 0.2, 0.0]}))]
     for robot, terrain, steps, seed, kw in cases:
         res = record(robot, terrain, steps, seed, **kw)
         tag = f"{robot}__{terrain}" + ("__hm" if kw.get("height_map") else "") + ("__poscmd" if kw.get("position_command") else "") + \
-              ("__short" if kw.get("max_duration") else "") + ("__freq" if kw.get("freq_override") else "")
+              ("__short" if kw.get("max_duration") else "") + ("__freq" if kw.get("freq_override") else "") + ("__push" if kw.get("push") else "")
         np.savez_compressed(os.path.join(outdir, tag + ".npz"), **res)
         print(tag, "steps", len(res["states"]), "state_dim", int(res["state_dim"]), "terminated", bool(res["terminated"][-1]), "truncated", bool(res["truncated"][-1]))
     with open(os.path.join(outdir, "xml_semantics.json"), "w") as f:
