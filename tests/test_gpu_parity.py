@@ -242,6 +242,38 @@ def test_height_map_cells_and_values():
     env.close()
 
 
+def test_baseline_config_4096_envs_with_height_map():
+    """BASELINE.json configs[1]: flamingo_p_v3 on rocky_hard with the height map, 4096 envs, no randomization, correctness
+    against the per-env CPU step.  Envs are spread over the terrain so that they see different cells; teacher-forced control
+    steps: contact counts, height-map cells and states against the fp64 oracle."""
+    N = 4096
+    env = _env("flamingo_p_v3", "rocky_hard", N, hm=True)
+    orc = _oracle(env, N)
+    orc.reset(); env.reset()
+    rng = np.random.default_rng(17)
+    q = orc.get("qpos")
+    q[:, 0] = rng.uniform(-100, 100, N); q[:, 1] = rng.uniform(-100, 100, N); q[:, 2] += 0.25
+    orc.set("qpos", q); env.set("qpos", q)
+    same, cells_ok, errs = [], [], []
+    for i in range(6):
+        a = rng.uniform(-1, 1, (N, env.action_dim))
+        for k in ("qpos", "qvel", "qacc_warmstart"):
+            env.set(k, orc.get(k))
+        s_o, t_o, r_o = orc.step(a); s_g, t_g, r_g, _ = env.step(a)
+        s_g = s_g.cpu().numpy()
+        assert np.isfinite(s_g).all()
+        nco, ncg = orc.get("ncon")[:, 0].astype(int), env.get("counters")[:, 7].cpu().numpy()
+        same.append((nco == ncg).mean())
+        cells_ok.append((orc.get("hm_cell").astype(int) == env.get("hm_cell").cpu().numpy()).mean())
+        errs.append(np.abs(s_g[:, :88] - s_o[:, :88]).max(axis=1))
+        assert (t_g.cpu().numpy() == t_o).mean() > 0.995
+    errs = np.concatenate(errs)
+    assert min(same) >= 0.97, f"contact counts agree in {min(same):.3f} of the envs"
+    assert min(cells_ok) >= 0.995, f"height-map cells agree on {min(cells_ok):.4f} of the rays"
+    assert np.median(errs) < 2e-3 and (errs > 5e-2).mean() < 0.05, f"state error median {np.median(errs):.1e}, {(errs > 5e-2).mean():.1%} above 5e-2"
+    env.close()
+
+
 def test_sensor_noise_statistics():
     """Truncated-normal sensor noise (noise_generator_utils.py:22-28): bounded, right scale, GPU ~ oracle."""
     N = 256
