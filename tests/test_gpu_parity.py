@@ -274,6 +274,28 @@ def test_baseline_config_4096_envs_with_height_map():
     env.close()
 
 
+def test_cross_terrain_sweep():
+    """BASELINE.json configs[4]: every robot on every terrain with the full randomization table -- engine and oracle agree on
+    the reset state, and after a teacher-forced control step on contact counts (most envs) and on the state (median)."""
+    terrains = ["flat", "rocky_easy", "rocky_hard", "slope_easy", "slope_hard", "stairs_up_easy", "stairs_up_normal", "stairs_up_hard"]
+    N = 16
+    rng = np.random.default_rng(23)
+    for robot in ("flamingo_light_v1", "flamingo_p_v3", "w4_p_v2", "humanoid_p_v0"):
+        for terrain in terrains:
+            env = _env(robot, terrain, N, random=RANDOM_FULL, seed=4, debug=False)
+            orc = _oracle(env, N, seed=4)
+            s_o = orc.reset(); s_g, _ = env.reset()
+            np.testing.assert_allclose(s_g.cpu().numpy(), s_o, atol=2e-5, err_msg=f"{robot} {terrain} reset")
+            a = rng.uniform(-1, 1, (N, env.action_dim))
+            s_o, _, _ = orc.step(a); s_g, _, _, _ = env.step(a)
+            s_g = s_g.cpu().numpy()
+            assert np.isfinite(s_g).all(), (robot, terrain)
+            same = (orc.get("ncon")[:, 0].astype(int) == env.get("counters")[:, 7].cpu().numpy()).mean()
+            err = np.abs(s_g - s_o).max(axis=1)
+            assert same >= 0.75 and np.median(err) < 5e-2, f"{robot} on {terrain}: contact counts agree in {same:.2f} of the envs, median state error {np.median(err):.1e}"
+            env.close()
+
+
 def test_sensor_noise_statistics():
     """Truncated-normal sensor noise (noise_generator_utils.py:22-28): bounded, right scale, GPU ~ oracle."""
     N = 256
