@@ -715,13 +715,12 @@ DEV_NOINLINE F3 support_lane(const ModelDev& m, const float* ws, int g, int grp,
       if (v3 > bv || (v3 == bv && k3 < bk)) { bv = v3; bk = k3; px = c3.x; py = c3.y; pz = c3.z; }
     }
 #ifndef COSIM_HOST_EMU
-    if (gs > 1) {        // reduce over the lanes of the group, then fetch the winner's coordinates
-      const int mine = bk;
-      NOUNROLL for (int o = gs >> 1; o > 0; o >>= 1) {
-        const float ov = __shfl_xor_sync(gmask, bv, o); const int ok = __shfl_xor_sync(gmask, bk, o);
-        if (ov > bv || (ov == bv && ok < bk)) { bv = ov; bk = ok; }
-      }
-      const int src = __ffs(__ballot_sync(gmask, mine == bk)) - 1;
+    if (gs > 1) {        // reduce over the lanes of the group (largest support, ties: earliest candidate), then fetch the winner's coordinates
+      const float bvc = bv == 0.f ? 0.f : bv;                                   // -0 and +0 compare equal, as in the serial scan
+      unsigned key = __float_as_uint(bvc); key = (key & 0x80000000u) ? ~key : (key | 0x80000000u);      // order-preserving map float -> uint
+      const unsigned kmax = __reduce_max_sync(gmask, key);
+      const int kmin = __reduce_min_sync(gmask, key == kmax ? bk : 0x7fffffff);
+      const int src = __ffs(__ballot_sync(gmask, key == kmax && bk == kmin)) - 1;
       px = __shfl_sync(gmask, px, src); py = __shfl_sync(gmask, py, src); pz = __shfl_sync(gmask, pz, src);
     }
 #endif
