@@ -15,7 +15,7 @@ env = BatchedEnv(cfg, N, seed=0xC051)
 pol = MLPPolicy(synthetic_mlp(env.state_dim, env.action_dim), "elu")
 env.receive_user_command(torch.rand((N, env.command_dim), device="cuda") * 3 - 1.5)
 s, _ = env.reset()
-block = 50
+block = int(os.environ.get("COSIM_SOAK_BLOCK", "50"))
 for b0 in range(0, steps, block):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
