@@ -152,6 +152,10 @@ int cosim_create(const void* blob, size_t nbytes, int num_envs, int device, uint
   if (e3 == cudaSuccess) e3 = cudaFuncSetAttribute(k_substep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem);
   cudaFuncSetAttribute(k_step, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) { fprintf(stderr, "cosim_create: cudaFuncSetAttribute failed: %s\n", cudaGetErrorString(e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3))); for (void* p : h->allocs) cudaFree(p); delete h; return COSIM_ERR_CUDA; }
+  if (getenv("COSIM_PRINT_OCC")) {      // tuning aid: how many CTAs of this shape fit on an SM
+    int nb = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_step, 32 * h->wpb, h->smem);
+    fprintf(stderr, "cosim_create: k_step %d threads, %zu B dynamic smem -> %d CTA(s) per SM\n", 32 * h->wpb, h->smem, nb);
+  }
   cudaStreamCreate(&h->stream);     // blocking stream: ordered after work the caller queued on the legacy default stream (reset, set)
   k_init<<<grid_for(h), 32 * h->wpb, h->smem, h->stream>>>(h->m, h->E);
   h->launches++;
