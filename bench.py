@@ -36,7 +36,7 @@ def workload_config():
     et, _ = load_tables()
     non_stacked = list(et[ROBOT]["non_stacked_obs_order"]) + ["height_map"]
     return make_config(ROBOT, TERRAIN, random=RANDOM_FULL, non_stacked_obs_order=non_stacked,
-                       engine={"auto_reset": True, "seed": 0xC051, "ncon_max": 16})
+                       engine={"auto_reset": True, "seed": 0xC051})
 
 
 def _ncu_capture(envs):

@@ -30,30 +30,46 @@ extern __shared__ __align__(16) float g_smem[];
     __syncthreads();                                                                                     \
   }                                                                                                      \
   const ModelDev& m = *(const ModelDev*)g_smem;                                                          \
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;                                            \
-  const int env = blockIdx.x * (blockDim.x >> 5) + warp;                                                 \
-  float* ws = g_smem + m.shared_floats + (size_t)warp * m.ws_floats;
-#define ENV_PROLOGUE() CTA_PROLOGUE() if (env >= E.N) return;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb_ = blockDim.x >> 5;                    \
+  float* ws = g_smem + m.shared_floats + (size_t)warp * m.ws_floats;                                     \
+  /* global overflow slot of this resident warp (contact records beyond the shared-memory tier) */       \
+  if (lane == 0) *(float**)(ws + m.off[W_GPTR]) = m.gscratch + (size_t)(blockIdx.x * wpb_ + warp) * m.gslot_floats; \
+  __syncwarp();
+// The grid is sized to what is resident at once (engine.cu cosim_create); each CTA walks over chunks of wpb environments.
+#define FOR_ENV_CHUNKS() for (int env = blockIdx.x * wpb_ + warp; env - warp < E.N; env += gridDim.x * wpb_)
 
 __global__ void __launch_bounds__(640, 1) k_init(const __grid_constant__ ModelDev mp, const EnvArrays E) {
-  ENV_PROLOGUE();
-  init_env(m, E, env, ws, lane);
+  CTA_PROLOGUE();
+  FOR_ENV_CHUNKS() { if (env < E.N) init_env(m, E, env, ws, lane); __syncwarp(); }
 }
 __global__ void __launch_bounds__(640, 1) k_reset(const __grid_constant__ ModelDev mp, const EnvArrays E, const StepArgs a) {
-  ENV_PROLOGUE();
-  if (a.mask && !a.mask[env]) return;
-  const int cd = MD(command_dim);
-  reset_env(m, E, env, ws, a.command ? a.command + (size_t)env * cd : nullptr, a.state_out + (size_t)env * MD(state_dim), lane);
-}
-// k_step: every warp of the CTA (also the padding warps of the last CTA) walks through the phase barriers
-__global__ void __launch_bounds__(640, 1) k_step(const __grid_constant__ ModelDev mp, const EnvArrays E, const StepArgs a) {
   CTA_PROLOGUE();
-  const int have_env = env < E.N;
-  step_env(m, E, have_env ? env : 0, ws, a, lane, have_env, 1);
+  const int cd = MD(command_dim);
+  FOR_ENV_CHUNKS() {
+    if (env < E.N && !(a.mask && !a.mask[env]))
+      reset_env(m, E, env, ws, a.command ? a.command + (size_t)env * cd : nullptr, a.state_out + (size_t)env * MD(state_dim), lane);
+    __syncwarp();
+  }
+}
+// k_step: every warp of the CTA (also the padding warps of the last chunk) walks through the phase barriers.  Chunks of
+// wpb environments are claimed from a counter (dynamic: the cost of a chunk depends on what its robots are doing).
+__global__ void __launch_bounds__(640, 1) k_step(const __grid_constant__ ModelDev mp, const EnvArrays E, const StepArgs a, int* sched) {
+  CTA_PROLOGUE();
+  __shared__ int s_chunk;
+  const int nchunks = (E.N + wpb_ - 1) / wpb_;
+  for (;;) {
+    if (threadIdx.x == 0) s_chunk = atomicAdd(sched, 1);
+    __syncthreads();
+    const int chunk = s_chunk;
+    __syncthreads();
+    if (chunk >= nchunks) break;
+    const int env = chunk * wpb_ + warp, have_env = env < E.N;
+    step_env(m, E, have_env ? env : 0, ws, a, lane, have_env, 1);
+  }
 }
 __global__ void __launch_bounds__(640, 1) k_substep(const __grid_constant__ ModelDev mp, const EnvArrays E) {
-  ENV_PROLOGUE();
-  substep_env(m, E, env, ws, lane);
+  CTA_PROLOGUE();
+  FOR_ENV_CHUNKS() { if (env < E.N) substep_env(m, E, env, ws, lane); __syncwarp(); }
 }
 __global__ void k_push(const __grid_constant__ ModelDev m, const EnvArrays E, const uint8_t* mask, const float* vel) {
   const int env = blockIdx.x * blockDim.x + threadIdx.x;
@@ -91,8 +107,9 @@ __global__ void k_stats(const float* stats, int N, double* out) {
 // ------------------------------------------------------------------------------------------ handle
 struct cosim_handle {
   ModelDev m; EnvArrays E; EnvArrays Edbg;   // Edbg keeps the debug pointers while dumps are switched off
-  int N = 0, device = 0, wpb = 1, launches = 0, debug = 0;
+  int N = 0, device = 0, wpb = 1, grid = 1, launches = 0, debug = 0;
   size_t smem = 0;
+  int* sched = nullptr;                     // chunk counter of k_step (zeroed on the stream before every launch)
   std::string err;
   std::vector<void*> allocs;
   cudaStream_t stream = nullptr;            // used by cosim_step_host
@@ -113,7 +130,10 @@ static void* dev_zalloc(void* ctx, size_t bytes) {
   cudaMemset(p, 0, bytes ? bytes : 4);
   h->allocs.push_back(p); return p;
 }
-static int grid_for(const cosim_handle* h) { return (h->N + h->wpb - 1) / h->wpb; }
+static int grid_for(const cosim_handle* h) { return h->grid; }
+// every entry point runs on the handle's device, whatever the caller's current device is
+struct DeviceGuard { int prev = -1; explicit DeviceGuard(int d) { cudaGetDevice(&prev); if (prev != d) cudaSetDevice(d); else prev = -1; } ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); } };
+#define ON_DEVICE(h) DeviceGuard guard_((h)->device)
 
 extern "C" {
 
@@ -122,9 +142,10 @@ int cosim_create(const void* blob, size_t nbytes, int num_envs, int device, uint
   *out = nullptr;
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { fprintf(stderr, "cosim_b200: no CUDA device -- this library has no CPU path\n"); return COSIM_ERR_CUDA; }
+  if (device < 0 || device >= ndev) return COSIM_ERR_ARG;
   cosim_handle* h = new cosim_handle;
   h->N = num_envs; h->device = device;
-  if (cudaSetDevice(device) != cudaSuccess) { delete h; return COSIM_ERR_CUDA; }
+  ON_DEVICE(h);
   try {
     Uploader u = {dev_upload, h};
     setup::build_model(blob, nbytes, seed, env_offset, u, h->m);
@@ -146,15 +167,35 @@ int cosim_create(const void* blob, size_t nbytes, int num_envs, int device, uint
   if (num_envs < wpb * 148) { wpb = (num_envs + 147) / 148; if (wpb < 1) wpb = 1; }      // small batches: spread over the SMs
   if (per * wpb > 227 * 1024) { fprintf(stderr, "cosim_create: workspace %zu B/env exceeds shared memory\n", per); for (void* p : h->allocs) cudaFree(p); delete h; return COSIM_ERR_MODEL; }
   h->wpb = wpb; h->smem = per * wpb + h->m.shared_floats * sizeof(float);
-  cudaError_t e1 = cudaFuncSetAttribute(k_init, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem);
-  cudaError_t e2 = cudaFuncSetAttribute(k_reset, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem);
-  cudaError_t e3 = cudaFuncSetAttribute(k_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem);
-  if (e3 == cudaSuccess) e3 = cudaFuncSetAttribute(k_substep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem);
+  // The dynamic shared-memory limit is per-function state shared by every handle of the process: raise it to the device
+  // opt-in maximum once instead of to this handle's size (a second, smaller handle must not lower it for the first).
+  int optin = 0; cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+  if ((size_t)optin < h->smem + 16) { fprintf(stderr, "cosim_create: %zu B of shared memory per CTA exceed the device limit %d\n", h->smem, optin); for (void* p : h->allocs) cudaFree(p); delete h; return COSIM_ERR_MODEL; }
+  cudaError_t e1 = cudaFuncSetAttribute(k_init, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 16);
+  cudaError_t e2 = cudaFuncSetAttribute(k_reset, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 16);
+  cudaError_t e3 = cudaFuncSetAttribute(k_step, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 16);
+  if (e3 == cudaSuccess) e3 = cudaFuncSetAttribute(k_substep, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 16);
   cudaFuncSetAttribute(k_step, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) { fprintf(stderr, "cosim_create: cudaFuncSetAttribute failed: %s\n", cudaGetErrorString(e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3))); for (void* p : h->allocs) cudaFree(p); delete h; return COSIM_ERR_CUDA; }
-  if (getenv("COSIM_PRINT_OCC")) {      // tuning aid: how many CTAs of this shape fit on an SM
-    int nb = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_step, 32 * h->wpb, h->smem);
-    fprintf(stderr, "cosim_create: k_step %d threads, %zu B dynamic smem -> %d CTA(s) per SM\n", 32 * h->wpb, h->smem, nb);
+  // grid = the CTAs that are resident at once (persistent CTAs walk over chunks of wpb environments); every resident warp
+  // owns one global-memory slot for the contact records that do not fit its shared-memory tier
+  {
+    int per_sm = 0, nsm = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_step, 32 * h->wpb, h->smem);
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device);
+    if (per_sm < 1) per_sm = 1;
+    if (nsm < 1) nsm = 148;
+    const int nchunks = (num_envs + h->wpb - 1) / h->wpb;
+    h->grid = nchunks < per_sm * nsm ? nchunks : per_sm * nsm;
+    if (getenv("COSIM_PRINT_OCC")) fprintf(stderr, "cosim_create: k_step %d threads, %zu B dynamic smem -> %d CTA(s) per SM, grid %d, %d contact records in shared memory (capacity %d), %llu B overflow slot per warp\n",
+                                           32 * h->wpb, h->smem, per_sm, h->grid, h->m.cn_k, h->m.dims[CD_ncon_max], (unsigned long long)h->m.gslot_floats * 4);
+    try {
+      void* p = nullptr;
+      const size_t bytes = (size_t)h->grid * h->wpb * h->m.gslot_floats * sizeof(float);
+      if (cudaMalloc(&p, bytes ? bytes : 4) != cudaSuccess) throw std::runtime_error("cudaMalloc failed (contact overflow slots)");
+      h->allocs.push_back(p); h->m.gscratch = (float*)p;
+      h->sched = (int*)dev_zalloc(h, 16);
+    } catch (std::exception& e) { fprintf(stderr, "cosim_create: %s\n", e.what()); for (void* p : h->allocs) cudaFree(p); delete h; return COSIM_ERR_CUDA; }
   }
   cudaStreamCreate(&h->stream);     // blocking stream: ordered after work the caller queued on the legacy default stream (reset, set)
   k_init<<<grid_for(h), 32 * h->wpb, h->smem, h->stream>>>(h->m, h->E);
@@ -168,15 +209,16 @@ int cosim_create(const void* blob, size_t nbytes, int num_envs, int device, uint
 
 void cosim_destroy(cosim_handle* h) {
   if (!h) return;
-  cudaSetDevice(h->device);
+  { ON_DEVICE(h);
   for (void* p : h->allocs) cudaFree(p);
-  if (h->stream) cudaStreamDestroy(h->stream);
+  if (h->stream) cudaStreamDestroy(h->stream); }
   delete h;
 }
 const char* cosim_last_error(const cosim_handle* h) { return h ? h->err.c_str() : "null handle"; }
 
 int cosim_reset(cosim_handle* h, const uint8_t* mask, const float* command, float* state_out, void* stream) {
   if (!h || !state_out) return COSIM_ERR_ARG;
+  ON_DEVICE(h);
   StepArgs a = {nullptr, command, nullptr, state_out, nullptr, nullptr, mask};
   k_reset<<<grid_for(h), 32 * h->wpb, h->smem, (cudaStream_t)stream>>>(h->m, h->E, a);
   h->launches++;
@@ -187,8 +229,10 @@ int cosim_reset(cosim_handle* h, const uint8_t* mask, const float* command, floa
 int cosim_step(cosim_handle* h, const float* action, const float* command, const float* user_command, float* state_out,
                uint8_t* terminated, uint8_t* truncated, void* stream) {
   if (!h || !action || !state_out || !terminated || !truncated) return COSIM_ERR_ARG;
+  ON_DEVICE(h);
   StepArgs a = {action, command, user_command, state_out, terminated, truncated, nullptr};
-  k_step<<<grid_for(h), 32 * h->wpb, h->smem, (cudaStream_t)stream>>>(h->m, h->E, a);
+  CK(cudaMemsetAsync(h->sched, 0, sizeof(int), (cudaStream_t)stream));
+  k_step<<<grid_for(h), 32 * h->wpb, h->smem, (cudaStream_t)stream>>>(h->m, h->E, a, h->sched);
   h->launches++;
   CK(cudaGetLastError());
   return COSIM_OK;
@@ -197,6 +241,7 @@ int cosim_step(cosim_handle* h, const float* action, const float* command, const
 int cosim_step_host(cosim_handle* h, const float* action_host, const float* command_host, float* state_out_host,
                     uint8_t* terminated_host, uint8_t* truncated_host) {
   if (!h || !action_host || !state_out_host || !terminated_host || !truncated_host) return COSIM_ERR_ARG;
+  ON_DEVICE(h);
   const setup::EnvDims d = setup::env_dims(h->m);
   const size_t n = (size_t)h->N;
   if (!h->d_action) {
@@ -218,6 +263,7 @@ int cosim_step_host(cosim_handle* h, const float* action_host, const float* comm
 
 int cosim_substep(cosim_handle* h, void* stream) {
   if (!h) return COSIM_ERR_ARG;
+  ON_DEVICE(h);
   k_substep<<<grid_for(h), 32 * h->wpb, h->smem, (cudaStream_t)stream>>>(h->m, h->E);
   h->launches++;
   CK(cudaGetLastError());
@@ -226,6 +272,7 @@ int cosim_substep(cosim_handle* h, void* stream) {
 
 int cosim_push(cosim_handle* h, const uint8_t* mask, const float* vel_world, void* stream) {
   if (!h || !vel_world) return COSIM_ERR_ARG;
+  ON_DEVICE(h);
   k_push<<<(h->N + 127) / 128, 128, 0, (cudaStream_t)stream>>>(h->m, h->E, mask, vel_world);
   h->launches++;
   CK(cudaGetLastError());
@@ -244,6 +291,7 @@ int cosim_field_is_int(const cosim_handle* h, const char* field) {
 }
 int cosim_get(cosim_handle* h, const char* field, void* dst, void* stream) {
   if (!h || !field || !dst) return COSIM_ERR_ARG;
+  ON_DEVICE(h);
   for (auto& f : setup::env_fields(h->m, h->E)) if (!strcmp(f.name, field)) {
     if (!f.ptr) { h->err = std::string("field '") + field + "' needs cosim_set_debug(h, 1)"; return COSIM_ERR_FIELD; }
     CK(cudaMemcpyAsync(dst, f.ptr, (size_t)h->N * f.dim * 4, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
@@ -254,6 +302,7 @@ int cosim_get(cosim_handle* h, const char* field, void* dst, void* stream) {
 }
 int cosim_set(cosim_handle* h, const char* field, const void* src, void* stream) {
   if (!h || !field || !src) return COSIM_ERR_ARG;
+  ON_DEVICE(h);
   const std::string n(field);
   if (n != "qpos" && n != "qvel" && n != "qacc_warmstart" && n != "torque") { h->err = "cosim_set: only qpos, qvel, qacc_warmstart, torque are writable"; return COSIM_ERR_FIELD; }
   for (auto& f : setup::env_fields(h->m, h->E)) if (n == f.name) {
@@ -264,6 +313,7 @@ int cosim_set(cosim_handle* h, const char* field, const void* src, void* stream)
 }
 int cosim_set_debug(cosim_handle* h, int enable) {
   if (!h) return COSIM_ERR_ARG;
+  ON_DEVICE(h);
   if (enable) {
     if (h->debug == 2) h->E = h->Edbg;      // re-enable: restore the saved pointers
     else if (!h->E.dbg_contacts) { try { setup::alloc_debug(h->m, h->N, h->E, dev_zalloc, h); } catch (std::exception& e) { h->err = e.what(); return COSIM_ERR_CUDA; } }
@@ -278,6 +328,7 @@ int cosim_set_debug(cosim_handle* h, int enable) {
 
 int cosim_stats_reduce(cosim_handle* h, double* out, void* stream) {
   if (!h || !out) return COSIM_ERR_ARG;
+  ON_DEVICE(h);
   CK(cudaMemsetAsync(out, 0, COSIM_NSTAT * sizeof(double), (cudaStream_t)stream));
   int blocks = (h->N + 1023) / 1024; if (blocks > 148) blocks = 148; if (blocks < 1) blocks = 1;
   k_stats<<<blocks, 8 * ST__COUNT, 0, (cudaStream_t)stream>>>(h->E.stats, h->N, out);
@@ -287,11 +338,13 @@ int cosim_stats_reduce(cosim_handle* h, double* out, void* stream) {
 }
 int cosim_stats_clear(cosim_handle* h, void* stream) {
   if (!h) return COSIM_ERR_ARG;
+  ON_DEVICE(h);
   CK(cudaMemsetAsync(h->E.stats, 0, (size_t)h->N * ST__COUNT * sizeof(float), (cudaStream_t)stream));
   return COSIM_OK;
 }
 int cosim_rng_probe(cosim_handle* h, uint32_t rng_stream, uint32_t step, int nidx, uint32_t* out, void* stream) {
   if (!h || !out || nidx <= 0) return COSIM_ERR_ARG;
+  ON_DEVICE(h);
   const int n = h->N * nidx;
   k_rng_probe<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(h->m, h->N, rng_stream, step, nidx, out);
   h->launches++;

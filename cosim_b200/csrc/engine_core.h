@@ -43,6 +43,8 @@ static inline float wsum(float v) { return v; }
 static inline float wmaxf(float v) { return v; }
 static inline int wor(int v) { return v; }
 static inline void wargmax(float& v, int& i) {}
+static inline unsigned wballot(int p) { return p ? 1u : 0u; }
+template <class T> static inline T wshfl(T v, int) { return v; }
 static inline float fast_ndtri(float p);
 static inline int popc32(unsigned x) { return __builtin_popcount(x); }
 static inline int __float_as_int_emu(float f) { int i; memcpy(&i, &f, 4); return i; }
@@ -71,6 +73,8 @@ DEV float wmaxf(float v) {
   return v;
 }
 DEV int wor(int v) { return __any_sync(0xffffffffu, v); }
+DEV unsigned wballot(int p) { return __ballot_sync(0xffffffffu, p); }
+template <class T> DEV T wshfl(T v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 // arg-max with lowest-index tie break; result broadcast to all lanes
 DEV void wargmax(float& v, int& i) {
 #pragma unroll
@@ -172,6 +176,13 @@ struct ModelDev {
   uint32_t seed_lo, seed_hi, env_offset;
   unsigned long long* phase;      // [PH__COUNT] cycle counters, profiling builds only (else NULL)
   int bsync_mask;                 // which of the CTA-wide phase barriers of forward() are enabled (bit 0 .. 3)
+  // contact store: one record of cr_stride floats per contact (layout CR_*).  The first cn_k records of an env live in
+  // its shared-memory workspace (W_CN_REC), the rest in the global-memory overflow slot of the resident warp
+  // (gscratch + slot * gslot_floats, L2-resident: only ~3000 slots exist per GPU).  Capacity = dims[CD_ncon_max].
+  int cn_k, cr_stride; float* gscratch; unsigned long long gslot_floats;
+  // conservative culls ahead of the terrain narrow phase: max height per 8 x 8 block of cells, and per-geom bounding
+  // cylinders (geom frame: centre, unit axis, radius, half length; radius 0 = none)
+  const float* hf_max8; int hf_mrow, hf_mcol; const float* geom_bcyl;
 };
 #define MD(name) (m.dims[CD_##name])
 #define MO(name) (m.opts[CO_##name])
@@ -182,12 +193,19 @@ enum WsField {
   W_FSMOOTH, W_ASMOOTH, W_FCON, W_GRAD, W_SEARCH, W_MV, W_MA, W_TMPV, W_TMPW,
   W_BMASS, W_INVWD, W_INVWB, W_FLOSS, W_GMU, W_SCAL,
   W_FR_D, W_FR_AREF, W_LM_SIGN, W_LM_D, W_LM_AREF,
-  W_CN_POS, W_CN_FRAME, W_CN_DIST, W_CN_MU, W_CN_BODY, W_CN_GEOM, W_CN_CELL, W_CN_D, W_CN_AREF, W_CN_J, W_CN_F, W_CN_X, W_CN_V,
+  W_CN_REC, W_GPTR, W_RING,
   W_EQ_J, W_EQ_D, W_EQ_AREF, W_EQ_X, W_EQ_V, W_EQ_F, W_SENS, W_RAW, W_ACT, W_FILT, W_KP, W_KD, W_GTASK, W_CNT, W_PAXIS, W__COUNT   // keep <= 80 (ModelDev::off)
 };
 static_assert(W__COUNT <= 80, "ModelDev::off too small");
 #define WS(f) (ws + m.off[f])
 #define WSI(f) ((int*)(ws + m.off[f]))
+// record of contact c: shared-memory tier below cn_k, else the warp's global overflow slot (pointer kept in W_GPTR)
+#define CREC(c) cn_rec(m, ws, (c))
+#define CRECI(c) ((int*)cn_rec(m, ws, (c)))
+// contact record (floats): position, frame (normal, t1, t2 rows), distance, friction, body / geom / cell (ints), the
+// pyramid's shared D, then per edge: reference acceleration, residual X = J a - aref, V = J search; frame force; 3 x nv frame Jacobian
+enum { CR_POS = 0, CR_FRAME = 3, CR_DIST = 12, CR_MU = 13, CR_BODY = 14, CR_GEOM = 15, CR_CELL = 16, CR_D = 17, CR_AREF = 18, CR_X = 22, CR_V = 26, CR_F = 30, CR_J = 33 };
+enum { RING_SIZE = 64 };
 // W_SCAL: [0] ground mu, [1] meaninertia, [2] delay_prob, [3] unused
 // W_CNT (ints, warp-uniform counters kept in shared memory so they need not travel by reference through the out-of-line
 // calls): [0] contacts of the last forward pass, [1] contacts dropped in it, [2] NaN resets, [3] dropped in this control step
@@ -270,6 +288,12 @@ DEV void cross_motion(float* r, const float* v, const float* s) {
 DEV void cross_force(float* r, const float* v, const float* f) {
   float a[3], b[3], c[3]; v3cross(a, v, f); v3cross(b, v + 3, f + 3); v3cross(c, v, f + 3);
   r[0] = a[0] + b[0]; r[1] = a[1] + b[1]; r[2] = a[2] + b[2]; r[3] = c[0]; r[4] = c[1]; r[5] = c[2];
+}
+
+DEV float* cn_rec(const ModelDev& m, const float* ws, int c) {
+  if (c < m.cn_k) return (float*)ws + m.off[W_CN_REC] + c * m.cr_stride;
+  float* g = *(float* const*)(ws + m.off[W_GPTR]);
+  return g + (size_t)(c - m.cn_k) * m.cr_stride;
 }
 
 // ------------------------------------------------------------------------------------------ RNG
@@ -652,16 +676,17 @@ DEV void make_frame(float* frame) {
   v3addscl(t1, tmp, n, -dn); v3normalize(t1);
   v3cross(t2, n, t1);
 }
+// write the geometric part of contact record `slot` (one lane)
+DEV void write_contact(const ModelDev& m, float* ws, int slot, const float* pos, const float* normal, float dist, float mu, int body, int g, int cell) {
+  float* r = CREC(slot);
+  v3copy(r + CR_POS, pos); v3copy(r + CR_FRAME, normal); make_frame(r + CR_FRAME);
+  r[CR_DIST] = dist; r[CR_MU] = mu;
+  ((int*)r)[CR_BODY] = body; ((int*)r)[CR_GEOM] = g; ((int*)r)[CR_CELL] = cell;
+}
 // all lanes call with identical arguments; lane 0 writes.  ncon is warp-uniform (register) state
 DEV_NOINLINE void add_contact(const ModelDev& m, float* ws, int& ncon, int& dropped, const float* pos, const float* normal, float dist, int g, int cell, int lane) {
   if (ncon >= MD(ncon_max)) { ++dropped; return; }
-  if (lane == 0) {
-    float* cp = WS(W_CN_POS) + 3 * ncon; float* fr = WS(W_CN_FRAME) + 9 * ncon;
-    v3copy(cp, pos); v3copy(fr, normal); make_frame(fr);
-    WS(W_CN_DIST)[ncon] = dist;
-    WS(W_CN_MU)[ncon] = fmaxf(WS(W_SCAL)[0], WS(W_GMU)[g]);
-    WSI(W_CN_BODY)[ncon] = m.geom_body[g]; WSI(W_CN_GEOM)[ncon] = g; WSI(W_CN_CELL)[ncon] = cell;
-  }
+  if (lane == 0) write_contact(m, ws, ncon, pos, normal, dist, fmaxf(WS(W_SCAL)[0], WS(W_GMU)[g]), m.geom_body[g], g, cell);
   ++ncon;
 }
 
@@ -904,13 +929,130 @@ template <class A> DEV int mpr_lane(const A& P, GQ_PARAMS, const float* gcenter,
   }
 }
 
-// per-geom task record in W_GTASK: [cmin, rmin, ncols, nrows, first task, contacts so far, zmin (float), unused]
+// Conservative separation tests between a terrain prism and the BOUNDING shapes of a geom (oriented box from geom_aabb,
+// bounding sphere, bounding cylinder of wheel-like hulls), in the local frame of the query.  A prism they remove is separated
+// from the geom by more than CULL_MARGIN, so the MPR query of the serial reference loop would report "no contact" for it:
+// results do not change, only the number of MPR queries (w4_p_v2 on the 9.8 mm stairs raster: thousands of prisms per sub-step
+// under the AABBs of its 17 hulls, a few dozen of them near a wheel).
+#define CULL_MARGIN 2e-5f
+struct GeomBound { float cb[3], h[3], cs[3], rb, cc[3], ca[3], cr, chl; const float* R; };
+// largest d . y over the bounding shapes (d unit length)
+DEV float bound_support(const GeomBound& B, const float* d) {
+  const float* R = B.R;
+  const float a0 = d[0] * R[0] + d[1] * R[3] + d[2] * R[6], a1 = d[0] * R[1] + d[1] * R[4] + d[2] * R[7], a2 = d[0] * R[2] + d[1] * R[5] + d[2] * R[8];
+  float s = v3dot(d, B.cb) + B.h[0] * fabsf(a0) + B.h[1] * fabsf(a1) + B.h[2] * fabsf(a2);
+  s = fminf(s, v3dot(d, B.cs) + B.rb);
+  if (B.cr > 0.f) { const float ad = v3dot(d, B.ca); s = fminf(s, v3dot(d, B.cc) + B.chl * fabsf(ad) + B.cr * sqrtf(fmaxf(0.f, 1.f - ad * ad))); }
+  return s;
+}
+DEV void make_bound(const ModelDev& m, const float* ws, int g, float ox, float oy, GeomBound& B) {
+  const float* R = WS(W_GXMAT) + 9 * g; const float* pos = WS(W_GXPOS) + 3 * g; const float* ab = m.geom_aabb + 6 * g; const float* bc = m.geom_bcyl + 8 * g;
+  B.R = R;
+  const float o[3] = {pos[0] - ox, pos[1] - oy, pos[2]};
+  { const float c[3] = {LDG(ab), LDG(ab + 1), LDG(ab + 2)}; float r[3]; m3mulv(r, R, c); v3add(B.cb, o, r); B.h[0] = LDG(ab + 3); B.h[1] = LDG(ab + 4); B.h[2] = LDG(ab + 5); }
+  { const float c[3] = {LDG(m.geom_center + 3 * g), LDG(m.geom_center + 3 * g + 1), LDG(m.geom_center + 3 * g + 2)}; float r[3]; m3mulv(r, R, c); v3add(B.cs, o, r); B.rb = LDG(m.geom_rbound + g) * 1.0001f + 1e-6f; }
+  B.cr = LDG(bc + 6); B.chl = LDG(bc + 7);
+  { const float c[3] = {LDG(bc), LDG(bc + 1), LDG(bc + 2)}, a[3] = {LDG(bc + 3), LDG(bc + 4), LDG(bc + 5)}; float r[3]; m3mulv(r, R, c); v3add(B.cc, o, r); m3mulv(B.ca, R, a); }
+}
+// true = the prism with top vertices (x, y, z)[0..2] (bottoms at -base) cannot touch the geom
+DEV bool prism_culled(const GeomBound& B, const float* x, const float* y, const float* z) {
+  // (1) the prism lies below the plane of its top face
+  float n[3]; { const float e1[3] = {x[1] - x[0], y[1] - y[0], z[1] - z[0]}, e2[3] = {x[2] - x[0], y[2] - y[0], z[2] - z[0]}; v3cross(n, e1, e2); }
+  const float nn = v3norm(n);
+  if (nn > 1e-12f) {
+    const float sgn = n[2] < 0.f ? 1.f / nn : -1.f / nn;        // d = downward unit normal of the top face
+    const float d[3] = {n[0] * sgn, n[1] * sgn, n[2] * sgn};
+    if (bound_support(B, d) < d[0] * x[0] + d[1] * y[0] + d[2] * z[0] - CULL_MARGIN) return true;
+  }
+  // (2) direction from the bounding shape's core (cylinder axis segment, else box centre) to the top face
+  const float p[3] = {(x[0] + x[1] + x[2]) * (1.f / 3.f), (y[0] + y[1] + y[2]) * (1.f / 3.f), (z[0] + z[1] + z[2]) * (1.f / 3.f)};
+  float q[3];
+  if (B.cr > 0.f) { float w[3]; v3sub(w, p, B.cc); const float t = fminf(B.chl, fmaxf(-B.chl, v3dot(w, B.ca))); v3addscl(q, B.cc, B.ca, t); }
+  else v3copy(q, B.cb);
+  float d[3]; v3sub(d, p, q);
+  const float dn = v3norm(d);
+  if (dn > 1e-6f && d[2] < 0.f) {       // pointing down: the prism's smallest d . x is at a top vertex
+    v3scl(d, d, 1.f / dn);
+    const float pm = fminf(d[0] * x[0] + d[1] * y[0] + d[2] * z[0], fminf(d[0] * x[1] + d[1] * y[1] + d[2] * z[1], d[0] * x[2] + d[1] * y[2] + d[2] * z[2]));
+    if (pm - bound_support(B, d) > CULL_MARGIN) return true;
+  }
+  return false;
+}
+
+// per-geom task record in W_GTASK: [cmin, rmin, ncols, nrows, unused, contacts so far, zmin (float), unused]
+// one batch of `n` (<= LANES / gs) narrow-phase queries from the ring (entry = geom << 24 | prism index inside the geom's sub-grid),
+// gs lanes per query; hits are appended in ring (= task) order, honouring the 50-per-geom cap and the store's capacity
+DEV_NOINLINE void mpr_batch(const ModelDev& m, float* ws, int head, int n, int gs, int lane) {
+  const int ncol = MD(hf_ncol), nrow = MD(hf_nrow);
+  const float sx = MO(hf_sx), sy = MO(hf_sy), sz = MO(hf_sz), base = MO(hf_base);
+  const float dx = 2.f * sx / (float)(ncol - 1), dy = 2.f * sy / (float)(nrow - 1);
+  int* task = WSI(W_GTASK); const int* ring = WSI(W_RING);
+  int ncon = WSI(W_CNT)[CNT_NCON], dropped = WSI(W_CNT)[CNT_DROPPED];
+  const int sub = lane & (gs - 1), k = lane / gs;
+  const unsigned gmask = ((gs >= 32 ? 0u : (1u << gs)) - 1u) << (lane & ~(gs - 1));
+  int hit = 0, g = 0, cell = -1; float depth = 0.f, nrm[3] = {0.f, 0.f, 0.f}, cp[3] = {0.f, 0.f, 0.f};
+  if (k < n) {
+    const int ent = ring[(head + k) & (RING_SIZE - 1)];
+    g = (int)((unsigned)ent >> 24);
+    const int local = ent & 0xffffff;
+    const int* tk = task + 8 * g;
+    if (tk[5] < 50) {
+      const int per_row = 2 * tk[2];
+      const int r = tk[1] + local / per_row, rem = local % per_row, c = tk[0] + 1 + (rem >> 1), i = rem & 1;
+      // strip walk of the reference: triangle i of cell (r, c-1): i = 0 -> (c-1,r) (c-1,r+1) (c,r); i = 1 -> (c-1,r+1) (c,r) (c,r+1)
+      const int ca = c - 1, ra = r + i, cb = i ? c : c - 1, rbb = i ? r : r + 1, cc = c, rc = r + i;
+      // The query runs in a frame whose xy origin is the first grid vertex of this geom's sub-grid: far from the world
+      // origin (terrains span +-140 m) fp32 world coordinates resolve ~1e-5 m, ten times the MPR tolerance, while the
+      // local coordinates of prism and geom stay below a few metres.  Only the origin shift is rounded, and it is the
+      // same for both shapes.
+      const float ox = dx * (float)tk[0] - sx, oy = dy * (float)tk[1] - sy;
+      PrismA PA; PrismL& P = PA.P; P.base = base;
+      P.x[0] = dx * (float)(ca - tk[0]); P.y[0] = dy * (float)(ra - tk[1]); P.z[0] = LDGB(m.hfield_data + (size_t)ra * ncol + ca) * sz;
+      P.x[1] = dx * (float)(cb - tk[0]); P.y[1] = dy * (float)(rbb - tk[1]); P.z[1] = LDGB(m.hfield_data + (size_t)rbb * ncol + cb) * sz;
+      P.x[2] = dx * (float)(cc - tk[0]); P.y[2] = dy * (float)(rc - tk[1]); P.z[2] = LDGB(m.hfield_data + (size_t)rc * ncol + cc) * sz;
+#if defined(COSIM_PHASE_TIMING) && !defined(COSIM_HOST_EMU)
+      if (sub == 0) atomicAdd(m.phase + PH_MPR_CALLS, 1ull);
+#endif
+      const float cl[3] = {LDG(m.geom_center + 3 * g), LDG(m.geom_center + 3 * g + 1), LDG(m.geom_center + 3 * g + 2)};
+      const float* gpos = WS(W_GXPOS) + 3 * g;
+      float gc[3]; m3mulv(gc, WS(W_GXMAT) + 9 * g, cl);
+      gc[0] += gpos[0] - ox; gc[1] += gpos[1] - oy; gc[2] += gpos[2];
+      if (mpr_lane(PA, m, ws, g, sub | (gs << 8), gmask, ox, oy, gc, &depth, nrm, cp) == 0 && !(nrm[0] == 0.f && nrm[1] == 0.f && nrm[2] == 0.f) && depth == depth) {
+        hit = (sub == 0); cell = ((r * ncol + (c - 1)) << 1) | i;       // one lane per group reports the contact
+        cp[0] += ox; cp[1] += oy;
+      }
+    }
+  }
+  // ---- append the hits of this batch in task order, honouring the per-geom cap (50) and the capacity of the store
+  const int cap = MD(ncon_max);
+  unsigned hits = wballot(hit);
+  while (hits) {
+    const int src = ctz32(hits);
+    const int gsrc = wshfl(g, src);
+    const unsigned same = wballot(hit && g == gsrc);      // hits of this geom, in task order
+    const int have = task[8 * gsrc + 5];
+    const int rank = popc32(same & ((1u << lane) - 1u));
+    const int keep = hit && g == gsrc && (have + rank) < 50;
+    const unsigned keepm = wballot(keep);
+    const int slot = ncon + popc32(keepm & ((1u << lane) - 1u));
+    if (keep && slot < cap) write_contact(m, ws, slot, cp, nrm, -depth, fmaxf(WS(W_SCAL)[0], WS(W_GMU)[g]), m.geom_body[g], g, cell);
+    const int nkeep = popc32(keepm), room = imax(0, cap - ncon);
+    dropped += imax(0, nkeep - room); ncon += imin(nkeep, room);
+    SYNC();
+    if (lane == 0) task[8 * gsrc + 5] = have + nkeep;
+    SYNC();
+    hits &= ~same;
+  }
+  if (lane == 0) { WSI(W_CNT)[CNT_NCON] = ncon; WSI(W_CNT)[CNT_DROPPED] = dropped; }
+  SYNC();
+}
+
 DEV_NOINLINE void collide_hfield_all(const ModelDev& m, float* ws, int lane) {
-  int ncon = 0, dropped = 0;
   const int ng = MD(ngeom), nrow = MD(hf_nrow), ncol = MD(hf_ncol);
   const float sx = MO(hf_sx), sy = MO(hf_sy), sz = MO(hf_sz), base = MO(hf_base);
   const float dx = 2.f * sx / (float)(ncol - 1), dy = 2.f * sy / (float)(nrow - 1);
   int* task = WSI(W_GTASK);
+  if (lane == 0) { WSI(W_CNT)[CNT_NCON] = 0; WSI(W_CNT)[CNT_DROPPED] = 0; }
   // ---- stage 1: one group of gs1 lanes per geom (gs1 = largest power of two with ng * gs1 <= LANES)
   int gs1 = 1;
 #ifndef COSIM_HOST_EMU
@@ -941,8 +1083,13 @@ DEV_NOINLINE void collide_hfield_all(const ModelDev& m, float* ws, int lane) {
           hmax = fmaxf(fmaxf(hmax, fmaxf(h0, h1)), fmaxf(h2, h3));
         }
         hmax *= sz;
-        if (pos[2] - rb > hmax) continue;
+      } else if (m.hf_max8 && c1 >= c0 && r1 >= r0) {        // fine rasters: block maxima (8 x 8 cells per block)
+        hmax = -INFINITY;
+        const int bw = (c1 >> 3) - (c0 >> 3) + 1, bcnt = bw * ((r1 >> 3) - (r0 >> 3) + 1);
+        NOUNROLL for (int t = 0; t < bcnt; ++t) hmax = fmaxf(hmax, LDGB(m.hf_max8 + (size_t)((r0 >> 3) + t / bw) * m.hf_mcol + (c0 >> 3) + t % bw));
+        hmax *= sz;
       }
+      if (pos[2] - rb > hmax) continue;
     }
     float xmin[3], xmax[3];
     xmin[2] = support_lane(m, ws, g, grp1, gmask1, 0.f, 0.f, 0.f, 0.f, -1.f).z;
@@ -960,91 +1107,53 @@ DEV_NOINLINE void collide_hfield_all(const ModelDev& m, float* ws, int lane) {
     if (sub1 == 0) { tk[0] = cmin; tk[1] = rmin; tk[2] = cmax - cmin; tk[3] = rmax - rmin; ((float*)tk)[6] = xmin[2]; }
   }
   SYNC();
-  // ---- prefix of task counts (ngeom <= 32 is not required: serial scan by every lane over <= ngeom entries)
-  int T = 0;
-  NOUNROLL for (int g = 0; g < ng; ++g) { const int n = 2 * task[8 * g + 2] * task[8 * g + 3]; if (lane == 0) task[8 * g + 4] = T; T += n; }
-  SYNC();
-  // ---- stage 2: one group of gs2 lanes per prism (few prisms: wide groups share the candidate scans), chunks of
-  //      LANES / gs2 tasks in reference order
-  int gs2 = 1;
-#ifndef COSIM_HOST_EMU
-  gs2 = T <= 4 ? 8 : (T <= 8 ? 4 : (T <= 16 ? 2 : 1));
-#endif
-  const int sub2 = lane & (gs2 - 1);
-  const unsigned gmask2 = ((gs2 >= 32 ? 0u : (1u << gs2)) - 1u) << (lane & ~(gs2 - 1));
-  NOUNROLL for (int t0 = 0; t0 < T; t0 += LANES / gs2) {
-    const int t = t0 + lane / gs2;
-    int hit = 0, g = 0, cell = -1; float depth = 0.f, nrm[3] = {0.f, 0.f, 0.f}, cp[3] = {0.f, 0.f, 0.f};
-    if (t < T) {
-      NOUNROLL for (int k = 1; k < ng; ++k) if (task[8 * k + 4] <= t && task[8 * k + 2] * task[8 * k + 3] > 0) g = k;
-      // (the scan keeps the LAST geom whose first task is <= t and that has tasks; geoms without tasks never own t)
-      const int* tk = task + 8 * g;
-      if (tk[2] * tk[3] > 0 && t >= tk[4] && tk[5] < 50) {
-        const int local = t - tk[4], per_row = 2 * tk[2];
-        const int r = tk[1] + local / per_row, rem = local % per_row, c = tk[0] + 1 + (rem >> 1), i = rem & 1;
-        // strip walk of the reference: triangle i of cell (r, c-1): i = 0 -> (c-1,r) (c-1,r+1) (c,r); i = 1 -> (c-1,r+1) (c,r) (c,r+1)
+  // ---- stage 2: a lane per prism runs the reference's height test and the bounding-shape culls; the survivors queue up in
+  //      a ring (task order), and whenever 32 of them wait one MPR batch runs with a lane per query.  What is left at the
+  //      end runs with wider lane groups that share the hull scans (the common case on coarse rasters: a handful of prisms).
+  int* ring = WSI(W_RING);
+  int rhead = 0, rcount = 0;
+  NOUNROLL for (int g = 0; g < ng; ++g) {
+    const int* tk = task + 8 * g;
+    const int cmin = tk[0], rmin = tk[1], ncols = tk[2], nrows = tk[3], Tg = 2 * ncols * nrows;
+    if (Tg == 0) continue;
+    if (Tg >= (1 << 24)) { if (lane == 0) WSI(W_CNT)[CNT_DROPPED] += 1; continue; }      // sub-grid beyond the task encoding (a geom spanning > 2000 x 2000 cells)
+    const float zmin = ((const float*)tk)[6];
+    const float ox = dx * (float)cmin - sx, oy = dy * (float)rmin - sy;
+    GeomBound B; make_bound(m, ws, g, ox, oy, B);
+    const int per_row = 2 * ncols;
+    NOUNROLL for (int t0 = 0; t0 < Tg; t0 += LANES) {
+      if (tk[5] >= 50) break;                 // this geom already has its 50 contacts (mjMAXCONPAIR)
+      const int t = t0 + lane;
+      int pass = 0;
+      if (t < Tg) {
+        const int r = rmin + t / per_row, rem = t % per_row, c = cmin + 1 + (rem >> 1), i = rem & 1;
         const int ca = c - 1, ra = r + i, cb = i ? c : c - 1, rbb = i ? r : r + 1, cc = c, rc = r + i;
-        // The query runs in a frame whose xy origin is the first grid vertex of this geom's sub-grid: far from the world
-        // origin (terrains span +-140 m) fp32 world coordinates resolve ~1e-5 m, ten times the MPR tolerance, while the
-        // local coordinates of prism and geom stay below a few metres.  Only the origin shift is rounded, and it is the
-        // same for both shapes.
-        const float ox = dx * (float)tk[0] - sx, oy = dy * (float)tk[1] - sy;
-        PrismA PA; PrismL& P = PA.P; P.base = base;
-        P.x[0] = dx * (float)(ca - tk[0]); P.y[0] = dy * (float)(ra - tk[1]); P.z[0] = LDGB(m.hfield_data + (size_t)ra * ncol + ca) * sz;
-        P.x[1] = dx * (float)(cb - tk[0]); P.y[1] = dy * (float)(rbb - tk[1]); P.z[1] = LDGB(m.hfield_data + (size_t)rbb * ncol + cb) * sz;
-        P.x[2] = dx * (float)(cc - tk[0]); P.y[2] = dy * (float)(rc - tk[1]); P.z[2] = LDGB(m.hfield_data + (size_t)rc * ncol + cc) * sz;
-        const float zmin = ((const float*)tk)[6];
-        if (!(P.z[0] < zmin && P.z[1] < zmin && P.z[2] < zmin)) {
-#if defined(COSIM_PHASE_TIMING) && !defined(COSIM_HOST_EMU)
-          if (sub2 == 0) atomicAdd(m.phase + PH_MPR_CALLS, 1ull);
-#endif
-          const float cl[3] = {LDG(m.geom_center + 3 * g), LDG(m.geom_center + 3 * g + 1), LDG(m.geom_center + 3 * g + 2)};
-          const float* gpos = WS(W_GXPOS) + 3 * g;
-          float gc[3]; m3mulv(gc, WS(W_GXMAT) + 9 * g, cl);
-          gc[0] += gpos[0] - ox; gc[1] += gpos[1] - oy; gc[2] += gpos[2];
-          if (mpr_lane(PA, m, ws, g, sub2 | (gs2 << 8), gmask2, ox, oy, gc, &depth, nrm, cp) == 0 && !(nrm[0] == 0.f && nrm[1] == 0.f && nrm[2] == 0.f) && depth == depth) {
-            hit = (sub2 == 0); cell = ((r * ncol + (c - 1)) << 1) | i;       // one lane per group reports the contact
-            cp[0] += ox; cp[1] += oy;
-          }
-        }
+        float x[3], y[3], z[3];
+        x[0] = dx * (float)(ca - cmin); y[0] = dy * (float)(ra - rmin); z[0] = LDGB(m.hfield_data + (size_t)ra * ncol + ca) * sz;
+        x[1] = dx * (float)(cb - cmin); y[1] = dy * (float)(rbb - rmin); z[1] = LDGB(m.hfield_data + (size_t)rbb * ncol + cb) * sz;
+        x[2] = dx * (float)(cc - cmin); y[2] = dy * (float)(rc - rmin); z[2] = LDGB(m.hfield_data + (size_t)rc * ncol + cc) * sz;
+        pass = !(z[0] < zmin && z[1] < zmin && z[2] < zmin) && !prism_culled(B, x, y, z);
       }
-    }
-    // ---- append the hits of this chunk in task order, honouring the per-geom cap (50) and ncon_max
-#ifdef COSIM_HOST_EMU
-    if (hit && task[8 * g + 5] < 50) { add_contact(m, ws, ncon, dropped, cp, nrm, -depth, g, cell, lane); task[8 * g + 5]++; }
-#else
-    unsigned hits = __ballot_sync(0xffffffffu, hit);
-    while (hits) {
-      const int src = __ffs(hits) - 1;
-      const int gs = __shfl_sync(0xffffffffu, g, src);
-      const unsigned same = __ballot_sync(0xffffffffu, hit && g == gs);      // hits of this geom, in task order
-      const int have = task[8 * gs + 5];
-      const int rank = __popc(same & ((1u << lane) - 1u));
-      const int keep = hit && g == gs && (have + rank) < 50;
-      const unsigned keepm = __ballot_sync(0xffffffffu, keep);
-      const int slot = ncon + __popc(keepm & ((1u << lane) - 1u));
-      if (keep && slot < MD(ncon_max)) {
-        float* cpp = WS(W_CN_POS) + 3 * slot; float* fr = WS(W_CN_FRAME) + 9 * slot;
-        v3copy(cpp, cp); v3copy(fr, nrm); make_frame(fr);
-        WS(W_CN_DIST)[slot] = -depth;
-        WS(W_CN_MU)[slot] = fmaxf(WS(W_SCAL)[0], WS(W_GMU)[g]);
-        WSI(W_CN_BODY)[slot] = m.geom_body[g]; WSI(W_CN_GEOM)[slot] = g; WSI(W_CN_CELL)[slot] = cell;
-      }
-      const int nkeep = __popc(keepm), room = imax(0, MD(ncon_max) - ncon);
-      dropped += imax(0, nkeep - room); ncon += imin(nkeep, room);
+      const unsigned pm = wballot(pass);
+      if (pass) ring[(rhead + rcount + popc32(pm & ((1u << lane) - 1u))) & (RING_SIZE - 1)] = (g << 24) | t;
+      rcount += popc32(pm);
       SYNC();
-      if (lane == 0) task[8 * gs + 5] = have + nkeep;
-      SYNC();
-      hits &= ~same;
+      NOUNROLL while (rcount >= LANES) { mpr_batch(m, ws, rhead, LANES, 1, lane); rhead += LANES; rcount -= LANES; }
     }
-#endif
   }
-  if (lane == 0) { WSI(W_CNT)[CNT_NCON] = ncon; WSI(W_CNT)[CNT_DROPPED] = dropped; }
+  NOUNROLL while (rcount > 0) {
+    int gs2 = 1;
+#ifndef COSIM_HOST_EMU
+    gs2 = rcount <= 4 ? 8 : (rcount <= 8 ? 4 : (rcount <= 16 ? 2 : 1));
+#endif
+    const int n = imin(rcount, LANES / gs2);
+    mpr_batch(m, ws, rhead, n, gs2, lane); rhead += n; rcount -= n;
+  }
   SYNC();
 }
 
-// body of the first geom of a contact: 0 (world) for ground contacts; geom-geom contacts carry -2 - geom1 in W_CN_CELL
-DEV int contact_body1(const ModelDev& m, const float* ws, int c) { const int cell = WSI(W_CN_CELL)[c]; return cell <= -2 ? m.geom_body[-2 - cell] : 0; }
+// body of the first geom of a contact: 0 (world) for ground contacts; geom-geom contacts carry -2 - geom1 in the record's cell slot
+DEV int contact_body1(const ModelDev& m, const float* ws, int c) { const int cell = CRECI(c)[CR_CELL]; return cell <= -2 ? m.geom_body[-2 - cell] : 0; }
 
 // mjc_fixNormal restated (oracle/oracle.hpp fix_normal): for smooth primitives the contact normal is rebuilt from the contact
 // point -- sphere: centre to point; cylinder: radial direction of the wall unless the point sits on / near a cap.  A normal
@@ -1177,13 +1286,7 @@ DEV_NOINLINE void collide_pairs(const ModelDev& m, float* ws, int lane) {
       const unsigned hits = __ballot_sync(0xffffffffu, hit);
       const int nhit = __popc(hits), slot = ncon + __popc(hits & ((1u << lane) - 1u));
 #endif
-      if (hit && slot < MD(ncon_max)) {
-        float* cpp = WS(W_CN_POS) + 3 * slot; float* fr = WS(W_CN_FRAME) + 9 * slot;
-        v3copy(cpp, cp); v3copy(fr, nrm); make_frame(fr);
-        WS(W_CN_DIST)[slot] = -depth;
-        WS(W_CN_MU)[slot] = fmaxf(WS(W_GMU)[g1], WS(W_GMU)[g2]);
-        WSI(W_CN_BODY)[slot] = m.geom_body[g2]; WSI(W_CN_GEOM)[slot] = g2; WSI(W_CN_CELL)[slot] = -2 - g1;
-      }
+      if (hit && slot < MD(ncon_max)) write_contact(m, ws, slot, cp, nrm, -depth, fmaxf(WS(W_GMU)[g1], WS(W_GMU)[g2]), m.geom_body[g2], g2, -2 - g1);
       const int room = imax(0, MD(ncon_max) - ncon);
       dropped += imax(0, nhit - room); ncon += imin(nhit, room);
       SYNC();       // cached axes written above are read by the next chunk's candidate test
@@ -1352,27 +1455,29 @@ DEV_NOINLINE void make_constraint(const ModelDev& m, float* ws, int ncon, int la
   // contacts: 3 x nv frame Jacobian per contact; 4 pyramid edges share D = 1/(2 mu^2 R_first)
   NOUNROLL for (int idx = lane; idx < ncon * nv; idx += LANES) {
     const int c = idx / nv, k = idx - c * nv;
-    const float* fr = WS(W_CN_FRAME) + 9 * c; float off[3], jp[3];
-    v3sub(off, WS(W_CN_POS) + 3 * c, scom);
-    jac_col(m, ws, WSI(W_CN_BODY)[c], k, off, jp);
-    { const int b1 = contact_body1(m, ws, c); if (b1 > 0) { float j1[3]; jac_col(m, ws, b1, k, off, j1); v3sub(jp, jp, j1); } }
-    float* J = WS(W_CN_J) + (size_t)3 * c * nv;
+    float* rec = CREC(c);
+    const float* fr = rec + CR_FRAME; float off[3], jp[3];
+    v3sub(off, rec + CR_POS, scom);
+    jac_col(m, ws, ((const int*)rec)[CR_BODY], k, off, jp);
+    { const int cell = ((const int*)rec)[CR_CELL]; if (cell <= -2) { const int b1 = m.geom_body[-2 - cell]; if (b1 > 0) { float j1[3]; jac_col(m, ws, b1, k, off, j1); v3sub(jp, jp, j1); } } }
+    float* J = rec + CR_J;
     J[k] = v3dot(fr, jp); J[nv + k] = v3dot(fr + 3, jp); J[2 * nv + k] = v3dot(fr + 6, jp);
   }
   SYNC();
   NOUNROLL for (int idx = lane; idx < ncon * 4; idx += LANES) {
     const int c = idx >> 2, e = idx & 3;
-    const float* J = WS(W_CN_J) + (size_t)3 * c * nv; const float* Jt = J + (1 + (e >> 1)) * nv;
-    const float mu = WS(W_CN_MU)[c], sg = (e & 1) ? -mu : mu, dist = WS(W_CN_DIST)[c];
+    float* rec = CREC(c);
+    const float* J = rec + CR_J; const float* Jt = J + (1 + (e >> 1)) * nv;
+    const float mu = rec[CR_MU], sg = (e & 1) ? -mu : mu, dist = rec[CR_DIST];
     float vel = 0.f;
     NOUNROLL for (int k = 0; k < nv; ++k) vel += (J[k] + sg * Jt[k]) * qvel[k];
     float imp = impedance(solimp, dist);
-    WS(W_CN_AREF)[idx] = -B * vel - K * imp * dist;
+    rec[CR_AREF + e] = -B * vel - K * imp * dist;
     if (e == 0) {
-      float tran = WS(W_INVWB)[WSI(W_CN_BODY)[c]];
+      float tran = WS(W_INVWB)[((const int*)rec)[CR_BODY]];
       { const int b1 = contact_body1(m, ws, c); if (b1 > 0) tran += WS(W_INVWB)[b1]; }
       float R = fmaxf(MINVALF, (1.f - imp) * (tran + mu * mu * tran) / imp);
-      WS(W_CN_D)[c] = 1.f / (2.f * mu * mu * R);
+      rec[CR_D] = 1.f / (2.f * mu * mu * R);
     }
   }
   SYNC();
@@ -1404,7 +1509,7 @@ DEV_NOINLINE RowSum eval_rows(const ModelDev& m, const float* ws, int ncon, floa
     const float sg = WS(W_LM_SIGN)[j];
     if (sg != 0.f) { const int k = m.jnt_dofadr[j]; row_acc(s, sg * WS(W_QACC)[k] - WS(W_LM_AREF)[j], use_v ? sg * WS(W_SEARCH)[k] : 0.f, a, WS(W_LM_D)[j], 2, 0.f, 0.f); }
   }
-  NOUNROLL for (int idx = lane; idx < 4 * ncon; idx += LANES) row_acc(s, WS(W_CN_X)[idx], use_v ? WS(W_CN_V)[idx] : 0.f, a, WS(W_CN_D)[idx >> 2], 2, 0.f, 0.f);
+  NOUNROLL for (int idx = lane; idx < 4 * ncon; idx += LANES) { const float* rec = CREC(idx >> 2); const int e = idx & 3; row_acc(s, rec[CR_X + e], use_v ? rec[CR_V + e] : 0.f, a, rec[CR_D], 2, 0.f, 0.f); }
   return s;
 }
 // X = J*q - aref for every row class, given q (length nv).  friction rows' X go to W_TMPW.
@@ -1414,10 +1519,11 @@ DEV_NOINLINE void compute_jaref(const ModelDev& m, float* ws, int ncon, const fl
   FOR_LANE(k, nv) WS(W_TMPW)[k] = q[k] - WS(W_FR_AREF)[k];
   NOUNROLL for (int idx = lane; idx < 4 * ncon; idx += LANES) {
     const int c = idx >> 2, e = idx & 3;
-    const float* J = WS(W_CN_J) + (size_t)3 * c * nv; const float* Jt = J + (1 + (e >> 1)) * nv;
-    const float mu = WS(W_CN_MU)[c], sg = (e & 1) ? -mu : mu;
+    float* rec = CREC(c);
+    const float* J = rec + CR_J; const float* Jt = J + (1 + (e >> 1)) * nv;
+    const float mu = rec[CR_MU], sg = (e & 1) ? -mu : mu;
     float s = 0.f; NOUNROLL for (int k = 0; k < nv; ++k) s += (J[k] + sg * Jt[k]) * q[k];
-    WS(W_CN_X)[idx] = s - WS(W_CN_AREF)[idx];
+    rec[CR_X + e] = s - rec[CR_AREF + e];
   }
   SYNC();
 }
@@ -1426,10 +1532,11 @@ DEV_NOINLINE void compute_jv(const ModelDev& m, float* ws, int ncon, const float
   FOR_LANE(i, neq3) { const float* J = WS(W_EQ_J) + (size_t)i * nv; float s = 0.f; NOUNROLL for (int k = 0; k < nv; ++k) s += J[k] * v[k]; WS(W_EQ_V)[i] = s; }
   NOUNROLL for (int idx = lane; idx < 4 * ncon; idx += LANES) {
     const int c = idx >> 2, e = idx & 3;
-    const float* J = WS(W_CN_J) + (size_t)3 * c * nv; const float* Jt = J + (1 + (e >> 1)) * nv;
-    const float mu = WS(W_CN_MU)[c], sg = (e & 1) ? -mu : mu;
+    float* rec = CREC(c);
+    const float* J = rec + CR_J; const float* Jt = J + (1 + (e >> 1)) * nv;
+    const float mu = rec[CR_MU], sg = (e & 1) ? -mu : mu;
     float s = 0.f; NOUNROLL for (int k = 0; k < nv; ++k) s += (J[k] + sg * Jt[k]) * v[k];
-    WS(W_CN_V)[idx] = s;
+    rec[CR_V + e] = s;
   }
   SYNC();
 }
@@ -1437,16 +1544,17 @@ DEV_NOINLINE void mat_vec(const float* M, const float* x, float* y, int n, int l
   FOR_LANE(i, n) { float s = 0.f; NOUNROLL for (int k = 0; k < n; ++k) s += M[i * n + k] * x[k]; y[i] = s; }
   SYNC();
 }
-// constraint forces from current X; qfrc_constraint -> W_FCON; contact frame forces -> W_CN_F; returns constraint cost
+// constraint forces from current X; qfrc_constraint -> W_FCON; contact frame forces -> the records; returns constraint cost
 DEV_NOINLINE float update_forces(const ModelDev& m, float* ws, int ncon, int lane) {
   const int nv = MD(nv), njnt = MD(njnt), neq = MD(neq);
   float cost = 0.f;
   FOR_LANE(i, 3 * neq) { const float x = WS(W_EQ_X)[i], D = WS(W_EQ_D)[i]; WS(W_EQ_F)[i] = -D * x; cost += 0.5f * D * x * x; }
   NOUNROLL for (int c = lane; c < ncon; c += LANES) {
-    const float D = WS(W_CN_D)[c], mu = WS(W_CN_MU)[c]; float f[4];
+    float* rec = CREC(c);
+    const float D = rec[CR_D], mu = rec[CR_MU]; float f[4];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) { const float x = WS(W_CN_X)[4 * c + e]; f[e] = x < 0.f ? -D * x : 0.f; if (x < 0.f) cost += 0.5f * D * x * x; }
-    WS(W_CN_F)[3 * c] = f[0] + f[1] + f[2] + f[3]; WS(W_CN_F)[3 * c + 1] = mu * (f[0] - f[1]); WS(W_CN_F)[3 * c + 2] = mu * (f[2] - f[3]);
+    for (int e = 0; e < 4; ++e) { const float x = rec[CR_X + e]; f[e] = x < 0.f ? -D * x : 0.f; if (x < 0.f) cost += 0.5f * D * x * x; }
+    rec[CR_F] = f[0] + f[1] + f[2] + f[3]; rec[CR_F + 1] = mu * (f[0] - f[1]); rec[CR_F + 2] = mu * (f[2] - f[3]);
   }
   SYNC();
   FOR_LANE(k, nv) {
@@ -1465,7 +1573,7 @@ DEV_NOINLINE float update_forces(const ModelDev& m, float* ws, int ncon, int lan
       if (x < 0.f) { q += sg * (-Dl * x); cost += 0.5f * Dl * x * x; }
     }
     NOUNROLL for (int c = 0; c < ncon; ++c) {
-      const float* J = WS(W_CN_J) + (size_t)3 * c * nv; const float* F = WS(W_CN_F) + 3 * c;
+      const float* rec = CREC(c); const float* J = rec + CR_J; const float* F = rec + CR_F;
       q += J[k] * F[0] + J[nv + k] * F[1] + J[2 * nv + k] * F[2];
     }
     NOUNROLL for (int i = 0; i < 3 * neq; ++i) q += WS(W_EQ_J)[(size_t)i * nv + k] * WS(W_EQ_F)[i];
@@ -1573,7 +1681,7 @@ DEV uint32_t active_set_signature(const ModelDev& m, const float* ws, int ncon, 
   const int nv = MD(nv), njnt = MD(njnt);
   const float* qacc = WS(W_QACC);
   uint32_t h = 0;
-  NOUNROLL for (int idx = lane; idx < 4 * ncon; idx += LANES) if (WS(W_CN_X)[idx] < 0.f) h ^= (uint32_t)(idx + 1) * 2654435761u;
+  NOUNROLL for (int idx = lane; idx < 4 * ncon; idx += LANES) if (CREC(idx >> 2)[CR_X + (idx & 3)] < 0.f) h ^= (uint32_t)(idx + 1) * 2654435761u;
   FOR_LANE(k, nv) {
     const float D = WS(W_FR_D)[k];
     if (D > 0.f) { const float x = WS(W_TMPW)[k], Rf = WS(W_FLOSS)[k] / D; if (x > -Rf && x < Rf) h ^= (uint32_t)(k + 1001) * 2246822519u; }
@@ -1603,13 +1711,13 @@ DEV_NOINLINE float newton_direction(const ModelDev& m, float* ws, int ncon, int 
     return gn;
   }
   sig = now;
-  // per-contact 3x3 weight of the frame Jacobian (sum over the active pyramid edges), once per contact: W_CN_V is free here
-  float* cw = WS(W_CN_V);
+  // per-contact 3x3 weight of the frame Jacobian (sum over the active pyramid edges), once per contact: the V slots of the record are free here
   NOUNROLL for (int c = lane; c < ncon; c += LANES) {
-    const float* X = WS(W_CN_X) + 4 * c;
+    float* rec = CREC(c);
+    const float* X = rec + CR_X; float* cw = rec + CR_V;
     const float s0 = X[0] < 0.f, s1 = X[1] < 0.f, s2 = X[2] < 0.f, s3 = X[3] < 0.f;
-    const float D = WS(W_CN_D)[c], mu = WS(W_CN_MU)[c];
-    cw[4 * c] = D * (s0 + s1 + s2 + s3); cw[4 * c + 1] = D * mu * (s0 - s1); cw[4 * c + 2] = D * mu * (s2 - s3); cw[4 * c + 3] = D * mu * mu * (s0 + s1);
+    const float D = rec[CR_D], mu = rec[CR_MU];
+    cw[0] = D * (s0 + s1 + s2 + s3); cw[1] = D * mu * (s0 - s1); cw[2] = D * mu * (s2 - s3); cw[3] = D * mu * mu * (s0 + s1);
   }
   SYNC();
   const int npair = (nv * (nv + 1)) >> 1;
@@ -1617,10 +1725,11 @@ DEV_NOINLINE float newton_direction(const ModelDev& m, float* ws, int ncon, int 
     const int t = m.tri[idx], i = t >> 8, j = t & 255;
     float h = M[i * nv + j];
     NOUNROLL for (int c = 0; c < ncon; ++c) {
-      const float gnn = cw[4 * c];
+      const float* rec = CREC(c); const float* cw = rec + CR_V;
+      const float gnn = cw[0];
       if (gnn == 0.f) continue;
-      const float gn1 = cw[4 * c + 1], gn2 = cw[4 * c + 2], g11 = cw[4 * c + 3], mu = WS(W_CN_MU)[c], g22 = mu * mu * gnn - g11;
-      const float* J = WS(W_CN_J) + (size_t)3 * c * nv;
+      const float gn1 = cw[1], gn2 = cw[2], g11 = cw[3], mu = rec[CR_MU], g22 = mu * mu * gnn - g11;
+      const float* J = rec + CR_J;
       const float jn = J[j], j1 = J[nv + j], j2 = J[2 * nv + j];
       h += J[i] * (gnn * jn + gn1 * j1 + gn2 * j2) + J[nv + i] * (gn1 * jn + g11 * j1) + J[2 * nv + i] * (gn2 * jn + g22 * j2);
     }
@@ -1669,13 +1778,13 @@ DEV_NOINLINE int newton_solve(const ModelDev& m, float* ws, int ncon, int has_ro
       const float D = WS(W_FR_D)[k]; if (D > 0.f) absterms += fminf(fabsf(D * WS(W_TMPW)[k]), WS(W_FLOSS)[k]) * fabsf(search[k]);
     }
     FOR_LANE(i, 3 * neq) absterms += fabsf(WS(W_EQ_D)[i] * WS(W_EQ_X)[i] * WS(W_EQ_V)[i]);
-    NOUNROLL for (int idx = lane; idx < 4 * ncon; idx += LANES) absterms += fabsf(WS(W_CN_D)[idx >> 2] * WS(W_CN_X)[idx] * WS(W_CN_V)[idx]);
+    NOUNROLL for (int idx = lane; idx < 4 * ncon; idx += LANES) { const float* rec = CREC(idx >> 2); const int e = idx & 3; absterms += fabsf(rec[CR_D] * rec[CR_X + e] * rec[CR_V + e]); }
     q1 = wsum(q1); q2 = wsum(q2); sn = sqrtf(wsum(sn)); gauss = 0.5f * wsum(gauss); absterms = wsum(absterms);
     const float alpha = linesearch(m, ws, ncon, gauss, q1, q2, sn, absterms, lane);
     if (alpha == 0.f) break;
     FOR_LANE(k, nv) { qacc[k] += alpha * search[k]; Ma[k] += alpha * Mv[k]; }
     FOR_LANE(i, 3 * neq) WS(W_EQ_X)[i] += alpha * WS(W_EQ_V)[i];
-    NOUNROLL for (int idx = lane; idx < 4 * ncon; idx += LANES) WS(W_CN_X)[idx] += alpha * WS(W_CN_V)[idx];
+    NOUNROLL for (int idx = lane; idx < 4 * ncon; idx += LANES) { float* rec = CREC(idx >> 2); const int e = idx & 3; rec[CR_X + e] += alpha * rec[CR_V + e]; }
     SYNC();
     FOR_LANE(k, nv) WS(W_TMPW)[k] = qacc[k] - WS(W_FR_AREF)[k];
     SYNC();
@@ -1850,10 +1959,10 @@ DEV_NOINLINE void cfrc_ext(const ModelDev& m, float* ws, int ncon, int lane) {
   SYNC();
   if (lane == 0) {   // few contacts; sequential keeps the summation order fixed
     NOUNROLL for (int c = 0; c < ncon; ++c) {
-      const float* F = WS(W_CN_F) + 3 * c; float wf[3], arm[3], tq[3];
-      m3tmulv(wf, WS(W_CN_FRAME) + 9 * c, F);
-      v3sub(arm, WS(W_CN_POS) + 3 * c, scom); v3cross(tq, arm, wf);
-      float* o = out + 6 * WSI(W_CN_BODY)[c];
+      const float* rec = CREC(c); const float* F = rec + CR_F; float wf[3], arm[3], tq[3];
+      m3tmulv(wf, rec + CR_FRAME, F);
+      v3sub(arm, rec + CR_POS, scom); v3cross(tq, arm, wf);
+      float* o = out + 6 * ((const int*)rec)[CR_BODY];
       for (int k = 0; k < 3; ++k) { o[k] += tq[k]; o[3 + k] += wf[k]; }
       const int b1 = contact_body1(m, ws, c);
       if (b1 > 0) { float* o1 = out + 6 * b1; for (int k = 0; k < 3; ++k) { o1[k] -= tq[k]; o1[3 + k] -= wf[k]; } }

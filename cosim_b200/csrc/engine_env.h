@@ -245,9 +245,10 @@ DEV_NOINLINE void dump_contacts(const ModelDev& m, const EnvArrays& E, int env, 
   float* out = E.dbg_contacts + (size_t)env * cap * 10;
   FOR_LANE(c, ncon) {
     float* o = out + 10 * c;
-    o[0] = WS(W_CN_DIST)[c];
-    NOUNROLL for (int k = 0; k < 3; ++k) { o[1 + k] = WS(W_CN_POS)[3 * c + k]; o[4 + k] = WS(W_CN_FRAME)[9 * c + k]; }
-    o[7] = (float)WSI(W_CN_GEOM)[c]; o[8] = (float)WSI(W_CN_CELL)[c]; o[9] = WS(W_CN_MU)[c];
+    const float* rec = CREC(c);
+    o[0] = rec[CR_DIST];
+    NOUNROLL for (int k = 0; k < 3; ++k) { o[1 + k] = rec[CR_POS + k]; o[4 + k] = rec[CR_FRAME + k]; }
+    o[7] = (float)((const int*)rec)[CR_GEOM]; o[8] = (float)((const int*)rec)[CR_CELL]; o[9] = rec[CR_MU];
   }
 }
 

@@ -159,6 +159,41 @@ static inline void build_model(const void* blob, size_t nbytes, uint64_t seed, u
       for (int c = 0; c < 3; ++c) { aabb[6 * g + c] = 0.5f * (lo[c] + hi[c]); aabb[6 * g + 3 + c] = 0.5f * (hi[c] - lo[c]) * 1.0001f + 1e-6f; }
     }
     arena.add(m, m.geom_aabb, aabb);
+    // bounding cylinders (geom frame) for the terrain culls: [centre(3), unit axis(3), radius, half length]; radius 0 = none.
+    // Mesh hulls get the smallest of the three axis-aligned cylinders around the box centre when it is clearly smaller
+    // than the box (wheels); cylinder geoms get themselves.
+    std::vector<float> bcyl(8 * gtype.size(), 0.f);
+    for (size_t g = 0; g < gtype.size(); ++g) {
+      float* o = &bcyl[8 * g];
+      if (gtype[g] == 5) { o[5] = 1.f; o[6] = gsize[3 * g] * 1.0001f + 1e-6f; o[7] = gsize[3 * g + 1] * 1.0001f + 1e-6f; continue; }
+      if (gtype[g] != 7 || vnum[g] < 4) continue;
+      const float* c = &aabb[6 * g]; const float* h = c + 3;
+      double bestvol = 0.95 * 8.0 * h[0] * h[1] * h[2]; int best = -1; float bestr = 0.f;
+      for (int a = 0; a < 3; ++a) {
+        const int u = (a + 1) % 3, v = (a + 2) % 3;
+        float r2 = 0.f;
+        for (int i = 0; i < vnum[g]; ++i) { const float du = hv[3 * (size_t)(vadr[g] + i) + u] - c[u], dv = hv[3 * (size_t)(vadr[g] + i) + v] - c[v]; r2 = std::max(r2, du * du + dv * dv); }
+        const double vol = 3.14159265358979 * r2 * 2.0 * h[a];
+        if (vol < bestvol) { bestvol = vol; best = a; bestr = std::sqrt(r2); }
+      }
+      if (best >= 0) { o[0] = c[0]; o[1] = c[1]; o[2] = c[2]; o[3 + best] = 1.f; o[6] = bestr * 1.0001f + 1e-6f; o[7] = h[best]; }
+    }
+    arena.add(m, m.geom_bcyl, bcyl);
+  }
+  { // max height per 8 x 8 block of cells (normalised data, like hfield_data): early-out for geoms above a fine raster
+    std::vector<float> hf = section<float>(blob, "hfield_data");
+    const int nrow = m.dims[CD_hf_nrow], ncol = m.dims[CD_hf_ncol];
+    m.hf_max8 = nullptr; m.hf_mrow = m.hf_mcol = 0;
+    if (m.dims[CD_ground_type] == 1 && nrow > 1 && ncol > 1 && hf.size() >= (size_t)nrow * ncol) {
+      const int mr = ((nrow - 1) >> 3) + 1, mc = ((ncol - 1) >> 3) + 1;
+      std::vector<float> mx((size_t)mr * mc, 0.f);
+      for (int br = 0; br < mr; ++br) for (int bc = 0; bc < mc; ++bc) {
+        float v = 0.f;
+        for (int r = 8 * br; r <= std::min(8 * br + 8, nrow - 1); ++r) for (int c = 8 * bc; c <= std::min(8 * bc + 8, ncol - 1); ++c) v = std::max(v, hf[(size_t)r * ncol + c]);
+        mx[(size_t)br * mc + bc] = v;
+      }
+      m.hf_max8 = push(u, mx); m.hf_mrow = mr; m.hf_mcol = mc;
+    }
   }
   { // Cholesky pair table
     std::vector<int> tri;
@@ -185,64 +220,78 @@ static inline void build_model(const void* blob, size_t nbytes, uint64_t seed, u
   m.seed_lo = (uint32_t)seed; m.seed_hi = (uint32_t)(seed >> 32); m.env_offset = env_offset;
 
   // ---- workspace layout (floats), every field padded to 4 floats
-  const int nq = m.dims[CD_nq], nu = m.dims[CD_nu], ng = m.dims[CD_ngeom], neq = m.dims[CD_neq], nc = m.dims[CD_ncon_max];
+  const int nq = m.dims[CD_nq], nu = m.dims[CD_nu], ng = m.dims[CD_ngeom], neq = m.dims[CD_neq], ncap = m.dims[CD_ncon_max];
   const int nh = m.dims[CD_hm_res_x] * m.dims[CD_hm_res_y];
   const int nraw = m.dims[CD_n_dofpos] + m.dims[CD_n_dofvel] + 9 + nu + nh;
-  int size[W__COUNT];
-  for (int i = 0; i < W__COUNT; ++i) size[i] = 0;
-  size[W_QPOS] = nq; size[W_QVEL] = nv; size[W_CTRL] = nu; size[W_WARM] = nv; size[W_QACC] = nv;
-  size[W_XPOS] = 3 * nb; size[W_XQUAT] = 4 * nb; size[W_XMAT] = 9 * nb; size[W_XIPOS] = 3 * nb;
-  size[W_XANCHOR] = 3 * njnt; size[W_XAXIS] = 3 * njnt; size[W_GXPOS] = 3 * ng; size[W_GXMAT] = 9 * ng; size[W_SCOM] = 4;
-  size[W_CINERT] = 10 * nb; size[W_CRB] = 10 * nb; size[W_CDOF] = 6 * nv; size[W_CDOFDOT] = 6 * nv;
-  size[W_CVEL] = 6 * nb; size[W_CACC] = 6 * nb; size[W_CFRC] = 6 * nb; size[W_BUF] = 6 * nv;
-  size[W_M] = nv * nv; size[W_A] = nv * nv; size[W_INVD] = nv;
-  size[W_FSMOOTH] = size[W_ASMOOTH] = size[W_FCON] = size[W_GRAD] = size[W_SEARCH] = size[W_MV] = size[W_MA] = size[W_TMPV] = size[W_TMPW] = nv;
-  size[W_BMASS] = nb; size[W_INVWD] = nv; size[W_INVWB] = nb; size[W_FLOSS] = nv; size[W_GMU] = ng; size[W_SCAL] = 4;
-  size[W_FR_D] = nv; size[W_FR_AREF] = nv; size[W_LM_SIGN] = njnt; size[W_LM_D] = njnt; size[W_LM_AREF] = njnt;
-  size[W_CN_POS] = 3 * nc; size[W_CN_FRAME] = 9 * nc; size[W_CN_DIST] = nc; size[W_CN_MU] = nc; size[W_CN_BODY] = nc; size[W_CN_GEOM] = nc;
-  size[W_CN_CELL] = nc; size[W_CN_D] = nc; size[W_CN_AREF] = 4 * nc; size[W_CN_J] = 3 * nc * nv; size[W_CN_F] = 3 * nc; size[W_CN_X] = 4 * nc; size[W_CN_V] = 4 * nc;
-  size[W_EQ_J] = 3 * neq * nv; size[W_EQ_D] = size[W_EQ_AREF] = size[W_EQ_X] = size[W_EQ_V] = size[W_EQ_F] = 3 * neq;
-  size[W_SENS] = 12; size[W_RAW] = nraw; size[W_ACT] = nu; size[W_FILT] = 0; size[W_KP] = nu; size[W_KD] = nu; size[W_GTASK] = 8 * ng; size[W_CNT] = 4; size[W_PAXIS] = m.dims[CD_npair] > 0 ? 4 * PAXIS_SLOTS : 0;
-  // Lay the fields out back to back, then overlay fields whose lifetimes never overlap (shared memory per env bounds
-  // how many env-warps an SM holds, and the step is latency-bound, so every KB counts):
-  //   W_CRB    (only inside crb(), phase 1)            over  W_CVEL + W_CACC   (written from com_vel on, phase 3)
-  //   W_BUF    (crb() scratch; host-emulation solves)  over  W_CDOFDOT         (com_vel .. rne_bias, phase 3)
-  //   W_RAW    (observation build, after the sub-steps) over  W_CN_J           (dead after the last solve)
-  //   W_GTASK  (collision task table, phase 2)         over  W_CN_X + W_CN_V   (written by the solver, phase 4)
+  m.cr_stride = (CR_J + 3 * nv) | 1;            // odd record stride: records of neighbouring contacts fall on different shared-memory banks
   auto pad4 = [](int n) { return (n + 3) & ~3; };
-  int o = 0;
-  bool placed[W__COUNT];
-  for (int i = 0; i < W__COUNT; ++i) placed[i] = false;
-  auto place = [&](int f, int at) { m.off[f] = at; placed[f] = true; };
-  { const int n = std::max(pad4(size[W_CRB]), pad4(size[W_CVEL]) + pad4(size[W_CACC]));
-    place(W_CRB, o); place(W_CVEL, o); place(W_CACC, o + pad4(size[W_CVEL])); o += n; }
-  { const int n = std::max(pad4(size[W_BUF]), pad4(size[W_CDOFDOT])); place(W_BUF, o); place(W_CDOFDOT, o); o += n; }
-  { const int n = std::max(pad4(size[W_RAW]), pad4(size[W_CN_J])); place(W_RAW, o); place(W_CN_J, o); o += n; }
-  { const int n = std::max(pad4(size[W_GTASK]), pad4(size[W_CN_X]) + pad4(size[W_CN_V]));
-    place(W_GTASK, o); place(W_CN_X, o); place(W_CN_V, o + pad4(size[W_CN_X])); o += n; }
-  { // composite inertias live from com_pos to rne_bias (phases 1-3); contact forces, gradient, search direction and
-    // M * search exist only from the Newton solve on (phase 4 .. cfrc_ext) and are rewritten before every use
-    const int n = std::max(pad4(size[W_CINERT]), pad4(size[W_CN_F]) + pad4(size[W_GRAD]) + pad4(size[W_SEARCH]) + pad4(size[W_MV]));
-    place(W_CINERT, o); place(W_CN_F, o); place(W_GRAD, o + pad4(size[W_CN_F])); place(W_SEARCH, o + pad4(size[W_CN_F]) + pad4(size[W_GRAD]));
-    place(W_MV, o + pad4(size[W_CN_F]) + pad4(size[W_GRAD]) + pad4(size[W_SEARCH])); o += n; }
-  { // motion axes (cdof) serve the Jacobians and rne_bias (phases 1-3); M * qacc, the friction-row residuals and the
-    // constraint force are Newton-phase vectors (phase 4 .. integrate)
-    const int n = std::max(pad4(size[W_CDOF]), pad4(size[W_MA]) + pad4(size[W_TMPW]) + pad4(size[W_FCON]));
-    place(W_CDOF, o); place(W_MA, o); place(W_TMPW, o + pad4(size[W_MA])); place(W_FCON, o + pad4(size[W_MA]) + pad4(size[W_TMPW])); o += n; }
-  { // world joint anchors / axes are consumed by com_pos (phase 1); friction-loss and limit rows are built in phase 3
-    const int a = pad4(size[W_XANCHOR]) + pad4(size[W_XAXIS]);
-    const int b = pad4(size[W_FR_D]) + pad4(size[W_FR_AREF]) + pad4(size[W_LM_SIGN]) + pad4(size[W_LM_D]) + pad4(size[W_LM_AREF]);
-    place(W_XANCHOR, o); place(W_XAXIS, o + pad4(size[W_XANCHOR]));
-    int q = o; place(W_FR_D, q); q += pad4(size[W_FR_D]); place(W_FR_AREF, q); q += pad4(size[W_FR_AREF]);
-    place(W_LM_SIGN, q); q += pad4(size[W_LM_SIGN]); place(W_LM_D, q); q += pad4(size[W_LM_D]); place(W_LM_AREF, q);
-    o += std::max(a, b); }
-  for (int i = 0; i < W__COUNT; ++i) if (!placed[i]) { m.off[i] = o; o += pad4(size[i]); }
-  m.ws_floats = o;
-  if (!sup_off16.empty()) {       // shared-memory budget as in cosim_create: 224 KB per CTA, at most 20 env-warps
-    const size_t per = (size_t)m.ws_floats * 4, budget = 224 * 1024, head = (sizeof(ModelDev) + 15) / 16 * 16;
-    const size_t a0 = (arena.bytes.size() + 15) & ~(size_t)15, a1 = ((a0 + sup_off16.size() * 2 + 15) & ~(size_t)15);
-    const size_t w0 = std::min<size_t>(20, (budget - head - a0) / per), w1 = std::min<size_t>(20, (budget - head - a1) / per);
-    if (w1 == w0 && w1 >= 1) arena.add(m, m.sup_off16, sup_off16);
+  // Lays the fields out back to back, overlaying fields whose lifetimes never overlap (shared memory per env bounds how many
+  // env-warps an SM holds, and the step is latency-bound, so every KB counts).  K = contact records kept in shared memory.
+  auto layout = [&](int K, int* off) -> int {
+    int size[W__COUNT];
+    for (int i = 0; i < W__COUNT; ++i) size[i] = 0;
+    size[W_QPOS] = nq; size[W_QVEL] = nv; size[W_CTRL] = nu; size[W_WARM] = nv; size[W_QACC] = nv;
+    size[W_XPOS] = 3 * nb; size[W_XQUAT] = 4 * nb; size[W_XMAT] = 9 * nb; size[W_XIPOS] = 3 * nb;
+    size[W_XANCHOR] = 3 * njnt; size[W_XAXIS] = 3 * njnt; size[W_GXPOS] = 3 * ng; size[W_GXMAT] = 9 * ng; size[W_SCOM] = 4;
+    size[W_CINERT] = 10 * nb; size[W_CRB] = 10 * nb; size[W_CDOF] = 6 * nv; size[W_CDOFDOT] = 6 * nv;
+    size[W_CVEL] = 6 * nb; size[W_CACC] = 6 * nb; size[W_CFRC] = 6 * nb; size[W_BUF] = 6 * nv;
+    size[W_M] = nv * nv; size[W_A] = nv * nv; size[W_INVD] = nv;
+    size[W_FSMOOTH] = size[W_ASMOOTH] = size[W_FCON] = size[W_GRAD] = size[W_SEARCH] = size[W_MV] = size[W_MA] = size[W_TMPV] = size[W_TMPW] = nv;
+    size[W_BMASS] = nb; size[W_INVWD] = nv; size[W_INVWB] = nb; size[W_FLOSS] = nv; size[W_GMU] = ng; size[W_SCAL] = 4;
+    size[W_FR_D] = nv; size[W_FR_AREF] = nv; size[W_LM_SIGN] = njnt; size[W_LM_D] = njnt; size[W_LM_AREF] = njnt;
+    size[W_CN_REC] = K * m.cr_stride; size[W_GPTR] = 4; size[W_RING] = RING_SIZE;
+    size[W_EQ_J] = 3 * neq * nv; size[W_EQ_D] = size[W_EQ_AREF] = size[W_EQ_X] = size[W_EQ_V] = size[W_EQ_F] = 3 * neq;
+    size[W_SENS] = 12; size[W_RAW] = nraw; size[W_ACT] = nu; size[W_FILT] = 0; size[W_KP] = nu; size[W_KD] = nu; size[W_GTASK] = 8 * ng; size[W_CNT] = 4; size[W_PAXIS] = m.dims[CD_npair] > 0 ? 4 * PAXIS_SLOTS : 0;
+    int o = 0;
+    bool placed[W__COUNT];
+    for (int i = 0; i < W__COUNT; ++i) placed[i] = false;
+    auto place = [&](int f, int at) { off[f] = at; placed[f] = true; };
+    { // composite-inertia sums (crb(), phase 1) | collision task table (phase 2) | body velocities / accelerations (from com_vel on, phase 3)
+      const int n = std::max(std::max(pad4(size[W_CRB]), pad4(size[W_GTASK])), pad4(size[W_CVEL]) + pad4(size[W_CACC]));
+      place(W_CRB, o); place(W_GTASK, o); place(W_CVEL, o); place(W_CACC, o + pad4(size[W_CVEL])); o += n; }
+    { // crb() scratch (phase 1; the host emulation also uses it inside solves) | collision task ring (phase 2) | cdof_dot (com_vel .. rne_bias, phase 3)
+      const int n = std::max(std::max(pad4(size[W_BUF]), pad4(size[W_RING])), pad4(size[W_CDOFDOT]));
+      place(W_BUF, o); place(W_RING, o); place(W_CDOFDOT, o); o += n; }
+    { // observation staging (after the sub-steps) over the shared-memory contact records (dead after cfrc_ext / the contact dump)
+      const int n = std::max(pad4(size[W_RAW]), pad4(size[W_CN_REC])); place(W_RAW, o); place(W_CN_REC, o); o += n; }
+    { // composite inertias live from com_pos to rne_bias (phases 1-3); gradient, search direction and M * search exist only
+      // from the Newton solve on (phase 4) and are rewritten before every use
+      const int n = std::max(pad4(size[W_CINERT]), pad4(size[W_GRAD]) + pad4(size[W_SEARCH]) + pad4(size[W_MV]));
+      place(W_CINERT, o); place(W_GRAD, o); place(W_SEARCH, o + pad4(size[W_GRAD])); place(W_MV, o + pad4(size[W_GRAD]) + pad4(size[W_SEARCH])); o += n; }
+    { // motion axes (cdof) serve the Jacobians and rne_bias (phases 1-3); M * qacc, the friction-row residuals and the
+      // constraint force are Newton-phase vectors (phase 4 .. integrate)
+      const int n = std::max(pad4(size[W_CDOF]), pad4(size[W_MA]) + pad4(size[W_TMPW]) + pad4(size[W_FCON]));
+      place(W_CDOF, o); place(W_MA, o); place(W_TMPW, o + pad4(size[W_MA])); place(W_FCON, o + pad4(size[W_MA]) + pad4(size[W_TMPW])); o += n; }
+    { // world joint anchors / axes are consumed by com_pos (phase 1); friction-loss and limit rows are built in phase 3
+      const int a = pad4(size[W_XANCHOR]) + pad4(size[W_XAXIS]);
+      const int b = pad4(size[W_FR_D]) + pad4(size[W_FR_AREF]) + pad4(size[W_LM_SIGN]) + pad4(size[W_LM_D]) + pad4(size[W_LM_AREF]);
+      place(W_XANCHOR, o); place(W_XAXIS, o + pad4(size[W_XANCHOR]));
+      int q = o; place(W_FR_D, q); q += pad4(size[W_FR_D]); place(W_FR_AREF, q); q += pad4(size[W_FR_AREF]);
+      place(W_LM_SIGN, q); q += pad4(size[W_LM_SIGN]); place(W_LM_D, q); q += pad4(size[W_LM_D]); place(W_LM_AREF, q);
+      o += std::max(a, b); }
+    for (int i = 0; i < W__COUNT; ++i) if (!placed[i]) { off[i] = o; o += pad4(size[i]); }
+    return o;
+  };
+  // How many contact records stay in shared memory: the largest K (4 .. 24, at most the capacity) that still gives the
+  // largest number of env-warps per SM (<= 20: five warps of 96 registers per SM sub-partition); the rest of an env's
+  // contacts spills into the warp's global-memory slot.  COSIM_CN_K overrides (experiments).
+  {
+    const size_t budget = 224 * 1024;
+    int tmp[80];
+    auto warps = [&](int K, size_t extra) {
+      const size_t head = (sizeof(ModelDev) + 15) / 16 * 16 + ((arena.bytes.size() + extra + 31) & ~(size_t)15) + 64, per = (size_t)layout(K, tmp) * 4;
+      return (int)std::min<size_t>(20, (budget - head) / per); };
+    const int kmin = std::min(4, ncap), kmax = std::min(24, ncap);
+    // 16-bit copy of the support-map bucket offsets in the arena (one dependent L2 round trip less per hull support query)
+    // if that does not cost an env-warp
+    if (!sup_off16.empty() && warps(kmin, sup_off16.size() * 2) == warps(kmin, 0) && warps(kmin, 0) >= 1) arena.add(m, m.sup_off16, sup_off16);
+    int K = kmin; const int best = warps(kmin, 0);
+    for (int k = kmin; k <= kmax; ++k) if (warps(k, 0) == best) K = k;
+    { const char* e = getenv("COSIM_CN_K"); if (e && atoi(e) >= 1) K = std::min(atoi(e), ncap); }
+    m.cn_k = K;
+    m.ws_floats = layout(K, m.off);
+    m.gslot_floats = (unsigned long long)(((size_t)std::max(0, ncap - K) * m.cr_stride + 31) & ~(size_t)31);
+    m.gscratch = nullptr;
   }
   // upload the arena and point the fields at it; CTA-shared area in front of the per-warp workspaces: [ModelDev copy | arena copy]
   if (arena.slots.size() > sizeof(m.slot_field) / sizeof(m.slot_field[0])) throw std::runtime_error("too many model tables for ModelDev::slot_field");

@@ -466,8 +466,15 @@ def build_model(config, ncon_max=None, auto_reset=False):
 
     pair_geom = self_collision_pairs(rb) if eng.get("self_collision", True) else np.zeros((0, 2), np.int32)
 
+    # Contact capacity of one env.  MuJoCo has no per-env cap, only mjMAXCONPAIR = 50 contacts per geom pair: the default
+    # capacity is what the model can generate (50 per geom against a height field, 5 against the plane, 1 per geom-geom
+    # candidate pair), bounded by 1024 records.  The engine keeps the first few records of an env in shared memory and
+    # the rest in a global-memory slot (engine_setup.h), so a large capacity costs memory, not occupancy.
     if ncon_max is None:
-        ncon_max = int(eng.get("ncon_max", 24))
+        ncon_max = eng.get("ncon_max")
+    if ncon_max is None:
+        ncon_max = min(1024, (50 if ground_type == 1 else 5) * ngeom + len(pair_geom))
+    ncon_max = int(ncon_max)
     nefc_max = 3 * neq + nfl_upper + nlimit_max + 4 * ncon_max
 
     dims = np.zeros(64, np.int32)

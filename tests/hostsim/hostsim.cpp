@@ -37,7 +37,7 @@ static inline float fast_ndtri(float pf) {
 
 struct HostSim {
   ModelDev m; EnvArrays E; int N;
-  std::vector<void*> allocs; std::vector<float> ws;
+  std::vector<void*> allocs; std::vector<float> ws, overflow;
   ~HostSim() { for (void* p : allocs) free(p); }
 };
 static void* hs_up(void* ctx, const void* src, size_t bytes) { void* p = malloc(bytes); memcpy(p, src, bytes); ((HostSim*)ctx)->allocs.push_back(p); return p; }
@@ -54,6 +54,8 @@ void* hs_create(const void* blob, uint64_t nbytes, int num_envs, uint64_t seed, 
   setup::alloc_env(h->m, num_envs, h->E, hs_za, h);
   setup::alloc_debug(h->m, num_envs, h->E, hs_za, h);
   h->ws.assign(h->m.ws_floats, 0.f);
+  h->overflow.assign((size_t)h->m.gslot_floats + 4, 0.f);          // contact records beyond the shared-memory tier (the GPU's global slot)
+  *(float**)(h->ws.data() + h->m.off[W_GPTR]) = h->overflow.data();
   for (int e = 0; e < num_envs; ++e) init_env(h->m, h->E, e, h->ws.data(), 0);
   return h;
 }

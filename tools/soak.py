@@ -10,7 +10,7 @@ from cosim_b200.envs import BatchedEnv
 from cosim_b200.policy import MLPPolicy, synthetic_mlp
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 300
 N = int(sys.argv[2]) if len(sys.argv) > 2 else 65536
-cfg = bench.workload_config() if len(sys.argv) < 5 else make_config(sys.argv[3], sys.argv[4], random=RANDOM_FULL, engine={"auto_reset": True, "ncon_max": int(os.environ.get("COSIM_NCON", "24"))})
+cfg = bench.workload_config() if len(sys.argv) < 5 else make_config(sys.argv[3], sys.argv[4], random=RANDOM_FULL, engine=dict({"auto_reset": True}, **({"ncon_max": int(os.environ["COSIM_NCON"])} if "COSIM_NCON" in os.environ else {})))
 env = BatchedEnv(cfg, N, seed=0xC051)
 pol = MLPPolicy(synthetic_mlp(env.state_dim, env.action_dim), "elu")
 env.receive_user_command(torch.rand((N, env.command_dim), device="cuda") * 3 - 1.5)
