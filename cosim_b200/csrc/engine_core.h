@@ -193,7 +193,7 @@ enum WsField {
   W_FSMOOTH, W_ASMOOTH, W_FCON, W_GRAD, W_SEARCH, W_MV, W_MA, W_TMPV, W_TMPW,
   W_BMASS, W_INVWD, W_INVWB, W_FLOSS, W_GMU, W_SCAL,
   W_FR_D, W_FR_AREF, W_LM_SIGN, W_LM_D, W_LM_AREF,
-  W_CN_REC, W_GPTR, W_RING,
+  W_CN_REC, W_GPTR, W_RING, W_BV, W_CSTART, W_BS, W_CN_J,
   W_EQ_J, W_EQ_D, W_EQ_AREF, W_EQ_X, W_EQ_V, W_EQ_F, W_SENS, W_RAW, W_ACT, W_FILT, W_KP, W_KD, W_GTASK, W_CNT, W_PAXIS, W__COUNT   // keep <= 80 (ModelDev::off)
 };
 static_assert(W__COUNT <= 80, "ModelDev::off too small");
@@ -201,15 +201,20 @@ static_assert(W__COUNT <= 80, "ModelDev::off too small");
 #define WSI(f) ((int*)(ws + m.off[f]))
 // record of contact c: shared-memory tier below cn_k, else the warp's global overflow slot (pointer kept in W_GPTR)
 #define CREC(c) cn_rec(m, ws, (c))
+#define CRECS(c) (ws + m.off[W_CN_REC] + (c) * CR_STRIDE)      /* few-contact paths: every record is in the shared-memory tier (cn_k >= FEW_CONTACTS) */
 #define CRECI(c) ((int*)cn_rec(m, ws, (c)))
 // contact record (floats): position, frame (normal, t1, t2 rows), distance, friction, body / geom / cell (ints), the
-// pyramid's shared D, then per edge: reference acceleration, residual X = J a - aref, V = J search; frame force; 3 x nv frame Jacobian
-enum { CR_POS = 0, CR_FRAME = 3, CR_DIST = 12, CR_MU = 13, CR_BODY = 14, CR_GEOM = 15, CR_CELL = 16, CR_D = 17, CR_AREF = 18, CR_X = 22, CR_V = 26, CR_F = 30, CR_J = 33 };
+// pyramid's shared D, then per edge: reference acceleration, residual X = J a - aref, V = J search (also: the Hessian weights
+// of the contact); frame force; world wrench about the subtree COM (torque, force); world 3 x 3 Hessian weight (xx yy zz xy xz yz).
+// There is NO stored contact Jacobian: J v, J^T f and J^T W J are evaluated through the bodies (see "Jacobian-free rows").
+enum { CR_POS = 0, CR_FRAME = 3, CR_DIST = 12, CR_MU = 13, CR_BODY = 14, CR_GEOM = 15, CR_CELL = 16, CR_D = 17, CR_AREF = 18, CR_X = 22, CR_V = 26, CR_F = 30, CR_WF = 33, CR_WW = 39, CR_STRIDE = 45 };
 enum { RING_SIZE = 64 };
 // W_SCAL: [0] ground mu, [1] meaninertia, [2] delay_prob, [3] unused
 // W_CNT (ints, warp-uniform counters kept in shared memory so they need not travel by reference through the out-of-line
 // calls): [0] contacts of the last forward pass, [1] contacts dropped in it, [2] NaN resets, [3] dropped in this control step
-enum { CNT_NCON = 0, CNT_DROPPED = 1, CNT_NAN = 2, CNT_DROPPED_STEP = 3 };
+// [4] ground contacts of the last pass (they come first; geom-geom contacts follow), [5] bit mask of the bodies that carry a contact
+// [6] bit mask of the bodies with ground contacts of their own
+enum { CNT_NCON = 0, CNT_DROPPED = 1, CNT_NAN = 2, CNT_DROPPED_STEP = 3, CNT_NCG = 4, CNT_CBMASK = 5, CNT_CBGMASK = 6 };
 
 // Per-env arrays in HBM: one row per env, rows contiguous (a warp reads its env's row coalesced).
 struct EnvArrays {
@@ -291,9 +296,9 @@ DEV void cross_force(float* r, const float* v, const float* f) {
 }
 
 DEV float* cn_rec(const ModelDev& m, const float* ws, int c) {
-  if (c < m.cn_k) return (float*)ws + m.off[W_CN_REC] + c * m.cr_stride;
+  if (c < m.cn_k) return (float*)ws + m.off[W_CN_REC] + c * CR_STRIDE;
   float* g = *(float* const*)(ws + m.off[W_GPTR]);
-  return g + (size_t)(c - m.cn_k) * m.cr_stride;
+  return g + (size_t)(c - m.cn_k) * CR_STRIDE;
 }
 
 // ------------------------------------------------------------------------------------------ RNG
@@ -837,7 +842,116 @@ template <class V> DEV void pv_expand(const V& p0, V& p1, V& p2, V& p3, const V&
 // MPR (XenoCollide) penetration query, restating libccd ccdMPRPenetration as driven by mjc_ConvexHField / mjc_Convex
 // (oracle/oracle.hpp mpr_core is the readable fp64 version); 0 = hit.  Run by one lane, or by a group of lanes in lock
 // step that share the hull support scans (grp = sub | gsize << 8).
-template <class A> DEV int mpr_lane(const A& P, GQ_PARAMS, const float* gcenter, float* depth, float* dir_out, float* pos) {
+// The control flow is a state machine with ONE Minkowski-support call per trip: the lanes of a warp work on different
+// queries that sit in different stages of the algorithm (first / second vertex, portal discovery, portal refinement,
+// penetration depth), and with a call site per stage every stage's hull scan ran on its own handful of lanes (7 of 32
+// active in support_lane, profiles/r02_w4_by_function_before.txt).  Same steps in the same order with the same arithmetic
+// as the staged version; the result of a hit is computed after the loop, once for all lanes.
+template <class A> DEV int mpr_lane_sm(const A& P, GQ_PARAMS, const float* gcenter, float* depth, float* dir_out, float* pos) {
+  typedef typename A::PV PV;
+  enum { S_P1 = 0, S_P2, S_DISCOVER, S_REFINE, S_PENETRATE, S_DONE, S_TOUCH, S_HIT };
+  const float tol = MO(ccd_tolerance); const int maxit = MD(ccd_iterations);
+  float c1[3]; P.center(c1);
+  PV p0 = P.make_p0(c1, gcenter), p1 = p0, p2 = p0, p3 = p0;
+  if (f_eq(p0.x, 0.f) && f_eq(p0.y, 0.f) && f_eq(p0.z, 0.f)) p0.x += CCD_EPS * 10.f;
+  float dir[3] = {-p0.x, -p0.y, -p0.z}; v3normalize(dir);
+  int state = S_P1, ret = -2, guard = 0, it = 0;
+  NOUNROLL while (state < S_DONE) {
+    // ---- what the stage does before its support query
+    if (state == S_DISCOVER) { if (++guard > 100) { ret = -2; state = S_DONE; } }
+    else if (state == S_REFINE) {
+      if (++guard > 1000) { ret = -2; state = S_DONE; }
+      else {
+        pv_portal_dir(p1, p2, p3, dir);
+        const float d1 = pv_dot(p1, dir[0], dir[1], dir[2]);
+        if (f_is_zero(d1) || d1 > 0.f) state = S_PENETRATE;      // the origin is inside the portal; the depth stage starts from the same direction
+      }
+    } else if (state == S_PENETRATE) pv_portal_dir(p1, p2, p3, dir);
+    if (state >= S_DONE) break;
+    const PV v = P.mink(GQ_ARGS, dir[0], dir[1], dir[2]);
+    const float dot = pv_dot(v, dir[0], dir[1], dir[2]);
+    if (state == S_P1) {
+      p1 = v;
+      if (f_is_zero(dot) || dot < 0.f) { v3copy(dir_out, dir); ret = -1; state = S_DONE; }      // -1: `dir_out` separates the two objects
+      else {
+        { const float a[3] = {p0.x, p0.y, p0.z}, b[3] = {p1.x, p1.y, p1.z}; v3cross(dir, a, b); }
+        if (f_is_zero(v3dot(dir, dir))) state = S_TOUCH;
+        else { v3normalize(dir); state = S_P2; }
+      }
+    } else if (state == S_P2) {
+      p2 = v;
+      if (f_is_zero(dot) || dot < 0.f) { v3copy(dir_out, dir); ret = -1; state = S_DONE; }
+      else {
+        { float va[3] = {p1.x - p0.x, p1.y - p0.y, p1.z - p0.z}, vb[3] = {p2.x - p0.x, p2.y - p0.y, p2.z - p0.z}; v3cross(dir, va, vb); v3normalize(dir); }
+        if (pv_dot(p0, dir[0], dir[1], dir[2]) > 0.f) { const PV t = p1; p1 = p2; p2 = t; dir[0] = -dir[0]; dir[1] = -dir[1]; dir[2] = -dir[2]; }
+        state = S_DISCOVER; guard = 0;
+      }
+    } else if (state == S_DISCOVER) {
+      p3 = v;
+      if (f_is_zero(dot) || dot < 0.f) { v3copy(dir_out, dir); ret = -1; state = S_DONE; }
+      else {
+        int cont = 0; float d2;
+        { const float a[3] = {p1.x, p1.y, p1.z}, b[3] = {p3.x, p3.y, p3.z}; float va[3]; v3cross(va, a, b); d2 = pv_dot(p0, va[0], va[1], va[2]); }
+        if (d2 < 0.f && !f_is_zero(d2)) { p2 = p3; cont = 1; }
+        if (!cont) {
+          const float a[3] = {p3.x, p3.y, p3.z}, b[3] = {p2.x, p2.y, p2.z}; float va[3]; v3cross(va, a, b); d2 = pv_dot(p0, va[0], va[1], va[2]);
+          if (d2 < 0.f && !f_is_zero(d2)) { p1 = p3; cont = 1; }
+        }
+        if (cont) { float va[3] = {p1.x - p0.x, p1.y - p0.y, p1.z - p0.z}, vb[3] = {p2.x - p0.x, p2.y - p0.y, p2.z - p0.z}; v3cross(dir, va, vb); v3normalize(dir); }
+        else { state = S_REFINE; guard = 0; }
+      }
+    } else if (state == S_REFINE) {
+      if (!(f_is_zero(dot) || dot > 0.f)) { v3copy(dir_out, dir); ret = -1; state = S_DONE; }
+      else if (pv_reach_tol(p1, p2, p3, v, dir, tol)) { ret = -2; state = S_DONE; }            // no intersection, but `dir` is not a separating axis
+      else pv_expand(p0, p1, p2, p3, v);
+    } else {        // S_PENETRATE
+      if (pv_reach_tol(p1, p2, p3, v, dir, tol) || it > maxit) state = S_HIT;
+      else { pv_expand(p0, p1, p2, p3, v); ++it; }
+    }
+  }
+  if (state == S_TOUCH) {
+    float v1[3]; P.witness(p1, c1, v1);
+    for (int k = 0; k < 3; ++k) { const float pk = k == 0 ? p1.x : (k == 1 ? p1.y : p1.z); pos[k] = (v1[k] + (v1[k] - pk)) * 0.5f; }
+    if (f_eq(p1.x, 0.f) && f_eq(p1.y, 0.f) && f_eq(p1.z, 0.f)) { *depth = 0.f; dir_out[0] = dir_out[1] = dir_out[2] = 0.f; return 0; }
+    float pv[3] = {p1.x, p1.y, p1.z};
+    *depth = v3norm(pv); v3copy(dir_out, pv); v3normalize(dir_out); return 0;
+  }
+  if (state == S_HIT) {
+    const float a[3] = {p1.x, p1.y, p1.z}, b[3] = {p2.x, p2.y, p2.z}, c[3] = {p3.x, p3.y, p3.z};
+    float wit[3];
+    const float d2 = point_tri_dist2(a, b, c, wit);
+    *depth = sqrtf(d2);
+    if (f_is_zero(*depth)) { dir_out[0] = dir_out[1] = dir_out[2] = 0.f; } else { v3copy(dir_out, wit); v3normalize(dir_out); }
+    // find_pos: barycentric blend of the witness points
+    const float z0[3] = {p0.x, p0.y, p0.z};
+    float bw[4], vec[3];
+    v3cross(vec, a, b); bw[0] = v3dot(vec, c);
+    v3cross(vec, c, b); bw[1] = v3dot(vec, z0);
+    v3cross(vec, z0, a); bw[2] = v3dot(vec, c);
+    v3cross(vec, b, a); bw[3] = v3dot(vec, z0);
+    float sum = bw[0] + bw[1] + bw[2] + bw[3];
+    if (f_is_zero(sum) || sum < 0.f) {
+      bw[0] = 0.f;
+      v3cross(vec, b, c); bw[1] = v3dot(vec, dir);
+      v3cross(vec, c, a); bw[2] = v3dot(vec, dir);
+      v3cross(vec, a, b); bw[3] = v3dot(vec, dir);
+      sum = bw[1] + bw[2] + bw[3];
+    }
+    const float inv = 1.f / sum;
+    float s1[3] = {0.f, 0.f, 0.f}, s2[3] = {0.f, 0.f, 0.f}, v1[3];
+    P.witness(p0, c1, v1); v3addscl(s1, s1, v1, bw[0]); { const float v2[3] = {v1[0] - p0.x, v1[1] - p0.y, v1[2] - p0.z}; v3addscl(s2, s2, v2, bw[0]); }
+    P.witness(p1, c1, v1); v3addscl(s1, s1, v1, bw[1]); { const float v2[3] = {v1[0] - p1.x, v1[1] - p1.y, v1[2] - p1.z}; v3addscl(s2, s2, v2, bw[1]); }
+    P.witness(p2, c1, v1); v3addscl(s1, s1, v1, bw[2]); { const float v2[3] = {v1[0] - p2.x, v1[1] - p2.y, v1[2] - p2.z}; v3addscl(s2, s2, v2, bw[2]); }
+    P.witness(p3, c1, v1); v3addscl(s1, s1, v1, bw[3]); { const float v2[3] = {v1[0] - p3.x, v1[1] - p3.y, v1[2] - p3.z}; v3addscl(s2, s2, v2, bw[3]); }
+    for (int k = 0; k < 3; ++k) pos[k] = (s1[k] * inv + s2[k] * inv) * 0.5f;
+    return 0;
+  }
+  return ret;
+}
+
+// The same query with one support call site per stage: less bookkeeping per trip, used when a few queries run on wide lane
+// groups in lock step (coarse rasters: 2 - 3 prisms per sub-step, 8 lanes each), where stage divergence does not occur.
+template <class A> DEV int mpr_lane_staged(const A& P, GQ_PARAMS, const float* gcenter, float* depth, float* dir_out, float* pos) {
   typedef typename A::PV PV;
   const float tol = MO(ccd_tolerance); const int maxit = MD(ccd_iterations);
   float c1[3]; P.center(c1);
@@ -927,6 +1041,11 @@ template <class A> DEV int mpr_lane(const A& P, GQ_PARAMS, const float* gcenter,
     pv_expand(p0, p1, p2, p3, v4);
     ++it;
   }
+}
+
+
+template <class A> DEV int mpr_lane(const A& P, GQ_PARAMS, const float* gcenter, float* depth, float* dir_out, float* pos) {
+  return (grp >> 8) > 1 ? mpr_lane_staged(P, GQ_ARGS, gcenter, depth, dir_out, pos) : mpr_lane_sm(P, GQ_ARGS, gcenter, depth, dir_out, pos);
 }
 
 // Conservative separation tests between a terrain prism and the BOUNDING shapes of a geom (oriented box from geom_aabb,
@@ -1110,7 +1229,11 @@ DEV_NOINLINE void collide_hfield_all(const ModelDev& m, float* ws, int lane) {
   // ---- stage 2: a lane per prism runs the reference's height test and the bounding-shape culls; the survivors queue up in
   //      a ring (task order), and whenever 32 of them wait one MPR batch runs with a lane per query.  What is left at the
   //      end runs with wider lane groups that share the hull scans (the common case on coarse rasters: a handful of prisms).
+  //      Large sub-grids (fine rasters: thousands of prisms under one hull) are walked by blocks of 8 x 8 cells: of every
+  //      band of 8 rows only the column blocks whose highest vertex reaches the geom's lowest point are enumerated, as
+  //      `segments` of each row; rows and cells keep the reference order.
   int* ring = WSI(W_RING);
+  int* seg = ring + RING_SIZE;              // [0..7] first cell column of a segment, [8..16] prisms of a row before it
   int rhead = 0, rcount = 0;
   NOUNROLL for (int g = 0; g < ng; ++g) {
     const int* tk = task + 8 * g;
@@ -1119,26 +1242,62 @@ DEV_NOINLINE void collide_hfield_all(const ModelDev& m, float* ws, int lane) {
     if (Tg >= (1 << 24)) { if (lane == 0) WSI(W_CNT)[CNT_DROPPED] += 1; continue; }      // sub-grid beyond the task encoding (a geom spanning > 2000 x 2000 cells)
     const float zmin = ((const float*)tk)[6];
     const float ox = dx * (float)cmin - sx, oy = dy * (float)rmin - sy;
-    GeomBound B; make_bound(m, ws, g, ox, oy, B);
+    // the bounding-shape culls pay off on fine rasters (dozens to thousands of prisms under a hull); a handful of prisms goes
+    // straight to the narrow phase after the reference's height test
+    const bool cull = Tg > 16;
+    GeomBound B;
+    if (cull) make_bound(m, ws, g, ox, oy, B);
     const int per_row = 2 * ncols;
-    NOUNROLL for (int t0 = 0; t0 < Tg; t0 += LANES) {
-      if (tk[5] >= 50) break;                 // this geom already has its 50 contacts (mjMAXCONPAIR)
-      const int t = t0 + lane;
-      int pass = 0;
-      if (t < Tg) {
-        const int r = rmin + t / per_row, rem = t % per_row, c = cmin + 1 + (rem >> 1), i = rem & 1;
-        const int ca = c - 1, ra = r + i, cb = i ? c : c - 1, rbb = i ? r : r + 1, cc = c, rc = r + i;
-        float x[3], y[3], z[3];
-        x[0] = dx * (float)(ca - cmin); y[0] = dy * (float)(ra - rmin); z[0] = LDGB(m.hfield_data + (size_t)ra * ncol + ca) * sz;
-        x[1] = dx * (float)(cb - cmin); y[1] = dy * (float)(rbb - rmin); z[1] = LDGB(m.hfield_data + (size_t)rbb * ncol + cb) * sz;
-        x[2] = dx * (float)(cc - cmin); y[2] = dy * (float)(rc - rmin); z[2] = LDGB(m.hfield_data + (size_t)rc * ncol + cc) * sz;
-        pass = !(z[0] < zmin && z[1] < zmin && z[2] < zmin) && !prism_culled(B, x, y, z);
-      }
-      const unsigned pm = wballot(pass);
-      if (pass) ring[(rhead + rcount + popc32(pm & ((1u << lane) - 1u))) & (RING_SIZE - 1)] = (g << 24) | t;
-      rcount += popc32(pm);
+    const int cb0 = cmin >> 3, ncb = ((cmin + ncols - 1) >> 3) - cb0 + 1;
+    const bool blocked = m.hf_max8 != nullptr && Tg > 256 && ncb <= 8;
+    const int band0 = blocked ? (rmin >> 3) : 0, band1 = blocked ? ((rmin + nrows - 1) >> 3) : 0;
+    bool full = false;
+    NOUNROLL for (int band = band0; band <= band1 && !full; ++band) {
+      int ra = rmin, re = rmin + nrows, nseg = 1, row_prisms = per_row;
       SYNC();
-      NOUNROLL while (rcount >= LANES) { mpr_batch(m, ws, rhead, LANES, 1, lane); rhead += LANES; rcount -= LANES; }
+      if (!blocked) { if (lane == 0) { seg[0] = cmin; seg[8] = 0; } }
+      else {
+        ra = imax(rmin, 8 * band); re = imin(rmin + nrows, 8 * band + 8);
+        unsigned live = 0u;
+        NOUNROLL for (int j0 = 0; j0 < ncb; j0 += LANES) {      // one pass on the GPU (ncb <= 8); the single-lane host emulation loops
+          const int j = j0 + lane;
+          const int isl = j < ncb && LDGB(m.hf_max8 + (size_t)band * m.hf_mcol + cb0 + j) * sz >= zmin;
+          live |= wballot(isl) << j0;
+        }
+        if (!live) continue;
+        nseg = 0; row_prisms = 0;
+        NOUNROLL while (live) {
+          const int j = ctz32(live); live &= live - 1u;
+          const int c0 = imax(cmin, 8 * (cb0 + j)), c1 = imin(cmin + ncols, 8 * (cb0 + j) + 8);
+          if (lane == 0) { seg[nseg] = c0; seg[8 + nseg] = row_prisms; }
+          row_prisms += 2 * (c1 - c0); ++nseg;
+        }
+      }
+      SYNC();
+      const int total = (re - ra) * row_prisms;
+      NOUNROLL for (int s0 = 0; s0 < total; s0 += LANES) {
+        if (tk[5] >= 50) { full = true; break; }                 // this geom already has its 50 contacts (mjMAXCONPAIR)
+        const int slot = s0 + lane;
+        int pass = 0, t = 0;
+        if (slot < total) {
+          const int rr = slot / row_prisms, rem = slot - rr * row_prisms, r = ra + rr;
+          int sg = 0;
+          NOUNROLL while (sg + 1 < nseg && seg[8 + sg + 1] <= rem) ++sg;
+          const int rem2 = rem - seg[8 + sg], cellc = seg[sg] + (rem2 >> 1), i = rem2 & 1, c = cellc + 1;
+          t = (r - rmin) * per_row + 2 * (cellc - cmin) + i;
+          const int ca = c - 1, rra = r + i, cb = i ? c : c - 1, rbb = i ? r : r + 1, cc = c, rc = r + i;
+          float x[3], y[3], z[3];
+          x[0] = dx * (float)(ca - cmin); y[0] = dy * (float)(rra - rmin); z[0] = LDGB(m.hfield_data + (size_t)rra * ncol + ca) * sz;
+          x[1] = dx * (float)(cb - cmin); y[1] = dy * (float)(rbb - rmin); z[1] = LDGB(m.hfield_data + (size_t)rbb * ncol + cb) * sz;
+          x[2] = dx * (float)(cc - cmin); y[2] = dy * (float)(rc - rmin); z[2] = LDGB(m.hfield_data + (size_t)rc * ncol + cc) * sz;
+          pass = !(z[0] < zmin && z[1] < zmin && z[2] < zmin) && !(cull && prism_culled(B, x, y, z));
+        }
+        const unsigned pm = wballot(pass);
+        if (pass) ring[(rhead + rcount + popc32(pm & ((1u << lane) - 1u))) & (RING_SIZE - 1)] = (g << 24) | t;
+        rcount += popc32(pm);
+        SYNC();
+        NOUNROLL while (rcount >= LANES) { mpr_batch(m, ws, rhead, LANES, 1, lane); rhead += LANES; rcount -= LANES; }
+      }
     }
   }
   NOUNROLL while (rcount > 0) {
@@ -1397,6 +1556,69 @@ DEV void jac_col(const ModelDev& m, const float* ws, int body, int k, const floa
   } else { jp[0] = jp[1] = jp[2] = 0.f; }
 }
 
+// ------------------------------------------------------------------------------------------ Jacobian-free contact rows
+// The contact Jacobian is never stored (3 x nv floats per contact would push the records of a contact-rich env out of shared
+// memory: w4_p_v2 on the 9.8 mm stairs raster carries 30 - 150 contacts).  Instead
+//   J v      = velocity of the contact point under the generalized velocity v  -> body spatial velocities (body_vel), then
+//              3 dot products per contact (contact_edge_rows);
+//   J^T f    = the contact wrenches summed per body, then projected on the motion axes of the ancestor dofs (update_forces);
+//   J^T W J  = for the dof pair (i, j), j an ancestor of i: sum over the contacts of the subtree of body(i) of
+//              jac_i^T W jac_j with jac_k = cdof_lin[k] + cdof_ang[k] x offset (newton_direction).
+// Ground contacts are generated in geom order and geoms are numbered in body (depth-first) order, so the contacts of a body --
+// and of a whole subtree -- form one contiguous range of the list: W_CSTART[b] = first contact of body b.  Geom-geom contacts
+// (two bodies, appended after the ground contacts) are handled by explicit loops; they are few.
+DEV void point_vel(const float* v6, const float* off, float* vp) { float c[3]; v3cross(c, v6, off); vp[0] = v6[3] + c[0]; vp[1] = v6[4] + c[1]; vp[2] = v6[5] + c[2]; }
+// Up to FEW_CONTACTS contacts (the common case on coarse terrain: one or two wheel contacts) the solver keeps explicit 3 x nv
+// frame Jacobians in shared memory (W_CN_J) -- cheaper than the per-body passes when there is next to nothing to sum; above
+// that the Jacobian-free formulation takes over.  Both evaluate the same rows.
+enum { FEW_CONTACTS = 8 };
+// the four pyramid-edge projections n +- mu t1, n +- mu t2 of the contact-point velocity given the body velocities `bv` [nbody][6]
+DEV void contact_edge_rows(const ModelDev& m, const float* ws, const float* rec, const float* bv, float* r) {
+  float off[3], vp[3]; v3sub(off, rec + CR_POS, WS(W_SCOM));
+  point_vel(bv + 6 * ((const int*)rec)[CR_BODY], off, vp);
+  const int cell = ((const int*)rec)[CR_CELL];
+  if (cell <= -2) { const int b1 = m.geom_body[-2 - cell]; if (b1 > 0) { float v1[3]; point_vel(bv + 6 * b1, off, v1); v3sub(vp, vp, v1); } }
+  const float* fr = rec + CR_FRAME; const float mu = rec[CR_MU];
+  const float vn = v3dot(fr, vp), v1 = mu * v3dot(fr + 3, vp), v2 = mu * v3dot(fr + 6, vp);
+  r[0] = vn + v1; r[1] = vn - v1; r[2] = vn + v2; r[3] = vn - v2;
+}
+// per-body contact ranges, number of ground contacts, mask of the bodies in contact
+DEV_NOINLINE void contact_index(const ModelDev& m, float* ws, int ncon, int lane) {
+  const int nb = MD(nbody);
+  int ng_ = 0; unsigned mask = 0;
+  NOUNROLL for (int c = lane; c < ncon; c += LANES) {
+    const int* rec = CRECI(c); const int cell = rec[CR_CELL];
+    ng_ += cell > -2; mask |= 1u << rec[CR_BODY];
+    if (cell <= -2) mask |= 1u << m.geom_body[-2 - cell];
+  }
+#ifndef COSIM_HOST_EMU
+  ng_ = __reduce_add_sync(0xffffffffu, ng_); mask = __reduce_or_sync(0xffffffffu, mask);
+#endif
+  const int ncg = ng_;
+  int* cs = WSI(W_CSTART);
+  unsigned gm = 0;
+  NOUNROLL for (int b0 = 0; b0 <= nb; b0 += LANES) {
+    const int b = b0 + lane; int n = 0, own = 0;
+    if (b <= nb) { NOUNROLL for (int c = 0; c < ncg; ++c) { const int cb_ = CRECI(c)[CR_BODY]; n += cb_ < b; own |= cb_ == b; } cs[b] = n; }
+    gm |= wballot(own) << b0;
+  }
+  if (lane == 0) { WSI(W_CNT)[CNT_NCG] = ncg; WSI(W_CNT)[CNT_CBMASK] = (int)(mask & ~1u); WSI(W_CNT)[CNT_CBGMASK] = (int)(gm & ~1u); }
+  SYNC();
+}
+// W_BV[b] = spatial velocity (about the subtree COM) of body b under the generalized velocity `vec`, for the bodies in contact
+DEV_NOINLINE void body_vel(const ModelDev& m, float* ws, const float* vec, int lane) {
+  const int nb = MD(nbody); const unsigned cb = (unsigned)WSI(W_CNT)[CNT_CBMASK];
+  float* bv = WS(W_BV); const float* cdof = WS(W_CDOF);
+  NOUNROLL for (int idx = lane; idx < 6 * nb; idx += LANES) {
+    const int b = idx / 6, i = idx - 6 * b;
+    if (!((cb >> b) & 1u)) continue;
+    unsigned mask = (unsigned)m.body_dofmask[b]; float acc = 0.f;
+    NOUNROLL while (mask) { const int k = ctz32(mask); mask &= mask - 1u; acc += cdof[6 * k + i] * vec[k]; }
+    bv[idx] = acc;
+  }
+  SYNC();
+}
+
 DEV_NOINLINE void make_constraint(const ModelDev& m, float* ws, int ncon, int lane) {
   const int nv = MD(nv), njnt = MD(njnt), neq = MD(neq);
   const float solref[2] = {MO(solref0), MO(solref1)};
@@ -1452,33 +1674,52 @@ DEV_NOINLINE void make_constraint(const ModelDev& m, float* ws, int ncon, int la
     }
     WS(W_LM_SIGN)[j] = sign; WS(W_LM_D)[j] = D; WS(W_LM_AREF)[j] = aref;
   }
-  // contacts: 3 x nv frame Jacobian per contact; 4 pyramid edges share D = 1/(2 mu^2 R_first)
-  NOUNROLL for (int idx = lane; idx < ncon * nv; idx += LANES) {
-    const int c = idx / nv, k = idx - c * nv;
-    float* rec = CREC(c);
-    const float* fr = rec + CR_FRAME; float off[3], jp[3];
-    v3sub(off, rec + CR_POS, scom);
-    jac_col(m, ws, ((const int*)rec)[CR_BODY], k, off, jp);
-    { const int cell = ((const int*)rec)[CR_CELL]; if (cell <= -2) { const int b1 = m.geom_body[-2 - cell]; if (b1 > 0) { float j1[3]; jac_col(m, ws, b1, k, off, j1); v3sub(jp, jp, j1); } } }
-    float* J = rec + CR_J;
-    J[k] = v3dot(fr, jp); J[nv + k] = v3dot(fr + 3, jp); J[2 * nv + k] = v3dot(fr + 6, jp);
-  }
-  SYNC();
-  NOUNROLL for (int idx = lane; idx < ncon * 4; idx += LANES) {
-    const int c = idx >> 2, e = idx & 3;
-    float* rec = CREC(c);
-    const float* J = rec + CR_J; const float* Jt = J + (1 + (e >> 1)) * nv;
-    const float mu = rec[CR_MU], sg = (e & 1) ? -mu : mu, dist = rec[CR_DIST];
-    float vel = 0.f;
-    NOUNROLL for (int k = 0; k < nv; ++k) vel += (J[k] + sg * Jt[k]) * qvel[k];
-    float imp = impedance(solimp, dist);
-    rec[CR_AREF + e] = -B * vel - K * imp * dist;
-    if (e == 0) {
-      float tran = WS(W_INVWB)[((const int*)rec)[CR_BODY]];
-      { const int b1 = contact_body1(m, ws, c); if (b1 > 0) tran += WS(W_INVWB)[b1]; }
-      float R = fmaxf(MINVALF, (1.f - imp) * (tran + mu * mu * tran) / imp);
-      rec[CR_D] = 1.f / (2.f * mu * mu * R);
+  // contacts: 4 pyramid edges share D = 1/(2 mu^2 R_first)
+  if (ncon <= FEW_CONTACTS) {        // few contacts: explicit 3 x nv frame Jacobians in W_CN_J
+    NOUNROLL for (int idx = lane; idx < ncon * nv; idx += LANES) {
+      const int c = idx / nv, k = idx - c * nv;
+      const float* rec = CRECS(c);
+      const float* fr = rec + CR_FRAME; float off[3], jp[3];
+      v3sub(off, rec + CR_POS, scom);
+      jac_col(m, ws, ((const int*)rec)[CR_BODY], k, off, jp);
+      { const int cell = ((const int*)rec)[CR_CELL]; if (cell <= -2) { const int b1 = m.geom_body[-2 - cell]; if (b1 > 0) { float j1[3]; jac_col(m, ws, b1, k, off, j1); v3sub(jp, jp, j1); } } }
+      float* J = WS(W_CN_J) + (size_t)3 * c * nv;
+      J[k] = v3dot(fr, jp); J[nv + k] = v3dot(fr + 3, jp); J[2 * nv + k] = v3dot(fr + 6, jp);
     }
+    SYNC();
+    NOUNROLL for (int idx = lane; idx < ncon * 4; idx += LANES) {
+      const int c = idx >> 2, e = idx & 3;
+      float* rec = CRECS(c);
+      const float* J = WS(W_CN_J) + (size_t)3 * c * nv; const float* Jt = J + (1 + (e >> 1)) * nv;
+      const float mu = rec[CR_MU], sg = (e & 1) ? -mu : mu, dist = rec[CR_DIST];
+      float vel = 0.f;
+      NOUNROLL for (int k = 0; k < nv; ++k) vel += (J[k] + sg * Jt[k]) * qvel[k];
+      const float imp = impedance(solimp, dist);
+      rec[CR_AREF + e] = -B * vel - K * imp * dist;
+      if (e == 0) {
+        float tran = WS(W_INVWB)[((const int*)rec)[CR_BODY]];
+        { const int b1 = contact_body1(m, ws, c); if (b1 > 0) tran += WS(W_INVWB)[b1]; }
+        const float R = fmaxf(MINVALF, (1.f - imp) * (tran + mu * mu * tran) / imp);
+        rec[CR_D] = 1.f / (2.f * mu * mu * R);
+      }
+    }
+    SYNC();
+    return;
+  }
+  // many contacts: no Jacobian; the edge velocities come from the body velocities
+  contact_index(m, ws, ncon, lane);
+  const float* cvel = WS(W_CVEL);
+  NOUNROLL for (int c = lane; c < ncon; c += LANES) {
+    float* rec = CREC(c);
+    float r[4]; contact_edge_rows(m, ws, rec, cvel, r);
+    const float mu = rec[CR_MU], dist = rec[CR_DIST];
+    const float imp = impedance(solimp, dist);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) rec[CR_AREF + e] = -B * r[e] - K * imp * dist;
+    float tran = WS(W_INVWB)[((const int*)rec)[CR_BODY]];
+    { const int b1 = contact_body1(m, ws, c); if (b1 > 0) tran += WS(W_INVWB)[b1]; }
+    const float R = fmaxf(MINVALF, (1.f - imp) * (tran + mu * mu * tran) / imp);
+    rec[CR_D] = 1.f / (2.f * mu * mu * R);
   }
   SYNC();
 }
@@ -1509,7 +1750,8 @@ DEV_NOINLINE RowSum eval_rows(const ModelDev& m, const float* ws, int ncon, floa
     const float sg = WS(W_LM_SIGN)[j];
     if (sg != 0.f) { const int k = m.jnt_dofadr[j]; row_acc(s, sg * WS(W_QACC)[k] - WS(W_LM_AREF)[j], use_v ? sg * WS(W_SEARCH)[k] : 0.f, a, WS(W_LM_D)[j], 2, 0.f, 0.f); }
   }
-  NOUNROLL for (int idx = lane; idx < 4 * ncon; idx += LANES) { const float* rec = CREC(idx >> 2); const int e = idx & 3; row_acc(s, rec[CR_X + e], use_v ? rec[CR_V + e] : 0.f, a, rec[CR_D], 2, 0.f, 0.f); }
+  if (ncon <= FEW_CONTACTS) { NOUNROLL for (int idx = lane; idx < 4 * ncon; idx += LANES) { const float* rec = CRECS(idx >> 2); const int e = idx & 3; row_acc(s, rec[CR_X + e], use_v ? rec[CR_V + e] : 0.f, a, rec[CR_D], 2, 0.f, 0.f); } }
+  else NOUNROLL for (int idx = lane; idx < 4 * ncon; idx += LANES) { const float* rec = CREC(idx >> 2); const int e = idx & 3; row_acc(s, rec[CR_X + e], use_v ? rec[CR_V + e] : 0.f, a, rec[CR_D], 2, 0.f, 0.f); }
   return s;
 }
 // X = J*q - aref for every row class, given q (length nv).  friction rows' X go to W_TMPW.
@@ -1517,26 +1759,44 @@ DEV_NOINLINE void compute_jaref(const ModelDev& m, float* ws, int ncon, const fl
   const int nv = MD(nv), neq3 = 3 * MD(neq);
   FOR_LANE(i, neq3) { const float* J = WS(W_EQ_J) + (size_t)i * nv; float s = 0.f; NOUNROLL for (int k = 0; k < nv; ++k) s += J[k] * q[k]; WS(W_EQ_X)[i] = s - WS(W_EQ_AREF)[i]; }
   FOR_LANE(k, nv) WS(W_TMPW)[k] = q[k] - WS(W_FR_AREF)[k];
-  NOUNROLL for (int idx = lane; idx < 4 * ncon; idx += LANES) {
-    const int c = idx >> 2, e = idx & 3;
-    float* rec = CREC(c);
-    const float* J = rec + CR_J; const float* Jt = J + (1 + (e >> 1)) * nv;
-    const float mu = rec[CR_MU], sg = (e & 1) ? -mu : mu;
-    float s = 0.f; NOUNROLL for (int k = 0; k < nv; ++k) s += (J[k] + sg * Jt[k]) * q[k];
-    rec[CR_X + e] = s - rec[CR_AREF + e];
+  if (ncon > FEW_CONTACTS) {
+    body_vel(m, ws, q, lane);
+    NOUNROLL for (int c = lane; c < ncon; c += LANES) {
+      float* rec = CREC(c); float r[4]; contact_edge_rows(m, ws, rec, WS(W_BV), r);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) rec[CR_X + e] = r[e] - rec[CR_AREF + e];
+    }
+  } else {
+    NOUNROLL for (int idx = lane; idx < 4 * ncon; idx += LANES) {
+      const int c = idx >> 2, e = idx & 3;
+      float* rec = CRECS(c);
+      const float* J = WS(W_CN_J) + (size_t)3 * c * nv; const float* Jt = J + (1 + (e >> 1)) * nv;
+      const float mu = rec[CR_MU], sg = (e & 1) ? -mu : mu;
+      float s = 0.f; NOUNROLL for (int k = 0; k < nv; ++k) s += (J[k] + sg * Jt[k]) * q[k];
+      rec[CR_X + e] = s - rec[CR_AREF + e];
+    }
   }
   SYNC();
 }
 DEV_NOINLINE void compute_jv(const ModelDev& m, float* ws, int ncon, const float* v, int lane) {
   const int nv = MD(nv), neq3 = 3 * MD(neq);
   FOR_LANE(i, neq3) { const float* J = WS(W_EQ_J) + (size_t)i * nv; float s = 0.f; NOUNROLL for (int k = 0; k < nv; ++k) s += J[k] * v[k]; WS(W_EQ_V)[i] = s; }
-  NOUNROLL for (int idx = lane; idx < 4 * ncon; idx += LANES) {
-    const int c = idx >> 2, e = idx & 3;
-    float* rec = CREC(c);
-    const float* J = rec + CR_J; const float* Jt = J + (1 + (e >> 1)) * nv;
-    const float mu = rec[CR_MU], sg = (e & 1) ? -mu : mu;
-    float s = 0.f; NOUNROLL for (int k = 0; k < nv; ++k) s += (J[k] + sg * Jt[k]) * v[k];
-    rec[CR_V + e] = s;
+  if (ncon > FEW_CONTACTS) {
+    body_vel(m, ws, v, lane);
+    NOUNROLL for (int c = lane; c < ncon; c += LANES) {
+      float* rec = CREC(c); float r[4]; contact_edge_rows(m, ws, rec, WS(W_BV), r);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) rec[CR_V + e] = r[e];
+    }
+  } else {
+    NOUNROLL for (int idx = lane; idx < 4 * ncon; idx += LANES) {
+      const int c = idx >> 2, e = idx & 3;
+      float* rec = CRECS(c);
+      const float* J = WS(W_CN_J) + (size_t)3 * c * nv; const float* Jt = J + (1 + (e >> 1)) * nv;
+      const float mu = rec[CR_MU], sg = (e & 1) ? -mu : mu;
+      float s = 0.f; NOUNROLL for (int k = 0; k < nv; ++k) s += (J[k] + sg * Jt[k]) * v[k];
+      rec[CR_V + e] = s;
+    }
   }
   SYNC();
 }
@@ -1544,9 +1804,9 @@ DEV_NOINLINE void mat_vec(const float* M, const float* x, float* y, int n, int l
   FOR_LANE(i, n) { float s = 0.f; NOUNROLL for (int k = 0; k < n; ++k) s += M[i * n + k] * x[k]; y[i] = s; }
   SYNC();
 }
-// constraint forces from current X; qfrc_constraint -> W_FCON; contact frame forces -> the records; returns constraint cost
+// constraint forces from current X; qfrc_constraint -> W_FCON; contact frame forces / world wrenches -> the records; returns constraint cost
 DEV_NOINLINE float update_forces(const ModelDev& m, float* ws, int ncon, int lane) {
-  const int nv = MD(nv), njnt = MD(njnt), neq = MD(neq);
+  const int nv = MD(nv), njnt = MD(njnt), neq = MD(neq), nb = MD(nbody);
   float cost = 0.f;
   FOR_LANE(i, 3 * neq) { const float x = WS(W_EQ_X)[i], D = WS(W_EQ_D)[i]; WS(W_EQ_F)[i] = -D * x; cost += 0.5f * D * x * x; }
   NOUNROLL for (int c = lane; c < ncon; c += LANES) {
@@ -1554,9 +1814,32 @@ DEV_NOINLINE float update_forces(const ModelDev& m, float* ws, int ncon, int lan
     const float D = rec[CR_D], mu = rec[CR_MU]; float f[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) { const float x = rec[CR_X + e]; f[e] = x < 0.f ? -D * x : 0.f; if (x < 0.f) cost += 0.5f * D * x * x; }
-    rec[CR_F] = f[0] + f[1] + f[2] + f[3]; rec[CR_F + 1] = mu * (f[0] - f[1]); rec[CR_F + 2] = mu * (f[2] - f[3]);
+    const float F[3] = {f[0] + f[1] + f[2] + f[3], mu * (f[0] - f[1]), mu * (f[2] - f[3])};
+    rec[CR_F] = F[0]; rec[CR_F + 1] = F[1]; rec[CR_F + 2] = F[2];
+    if (ncon > FEW_CONTACTS) {
+      float wf[3], off[3], tq[3];
+      m3tmulv(wf, rec + CR_FRAME, F); v3sub(off, rec + CR_POS, WS(W_SCOM)); v3cross(tq, off, wf);
+      rec[CR_WF] = tq[0]; rec[CR_WF + 1] = tq[1]; rec[CR_WF + 2] = tq[2]; rec[CR_WF + 3] = wf[0]; rec[CR_WF + 4] = wf[1]; rec[CR_WF + 5] = wf[2];
+    }
   }
   SYNC();
+  const unsigned cb = ncon > FEW_CONTACTS ? (unsigned)WSI(W_CNT)[CNT_CBMASK] : 0u;
+  if (cb) {      // wrench per body (fixed summation order: contact order)
+    const int* cs = WSI(W_CSTART); const int ncg = WSI(W_CNT)[CNT_NCG]; float* bf = WS(W_BV);
+    NOUNROLL for (int idx = lane; idx < 6 * nb; idx += LANES) {
+      const int b = idx / 6, i = idx - 6 * b;
+      if (!((cb >> b) & 1u)) continue;
+      float acc = 0.f;
+      NOUNROLL for (int c = cs[b]; c < cs[b + 1]; ++c) acc += CREC(c)[CR_WF + i];
+      NOUNROLL for (int c = ncg; c < ncon; ++c) {
+        const float* rec = CREC(c);
+        if (((const int*)rec)[CR_BODY] == b) acc += rec[CR_WF + i];
+        if (m.geom_body[-2 - ((const int*)rec)[CR_CELL]] == b) acc -= rec[CR_WF + i];
+      }
+      bf[idx] = acc;
+    }
+    SYNC();
+  }
   FOR_LANE(k, nv) {
     float q = 0.f;
     const float D = WS(W_FR_D)[k];
@@ -1572,9 +1855,19 @@ DEV_NOINLINE float update_forces(const ModelDev& m, float* ws, int ncon, int lan
       const float x = sg * WS(W_QACC)[k] - WS(W_LM_AREF)[j], Dl = WS(W_LM_D)[j];
       if (x < 0.f) { q += sg * (-Dl * x); cost += 0.5f * Dl * x * x; }
     }
-    NOUNROLL for (int c = 0; c < ncon; ++c) {
-      const float* rec = CREC(c); const float* J = rec + CR_J; const float* F = rec + CR_F;
-      q += J[k] * F[0] + J[nv + k] * F[1] + J[2 * nv + k] * F[2];
+    if (cb) {      // J^T f: the wrenches of the bodies below dof k, projected on its motion axis
+      const int b0 = m.dof_body[k], b1 = b0 + m.body_subsize[b0];
+      const float* cd = WS(W_CDOF) + 6 * k; const float* bf = WS(W_BV);
+      NOUNROLL for (int b = b0; b < b1; ++b) if ((cb >> b) & 1u) {
+        const float* w = bf + 6 * b;
+        q += cd[0] * w[0] + cd[1] * w[1] + cd[2] * w[2] + cd[3] * w[3] + cd[4] * w[4] + cd[5] * w[5];
+      }
+    }
+    if (!cb) {      // few contacts: J^T f from the explicit Jacobians
+      NOUNROLL for (int c = 0; c < ncon; ++c) {
+        const float* J = WS(W_CN_J) + (size_t)3 * c * nv; const float* F = CRECS(c) + CR_F;
+        q += J[k] * F[0] + J[nv + k] * F[1] + J[2 * nv + k] * F[2];
+      }
     }
     NOUNROLL for (int i = 0; i < 3 * neq; ++i) q += WS(W_EQ_J)[(size_t)i * nv + k] * WS(W_EQ_F)[i];
     WS(W_FCON)[k] = q;
@@ -1711,27 +2004,99 @@ DEV_NOINLINE float newton_direction(const ModelDev& m, float* ws, int ncon, int 
     return gn;
   }
   sig = now;
-  // per-contact 3x3 weight of the frame Jacobian (sum over the active pyramid edges), once per contact: the V slots of the record are free here
+  const int npair = (nv * (nv + 1)) >> 1;
+  const bool few = ncon <= FEW_CONTACTS;
+  const int* cs = WSI(W_CSTART); const int ncg = few ? 0 : WSI(W_CNT)[CNT_NCG];
+  const unsigned cbg = few ? 0u : (unsigned)WSI(W_CNT)[CNT_CBGMASK];
+  const float* scom = WS(W_SCOM); const float* cdof = WS(W_CDOF);
+  float* BS = WS(W_BS);
+  // per-contact 3x3 weight in the contact frame (sum over the active pyramid edges), once per contact.  Few contacts: kept
+  // as (gnn, gn1, gn2, g11) in the V slots of the record (free here).  Many: its world-frame image WW = R^T Wf R (rows of
+  // R = normal, t1, t2); WW[0] < 0 marks a contact without an active edge
   NOUNROLL for (int c = lane; c < ncon; c += LANES) {
     float* rec = CREC(c);
-    const float* X = rec + CR_X; float* cw = rec + CR_V;
+    const float* X = rec + CR_X;
     const float s0 = X[0] < 0.f, s1 = X[1] < 0.f, s2 = X[2] < 0.f, s3 = X[3] < 0.f;
     const float D = rec[CR_D], mu = rec[CR_MU];
-    cw[0] = D * (s0 + s1 + s2 + s3); cw[1] = D * mu * (s0 - s1); cw[2] = D * mu * (s2 - s3); cw[3] = D * mu * mu * (s0 + s1);
+    const float gnn = D * (s0 + s1 + s2 + s3), gn1 = D * mu * (s0 - s1), gn2 = D * mu * (s2 - s3), g11 = D * mu * mu * (s0 + s1), g22 = mu * mu * gnn - g11;
+    if (few) { float* cw = rec + CR_V; cw[0] = gnn; cw[1] = gn1; cw[2] = gn2; cw[3] = g11; continue; }
+    float* W = rec + CR_WW;
+    if (gnn == 0.f) { W[0] = -1.f; continue; }
+    const float* n = rec + CR_FRAME; const float* t1 = n + 3; const float* t2 = n + 6;
+    float a[3], b[3], cc[3];       // Wf R, row by row: a = gnn n + gn1 t1 + gn2 t2, b = gn1 n + g11 t1, cc = gn2 n + g22 t2
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { a[k] = gnn * n[k] + gn1 * t1[k] + gn2 * t2[k]; b[k] = gn1 * n[k] + g11 * t1[k]; cc[k] = gn2 * n[k] + g22 * t2[k]; }
+    W[0] = fmaxf(0.f, n[0] * a[0] + t1[0] * b[0] + t2[0] * cc[0]); W[1] = n[1] * a[1] + t1[1] * b[1] + t2[1] * cc[1]; W[2] = n[2] * a[2] + t1[2] * b[2] + t2[2] * cc[2];
+    W[3] = n[0] * a[1] + t1[0] * b[1] + t2[0] * cc[1]; W[4] = n[0] * a[2] + t1[0] * b[2] + t2[0] * cc[2]; W[5] = n[1] * a[2] + t1[1] * b[2] + t2[1] * cc[2];
   }
   SYNC();
-  const int npair = (nv * (nv + 1)) >> 1;
+  // Many contacts: the ground contacts of one body enter the Hessian only through S_b = sum_c X_c^T WW_c X_c, a symmetric 6 x 6
+  // "contact inertia" about the subtree COM (X_c = [A_c | 1] maps the body's spatial velocity to the velocity of the contact
+  // point, A_c w = w x offset): J^T W J for the dof pair (i, j) is cdof_i^T (sum of S_b over the bodies below dof i) cdof_j.  The
+  // cost of the assembly no longer grows with (contacts x dof pairs): 21 sums per body in contact, then 21 terms per pair and body.
+  if (cbg) {
+    const int nb = MD(nbody);
+    NOUNROLL for (int idx = lane; idx < 21 * nb; idx += LANES) {
+      const int b = idx / 21, e = idx - 21 * b;
+      if (!((cbg >> b) & 1u)) continue;
+      int p = 0; NOUNROLL while (((p + 1) * (p + 2)) >> 1 <= e) ++p;
+      const int q = e - ((p * (p + 1)) >> 1);          // packed lower triangle: e = p (p + 1) / 2 + q, q <= p
+      float acc = 0.f;
+      NOUNROLL for (int c = cs[b]; c < cs[b + 1]; ++c) {
+        const float* rec = CREC(c); const float* W = rec + CR_WW;
+        if (W[0] < 0.f) continue;
+        const float ox_ = rec[CR_POS] - scom[0], oy_ = rec[CR_POS + 1] - scom[1], oz_ = rec[CR_POS + 2] - scom[2];
+        // columns of X: 0..2 = columns of A (w x offset), 3..5 = unit vectors
+        const float xq0 = q == 0 ? 0.f : (q == 1 ? oz_ : (q == 2 ? -oy_ : (q == 3 ? 1.f : 0.f)));
+        const float xq1 = q == 0 ? -oz_ : (q == 1 ? 0.f : (q == 2 ? ox_ : (q == 4 ? 1.f : 0.f)));
+        const float xq2 = q == 0 ? oy_ : (q == 1 ? -ox_ : (q == 2 ? 0.f : (q == 5 ? 1.f : 0.f)));
+        const float xp0 = p == 0 ? 0.f : (p == 1 ? oz_ : (p == 2 ? -oy_ : (p == 3 ? 1.f : 0.f)));
+        const float xp1 = p == 0 ? -oz_ : (p == 1 ? 0.f : (p == 2 ? ox_ : (p == 4 ? 1.f : 0.f)));
+        const float xp2 = p == 0 ? oy_ : (p == 1 ? -ox_ : (p == 2 ? 0.f : (p == 5 ? 1.f : 0.f)));
+        acc += xp0 * (W[0] * xq0 + W[3] * xq1 + W[4] * xq2) + xp1 * (W[3] * xq0 + W[1] * xq1 + W[5] * xq2) + xp2 * (W[4] * xq0 + W[5] * xq1 + W[2] * xq2);
+      }
+      BS[idx] = acc;
+    }
+    SYNC();
+  }
   NOUNROLL for (int idx = lane; idx < npair; idx += LANES) {          // lower triangle only, one (i, j <= i) pair per lane
     const int t = m.tri[idx], i = t >> 8, j = t & 255;
     float h = M[i * nv + j];
-    NOUNROLL for (int c = 0; c < ncon; ++c) {
-      const float* rec = CREC(c); const float* cw = rec + CR_V;
-      const float gnn = cw[0];
-      if (gnn == 0.f) continue;
-      const float gn1 = cw[1], gn2 = cw[2], g11 = cw[3], mu = rec[CR_MU], g22 = mu * mu * gnn - g11;
-      const float* J = rec + CR_J;
-      const float jn = J[j], j1 = J[nv + j], j2 = J[2 * nv + j];
-      h += J[i] * (gnn * jn + gn1 * j1 + gn2 * j2) + J[nv + i] * (gn1 * jn + g11 * j1) + J[2 * nv + i] * (gn2 * jn + g22 * j2);
+    if (few) {
+      NOUNROLL for (int c = 0; c < ncon; ++c) {
+        const float* rec = CRECS(c); const float* cw = rec + CR_V;
+        const float gnn = cw[0];
+        if (gnn == 0.f) continue;
+        const float gn1 = cw[1], gn2 = cw[2], g11 = cw[3], mu = rec[CR_MU], g22 = mu * mu * gnn - g11;
+        const float* J = WS(W_CN_J) + (size_t)3 * c * nv;
+        const float jn = J[j], j1 = J[nv + j], j2 = J[2 * nv + j];
+        h += J[i] * (gnn * jn + gn1 * j1 + gn2 * j2) + J[nv + i] * (gn1 * jn + g11 * j1) + J[2 * nv + i] * (gn2 * jn + g22 * j2);
+      }
+    } else {
+      const int bi = m.dof_body[i];
+      if (cbg && ((m.body_dofmask[bi] >> j) & 1)) {        // j moves body(i): contact inertias of the subtree of body(i)
+        const int bend = bi + m.body_subsize[bi];
+        const float* di = cdof + 6 * i; const float* dj = cdof + 6 * j;
+        NOUNROLL for (int b = bi; b < bend; ++b) if ((cbg >> b) & 1u) {
+          const float* S = BS + 21 * b;
+          float acc = 0.f; int e = 0;
+#pragma unroll
+          for (int p = 0; p < 6; ++p) {
+#pragma unroll
+            for (int q = 0; q <= p; ++q, ++e) acc += S[e] * (p == q ? di[p] * dj[p] : di[p] * dj[q] + di[q] * dj[p]);
+          }
+          h += acc;
+        }
+      }
+      NOUNROLL for (int c = ncg; c < ncon; ++c) {        // geom-geom contacts: J = J(body 2) - J(body 1)
+        const float* rec = CREC(c); const float* W = rec + CR_WW;
+        if (W[0] < 0.f) continue;
+        const int b2 = ((const int*)rec)[CR_BODY], b1 = m.geom_body[-2 - ((const int*)rec)[CR_CELL]];
+        float off[3], ji[3], jj[3], t3[3]; v3sub(off, rec + CR_POS, scom);
+        jac_col(m, ws, b2, i, off, ji); jac_col(m, ws, b1, i, off, t3); v3sub(ji, ji, t3);
+        jac_col(m, ws, b2, j, off, jj); jac_col(m, ws, b1, j, off, t3); v3sub(jj, jj, t3);
+        h += ji[0] * (W[0] * jj[0] + W[3] * jj[1] + W[4] * jj[2]) + ji[1] * (W[3] * jj[0] + W[1] * jj[1] + W[5] * jj[2]) + ji[2] * (W[4] * jj[0] + W[5] * jj[1] + W[2] * jj[2]);
+      }
     }
     NOUNROLL for (int e = 0; e < 3 * neq; ++e) h += WS(W_EQ_D)[e] * WS(W_EQ_J)[(size_t)e * nv + i] * WS(W_EQ_J)[(size_t)e * nv + j];
     if (i == j) {
@@ -1856,12 +2221,10 @@ DEV_NOINLINE int forward(const ModelDev& m, float* ws, int lane, int active = 1,
   PH_MARK(PH_COLLIDE);
   BSYNC_IF(bsync, 1);
   PH_MARK(PH_WAIT_COLLIDE);
-  if (active) {           // ---- phase 3: constraint rows, sensors, smooth forces and acceleration
+  if (active) {           // ---- phase 3: sensors, smooth forces and acceleration, constraint rows
     ncon = WSI(W_CNT)[CNT_NCON];
     com_vel(m, ws, lane);
-    make_constraint(m, ws, ncon, lane);
     sensors(m, ws, lane);
-    PH_MARK(PH_CONSTRAINT);
     // smooth forces: passive damping - bias + actuation (ctrl clamp, gear, actuatorfrcrange clamp)
     rne_bias(m, ws, WS(W_TMPV), lane);
     float* fs = WS(W_FSMOOTH);
@@ -1879,6 +2242,11 @@ DEV_NOINLINE int forward(const ModelDev& m, float* ws, int lane, int active = 1,
     FOR_LANE(k, nv) WS(W_TMPV)[k] = fs[k];
     SYNC();
     chol_solve(A, WS(W_INVD), WS(W_TMPV), WS(W_BUF), WS(W_ASMOOTH), nv, lane);
+    PH_MARK(PH_SMOOTH);
+    // constraint rows last: the few-contact Jacobians (W_CN_J) take the place of the body velocities / accelerations,
+    // which sensors() and rne_bias() have consumed by now
+    make_constraint(m, ws, ncon, lane);
+    PH_MARK(PH_CONSTRAINT);
     // any constraint row?
     rows = (ncon > 0) || (MD(neq) > 0);
     { int r = 0; FOR_LANE(k, nv) r |= (WS(W_FR_D)[k] > 0.f); FOR_LANE(j, njnt) r |= (WS(W_LM_SIGN)[j] != 0.f); rows |= wor(r); }

@@ -62,6 +62,9 @@ static inline void build_model(const void* blob, size_t nbytes, uint64_t seed, u
   for (int i = 0; i < 48; ++i) { m.dims[i] = i < (int)dims.size() ? dims[i] : 0; m.opts[i] = i < (int)opts.size() ? (float)opts[i] : 0.f; }
   const int nb = m.dims[CD_nbody], nv = m.dims[CD_nv], njnt = m.dims[CD_njnt];
   if (nv > 31) throw std::runtime_error("engine supports nv <= 31 (dof masks are 32-bit)");
+  if (nb > 32) throw std::runtime_error("engine supports nbody <= 32 (body masks are 32-bit)");
+  { std::vector<int> gb = section<int>(blob, "geom_body");      // contact ranges per body rely on geoms numbered in body order
+    for (size_t g = 1; g < gb.size(); ++g) if (gb[g] < gb[g - 1]) throw std::runtime_error("geoms must be numbered in body order"); }
 
 #define FSEC(field, name) arena.add(m, m.field, section<float>(blob, name))
 #define ISEC(field, name) arena.add(m, m.field, section<int>(blob, name))
@@ -223,7 +226,7 @@ static inline void build_model(const void* blob, size_t nbytes, uint64_t seed, u
   const int nq = m.dims[CD_nq], nu = m.dims[CD_nu], ng = m.dims[CD_ngeom], neq = m.dims[CD_neq], ncap = m.dims[CD_ncon_max];
   const int nh = m.dims[CD_hm_res_x] * m.dims[CD_hm_res_y];
   const int nraw = m.dims[CD_n_dofpos] + m.dims[CD_n_dofvel] + 9 + nu + nh;
-  m.cr_stride = (CR_J + 3 * nv) | 1;            // odd record stride: records of neighbouring contacts fall on different shared-memory banks
+  m.cr_stride = CR_STRIDE;                      // odd record stride: records of neighbouring contacts fall on different shared-memory banks
   auto pad4 = [](int n) { return (n + 3) & ~3; };
   // Lays the fields out back to back, overlaying fields whose lifetimes never overlap (shared memory per env bounds how many
   // env-warps an SM holds, and the step is latency-bound, so every KB counts).  K = contact records kept in shared memory.
@@ -239,29 +242,29 @@ static inline void build_model(const void* blob, size_t nbytes, uint64_t seed, u
     size[W_FSMOOTH] = size[W_ASMOOTH] = size[W_FCON] = size[W_GRAD] = size[W_SEARCH] = size[W_MV] = size[W_MA] = size[W_TMPV] = size[W_TMPW] = nv;
     size[W_BMASS] = nb; size[W_INVWD] = nv; size[W_INVWB] = nb; size[W_FLOSS] = nv; size[W_GMU] = ng; size[W_SCAL] = 4;
     size[W_FR_D] = nv; size[W_FR_AREF] = nv; size[W_LM_SIGN] = njnt; size[W_LM_D] = njnt; size[W_LM_AREF] = njnt;
-    size[W_CN_REC] = K * m.cr_stride; size[W_GPTR] = 4; size[W_RING] = RING_SIZE;
+    size[W_CN_REC] = K * m.cr_stride; size[W_GPTR] = 4; size[W_RING] = RING_SIZE + 20; size[W_BV] = 6 * nb; size[W_CSTART] = nb + 1; size[W_BS] = 21 * nb; size[W_CN_J] = FEW_CONTACTS * 3 * nv;
     size[W_EQ_J] = 3 * neq * nv; size[W_EQ_D] = size[W_EQ_AREF] = size[W_EQ_X] = size[W_EQ_V] = size[W_EQ_F] = 3 * neq;
-    size[W_SENS] = 12; size[W_RAW] = nraw; size[W_ACT] = nu; size[W_FILT] = 0; size[W_KP] = nu; size[W_KD] = nu; size[W_GTASK] = 8 * ng; size[W_CNT] = 4; size[W_PAXIS] = m.dims[CD_npair] > 0 ? 4 * PAXIS_SLOTS : 0;
+    size[W_SENS] = 12; size[W_RAW] = nraw; size[W_ACT] = nu; size[W_FILT] = 0; size[W_KP] = nu; size[W_KD] = nu; size[W_GTASK] = 8 * ng; size[W_CNT] = 8; size[W_PAXIS] = m.dims[CD_npair] > 0 ? 4 * PAXIS_SLOTS : 0;
     int o = 0;
     bool placed[W__COUNT];
     for (int i = 0; i < W__COUNT; ++i) placed[i] = false;
     auto place = [&](int f, int at) { off[f] = at; placed[f] = true; };
-    { // composite-inertia sums (crb(), phase 1) | collision task table (phase 2) | body velocities / accelerations (from com_vel on, phase 3)
-      const int n = std::max(std::max(pad4(size[W_CRB]), pad4(size[W_GTASK])), pad4(size[W_CVEL]) + pad4(size[W_CACC]));
-      place(W_CRB, o); place(W_GTASK, o); place(W_CVEL, o); place(W_CACC, o + pad4(size[W_CVEL])); o += n; }
+    { // composite-inertia sums (crb(), phase 1) | collision task table (phase 2) | body velocities / accelerations (from com_vel
+      // on, phase 3; cfrc_ext output after the last solve) | per-body contact inertias of the Hessian assembly (phase 4)
+      // | explicit Jacobians of the few-contact solver path (end of phase 3 .. phase 4; never together with the contact inertias)
+      const int n = std::max(std::max(std::max(std::max(pad4(size[W_CRB]), pad4(size[W_GTASK])), pad4(size[W_CVEL]) + pad4(size[W_CACC])), pad4(size[W_BS])), pad4(size[W_CN_J]));
+      place(W_CRB, o); place(W_GTASK, o); place(W_CVEL, o); place(W_CACC, o + pad4(size[W_CVEL])); place(W_BS, o); place(W_CN_J, o); o += n; }
     { // crb() scratch (phase 1; the host emulation also uses it inside solves) | collision task ring (phase 2) | cdof_dot (com_vel .. rne_bias, phase 3)
       const int n = std::max(std::max(pad4(size[W_BUF]), pad4(size[W_RING])), pad4(size[W_CDOFDOT]));
       place(W_BUF, o); place(W_RING, o); place(W_CDOFDOT, o); o += n; }
+    { // body forces of rne_bias (phase 3) | body velocities / wrenches of the Jacobian-free contact rows (phase 4)
+      const int n = std::max(pad4(size[W_CFRC]), pad4(size[W_BV])); place(W_CFRC, o); place(W_BV, o); o += n; }
     { // observation staging (after the sub-steps) over the shared-memory contact records (dead after cfrc_ext / the contact dump)
       const int n = std::max(pad4(size[W_RAW]), pad4(size[W_CN_REC])); place(W_RAW, o); place(W_CN_REC, o); o += n; }
     { // composite inertias live from com_pos to rne_bias (phases 1-3); gradient, search direction and M * search exist only
       // from the Newton solve on (phase 4) and are rewritten before every use
       const int n = std::max(pad4(size[W_CINERT]), pad4(size[W_GRAD]) + pad4(size[W_SEARCH]) + pad4(size[W_MV]));
       place(W_CINERT, o); place(W_GRAD, o); place(W_SEARCH, o + pad4(size[W_GRAD])); place(W_MV, o + pad4(size[W_GRAD]) + pad4(size[W_SEARCH])); o += n; }
-    { // motion axes (cdof) serve the Jacobians and rne_bias (phases 1-3); M * qacc, the friction-row residuals and the
-      // constraint force are Newton-phase vectors (phase 4 .. integrate)
-      const int n = std::max(pad4(size[W_CDOF]), pad4(size[W_MA]) + pad4(size[W_TMPW]) + pad4(size[W_FCON]));
-      place(W_CDOF, o); place(W_MA, o); place(W_TMPW, o + pad4(size[W_MA])); place(W_FCON, o + pad4(size[W_MA]) + pad4(size[W_TMPW])); o += n; }
     { // world joint anchors / axes are consumed by com_pos (phase 1); friction-loss and limit rows are built in phase 3
       const int a = pad4(size[W_XANCHOR]) + pad4(size[W_XAXIS]);
       const int b = pad4(size[W_FR_D]) + pad4(size[W_FR_AREF]) + pad4(size[W_LM_SIGN]) + pad4(size[W_LM_D]) + pad4(size[W_LM_AREF]);
@@ -281,12 +284,17 @@ static inline void build_model(const void* blob, size_t nbytes, uint64_t seed, u
     auto warps = [&](int K, size_t extra) {
       const size_t head = (sizeof(ModelDev) + 15) / 16 * 16 + ((arena.bytes.size() + extra + 31) & ~(size_t)15) + 64, per = (size_t)layout(K, tmp) * 4;
       return (int)std::min<size_t>(20, (budget - head) / per); };
-    const int kmin = std::min(4, ncap), kmax = std::min(24, ncap);
+    const int kmin = std::min(4, ncap), kmax = std::min(64, ncap);
     // 16-bit copy of the support-map bucket offsets in the arena (one dependent L2 round trip less per hull support query)
     // if that does not cost an env-warp
     if (!sup_off16.empty() && warps(kmin, sup_off16.size() * 2) == warps(kmin, 0) && warps(kmin, 0) >= 1) arena.add(m, m.sup_off16, sup_off16);
-    int K = kmin; const int best = warps(kmin, 0);
-    for (int k = kmin; k <= kmax; ++k) if (warps(k, 0) == best) K = k;
+    // Coarse rasters / the plane: a handful of contacts per env, keep every env-warp the SM can hold.  Fine rasters (cells
+    // under 5 cm: a wheel alone touches a dozen prisms) give up env-warps, down to 12 per SM, for records in shared memory.
+    const double cell = m.dims[CD_ground_type] == 1 ? 2.0 * opts[CO_hf_sx] / std::max(1, m.dims[CD_hf_ncol] - 1) : 1.0;
+    const int best = warps(kmin, 0), floor_w = cell < 0.05 ? std::min(best, 12) : best;
+    int K = kmin;
+    for (int k = kmin; k <= kmax; ++k) if (warps(k, 0) >= floor_w) K = k;
+    K = std::max(K, std::min(8, ncap));          // at least 8 records in shared memory, even if that costs an env-warp
     { const char* e = getenv("COSIM_CN_K"); if (e && atoi(e) >= 1) K = std::min(atoi(e), ncap); }
     m.cn_k = K;
     m.ws_floats = layout(K, m.off);

@@ -1,0 +1,5 @@
+python tools/quick_rate.py 65536 20 5 2>&1 | tail -1
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/r2h_pytest.log 2>&1; tail -3 gpurun_out/r2h_pytest.log
+timeout 300 python tools/soak.py 60 16384 w4_p_v2 stairs_up_hard 2>&1 | tail -2
+timeout 300 python tools/soak.py 100 16384 humanoid_p_v0 slope_hard 2>&1 | tail -2
+python tools/phase_profile.py flamingo_p_v3 rocky_hard 16384 10 2>&1 | grep -v histogram
