@@ -244,6 +244,60 @@ class BatchedEnv:
         _as_cpu_tensor(truncated_out_host).copy_(self._trunc, non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
 
+    def step_policy_pipelined(self, policy, user_command_host):
+        """The same loop body with the host transfers OVERLAPPED with the next step: the device state is double-buffered, the
+        device->host copy of step k runs on a copy stream while the policy and k_step of step k + 1 run on the compute stream
+        (the policy only needs the device copy of the state), and the host waits for one event per step instead of
+        draining the stream.  Returns the results of the PREVIOUS call as pinned host tensors (state, terminated,
+        truncated) -- valid until the call after next -- or None on the first call; `flush_pipelined()` completes and
+        returns the last step.  One cudaMemcpyAsync per buffer, as in the synchronous call."""
+        assert self.reset_flag is True, "Call 'reset()' before calling 'step()'."
+        dev, N = self.device, self.num_envs
+        P = getattr(self, "_pipe", None)
+        if P is None:
+            pin = lambda shape, dt: torch.empty(shape, dtype=dt, pin_memory=True)
+            P = self._pipe = {
+                "copy": torch.cuda.Stream(device=dev), "k": 0, "pending": None,
+                "d_state": [self._state, torch.zeros_like(self._state)], "d_term": [self._term, torch.zeros_like(self._term)],
+                "d_trunc": [self._trunc, torch.zeros_like(self._trunc)],
+                "h_state": [pin((N, self.state_dim), torch.float32) for _ in range(2)], "h_term": [pin((N,), torch.uint8) for _ in range(2)],
+                "h_trunc": [pin((N,), torch.uint8) for _ in range(2)],
+                "computed": [torch.cuda.Event() for _ in range(2)], "copied": [torch.cuda.Event() for _ in range(2)],
+                "uc": torch.empty((N, max(1, self.command_dim)), dtype=torch.float32, device=dev), "cur": 0}
+        cs = torch.cuda.current_stream(dev)
+        cur, nxt = P["cur"], 1 - P["cur"]
+        if self.command_dim > 0:
+            P["uc"].copy_(_as_cpu_tensor(user_command_host), non_blocking=True)                 # H2D: this step's inputs
+            self.receive_user_command(P["uc"])
+        action = policy.get_action(P["d_state"][cur])                                           # reads the state of the previous step
+        if P["k"] >= 2:
+            cs.wait_event(P["copied"][nxt])           # the buffer about to be overwritten has reached the host
+        self._state, self._term, self._trunc = P["d_state"][nxt], P["d_term"][nxt], P["d_trunc"][nxt]
+        self.step(action)
+        P["computed"][nxt].record(cs)
+        with torch.cuda.stream(P["copy"]):                                                      # D2H: this step's results, off the compute stream
+            P["copy"].wait_event(P["computed"][nxt])
+            P["h_state"][nxt].copy_(P["d_state"][nxt], non_blocking=True)
+            P["h_term"][nxt].copy_(P["d_term"][nxt], non_blocking=True)
+            P["h_trunc"][nxt].copy_(P["d_trunc"][nxt], non_blocking=True)
+            P["copied"][nxt].record(P["copy"])
+        out = None
+        if P["pending"] is not None:
+            P["copied"][P["pending"]].synchronize()                                              # one event wait per step
+            out = (P["h_state"][P["pending"]], P["h_term"][P["pending"]], P["h_trunc"][P["pending"]])
+        P["pending"], P["cur"], P["k"] = nxt, nxt, P["k"] + 1
+        return out
+
+    def flush_pipelined(self):
+        """Completes the last pipelined step and returns its host results (or None)."""
+        P = getattr(self, "_pipe", None)
+        if P is None or P["pending"] is None:
+            return None
+        P["copied"][P["pending"]].synchronize()
+        out = (P["h_state"][P["pending"]], P["h_term"][P["pending"]], P["h_trunc"][P["pending"]])
+        P["pending"] = None
+        return out
+
     def substep(self):
         """One raw physics sub-step with ctrl = last applied torque (parity aid, see cosim_substep)."""
         self._check(self._L.cosim_substep(self._h, self._stream()), "cosim_substep")

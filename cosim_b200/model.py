@@ -158,13 +158,19 @@ def support_buckets(D, G=SUP_G):
     return (face * G + iu) * G + iv
 
 
-def build_support_map(verts, G=SUP_G, samples=9, checks=20000, seed=0):
+def build_support_map(verts, G=SUP_G, depth=7, checks=20000, seed=0):
     """Per direction bucket, the hull vertices that can be the support point for a direction in that bucket.
 
-    The engine's hull support (`support()` in csrc/engine_core.h) scans only the bucket's candidates instead of
-    all vertices (696 for a wheel).  Candidates = arg-max vertices of a dense direction sample of the bucket
-    (borders included) + their hull neighbours; then verified against brute force on random directions and
-    patched until clean.  Returns (offsets[6*G*G + 1], indices)."""
+    The engine's hull support (`support_lane()` in csrc/engine_core.h) scans only the bucket's candidates instead of all
+    vertices (696 for a wheel).  The set of directions for which a vertex is the support point is a convex cone (its normal
+    cone), and a bucket -- a rectangle on a face of the direction cube -- is the convex cone of its four corner rays: if
+    ONE vertex is the arg-max at all four corners it is the arg-max on the whole rectangle.  Every bucket is therefore
+    subdivided (quad-tree) until the four corners of a cell agree, to a depth of `depth` levels (cells of 1/128 of a
+    bucket, ~0.1 degrees); leaf cells that still disagree contribute their corner arg-max vertices (ties included); a
+    verification pass on random directions patches what is left.  A round-1 version sampled 9 x 9 directions per bucket and missed vertices whose normal
+    cone is a thin sliver between two samples (humanoid foot mesh: a contact of 1 cm depth went undetected); the fp64 oracle's
+    brute-force scan and tests/test_model.py::test_support_map_is_complete pin this construction.
+    Returns (offsets[6*G*G + 1], indices)."""
     from scipy.spatial import ConvexHull
     V = np.asarray(verts, dtype=np.float64)
     n = len(V)
@@ -176,28 +182,57 @@ def build_support_map(verts, G=SUP_G, samples=9, checks=20000, seed=0):
     for tri in hull.simplices:
         for a in tri:
             nbr[a].update(int(b) for b in tri if b != a)
-    cand = [set() for _ in range(nb)]
-    t = np.linspace(0.0, 1.0, samples)
-    for face in range(6):
+    cmat = np.zeros((nb, n), dtype=bool)          # candidate matrix [bucket, vertex]
+
+    def argmax_sets(face, uv):
+        """For direction samples (u, v) on a cube face: arg-max vertex and the mask of (near-)tied vertices."""
         ax, sgn = face // 2, (-1.0 if face % 2 else 1.0)
-        for iu in range(G):
-            for iv in range(G):
-                u = -1.0 + 2.0 * (iu + t) / G
-                v = -1.0 + 2.0 * (iv + t) / G
-                uu, vv = np.meshgrid(u, v, indexing="ij")
-                D = np.zeros((samples * samples, 3))
-                D[:, ax] = sgn
-                D[:, (ax + 1) % 3] = uu.ravel()
-                D[:, (ax + 2) % 3] = vv.ravel()
-                P = D @ V.T
-                mx = P.max(axis=1, keepdims=True)
-                hit = np.unique(np.nonzero(P >= mx - 1e-9 * (1.0 + np.abs(mx)))[1])
-                c = cand[(face * G + iu) * G + iv]
-                for h in hit:
-                    c.add(int(h))
-                    c.update(nbr[int(h)])
+        D = np.zeros((len(uv), 3))
+        D[:, ax] = sgn; D[:, (ax + 1) % 3] = uv[:, 0]; D[:, (ax + 2) % 3] = uv[:, 1]
+        P = D @ V.T
+        mx = P.max(axis=1, keepdims=True)
+        # near-ties count as ties: the engine scans in float32 and breaks ties towards the lowest vertex index, like the oracle's
+        # scan over all vertices -- every vertex that can be the float32 maximum has to be listed (flat mesh faces!)
+        return np.argmax(P, axis=1), P >= mx - 1e-6 * (1.0 + np.abs(mx))
+
+    for face in range(6):
+        # level-0 cells = the buckets of this face; cells: [bucket, u0, v0, size]
+        iu, iv = np.meshgrid(np.arange(G), np.arange(G), indexing="ij")
+        cells = np.stack([((face * G + iu) * G + iv).ravel().astype(np.float64), -1.0 + 2.0 * iu.ravel() / G, -1.0 + 2.0 * iv.ravel() / G,
+                          np.full(G * G, 2.0 / G)], axis=1)
+        for level in range(depth + 1):
+            if not len(cells):
+                break
+            corners = np.concatenate([cells[:, 1:3] + cells[:, 3:4] * np.array(o) for o in ((0, 0), (1, 0), (0, 1), (1, 1))], axis=0)
+            am, tie = argmax_sets(face, corners)
+            am = am.reshape(4, -1); tie = tie.reshape(4, len(cells), n).any(axis=0)
+            agree = (am[0] == am[1]) & (am[0] == am[2]) & (am[0] == am[3])
+            done = agree | (level == depth)
+            kk, vv = np.nonzero(tie[done])
+            cmat[cells[done][kk, 0].astype(np.int64), vv] = True
+            split = cells[~done]
+            if len(split):
+                h = split[:, 3:4] * 0.5
+                cells = np.concatenate([np.concatenate([split[:, 0:1], split[:, 1:2] + ou * h, split[:, 2:3] + ov * h, h], axis=1)
+                                        for ou, ov in ((0, 0), (1, 0), (0, 1), (1, 1))], axis=0)
+            else:
+                cells = split
+    # Gauss-map vertices: the unit normal of every hull triangle is a direction in which its three corners tie, and around it
+    # the normal cones of all the vertices of a (near-)flat face meet in wedges thinner than any cell -- list the corners in
+    # the bucket(s) of the normal and of its close neighbourhood (bucket borders, float32 binning)
+    tn = hull.equations[:, :3]
+    e1 = np.cross(tn, np.array([1.0, 0.0, 0.0])); bad1 = np.linalg.norm(e1, axis=1) < 0.1
+    e1[bad1] = np.cross(tn[bad1], np.array([0.0, 1.0, 0.0]))
+    e1 /= np.linalg.norm(e1, axis=1, keepdims=True)
+    e2 = np.cross(tn, e1)
+    for a, b in ((0, 0), (1, 0), (-1, 0), (0, 1), (0, -1), (1, 1), (1, -1), (-1, 1), (-1, -1)):
+        dirs = (tn + 4e-3 * (a * e1 + b * e2)).astype(np.float32)
+        bk = support_buckets(dirs, G)
+        for c in range(3):
+            cmat[bk, hull.simplices[:, c]] = True
+    cand = [set(np.nonzero(cmat[k])[0].tolist()) for k in range(nb)]
     rng = np.random.default_rng(seed)
-    for _ in range(8):                            # verify + patch
+    for _ in range(8):                            # verify on random directions (float32, as the engine computes the bucket) + patch
         D = rng.standard_normal((checks, 3)).astype(np.float32)
         best = np.argmax(D.astype(np.float64) @ V.T, axis=1)
         bad = 0
@@ -206,6 +241,8 @@ def build_support_map(verts, G=SUP_G, samples=9, checks=20000, seed=0):
                 cand[int(k)].add(int(b)); cand[int(k)].update(nbr[int(b)]); bad += 1
         if bad == 0:
             break
+    # a direction on a bucket border may be binned to either side in float32: a bucket also lists what its 8 neighbours on the
+    # same face list for their border cells -- covered by the closed corner samples above (borders are shared corners)
     off = np.zeros(nb + 1, dtype=np.int32)
     idx = []
     for k in range(nb):
@@ -260,9 +297,25 @@ _SUP_CACHE = {}
 
 
 def _support_map_cached(verts):
+    """Support maps are a function of the hull vertices only: kept in-process and as baked assets
+    (cosim_b200/assets/supmaps/<sha1>.npz, committed for the shipped meshes; rebuilt and stored for new ones)."""
+    import hashlib
     key = verts.tobytes()
     if key not in _SUP_CACHE:
-        _SUP_CACHE[key] = build_support_map(verts)
+        tag = hashlib.sha1(key + f"G{SUP_G}d7t6n".encode()).hexdigest()[:20]
+        path = os.path.join(_ASSETS, "supmaps", tag + ".npz")
+        if os.path.exists(path):
+            z = np.load(path, allow_pickle=False)
+            _SUP_CACHE[key] = (z["off"], z["idx"])
+        else:
+            _SUP_CACHE[key] = build_support_map(verts)
+            try:
+                os.makedirs(os.path.dirname(path), exist_ok=True)
+                tmp = path + f".{os.getpid()}.tmp.npz"
+                np.savez_compressed(tmp, off=_SUP_CACHE[key][0], idx=_SUP_CACHE[key][1])
+                os.replace(tmp, path)
+            except OSError:
+                pass
     return _SUP_CACHE[key]
 
 

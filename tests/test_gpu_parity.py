@@ -12,15 +12,19 @@ pytestmark = pytest.mark.gpu
 from cosim_b200.config import make_config, load_tables, RANDOM_NONE, RANDOM_FULL, RANDOM_DEFAULTS  # noqa: E402
 
 CASES = [("flamingo_p_v3", "rocky_hard"), ("flamingo_light_v1", "flat"), ("w4_p_v2", "stairs_up_hard"), ("humanoid_p_v0", "slope_hard")]
-# stated tolerance through contact, teacher-forced per control step (4 sub-steps), fp32 engine vs fp64 oracle:
-# median over envs of max |qvel error| and the fraction of envs allowed above 1e-2 (contact events are discontinuous:
-# an fp32 round-off can move a touch-down across a sub-step boundary)
+from tests.parity_util import (geometry_gap, compare_contact_lists, hm_ray_margin, decade_histogram, DEPTH_SAME, NORMAL_SAME,  # noqa: E402
+                               BORDERLINE_DEPTH)
+# Stated tolerance through contact (fp32 engine vs fp64 oracle, single sub-steps teacher-forced from the oracle):
+#  * contact lists (geoms, height-field cells, order) identical; a contact found by one side only must be grazing
+#    (|dist| < BORDERLINE_DEPTH = 2e-5 m), sit on a geom at the 50-contact cap, or come from an MPR query on a flat-faced shape
+#    (tied support vertices, tests/parity_util.py); at most 3 % of the lists may differ at all;
+#  * sub-steps on which the fp32 MPR returns the fp64 contact geometry (depth within 2e-6 m, normal within 1e-4): |dqvel| < 3e-3,
+#    median < 2e-4;
+#  * an fp32 MPR that stops on another portal of a finely tessellated hull returns another penetration direction (the fp32
+#    build of the ORACLE shows the same: normals off by 0.1 - 0.9 on w4 / stairs); only such sub-steps may be far off, and the
+#    test prints the error histogram and how many outliers the geometry explains.
+SAME_GEOMETRY_TOL = 3e-3
 CONTACT_MEDIAN_TOL = 2e-4
-CONTACT_OUTLIER_FRAC = 0.10
-# w4 on the 9.8 mm stairs raster: dozens of prism contacts per wheel, contact buffer saturated (contacts are dropped in the
-# same order by oracle and engine).  The fp32 build of the ORACLE itself is off by > 1e-3 in 20 % of such sub-steps
-# (tools: /tmp-style comparison in DESIGN.md section 4), so this case gets a wider outlier allowance.
-CONTACT_OUTLIER_FRAC_CASE = {("w4_p_v2", "stairs_up_hard"): 0.30}
 
 
 def _env(robot, terrain, N, random=RANDOM_NONE, seed=1, hm=False, debug=True, **kw):
@@ -80,32 +84,46 @@ def test_contact_free_window_1e5():
 
 @pytest.mark.parametrize("robot,terrain", CASES)
 def test_contact_parity_teacher_forced(robot, terrain):
-    """Through contact.  (a) single sub-steps (= mj_step) teacher-forced from the oracle: tight; (b) whole control
-    steps (4 sub-steps free-running inside): contact events are discontinuous, so only a looser bound holds."""
+    """Through contact.  (a) single sub-steps (= mj_step) teacher-forced from the oracle: contact lists identical (mismatches
+    only for grazing contacts), velocities tight whenever the contact geometry agrees; (b) whole control steps (4 sub-steps
+    free-running inside): contact events are discontinuous, so only a looser bound holds."""
     N, steps = 64, 8
     env = _env(robot, terrain, N)
     orc = _oracle(env, N)
     orc.reset(); env.reset()
     rng = np.random.default_rng(0)
-    sub_err, step_err, same_count, total = [], [], 0, 0
-    depth_err = []
+    cap = env.model.dim("ncon_max")
+    gtype = env.model.sections["geom_type"]
+    sub_err, step_err, same_geo_err, depth_err = [], [], [], []
+    n_lists = n_same_lists = n_far = n_far_explained = 0
+    worst_unmatched = 0.0
 
     def sync():
         for k in ("qpos", "qvel", "qacc_warmstart", "torque"):
             env.set(k, orc.get(k))
 
-    def check_contacts(err):
-        nonlocal same_count, total
-        nc_o, nc_g = orc.get("ncon")[:, 0].astype(int), env.get("counters")[:, 7].cpu().numpy()
-        same = nc_o == nc_g
-        same_count += int(same.sum()); total += N
-        cg_all = env.get("contacts").cpu().numpy()
-        for e in np.nonzero(same & (err < 1e-3))[0][:16]:     # same geoms and height-field cells, in the same order
-            co = orc.contacts(int(e)); cg = cg_all[e].reshape(-1, 10)[:len(co)]
-            if len(co):
-                assert (co[:, 7].astype(int) == cg[:, 7].astype(int)).all(), "contact geoms differ"
-                assert (co[:, 8].astype(int) == cg[:, 8].astype(int)).all(), "height-field cells differ"
-                depth_err.append(np.abs(cg[:, 0] - co[:, 0]))              # penetration depth (MPR converges to ccd_tolerance 1e-6 in fp32 vs fp64)
+    def check_contacts(err, classify):
+        nonlocal n_lists, n_same_lists, n_far, n_far_explained, worst_unmatched
+        assert (orc.get("ncon_dropped") == 0).all() and float(env.get("stats")[:, 13].sum()) == 0.0, "a contact was dropped"
+        cg_all = env.get("contacts").cpu().numpy().reshape(N, cap, 10)
+        ncg = env.get("counters")[:, 7].cpu().numpy()
+        for e in range(N):
+            co = orc.contacts(e, cap); cg = cg_all[e, :ncg[e]]
+            same, unmatched = compare_contact_lists(co, cg, gtype)
+            n_lists += 1; n_same_lists += int(same)
+            worst_unmatched = max(worst_unmatched, unmatched)
+            if not classify:
+                continue
+            if same:
+                dd, dn = geometry_gap(co, cg)
+                if len(co):
+                    depth_err.append(np.abs(cg[:, 0] - co[:, 0]))
+                if dd < DEPTH_SAME and dn < NORMAL_SAME:
+                    same_geo_err.append(err[e])
+                if err[e] > 1e-2:
+                    n_far += 1; n_far_explained += int(dd > DEPTH_SAME or dn > NORMAL_SAME)
+            elif err[e] > 1e-2:
+                n_far += 1; n_far_explained += 1          # a grazing contact on one side only
     for i in range(steps):
         a = rng.uniform(-1, 1, (N, env.action_dim))
         sync()
@@ -114,22 +132,25 @@ def test_contact_parity_teacher_forced(robot, terrain):
         assert np.isfinite(s_g.cpu().numpy()).all()
         err = np.abs(orc.get("qvel") - env.get("qvel").cpu().numpy()).max(axis=1)
         step_err.append(err)
-        check_contacts(err)
+        check_contacts(err, False)
         for _ in range(2):
             sync()
             orc.substep(); env.substep()
             err = np.abs(orc.get("qvel") - env.get("qvel").cpu().numpy()).max(axis=1)
             sub_err.append(err)
-            check_contacts(err)
-    sub_err, step_err = np.concatenate(sub_err), np.concatenate(step_err)
-    if depth_err:
-        depth_err = np.concatenate(depth_err)
-        assert np.median(depth_err) < 2e-6 and (depth_err > 2e-5).mean() < 0.05 and depth_err.max() < 2e-2, \
-            f"contact depth: median {np.median(depth_err):.1e}, {(depth_err > 2e-5).mean():.1%} above 2e-5, max {depth_err.max():.1e}"
-    assert same_count / total >= 0.97, f"contact counts agree in only {same_count}/{total} cases"
+            check_contacts(err, True)
+    sub_err, step_err, same_geo_err = np.concatenate(sub_err), np.concatenate(step_err), np.array(same_geo_err)
+    depth_err = np.concatenate(depth_err) if depth_err else np.zeros(1)
+    print(f"\n{robot}/{terrain}: sub-step |dqvel| histogram (decades 1e-7..1e0) {decade_histogram(sub_err)}; contact lists identical "
+          f"{n_same_lists}/{n_lists}, worst one-sided contact {worst_unmatched:.1e} m; same-geometry sub-steps {len(same_geo_err)}/{len(sub_err)} "
+          f"worst {same_geo_err.max() if len(same_geo_err) else 0:.1e}; far off {n_far}, explained by MPR geometry {n_far_explained}; "
+          f"depth error histogram {decade_histogram(depth_err)}")
+    assert worst_unmatched < BORDERLINE_DEPTH, f"a contact of depth {worst_unmatched:.1e} m exists on one side only"
+    assert n_same_lists >= 0.97 * n_lists, f"contact lists identical in only {n_same_lists}/{n_lists} cases"
+    assert np.median(depth_err) < 2e-6 and (depth_err > 2e-5).mean() < 0.05 and depth_err.max() < 2e-2
+    assert len(same_geo_err) >= 0.3 * len(sub_err) and same_geo_err.max() < SAME_GEOMETRY_TOL
+    assert n_far == n_far_explained, "a sub-step is far off although the contact geometry agrees"
     assert np.median(sub_err) < CONTACT_MEDIAN_TOL, f"median per-sub-step qvel error through contact {np.median(sub_err):.2e}"
-    frac = CONTACT_OUTLIER_FRAC_CASE.get((robot, terrain), CONTACT_OUTLIER_FRAC)
-    assert (sub_err > 1e-2).mean() <= frac, f"{(sub_err > 1e-2).mean():.1%} of sub-steps off by > 1e-2"
     assert np.median(step_err) < 50 * CONTACT_MEDIAN_TOL, f"median per-control-step qvel error {np.median(step_err):.2e}"
     env.close()
 
@@ -221,6 +242,19 @@ def test_randomization_parameters():
     env.close()
 
 
+def _assert_hm_cells(model, qpos, cells_o, cells_g, qpos_engine=None):
+    """Height-field cell / triangle indices of the height-map rays: identical, except for rays that land within fp32 resolution
+    of a cell edge or of the cell diagonal (where the index flips): every mismatch is checked to be such a ray."""
+    bad = np.argwhere(cells_o != cells_g)
+    for e, r in bad:
+        margin = hm_ray_margin(model, qpos[e], r)
+        tol = 2e-5 + 5e-7 * float(np.abs(qpos[e, :2]).max())       # fp32 resolution of the ray's world coordinates
+        if qpos_engine is not None:                                  # after a free-running step the two sides cast from slightly different poses
+            tol += 2.0 * float(np.abs(qpos_engine[e, :7] - qpos[e, :7]).max())
+        assert margin < tol, f"height-map ray {r} of env {e}: cells {cells_o[e, r]} vs {cells_g[e, r]}, but the ray is {margin:.2e} m from the nearest cell boundary"
+    return len(bad)
+
+
 def test_height_map_cells_and_values():
     N = 32
     env = _env("flamingo_p_v3", "rocky_hard", N, hm=True)
@@ -232,9 +266,9 @@ def test_height_map_cells_and_values():
         for k in ("qpos", "qvel", "qacc_warmstart"):
             env.set(k, orc.get(k))
         s_o, _, _ = orc.step(a); s_g, _, _, _ = env.step(a)
+        q_before = orc.get("qpos")          # the rays are cast from the state after the step
         cells_o, cells_g = orc.get("hm_cell").astype(int), env.get("hm_cell").cpu().numpy()
-        agree = (cells_o == cells_g).mean()
-        assert agree >= 0.995, f"height-map cells agree on {agree:.4f} of the rays"      # rays landing exactly on a cell edge may flip in fp32
+        _assert_hm_cells(env.model, q_before, cells_o, cells_g, env.get("qpos").cpu().numpy().astype(np.float64))
         hm_o, hm_g = orc.get("heightmap"), env.get("heightmap").cpu().numpy()
         ok = cells_o == cells_g
         np.testing.assert_allclose(hm_g[ok], hm_o[ok], atol=2e-5)
@@ -255,6 +289,7 @@ def test_baseline_config_4096_envs_with_height_map():
     q[:, 0] = rng.uniform(-100, 100, N); q[:, 1] = rng.uniform(-100, 100, N); q[:, 2] += 0.25
     orc.set("qpos", q); env.set("qpos", q)
     same, cells_ok, errs = [], [], []
+    cap, nflip, worst_unmatched = env.model.dim("ncon_max"), 0, 0.0
     for i in range(6):
         a = rng.uniform(-1, 1, (N, env.action_dim))
         for k in ("qpos", "qvel", "qacc_warmstart"):
@@ -264,10 +299,19 @@ def test_baseline_config_4096_envs_with_height_map():
         assert np.isfinite(s_g).all()
         nco, ncg = orc.get("ncon")[:, 0].astype(int), env.get("counters")[:, 7].cpu().numpy()
         same.append((nco == ncg).mean())
-        cells_ok.append((orc.get("hm_cell").astype(int) == env.get("hm_cell").cpu().numpy()).mean())
+        cells_o, cells_g = orc.get("hm_cell").astype(int), env.get("hm_cell").cpu().numpy()
+        nflip += _assert_hm_cells(env.model, orc.get("qpos"), cells_o, cells_g, env.get("qpos").cpu().numpy().astype(np.float64))
+        cells_ok.append((cells_o == cells_g).mean())
+        cg_all = env.get("contacts").cpu().numpy().reshape(N, cap, 10)
+        for e in np.nonzero(nco != ncg)[0]:          # a differing contact count must come from a grazing contact
+            _, unmatched = compare_contact_lists(orc.contacts(int(e), cap), cg_all[e, :ncg[e]])
+            worst_unmatched = max(worst_unmatched, unmatched)
         errs.append(np.abs(s_g[:, :88] - s_o[:, :88]).max(axis=1))
         assert (t_g.cpu().numpy() == t_o).mean() > 0.995
     errs = np.concatenate(errs)
+    print(f"\ncontact counts agree in {min(same):.4f} of the envs (worst one-sided contact {worst_unmatched:.1e} m); height-map cells agree on {min(cells_ok):.5f} of the rays, {nflip} flips, all on cell boundaries")
+    # whole control steps (the last 3 of the 4 sub-steps run free): a one-sided contact may be as deep as the drift of the state
+    assert worst_unmatched < 1e-3, f"a contact of depth {worst_unmatched:.1e} m exists on one side only"
     assert min(same) >= 0.97, f"contact counts agree in {min(same):.3f} of the envs"
     assert min(cells_ok) >= 0.995, f"height-map cells agree on {min(cells_ok):.4f} of the rays"
     assert np.median(errs) < 2e-3 and (errs > 5e-2).mean() < 0.05, f"state error median {np.median(errs):.1e}, {(errs > 5e-2).mean():.1%} above 5e-2"
@@ -280,6 +324,7 @@ def test_cross_terrain_sweep():
     terrains = ["flat", "rocky_easy", "rocky_hard", "slope_easy", "slope_hard", "stairs_up_easy", "stairs_up_normal", "stairs_up_hard"]
     N = 16
     rng = np.random.default_rng(23)
+    report = []
     for robot in ("flamingo_light_v1", "flamingo_p_v3", "w4_p_v2", "humanoid_p_v0"):
         for terrain in terrains:
             env = _env(robot, terrain, N, random=RANDOM_FULL, seed=4, debug=False)
@@ -292,8 +337,10 @@ def test_cross_terrain_sweep():
             assert np.isfinite(s_g).all(), (robot, terrain)
             same = (orc.get("ncon")[:, 0].astype(int) == env.get("counters")[:, 7].cpu().numpy()).mean()
             err = np.abs(s_g - s_o).max(axis=1)
-            assert same >= 0.75 and np.median(err) < 5e-2, f"{robot} on {terrain}: contact counts agree in {same:.2f} of the envs, median state error {np.median(err):.1e}"
+            report.append(f"{robot:18s} {terrain:17s} same contact count {same:.2f}  median state error {np.median(err):.1e}")
+            assert same >= 0.85 and np.median(err) < 5e-3, f"{robot} on {terrain}: contact counts agree in {same:.2f} of the envs, median state error {np.median(err):.1e}"
             env.close()
+    print("\n" + "\n".join(report))
 
 
 def test_sensor_noise_statistics():
@@ -460,7 +507,8 @@ def test_full_size_properties():
     assert torch.equal(outs[0], outs[1])
 
 
-@pytest.mark.parametrize("name", ["flamingo_p_v3__rocky_hard__hm", "flamingo_light_v1__flat__freq", "humanoid_p_v0__slope_hard__poscmd", "flamingo_p_v3__rocky_hard__push"])
+@pytest.mark.parametrize("name", ["flamingo_p_v3__rocky_hard__hm", "flamingo_light_v1__flat__freq", "humanoid_p_v0__slope_hard__poscmd", "flamingo_p_v3__rocky_hard__push",
+                                  "flamingo_p_v3__flat__short", "w4_p_v2__stairs_up_hard"])
 def test_engine_replays_reference_python_golden(name):
     """tests/golden/*.npz were recorded by the reference's own Python env stack (tools/gen_golden.py).  Replay through the
     CUDA engine, teacher-forced from the oracle (which reproduces the fixture exactly, tests/test_golden.py)."""
@@ -469,11 +517,12 @@ def test_engine_replays_reference_python_golden(name):
     from oracle.oracle import Oracle
     z = np.load(os.path.join(os.path.dirname(__file__), "golden", name + ".npz"), allow_pickle=False)
     cfg = json.loads(str(z["config_json"])); cfg["random"]["sensor_noise"] = "zero"
-    env = BatchedEnv(cfg, 1, seed=0)
+    env = BatchedEnv(cfg, 1, seed=0, debug=True)
     orc = Oracle(env.model, 1, seed=0)
     orc.reset(); s, _ = env.reset()
     np.testing.assert_allclose(s.cpu().numpy()[0], z["reset_state"], atol=1e-5)
-    diffs = []
+    diffs, same_geo = [], []
+    cap = env.model.dim("ncon_max")
     pushes = dict(zip(z["push_steps"].tolist(), z["push_vels"])) if "push_steps" in z.files else {}
     for k in range(len(z["states"])):
         for f in ("qpos", "qvel", "qacc_warmstart"):
@@ -482,8 +531,13 @@ def test_engine_replays_reference_python_golden(name):
             from tests.test_golden import push_oracle
             env.event("push", pushes[k]); push_oracle(orc, pushes[k])
             np.testing.assert_allclose(env.get("qvel").cpu().numpy(), orc.get("qvel"), atol=1e-6)
-        env.applied_command = torch.tensor(z["applied"][k][None, :], dtype=torch.float32, device="cuda")
-        env.user_command = env.applied_command
+        # CommandWrapper.receive_user_command (wrappers.py:349-375) on the engine side: velocity mode scales the command, position
+        # mode rotates the world offset to the target into the robot frame (uses the teacher-forced qpos); both against the fixture
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            env.receive_user_command(z["commands"][k][None, :])
+        np.testing.assert_allclose(env.applied_command.cpu().numpy()[0], z["applied"][k], atol=2e-5, rtol=1e-5)
         s, term, trunc, info = env.step(z["actions"][k][None, :])
         orc.step(z["actions"][k][None, :], z["applied"][k][None, :])
         np.testing.assert_allclose(info["torque"].cpu().numpy()[0], z["torque"][k], atol=2e-3, rtol=1e-5)
@@ -491,9 +545,18 @@ def test_engine_replays_reference_python_golden(name):
         sd, tot = env.model.dim("stacked_dim"), env.model.dim("stack_size") * env.model.dim("stacked_dim")
         d = np.abs(s.cpu().numpy()[0] - z["states"][k])
         diffs.append(float(max(d[:sd].max(), d[tot:].max() if len(d) > tot else 0.0)))      # newest frame + non-stacked part (older frames repeat earlier steps)
-    diffs = np.array(diffs)       # per control step, teacher-forced; contact onsets give the occasional fp32 outlier (see CONTACT_* above)
-    assert np.median(diffs) < 2e-3 and (diffs > 2e-2).mean() <= 0.15 and diffs.max() < 0.5, \
-        f"state vs reference-python golden: median {np.median(diffs):.1e}, {(diffs > 2e-2).mean():.0%} of steps above 2e-2, max {diffs.max():.1e}"
+        # did the last sub-step see the contact geometry of the fp64 oracle?  (same list, depth within 2e-6, normals within 1e-4)
+        co = orc.contacts(0, cap); cg = env.get("contacts").cpu().numpy().reshape(cap, 10)[:int(env.get("counters")[0, 7])]
+        same, _ = compare_contact_lists(co, cg)
+        dd, dn = geometry_gap(co, cg) if same else (1.0, 1.0)
+        same_geo.append(same and dd < DEPTH_SAME and dn < NORMAL_SAME)
+    diffs, same_geo = np.array(diffs), np.array(same_geo)       # per control step, teacher-forced
+    print(f"\n{name}: state error histogram (decades 1e-7..1e0) {decade_histogram(diffs)}; steps whose final contact geometry equals the oracle's: "
+          f"{int(same_geo.sum())}/{len(diffs)}, worst among them {diffs[same_geo].max() if same_geo.any() else 0:.1e}")
+    # steps on which the fp32 MPR reproduced the fp64 contact geometry must agree closely; the others (another MPR portal ->
+    # another contact normal, see test_contact_parity_teacher_forced) are bounded loosely
+    assert np.median(diffs) < 2e-3 and diffs.max() < 0.5
+    assert (diffs[same_geo] < 2e-2).all() and (diffs[same_geo] > 2e-3).mean() <= 0.15 if same_geo.any() else True
     env.close()
 
 
@@ -534,6 +597,34 @@ def test_step_policy_host_equals_device_loop():
         s1, t1, r1, _ = e1.step(pol.get_action(s1).clone())
         e2.step_policy_host(pol, hc, hs, ht, hr)
         assert (s1.cpu().numpy() == hs).all() and (t1.cpu().numpy() == ht.astype(bool)).all()
+    e1.close(); e2.close(); pol.close()
+
+
+def test_step_policy_pipelined_equals_device_loop():
+    """The overlapped e2e call (double-buffered device state, device->host copies on a copy stream, results one call later)
+    delivers exactly what the device loop computes, step for step, including across an auto-reset."""
+    from cosim_b200.policy import MLPPolicy, synthetic_mlp
+    N = 512
+    kw = dict(random=RANDOM_DEFAULTS, debug=False, hm=True, engine={"auto_reset": True}, max_duration=0.12)     # truncation after 6 control steps
+    e1, e2 = _env("flamingo_p_v3", "rocky_hard", N, **kw), _env("flamingo_p_v3", "rocky_hard", N, **kw)
+    pol = MLPPolicy(synthetic_mlp(e1.state_dim, e1.action_dim), "elu")
+    cmd = np.random.default_rng(2).uniform(-1, 1, (N, e1.command_dim)).astype(np.float32)
+    hc = torch.from_numpy(cmd).pin_memory()
+    s1, _ = e1.reset(); e2.reset()
+    want = []
+    for _ in range(10):
+        e1.receive_user_command(cmd)
+        s1, t1, r1, _ = e1.step(pol.get_action(s1).clone())
+        want.append((s1.cpu().numpy().copy(), t1.cpu().numpy().copy(), r1.cpu().numpy().copy()))
+    got = []
+    for _ in range(10):
+        r = e2.step_policy_pipelined(pol, hc)
+        if r is not None:
+            got.append(tuple(x.numpy().copy() for x in r))
+    got.append(tuple(x.numpy().copy() for x in e2.flush_pipelined()))
+    assert len(got) == 10 and any(w[2].any() for w in want)
+    for k, (w, g) in enumerate(zip(want, got)):
+        assert (w[0] == g[0]).all() and (w[1] == g[1].astype(bool)).all() and (w[2] == g[2].astype(bool)).all(), f"step {k}"
     e1.close(); e2.close(); pol.close()
 
 
