@@ -34,6 +34,21 @@ def build(force=False, verbose=False):
     if not (force or _stale()):
         return LIB_PATH
     os.makedirs(BUILD_DIR, exist_ok=True)
+    # one builder at a time (torchrun starts one process per GPU; all of them may find the library stale): the others wait on the
+    # lock and then find a fresh library.  Objects and the library are written under private names and renamed into place.
+    import fcntl
+    lock = open(os.path.join(BUILD_DIR, ".build.lock"), "w")
+    fcntl.flock(lock, fcntl.LOCK_EX)
+    try:
+        if not (force or _stale()):
+            return LIB_PATH
+        return _build_locked(verbose)
+    finally:
+        fcntl.flock(lock, fcntl.LOCK_UN)
+        lock.close()
+
+
+def _build_locked(verbose):
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
     objs = []
@@ -48,7 +63,9 @@ def build(force=False, verbose=False):
     for cmd, p in procs:
         if p.wait() != 0:
             raise RuntimeError("nvcc failed: " + " ".join(cmd))
-    subprocess.check_call([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB_PATH] + objs)
+    tmp = LIB_PATH + f".{os.getpid()}.tmp"
+    subprocess.check_call([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", tmp] + objs)
+    os.replace(tmp, LIB_PATH)
     return LIB_PATH
 
 

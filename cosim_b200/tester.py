@@ -93,6 +93,8 @@ class Tester:
             state, terminated, truncated, info = self.env.step(action)
             if batched:
                 ended = terminated | truncated
+                if hasattr(self.policy, "reset") and bool(ended.any()):
+                    self.policy.reset(mask=ended)         # recurrent state must not leak into the auto-reset episode (reference: a fresh policy per run)
                 traced_running = finished is None or not bool(finished[self.trace_env])
                 finished = ended.clone() if finished is None else finished | ended
                 if traced_running:
