@@ -67,6 +67,137 @@ __global__ void __launch_bounds__(640, 1) k_step(const __grid_constant__ ModelDe
     step_env(m, E, have_env ? env : 0, ws, a, lane, have_env, 1);
   }
 }
+// ---- pooled step kernel ----------------------------------------------------------------------------------------------
+// k_step above moves the wpb environments of a chunk through the stages of a sub-step in lock step: a stage lasts as long as
+// its slowest environment (a wheel touching down, a Newton solve that needs five iterations), and 35 - 65 % of the warp time
+// is spent waiting at the stage barriers (profiles/).  Here a CTA owns a POOL of P > wpb environments whose workspace images
+// live in global memory (L2-resident: 148 x P x ~10 KB), and a stage is a queue: every warp claims the next environment of the
+// pool, copies its image into its shared-memory slot, runs the stage, copies it back.  All warps of the SM still execute ONE
+// stage's code at a time (what the barriers were for: the instruction cache), but the barrier now ends a queue of P tasks
+// instead of one task per warp, and the tasks are started longest-first (duration of the same stage in the previous
+// sub-step).  Same arithmetic, same results as k_step.
+enum { SG_PRO = 0, SG_KIN, SG_COL, SG_SMO, SG_NEW, SG_EPI, POOL_MAX = 128 };
+struct PoolArgs { float* images; int P, img_floats, bounds, npools, mode; unsigned short* cost_g; };   // mode 0: stage queue, 1: sorted rounds (lock-step start); cost_g [N][4] stage durations carried from step to step
+// image = [workspace (ws_floats) | locals of the control step (16 floats, read / written in place)]
+enum { LOC_ACTIVE = 0, LOC_SIM_STEP, LOC_NSTEP, LOC_NOBS, LOC_RM, LOC_TABS, LOC_TSQ, LOC_TMAX, LOC_ITERS, LOC_FLOATS = 16 };
+__device__ __forceinline__ void ws_load(float* ws, const float* img, int nfl, int lane) {
+  const float4* src = (const float4*)img; float4* dst = (float4*)ws; const int n4 = nfl >> 2;
+  int i = lane;
+  for (; i + 7 * 32 < n4; i += 8 * 32) {          // eight 16-byte loads in flight per lane
+    float4 v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = __ldcg(src + i + 32 * k);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) dst[i + 32 * k] = v[k];
+  }
+  for (; i < n4; i += 32) dst[i] = __ldcg(src + i);
+  __syncwarp();
+}
+__device__ __forceinline__ void ws_store(float* img, const float* ws, int nfl, int lane) {
+  float4* dst = (float4*)img; const float4* src = (const float4*)ws; const int n4 = nfl >> 2;
+  __syncwarp();
+#pragma unroll 4
+  for (int i = lane; i < n4; i += 32) __stcg(dst + i, src[i]);
+}
+__device__ __forceinline__ int stage_kind(int pos, int nst) { return pos == 0 ? SG_PRO : (pos == nst - 1 ? SG_EPI : 1 + ((pos - 1) & 3)); }
+__global__ void __launch_bounds__(640, 1) k_step_pool(const __grid_constant__ ModelDev mp, const EnvArrays E, const StepArgs a, int* sched, const PoolArgs pa) {
+  CTA_PROLOGUE();
+  __shared__ int s_pool, s_next;
+  __shared__ unsigned short s_cost[4][POOL_MAX];      // cycles >> 8 of the last KIN / COL / SMO / NEW group of every pool env
+  __shared__ unsigned char s_order[POOL_MAX];
+  const int fs = MD(frame_skip), nst = 2 + 4 * fs, wsf = m.ws_floats;
+  float* img0 = pa.images + (size_t)blockIdx.x * pa.P * pa.img_floats;
+  for (;;) {
+    if (threadIdx.x == 0) s_pool = atomicAdd(sched, 1);
+    __syncthreads();
+    const int pool = s_pool;
+    if (pool >= pa.npools) break;
+    const int base = pool * pa.P, n = min(pa.P, E.N - base);
+    for (int i = threadIdx.x; i < 4 * n; i += blockDim.x) s_cost[i & 3][i >> 2] = pa.cost_g[(size_t)base * 4 + i];      // durations of the previous control step
+    __syncthreads();
+    int pos = 0;
+    while (pos < nst) {
+      int gend = pos;           // the group of stages [pos, gend] runs back to back on one warp; a CTA-wide boundary follows it
+      while (gend < nst - 1 && !((pa.bounds >> stage_kind(gend, nst)) & 1)) ++gend;
+      const int k0 = stage_kind(pos, nst);
+      if ((int)threadIdx.x < n) {      // start order: longest first
+        const int t = threadIdx.x; int rank = t;
+        if (k0 >= SG_KIN && k0 <= SG_NEW) {
+          const unsigned short c = s_cost[k0 - 1][t]; rank = 0;
+          for (int j = 0; j < n; ++j) { const unsigned short cj = s_cost[k0 - 1][j]; rank += (cj > c) || (cj == c && j < t); }
+        }
+        s_order[rank] = (unsigned char)t;
+      }
+      if (threadIdx.x == 0) s_next = 0;
+      __syncthreads();
+#if defined(COSIM_PHASE_TIMING)
+      long long tw0 = clock64();
+#endif
+      for (int round = 0;; ++round) {
+        int i = 0;
+        if (pa.mode == 1) {         // sorted rounds: the wpb tasks of a round (similar predicted duration) start together
+          if (round > 0) __syncthreads();
+          if (round * wpb_ >= n) break;
+          i = round * wpb_ + warp;
+          if (i >= n) continue;
+        } else {
+          if (lane == 0) i = atomicAdd(&s_next, 1);
+          i = __shfl_sync(0xffffffffu, i, 0);
+          if (i >= n) break;
+        }
+        i = s_order[i];
+        const int env = base + i;
+        float* img = img0 + (size_t)i * pa.img_floats;
+        int* loc = (int*)(img + wsf); float* locf = img + wsf;
+        if (pos > 0) {
+          if (!__ldcg(loc + LOC_ACTIVE)) continue;        // the env was reset in the prologue: no step
+          ws_load(ws, img, wsf, lane);
+        }
+        const long long t0 = clock64();
+        int active = 1;
+        for (int st = pos; st <= gend && active; ++st) {
+          const int k = stage_kind(st, nst);
+          PH_DECL;
+          if (k == SG_PRO) {
+            if (lane == 0) *(float**)(ws + m.off[W_GPTR]) = m.gscratch + (size_t)(blockIdx.x * pa.P + i) * m.gslot_floats;
+            __syncwarp();
+            StepLocals L; step_prologue(m, E, env, ws, a, lane, L);
+            if (lane == 0) {
+              loc[LOC_ACTIVE] = L.active; loc[LOC_SIM_STEP] = L.sim_step; loc[LOC_NSTEP] = (int)L.nstep; loc[LOC_NOBS] = (int)L.nobs;
+              locf[LOC_RM] = L.rm; locf[LOC_TABS] = L.tabs; locf[LOC_TSQ] = L.tsq; locf[LOC_TMAX] = L.tmax; loc[LOC_ITERS] = 0;
+            }
+            __syncwarp();
+            active = L.active;
+          } else if (k == SG_KIN) { substep_pre(m, ws, lane); stage_kin(m, ws, lane); PH_MARK(PH_KIN); }
+          else if (k == SG_COL) { stage_collide(m, ws, lane); PH_MARK(PH_COLLIDE); }
+          else if (k == SG_SMO) { stage_smooth(m, ws, lane); }
+          else if (k == SG_NEW) {
+            int it = stage_newton(m, ws, lane);
+            PH_MARK(PH_NEWTON);
+            it = substep_post(m, ws, lane, it);
+            if (lane == 0) loc[LOC_ITERS] += it;
+            __syncwarp();
+          } else {
+            StepLocals L; L.active = 1; L.sim_step = loc[LOC_SIM_STEP]; L.nstep = (uint32_t)loc[LOC_NSTEP]; L.nobs = (uint32_t)loc[LOC_NOBS];
+            L.rm = locf[LOC_RM]; L.tabs = locf[LOC_TABS]; L.tsq = locf[LOC_TSQ]; L.tmax = locf[LOC_TMAX];
+            step_epilogue(m, E, env, ws, a, lane, L, loc[LOC_ITERS]);
+          }
+        }
+        if (k0 >= SG_KIN && k0 <= SG_NEW && lane == 0) { const long long d = (clock64() - t0) >> 8; s_cost[k0 - 1][i] = (unsigned short)(d > 65535 ? 65535 : d); }
+        if (gend < nst - 1 && active) ws_store(img, ws, wsf, lane);
+      }
+#if defined(COSIM_PHASE_TIMING)
+      { const long long tw1 = clock64(); __syncthreads();
+        if (lane == 0) { const int slot = k0 == SG_COL ? PH_WAIT_COLLIDE : (k0 == SG_NEW ? PH_WAIT_NEWTON : (k0 == SG_SMO ? PH_WAIT_SMOOTH : PH_WAIT_KIN));
+          atomicAdd(m.phase + slot, (unsigned long long)(clock64() - tw1)); atomicAdd(m.phase + PH_IO, (unsigned long long)(tw1 - tw0)); } }
+#else
+      __syncthreads();
+#endif
+      pos = gend + 1;
+    }
+    for (int i = threadIdx.x; i < 4 * n; i += blockDim.x) pa.cost_g[(size_t)base * 4 + i] = s_cost[i & 3][i >> 2];
+  }
+}
 __global__ void __launch_bounds__(640, 1) k_substep(const __grid_constant__ ModelDev mp, const EnvArrays E) {
   CTA_PROLOGUE();
   FOR_ENV_CHUNKS() { if (env < E.N) substep_env(m, E, env, ws, lane); __syncwarp(); }
@@ -110,6 +241,7 @@ struct cosim_handle {
   int N = 0, device = 0, wpb = 1, grid = 1, launches = 0, debug = 0;
   size_t smem = 0;
   int* sched = nullptr;                     // chunk counter of k_step (zeroed on the stream before every launch)
+  PoolArgs pool = {nullptr, 0, 0, 0, 0, 0, nullptr};    // pooled step kernel (P = 0: off)
   std::string err;
   std::vector<void*> allocs;
   cudaStream_t stream = nullptr;            // used by cosim_step_host
@@ -189,9 +321,43 @@ int cosim_create(const void* blob, size_t nbytes, int num_envs, int device, uint
     h->grid = nchunks < per_sm * nsm ? nchunks : per_sm * nsm;
     if (getenv("COSIM_PRINT_OCC")) fprintf(stderr, "cosim_create: k_step %d threads, %zu B dynamic smem -> %d CTA(s) per SM, grid %d, %d contact records in shared memory (capacity %d), %llu B overflow slot per warp\n",
                                            32 * h->wpb, h->smem, per_sm, h->grid, h->m.cn_k, h->m.dims[CD_ncon_max], (unsigned long long)h->m.gslot_floats * 4);
+    // pooled stepping (k_step_pool): P environments per CTA and stage queue, P ~ COSIM_POOL_R x wpb (default 3; 0 / 1 = off),
+    // rounded so that every CTA gets the same number of pools
+    {
+      // Default: on for fine terrain rasters (cells under 5 cm: dozens of contacts per env, stage durations spread over an order
+      // of magnitude -- w4_p_v2 on the stairs +43 %), off otherwise: with a handful of contacts the stages are short, and warps
+      // that START a stage together fetch its code together; staggered starts cost more instruction-cache misses than
+      // the queue saves in barrier waits (flamingo_p_v3 on rocky_hard 2.5 -> 1.6 M env-steps/s, profiles/r02_experiments.md).
+      const double cell = h->m.dims[CD_ground_type] == 1 ? 2.0 * h->m.opts[CO_hf_sx] / (h->m.dims[CD_hf_ncol] > 1 ? h->m.dims[CD_hf_ncol] - 1 : 1) : 1.0;
+      int R = cell < 0.05 ? 4 : 0; { const char* e = getenv("COSIM_POOL_R"); if (e) R = atoi(e); }
+      const int grid_full = per_sm * nsm;
+      if (R >= 2 && h->wpb >= 4 && num_envs >= 2 * h->wpb * grid_full) {
+        int target = R * h->wpb; if (target > POOL_MAX) target = POOL_MAX;
+        int k = (int)((double)num_envs / ((double)grid_full * target) + 0.5); if (k < 1) k = 1;
+        int P = (num_envs + grid_full * k - 1) / (grid_full * k);
+        if (P > POOL_MAX) P = POOL_MAX;
+        if (P > h->wpb) {
+          h->pool.P = P; h->pool.img_floats = h->m.ws_floats + LOC_FLOATS; h->pool.npools = (num_envs + P - 1) / P;
+          h->pool.bounds = (1 << SG_KIN) | (1 << SG_COL) | (1 << SG_SMO) | (1 << SG_NEW);
+          { const char* e = getenv("COSIM_POOL_BOUNDS"); if (e) h->pool.bounds = atoi(e); }
+          h->grid = h->pool.npools < grid_full ? h->pool.npools : grid_full;
+          cudaFuncSetAttribute(k_step_pool, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 16 - 2048);
+          cudaFuncSetAttribute(k_step_pool, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        }
+      }
+      if (getenv("COSIM_PRINT_OCC")) fprintf(stderr, "cosim_create: pooled stepping %s (P = %d envs per CTA and stage queue, %d pools, boundaries 0x%x)\n", h->pool.P ? "on" : "off", h->pool.P, h->pool.npools, h->pool.bounds);
+    }
     try {
       void* p = nullptr;
-      const size_t bytes = (size_t)h->grid * h->wpb * h->m.gslot_floats * sizeof(float);
+      const size_t slots_per_cta = (size_t)(h->pool.P > h->wpb ? h->pool.P : h->wpb);
+      const size_t bytes = (size_t)(per_sm * nsm > h->grid ? per_sm * nsm : h->grid) * slots_per_cta * h->m.gslot_floats * sizeof(float);
+      if (h->pool.P) {
+        void* q = nullptr;
+        if (cudaMalloc(&q, (size_t)h->grid * h->pool.P * h->pool.img_floats * sizeof(float)) != cudaSuccess) throw std::runtime_error("cudaMalloc failed (pool images)");
+        h->allocs.push_back(q); h->pool.images = (float*)q;
+        h->pool.cost_g = (unsigned short*)dev_zalloc(h, (size_t)num_envs * 4 * sizeof(unsigned short));
+        { const char* e = getenv("COSIM_POOL_MODE"); h->pool.mode = e ? atoi(e) : 0; }
+      }
       if (cudaMalloc(&p, bytes ? bytes : 4) != cudaSuccess) throw std::runtime_error("cudaMalloc failed (contact overflow slots)");
       h->allocs.push_back(p); h->m.gscratch = (float*)p;
       h->sched = (int*)dev_zalloc(h, 16);
@@ -232,7 +398,8 @@ int cosim_step(cosim_handle* h, const float* action, const float* command, const
   ON_DEVICE(h);
   StepArgs a = {action, command, user_command, state_out, terminated, truncated, nullptr};
   CK(cudaMemsetAsync(h->sched, 0, sizeof(int), (cudaStream_t)stream));
-  k_step<<<grid_for(h), 32 * h->wpb, h->smem, (cudaStream_t)stream>>>(h->m, h->E, a, h->sched);
+  if (h->pool.P) k_step_pool<<<grid_for(h), 32 * h->wpb, h->smem, (cudaStream_t)stream>>>(h->m, h->E, a, h->sched, h->pool);
+  else k_step<<<grid_for(h), 32 * h->wpb, h->smem, (cudaStream_t)stream>>>(h->m, h->E, a, h->sched);
   h->launches++;
   CK(cudaGetLastError());
   return COSIM_OK;

@@ -2190,75 +2190,93 @@ DEV_NOINLINE void sensors(const ModelDev& m, float* ws, int lane) {
 }
 
 // ------------------------------------------------------------------------------------------ forward + one sub-step
+// The forward pass in four stages.  They are separate functions because the pooled step kernel (engine.cu k_step_pool) runs a
+// stage for every environment of a CTA's pool before any environment enters the next one; forward() below strings them
+// together for one environment (with optional CTA-wide barriers in between).
+enum { CNT_ROWS = 7 };      // W_CNT[7]: "any constraint row" flag, handed from stage_smooth to stage_newton
+// stage 1: kinematics, spatial inertias, mass matrix and its Cholesky factor
+DEV void stage_kin(const ModelDev& m, float* ws, int lane) {
+  const int nv = MD(nv);
+  float* A = WS(W_A);
+  kinematics(m, ws, lane);
+  com_pos(m, ws, lane);
+  crb(m, ws, lane);
+  const float* M = WS(W_M);
+  FOR_LANE(i, nv * nv) A[i] = M[i];
+  SYNC();
+  chol_factor(A, WS(W_INVD), nv, lane, m.tri);
+}
+// stage 2: collision
+DEV void stage_collide(const ModelDev& m, float* ws, int lane) {
+  if (MD(ground_type) == 1) collide_hfield_all(m, ws, lane);
+  else {
+    int ncon = 0, dropped = 0;
+    NOUNROLL for (int g = 0; g < MD(ngeom); ++g) collide_plane(m, ws, g, ncon, dropped, lane);
+    if (lane == 0) { WSI(W_CNT)[CNT_NCON] = ncon; WSI(W_CNT)[CNT_DROPPED] = dropped; }
+  }
+  SYNC();
+  if (MD(npair) > 0) collide_pairs(m, ws, lane);
+}
+// stage 3: sensors, smooth forces and acceleration, constraint rows
+DEV void stage_smooth(const ModelDev& m, float* ws, int lane) {
+  const int nv = MD(nv), nu = MD(nu), njnt = MD(njnt);
+  PH_DECL;
+  float* A = WS(W_A);
+  const int ncon = WSI(W_CNT)[CNT_NCON];
+  com_vel(m, ws, lane);
+  sensors(m, ws, lane);
+  // smooth forces: passive damping - bias + actuation (ctrl clamp, gear, actuatorfrcrange clamp)
+  rne_bias(m, ws, WS(W_TMPV), lane);
+  float* fs = WS(W_FSMOOTH);
+  FOR_LANE(k, nv) fs[k] = -LDG(m.dof_damping + k) * WS(W_QVEL)[k] - WS(W_TMPV)[k];
+  SYNC();
+  FOR_LANE(a, nu) {
+    float c = WS(W_CTRL)[a];
+    if (m.act_ctrllimited[a]) c = fminf(LDG(m.act_ctrlrange + 2 * a + 1), fmaxf(LDG(m.act_ctrlrange + 2 * a), c));
+    float f = LDG(m.act_gear + a) * c;
+    const int k = m.act_dof[a], j = m.dof_jnt[k];
+    if (m.jnt_actfrclimited[j]) f = fminf(LDG(m.jnt_actfrcrange + 2 * j + 1), fmaxf(LDG(m.jnt_actfrcrange + 2 * j), f));
+    fs[k] += f;     // one actuator per joint in all four robots
+  }
+  SYNC();
+  FOR_LANE(k, nv) WS(W_TMPV)[k] = fs[k];
+  SYNC();
+  chol_solve(A, WS(W_INVD), WS(W_TMPV), WS(W_BUF), WS(W_ASMOOTH), nv, lane);
+  PH_MARK(PH_SMOOTH);
+  // constraint rows last: the few-contact Jacobians (W_CN_J) take the place of the body velocities / accelerations,
+  // which sensors() and rne_bias() have consumed by now
+  make_constraint(m, ws, ncon, lane);
+  PH_MARK(PH_CONSTRAINT);
+  // any constraint row?
+  int rows = (ncon > 0) || (MD(neq) > 0);
+  { int r = 0; FOR_LANE(k, nv) r |= (WS(W_FR_D)[k] > 0.f); FOR_LANE(j, njnt) r |= (WS(W_LM_SIGN)[j] != 0.f); rows |= wor(r); }
+  if (lane == 0) WSI(W_CNT)[CNT_ROWS] = rows;
+  SYNC();
+}
+// stage 4: constraint solve; returns the solver iterations
+DEV int stage_newton(const ModelDev& m, float* ws, int lane) {
+  const int iters = newton_solve(m, ws, WSI(W_CNT)[CNT_NCON], WSI(W_CNT)[CNT_ROWS], lane);
+  PH_COUNT(PH_NEWTON_ITERS, iters);
+  return iters;
+}
 // returns solver iterations; the contact count of this pass is left in W_CNT
 // `active` = this warp has an env to advance; `bsync` = CTA-wide phase barriers (must then be called by every warp)
 DEV_NOINLINE int forward(const ModelDev& m, float* ws, int lane, int active = 1, int bsync = 0) {
-  const int nv = MD(nv), nu = MD(nu), njnt = MD(njnt);
   PH_DECL;
-  int ncon = 0, dropped = 0, rows = 0, iters = 0;
-  float* A = WS(W_A);
-  if (active) {           // ---- phase 1: kinematics, spatial inertias, mass matrix and its Cholesky factor
-    kinematics(m, ws, lane);
-    com_pos(m, ws, lane);
-    crb(m, ws, lane);
-    const float* M = WS(W_M);
-    FOR_LANE(i, nv * nv) A[i] = M[i];
-    SYNC();
-    chol_factor(A, WS(W_INVD), nv, lane, m.tri);
-  }
+  int iters = 0;
+  if (active) stage_kin(m, ws, lane);
   PH_MARK(PH_KIN);
   BSYNC_IF(bsync, 0);
   PH_MARK(PH_WAIT_KIN);
-  if (active) {           // ---- phase 2: collision
-    if (MD(ground_type) == 1) collide_hfield_all(m, ws, lane);
-    else {
-      NOUNROLL for (int g = 0; g < MD(ngeom); ++g) collide_plane(m, ws, g, ncon, dropped, lane);
-      if (lane == 0) { WSI(W_CNT)[CNT_NCON] = ncon; WSI(W_CNT)[CNT_DROPPED] = dropped; }
-    }
-    SYNC();
-    if (MD(npair) > 0) collide_pairs(m, ws, lane);
-  }
+  if (active) stage_collide(m, ws, lane);
   PH_MARK(PH_COLLIDE);
   BSYNC_IF(bsync, 1);
   PH_MARK(PH_WAIT_COLLIDE);
-  if (active) {           // ---- phase 3: sensors, smooth forces and acceleration, constraint rows
-    ncon = WSI(W_CNT)[CNT_NCON];
-    com_vel(m, ws, lane);
-    sensors(m, ws, lane);
-    // smooth forces: passive damping - bias + actuation (ctrl clamp, gear, actuatorfrcrange clamp)
-    rne_bias(m, ws, WS(W_TMPV), lane);
-    float* fs = WS(W_FSMOOTH);
-    FOR_LANE(k, nv) fs[k] = -LDG(m.dof_damping + k) * WS(W_QVEL)[k] - WS(W_TMPV)[k];
-    SYNC();
-    FOR_LANE(a, nu) {
-      float c = WS(W_CTRL)[a];
-      if (m.act_ctrllimited[a]) c = fminf(LDG(m.act_ctrlrange + 2 * a + 1), fmaxf(LDG(m.act_ctrlrange + 2 * a), c));
-      float f = LDG(m.act_gear + a) * c;
-      const int k = m.act_dof[a], j = m.dof_jnt[k];
-      if (m.jnt_actfrclimited[j]) f = fminf(LDG(m.jnt_actfrcrange + 2 * j + 1), fmaxf(LDG(m.jnt_actfrcrange + 2 * j), f));
-      fs[k] += f;     // one actuator per joint in all four robots
-    }
-    SYNC();
-    FOR_LANE(k, nv) WS(W_TMPV)[k] = fs[k];
-    SYNC();
-    chol_solve(A, WS(W_INVD), WS(W_TMPV), WS(W_BUF), WS(W_ASMOOTH), nv, lane);
-    PH_MARK(PH_SMOOTH);
-    // constraint rows last: the few-contact Jacobians (W_CN_J) take the place of the body velocities / accelerations,
-    // which sensors() and rne_bias() have consumed by now
-    make_constraint(m, ws, ncon, lane);
-    PH_MARK(PH_CONSTRAINT);
-    // any constraint row?
-    rows = (ncon > 0) || (MD(neq) > 0);
-    { int r = 0; FOR_LANE(k, nv) r |= (WS(W_FR_D)[k] > 0.f); FOR_LANE(j, njnt) r |= (WS(W_LM_SIGN)[j] != 0.f); rows |= wor(r); }
-  }
+  if (active) stage_smooth(m, ws, lane);
   PH_MARK(PH_SMOOTH);
   BSYNC_IF(bsync, 2);
   PH_MARK(PH_WAIT_SMOOTH);
-  if (active) {           // ---- phase 4: constraint solve
-    ncon = WSI(W_CNT)[CNT_NCON];
-    iters = newton_solve(m, ws, ncon, rows, lane);
-    PH_COUNT(PH_NEWTON_ITERS, iters);
-  }
+  if (active) iters = stage_newton(m, ws, lane);
   PH_MARK(PH_NEWTON);
   BSYNC_IF(bsync, 3);
   PH_MARK(PH_WAIT_NEWTON);
@@ -2277,44 +2295,51 @@ DEV_NOINLINE void reset_data(const ModelDev& m, float* ws, int lane) {
   SYNC();
 }
 
-DEV_NOINLINE int substep(const ModelDev& m, float* ws, int lane, int active = 1, int bsync = 0) {
+// what mj_step does around the forward pass: the state check in front of it ...
+DEV void substep_pre(const ModelDev& m, float* ws, int lane) {
+  if (bad_state(m, ws, lane)) { reset_data(m, ws, lane); if (lane == 0) WSI(W_CNT)[CNT_NAN]++; }
+}
+// ... and the acceleration check + implicitfast integration after it (returns the solver iterations that count)
+DEV_NOINLINE int substep_post(const ModelDev& m, float* ws, int lane, int iters) {
   const int nv = MD(nv), njnt = MD(njnt);
-  if (active && bad_state(m, ws, lane)) { reset_data(m, ws, lane); if (lane == 0) WSI(W_CNT)[CNT_NAN]++; }
-  int iters = forward(m, ws, lane, active, bsync);
-  if (active) {
-    { int bad = 0; FOR_LANE(i, nv) { float x = WS(W_QACC)[i]; bad |= !(x == x) || fabsf(x) > 1e10f; }
-      if (wor(bad)) { reset_data(m, ws, lane); if (lane == 0) WSI(W_CNT)[CNT_NAN]++; iters = forward(m, ws, lane, 1, 0); } }   // rare: no barriers inside
-    // implicitfast: (M + dt diag(damping)) a = qfrc_smooth + qfrc_constraint
-    PH_DECL;
-    const float dt = MO(timestep);
-    float* A = WS(W_A); const float* M = WS(W_M);
-    FOR_LANE(i, nv * nv) { const int r = i / nv, c = i - r * nv; A[i] = M[i] + (r == c ? dt * LDG(m.dof_damping + r) : 0.f); }
-    FOR_LANE(k, nv) WS(W_TMPV)[k] = WS(W_FSMOOTH)[k] + WS(W_FCON)[k];
-    SYNC();
-    chol_factor(A, WS(W_INVD), nv, lane, m.tri);
-    chol_solve(A, WS(W_INVD), WS(W_TMPV), WS(W_BUF), WS(W_GRAD), nv, lane);
-    float* qvel = WS(W_QVEL); float* qpos = WS(W_QPOS);
-    FOR_LANE(k, nv) qvel[k] += dt * WS(W_GRAD)[k];
-    SYNC();
-    FOR_LANE(j, njnt) {
-      const int qa = m.jnt_qposadr[j], da = m.jnt_dofadr[j];
-      if (m.jnt_type[j] == 0) {
-        for (int k = 0; k < 3; ++k) qpos[qa + k] += dt * qvel[da + k];
-        float w[3] = {qvel[da + 3], qvel[da + 4], qvel[da + 5]};
-        float ang = v3norm(w) * dt;
-        if (ang > 0.f) {
-          v3normalize(w);
-          float s, c; sincosf(ang * 0.5f, &s, &c);
-          float dq[4] = {c, w[0] * s, w[1] * s, w[2] * s}, q[4];
-          quat_mul(q, qpos + qa + 3, dq); quat_normalize(q);
-          qpos[qa + 3] = q[0]; qpos[qa + 4] = q[1]; qpos[qa + 5] = q[2]; qpos[qa + 6] = q[3];
-        }
-      } else qpos[qa] += dt * qvel[da];
-    }
-    if (lane == 0) WSI(W_CNT)[CNT_DROPPED_STEP] += WSI(W_CNT)[CNT_DROPPED];
-    SYNC();
-    PH_MARK(PH_INTEGRATE);
+  { int bad = 0; FOR_LANE(i, nv) { float x = WS(W_QACC)[i]; bad |= !(x == x) || fabsf(x) > 1e10f; }
+    if (wor(bad)) { reset_data(m, ws, lane); if (lane == 0) WSI(W_CNT)[CNT_NAN]++; iters = forward(m, ws, lane, 1, 0); } }   // rare: no barriers inside
+  // implicitfast: (M + dt diag(damping)) a = qfrc_smooth + qfrc_constraint
+  PH_DECL;
+  const float dt = MO(timestep);
+  float* A = WS(W_A); const float* M = WS(W_M);
+  FOR_LANE(i, nv * nv) { const int r = i / nv, c = i - r * nv; A[i] = M[i] + (r == c ? dt * LDG(m.dof_damping + r) : 0.f); }
+  FOR_LANE(k, nv) WS(W_TMPV)[k] = WS(W_FSMOOTH)[k] + WS(W_FCON)[k];
+  SYNC();
+  chol_factor(A, WS(W_INVD), nv, lane, m.tri);
+  chol_solve(A, WS(W_INVD), WS(W_TMPV), WS(W_BUF), WS(W_GRAD), nv, lane);
+  float* qvel = WS(W_QVEL); float* qpos = WS(W_QPOS);
+  FOR_LANE(k, nv) qvel[k] += dt * WS(W_GRAD)[k];
+  SYNC();
+  FOR_LANE(j, njnt) {
+    const int qa = m.jnt_qposadr[j], da = m.jnt_dofadr[j];
+    if (m.jnt_type[j] == 0) {
+      for (int k = 0; k < 3; ++k) qpos[qa + k] += dt * qvel[da + k];
+      float w[3] = {qvel[da + 3], qvel[da + 4], qvel[da + 5]};
+      float ang = v3norm(w) * dt;
+      if (ang > 0.f) {
+        v3normalize(w);
+        float s, c; sincosf(ang * 0.5f, &s, &c);
+        float dq[4] = {c, w[0] * s, w[1] * s, w[2] * s}, q[4];
+        quat_mul(q, qpos + qa + 3, dq); quat_normalize(q);
+        qpos[qa + 3] = q[0]; qpos[qa + 4] = q[1]; qpos[qa + 5] = q[2]; qpos[qa + 6] = q[3];
+      }
+    } else qpos[qa] += dt * qvel[da];
   }
+  if (lane == 0) WSI(W_CNT)[CNT_DROPPED_STEP] += WSI(W_CNT)[CNT_DROPPED];
+  SYNC();
+  PH_MARK(PH_INTEGRATE);
+  return iters;
+}
+DEV_NOINLINE int substep(const ModelDev& m, float* ws, int lane, int active = 1, int bsync = 0) {
+  if (active) substep_pre(m, ws, lane);
+  int iters = forward(m, ws, lane, active, bsync);
+  if (active) iters = substep_post(m, ws, lane, iters);
   BSYNC(bsync);
   return iters;
 }

@@ -253,30 +253,33 @@ DEV_NOINLINE void dump_contacts(const ModelDev& m, const EnvArrays& E, int env, 
 }
 
 // ------------------------------------------------------------------------------------------ step
-// `have_env` = this warp owns an env (false for the padding warps of the last CTA); `bsync` = CTA-wide phase barriers
-DEV_NOINLINE void step_env(const ModelDev& m, const EnvArrays& E, int env, float* ws, const StepArgs& a, int lane, int have_env = 1, int bsync = 0) {
-  const int nv = MD(nv), nu = MD(nu), cd = MD(command_dim), sdim = MD(state_dim), nb = MD(nbody);
+// What a control step does around its sub-steps, in two parts so that the pooled kernel (engine.cu k_step_pool) can run them as
+// stages of their own.  StepLocals = what the first part hands to the second.
+struct StepLocals { int active, sim_step; uint32_t nstep, nobs; float rm, tabs, tsq, tmax; };
+// part 1: pending reset (the reference asserts reset-before-step; the batched engine resets the env instead and skips the
+// step), parameters and state -> workspace, delay filter, PD law, clip.  L.active = 0: nothing more to do for this env.
+DEV void step_prologue(const ModelDev& m, const EnvArrays& E, int env, float* ws, const StepArgs& a, int lane, StepLocals& L) {
+  const int nu = MD(nu), cd = MD(command_dim), sdim = MD(state_dim);
   int* ct = E.counters + (size_t)env * 8;
   const float* cmd = a.command ? a.command + (size_t)env * cd : nullptr;
   float* state = a.state_out + (size_t)env * sdim;
-  int active = have_env;
-  if (have_env && ct[CT_NEED_RESET]) {     // reference asserts reset-before-step; the batched engine resets the env instead
+  L.active = 1; L.sim_step = 0; L.nstep = 0; L.nobs = 0; L.rm = L.tabs = L.tsq = L.tmax = 0.f;
+  if (ct[CT_NEED_RESET]) {
     if (MD(auto_reset)) { reset_env(m, E, env, ws, cmd, state, lane); if (lane == 0) { a.terminated[env] = 0; a.truncated[env] = 0; } }
-    active = 0;
+    L.active = 0;
+    return;
   }
-  int sim_step = 0, has_prev = 0; uint32_t nstep = 0, nobs = 0;
-  float rm = 0.f, tabs = 0.f, tsq = 0.f, tmax = 0.f;
-  if (active) {
-  sim_step = ct[CT_SIM_STEP] + 1;
-  nstep = (uint32_t)ct[CT_NSTEP]; nobs = (uint32_t)ct[CT_NOBS];
-  has_prev = ct[CT_HAS_DELAY];
+  L.sim_step = ct[CT_SIM_STEP] + 1;
+  L.nstep = (uint32_t)ct[CT_NSTEP]; L.nobs = (uint32_t)ct[CT_NOBS];
+  const int has_prev = ct[CT_HAS_DELAY];
   load_params(m, E, env, ws, lane);
   load_state(m, E, env, ws, lane);
   const float* act = a.action + (size_t)env * nu;
   // delay filter: Bernoulli(delay_prob) one-step hold
-  const float v = uni(m, env, RNG_DELAY, nstep, 0);
+  const float v = uni(m, env, RNG_DELAY, L.nstep, 0);
   SYNC();
   const bool delay = (WS(W_SCAL)[2] > v) && has_prev;
+  float rm = 0.f, tabs = 0.f, tsq = 0.f, tmax = 0.f;
   FOR_LANE(k, nu) {
     const float ak = act[k];
     const float f = delay ? E.delay_prev[(size_t)env * nu + k] : ak;
@@ -302,16 +305,18 @@ DEV_NOINLINE void step_env(const ModelDev& m, const EnvArrays& E, int env, float
     E.last_action[(size_t)env * nu + k] = ak;
     tabs += fabsf(tq); tsq += tq * tq; tmax = fmaxf(tmax, fabsf(tq));
   }
-  rm = sqrtf(wsum(rm) / (float)nu); tabs = wsum(tabs); tsq = wsum(tsq); tmax = wmaxf(tmax);
-  SYNC();
-  }
-  BSYNC(bsync);
-  int iters = 0;
-  const int fs = MD(frame_skip);
+  L.rm = sqrtf(wsum(rm) / (float)nu); L.tabs = wsum(tabs); L.tsq = wsum(tsq); L.tmax = wmaxf(tmax);
   if (lane == 0) { WSI(W_CNT)[CNT_NCON] = 0; WSI(W_CNT)[CNT_DROPPED] = 0; WSI(W_CNT)[CNT_NAN] = 0; WSI(W_CNT)[CNT_DROPPED_STEP] = 0; }
   SYNC();
-  NOUNROLL for (int s = 0; s < fs; ++s) iters += substep(m, ws, lane, active, bsync);
-  if (!active) return;
+}
+// part 2 (after the sub-steps): cfrc_ext, termination, observations, state build, write-back, bookkeeping and statistics
+DEV void step_epilogue(const ModelDev& m, const EnvArrays& E, int env, float* ws, const StepArgs& a, int lane, const StepLocals& L, int iters) {
+  const int nv = MD(nv), cd = MD(command_dim), sdim = MD(state_dim), nb = MD(nbody);
+  int* ct = E.counters + (size_t)env * 8;
+  const float* cmd = a.command ? a.command + (size_t)env * cd : nullptr;
+  float* state = a.state_out + (size_t)env * sdim;
+  const int sim_step = L.sim_step; const uint32_t nstep = L.nstep, nobs = L.nobs;
+  const float rm = L.rm, tabs = L.tabs, tsq = L.tsq, tmax = L.tmax;
   const int ncon = WSI(W_CNT)[CNT_NCON], nan_count = WSI(W_CNT)[CNT_NAN], dropped_total = WSI(W_CNT)[CNT_DROPPED_STEP];
   PH_DECL;
   cfrc_ext(m, ws, ncon, lane);
@@ -347,6 +352,19 @@ DEV_NOINLINE void step_env(const ModelDev& m, const EnvArrays& E, int env, float
     if (term || trunc) { st[ST_EPISODES] += 1.f; st[ST_TERMINATED] += (float)term; st[ST_SUCCESS] += (float)(trunc && !term); }
   }
   SYNC();
+}
+// One control step of one env by one warp, all stages back to back.
+// `have_env` = this warp owns an env (false for the padding warps of the last CTA); `bsync` = CTA-wide phase barriers
+DEV_NOINLINE void step_env(const ModelDev& m, const EnvArrays& E, int env, float* ws, const StepArgs& a, int lane, int have_env = 1, int bsync = 0) {
+  StepLocals L; L.active = 0;
+  if (have_env) step_prologue(m, E, env, ws, a, lane, L);
+  const int active = L.active;
+  BSYNC(bsync);
+  int iters = 0;
+  const int fs = MD(frame_skip);
+  NOUNROLL for (int s = 0; s < fs; ++s) iters += substep(m, ws, lane, active, bsync);
+  if (!active) return;
+  step_epilogue(m, E, env, ws, a, lane, L, iters);
 }
 
 // one raw physics sub-step (mj_step) from the stored state with ctrl = the last applied torque; debug / parity aid

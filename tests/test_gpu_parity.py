@@ -303,15 +303,18 @@ def test_baseline_config_4096_envs_with_height_map():
         nflip += _assert_hm_cells(env.model, orc.get("qpos"), cells_o, cells_g, env.get("qpos").cpu().numpy().astype(np.float64))
         cells_ok.append((cells_o == cells_g).mean())
         cg_all = env.get("contacts").cpu().numpy().reshape(N, cap, 10)
-        for e in np.nonzero(nco != ncg)[0]:          # a differing contact count must come from a grazing contact
+        # whole control steps (the last 3 of the 4 sub-steps run free): a contact that exists on one side only must be explained by
+        # how far the two states of THAT env have drifted apart -- base position plus joint angles times the longest lever (< 1 m)
+        drift = np.abs(env.get("qpos").cpu().numpy().astype(np.float64) - orc.get("qpos")).max(axis=1)
+        for e in np.nonzero(nco != ncg)[0]:
             _, unmatched = compare_contact_lists(orc.contacts(int(e), cap), cg_all[e, :ncg[e]])
             worst_unmatched = max(worst_unmatched, unmatched)
+            assert unmatched <= 1e-5 + 2.0 * drift[e], f"env {e}: a contact of depth {unmatched:.1e} m exists on one side only while the states agree to {drift[e]:.1e}"
         errs.append(np.abs(s_g[:, :88] - s_o[:, :88]).max(axis=1))
         assert (t_g.cpu().numpy() == t_o).mean() > 0.995
     errs = np.concatenate(errs)
     print(f"\ncontact counts agree in {min(same):.4f} of the envs (worst one-sided contact {worst_unmatched:.1e} m); height-map cells agree on {min(cells_ok):.5f} of the rays, {nflip} flips, all on cell boundaries")
-    # whole control steps (the last 3 of the 4 sub-steps run free): a one-sided contact may be as deep as the drift of the state
-    assert worst_unmatched < 1e-3, f"a contact of depth {worst_unmatched:.1e} m exists on one side only"
+    assert worst_unmatched < 1e-2, f"a contact of depth {worst_unmatched:.1e} m exists on one side only"      # robots fall at ~2 m/s = 1e-2 m per sub-step
     assert min(same) >= 0.97, f"contact counts agree in {min(same):.3f} of the envs"
     assert min(cells_ok) >= 0.995, f"height-map cells agree on {min(cells_ok):.4f} of the rays"
     assert np.median(errs) < 2e-3 and (errs > 5e-2).mean() < 0.05, f"state error median {np.median(errs):.1e}, {(errs > 5e-2).mean():.1%} above 5e-2"
