@@ -21,25 +21,36 @@ struct StepArgs {
   const uint8_t* mask;         // reset: [N] or NULL (all)
 };
 
+// Per-env rows in HBM are touched once per control step: streaming loads / stores (evict-first) keep them from pushing the
+// warps' local-memory lines (callee-saved registers of the out-of-line stage functions) out of L2 -- those evictions, not the
+// env rows, were 80 % of the DRAM writes of a step (profiles/r02_dram_traffic.md).
+#ifdef COSIM_HOST_EMU
+#define ELD(p) (*(p))
+#define EST(p, v) (*(p) = (v))
+#else
+#define ELD(p) __ldcs(p)
+#define EST(p, v) __stcs((p), (v))
+#endif
+
 DEV_NOINLINE void load_params(const ModelDev& m, const EnvArrays& E, int env, float* ws, int lane) {
   const int nb = MD(nbody), nv = MD(nv), ng = MD(ngeom), nu = MD(nu);
-  FOR_LANE(i, nb) { WS(W_BMASS)[i] = E.body_mass[(size_t)env * nb + i]; WS(W_INVWB)[i] = E.invw_body[(size_t)env * nb + i]; }
-  FOR_LANE(i, nv) { WS(W_INVWD)[i] = E.invw_dof[(size_t)env * nv + i]; WS(W_FLOSS)[i] = E.floss[(size_t)env * nv + i]; }
-  FOR_LANE(i, ng) WS(W_GMU)[i] = E.gmu[(size_t)env * ng + i];
-  FOR_LANE(i, nu) { WS(W_KP)[i] = E.kp[(size_t)env * nu + i]; WS(W_KD)[i] = E.kd[(size_t)env * nu + i]; }
-  FOR_LANE(i, 4) WS(W_SCAL)[i] = E.scal[(size_t)env * 4 + i];
+  FOR_LANE(i, nb) { WS(W_BMASS)[i] = ELD(E.body_mass + (size_t)env * nb + i); WS(W_INVWB)[i] = ELD(E.invw_body + (size_t)env * nb + i); }
+  FOR_LANE(i, nv) { WS(W_INVWD)[i] = ELD(E.invw_dof + (size_t)env * nv + i); WS(W_FLOSS)[i] = ELD(E.floss + (size_t)env * nv + i); }
+  FOR_LANE(i, ng) WS(W_GMU)[i] = ELD(E.gmu + (size_t)env * ng + i);
+  FOR_LANE(i, nu) { WS(W_KP)[i] = ELD(E.kp + (size_t)env * nu + i); WS(W_KD)[i] = ELD(E.kd + (size_t)env * nu + i); }
+  FOR_LANE(i, 4) WS(W_SCAL)[i] = ELD(E.scal + (size_t)env * 4 + i);
 }
 DEV_NOINLINE void load_state(const ModelDev& m, const EnvArrays& E, int env, float* ws, int lane) {
   const int nq = MD(nq), nv = MD(nv);
-  FOR_LANE(i, nq) WS(W_QPOS)[i] = E.qpos[(size_t)env * nq + i];
-  FOR_LANE(i, nv) { WS(W_QVEL)[i] = E.qvel[(size_t)env * nv + i]; WS(W_WARM)[i] = E.warm[(size_t)env * nv + i]; }
-  if (MD(npair) > 0) FOR_LANE(i, 4 * PAXIS_SLOTS) WS(W_PAXIS)[i] = E.paxis[(size_t)env * 4 * PAXIS_SLOTS + i];
+  FOR_LANE(i, nq) WS(W_QPOS)[i] = ELD(E.qpos + (size_t)env * nq + i);
+  FOR_LANE(i, nv) { WS(W_QVEL)[i] = ELD(E.qvel + (size_t)env * nv + i); WS(W_WARM)[i] = ELD(E.warm + (size_t)env * nv + i); }
+  if (MD(npair) > 0) FOR_LANE(i, 4 * PAXIS_SLOTS) WS(W_PAXIS)[i] = ELD(E.paxis + (size_t)env * 4 * PAXIS_SLOTS + i);
 }
 DEV_NOINLINE void store_state(const ModelDev& m, const EnvArrays& E, int env, const float* ws, int lane) {
   const int nq = MD(nq), nv = MD(nv);
-  FOR_LANE(i, nq) E.qpos[(size_t)env * nq + i] = WS(W_QPOS)[i];
-  FOR_LANE(i, nv) { E.qvel[(size_t)env * nv + i] = WS(W_QVEL)[i]; E.warm[(size_t)env * nv + i] = WS(W_WARM)[i]; }
-  if (MD(npair) > 0) FOR_LANE(i, 4 * PAXIS_SLOTS) E.paxis[(size_t)env * 4 * PAXIS_SLOTS + i] = WS(W_PAXIS)[i];
+  FOR_LANE(i, nq) EST(E.qpos + (size_t)env * nq + i, WS(W_QPOS)[i]);
+  FOR_LANE(i, nv) { EST(E.qvel + (size_t)env * nv + i, WS(W_QVEL)[i]); EST(E.warm + (size_t)env * nv + i, WS(W_WARM)[i]); }
+  if (MD(npair) > 0) FOR_LANE(i, 4 * PAXIS_SLOTS) EST(E.paxis + (size_t)env * 4 * PAXIS_SLOTS + i, WS(W_PAXIS)[i]);
 }
 
 // ------------------------------------------------------------------------------------------ init: randomise + setConst
@@ -175,13 +186,13 @@ DEV_NOINLINE void concat_obs(const ModelDev& m, const EnvArrays& E, int env, con
   int o = 0;
   NOUNROLL for (int k = 0; k < n; ++k) {
     const int d = dim[k];
-    if (kind[k] == OBS_COMMAND) { FOR_LANE(i, d) out[o + i] = cmd ? cmd[i] : 0.f; o += d; continue; }
+    if (kind[k] == OBS_COMMAND) { FOR_LANE(i, d) EST(out + o + i, cmd ? cmd[i] : 0.f); o += d; continue; }
     const bool upd = (sim_step == 0) || (sim_step % itv[k] == 0);
     const int ro = raw_offset(m, kind[k]);
     FOR_LANE(i, d) {
       float v;
-      if (upd) { v = WS(W_RAW)[ro + i] * LDG(scale + k); cache[off[k] + i] = v; } else v = cache[off[k] + i];
-      out[o + i] = v;
+      if (upd) { v = WS(W_RAW)[ro + i] * LDG(scale + k); EST(cache + off[k] + i, v); } else v = ELD(cache + off[k] + i);
+      EST(out + o + i, v);
     }
     o += d;
   }
@@ -195,17 +206,17 @@ DEV_NOINLINE void build_state(const ModelDev& m, const EnvArrays& E, int env, fl
   SYNC();
   FOR_LANE(i, sd) {
     const float v = state[i];
-    if (reset) { for (int k = 0; k < ss; ++k) { buf[k * sd + i] = v; state[k * sd + i] = v; } }
+    if (reset) { for (int k = 0; k < ss; ++k) { EST(buf + k * sd + i, v); EST(state + k * sd + i, v); } }
     else {
-      NOUNROLL for (int k = ss - 1; k > 0; --k) { const float o = buf[(k - 1) * sd + i]; buf[k * sd + i] = o; state[k * sd + i] = o; }
-      buf[i] = v;
+      NOUNROLL for (int k = ss - 1; k > 0; --k) { const float o = ELD(buf + (k - 1) * sd + i); EST(buf + k * sd + i, o); EST(state + k * sd + i, o); }
+      EST(buf + i, v);
     }
   }
   concat_obs(m, E, env, ws, sim_step, false, cmd, state + ss * sd, lane);
   // command slots inside stacked frames carry the current command in every frame
   int o = 0;
   NOUNROLL for (int k = 0; k < MD(n_sobs); ++k) {
-    if (m.sobs_kind[k] == OBS_COMMAND) for (int f = 1; f < ss; ++f) FOR_LANE(i, m.sobs_dim[k]) state[f * sd + o + i] = cmd ? cmd[i] : 0.f;
+    if (m.sobs_kind[k] == OBS_COMMAND) for (int f = 1; f < ss; ++f) FOR_LANE(i, m.sobs_dim[k]) EST(state + f * sd + o + i, cmd ? cmd[i] : 0.f);
     o += m.sobs_dim[k];
   }
 }
