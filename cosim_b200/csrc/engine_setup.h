@@ -375,7 +375,7 @@ static inline int dim_by_name(const ModelDev& m, const std::string& n) {
     "frame_skip", "iterations", "ls_iterations", "ccd_iterations", "ncon_max", "hm_res_x", "hm_res_y", "state_dim", "stack_size",
     "stacked_dim", "nonstacked_dim", "command_dim", "n_term_body", "n_dofpos", "n_dofvel", "n_initnoise", "max_episode_steps",
     "lin_vel_f32", "n_sobs", "n_nobs", "cache_dim", "n_state_pos", "n_state_vel", "position_command", "nefc_max", "imu_body",
-    "n_massnoise", "base_body", "zero_noise", "auto_reset", "nfl", "nlimit_max"};
+    "n_massnoise", "base_body", "zero_noise", "auto_reset", "nfl", "nlimit_max", "npair", "condim", "cone", "solver"};
   if (n == "action_dim") return m.dims[CD_nu];
   for (int i = 0; i < CD__count; ++i) if (n == names[i]) return m.dims[i];
   return -1;

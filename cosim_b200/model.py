@@ -30,13 +30,13 @@ DIMS = ["nq", "nv", "nu", "nbody", "njnt", "ngeom", "nhullvert", "neq", "ground_
         "state_dim", "stack_size", "stacked_dim", "nonstacked_dim", "command_dim", "n_term_body", "n_dofpos",
         "n_dofvel", "n_initnoise", "max_episode_steps", "lin_vel_f32", "n_sobs", "n_nobs", "cache_dim",
         "n_state_pos", "n_state_vel", "position_command", "nefc_max", "imu_body", "n_massnoise", "base_body",
-        "zero_noise", "auto_reset", "nfl", "nlimit_max", "npair"]
+        "zero_noise", "auto_reset", "nfl", "nlimit_max", "npair", "condim", "cone", "solver"]
 OPTS = ["timestep", "gx", "gy", "gz", "tolerance", "ls_tolerance", "ccd_tolerance", "hf_sx", "hf_sy", "hf_sz",
         "hf_base", "z0", "hm_size_x", "hm_size_y", "hm_zmin", "term_threshold", "init_noise",
         "solref0", "solref1", "solimp0", "solimp1", "solimp2", "solimp3", "solimp4",
         "slide_lo", "slide_hi", "tors_lo", "tors_hi", "roll_lo", "roll_hi", "floss_lo", "floss_hi",
         "delay_lo", "delay_hi", "mass_noise", "load_lo", "load_hi", "kp_lo", "kp_hi", "kd_lo", "kd_hi",
-        "plane_sx", "plane_sy"]
+        "plane_sx", "plane_sy", "impratio"]
 DIM = {k: i for i, k in enumerate(DIMS)}
 OPT = {k: i for i, k in enumerate(OPTS)}
 
@@ -376,6 +376,8 @@ def build_model(config, ncon_max=None, auto_reset=False):
     # ---- precision (xml_manager.py:34-41, flamingo_p_v3.py:48-55)
     prec = rtab["precision"][rnd["precision"]]
     timestep, iterations, frame_skip = float(prec["timestep"]), int(prec["iterations"]), int(prec["frame_skip"])
+    if eng.get("iterations") is not None:        # solver iteration budget override (PGS needs many more sweeps than Newton needs iterations)
+        iterations = int(eng["iterations"])
     control_freq = 1.0 / (timestep * frame_skip)
     assert control_freq == 50, "Currently, only control frequency of 50 is supported."
 
@@ -528,7 +530,18 @@ def build_model(config, ncon_max=None, auto_reset=False):
     if ncon_max is None:
         ncon_max = min(1024, (50 if ground_type == 1 else 5) * ngeom + len(pair_geom))
     ncon_max = int(ncon_max)
-    nefc_max = 3 * neq + nfl_upper + nlimit_max + 4 * ncon_max
+    # Friction-cone / solver options of the general constraint path (MuJoCo <option cone= solver= impratio=>, geom condim).  The
+    # reference's four MJCF files all say condim 3 / pyramidal / Newton / impratio 1, which is the specialised fast path.
+    condim = int(eng.get("condim", 3))
+    if condim not in (1, 3, 4, 6):
+        raise ValueError("engine.condim must be 1, 3, 4 or 6")
+    cone = {"pyramidal": 0, "elliptic": 1}[str(eng.get("cone", "pyramidal")).lower()]
+    solver = {"newton": 0, "pgs": 1}[str(eng.get("solver", "newton")).lower()]
+    impratio = float(eng.get("impratio", 1.0))
+    if impratio <= 0:
+        raise ValueError("engine.impratio must be positive")
+    rows_per_contact = 1 if condim == 1 else (condim if cone == 1 else 2 * (condim - 1))
+    nefc_max = 3 * neq + nfl_upper + nlimit_max + rows_per_contact * ncon_max
 
     dims = np.zeros(64, np.int32)
     opts = np.zeros(64, np.float64)
@@ -553,7 +566,7 @@ def build_model(config, ncon_max=None, auto_reset=False):
          position_command=int(bool(config["env"]["position_command"])), nefc_max=nefc_max,
          imu_body=int(rb["imu_body"]), n_massnoise=len(massnoise_body), base_body=bname[spec.base_body],
          zero_noise=zero_noise, auto_reset=int(bool(eng.get("auto_reset", auto_reset))), nfl=nfl_upper,
-         nlimit_max=nlimit_max, npair=len(pair_geom))
+         nlimit_max=nlimit_max, npair=len(pair_geom), condim=condim, cone=cone, solver=solver)
     g = rb["gravity"]
     sl, tl, rl = _rng_pair(rnd["sliding_friction"]), _rng_pair(rnd["torsional_friction"]), _rng_pair(rnd["rolling_friction"])
     fl, dl, ld = _rng_pair(rnd["friction_loss"]), _rng_pair(rnd["action_delay_prob"]), _rng_pair(rnd["load"])
@@ -566,7 +579,7 @@ def build_model(config, ncon_max=None, auto_reset=False):
          slide_lo=sl[0], slide_hi=sl[1], tors_lo=tl[0], tors_hi=tl[1], roll_lo=rl[0], roll_hi=rl[1],
          floss_lo=fl[0], floss_hi=fl[1], delay_lo=dl[0], delay_hi=dl[1], mass_noise=float(rnd["mass_noise"]),
          load_lo=ld[0], load_hi=ld[1], kp_lo=kpr[0], kp_hi=kpr[1], kd_lo=kdr[0], kd_hi=kdr[1],
-         plane_sx=100.0, plane_sy=100.0)
+         plane_sx=100.0, plane_sy=100.0, impratio=impratio)
 
     def w0(a, fill=0.0):  # prepend the world body row
         a = np.asarray(a)

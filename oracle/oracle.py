@@ -35,6 +35,7 @@ def lib():
         L.orc_forward.argtypes = [ctypes.c_void_p]
         L.orc_substep.argtypes = [ctypes.c_void_p]
         L.orc_contacts.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int]
+        L.orc_contact_forces.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int]
         L.orc_philox.restype = ctypes.c_uint32
         L.orc_philox.argtypes = [ctypes.c_uint64] + [ctypes.c_uint32] * 4
         L.orc_philox_block.argtypes = [ctypes.c_uint32] * 6 + [ctypes.c_void_p]
@@ -152,6 +153,12 @@ class Oracle:
     def contacts(self, env=0, cap=256):
         out = np.zeros((cap, 10), dtype=np.float64)
         n = lib().orc_contacts(self.h, int(env), _p(out), cap)
+        return out[:min(n, cap)]
+
+    def contact_forces(self, env=0, cap=256):
+        """Per contact: force in the contact frame (normal, t1, t2, torsion, roll1, roll2), friction[5], condim."""
+        out = np.zeros((cap, 12), dtype=np.float64)
+        n = lib().orc_contact_forces(self.h, int(env), _p(out), cap)
         return out[:min(n, cap)]
 
 

@@ -18,6 +18,7 @@ struct IOracle {
   virtual void forward_all() = 0;
   virtual void substep_all() = 0;
   virtual int contacts(int env, double* out, int cap) = 0;
+  virtual int contact_forces(int env, double* out, int cap) = 0;
   virtual void rne_post_all() = 0;
   virtual double ray_hfield(double x, double y) = 0;
   virtual int convex_pair(const double* geoms, double* out) = 0;
@@ -125,6 +126,23 @@ template <class T> struct OracleT : IOracle {
     }
     return (int)d.con.size();
   }
+  // per contact: force in the contact frame (normal, t1, t2, torsion, roll1, roll2), friction[5], condim -> 12 doubles [upstream mj_contactForce]
+  int contact_forces(int env, double* out, int cap) override {
+    auto& d = E.envs[env]; int n = 0;
+    for (auto& c : d.con) {
+      if (n >= cap) break;
+      double* o = out + 12 * n++;
+      for (int k = 0; k < 12; ++k) o[k] = 0;
+      if (c.efc < 0) continue;
+      const T* f = &d.efc_force[c.efc];
+      if (c.dim == 1) o[0] = f[0];
+      else if (!E.elliptic()) { for (int k = 0; k < c.dim - 1; ++k) { o[0] += f[2 * k] + f[2 * k + 1]; o[1 + k] = (f[2 * k] - f[2 * k + 1]) * c.fric[k]; } }
+      else for (int k = 0; k < c.dim; ++k) o[k] = f[k];
+      for (int k = 0; k < 5; ++k) o[6 + k] = c.fric[k];
+      o[11] = c.dim;
+    }
+    return (int)d.con.size();
+  }
 };
 }  // namespace
 
@@ -144,6 +162,7 @@ int orc_set(void* h, const char* name, const double* in) { return ((IOracle*)h)-
 void orc_forward(void* h) { ((IOracle*)h)->forward_all(); }
 void orc_substep(void* h) { ((IOracle*)h)->substep_all(); }
 int orc_contacts(void* h, int env, double* out, int cap) { return ((IOracle*)h)->contacts(env, out, cap); }
+int orc_contact_forces(void* h, int env, double* out, int cap) { return ((IOracle*)h)->contact_forces(env, out, cap); }
 uint32_t orc_philox(uint64_t seed, uint32_t env, uint32_t stream, uint32_t step, uint32_t idx) { return orc::Philox::draw(seed, env, stream, step, idx); }
 void orc_philox_block(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t* out) {
   orc::Philox::gen(out, c0, c1, c2, c3, (uint64_t)k0 | ((uint64_t)k1 << 32));
