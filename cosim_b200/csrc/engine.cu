@@ -5,203 +5,13 @@
 #include <stdio.h>
 #include <string>
 #include <vector>
-#include "engine_env.h"
+#include "engine_kernels.cuh"
 #include "engine_setup.h"
 #include "../../include/cosim_b200.h"
 
 // ------------------------------------------------------------------------------------------ kernels
-extern __shared__ __align__(16) float g_smem[];
-
-// The model header (dims, opts, table pointers, workspace offsets: ~1.8 KB) is copied to shared memory once per
-// CTA so that the out-of-line device functions read it with LDS instead of generic loads from the param bank.
-#define MODEL_FLOATS ((int)((sizeof(ModelDev) + 15) / 16 * 4))
-// CTA prologue: copy the model header and the table arena to shared memory, re-point the table pointers at the copy
-#define CTA_PROLOGUE()                                                                                   \
-  {                                                                                                      \
-    const uint32_t* src_ = (const uint32_t*)&mp;                                                         \
-    uint32_t* dst_ = (uint32_t*)g_smem;                                                                  \
-    for (int i = threadIdx.x; i < (int)(sizeof(ModelDev) / 4); i += blockDim.x) dst_[i] = src_[i];       \
-    const uint4* asrc_ = (const uint4*)mp.arena_g;                                                       \
-    uint4* adst_ = (uint4*)(g_smem + MODEL_FLOATS);                                                      \
-    for (int i = threadIdx.x; i < mp.arena_bytes / 16; i += blockDim.x) adst_[i] = __ldg(asrc_ + i);     \
-    __syncthreads();                                                                                     \
-    for (int i = threadIdx.x; i < mp.nslots; i += blockDim.x)                                            \
-      *(const uint8_t**)((char*)g_smem + mp.slot_field[i]) = (const uint8_t*)adst_ + 16 * (size_t)mp.slot_off16[i]; \
-    __syncthreads();                                                                                     \
-  }                                                                                                      \
-  const ModelDev& m = *(const ModelDev*)g_smem;                                                          \
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb_ = blockDim.x >> 5;                    \
-  float* ws = g_smem + m.shared_floats + (size_t)warp * m.ws_floats;                                     \
-  /* global overflow slot of this resident warp (contact records beyond the shared-memory tier) */       \
-  if (lane == 0) *(float**)(ws + m.off[W_GPTR]) = m.gscratch + (size_t)(blockIdx.x * wpb_ + warp) * m.gslot_floats; \
-  __syncwarp();
-// The grid is sized to what is resident at once (engine.cu cosim_create); each CTA walks over chunks of wpb environments.
-#define FOR_ENV_CHUNKS() for (int env = blockIdx.x * wpb_ + warp; env - warp < E.N; env += gridDim.x * wpb_)
-
-__global__ void __launch_bounds__(640, 1) k_init(const __grid_constant__ ModelDev mp, const EnvArrays E) {
-  CTA_PROLOGUE();
-  FOR_ENV_CHUNKS() { if (env < E.N) init_env(m, E, env, ws, lane); __syncwarp(); }
-}
-__global__ void __launch_bounds__(640, 1) k_reset(const __grid_constant__ ModelDev mp, const EnvArrays E, const StepArgs a) {
-  CTA_PROLOGUE();
-  const int cd = MD(command_dim);
-  FOR_ENV_CHUNKS() {
-    if (env < E.N && !(a.mask && !a.mask[env]))
-      reset_env(m, E, env, ws, a.command ? a.command + (size_t)env * cd : nullptr, a.state_out + (size_t)env * MD(state_dim), lane);
-    __syncwarp();
-  }
-}
-// k_step: every warp of the CTA (also the padding warps of the last chunk) walks through the phase barriers.  Chunks of
-// wpb environments are claimed from a counter (dynamic: the cost of a chunk depends on what its robots are doing).
-__global__ void __launch_bounds__(640, 1) k_step(const __grid_constant__ ModelDev mp, const EnvArrays E, const StepArgs a, int* sched) {
-  CTA_PROLOGUE();
-  __shared__ int s_chunk;
-  const int nchunks = (E.N + wpb_ - 1) / wpb_;
-  for (;;) {
-    if (threadIdx.x == 0) s_chunk = atomicAdd(sched, 1);
-    __syncthreads();
-    const int chunk = s_chunk;
-    __syncthreads();
-    if (chunk >= nchunks) break;
-    const int env = chunk * wpb_ + warp, have_env = env < E.N;
-    step_env(m, E, have_env ? env : 0, ws, a, lane, have_env, 1);
-  }
-}
-// ---- pooled step kernel ----------------------------------------------------------------------------------------------
-// k_step above moves the wpb environments of a chunk through the stages of a sub-step in lock step: a stage lasts as long as
-// its slowest environment (a wheel touching down, a Newton solve that needs five iterations), and 35 - 65 % of the warp time
-// is spent waiting at the stage barriers (profiles/).  Here a CTA owns a POOL of P > wpb environments whose workspace images
-// live in global memory (L2-resident: 148 x P x ~10 KB), and a stage is a queue: every warp claims the next environment of the
-// pool, copies its image into its shared-memory slot, runs the stage, copies it back.  All warps of the SM still execute ONE
-// stage's code at a time (what the barriers were for: the instruction cache), but the barrier now ends a queue of P tasks
-// instead of one task per warp, and the tasks are started longest-first (duration of the same stage in the previous
-// sub-step).  Same arithmetic, same results as k_step.
-enum { SG_PRO = 0, SG_KIN, SG_COL, SG_SMO, SG_NEW, SG_EPI, POOL_MAX = 128 };
-struct PoolArgs { float* images; int P, img_floats, bounds, npools, mode; unsigned short* cost_g; };   // mode 0: stage queue, 1: sorted rounds (lock-step start); cost_g [N][4] stage durations carried from step to step
-// image = [workspace (ws_floats) | locals of the control step (16 floats, read / written in place)]
-enum { LOC_ACTIVE = 0, LOC_SIM_STEP, LOC_NSTEP, LOC_NOBS, LOC_RM, LOC_TABS, LOC_TSQ, LOC_TMAX, LOC_ITERS, LOC_FLOATS = 16 };
-__device__ __forceinline__ void ws_load(float* ws, const float* img, int nfl, int lane) {
-  const float4* src = (const float4*)img; float4* dst = (float4*)ws; const int n4 = nfl >> 2;
-  int i = lane;
-  for (; i + 7 * 32 < n4; i += 8 * 32) {          // eight 16-byte loads in flight per lane
-    float4 v[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) v[k] = __ldcg(src + i + 32 * k);
-#pragma unroll
-    for (int k = 0; k < 8; ++k) dst[i + 32 * k] = v[k];
-  }
-  for (; i < n4; i += 32) dst[i] = __ldcg(src + i);
-  __syncwarp();
-}
-__device__ __forceinline__ void ws_store(float* img, const float* ws, int nfl, int lane) {
-  float4* dst = (float4*)img; const float4* src = (const float4*)ws; const int n4 = nfl >> 2;
-  __syncwarp();
-#pragma unroll 4
-  for (int i = lane; i < n4; i += 32) __stcg(dst + i, src[i]);
-}
-__device__ __forceinline__ int stage_kind(int pos, int nst) { return pos == 0 ? SG_PRO : (pos == nst - 1 ? SG_EPI : 1 + ((pos - 1) & 3)); }
-__global__ void __launch_bounds__(640, 1) k_step_pool(const __grid_constant__ ModelDev mp, const EnvArrays E, const StepArgs a, int* sched, const PoolArgs pa) {
-  CTA_PROLOGUE();
-  __shared__ int s_pool, s_next;
-  __shared__ unsigned short s_cost[4][POOL_MAX];      // cycles >> 8 of the last KIN / COL / SMO / NEW group of every pool env
-  __shared__ unsigned char s_order[POOL_MAX];
-  const int fs = MD(frame_skip), nst = 2 + 4 * fs, wsf = m.ws_floats;
-  float* img0 = pa.images + (size_t)blockIdx.x * pa.P * pa.img_floats;
-  for (;;) {
-    if (threadIdx.x == 0) s_pool = atomicAdd(sched, 1);
-    __syncthreads();
-    const int pool = s_pool;
-    if (pool >= pa.npools) break;
-    const int base = pool * pa.P, n = min(pa.P, E.N - base);
-    for (int i = threadIdx.x; i < 4 * n; i += blockDim.x) s_cost[i & 3][i >> 2] = pa.cost_g[(size_t)base * 4 + i];      // durations of the previous control step
-    __syncthreads();
-    int pos = 0;
-    while (pos < nst) {
-      int gend = pos;           // the group of stages [pos, gend] runs back to back on one warp; a CTA-wide boundary follows it
-      while (gend < nst - 1 && !((pa.bounds >> stage_kind(gend, nst)) & 1)) ++gend;
-      const int k0 = stage_kind(pos, nst);
-      if ((int)threadIdx.x < n) {      // start order: longest first
-        const int t = threadIdx.x; int rank = t;
-        if (k0 >= SG_KIN && k0 <= SG_NEW) {
-          const unsigned short c = s_cost[k0 - 1][t]; rank = 0;
-          for (int j = 0; j < n; ++j) { const unsigned short cj = s_cost[k0 - 1][j]; rank += (cj > c) || (cj == c && j < t); }
-        }
-        s_order[rank] = (unsigned char)t;
-      }
-      if (threadIdx.x == 0) s_next = 0;
-      __syncthreads();
-#if defined(COSIM_PHASE_TIMING)
-      long long tw0 = clock64();
-#endif
-      for (int round = 0;; ++round) {
-        int i = 0;
-        if (pa.mode == 1) {         // sorted rounds: the wpb tasks of a round (similar predicted duration) start together
-          if (round > 0) __syncthreads();
-          if (round * wpb_ >= n) break;
-          i = round * wpb_ + warp;
-          if (i >= n) continue;
-        } else {
-          if (lane == 0) i = atomicAdd(&s_next, 1);
-          i = __shfl_sync(0xffffffffu, i, 0);
-          if (i >= n) break;
-        }
-        i = s_order[i];
-        const int env = base + i;
-        float* img = img0 + (size_t)i * pa.img_floats;
-        int* loc = (int*)(img + wsf); float* locf = img + wsf;
-        if (pos > 0) {
-          if (!__ldcg(loc + LOC_ACTIVE)) continue;        // the env was reset in the prologue: no step
-          ws_load(ws, img, wsf, lane);
-        }
-        const long long t0 = clock64();
-        int active = 1;
-        for (int st = pos; st <= gend && active; ++st) {
-          const int k = stage_kind(st, nst);
-          PH_DECL;
-          if (k == SG_PRO) {
-            if (lane == 0) *(float**)(ws + m.off[W_GPTR]) = m.gscratch + (size_t)(blockIdx.x * pa.P + i) * m.gslot_floats;
-            __syncwarp();
-            StepLocals L; step_prologue(m, E, env, ws, a, lane, L);
-            if (lane == 0) {
-              loc[LOC_ACTIVE] = L.active; loc[LOC_SIM_STEP] = L.sim_step; loc[LOC_NSTEP] = (int)L.nstep; loc[LOC_NOBS] = (int)L.nobs;
-              locf[LOC_RM] = L.rm; locf[LOC_TABS] = L.tabs; locf[LOC_TSQ] = L.tsq; locf[LOC_TMAX] = L.tmax; loc[LOC_ITERS] = 0;
-            }
-            __syncwarp();
-            active = L.active;
-          } else if (k == SG_KIN) { substep_pre(m, ws, lane); stage_kin(m, ws, lane); PH_MARK(PH_KIN); }
-          else if (k == SG_COL) { stage_collide(m, ws, lane); PH_MARK(PH_COLLIDE); }
-          else if (k == SG_SMO) { stage_smooth(m, ws, lane); }
-          else if (k == SG_NEW) {
-            int it = stage_newton(m, ws, lane);
-            PH_MARK(PH_NEWTON);
-            it = substep_post(m, ws, lane, it);
-            if (lane == 0) loc[LOC_ITERS] += it;
-            __syncwarp();
-          } else {
-            StepLocals L; L.active = 1; L.sim_step = loc[LOC_SIM_STEP]; L.nstep = (uint32_t)loc[LOC_NSTEP]; L.nobs = (uint32_t)loc[LOC_NOBS];
-            L.rm = locf[LOC_RM]; L.tabs = locf[LOC_TABS]; L.tsq = locf[LOC_TSQ]; L.tmax = locf[LOC_TMAX];
-            step_epilogue(m, E, env, ws, a, lane, L, loc[LOC_ITERS]);
-          }
-        }
-        if (k0 >= SG_KIN && k0 <= SG_NEW && lane == 0) { const long long d = (clock64() - t0) >> 8; s_cost[k0 - 1][i] = (unsigned short)(d > 65535 ? 65535 : d); }
-        if (gend < nst - 1 && active) ws_store(img, ws, wsf, lane);
-      }
-#if defined(COSIM_PHASE_TIMING)
-      { const long long tw1 = clock64(); __syncthreads();
-        if (lane == 0) { const int slot = k0 == SG_COL ? PH_WAIT_COLLIDE : (k0 == SG_NEW ? PH_WAIT_NEWTON : (k0 == SG_SMO ? PH_WAIT_SMOOTH : PH_WAIT_KIN));
-          atomicAdd(m.phase + slot, (unsigned long long)(clock64() - tw1)); atomicAdd(m.phase + PH_IO, (unsigned long long)(tw1 - tw0)); } }
-#else
-      __syncthreads();
-#endif
-      pos = gend + 1;
-    }
-    for (int i = threadIdx.x; i < 4 * n; i += blockDim.x) pa.cost_g[(size_t)base * 4 + i] = s_cost[i & 3][i >> 2];
-  }
-}
-__global__ void __launch_bounds__(640, 1) k_substep(const __grid_constant__ ModelDev mp, const EnvArrays E) {
-  CTA_PROLOGUE();
-  FOR_ENV_CHUNKS() { if (env < E.N) substep_env(m, E, env, ws, lane); __syncwarp(); }
-}
+// per-env kernels: engine_kernels.cuh, instantiated here without and in engine_gen.cu with the general constraint path
+KernelSet kernel_set_gen();
 __global__ void k_push(const __grid_constant__ ModelDev m, const EnvArrays E, const uint8_t* mask, const float* vel) {
   const int env = blockIdx.x * blockDim.x + threadIdx.x;
   if (env >= E.N) return;
@@ -242,6 +52,7 @@ struct cosim_handle {
   size_t smem = 0;
   int* sched = nullptr;                     // chunk counter of k_step (zeroed on the stream before every launch)
   PoolArgs pool = {nullptr, 0, 0, 0, 0, 0, nullptr};    // pooled step kernel (P = 0: off)
+  KernelSet k = {nullptr, nullptr, nullptr, nullptr, nullptr};      // the kernel instance this model runs on (with / without the general constraint path)
   std::string err;
   std::vector<void*> allocs;
   cudaStream_t stream = nullptr;            // used by cosim_step_host
@@ -303,17 +114,18 @@ int cosim_create(const void* blob, size_t nbytes, int num_envs, int device, uint
   // opt-in maximum once instead of to this handle's size (a second, smaller handle must not lower it for the first).
   int optin = 0; cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
   if ((size_t)optin < h->smem + 16) { fprintf(stderr, "cosim_create: %zu B of shared memory per CTA exceed the device limit %d\n", h->smem, optin); for (void* p : h->allocs) cudaFree(p); delete h; return COSIM_ERR_MODEL; }
-  cudaError_t e1 = cudaFuncSetAttribute(k_init, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 16);
-  cudaError_t e2 = cudaFuncSetAttribute(k_reset, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 16);
-  cudaError_t e3 = cudaFuncSetAttribute(k_step, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 16);
-  if (e3 == cudaSuccess) e3 = cudaFuncSetAttribute(k_substep, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 16);
-  cudaFuncSetAttribute(k_step, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  h->k = h->m.general ? kernel_set_gen() : kernel_set_fast();
+  cudaError_t e1 = cudaFuncSetAttribute(h->k.init, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 16);
+  cudaError_t e2 = cudaFuncSetAttribute(h->k.reset, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 16);
+  cudaError_t e3 = cudaFuncSetAttribute(h->k.step, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 16);
+  if (e3 == cudaSuccess) e3 = cudaFuncSetAttribute(h->k.substep, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 16);
+  cudaFuncSetAttribute(h->k.step, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) { fprintf(stderr, "cosim_create: cudaFuncSetAttribute failed: %s\n", cudaGetErrorString(e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3))); for (void* p : h->allocs) cudaFree(p); delete h; return COSIM_ERR_CUDA; }
   // grid = the CTAs that are resident at once (persistent CTAs walk over chunks of wpb environments); every resident warp
   // owns one global-memory slot for the contact records that do not fit its shared-memory tier
   {
     int per_sm = 0, nsm = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_step, 32 * h->wpb, h->smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, h->k.step, 32 * h->wpb, h->smem);
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device);
     if (per_sm < 1) per_sm = 1;
     if (nsm < 1) nsm = 148;
@@ -341,8 +153,8 @@ int cosim_create(const void* blob, size_t nbytes, int num_envs, int device, uint
           h->pool.bounds = (1 << SG_KIN) | (1 << SG_COL) | (1 << SG_SMO) | (1 << SG_NEW);
           { const char* e = getenv("COSIM_POOL_BOUNDS"); if (e) h->pool.bounds = atoi(e); }
           h->grid = h->pool.npools < grid_full ? h->pool.npools : grid_full;
-          cudaFuncSetAttribute(k_step_pool, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 16 - 2048);
-          cudaFuncSetAttribute(k_step_pool, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+          cudaFuncSetAttribute(h->k.step_pool, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 16 - 2048);
+          cudaFuncSetAttribute(h->k.step_pool, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         }
       }
       if (getenv("COSIM_PRINT_OCC")) fprintf(stderr, "cosim_create: pooled stepping %s (P = %d envs per CTA and stage queue, %d pools, boundaries 0x%x)\n", h->pool.P ? "on" : "off", h->pool.P, h->pool.npools, h->pool.bounds);
@@ -364,7 +176,7 @@ int cosim_create(const void* blob, size_t nbytes, int num_envs, int device, uint
     } catch (std::exception& e) { fprintf(stderr, "cosim_create: %s\n", e.what()); for (void* p : h->allocs) cudaFree(p); delete h; return COSIM_ERR_CUDA; }
   }
   cudaStreamCreate(&h->stream);     // blocking stream: ordered after work the caller queued on the legacy default stream (reset, set)
-  k_init<<<grid_for(h), 32 * h->wpb, h->smem, h->stream>>>(h->m, h->E);
+  { void* args[] = {&h->m, &h->E}; cudaLaunchKernel(h->k.init, dim3(grid_for(h)), dim3(32 * h->wpb), args, h->smem, h->stream); }
   h->launches++;
   cudaError_t e = cudaStreamSynchronize(h->stream);
   if (e == cudaSuccess) e = cudaGetLastError();
@@ -386,7 +198,7 @@ int cosim_reset(cosim_handle* h, const uint8_t* mask, const float* command, floa
   if (!h || !state_out) return COSIM_ERR_ARG;
   ON_DEVICE(h);
   StepArgs a = {nullptr, command, nullptr, state_out, nullptr, nullptr, mask};
-  k_reset<<<grid_for(h), 32 * h->wpb, h->smem, (cudaStream_t)stream>>>(h->m, h->E, a);
+  { void* args[] = {&h->m, &h->E, &a}; cudaLaunchKernel(h->k.reset, dim3(grid_for(h)), dim3(32 * h->wpb), args, h->smem, (cudaStream_t)stream); }
   h->launches++;
   CK(cudaGetLastError());
   return COSIM_OK;
@@ -398,8 +210,8 @@ int cosim_step(cosim_handle* h, const float* action, const float* command, const
   ON_DEVICE(h);
   StepArgs a = {action, command, user_command, state_out, terminated, truncated, nullptr};
   CK(cudaMemsetAsync(h->sched, 0, sizeof(int), (cudaStream_t)stream));
-  if (h->pool.P) k_step_pool<<<grid_for(h), 32 * h->wpb, h->smem, (cudaStream_t)stream>>>(h->m, h->E, a, h->sched, h->pool);
-  else k_step<<<grid_for(h), 32 * h->wpb, h->smem, (cudaStream_t)stream>>>(h->m, h->E, a, h->sched);
+  { void* args[] = {&h->m, &h->E, &a, &h->sched, &h->pool};       // k_step takes the first four
+    cudaLaunchKernel(h->pool.P ? h->k.step_pool : h->k.step, dim3(grid_for(h)), dim3(32 * h->wpb), args, h->smem, (cudaStream_t)stream); }
   h->launches++;
   CK(cudaGetLastError());
   return COSIM_OK;
@@ -431,7 +243,7 @@ int cosim_step_host(cosim_handle* h, const float* action_host, const float* comm
 int cosim_substep(cosim_handle* h, void* stream) {
   if (!h) return COSIM_ERR_ARG;
   ON_DEVICE(h);
-  k_substep<<<grid_for(h), 32 * h->wpb, h->smem, (cudaStream_t)stream>>>(h->m, h->E);
+  { void* args[] = {&h->m, &h->E}; cudaLaunchKernel(h->k.substep, dim3(grid_for(h)), dim3(32 * h->wpb), args, h->smem, (cudaStream_t)stream); }
   h->launches++;
   CK(cudaGetLastError());
   return COSIM_OK;

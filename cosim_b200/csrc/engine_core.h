@@ -23,6 +23,17 @@
 //   sensors/observe         <- mj_sensor*, _get_obs, StateBuildWrapper (K8)
 //   height_map              <- get_height_map + mj_rayHfield           (K9)
 #pragma once
+// COSIM_GENERAL = 1 compiles the general constraint path (engine_general.h) into the stage functions; the library builds its
+// kernels twice (engine.cu: 0, engine_gen.cu: 1) and picks per model, so the reference's condim 3 / pyramidal / Newton case
+// carries none of that code (it cost 4.7 % when it was a run-time branch of one kernel, profiles/r02_experiments.md).
+#ifndef COSIM_GENERAL
+#define COSIM_GENERAL 0
+#endif
+#if COSIM_GENERAL
+#define IF_GENERAL(m) ((m).general)
+#else
+#define IF_GENERAL(m) 0
+#endif
 #include <stdint.h>
 #include <math.h>
 #include <float.h>
@@ -51,13 +62,13 @@ static inline int __float_as_int_emu(float f) { int i; memcpy(&i, &f, 4); return
 static inline float __int_as_float_emu(int i) { float f; memcpy(&f, &i, 4); return f; }
 static inline int ctz32(unsigned x) { return __builtin_ctz(x); }
 #else
-#define DEV __device__ __forceinline__
+#define DEV static __device__ __forceinline__      /* internal linkage: engine.cu and engine_gen.cu compile different bodies */
 #define DEVM __device__ __forceinline__
-__device__ __forceinline__ int popc32(unsigned x) { return __popc(x); }
-__device__ __forceinline__ int __float_as_int_emu(float f) { return __float_as_int(f); }
-__device__ __forceinline__ float __int_as_float_emu(int i) { return __int_as_float(i); }
-__device__ __forceinline__ int ctz32(unsigned x) { return __ffs(x) - 1; }
-#define DEV_NOINLINE __device__ __noinline__
+static __device__ __forceinline__ int popc32(unsigned x) { return __popc(x); }
+static __device__ __forceinline__ int __float_as_int_emu(float f) { return __float_as_int(f); }
+static __device__ __forceinline__ float __int_as_float_emu(int i) { return __int_as_float(i); }
+static __device__ __forceinline__ int ctz32(unsigned x) { return __ffs(x) - 1; }
+#define DEV_NOINLINE static __device__ __noinline__
 #define LANES 32
 #define SYNC() __syncwarp()
 #define LDG(p) (*(p))          // small model tables: shared-memory copy of the arena (plain load; __ldg would fault)
@@ -183,7 +194,13 @@ struct ModelDev {
   // conservative culls ahead of the terrain narrow phase: max height per 8 x 8 block of cells, and per-geom bounding
   // cylinders (geom frame: centre, unit axis, radius, half length; radius 0 = none)
   const float* hf_max8; int hf_mrow, hf_mcol; const float* geom_bcyl;
+  // general constraint path (engine_general.h: condim 1 / 4 / 6, elliptic cone, PGS): on / off, row capacity, float offset of its
+  // region inside the env's global-memory slot (behind the contact-record overflow)
+  int general, gen_rows; unsigned long long gen_off;
 };
+// general path: contacts that get rows, and the floats of its region for NR rows of nv columns and NC contacts (layout: engine_general.h gen_view)
+enum { GEN_MAX_CON = 64, GEN_CON_STRIDE = 44 };
+static inline size_t gen_region_floats(int NR, int nv, int NC) { return (size_t)2 * NR * nv + (size_t)13 * NR + (size_t)NC * GEN_CON_STRIDE + 32; }
 #define MD(name) (m.dims[CD_##name])
 #define MO(name) (m.opts[CO_##name])
 
@@ -209,12 +226,12 @@ static_assert(W__COUNT <= 80, "ModelDev::off too small");
 // There is NO stored contact Jacobian: J v, J^T f and J^T W J are evaluated through the bodies (see "Jacobian-free rows").
 enum { CR_POS = 0, CR_FRAME = 3, CR_DIST = 12, CR_MU = 13, CR_BODY = 14, CR_GEOM = 15, CR_CELL = 16, CR_D = 17, CR_AREF = 18, CR_X = 22, CR_V = 26, CR_F = 30, CR_WF = 33, CR_WW = 39, CR_STRIDE = 45 };
 enum { RING_SIZE = 64 };
-// W_SCAL: [0] ground mu, [1] meaninertia, [2] delay_prob, [3] unused
+// W_SCAL: [0] ground mu, [1] meaninertia, [2] delay_prob, [3] unused, [4] torsional / [5] rolling friction draw of the env (general path only)
 // W_CNT (ints, warp-uniform counters kept in shared memory so they need not travel by reference through the out-of-line
 // calls): [0] contacts of the last forward pass, [1] contacts dropped in it, [2] NaN resets, [3] dropped in this control step
 // [4] ground contacts of the last pass (they come first; geom-geom contacts follow), [5] bit mask of the bodies that carry a contact
 // [6] bit mask of the bodies with ground contacts of their own
-enum { CNT_NCON = 0, CNT_DROPPED = 1, CNT_NAN = 2, CNT_DROPPED_STEP = 3, CNT_NCG = 4, CNT_CBMASK = 5, CNT_CBGMASK = 6 };
+enum { CNT_NCON = 0, CNT_DROPPED = 1, CNT_NAN = 2, CNT_DROPPED_STEP = 3, CNT_NCG = 4, CNT_CBMASK = 5, CNT_CBGMASK = 6, CNT_ROWS = 7 };      // [7]: "any constraint row" flag (general path: the row count), handed from stage_smooth to stage_newton
 
 // Per-env arrays in HBM: one row per env, rows contiguous (a warp reads its env's row coalesced).
 struct EnvArrays {
@@ -1674,6 +1691,7 @@ DEV_NOINLINE void make_constraint(const ModelDev& m, float* ws, int ncon, int la
     }
     WS(W_LM_SIGN)[j] = sign; WS(W_LM_D)[j] = D; WS(W_LM_AREF)[j] = aref;
   }
+  if (IF_GENERAL(m)) { SYNC(); return; }      // contact rows of the general path: gen_make_rows()
   // contacts: 4 pyramid edges share D = 1/(2 mu^2 R_first)
   if (ncon <= FEW_CONTACTS) {        // few contacts: explicit 3 x nv frame Jacobians in W_CN_J
     NOUNROLL for (int idx = lane; idx < ncon * nv; idx += LANES) {
@@ -1903,8 +1921,15 @@ DEV_NOINLINE float total_cost(const ModelDev& m, float* ws, int ncon, const floa
 static long g_emu_ls_evals = 0;      // analysis aid of the host emulation (tests/hostsim)
 #endif
 struct LSPoint { float alpha, cost, d0, d1; };
+#if COSIM_GENERAL
+DEV_NOINLINE RowSum gen_eval_rows(const ModelDev& m, const float* ws, int nefc, float a, int lane);      // engine_general.h
+#endif
 DEV_NOINLINE LSPoint ls_eval(const ModelDev& m, const float* ws, int ncon, float a, float q0, float q1, float q2, int lane) {
+#if COSIM_GENERAL
+  RowSum s = m.general ? gen_eval_rows(m, ws, ncon, a, lane) : eval_rows(m, ws, ncon, a, true, lane);       // general path: `ncon` carries the row count
+#else
   RowSum s = eval_rows(m, ws, ncon, a, true, lane);
+#endif
   PH_COUNT(PH_LS_EVALS, 1);
 #ifdef COSIM_HOST_EMU
   ++g_emu_ls_evals;
@@ -2189,11 +2214,14 @@ DEV_NOINLINE void sensors(const ModelDev& m, float* ws, int lane) {
   }
 }
 
+#if COSIM_GENERAL
+#include "engine_general.h"
+#endif
+
 // ------------------------------------------------------------------------------------------ forward + one sub-step
 // The forward pass in four stages.  They are separate functions because the pooled step kernel (engine.cu k_step_pool) runs a
 // stage for every environment of a CTA's pool before any environment enters the next one; forward() below strings them
 // together for one environment (with optional CTA-wide barriers in between).
-enum { CNT_ROWS = 7 };      // W_CNT[7]: "any constraint row" flag, handed from stage_smooth to stage_newton
 // stage 1: kinematics, spatial inertias, mass matrix and its Cholesky factor
 DEV void stage_kin(const ModelDev& m, float* ws, int lane) {
   const int nv = MD(nv);
@@ -2247,6 +2275,9 @@ DEV void stage_smooth(const ModelDev& m, float* ws, int lane) {
   // which sensors() and rne_bias() have consumed by now
   make_constraint(m, ws, ncon, lane);
   PH_MARK(PH_CONSTRAINT);
+#if COSIM_GENERAL
+  if (m.general) { gen_make_rows(m, ws, ncon, lane); return; }      // leaves the row count in W_CNT[CNT_ROWS]
+#endif
   // any constraint row?
   int rows = (ncon > 0) || (MD(neq) > 0);
   { int r = 0; FOR_LANE(k, nv) r |= (WS(W_FR_D)[k] > 0.f); FOR_LANE(j, njnt) r |= (WS(W_LM_SIGN)[j] != 0.f); rows |= wor(r); }
@@ -2255,7 +2286,11 @@ DEV void stage_smooth(const ModelDev& m, float* ws, int lane) {
 }
 // stage 4: constraint solve; returns the solver iterations
 DEV int stage_newton(const ModelDev& m, float* ws, int lane) {
+#if COSIM_GENERAL
+  const int iters = m.general ? gen_solve(m, ws, WSI(W_CNT)[CNT_NCON], lane) : newton_solve(m, ws, WSI(W_CNT)[CNT_NCON], WSI(W_CNT)[CNT_ROWS], lane);
+#else
   const int iters = newton_solve(m, ws, WSI(W_CNT)[CNT_NCON], WSI(W_CNT)[CNT_ROWS], lane);
+#endif
   PH_COUNT(PH_NEWTON_ITERS, iters);
   return iters;
 }
@@ -2355,6 +2390,7 @@ DEV_NOINLINE void cfrc_ext(const ModelDev& m, float* ws, int ncon, int lane) {
       const float* rec = CREC(c); const float* F = rec + CR_F; float wf[3], arm[3], tq[3];
       m3tmulv(wf, rec + CR_FRAME, F);
       v3sub(arm, rec + CR_POS, scom); v3cross(tq, arm, wf);
+      if (IF_GENERAL(m)) { float wt[3]; m3tmulv(wt, rec + CR_FRAME, rec + CR_WF); v3add(tq, tq, wt); }      // torsional / rolling moments (contact frame -> world)
       float* o = out + 6 * ((const int*)rec)[CR_BODY];
       for (int k = 0; k < 3; ++k) { o[k] += tq[k]; o[3 + k] += wf[k]; }
       const int b1 = contact_body1(m, ws, c);

@@ -39,6 +39,9 @@ DEV_NOINLINE void load_params(const ModelDev& m, const EnvArrays& E, int env, fl
   FOR_LANE(i, ng) WS(W_GMU)[i] = ELD(E.gmu + (size_t)env * ng + i);
   FOR_LANE(i, nu) { WS(W_KP)[i] = ELD(E.kp + (size_t)env * nu + i); WS(W_KD)[i] = ELD(E.kd + (size_t)env * nu + i); }
   FOR_LANE(i, 4) WS(W_SCAL)[i] = ELD(E.scal + (size_t)env * 4 + i);
+  // torsional / rolling friction of the env (xml_manager.py:57-75 writes them next to the sliding coefficient): the same draws
+  // init_env() makes, recomputed from the counter-based RNG -- only the general constraint path reads them
+  if (IF_GENERAL(m)) FOR_LANE(i, 2) WS(W_SCAL)[4 + i] = fmaf(uni(m, env, RNG_MODEL, 0, 1 + i), m.rnd_span[1 + i], m.rnd_lo[1 + i]);
 }
 DEV_NOINLINE void load_state(const ModelDev& m, const EnvArrays& E, int env, float* ws, int lane) {
   const int nq = MD(nq), nv = MD(nv);

@@ -240,7 +240,7 @@ static inline void build_model(const void* blob, size_t nbytes, uint64_t seed, u
     size[W_CVEL] = 6 * nb; size[W_CACC] = 6 * nb; size[W_CFRC] = 6 * nb; size[W_BUF] = 6 * nv;
     size[W_M] = nv * nv; size[W_A] = nv * nv; size[W_INVD] = nv;
     size[W_FSMOOTH] = size[W_ASMOOTH] = size[W_FCON] = size[W_GRAD] = size[W_SEARCH] = size[W_MV] = size[W_MA] = size[W_TMPV] = size[W_TMPW] = nv;
-    size[W_BMASS] = nb; size[W_INVWD] = nv; size[W_INVWB] = nb; size[W_FLOSS] = nv; size[W_GMU] = ng; size[W_SCAL] = 4;
+    size[W_BMASS] = nb; size[W_INVWD] = nv; size[W_INVWB] = nb; size[W_FLOSS] = nv; size[W_GMU] = ng; size[W_SCAL] = 8;
     size[W_FR_D] = nv; size[W_FR_AREF] = nv; size[W_LM_SIGN] = njnt; size[W_LM_D] = njnt; size[W_LM_AREF] = njnt;
     size[W_CN_REC] = K * m.cr_stride; size[W_GPTR] = 4; size[W_RING] = RING_SIZE + 20; size[W_BV] = 6 * nb; size[W_CSTART] = nb + 1; size[W_BS] = 21 * nb; size[W_CN_J] = FEW_CONTACTS * 3 * nv;
     size[W_EQ_J] = 3 * neq * nv; size[W_EQ_D] = size[W_EQ_AREF] = size[W_EQ_X] = size[W_EQ_V] = size[W_EQ_F] = 3 * neq;
@@ -300,6 +300,16 @@ static inline void build_model(const void* blob, size_t nbytes, uint64_t seed, u
     m.ws_floats = layout(K, m.off);
     m.gslot_floats = (unsigned long long)(((size_t)std::max(0, ncap - K) * m.cr_stride + 31) & ~(size_t)31);
     m.gscratch = nullptr;
+    // general constraint path (engine_general.h): anything but condim 3 / pyramidal / Newton / impratio 1
+    const int condim = m.dims[CD_condim];
+    m.general = ((condim == 1 || condim == 4 || condim == 6) || m.dims[CD_cone] == 1 || m.dims[CD_solver] == 1 || (opts[CO_impratio] > 0 && opts[CO_impratio] != 1.0)) ? 1 : 0;
+    m.gen_rows = 0; m.gen_off = m.gslot_floats;
+    if (m.general) {
+      const int cd = (condim == 1 || condim == 4 || condim == 6) ? condim : 3, rpc = cd == 1 ? 1 : (m.dims[CD_cone] == 1 ? cd : 2 * (cd - 1));
+      const int NC = std::min(ncap, (int)GEN_MAX_CON);
+      m.gen_rows = 3 * neq + nv + njnt + rpc * NC;
+      m.gslot_floats += (unsigned long long)((gen_region_floats(m.gen_rows, nv, NC) + 31) & ~(size_t)31);
+    }
   }
   // upload the arena and point the fields at it; CTA-shared area in front of the per-warp workspaces: [ModelDev copy | arena copy]
   if (arena.slots.size() > sizeof(m.slot_field) / sizeof(m.slot_field[0])) throw std::runtime_error("too many model tables for ModelDev::slot_field");

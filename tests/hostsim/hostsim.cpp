@@ -6,6 +6,7 @@
 // (`pytest -m "not gpu"`).  It is never loaded by the cosim_b200 package: the product path is
 // libcosim_b200.so (engine.cu) and fails loudly without a GPU.
 #define COSIM_HOST_EMU 1
+#define COSIM_GENERAL 1      // the emulation carries the general constraint path too (tests/test_cones.py)
 #ifndef _GNU_SOURCE
 #define _GNU_SOURCE
 #endif

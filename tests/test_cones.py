@@ -150,3 +150,63 @@ def test_resting_contact_supports_weight_general(eng):
     mg = m.sections["body_mass"].sum() * abs(m.opt("gz"))
     assert abs(f[:, 5].sum() - mg) / mg < 0.02
     assert abs(o.get("qvel")[0, :3]).max() < 0.05
+
+
+# ---- the engine's general constraint path (cosim_b200/csrc/engine_general.h) in the single-lane host emulation against the oracle
+GENERAL = [dict(condim=1), dict(condim=4), dict(condim=6), dict(cone="elliptic"), dict(cone="elliptic", condim=4),
+           dict(cone="elliptic", condim=6, impratio=3.0), dict(solver="pgs", iterations=200), dict(solver="pgs", cone="elliptic", condim=4, iterations=200)]
+
+
+@pytest.mark.parametrize("eng", GENERAL, ids=lambda e: "-".join(f"{k}{v}" for k, v in e.items()))
+@pytest.mark.parametrize("robot,terrain", [("flamingo_p_v3", "rocky_hard"), ("flamingo_light_v1", "flat")])
+def test_engine_general_path_matches_oracle(robot, terrain, eng):
+    """Teacher-forced sub-steps: the engine's general rows / cone / PGS code (fp32) against the fp64 oracle with the same options."""
+    from tests.hostsim.hostsim import HostSim
+    m = _model(robot, terrain, **eng)
+    N = 3
+    o, h = Oracle(m, N, seed=2), HostSim(m, N, seed=2)
+    np.testing.assert_allclose(h.reset(), o.reset(), atol=2e-5)
+    rng = np.random.default_rng(1)
+    errs, same_geo, ncon_seen, cap = [], [], 0, m.dim("ncon_max")
+    from tests.test_hostsim_vs_oracle import geometry_gap
+    for i in range(6):
+        o.step(rng.uniform(-1, 1, (N, m.dim("nu"))))
+        for s in range(2):
+            for k in ("qpos", "qvel", "qacc_warmstart", "torque"):
+                h.set(k, o.get(k))
+            o.substep(); h.substep()
+            assert (o.get("ncon")[:, 0].astype(int) == h.get("counters")[:, 7]).all()
+            ncon_seen += int(o.get("ncon").sum())
+            err = np.abs(o.get("qvel") - h.get("qvel")).max(axis=1)
+            errs.append(err)
+            cg_all = h.get("contacts").reshape(N, cap, 10)
+            for e in range(N):          # a sub-step may be far off only where the fp32 MPR returned another contact geometry (as in test_hostsim_vs_oracle)
+                co = o.contacts(e, cap); dd, dn = geometry_gap(co, cg_all[e, :len(co)])
+                if dd < 2e-6 and dn < 1e-4:
+                    same_geo.append(err[e])
+    errs, same_geo = np.concatenate(errs), np.array(same_geo)
+    assert ncon_seen > 0
+    tol = 5e-3 if eng.get("solver") == "pgs" else 1e-3          # PGS stops on a cost decrease of 1e-8: its answer is looser in fp32
+    assert np.median(errs) < tol / 5 and len(same_geo) >= 0.3 * len(errs) and same_geo.max() < 2 * tol, \
+        f"qvel error median {np.median(errs):.1e}, same-geometry sub-steps {len(same_geo)}/{len(errs)} worst {same_geo.max():.1e}"
+
+
+def test_engine_general_cfrc_ext_and_friction_draws():
+    """cfrc_ext (used by the termination test) includes the torsional / rolling moments; the per-env torsional and rolling
+    coefficients come from the same counter-based draws as the oracle's randomization."""
+    from tests.hostsim.hostsim import HostSim
+    from cosim_b200.config import RANDOM_FULL
+    m = build_model(make_config("flamingo_light_v1", "flat", random=RANDOM_FULL, engine=dict(cone="elliptic", condim=6)))
+    N = 4
+    o, h = Oracle(m, N, seed=9), HostSim(m, N, seed=9)
+    o.reset(); h.reset()
+    rng = np.random.default_rng(4)
+    for i in range(8):
+        o.step(rng.uniform(-1, 1, (N, m.dim("nu"))))
+    v = o.get("qvel"); v[:, 5] += 2.0; o.set("qvel", v)         # spin: torsional rows carry force
+    for k in ("qpos", "qvel", "qacc_warmstart", "torque"):
+        h.set(k, o.get(k))
+    o.substep(); h.substep(); o.rne_post()
+    assert (o.get("ncon")[:, 0].astype(int) == h.get("counters")[:, 7]).all() and o.get("ncon").sum() > 0
+    cf_o, cf_h = o.get("cfrc_ext"), h.get("cfrc_ext")
+    np.testing.assert_allclose(cf_h, cf_o, atol=2e-3 * max(1.0, np.abs(cf_o).max()))
