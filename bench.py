@@ -398,8 +398,10 @@ def main():
                    "path": "BatchedEnv.step_policy_pipelined: pinned host commands -> device, tcgen05 policy on the device state, cosim_step, state + done flags -> "
                            "pinned host on a copy stream (double-buffered, overlaps the next step), one event wait per step"},
            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": measured_traffic(N, args.config),
-                        "kernel": "k_step", "kernel_ms": kernel_ms, "bytes_per_env_step": b_alg, "peak_source": peak_src,
+                        "kernel": "k_step_pool" if getattr(env, "pooled", False) else "k_step", "kernel_ms": kernel_ms, "bytes_per_env_step": b_alg, "peak_source": peak_src,
                         "issue": issue_metrics(N, args.config), "policy_kernel": policy_metrics(),
+                        "fp32_pipe_frac": (lambda t: None if not t or t.get("fp32_pipe_fma_pct") is None else t["fp32_pipe_fma_pct"] / 100.0)(issue_metrics(N, args.config)),
+                        "tensor_pipe_frac": (lambda t: None if not t or t.get("tensor_pipe_active_pct") is None else t["tensor_pipe_active_pct"] / 100.0)(policy_metrics()),
                         "note": "the step is bound by instruction issue / dependent-latency stalls of the warp-per-env solver and by phase-barrier waits, not by HBM (DESIGN.md section 3.2)"},
            "reporter_stats": {k: window_stats[k] for k in ("steps", "episodes", "success_rate", "termination_rate", "mean_abs_err_lin_vel_x",
                                                            "mean_abs_err_ang_vel_yaw", "mean_contacts", "mean_solver_iters_per_step", "nan_resets", "ncon_dropped")}}

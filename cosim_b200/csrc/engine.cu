@@ -347,5 +347,7 @@ int cosim_dim(const cosim_handle* h, const char* name) { return (h && name) ? se
 int cosim_launch_count(const cosim_handle* h) { return h ? h->launches : COSIM_ERR_ARG; }
 int cosim_smem_bytes_per_env(const cosim_handle* h) { return h ? h->m.ws_floats * 4 : COSIM_ERR_ARG; }
 int cosim_warps_per_block(const cosim_handle* h) { return h ? h->wpb : COSIM_ERR_ARG; }
+int cosim_pool_size(const cosim_handle* h) { return h ? h->pool.P : COSIM_ERR_ARG; }
+int cosim_general_path(const cosim_handle* h) { return h ? h->m.general : COSIM_ERR_ARG; }
 
 }  // extern "C"

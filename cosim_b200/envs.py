@@ -316,6 +316,16 @@ class BatchedEnv:
     def render(self):
         pass
 
+    @property
+    def pooled(self):
+        """True when the model is stepped by the pooled kernel (k_step_pool: stage queues over a pool of envs per CTA)."""
+        return self._L.cosim_pool_size(self._h) > 0
+
+    @property
+    def general_path(self):
+        """True when the model's friction-cone / solver options select the general constraint path (engine_general.h)."""
+        return self._L.cosim_general_path(self._h) > 0
+
     def close(self):
         if getattr(self, "_h", None) is not None and self._h:
             self._L.cosim_destroy(self._h)

@@ -104,6 +104,8 @@ def lib():
     L.cosim_launch_count.argtypes = [vp]
     L.cosim_smem_bytes_per_env.argtypes = [vp]
     L.cosim_warps_per_block.argtypes = [vp]
+    L.cosim_pool_size.argtypes = [vp]
+    L.cosim_general_path.argtypes = [vp]
     if hasattr(L, "cosim_policy_create"):
         L.cosim_policy_create.argtypes = [i32, i32, vp, vp, vp, i32, ctypes.POINTER(vp)]
         L.cosim_policy_destroy.argtypes = [vp]
@@ -118,5 +120,5 @@ def lib():
 EXPORTS = ["cosim_create", "cosim_destroy", "cosim_last_error", "cosim_reset", "cosim_step", "cosim_step_host",
            "cosim_push", "cosim_substep", "cosim_field_dim", "cosim_field_is_int", "cosim_get", "cosim_set", "cosim_set_debug",
            "cosim_stats_reduce", "cosim_stats_clear", "cosim_rng_probe", "cosim_num_envs", "cosim_dim",
-           "cosim_launch_count", "cosim_smem_bytes_per_env", "cosim_warps_per_block",
+           "cosim_launch_count", "cosim_smem_bytes_per_env", "cosim_warps_per_block", "cosim_pool_size", "cosim_general_path",
            "cosim_policy_create", "cosim_policy_destroy", "cosim_policy_forward", "cosim_policy_launch_count", "cosim_lstm_cell"]

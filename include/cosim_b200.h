@@ -84,6 +84,8 @@ int cosim_dim(const cosim_handle* h, const char* name);      /* "state_dim", "ac
 int cosim_launch_count(const cosim_handle* h);               /* kernels launched so far */
 int cosim_smem_bytes_per_env(const cosim_handle* h);
 int cosim_warps_per_block(const cosim_handle* h);
+int cosim_pool_size(const cosim_handle* h);                  /* environments per CTA of the pooled step kernel; 0 = lock-step kernel */
+int cosim_general_path(const cosim_handle* h);               /* 1 = the model runs on the general constraint path (condim 1/4/6, elliptic cone, PGS, impratio) */
 
 /* ---- policy MLP (core/policy.py:11-21 MLPPolicy.get_action: clip(MLP(state), -1, 1)) ---- */
 typedef struct cosim_policy cosim_policy;

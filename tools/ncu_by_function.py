@@ -8,7 +8,7 @@ funcs = []
 for l in txt.splitlines():
     m = re.match(r"\s*0x[0-9a-f]+\s+(0x[0-9a-f]+|0)\s+(0x[0-9a-f]+|0)\s+0x2\s+\S+\s+\S+\s+\$(\S+?)\$(\S+)", l)
     if m and kern in m.group(3):
-        funcs.append((int(m.group(1), 16), int(m.group(2), 16), re.sub(r"^_Z\d+", "", m.group(4))[:28]))
+        funcs.append((int(m.group(1), 16), int(m.group(2), 16), re.sub(r"^_ZN\d+_INTERNAL_[0-9a-f]+_\d+_\w+?_cu_[0-9a-f]{8}\d+|^_Z\d+", "", m.group(4))[:28]))
 funcs.sort()
 rows = list(csv.reader(open(sass_csv)))
 hdr = rows[1]
