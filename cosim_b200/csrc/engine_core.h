@@ -197,6 +197,8 @@ struct ModelDev {
   // general constraint path (engine_general.h: condim 1 / 4 / 6, elliptic cone, PGS): on / off, row capacity, float offset of its
   // region inside the env's global-memory slot (behind the contact-record overflow)
   int general, gen_rows; unsigned long long gen_off;
+  // box-box pairs (mjc_BoxBox: up to 8 contacts): scratch of 32 x 56 floats in the env's global-memory slot, offset bb_off (0 pairs: unused)
+  int n_boxbox; unsigned long long bb_off;
 };
 // general path: contacts that get rows, and the floats of its region for NR rows of nv columns and NC contacts (layout: engine_general.h gen_view)
 enum { GEN_MAX_CON = 64, GEN_CON_STRIDE = 44 };
@@ -1361,6 +1363,111 @@ DEV void fix_normal(const ModelDev& m, const float* ws, int g1, int g2, const fl
   v3scl(normal, acc, 1.f / nn);
 }
 
+// ------------------------------------------------------------------------------------------ box-box (mjc_BoxBox)
+// Restates oracle/oracle.hpp box_box (separating axes: 3 + 3 face normals, 9 edge-edge directions with the faces preferred by a
+// factor 1.05; face contact = incident face clipped against the reference rectangle, up to 8 points; edge-edge = one point).
+// out[k] = pos(3), normal(3), dist; positions relative to the caller's origin (p1 / p2 are given in that frame).
+DEV int clip_rect_quad(const float* h, const float* quad, float* ret) {
+  int nq = 4, nr = 0; float buf[16]; const float* q = quad; float* r = ret;
+  for (int dir = 0; dir <= 1; ++dir) for (int sign = -1; sign <= 1; sign += 2) {
+    const float* pq = q; float* pr = r; nr = 0; bool full = false;
+    for (int i = nq; i > 0 && !full; --i) {
+      if (sign * pq[dir] < h[dir]) { pr[0] = pq[0]; pr[1] = pq[1]; pr += 2; ++nr; if (nr & 8) { full = true; break; } }
+      const float* nextq = (i > 1) ? pq + 2 : q;
+      if ((sign * pq[dir] < h[dir]) ^ (sign * nextq[dir] < h[dir])) {
+        pr[1 - dir] = pq[1 - dir] + (nextq[1 - dir] - pq[1 - dir]) / (nextq[dir] - pq[dir]) * (sign * h[dir] - pq[dir]);
+        pr[dir] = sign * h[dir]; pr += 2; ++nr; if (nr & 8) { full = true; break; }
+      }
+      pq += 2;
+    }
+    q = r;
+    if (full) { dir = 2; break; }
+    r = (q == ret) ? buf : ret; nq = nr;
+  }
+  if (q != ret) for (int i = 0; i < 2 * nr; ++i) ret[i] = q[i];
+  return nr;
+}
+DEV_NOINLINE int box_box(const float* p1, const float* R1, const float* A, const float* p2, const float* R2, const float* B, float* out) {
+  const float fudge = 1.05f, eps = 1e-6f;
+  float p[3], pp[3], Rm[3][3], Q[3][3], a1[3][3], a2[3][3];
+  v3sub(p, p2, p1);
+  for (int j = 0; j < 3; ++j) { a1[j][0] = R1[j]; a1[j][1] = R1[3 + j]; a1[j][2] = R1[6 + j]; a2[j][0] = R2[j]; a2[j][1] = R2[3 + j]; a2[j][2] = R2[6 + j]; }
+  for (int i = 0; i < 3; ++i) { pp[i] = v3dot(a1[i], p); for (int j = 0; j < 3; ++j) { Rm[i][j] = v3dot(a1[i], a2[j]); Q[i][j] = fabsf(Rm[i][j]); } }
+  float s = -INFINITY, normal[3] = {0.f, 0.f, 0.f}; int code = 0; bool invert = false;
+  for (int i = 0; i < 3; ++i) {
+    const float e = pp[i], s2 = fabsf(e) - (A[i] + B[0] * Q[i][0] + B[1] * Q[i][1] + B[2] * Q[i][2]);
+    if (s2 > 0.f) return 0;
+    if (s2 > s) { s = s2; v3copy(normal, a1[i]); invert = e < 0.f; code = 1 + i; }
+  }
+  for (int j = 0; j < 3; ++j) {
+    const float e = v3dot(a2[j], p), s2 = fabsf(e) - (A[0] * Q[0][j] + A[1] * Q[1][j] + A[2] * Q[2][j] + B[j]);
+    if (s2 > 0.f) return 0;
+    if (s2 > s) { s = s2; v3copy(normal, a2[j]); invert = e < 0.f; code = 4 + j; }
+  }
+  for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) {
+    const float r[3] = {Rm[0][j], Rm[1][j], Rm[2][j]}; float n[3] = {0.f, 0.f, 0.f};
+    const int i1 = (i + 1) % 3, i2 = (i + 2) % 3, j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+    n[i1] = -r[i2]; n[i2] = r[i1];
+    const float e = pp[0] * n[0] + pp[1] * n[1] + pp[2] * n[2];
+    float s2 = fabsf(e) - (A[i1] * (Q[i2][j] + eps) + A[i2] * (Q[i1][j] + eps) + B[j1] * (Q[i][j2] + eps) + B[j2] * (Q[i][j1] + eps));
+    if (s2 > eps) return 0;
+    const float l = sqrtf(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+    if (l > eps) {
+      s2 /= l;
+      if (s2 * fudge > s) { s = s2; for (int k = 0; k < 3; ++k) normal[k] = (a1[0][k] * n[0] + a1[1][k] * n[1] + a1[2][k] * n[2]) / l; invert = e < 0.f; code = 7 + 3 * i + j; }
+    }
+  }
+  if (!code) return 0;
+  if (invert) { normal[0] = -normal[0]; normal[1] = -normal[1]; normal[2] = -normal[2]; }
+  const float depth = -s;
+  if (code > 6) {
+    float pa[3], pb[3]; v3copy(pa, p1); v3copy(pb, p2);
+    for (int j = 0; j < 3; ++j) { const float sg = v3dot(normal, a1[j]) > 0.f ? 1.f : -1.f; v3addscl(pa, pa, a1[j], sg * A[j]); }
+    for (int j = 0; j < 3; ++j) { const float sg = v3dot(normal, a2[j]) > 0.f ? -1.f : 1.f; v3addscl(pb, pb, a2[j], sg * B[j]); }
+    const float* ua = a1[(code - 7) / 3]; const float* ub = a2[(code - 7) % 3];
+    float dp[3]; v3sub(dp, pb, pa);
+    const float uaub = v3dot(ua, ub), q1 = v3dot(ua, dp), q2 = -v3dot(ub, dp), dd = 1.f - uaub * uaub;
+    float alpha = 0.f, beta = 0.f;
+    if (dd > 1e-4f) { alpha = (q1 + uaub * q2) / dd; beta = (uaub * q1 + q2) / dd; }
+    v3addscl(pa, pa, ua, alpha); v3addscl(pb, pb, ub, beta);
+    for (int k = 0; k < 3; ++k) { out[k] = 0.5f * (pa[k] + pb[k]); out[3 + k] = normal[k]; }
+    out[6] = -depth;
+    return 1;
+  }
+  const bool first = code <= 3;
+  const float (*Aa)[3] = first ? a1 : a2; const float (*Ab)[3] = first ? a2 : a1;
+  const float* pa = first ? p1 : p2; const float* pb = first ? p2 : p1; const float* Sa = first ? A : B; const float* Sb = first ? B : A;
+  float n2[3]; for (int k = 0; k < 3; ++k) n2[k] = first ? normal[k] : -normal[k];
+  float nr[3], anr[3]; for (int j = 0; j < 3; ++j) { nr[j] = v3dot(Ab[j], n2); anr[j] = fabsf(nr[j]); }
+  int lanr, b1, b2;
+  if (anr[1] > anr[0]) { if (anr[1] > anr[2]) { b1 = 0; lanr = 1; b2 = 2; } else { b1 = 0; b2 = 1; lanr = 2; } }
+  else { if (anr[0] > anr[2]) { lanr = 0; b1 = 1; b2 = 2; } else { b1 = 0; b2 = 1; lanr = 2; } }
+  float center[3];
+  for (int k = 0; k < 3; ++k) center[k] = pb[k] - pa[k] + (nr[lanr] < 0.f ? 1.f : -1.f) * Sb[lanr] * Ab[lanr][k];
+  const int codeN = first ? code - 1 : code - 4, c1i = codeN == 0 ? 1 : 0, c2i = codeN == 2 ? 1 : 2;
+  const float c1 = v3dot(center, Aa[c1i]), c2 = v3dot(center, Aa[c2i]);
+  const float m11 = v3dot(Aa[c1i], Ab[b1]), m12 = v3dot(Aa[c1i], Ab[b2]), m21 = v3dot(Aa[c2i], Ab[b1]), m22 = v3dot(Aa[c2i], Ab[b2]);
+  const float k1 = m11 * Sb[b1], k2 = m21 * Sb[b1], k3 = m12 * Sb[b2], k4 = m22 * Sb[b2];
+  const float quad[8] = {c1 - k1 - k3, c2 - k2 - k4, c1 - k1 + k3, c2 - k2 + k4, c1 + k1 + k3, c2 + k2 + k4, c1 + k1 - k3, c2 + k2 - k4};
+  const float rect[2] = {Sa[c1i], Sa[c2i]};
+  float ret[16];
+  const int n = clip_rect_quad(rect, quad, ret);
+  if (n < 1) return 0;
+  const float det1 = 1.f / (m11 * m22 - m12 * m21);
+  int cnum = 0;
+  for (int j = 0; j < n && cnum < 8; ++j) {
+    const float kk1 = (m22 * (ret[2 * j] - c1) - m12 * (ret[2 * j + 1] - c2)) * det1, kk2 = (-m21 * (ret[2 * j] - c1) + m11 * (ret[2 * j + 1] - c2)) * det1;
+    float pt[3]; for (int k = 0; k < 3; ++k) pt[k] = center[k] + kk1 * Ab[b1][k] + kk2 * Ab[b2][k];
+    const float dep = Sa[codeN] - v3dot(n2, pt);
+    if (dep >= 0.f) {
+      float* o = out + 7 * cnum;
+      for (int k = 0; k < 3; ++k) { o[k] = pt[k] + pa[k] + n2[k] * dep * 0.5f; o[3 + k] = normal[k]; }
+      o[6] = -dep; ++cnum;
+    }
+  }
+  return cnum;
+}
+
 // ------------------------------------------------------------------------------------------ geom-geom (self) collision
 // mj_collideGeoms -> mj_filterSphere -> mjc_Convex restated (oracle/oracle.hpp collide_pairs is the serial version), different
 // schedule: (1) a lane per candidate pair runs a separating-axis cull on the two geom-frame bounding boxes (conservative: it
@@ -1414,6 +1521,7 @@ DEV_NOINLINE void collide_pairs(const ModelDev& m, float* ws, int lane) {
     NOUNROLL for (int k0 = 0; k0 < nc; k0 += LANES / gs) {
       const int k = k0 + lane / gs;           // k-th surviving pair of this chunk (pair order)
       int hit = 0, g1 = 0, g2 = 0; float depth = 0.f, nrm[3] = {0.f, 0.f, 0.f}, cp[3] = {0.f, 0.f, 0.f};
+      float* bbout = nullptr; float bbx = 0.f, bby = 0.f;          // box-box pair: `hit` = number of contacts waiting in the lane's scratch block
       if (k < nc) {
         unsigned mm = cmask; for (int i = 0; i < k; ++i) mm &= mm - 1;
         const int pp = p0 + ctz32(mm);
@@ -1427,7 +1535,16 @@ DEV_NOINLINE void collide_pairs(const ModelDev& m, float* ws, int lane) {
         const float gc[3] = {(x2[0] - ox) + r2[0], (x2[1] - oy) + r2[1], x2[2] + r2[2]};
         const float dv[3] = {gc[0] - A.c[0], gc[1] - A.c[1], gc[2] - A.c[2]};
         const float bound = LDG(m.geom_rbound + g1) + LDG(m.geom_rbound + g2);
-        if (v3dot(dv, dv) <= bound * bound) {      // mj_filterSphere, margin 0
+        if (v3dot(dv, dv) <= bound * bound && m.geom_type[g1] == GEOM_BOX && m.geom_type[g2] == GEOM_BOX) {      // mjc_BoxBox: up to 8 contacts, one lane
+          if (sub == 0) {
+            bbout = *(float* const*)(ws + m.off[W_GPTR]) + m.bb_off + 56 * lane;
+            const float q1[3] = {0.f, 0.f, x1[2]}, q2[3] = {x2[0] - ox, x2[1] - oy, x2[2]};      // frame centred on geom 1 in x, y
+            const float sA[3] = {LDG(m.geom_size + 3 * g1), LDG(m.geom_size + 3 * g1 + 1), LDG(m.geom_size + 3 * g1 + 2)};
+            const float sB[3] = {LDG(m.geom_size + 3 * g2), LDG(m.geom_size + 3 * g2 + 1), LDG(m.geom_size + 3 * g2 + 2)};
+            hit = box_box(q1, WS(W_GXMAT) + 9 * g1, sA, q2, WS(W_GXMAT) + 9 * g2, sB, bbout);
+            bbx = ox; bby = oy;
+          }
+        } else if (v3dot(dv, dv) <= bound * bound) {      // mj_filterSphere, margin 0
           // temporal coherence: the direction along which MPR last found this pair separated (kept in geom 1's frame, so
           // it follows the robot).  If the two supports still leave a gap the pair cannot intersect and the query is
           // skipped; a stale or useless axis only fails this test, so the cull is conservative like the ones above.
@@ -1459,10 +1576,16 @@ DEV_NOINLINE void collide_pairs(const ModelDev& m, float* ws, int lane) {
 #ifdef COSIM_HOST_EMU
       const int nhit = hit, slot = ncon;
 #else
-      const unsigned hits = __ballot_sync(0xffffffffu, hit);
-      const int nhit = __popc(hits), slot = ncon + __popc(hits & ((1u << lane) - 1u));
+      int incl = hit;          // contacts are appended in pair order: exclusive prefix sum of the per-lane counts
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+      const int nhit = __shfl_sync(0xffffffffu, incl, 31), slot = ncon + incl - hit;
 #endif
-      if (hit && slot < MD(ncon_max)) write_contact(m, ws, slot, cp, nrm, -depth, fmaxf(WS(W_GMU)[g1], WS(W_GMU)[g2]), m.geom_body[g2], g2, -2 - g1);
+      if (hit && !bbout) { if (slot < MD(ncon_max)) write_contact(m, ws, slot, cp, nrm, -depth, fmaxf(WS(W_GMU)[g1], WS(W_GMU)[g2]), m.geom_body[g2], g2, -2 - g1); }
+      else NOUNROLL for (int c = 0; c < hit; ++c) if (slot + c < MD(ncon_max)) {
+        const float* o = bbout + 7 * c; const float wp[3] = {o[0] + bbx, o[1] + bby, o[2]};
+        write_contact(m, ws, slot + c, wp, o + 3, o[6], fmaxf(WS(W_GMU)[g1], WS(W_GMU)[g2]), m.geom_body[g2], g2, -2 - g1);
+      }
       const int room = imax(0, MD(ncon_max) - ncon);
       dropped += imax(0, nhit - room); ncon += imin(nhit, room);
       SYNC();       // cached axes written above are read by the next chunk's candidate test

@@ -302,6 +302,12 @@ static inline void build_model(const void* blob, size_t nbytes, uint64_t seed, u
     m.gscratch = nullptr;
     // general constraint path (engine_general.h): anything but condim 3 / pyramidal / Newton / impratio 1
     const int condim = m.dims[CD_condim];
+    { // box-box pairs get a scratch block per lane for their up to 8 contacts
+      std::vector<int> pg = section<int>(blob, "pair_geom"), gt = section<int>(blob, "geom_type");
+      m.n_boxbox = 0; for (size_t i = 0; i + 1 < pg.size(); i += 2) m.n_boxbox += (gt[pg[i]] == 6 && gt[pg[i + 1]] == 6);
+      m.bb_off = m.gslot_floats;
+      if (m.n_boxbox) m.gslot_floats += 32 * 56;
+    }
     m.general = ((condim == 1 || condim == 4 || condim == 6) || m.dims[CD_cone] == 1 || m.dims[CD_solver] == 1 || (opts[CO_impratio] > 0 && opts[CO_impratio] != 1.0)) ? 1 : 0;
     m.gen_rows = 0; m.gen_off = m.gslot_floats;
     if (m.general) {

@@ -528,7 +528,8 @@ def build_model(config, ncon_max=None, auto_reset=False):
     if ncon_max is None:
         ncon_max = eng.get("ncon_max")
     if ncon_max is None:
-        ncon_max = min(1024, (50 if ground_type == 1 else 5) * ngeom + len(pair_geom))
+        n_boxbox = int(sum(1 for a, b in pair_geom if rb["geom_type"][a] == 6 and rb["geom_type"][b] == 6))      # mjc_BoxBox: up to 8 contacts
+        ncon_max = min(1024, (50 if ground_type == 1 else 5) * ngeom + len(pair_geom) + 7 * n_boxbox)
     ncon_max = int(ncon_max)
     # Friction-cone / solver options of the general constraint path (MuJoCo <option cone= solver= impratio=>, geom condim).  The
     # reference's four MJCF files all say condim 3 / pyramidal / Newton / impratio 1, which is the specialised fast path.

@@ -43,6 +43,7 @@ def lib():
         L.orc_ray_hfield.restype = ctypes.c_double
         L.orc_ray_hfield.argtypes = [ctypes.c_void_p, ctypes.c_double, ctypes.c_double]
         L.orc_convex_pair.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+        L.orc_box_box.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
         L.orc_norm_ppf.restype = ctypes.c_double
         L.orc_norm_ppf.argtypes = [ctypes.c_double]
         _lib = L
@@ -149,6 +150,18 @@ class Oracle:
         out = np.zeros(7)
         r = lib().orc_convex_pair(self.h, _p(buf), _p(out))
         return r == 0, float(out[0]), out[1:4].copy(), out[4:7].copy()
+
+    def box_box(self, b1, b2):
+        """mjc_BoxBox restatement between two boxes, each (size[3], pos[3], mat[3, 3]); -> array [n, 7] of pos(3), normal(3), dist."""
+        buf = np.zeros(32)
+        for i, (size, pos, mat) in enumerate((b1, b2)):
+            buf[16 * i] = 6
+            buf[16 * i + 1:16 * i + 4] = size
+            buf[16 * i + 4:16 * i + 7] = pos
+            buf[16 * i + 7:16 * i + 16] = np.asarray(mat, dtype=np.float64).reshape(9)
+        out = np.zeros((8, 7))
+        n = lib().orc_box_box(self.h, _p(buf), _p(out))
+        return out[:n].copy()
 
     def contacts(self, env=0, cap=256):
         out = np.zeros((cap, 10), dtype=np.float64)

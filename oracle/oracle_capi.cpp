@@ -19,6 +19,7 @@ struct IOracle {
   virtual void substep_all() = 0;
   virtual int contacts(int env, double* out, int cap) = 0;
   virtual int contact_forces(int env, double* out, int cap) = 0;
+  virtual int box_box(const double* geoms, double* out) = 0;
   virtual void rne_post_all() = 0;
   virtual double ray_hfield(double x, double y) = 0;
   virtual int convex_pair(const double* geoms, double* out) = 0;
@@ -70,6 +71,14 @@ template <class T> struct OracleT : IOracle {
     if (r == 0 && !(dir[0] == 0 && dir[1] == 0 && dir[2] == 0)) orc::Engine<T>::fix_normal(G[0], G[1], cp, dir);      // as mjc_Convex does
     out[0] = depth; for (int k = 0; k < 3; ++k) { out[1 + k] = dir[k]; out[4 + k] = cp[k]; }
     return r;
+  }
+  // known-answer hook for mjc_BoxBox: geoms = 2 x [type, size(3), pos(3), mat(9)]; out = up to 8 x [pos(3), normal(3), dist]
+  int box_box(const double* geoms, double* out) override {
+    T sz[2][3], pos[2][3], mat[2][9], bb[8][7];
+    for (int i = 0; i < 2; ++i) { const double* g = geoms + 16 * i; for (int k = 0; k < 3; ++k) { sz[i][k] = (T)g[1 + k]; pos[i][k] = (T)g[4 + k]; } for (int k = 0; k < 9; ++k) mat[i][k] = (T)g[7 + k]; }
+    const int n = orc::Engine<T>::box_box(pos[0], mat[0], sz[0], pos[1], mat[1], sz[1], bb);
+    for (int c = 0; c < n; ++c) for (int k = 0; k < 7; ++k) out[7 * c + k] = (double)bb[c][k];
+    return n;
   }
   template <class V> static void put(double* out, const V& v, size_t stride, int e) { for (size_t i = 0; i < stride; ++i) out[(size_t)e * stride + i] = (double)v[i]; }
   int get(const char* name_, double* out) override {
@@ -172,6 +181,7 @@ double orc_norm_ppf(double p) { return orc::norm_ppf(p); }
 void orc_rne_post(void* h) { ((IOracle*)h)->rne_post_all(); }
 double orc_ray_hfield(void* h, double x, double y) { return ((IOracle*)h)->ray_hfield(x, y); }
 int orc_convex_pair(void* h, const double* geoms, double* out) { return ((IOracle*)h)->convex_pair(geoms, out); }
+int orc_box_box(void* h, const double* geoms, double* out) { return ((IOracle*)h)->box_box(geoms, out); }
 int orc_max_threads() {
 #ifdef _OPENMP
   return omp_get_max_threads();

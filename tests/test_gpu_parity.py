@@ -695,3 +695,35 @@ def test_general_constraint_path(eng):
     assert np.median(errs) < CONTACT_MEDIAN_TOL * (5 if eng.get("solver") == "pgs" else 1)
     assert len(same_geo) >= 0.5 * len(errs) and same_geo.max() < tol and np.quantile(same_geo, 0.99) < SAME_GEOMETRY_TOL * (5 if eng.get("solver") == "pgs" else 1)
     env.close()
+
+
+def test_box_box_multi_contact():
+    """mjc_BoxBox on the GPU: the humanoid pose of tests/test_hostsim_vs_oracle.py in which its box geoms press into each other
+    (several contacts per box pair): same contact list as the oracle, positions / depths to fp32, velocities after the sub-step."""
+    from tests.test_hostsim_vs_oracle import HUMANOID_BOXBOX_POSE
+    N = 32
+    env = _env("humanoid_p_v0", "slope_hard", N)
+    orc = _oracle(env, N)
+    orc.reset(); env.reset()
+    gt = env.model.sections["geom_type"]
+    rng = np.random.default_rng(2)
+    q = np.tile(np.array(HUMANOID_BOXBOX_POSE), (N, 1)); q[1:, 7:] *= rng.uniform(0.95, 1.0, (N - 1, 1))
+    z = np.zeros((N, env.model.dim("nv")))
+    orc.set("qpos", q); orc.set("qvel", z); orc.set("qacc_warmstart", z)
+    env.set("qpos", q); env.set("qvel", z); env.set("qacc_warmstart", z)
+    orc.substep(); env.substep()
+    nco, ncg = orc.get("ncon")[:, 0].astype(int), env.get("counters")[:, 7].cpu().numpy()
+    assert (nco == ncg).mean() >= 0.9
+    cap, nbb = env.model.dim("ncon_max"), 0
+    cg_all = env.get("contacts").cpu().numpy().reshape(N, cap, 10)
+    for e in np.nonzero(nco == ncg)[0]:
+        co = orc.contacts(int(e), cap); cg = cg_all[e, :len(co)]
+        if not ((co[:, 7].astype(int) == cg[:, 7].astype(int)).all() and (co[:, 8].astype(int) == cg[:, 8].astype(int)).all()):
+            continue
+        bb = np.array([gt[int(a)] == 6 and c <= -2 and gt[int(-2 - c)] == 6 for a, c in zip(co[:, 7], co[:, 8])])
+        nbb += int(bb.sum())
+        np.testing.assert_allclose(cg[bb, 0], co[bb, 0], atol=5e-6); np.testing.assert_allclose(cg[bb, 1:4], co[bb, 1:4], atol=1e-5)
+    assert nbb >= 3 * N, f"only {nbb} box-box contacts compared"
+    same = nco == ncg
+    np.testing.assert_allclose(env.get("qvel").cpu().numpy()[same], orc.get("qvel")[same], atol=5e-3, rtol=5e-3)
+    env.close()

@@ -176,3 +176,34 @@ def test_self_collision_contacts_match_oracle():
     assert nself >= 60 and np.median(derr) < 5e-6 and (derr > 1e-4).mean() <= 0.10
     assert np.median(nerr) < 1e-4 and (nerr > 1e-2).mean() <= 0.10
     assert np.median(verr) < 1e-3 and (verr > 1e-2).mean() <= 0.10
+
+
+HUMANOID_BOXBOX_POSE = [0.0, 0.0, 4.105, 1.0, 0.0, 0.0, 0.0, 0.817, -0.049, -0.867, -0.311, -0.77, -0.341, 0.073, -0.736, -0.746, 0.097, 0.892, -0.46,
+                        -0.272, 0.541, 0.742, 0.66, 0.686, -0.233, 0.501, -0.851, 0.43, -0.65, -0.057]
+
+
+def test_box_box_contacts_match_oracle():
+    """mjc_BoxBox in the engine (engine_core.h box_box, multi-contact append in collide_pairs) against the oracle: a humanoid pose
+    (mid-air) in which its box geoms press into each other gives several contacts per box pair; same contacts in the same order,
+    positions / depths to fp32, and the accelerations from the multi-contact rows agree."""
+    m = build_model(make_config("humanoid_p_v0", "slope_hard", random=RANDOM_NONE))
+    gt = m.sections["geom_type"]
+    N = 2
+    o, h = Oracle(m, N, seed=1), HostSim(m, N, seed=1)
+    o.reset(); h.reset()
+    q = np.tile(np.array(HUMANOID_BOXBOX_POSE), (N, 1)); q[1, 7:] *= 0.97
+    for x in (o, h):
+        x.set("qpos", q); x.set("qvel", np.zeros((N, m.dim("nv")))); x.set("qacc_warmstart", np.zeros((N, m.dim("nv"))))
+    o.substep(); h.substep()
+    nco, nch = o.get("ncon")[:, 0].astype(int), h.get("counters")[:, 7]
+    assert (nco == nch).all() and nco.min() >= 4
+    nbb = 0
+    for e in range(N):
+        co = o.contacts(e); ch = h.get("contacts")[e].reshape(-1, 10)[:len(co)]
+        assert (co[:, 7].astype(int) == ch[:, 7].astype(int)).all() and (co[:, 8].astype(int) == ch[:, 8].astype(int)).all()
+        bb = np.array([gt[int(a)] == 6 and c <= -2 and gt[int(-2 - c)] == 6 for a, c in zip(co[:, 7], co[:, 8])])
+        nbb += int(bb.sum())
+        np.testing.assert_allclose(ch[bb, 0], co[bb, 0], atol=2e-6); np.testing.assert_allclose(ch[bb, 1:4], co[bb, 1:4], atol=5e-6)
+        np.testing.assert_allclose(ch[bb, 4:7], co[bb, 4:7], atol=1e-5)
+    assert nbb >= 6, "the pose no longer produces multi-contact box pairs"
+    np.testing.assert_allclose(h.get("qvel"), o.get("qvel"), atol=2e-3, rtol=2e-3)      # deep interpenetration: velocities up to 12 rad/s after one sub-step

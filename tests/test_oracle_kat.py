@@ -295,3 +295,31 @@ def test_terrain_authoring_from_png(tmp_path):
     np.testing.assert_array_equal(same.sections["hfield_data"], m.sections["hfield_data"])
     with pytest.raises(ValueError):
         build_model(make_config("flamingo_p_v3", {"raster": img.astype(np.float32), "size": size}))
+
+
+def test_box_box_known_answers():
+    """mjc_BoxBox restatement [upstream engine_collision_box.c]: face contacts give the clipped incident polygon (4 corners
+    when one face lies inside the other, 8 for two squares turned by 45 degrees), crossed edges give one point; position
+    midway between the surfaces, normal from box 1 to box 2, dist = -depth.  (humanoid_p_v0.xml:33,40,110,139: its box geoms.)"""
+    o = Oracle(build_model(make_config("flamingo_p_v3", "flat")), 1)
+    I = np.eye(3)
+    c = o.box_box(([0.5, 0.5, 0.1], [0, 0, 0], I), ([0.1, 0.2, 0.1], [0.05, 0.02, 0.19], I))      # small box resting on a big one, 1 cm deep
+    assert len(c) == 4
+    np.testing.assert_allclose(c[:, 6], -0.01, atol=1e-12); np.testing.assert_allclose(c[:, 3:6], [[0, 0, 1]] * 4, atol=1e-12)
+    np.testing.assert_allclose(c[:, 2], 0.095, atol=1e-12)
+    assert sorted(map(tuple, np.round(c[:, :2], 9))) == sorted([(-0.05, -0.18), (-0.05, 0.22), (0.15, 0.22), (0.15, -0.18)])
+    np.testing.assert_allclose(c[:, :2].mean(axis=0), [0.05, 0.02], atol=1e-12)      # centred under the small box: equal normal forces at rest
+    c = o.box_box(([0.1, 0.2, 0.1], [0, 0, 0], I), ([0.5, 0.5, 0.1], [0.05, 0.02, 0.19], I))      # the big one on top: corners of the small one
+    assert len(c) == 4 and sorted(map(tuple, np.round(c[:, :2], 9))) == sorted([(0.1, 0.2), (0.1, -0.2), (-0.1, -0.2), (-0.1, 0.2)])
+    a = np.pi / 4
+    Rz = np.array([[np.cos(a), -np.sin(a), 0], [np.sin(a), np.cos(a), 0], [0, 0, 1.0]])
+    c = o.box_box(([0.2, 0.2, 0.1], [0, 0, 0], I), ([0.2, 0.2, 0.1], [0, 0, 0.19], Rz))            # two squares at 45 degrees: an octagon
+    assert len(c) == 8
+    np.testing.assert_allclose(np.sort(np.abs(c[:, :2]), axis=1), [[0.2 * (np.sqrt(2) - 1), 0.2]] * 8, atol=1e-9)
+    Rx = np.array([[1, 0, 0], [0, np.cos(a), -np.sin(a)], [0, np.sin(a), np.cos(a)]]); Ry = np.array([[np.cos(a), 0, np.sin(a)], [0, 1, 0], [-np.sin(a), 0, np.cos(a)]])
+    c = o.box_box(([0.5, 0.1, 0.1], [0, 0, 0], Rx), ([0.1, 0.5, 0.1], [0, 0, 0.27], Ry))            # crossed edges
+    assert len(c) == 1
+    np.testing.assert_allclose(c[0], [0, 0, 0.135, 0, 0, 1, -(0.2 * np.sqrt(2) - 0.27)], atol=1e-6)      # the edge test pads its radii by 1e-6 per term against parallel edges
+    assert len(o.box_box(([0.1, 0.1, 0.1], [0, 0, 0], I), ([0.1, 0.1, 0.1], [0.3, 0, 0], I))) == 0
+    # through the collision pipeline: the normal forces of a symmetric 4-point support are equal -- checked on the solver level by
+    # tests/test_hostsim_vs_oracle.py::test_box_box_contacts_match_oracle (humanoid box geoms pressed flat on each other)
