@@ -186,7 +186,7 @@ struct ModelDev {
   int off[80]; int ws_floats;
   uint32_t seed_lo, seed_hi, env_offset;
   unsigned long long* phase;      // [PH__COUNT] cycle counters, profiling builds only (else NULL)
-  int bsync_mask;                 // which of the CTA-wide phase barriers of forward() are enabled (bit 0 .. 3)
+  int bsync_mask;                 // which of the CTA-wide phase barriers are enabled (bits 0 .. 3: forward(), 4: end of a sub-step, 5: after the step prologue)
   // contact store: one record of cr_stride floats per contact (layout CR_*).  The first cn_k records of an env live in
   // its shared-memory workspace (W_CN_REC), the rest in the global-memory overflow slot of the resident warp
   // (gscratch + slot * gslot_floats, L2-resident: only ~3000 slots exist per GPU).  Capacity = dims[CD_ncon_max].
@@ -2498,7 +2498,7 @@ DEV_NOINLINE int substep(const ModelDev& m, float* ws, int lane, int active = 1,
   if (active) substep_pre(m, ws, lane);
   int iters = forward(m, ws, lane, active, bsync);
   if (active) iters = substep_post(m, ws, lane, iters);
-  BSYNC(bsync);
+  BSYNC_IF(bsync, 4);
   return iters;
 }
 

