@@ -14,7 +14,7 @@
 // per SURVEY.md Appendix B; reference call site: gymnasium do_simulation from
 // /root/reference/envs/flamingo_p_v3/flamingo_p_v3.py:189):
 //   kinematics/com_pos/crb  <- mj_kinematics, mj_comPos, mj_crb       (K1 fk_crb)
-//   chol_factor/chol_solve  <- mj_factorM / mj_solveM (dense here)     (K2 ldl_smem)
+//   chol_factor/chol_solve  <- mj_factorM / mj_solveM (tree-sparse, leaf-first elimination; dense variant for coupled Hessians)
 //   collide_*               <- mj_collision: hfield|plane x convex     (K3 collide)
 //   make_constraint         <- mj_makeConstraint/Impedance/reference   (K4 constraints)
 //   newton_solve            <- mj_fwdConstraint, Newton + exact LS     (K5 newton)
@@ -167,7 +167,9 @@ struct ModelDev {
   const uint16_t* sup_off16; const int* geom_supbase;   // bucket offsets relative to the mesh's first candidate, in the shared-memory arena when they fit (else NULL)
   // lower-triangle (i, k) pairs of an nv x nv matrix sorted by k descending, packed (i << 8) | k: the trailing
   // sub-matrix update of Cholesky column j is the prefix of length (nv-j-1)(nv-j)/2
-  const int* tri; int shared_floats;
+  const int* tri; int shared_floats;          // tri: pairs (i, k <= i) of the lower triangle, rows in increasing order
+  const int *ctab, *coff;                     // tree-sparse elimination: pair list of column j = ctab[coff[j] .. coff[j + 1]) (ctab in global memory)
+  const uint16_t* ctab16;                     // 16-bit copy of ctab in the shared-memory arena when it fits without costing an env-warp (else NULL)
   // table arena (engine_setup.h): global copy + which pointer fields of this struct point into it
   const uint8_t* arena_g; int arena_bytes, nslots; uint16_t slot_field[112], slot_off16[112];
   float ground_friction[4];
@@ -489,12 +491,22 @@ DEV_NOINLINE void crb(const ModelDev& m, float* ws, int lane) {
   SYNC();
 }
 
-// dense Cholesky of the n x n SPD matrix in A (lower triangle).  The factor is kept UNSCALED: after the call
-// A[i][j] (i > j) holds L_ij * L_jj and invd[j] = 1 / L_jj, so L_ij = A[i][j] * invd[j]; chol_solve folds the scaling
-// into its pivots.  That drops the column-scaling pass and one warp barrier per column.  The trailing update of
-// column j runs over the flat list of (i, k) pairs `tri` (n must be the nv the table was built for), 32 pairs per pass.
-DEV_NOINLINE void chol_factor(float* A, float* invd, int n, int lane, const int* tri) {
-  NOUNROLL for (int j = 0; j < n; ++j) {
+// Cholesky-type factorization A = U U^T of the n x n SPD matrix in A (lower triangle used), eliminating the LAST dof first
+// [upstream mj_factorM: L^T D L from the leaves of the kinematic tree towards the root].  With dofs numbered parent-before-child
+// the mass matrix -- and every Hessian M + J^T D J whose rows act on single bodies (ground contacts, limits, friction loss) --
+// couples a dof only with its ancestors, and in this elimination order no fill-in appears: column j updates only the pairs
+// (i, k) of ancestors of j (`sparse` = 1: per-column pair lists m.ctab / m.coff; humanoid 1018 pair updates in 48 passes
+// instead of 4060 in 141, w4 555 / 29 instead of 1771 / 67, flamingo_p_v3 295 / 17 instead of 455 / 22).  Rows that couple two
+// branches (geom-geom contacts, connect constraints) need the dense variant (`sparse` = 0): all pairs i, k < j, which are the
+// first j (j + 1) / 2 entries of m.tri.  The factor is kept UNSCALED: after the call A[j][i] (i < j) holds U_ij * U_jj and
+// invd[j] = 1 / U_jj; chol_solve folds the scaling into its pivots (no column-scaling pass, one warp barrier per column).
+// Entries outside the tree pattern are never touched by the sparse variant and must be zero (chol_solve reads whole rows).
+DEV_NOINLINE void chol_factor(const ModelDev& m, float* A, float* invd, int n, int lane, int sparse) {
+  const int* tri = m.tri;
+#ifdef COSIM_CHOL_ALLDENSE
+  sparse = 0;        // A / B builds: dense elimination everywhere
+#endif
+  NOUNROLL for (int j = n - 1; j >= 0; --j) {
     const float d = fmaxf(A[j * n + j], 1e-30f);
 #ifdef COSIM_HOST_EMU
     const float inv = 1.f / sqrtf(d);
@@ -503,26 +515,36 @@ DEV_NOINLINE void chol_factor(float* A, float* invd, int n, int lane, const int*
 #endif
     const float inv2 = inv * inv;
     if (lane == 0) invd[j] = inv;
-    const int T = ((n - j - 1) * (n - j)) >> 1;
-    NOUNROLL for (int idx = lane; idx < T; idx += LANES) {
-      const int t = tri[idx], i = t >> 8, k = t & 255;
-      A[i * n + k] -= A[i * n + j] * A[k * n + j] * inv2;
+    const float* row = A + j * n;
+    if (sparse) {
+      const int o0 = m.coff[j], o1 = m.coff[j + 1];
+      const uint16_t* t16 = m.ctab16;
+      NOUNROLL for (int idx = o0 + lane; idx < o1; idx += LANES) {
+        const int t = t16 ? (int)t16[idx] : LDGB(m.ctab + idx), i = t >> 8, k = t & 255;
+        A[i * n + k] -= row[i] * row[k] * inv2;
+      }
+    } else {
+      const int T = (j * (j + 1)) >> 1;
+      NOUNROLL for (int idx = lane; idx < T; idx += LANES) {
+        const int t = tri[idx], i = t >> 8, k = t & 255;
+        A[i * n + k] -= row[i] * row[k] * inv2;
+      }
     }
     SYNC();
   }
 }
-// solves L L^T x = b with the unscaled factor of chol_factor.  b is destroyed, tmp is scratch, result in out
+// solves U U^T x = b with the unscaled factor of chol_factor (either variant).  b is destroyed, tmp is scratch, result in out
 DEV_NOINLINE void chol_solve(const float* A, const float* invd, float* b, float* tmp, float* out, int n, int lane) {
 #ifdef COSIM_HOST_EMU
-  for (int i = 0; i < n; ++i) {
-    const float xi = b[i] * invd[i], yi = xi * invd[i];
-    for (int k = i + 1 + lane; k < n; k += LANES) b[k] -= A[k * n + i] * yi;
-    if (lane == 0) tmp[i] = xi;
+  for (int j = n - 1; j >= 0; --j) {            // U z = b, column-oriented from the last dof
+    const float zj = b[j] * invd[j], s = zj * invd[j];
+    for (int i = lane; i < j; i += LANES) b[i] -= A[j * n + i] * s;
+    if (lane == 0) tmp[j] = zj;
     SYNC();
   }
-  for (int i = n - 1; i >= 0; --i) {
+  for (int i = 0; i < n; ++i) {                 // U^T x = z, column-oriented from the root
     const float xi = tmp[i] * invd[i];
-    for (int k = lane; k < i; k += LANES) tmp[k] -= A[i * n + k] * invd[k] * xi;
+    for (int j = i + 1 + lane; j < n; j += LANES) tmp[j] -= A[j * n + i] * invd[j] * xi;
     if (lane == 0) out[i] = xi;
     SYNC();
   }
@@ -530,15 +552,15 @@ DEV_NOINLINE void chol_solve(const float* A, const float* invd, float* b, float*
   // n <= 32: lane k keeps element k in a register, the pivot travels by shuffle (same arithmetic as above)
   float bk = lane < n ? b[lane] : 0.f;
   const float dk = lane < n ? invd[lane] : 0.f;
-  NOUNROLL for (int i = 0; i < n; ++i) {
-    const float di = __shfl_sync(0xffffffffu, dk, i);
-    const float xi = __shfl_sync(0xffffffffu, bk, i) * di;
-    if (lane > i && lane < n) bk -= A[lane * n + i] * (xi * di);
-    if (lane == i) bk = xi;
+  NOUNROLL for (int j = n - 1; j >= 0; --j) {
+    const float dj = __shfl_sync(0xffffffffu, dk, j);
+    const float zj = __shfl_sync(0xffffffffu, bk, j) * dj;
+    if (lane < j) bk -= A[j * n + lane] * (zj * dj);
+    if (lane == j) bk = zj;
   }
-  NOUNROLL for (int i = n - 1; i >= 0; --i) {
+  NOUNROLL for (int i = 0; i < n; ++i) {
     const float xi = __shfl_sync(0xffffffffu, bk, i) * __shfl_sync(0xffffffffu, dk, i);
-    if (lane < i) bk -= A[i * n + lane] * dk * xi;
+    if (lane > i && lane < n) bk -= A[lane * n + i] * dk * xi;
     if (lane == i) bk = xi;
   }
   if (lane < n) out[lane] = bk;
@@ -968,8 +990,12 @@ template <class A> DEV int mpr_lane_sm(const A& P, GQ_PARAMS, const float* gcent
   return ret;
 }
 
-// The same query with one support call site per stage: less bookkeeping per trip, used when a few queries run on wide lane
-// groups in lock step (coarse rasters: 2 - 3 prisms per sub-step, 8 lanes each), where stage divergence does not occur.
+// The same query with one support call site per stage (less bookkeeping per trip, five inlined copies of the Minkowski support).
+// Measured on B200 (round 2): with every query on the state machine above the executed code of the collision phase shrinks by
+// ~15 KB (the phase's 54 KB exceed the 32 KB L1.5 instruction cache) and the step runs 1.4 - 2.2 % faster on flamingo_p_v3 /
+// rocky_hard and 2 % faster on the humanoid, unchanged on w4 / stairs: the staged version is kept for reference behind
+// COSIM_MPR_STAGED and is not compiled by default.
+#ifdef COSIM_MPR_STAGED
 template <class A> DEV int mpr_lane_staged(const A& P, GQ_PARAMS, const float* gcenter, float* depth, float* dir_out, float* pos) {
   typedef typename A::PV PV;
   const float tol = MO(ccd_tolerance); const int maxit = MD(ccd_iterations);
@@ -1061,10 +1087,13 @@ template <class A> DEV int mpr_lane_staged(const A& P, GQ_PARAMS, const float* g
     ++it;
   }
 }
-
+#endif
 
 template <class A> DEV int mpr_lane(const A& P, GQ_PARAMS, const float* gcenter, float* depth, float* dir_out, float* pos) {
-  return (grp >> 8) > 1 ? mpr_lane_staged(P, GQ_ARGS, gcenter, depth, dir_out, pos) : mpr_lane_sm(P, GQ_ARGS, gcenter, depth, dir_out, pos);
+#ifdef COSIM_MPR_STAGED
+  if ((grp >> 8) > 1) return mpr_lane_staged(P, GQ_ARGS, gcenter, depth, dir_out, pos);
+#endif
+  return mpr_lane_sm(P, GQ_ARGS, gcenter, depth, dir_out, pos);
 }
 
 // Conservative separation tests between a terrain prism and the BOUNDING shapes of a geom (oriented box from geom_aabb,
@@ -2154,6 +2183,10 @@ DEV_NOINLINE float newton_direction(const ModelDev& m, float* ws, int ncon, int 
   sig = now;
   const int npair = (nv * (nv + 1)) >> 1;
   const bool few = ncon <= FEW_CONTACTS;
+  // a geom-geom contact couples the dofs of two branches: the Hessian then has entries outside the tree pattern
+  int coupled;
+  if (few) { int cc_ = 0; NOUNROLL for (int c = lane; c < ncon; c += LANES) cc_ |= (((const int*)CRECS(c))[CR_CELL] <= -2); coupled = wor(cc_); }
+  else coupled = WSI(W_CNT)[CNT_NCG] < ncon;
   const int* cs = WSI(W_CSTART); const int ncg = few ? 0 : WSI(W_CNT)[CNT_NCG];
   const unsigned cbg = few ? 0u : (unsigned)WSI(W_CNT)[CNT_CBGMASK];
   const float* scom = WS(W_SCOM); const float* cdof = WS(W_CDOF);
@@ -2256,7 +2289,8 @@ DEV_NOINLINE float newton_direction(const ModelDev& m, float* ws, int ncon, int 
     H[i * nv + j] = h;
   }
   SYNC();
-  chol_factor(H, WS(W_INVD), nv, lane, m.tri);
+  // rows that couple two branches of the tree (connect constraints, geom-geom contacts) fill the Hessian outside the tree pattern
+  chol_factor(m, H, WS(W_INVD), nv, lane, neq == 0 && !coupled);
   chol_solve(H, WS(W_INVD), WS(W_TMPV), WS(W_BUF), WS(W_SEARCH), nv, lane);
   return gn;
 }
@@ -2355,7 +2389,7 @@ DEV void stage_kin(const ModelDev& m, float* ws, int lane) {
   const float* M = WS(W_M);
   FOR_LANE(i, nv * nv) A[i] = M[i];
   SYNC();
-  chol_factor(A, WS(W_INVD), nv, lane, m.tri);
+  chol_factor(m, A, WS(W_INVD), nv, lane, 1);
 }
 // stage 2: collision
 DEV void stage_collide(const ModelDev& m, float* ws, int lane) {
@@ -2469,7 +2503,7 @@ DEV_NOINLINE int substep_post(const ModelDev& m, float* ws, int lane, int iters)
   FOR_LANE(i, nv * nv) { const int r = i / nv, c = i - r * nv; A[i] = M[i] + (r == c ? dt * LDG(m.dof_damping + r) : 0.f); }
   FOR_LANE(k, nv) WS(W_TMPV)[k] = WS(W_FSMOOTH)[k] + WS(W_FCON)[k];
   SYNC();
-  chol_factor(A, WS(W_INVD), nv, lane, m.tri);
+  chol_factor(m, A, WS(W_INVD), nv, lane, 1);
   chol_solve(A, WS(W_INVD), WS(W_TMPV), WS(W_BUF), WS(W_GRAD), nv, lane);
   float* qvel = WS(W_QVEL); float* qpos = WS(W_QPOS);
   FOR_LANE(k, nv) qvel[k] += dt * WS(W_GRAD)[k];

@@ -85,7 +85,7 @@ DEV_NOINLINE void init_env(const ModelDev& m, const EnvArrays& E, int env, float
   const float meaninertia = wsum(tr) / (float)nv;
   FOR_LANE(i, nv * nv) A[i] = M[i];
   SYNC();
-  chol_factor(A, WS(W_INVD), nv, lane, m.tri);
+  chol_factor(m, A, WS(W_INVD), nv, lane, 1);
   NOUNROLL for (int c = 0; c < nv; ++c) {           // column c of M^-1 overwrites M
     FOR_LANE(k, nv) WS(W_TMPV)[k] = (k == c) ? 1.f : 0.f;
     SYNC();

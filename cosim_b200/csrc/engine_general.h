@@ -269,7 +269,7 @@ DEV_NOINLINE float gen_direction(const ModelDev& m, float* ws, int nefc, int ncg
     H[i * nv + j] = h;
   }
   SYNC();
-  chol_factor(H, WS(W_INVD), nv, lane, m.tri);
+  chol_factor(m, H, WS(W_INVD), nv, lane, 0);      // general rows: dense variant
   chol_solve(H, WS(W_INVD), WS(W_TMPV), WS(W_BUF), WS(W_SEARCH), nv, lane);
   return gn;
 }

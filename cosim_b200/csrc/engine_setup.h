@@ -53,7 +53,7 @@ struct Arena {
 
 static inline void build_model(const void* blob, size_t nbytes, uint64_t seed, uint32_t env_offset, const Uploader& u, ModelDev& m) {
   Arena arena;
-  std::vector<uint16_t> sup_off16;
+  std::vector<uint16_t> sup_off16, ctab16;
   if (nbytes < 8 || memcmp(blob, "CSB1", 4) != 0) throw std::runtime_error("model blob: bad magic");
   memset(&m, 0, sizeof(m));
   std::vector<int> dims = section<int>(blob, "dims");
@@ -198,10 +198,20 @@ static inline void build_model(const void* blob, size_t nbytes, uint64_t seed, u
       m.hf_max8 = push(u, mx); m.hf_mrow = mr; m.hf_mcol = mc;
     }
   }
-  { // Cholesky pair table
-    std::vector<int> tri;
-    for (int k = nv - 1; k >= 0; --k) for (int i = k; i < nv; ++i) tri.push_back((i << 8) | k);
-    arena.add(m, m.tri, tri);
+  { // Cholesky pair tables (engine_core.h chol_factor).  tri: all pairs (i, k <= i), rows in increasing order, so that the first
+    // j (j + 1) / 2 entries are the pairs below row j (dense elimination of column j); ctab / coff: per column j the pairs of
+    // its ancestors (tree-sparse elimination; kept in global memory, it is read once per column by all warps alike)
+    std::vector<int> tri, ctab, coff(nv + 1, 0);
+    for (int i = 0; i < nv; ++i) for (int k = 0; k <= i; ++k) tri.push_back((i << 8) | k);
+    for (int j = 0; j < nv; ++j) {
+      std::vector<int> anc;
+      for (int a = dof_parent[j]; a >= 0; a = dof_parent[a]) anc.push_back(a);
+      coff[j] = (int)ctab.size();
+      for (size_t x = anc.size(); x-- > 0;) for (size_t y = anc.size(); y-- > x;) ctab.push_back((anc[x] << 8) | anc[y]);     // anc is descending: anc[x] >= anc[y] for y >= x
+    }
+    coff[nv] = (int)ctab.size();
+    arena.add(m, m.tri, tri); arena.add(m, m.coff, coff); m.ctab = push(u, ctab); m.ctab16 = nullptr;
+    ctab16.assign(ctab.begin(), ctab.end());
   }
   { std::vector<float> gf = section<float>(blob, "ground_friction"); for (int i = 0; i < 4; ++i) m.ground_friction[i] = i < (int)gf.size() ? gf[i] : 0.f; }
   ISEC(eq_body1, "eq_body1"); ISEC(eq_body2, "eq_body2");
@@ -288,6 +298,8 @@ static inline void build_model(const void* blob, size_t nbytes, uint64_t seed, u
     // 16-bit copy of the support-map bucket offsets in the arena (one dependent L2 round trip less per hull support query)
     // if that does not cost an env-warp
     if (!sup_off16.empty() && warps(kmin, sup_off16.size() * 2) == warps(kmin, 0) && warps(kmin, 0) >= 1) arena.add(m, m.sup_off16, sup_off16);
+    // likewise the pair lists of the tree-sparse Cholesky (read once per column of every factorization)
+    if (!ctab16.empty() && warps(kmin, ctab16.size() * 2) == warps(kmin, 0) && warps(kmin, 0) >= 1) arena.add(m, m.ctab16, ctab16);
     // Coarse rasters / the plane: a handful of contacts per env, keep every env-warp the SM can hold.  Fine rasters (cells
     // under 5 cm: a wheel alone touches a dozen prisms) give up env-warps, down to 12 per SM, for records in shared memory.
     const double cell = m.dims[CD_ground_type] == 1 ? 2.0 * opts[CO_hf_sx] / std::max(1, m.dims[CD_hf_ncol] - 1) : 1.0;

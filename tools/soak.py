@@ -5,6 +5,9 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import bench
+import cosim_b200.lib as _L
+if os.environ.get("COSIM_LIB_PATH"):
+    _L.LIB_PATH = os.environ["COSIM_LIB_PATH"]
 from cosim_b200.config import make_config, RANDOM_FULL
 from cosim_b200.envs import BatchedEnv
 from cosim_b200.policy import MLPPolicy, synthetic_mlp
