@@ -99,6 +99,16 @@ int hs_set(void* hp, const char* name, const void* src) {
   for (auto& f : setup::env_fields(h->m, h->E)) if (!strcmp(f.name, name)) { memcpy(f.ptr, src, (size_t)h->N * f.dim * 4); return 0; }
   return -1;
 }
+// unit access to the engine's Cholesky (engine_core.h chol_factor / chol_solve): A [nv x nv] row-major SPD, b [nv] -> x [nv]
+int hs_chol(void* hp, const float* A_in, const float* b, int sparse, float* x) {
+  HostSim* h = (HostSim*)hp; const ModelDev& m = h->m; float* ws = h->ws.data(); const int nv = MD(nv);
+  for (int i = 0; i < nv * nv; ++i) WS(W_A)[i] = A_in[i];
+  for (int i = 0; i < nv; ++i) WS(W_TMPV)[i] = b[i];
+  chol_factor(m, WS(W_A), WS(W_INVD), nv, 0, sparse);
+  chol_solve(WS(W_A), WS(W_INVD), WS(W_TMPV), WS(W_BUF), WS(W_GRAD), nv, 0);
+  for (int i = 0; i < nv; ++i) x[i] = WS(W_GRAD)[i];
+  return nv;
+}
 long hs_ls_evals() { return g_emu_ls_evals; }
 uint32_t hs_philox(void* hp, uint32_t env, uint32_t stream, uint32_t step, uint32_t idx) { return philox_draw(((HostSim*)hp)->m, env, stream, step, idx); }
 }

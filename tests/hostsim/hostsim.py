@@ -38,6 +38,7 @@ def lib():
         L.hs_get.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_void_p]
         L.hs_set.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_void_p]
         L.hs_ws_floats.argtypes = [ctypes.c_void_p]
+        L.hs_chol.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
         L.hs_philox.restype = ctypes.c_uint32
         L.hs_philox.argtypes = [ctypes.c_void_p] + [ctypes.c_uint32] * 4
         _lib = L
@@ -86,6 +87,14 @@ class HostSim:
 
     def substep(self):
         lib().hs_substep(self.h)
+
+    def chol_solve(self, A, b, sparse):
+        """x = A^-1 b through the engine's chol_factor / chol_solve (sparse: the tree-sparse pair lists)."""
+        nv = self.model.dim("nv")
+        A = np.ascontiguousarray(A, dtype=np.float32).reshape(nv, nv); b = np.ascontiguousarray(b, dtype=np.float32)
+        x = np.zeros(nv, np.float32)
+        lib().hs_chol(self.h, _p(A), _p(b), int(bool(sparse)), _p(x))
+        return x
 
     def push(self, vel, mask=None):
         v = np.ascontiguousarray(np.broadcast_to(np.asarray(vel, dtype=np.float32), (self.N, 3)))

@@ -207,3 +207,39 @@ def test_box_box_contacts_match_oracle():
         np.testing.assert_allclose(ch[bb, 4:7], co[bb, 4:7], atol=1e-5)
     assert nbb >= 6, "the pose no longer produces multi-contact box pairs"
     np.testing.assert_allclose(h.get("qvel"), o.get("qvel"), atol=2e-3, rtol=2e-3)      # deep interpenetration: velocities up to 12 rad/s after one sub-step
+
+
+@pytest.mark.parametrize("robot,terrain", [("flamingo_p_v3", "rocky_hard"), ("flamingo_light_v1", "flat"), ("w4_p_v2", "stairs_up_hard"), ("humanoid_p_v0", "slope_hard")])
+def test_tree_sparse_cholesky_against_numpy(robot, terrain):
+    """engine_core.h chol_factor / chol_solve (leaf-first elimination, [upstream mj_factorM / mj_solveM]): on a random SPD matrix with
+    the sparsity of the robot's kinematic tree the tree-sparse pair lists and the dense variant give numpy's solution; on a full
+    SPD matrix (a Hessian coupled across branches) the dense variant does."""
+    m = build_model(make_config(robot, terrain, random=RANDOM_NONE))
+    nv, dp = m.dim("nv"), m.sections["dof_parent"]
+    h = HostSim(m, 1, seed=1)
+    rng = np.random.default_rng(5)
+    L = np.eye(nv)
+    for i in range(nv):
+        j = dp[i]
+        while j >= 0:
+            L[i, j] = rng.uniform(-0.6, 0.6); j = dp[j]
+    D = rng.uniform(0.05, 3.0, nv)
+    A = L.T @ np.diag(D) @ L                    # M = L^T D L has the tree pattern: (a, b) nonzero only on a common root path
+    pattern = np.zeros((nv, nv), bool)
+    for i in range(nv):
+        j = i
+        while j >= 0:
+            pattern[i, j] = pattern[j, i] = True; j = dp[j]
+    assert not np.any(A[~pattern] != 0.0)
+    for trial in range(4):
+        b = rng.normal(size=nv)
+        ref = np.linalg.solve(A, b)
+        scale = np.abs(ref).max()
+        for sparse in (1, 0):
+            x = h.chol_solve(A, b, sparse)
+            assert np.abs(x - ref).max() < 2e-4 * scale * np.linalg.cond(A) ** 0.5, (robot, sparse)
+            assert np.abs(A @ x - b).max() < 1e-4 * max(1.0, np.abs(b).max()) * nv
+    G = rng.normal(size=(nv, nv)); F = A + 0.3 * G @ G.T          # fill outside the tree pattern: dense variant only
+    b = rng.normal(size=nv)
+    x = h.chol_solve(F, b, 0)
+    assert np.abs(F @ x - b).max() < 1e-4 * max(1.0, np.abs(b).max()) * nv
