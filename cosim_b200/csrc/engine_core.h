@@ -118,9 +118,11 @@ enum { PH_KIN = 0, PH_COLLIDE, PH_CONSTRAINT, PH_SMOOTH, PH_NEWTON, PH_INTEGRATE
 #ifdef COSIM_HOST_EMU
 #define BSYNC(on) ((void)0)
 #define BSYNC_IF(on, bit) ((void)0)
+#define CTA_SYNC() ((void)0)
 #else
 #define BSYNC(on) do { if (on) __syncthreads(); } while (0)
 #define BSYNC_IF(on, bit) do { if ((on) && ((m.bsync_mask >> (bit)) & 1)) __syncthreads(); } while (0)
+#define CTA_SYNC() __syncthreads()
 #endif
 
 DEV int imax(int a, int b) { return a > b ? a : b; }
@@ -188,7 +190,7 @@ struct ModelDev {
   int off[80]; int ws_floats;
   uint32_t seed_lo, seed_hi, env_offset;
   unsigned long long* phase;      // [PH__COUNT] cycle counters, profiling builds only (else NULL)
-  int bsync_mask;                 // which of the CTA-wide phase barriers are enabled (bits 0 .. 3: forward(), 4: end of a sub-step, 5: after the step prologue)
+  int bsync_mask;                 // which of the CTA-wide phase barriers are enabled (bits 0 .. 3: after the four phases of forward(), 4: end of a sub-step, 5: after the step prologue, 6 .. 8: inside the kinematics / collision / Newton phase)
   // contact store: one record of cr_stride floats per contact (layout CR_*).  The first cn_k records of an env live in
   // its shared-memory workspace (W_CN_REC), the rest in the global-memory overflow slot of the resident warp
   // (gscratch + slot * gslot_floats, L2-resident: only ~3000 slots exist per GPU).  Capacity = dims[CD_ncon_max].
@@ -1214,11 +1216,13 @@ DEV_NOINLINE void mpr_batch(const ModelDev& m, float* ws, int head, int n, int g
   SYNC();
 }
 
-DEV_NOINLINE void collide_hfield_all(const ModelDev& m, float* ws, int lane) {
+// part 0: the whole pass; 1: stage 1 only (per-geom bounds and sub-grids -> W_GTASK); 2: stage 2 only (prisms, narrow phase)
+DEV_NOINLINE void collide_hfield_all(const ModelDev& m, float* ws, int lane, int part = 0) {
   const int ng = MD(ngeom), nrow = MD(hf_nrow), ncol = MD(hf_ncol);
   const float sx = MO(hf_sx), sy = MO(hf_sy), sz = MO(hf_sz), base = MO(hf_base);
   const float dx = 2.f * sx / (float)(ncol - 1), dy = 2.f * sy / (float)(nrow - 1);
   int* task = WSI(W_GTASK);
+  if (part != 2) {
   if (lane == 0) { WSI(W_CNT)[CNT_NCON] = 0; WSI(W_CNT)[CNT_DROPPED] = 0; }
   // ---- stage 1: one group of gs1 lanes per geom (gs1 = largest power of two with ng * gs1 <= LANES)
   int gs1 = 1;
@@ -1274,6 +1278,8 @@ DEV_NOINLINE void collide_hfield_all(const ModelDev& m, float* ws, int lane) {
     if (sub1 == 0) { tk[0] = cmin; tk[1] = rmin; tk[2] = cmax - cmin; tk[3] = rmax - rmin; ((float*)tk)[6] = xmin[2]; }
   }
   SYNC();
+  }
+  if (part == 1) return;
   // ---- stage 2: a lane per prism runs the reference's height test and the bounding-shape culls; the survivors queue up in
   //      a ring (task order), and whenever 32 of them wait one MPR batch runs with a lane per query.  What is left at the
   //      end runs with wider lane groups that share the hull scans (the common case on coarse rasters: a handful of prisms).
@@ -2295,24 +2301,32 @@ DEV_NOINLINE float newton_direction(const ModelDev& m, float* ws, int ncon, int 
   return gn;
 }
 
-DEV_NOINLINE int newton_solve(const ModelDev& m, float* ws, int ncon, int has_rows, int lane) {
+// part 0: the whole solve; 1: up to the first search direction (cost and factor signature are handed back in nc);
+// 2: the iterations, continuing from part 1 (forward() may put a CTA-wide barrier between the two)
+struct NewtonCarry { float cost; uint32_t sig; };
+DEV_NOINLINE int newton_solve(const ModelDev& m, float* ws, int ncon, int has_rows, int lane, int part, NewtonCarry& nc) {
   const int nv = MD(nv), neq = MD(neq);
   float* qacc = WS(W_QACC); float* Ma = WS(W_MA); float* Mv = WS(W_MV); float* search = WS(W_SEARCH);
   const float* M = WS(W_M);
   if (!has_rows) {
+    if (part == 2) return 0;
     FOR_LANE(k, nv) { qacc[k] = WS(W_ASMOOTH)[k]; WS(W_WARM)[k] = WS(W_ASMOOTH)[k]; WS(W_FCON)[k] = 0.f; }
     SYNC(); return 0;
   }
   // warm start: cheaper of qacc_warmstart and qacc_smooth [upstream mj_fwdConstraint].  The warm start usually wins, so it
   // is evaluated last: its row residuals / forces are then already in place and only a smooth-start win pays a third pass.
-  const float cs = total_cost(m, ws, ncon, WS(W_ASMOOTH), Ma, lane);
-  float cost = total_cost(m, ws, ncon, WS(W_WARM), Ma, lane);
-  if (cost > cs) cost = total_cost(m, ws, ncon, WS(W_ASMOOTH), Ma, lane);
+  float cost = nc.cost; uint32_t sig = nc.sig;
+  if (part != 2) {
+    const float cs = total_cost(m, ws, ncon, WS(W_ASMOOTH), Ma, lane);
+    cost = total_cost(m, ws, ncon, WS(W_WARM), Ma, lane);
+    if (cost > cs) cost = total_cost(m, ws, ncon, WS(W_ASMOOTH), Ma, lane);
+    sig = 0;
+    (void)newton_direction(m, ws, ncon, lane, sig);
+    if (part == 1) { nc.cost = cost; nc.sig = sig; return 0; }
+  }
   const float scale = 1.f / (WS(W_SCAL)[1] * (float)imax(1, nv));
   const float tol = MO(tolerance);
   const int maxiter = MD(iterations);
-  uint32_t sig = 0;
-  (void)newton_direction(m, ws, ncon, lane, sig);
   int iter = 0;
   while (iter < maxiter) {
     mat_vec(M, search, Mv, nv, lane);
@@ -2380,11 +2394,14 @@ DEV_NOINLINE void sensors(const ModelDev& m, float* ws, int lane) {
 // stage for every environment of a CTA's pool before any environment enters the next one; forward() below strings them
 // together for one environment (with optional CTA-wide barriers in between).
 // stage 1: kinematics, spatial inertias, mass matrix and its Cholesky factor
-DEV void stage_kin(const ModelDev& m, float* ws, int lane) {
+DEV void stage_kin(const ModelDev& m, float* ws, int lane, int part = 0) {
   const int nv = MD(nv);
   float* A = WS(W_A);
-  kinematics(m, ws, lane);
-  com_pos(m, ws, lane);
+  if (part != 2) {
+    kinematics(m, ws, lane);
+    com_pos(m, ws, lane);
+  }
+  if (part == 1) return;
   crb(m, ws, lane);
   const float* M = WS(W_M);
   FOR_LANE(i, nv * nv) A[i] = M[i];
@@ -2392,8 +2409,9 @@ DEV void stage_kin(const ModelDev& m, float* ws, int lane) {
   chol_factor(m, A, WS(W_INVD), nv, lane, 1);
 }
 // stage 2: collision
-DEV void stage_collide(const ModelDev& m, float* ws, int lane) {
-  if (MD(ground_type) == 1) collide_hfield_all(m, ws, lane);
+DEV void stage_collide(const ModelDev& m, float* ws, int lane, int part = 0) {
+  if (MD(ground_type) == 1) { collide_hfield_all(m, ws, lane, part); if (part == 1) return; }
+  else if (part == 1) return;
   else {
     int ncon = 0, dropped = 0;
     NOUNROLL for (int g = 0; g < MD(ngeom); ++g) collide_plane(m, ws, g, ncon, dropped, lane);
@@ -2442,25 +2460,30 @@ DEV void stage_smooth(const ModelDev& m, float* ws, int lane) {
   SYNC();
 }
 // stage 4: constraint solve; returns the solver iterations
-DEV int stage_newton(const ModelDev& m, float* ws, int lane) {
+DEV int stage_newton(const ModelDev& m, float* ws, int lane, int part, NewtonCarry& nc) {
 #if COSIM_GENERAL
-  const int iters = m.general ? gen_solve(m, ws, WSI(W_CNT)[CNT_NCON], lane) : newton_solve(m, ws, WSI(W_CNT)[CNT_NCON], WSI(W_CNT)[CNT_ROWS], lane);
-#else
-  const int iters = newton_solve(m, ws, WSI(W_CNT)[CNT_NCON], WSI(W_CNT)[CNT_ROWS], lane);
+  if (m.general) { if (part == 2) return 0; const int it_ = gen_solve(m, ws, WSI(W_CNT)[CNT_NCON], lane); PH_COUNT(PH_NEWTON_ITERS, it_); return it_; }
 #endif
-  PH_COUNT(PH_NEWTON_ITERS, iters);
+  const int iters = newton_solve(m, ws, WSI(W_CNT)[CNT_NCON], WSI(W_CNT)[CNT_ROWS], lane, part, nc);
+  if (part != 1) PH_COUNT(PH_NEWTON_ITERS, iters);
   return iters;
 }
+DEV int stage_newton(const ModelDev& m, float* ws, int lane) { NewtonCarry nc = {0.f, 0u}; return stage_newton(m, ws, lane, 0, nc); }
 // returns solver iterations; the contact count of this pass is left in W_CNT
 // `active` = this warp has an env to advance; `bsync` = CTA-wide phase barriers (must then be called by every warp)
 DEV_NOINLINE int forward(const ModelDev& m, float* ws, int lane, int active = 1, int bsync = 0) {
   PH_DECL;
   int iters = 0;
-  if (active) stage_kin(m, ws, lane);
+  // extra barriers INSIDE the three big phases (bits 6, 7, 8 of the mask): the narrower the window of code the warps of an SM
+  // execute together, the fewer instruction-cache misses each of them takes (profiles/r02_experiments.md)
+  const int sp = bsync ? (m.bsync_mask >> 6) : 0;
+  if (active) stage_kin(m, ws, lane, (sp & 1) ? 1 : 0);
+  if (sp & 1) { CTA_SYNC(); if (active) stage_kin(m, ws, lane, 2); }
   PH_MARK(PH_KIN);
   BSYNC_IF(bsync, 0);
   PH_MARK(PH_WAIT_KIN);
-  if (active) stage_collide(m, ws, lane);
+  if (active) stage_collide(m, ws, lane, (sp & 2) ? 1 : 0);
+  if (sp & 2) { CTA_SYNC(); if (active) stage_collide(m, ws, lane, 2); }
   PH_MARK(PH_COLLIDE);
   BSYNC_IF(bsync, 1);
   PH_MARK(PH_WAIT_COLLIDE);
@@ -2468,7 +2491,9 @@ DEV_NOINLINE int forward(const ModelDev& m, float* ws, int lane, int active = 1,
   PH_MARK(PH_SMOOTH);
   BSYNC_IF(bsync, 2);
   PH_MARK(PH_WAIT_SMOOTH);
-  if (active) iters = stage_newton(m, ws, lane);
+  { NewtonCarry nc = {0.f, 0u};
+    if (active) iters = stage_newton(m, ws, lane, (sp & 4) ? 1 : 0, nc);
+    if (sp & 4) { CTA_SYNC(); if (active) iters = stage_newton(m, ws, lane, 2, nc); } }
   PH_MARK(PH_NEWTON);
   BSYNC_IF(bsync, 3);
   PH_MARK(PH_WAIT_NEWTON);
