@@ -1510,7 +1510,9 @@ DEV_NOINLINE int box_box(const float* p1, const float* R1, const float* A, const
 // reference's bounding-sphere filter; (2) the survivors of each 32-pair chunk are handed to lane groups (8 / 4
 // / 2 / 1 lanes per pair, sharing the hull support scans) that run the MPR query in a frame centred on the first geom.
 // Hits are appended after the ground contacts in pair order.
-DEV_NOINLINE void collide_pairs(const ModelDev& m, float* ws, int lane) {
+// BB: the model has box-box pairs (mjc_BoxBox: several contacts per pair, appended by prefix sum); models without them run the
+// instance that carries none of that code (the headline workload lost 2.5 % to it when there was one instance)
+template <bool BB> DEV_NOINLINE void collide_pairs(const ModelDev& m, float* ws, int lane) {
   const int npair = MD(npair);
   int ncon = WSI(W_CNT)[CNT_NCON], dropped = WSI(W_CNT)[CNT_DROPPED];
   SYNC();
@@ -1570,7 +1572,7 @@ DEV_NOINLINE void collide_pairs(const ModelDev& m, float* ws, int lane) {
         const float gc[3] = {(x2[0] - ox) + r2[0], (x2[1] - oy) + r2[1], x2[2] + r2[2]};
         const float dv[3] = {gc[0] - A.c[0], gc[1] - A.c[1], gc[2] - A.c[2]};
         const float bound = LDG(m.geom_rbound + g1) + LDG(m.geom_rbound + g2);
-        if (v3dot(dv, dv) <= bound * bound && m.geom_type[g1] == GEOM_BOX && m.geom_type[g2] == GEOM_BOX) {      // mjc_BoxBox: up to 8 contacts, one lane
+        if (BB && v3dot(dv, dv) <= bound * bound && m.geom_type[g1] == GEOM_BOX && m.geom_type[g2] == GEOM_BOX) {      // mjc_BoxBox: up to 8 contacts, one lane
           if (sub == 0) {
             bbout = *(float* const*)(ws + m.off[W_GPTR]) + m.bb_off + 56 * lane;
             const float q1[3] = {0.f, 0.f, x1[2]}, q2[3] = {x2[0] - ox, x2[1] - oy, x2[2]};      // frame centred on geom 1 in x, y
@@ -1611,12 +1613,18 @@ DEV_NOINLINE void collide_pairs(const ModelDev& m, float* ws, int lane) {
 #ifdef COSIM_HOST_EMU
       const int nhit = hit, slot = ncon;
 #else
-      int incl = hit;          // contacts are appended in pair order: exclusive prefix sum of the per-lane counts
+      int nhit, slot;
+      if (BB) {
+        int incl = hit;          // contacts are appended in pair order: exclusive prefix sum of the per-lane counts
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
-      const int nhit = __shfl_sync(0xffffffffu, incl, 31), slot = ncon + incl - hit;
+        for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+        nhit = __shfl_sync(0xffffffffu, incl, 31); slot = ncon + incl - hit;
+      } else {                   // at most one contact per pair
+        const unsigned hits = __ballot_sync(0xffffffffu, hit);
+        nhit = __popc(hits); slot = ncon + __popc(hits & ((1u << lane) - 1u));
+      }
 #endif
-      if (hit && !bbout) { if (slot < MD(ncon_max)) write_contact(m, ws, slot, cp, nrm, -depth, fmaxf(WS(W_GMU)[g1], WS(W_GMU)[g2]), m.geom_body[g2], g2, -2 - g1); }
+      if (!BB || !bbout) { if (hit && slot < MD(ncon_max)) write_contact(m, ws, slot, cp, nrm, -depth, fmaxf(WS(W_GMU)[g1], WS(W_GMU)[g2]), m.geom_body[g2], g2, -2 - g1); }
       else NOUNROLL for (int c = 0; c < hit; ++c) if (slot + c < MD(ncon_max)) {
         const float* o = bbout + 7 * c; const float wp[3] = {o[0] + bbx, o[1] + bby, o[2]};
         write_contact(m, ws, slot + c, wp, o + 3, o[6], fmaxf(WS(W_GMU)[g1], WS(W_GMU)[g2]), m.geom_body[g2], g2, -2 - g1);
@@ -2418,7 +2426,7 @@ DEV void stage_collide(const ModelDev& m, float* ws, int lane, int part = 0) {
     if (lane == 0) { WSI(W_CNT)[CNT_NCON] = ncon; WSI(W_CNT)[CNT_DROPPED] = dropped; }
   }
   SYNC();
-  if (MD(npair) > 0) collide_pairs(m, ws, lane);
+  if (MD(npair) > 0) { if (m.n_boxbox) collide_pairs<true>(m, ws, lane); else collide_pairs<false>(m, ws, lane); }
 }
 // stage 3: sensors, smooth forces and acceleration, constraint rows
 DEV void stage_smooth(const ModelDev& m, float* ws, int lane) {
