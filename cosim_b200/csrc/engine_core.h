@@ -504,12 +504,14 @@ DEV_NOINLINE void crb(const ModelDev& m, float* ws, int lane) {
 // invd[j] = 1 / U_jj; chol_solve folds the scaling into its pivots (no column-scaling pass, one warp barrier per column).
 // Entries outside the tree pattern are never touched by the sparse variant and must be zero (chol_solve reads whole rows).
 DEV_NOINLINE void chol_factor(const ModelDev& m, float* A, float* invd, int n, int lane, int sparse) {
-  const int* tri = m.tri;
 #ifdef COSIM_CHOL_ALLDENSE
   sparse = 0;        // A / B builds: dense elimination everywhere
 #endif
+  // table pointers and the column offsets' base in registers: the stores to A below would otherwise force their re-load per column
+  const int* const tri = m.tri; const int* const coff = m.coff; const int* const ctab = m.ctab; const uint16_t* const t16 = m.ctab16;
   NOUNROLL for (int j = n - 1; j >= 0; --j) {
-    const float d = fmaxf(A[j * n + j], 1e-30f);
+    const float* row = A + j * n;
+    const float d = fmaxf(row[j], 1e-30f);
 #ifdef COSIM_HOST_EMU
     const float inv = 1.f / sqrtf(d);
 #else
@@ -517,13 +519,18 @@ DEV_NOINLINE void chol_factor(const ModelDev& m, float* A, float* invd, int n, i
 #endif
     const float inv2 = inv * inv;
     if (lane == 0) invd[j] = inv;
-    const float* row = A + j * n;
     if (sparse) {
-      const int o0 = m.coff[j], o1 = m.coff[j + 1];
-      const uint16_t* t16 = m.ctab16;
-      NOUNROLL for (int idx = o0 + lane; idx < o1; idx += LANES) {
-        const int t = t16 ? (int)t16[idx] : LDGB(m.ctab + idx), i = t >> 8, k = t & 255;
-        A[i * n + k] -= row[i] * row[k] * inv2;
+      const int o0 = coff[j], o1 = coff[j + 1];
+      if (t16) {
+        NOUNROLL for (int idx = o0 + lane; idx < o1; idx += LANES) {
+          const int t = (int)t16[idx], i = t >> 8, k = t & 255;
+          A[i * n + k] -= row[i] * row[k] * inv2;
+        }
+      } else {
+        NOUNROLL for (int idx = o0 + lane; idx < o1; idx += LANES) {
+          const int t = LDGB(ctab + idx), i = t >> 8, k = t & 255;
+          A[i * n + k] -= row[i] * row[k] * inv2;
+        }
       }
     } else {
       const int T = (j * (j + 1)) >> 1;
