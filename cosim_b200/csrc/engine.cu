@@ -12,6 +12,7 @@
 // ------------------------------------------------------------------------------------------ kernels
 // per-env kernels: engine_kernels.cuh, instantiated here without and in engine_gen.cu with the general constraint path
 KernelSet kernel_set_gen();
+KernelSet kernel_set_fast24();
 __global__ void k_push(const __grid_constant__ ModelDev m, const EnvArrays E, const uint8_t* mask, const float* vel) {
   const int env = blockIdx.x * blockDim.x + threadIdx.x;
   if (env >= E.N) return;
@@ -104,7 +105,8 @@ int cosim_create(const void* blob, size_t nbytes, int num_envs, int device, uint
   // one CTA per SM with as many env-warps as its shared memory holds (<= 20: five warps of 96 registers fill the 16 K registers of each SM sub-partition): the warps of a CTA move through the
   // phases of a sub-step together (block barriers in k_step), which keeps the instruction working set per SM small
   int wpb = 20; size_t budget = 224 * 1024;         // tuning overrides (experiments): COSIM_MAX_WPB, COSIM_SMEM_KB
-  { const char* e = getenv("COSIM_MAX_WPB"); if (e && atoi(e) >= 1 && atoi(e) <= 20) wpb = atoi(e); }
+  wpb = h->m.wpb_cap > 20 ? 24 : 20;                // which kernel build the model was laid out for (engine_setup.h)
+  { const char* e = getenv("COSIM_MAX_WPB"); if (e && atoi(e) >= 1 && atoi(e) <= wpb) wpb = atoi(e); }
   { const char* e = getenv("COSIM_SMEM_KB"); if (e && atoi(e) >= 16 && atoi(e) <= 227) budget = (size_t)atoi(e) * 1024; }
   while (wpb > 1 && per * wpb + h->m.shared_floats * sizeof(float) > budget) --wpb;
   if (num_envs < wpb * 148) { wpb = (num_envs + 147) / 148; if (wpb < 1) wpb = 1; }      // small batches: spread over the SMs
@@ -114,7 +116,7 @@ int cosim_create(const void* blob, size_t nbytes, int num_envs, int device, uint
   // opt-in maximum once instead of to this handle's size (a second, smaller handle must not lower it for the first).
   int optin = 0; cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
   if ((size_t)optin < h->smem + 16) { fprintf(stderr, "cosim_create: %zu B of shared memory per CTA exceed the device limit %d\n", h->smem, optin); for (void* p : h->allocs) cudaFree(p); delete h; return COSIM_ERR_MODEL; }
-  h->k = h->m.general ? kernel_set_gen() : kernel_set_fast();
+  h->k = h->m.general ? kernel_set_gen() : (h->m.wpb_cap > 20 ? kernel_set_fast24() : kernel_set_fast());
   cudaError_t e1 = cudaFuncSetAttribute(h->k.init, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 16);
   cudaError_t e2 = cudaFuncSetAttribute(h->k.reset, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 16);
   cudaError_t e3 = cudaFuncSetAttribute(h->k.step, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 16);

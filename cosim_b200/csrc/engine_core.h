@@ -195,6 +195,7 @@ struct ModelDev {
   // its shared-memory workspace (W_CN_REC), the rest in the global-memory overflow slot of the resident warp
   // (gscratch + slot * gslot_floats, L2-resident: only ~3000 slots exist per GPU).  Capacity = dims[CD_ncon_max].
   int cn_k, cr_stride; float* gscratch; unsigned long long gslot_floats;
+  int wpb_cap;                    // env-warps per CTA the model was laid out for: 20 (640-thread kernels) or 24 (768-thread kernels, engine_w24.cu)
   // conservative culls ahead of the terrain narrow phase: max height per 8 x 8 block of cells, and per-geom bounding
   // cylinders (geom frame: centre, unit axis, radius, half length; radius 0 = none)
   const float* hf_max8; int hf_mrow, hf_mcol; const float* geom_bcyl;

@@ -7,8 +7,15 @@
 #include "engine_env.h"
 #if COSIM_GENERAL
 #define KN(name) name##_gen
+#elif defined(COSIM_W24)
+#define KN(name) name##_fast24
 #else
 #define KN(name) name##_fast
+#endif
+// threads per CTA the kernels are compiled for: 20 env-warps of 96 registers fill the register file of an SM (COSIM_LB = 768 compiles
+// for 24 warps of 80 registers; experiments)
+#ifndef COSIM_LB
+#define COSIM_LB 640
 #endif
 struct KernelSet { const void *init, *reset, *step, *step_pool, *substep; };
 enum { SG_PRO = 0, SG_KIN, SG_COL, SG_SMO, SG_NEW, SG_EPI, POOL_MAX = 128 };
@@ -45,11 +52,11 @@ extern __shared__ __align__(16) float g_smem[];
 // The grid is sized to what is resident at once (engine.cu cosim_create); each CTA walks over chunks of wpb environments.
 #define FOR_ENV_CHUNKS() for (int env = blockIdx.x * wpb_ + warp; env - warp < E.N; env += gridDim.x * wpb_)
 
-__global__ void __launch_bounds__(640, 1) KN(k_init)(const __grid_constant__ ModelDev mp, const EnvArrays E) {
+__global__ void __launch_bounds__(COSIM_LB, 1) KN(k_init)(const __grid_constant__ ModelDev mp, const EnvArrays E) {
   CTA_PROLOGUE();
   FOR_ENV_CHUNKS() { if (env < E.N) init_env(m, E, env, ws, lane); __syncwarp(); }
 }
-__global__ void __launch_bounds__(640, 1) KN(k_reset)(const __grid_constant__ ModelDev mp, const EnvArrays E, const StepArgs a) {
+__global__ void __launch_bounds__(COSIM_LB, 1) KN(k_reset)(const __grid_constant__ ModelDev mp, const EnvArrays E, const StepArgs a) {
   CTA_PROLOGUE();
   const int cd = MD(command_dim);
   FOR_ENV_CHUNKS() {
@@ -60,7 +67,7 @@ __global__ void __launch_bounds__(640, 1) KN(k_reset)(const __grid_constant__ Mo
 }
 // KN(k_step): every warp of the CTA (also the padding warps of the last chunk) walks through the phase barriers.  Chunks of
 // wpb environments are claimed from a counter (dynamic: the cost of a chunk depends on what its robots are doing).
-__global__ void __launch_bounds__(640, 1) KN(k_step)(const __grid_constant__ ModelDev mp, const EnvArrays E, const StepArgs a, int* sched) {
+__global__ void __launch_bounds__(COSIM_LB, 1) KN(k_step)(const __grid_constant__ ModelDev mp, const EnvArrays E, const StepArgs a, int* sched) {
   CTA_PROLOGUE();
   __shared__ int s_chunk;
   const int nchunks = (E.N + wpb_ - 1) / wpb_;
@@ -103,7 +110,7 @@ static __device__ __forceinline__ void ws_store(float* img, const float* ws, int
   for (int i = lane; i < n4; i += 32) __stcg(dst + i, src[i]);
 }
 static __device__ __forceinline__ int stage_kind(int pos, int nst) { return pos == 0 ? SG_PRO : (pos == nst - 1 ? SG_EPI : 1 + ((pos - 1) & 3)); }
-__global__ void __launch_bounds__(640, 1) KN(k_step_pool)(const __grid_constant__ ModelDev mp, const EnvArrays E, const StepArgs a, int* sched, const PoolArgs pa) {
+__global__ void __launch_bounds__(COSIM_LB, 1) KN(k_step_pool)(const __grid_constant__ ModelDev mp, const EnvArrays E, const StepArgs a, int* sched, const PoolArgs pa) {
   CTA_PROLOGUE();
   __shared__ int s_pool, s_next;
   __shared__ unsigned short s_cost[4][POOL_MAX];      // cycles >> 8 of the last KIN / COL / SMO / NEW group of every pool env
@@ -201,7 +208,7 @@ __global__ void __launch_bounds__(640, 1) KN(k_step_pool)(const __grid_constant_
     for (int i = threadIdx.x; i < 4 * n; i += blockDim.x) pa.cost_g[(size_t)base * 4 + i] = s_cost[i & 3][i >> 2];
   }
 }
-__global__ void __launch_bounds__(640, 1) KN(k_substep)(const __grid_constant__ ModelDev mp, const EnvArrays E) {
+__global__ void __launch_bounds__(COSIM_LB, 1) KN(k_substep)(const __grid_constant__ ModelDev mp, const EnvArrays E) {
   CTA_PROLOGUE();
   FOR_ENV_CHUNKS() { if (env < E.N) substep_env(m, E, env, ws, lane); __syncwarp(); }
 }

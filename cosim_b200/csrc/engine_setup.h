@@ -291,10 +291,21 @@ static inline void build_model(const void* blob, size_t nbytes, uint64_t seed, u
   {
     const size_t budget = 224 * 1024;
     int tmp[80];
+    // Two kernel builds exist for the fast path (engine.cu: 640 threads = 20 env-warps of 96 registers; engine_w24.cu: 768 threads
+    // = 24 env-warps of 80 registers).  A model whose workspace (with 8 contact records in shared memory) lets 24 env-warps
+    // share an SM runs the second one: +6 % on flamingo_p_v3 (B200, round 2) -- more environments in flight beat the extra
+    // spills; models that stay at <= 20 warps for shared memory (flamingo_light 18, w4 12, humanoid 11) lose 2 - 5 % on the
+    // 80-register build and keep the first.  COSIM_WPB_CAP = 20 forces the first build (A / B runs).
+    size_t wcap = 24;
+    { const int cdm = m.dims[CD_condim];
+      const bool general_path = (cdm == 1 || cdm == 4 || cdm == 6) || m.dims[CD_cone] == 1 || m.dims[CD_solver] == 1 || (opts[CO_impratio] > 0 && opts[CO_impratio] != 1.0);
+      if (general_path) wcap = 20; }
+    { const char* e = getenv("COSIM_WPB_CAP"); if (e && (atoi(e) == 20 || atoi(e) == 24)) wcap = (size_t)atoi(e); }
     auto warps = [&](int K, size_t extra) {
       const size_t head = (sizeof(ModelDev) + 15) / 16 * 16 + ((arena.bytes.size() + extra + 31) & ~(size_t)15) + 64, per = (size_t)layout(K, tmp) * 4;
-      return (int)std::min<size_t>(20, (budget - head) / per); };
+      return (int)std::min<size_t>(wcap, (budget - head) / per); };
     const int kmin = std::min(4, ncap), kmax = std::min(64, ncap);
+    if (wcap > 20 && warps(std::min(8, ncap), 0) <= 20) wcap = 20;      // shared memory holds no more than 20 env-warps anyway
     // 16-bit copy of the support-map bucket offsets in the arena (one dependent L2 round trip less per hull support query)
     // if that does not cost an env-warp
     if (!sup_off16.empty() && warps(kmin, sup_off16.size() * 2) == warps(kmin, 0) && warps(kmin, 0) >= 1) arena.add(m, m.sup_off16, sup_off16);
@@ -309,6 +320,7 @@ static inline void build_model(const void* blob, size_t nbytes, uint64_t seed, u
     K = std::max(K, std::min(8, ncap));          // at least 8 records in shared memory, even if that costs an env-warp
     { const char* e = getenv("COSIM_CN_K"); if (e && atoi(e) >= 1) K = std::min(atoi(e), ncap); }
     m.cn_k = K;
+    m.wpb_cap = (int)wcap;
     m.ws_floats = layout(K, m.off);
     m.gslot_floats = (unsigned long long)(((size_t)std::max(0, ncap - K) * m.cr_stride + 31) & ~(size_t)31);
     m.gscratch = nullptr;
