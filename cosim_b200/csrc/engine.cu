@@ -13,6 +13,7 @@
 // per-env kernels: engine_kernels.cuh, instantiated here without and in engine_gen.cu with the general constraint path
 KernelSet kernel_set_gen();
 KernelSet kernel_set_fast24();
+KernelSet kernel_set_fast12();
 __global__ void k_push(const __grid_constant__ ModelDev m, const EnvArrays E, const uint8_t* mask, const float* vel) {
   const int env = blockIdx.x * blockDim.x + threadIdx.x;
   if (env >= E.N) return;
@@ -116,7 +117,8 @@ int cosim_create(const void* blob, size_t nbytes, int num_envs, int device, uint
   // opt-in maximum once instead of to this handle's size (a second, smaller handle must not lower it for the first).
   int optin = 0; cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
   if ((size_t)optin < h->smem + 16) { fprintf(stderr, "cosim_create: %zu B of shared memory per CTA exceed the device limit %d\n", h->smem, optin); for (void* p : h->allocs) cudaFree(p); delete h; return COSIM_ERR_MODEL; }
-  h->k = h->m.general ? kernel_set_gen() : (h->m.wpb_cap > 20 ? kernel_set_fast24() : kernel_set_fast());
+  // the kernel build whose launch bound fits the env-warps per CTA: 24 x 80 registers, <= 20 x 96, <= 12 x 168 (engine_w24.cu / engine.cu / engine_w12.cu)
+  h->k = h->m.general ? kernel_set_gen() : (wpb > 20 ? kernel_set_fast24() : (wpb <= 12 ? kernel_set_fast12() : kernel_set_fast()));
   cudaError_t e1 = cudaFuncSetAttribute(h->k.init, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 16);
   cudaError_t e2 = cudaFuncSetAttribute(h->k.reset, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 16);
   cudaError_t e3 = cudaFuncSetAttribute(h->k.step, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 16);

@@ -9,11 +9,13 @@
 #define KN(name) name##_gen
 #elif defined(COSIM_W24)
 #define KN(name) name##_fast24
+#elif defined(COSIM_W12)
+#define KN(name) name##_fast12
 #else
 #define KN(name) name##_fast
 #endif
-// threads per CTA the kernels are compiled for: 20 env-warps of 96 registers fill the register file of an SM (COSIM_LB = 768 compiles
-// for 24 warps of 80 registers; experiments)
+// threads per CTA the kernels are compiled for: 20 env-warps of 96 registers fill the register file of an SM; engine_w24.cu compiles
+// the fast path for 768 threads (24 warps of 80 registers), engine_w12.cu for 384 (12 warps of up to 168 registers)
 #ifndef COSIM_LB
 #define COSIM_LB 640
 #endif

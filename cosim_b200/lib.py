@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 BUILD_DIR = os.path.join(CSRC, "_build")
 LIB_PATH = os.path.join(BUILD_DIR, "libcosim_b200.so")
-SOURCES = ["engine.cu", "engine_gen.cu", "engine_w24.cu", "policy.cu"]
+SOURCES = ["engine.cu", "engine_gen.cu", "engine_w24.cu", "engine_w12.cu", "policy.cu"]
 HEADERS = ["engine_core.h", "engine_env.h", "engine_setup.h", "engine_general.h", "engine_kernels.cuh", os.path.join("..", "..", "include", "cosim_b200.h"),
            os.path.join("..", "..", "include", "cosim_blob.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared",
