@@ -119,10 +119,12 @@ enum { PH_KIN = 0, PH_COLLIDE, PH_CONSTRAINT, PH_SMOOTH, PH_NEWTON, PH_INTEGRATE
 #define BSYNC(on) ((void)0)
 #define BSYNC_IF(on, bit) ((void)0)
 #define CTA_SYNC() ((void)0)
+#define CTA_SYNC_OR(x) ((x) != 0)
 #else
 #define BSYNC(on) do { if (on) __syncthreads(); } while (0)
 #define BSYNC_IF(on, bit) do { if ((on) && ((m.bsync_mask >> (bit)) & 1)) __syncthreads(); } while (0)
 #define CTA_SYNC() __syncthreads()
+#define CTA_SYNC_OR(x) __syncthreads_or(x)
 #endif
 
 DEV int imax(int a, int b) { return a > b ? a : b; }
@@ -2319,20 +2321,33 @@ DEV_NOINLINE float newton_direction(const ModelDev& m, float* ws, int ncon, int 
 
 // part 0: the whole solve; 1: up to the first search direction (cost and factor signature are handed back in nc);
 // 2: the iterations, continuing from part 1 (forward() may put a CTA-wide barrier between the two)
+// 3: the whole solve with the ITERATIONS of all env-warps of the CTA in lock step (a CTA-wide barrier in front of every
+//    iteration; converged warps keep answering the barrier until the last one is done): every warp of the CTA must call,
+//    the ones without an env with part 4 (barriers only).  The state of the solve stays in registers (no carry).
 struct NewtonCarry { float cost; uint32_t sig; };
-DEV_NOINLINE int newton_solve(const ModelDev& m, float* ws, int ncon, int has_rows, int lane, int part, NewtonCarry& nc) {
+// a second barrier per lock-step iteration, after the line search (its ~4 cost evaluations vary per env): same-box A / B of the
+// 768-thread build on flamingo_p_v3 / rocky_hard 2.765 -> 2.81 M env-steps/s at steady state, 3.306 -> 3.338 M at steps 3 - 23
+#ifndef COSIM_NEWTON_LS_BARRIER
+#define COSIM_NEWTON_LS_BARRIER 1
+#endif
+#if COSIM_NEWTON_LS_BARRIER
+#define NEWTON_LS_SYNC() CTA_SYNC()
+#else
+#define NEWTON_LS_SYNC() ((void)0)
+#endif
+template <bool LOCK> DEV_NOINLINE int newton_solve(const ModelDev& m, float* ws, int ncon, int has_rows, int lane, int part, NewtonCarry& nc) {
   const int nv = MD(nv), neq = MD(neq);
   float* qacc = WS(W_QACC); float* Ma = WS(W_MA); float* Mv = WS(W_MV); float* search = WS(W_SEARCH);
   const float* M = WS(W_M);
+  constexpr bool lock = LOCK;      // two instances: the lock-step one costs the plain one nothing
   if (!has_rows) {
-    if (part == 2) return 0;
-    FOR_LANE(k, nv) { qacc[k] = WS(W_ASMOOTH)[k]; WS(W_WARM)[k] = WS(W_ASMOOTH)[k]; WS(W_FCON)[k] = 0.f; }
-    SYNC(); return 0;
+    if (part != 2 && part != 4) { FOR_LANE(k, nv) { qacc[k] = WS(W_ASMOOTH)[k]; WS(W_WARM)[k] = WS(W_ASMOOTH)[k]; WS(W_FCON)[k] = 0.f; } SYNC(); }
+    if (!lock) return 0;
   }
   // warm start: cheaper of qacc_warmstart and qacc_smooth [upstream mj_fwdConstraint].  The warm start usually wins, so it
   // is evaluated last: its row residuals / forces are then already in place and only a smooth-start win pays a third pass.
   float cost = nc.cost; uint32_t sig = nc.sig;
-  if (part != 2) {
+  if (part != 2 && has_rows) {
     const float cs = total_cost(m, ws, ncon, WS(W_ASMOOTH), Ma, lane);
     cost = total_cost(m, ws, ncon, WS(W_WARM), Ma, lane);
     if (cost > cs) cost = total_cost(m, ws, ncon, WS(W_ASMOOTH), Ma, lane);
@@ -2344,7 +2359,12 @@ DEV_NOINLINE int newton_solve(const ModelDev& m, float* ws, int ncon, int has_ro
   const float tol = MO(tolerance);
   const int maxiter = MD(iterations);
   int iter = 0;
-  while (iter < maxiter) {
+  bool go = has_rows != 0;
+  if (lock) CTA_SYNC();
+  for (;;) {
+    const int cont = go && iter < maxiter;
+    if (lock) { if (!CTA_SYNC_OR(cont)) break; }
+    if (!cont) { if (lock) { NEWTON_LS_SYNC(); continue; } else break; }
     mat_vec(M, search, Mv, nv, lane);
     compute_jv(m, ws, ncon, search, lane);
     float q1 = 0.f, q2 = 0.f, sn = 0.f, gauss = 0.f, absterms = 0.f;
@@ -2358,7 +2378,8 @@ DEV_NOINLINE int newton_solve(const ModelDev& m, float* ws, int ncon, int has_ro
     NOUNROLL for (int idx = lane; idx < 4 * ncon; idx += LANES) { const float* rec = CREC(idx >> 2); const int e = idx & 3; absterms += fabsf(rec[CR_D] * rec[CR_X + e] * rec[CR_V + e]); }
     q1 = wsum(q1); q2 = wsum(q2); sn = sqrtf(wsum(sn)); gauss = 0.5f * wsum(gauss); absterms = wsum(absterms);
     const float alpha = linesearch(m, ws, ncon, gauss, q1, q2, sn, absterms, lane);
-    if (alpha == 0.f) break;
+    if (lock) NEWTON_LS_SYNC();
+    if (alpha == 0.f) { if (lock) { go = false; continue; } else break; }
     FOR_LANE(k, nv) { qacc[k] += alpha * search[k]; Ma[k] += alpha * Mv[k]; }
     FOR_LANE(i, 3 * neq) WS(W_EQ_X)[i] += alpha * WS(W_EQ_V)[i];
     NOUNROLL for (int idx = lane; idx < 4 * ncon; idx += LANES) { float* rec = CREC(idx >> 2); const int e = idx & 3; rec[CR_X + e] += alpha * rec[CR_V + e]; }
@@ -2376,8 +2397,9 @@ DEV_NOINLINE int newton_solve(const ModelDev& m, float* ws, int ncon, int has_ro
     // sum of O(|cost|) terms, so an improvement below a few ulps of it is noise (without the floor the fp32 engine spends
     // one more iteration per sub-step than the fp64 oracle just to see the improvement turn negative)
     // ... and the gradient is a difference of three force vectors of norm fn, so it cannot be resolved below a few ulps of fn
-    if ((old - cost) < fmaxf(tol / scale, COST_EPS * fabsf(old)) || gn < fmaxf(tol / scale, GRAD_EPS * fn)) break;
+    if ((old - cost) < fmaxf(tol / scale, COST_EPS * fabsf(old)) || gn < fmaxf(tol / scale, GRAD_EPS * fn)) { if (lock) go = false; else break; }
   }
+  if (!has_rows) return 0;
   FOR_LANE(k, nv) WS(W_WARM)[k] = qacc[k];
   SYNC();
   return iter;
@@ -2478,9 +2500,10 @@ DEV void stage_smooth(const ModelDev& m, float* ws, int lane) {
 // stage 4: constraint solve; returns the solver iterations
 DEV int stage_newton(const ModelDev& m, float* ws, int lane, int part, NewtonCarry& nc) {
 #if COSIM_GENERAL
-  if (m.general) { if (part == 2) return 0; const int it_ = gen_solve(m, ws, WSI(W_CNT)[CNT_NCON], lane); PH_COUNT(PH_NEWTON_ITERS, it_); return it_; }
+  if (m.general) { if (part == 2 || part == 4) return 0; const int it_ = gen_solve(m, ws, WSI(W_CNT)[CNT_NCON], lane); PH_COUNT(PH_NEWTON_ITERS, it_); return it_; }
 #endif
-  const int iters = newton_solve(m, ws, WSI(W_CNT)[CNT_NCON], WSI(W_CNT)[CNT_ROWS], lane, part, nc);
+  const int iters = part >= 3 ? newton_solve<true>(m, ws, part == 4 ? 0 : WSI(W_CNT)[CNT_NCON], part == 4 ? 0 : WSI(W_CNT)[CNT_ROWS], lane, part, nc)
+                              : newton_solve<false>(m, ws, WSI(W_CNT)[CNT_NCON], WSI(W_CNT)[CNT_ROWS], lane, part, nc);
   if (part != 1) PH_COUNT(PH_NEWTON_ITERS, iters);
   return iters;
 }
@@ -2508,8 +2531,10 @@ DEV_NOINLINE int forward(const ModelDev& m, float* ws, int lane, int active = 1,
   BSYNC_IF(bsync, 2);
   PH_MARK(PH_WAIT_SMOOTH);
   { NewtonCarry nc = {0.f, 0u};
-    if (active) iters = stage_newton(m, ws, lane, (sp & 4) ? 1 : 0, nc);
-    if (sp & 4) { CTA_SYNC(); if (active) iters = stage_newton(m, ws, lane, 2, nc); } }
+    if (sp & 8) iters = stage_newton(m, ws, lane, active ? 3 : 4, nc);      // iterations of all warps in lock step (fast path only)
+    else {
+      if (active) iters = stage_newton(m, ws, lane, (sp & 4) ? 1 : 0, nc);
+      if (sp & 4) { CTA_SYNC(); if (active) iters = stage_newton(m, ws, lane, 2, nc); } } }
   PH_MARK(PH_NEWTON);
   BSYNC_IF(bsync, 3);
   PH_MARK(PH_WAIT_NEWTON);

@@ -321,6 +321,9 @@ static inline void build_model(const void* blob, size_t nbytes, uint64_t seed, u
     { const char* e = getenv("COSIM_CN_K"); if (e && atoi(e) >= 1) K = std::min(atoi(e), ncap); }
     m.cn_k = K;
     m.wpb_cap = (int)wcap;
+    // 24 env-warps on a height field (flamingo_p_v3): Newton iterations of the whole CTA in lock step (bit 9; +3 % there, a loss for
+    // the humanoid's 11 and w4's 12 - 18 warps and on the plane, profiles/r02_experiments.md)
+    if (!getenv("COSIM_BSYNC_MASK") && wcap > 20 && m.dims[CD_ground_type] == 1) m.bsync_mask |= 512;
     m.ws_floats = layout(K, m.off);
     m.gslot_floats = (unsigned long long)(((size_t)std::max(0, ncap - K) * m.cr_stride + 31) & ~(size_t)31);
     m.gscratch = nullptr;
@@ -333,6 +336,7 @@ static inline void build_model(const void* blob, size_t nbytes, uint64_t seed, u
       if (m.n_boxbox) m.gslot_floats += 32 * 56;
     }
     m.general = ((condim == 1 || condim == 4 || condim == 6) || m.dims[CD_cone] == 1 || m.dims[CD_solver] == 1 || (opts[CO_impratio] > 0 && opts[CO_impratio] != 1.0)) ? 1 : 0;
+    if (m.general) m.bsync_mask &= ~(512 | 1024);      // the lock-step Newton iterations / narrow-phase batches exist on the fast path only
     m.gen_rows = 0; m.gen_off = m.gslot_floats;
     if (m.general) {
       const int cd = (condim == 1 || condim == 4 || condim == 6) ? condim : 3, rpc = cd == 1 ? 1 : (m.dims[CD_cone] == 1 ? cd : 2 * (cd - 1));
