@@ -50,6 +50,7 @@ struct float4 { float x, y, z, w; };
 #define SYNC() ((void)0)
 #define LDG(p) (*(p))
 #define LDGB(p) (*(p))
+#define SHP(p) (p)
 static inline float wsum(float v) { return v; }
 static inline float wmaxf(float v) { return v; }
 static inline int wor(int v) { return v; }
@@ -71,6 +72,23 @@ static __device__ __forceinline__ int ctz32(unsigned x) { return __ffs(x) - 1; }
 #define DEV_NOINLINE static __device__ __noinline__
 #define LANES 32
 #define SYNC() __syncwarp()
+// Pointers into the table arena: the kernels' prologue re-points them at the shared-memory copy, but they travel through ModelDev as
+// generic pointers, and a generic load costs LD.E + two R2UR (descriptor) where LDS would do.  SHP() wraps such a pointer into its
+// 32-bit shared-window address with ld.shared accessors (__builtin_assume(__isShared(p)) made nvcc 12.9 drop the loops that used p).
+// Never apply it to a field that may be NULL or that stays in global memory: hull_verts, hfield_data, sup_off, sup_cand, ctab, hf_max8.
+template <class T> struct ShTab {      // read-only table in shared memory, addressed by its 32-bit shared-window address
+  uint32_t a;
+  static __device__ __forceinline__ T ld(uint32_t addr) {
+    if constexpr (sizeof(T) == 2) { unsigned short v; asm("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr)); return (T)v; }
+    else { static_assert(sizeof(T) == 4, "ShTab: 2- or 4-byte elements"); uint32_t v; asm("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr)); T r; memcpy(&r, &v, 4); return r; }
+  }
+  __device__ __forceinline__ T operator[](int i) const { return ld(a + (uint32_t)i * (uint32_t)sizeof(T)); }
+  __device__ __forceinline__ T operator*() const { return ld(a); }
+  __device__ __forceinline__ ShTab operator+(int k) const { return ShTab{a + (uint32_t)k * (uint32_t)sizeof(T)}; }
+  __device__ __forceinline__ operator const T*() const { return (const T*)__cvta_shared_to_generic(a); }      // sites that hand the table to a pointer interface
+};
+template <class T> static __device__ __forceinline__ ShTab<T> shp_(const T* p) { return ShTab<T>{(uint32_t)__cvta_generic_to_shared(p)}; }
+#define SHP(p) shp_(p)
 #define LDG(p) (*(p))          // small model tables: shared-memory copy of the arena (plain load; __ldg would fault)
 #define LDGB(p) __ldg(p)       // big read-only tables in global memory: hull vertices, support maps, height field
 DEV float wsum(float v) {
@@ -210,6 +228,7 @@ struct ModelDev {
 // general path: contacts that get rows, and the floats of its region for NR rows of nv columns and NC contacts (layout: engine_general.h gen_view)
 enum { GEN_MAX_CON = 64, GEN_CON_STRIDE = 44 };
 static inline size_t gen_region_floats(int NR, int nv, int NC) { return (size_t)2 * NR * nv + (size_t)13 * NR + (size_t)NC * GEN_CON_STRIDE + 32; }
+#define TB(field) SHP(m.field)      /* arena table `field` (shared memory inside the kernels) */
 #define MD(name) (m.dims[CD_##name])
 #define MO(name) (m.opts[CO_##name])
 
@@ -370,30 +389,30 @@ DEV_NOINLINE void kinematics(const ModelDev& m, float* ws, int lane) {
   }
   SYNC();
   NOUNROLL for (int l = 1; l < m.nlevels; ++l) {
-    NOUNROLL for (int idx = m.level_start[l] + lane; idx < m.level_start[l + 1]; idx += LANES) {
-      const int b = m.level_body[idx], j = m.body_jnt[b];
+    NOUNROLL for (int idx = TB(level_start)[l] + lane; idx < TB(level_start)[l + 1]; idx += LANES) {
+      const int b = TB(level_body)[idx], j = TB(body_jnt)[b];
       float xp[3], xq[4];
-      if (j >= 0 && m.jnt_type[j] == 0) {
-        const int qa = m.jnt_qposadr[j];
+      if (j >= 0 && TB(jnt_type)[j] == 0) {
+        const int qa = TB(jnt_qposadr)[j];
         quat_normalize(qpos + qa + 3);
         v3copy(xp, qpos + qa);
         xq[0] = qpos[qa + 3]; xq[1] = qpos[qa + 4]; xq[2] = qpos[qa + 5]; xq[3] = qpos[qa + 6];
         v3copy(xanchor + 3 * j, xp);
-        float ax[3] = {LDG(m.jnt_axis + 3 * j), LDG(m.jnt_axis + 3 * j + 1), LDG(m.jnt_axis + 3 * j + 2)};
+        float ax[3] = {LDG(TB(jnt_axis) + 3 * j), LDG(TB(jnt_axis) + 3 * j + 1), LDG(TB(jnt_axis) + 3 * j + 2)};
         quat_rot(xaxis + 3 * j, xq, ax);
       } else {
-        const int p = m.body_parent[b];
-        float bp[3] = {LDG(m.body_pos + 3 * b), LDG(m.body_pos + 3 * b + 1), LDG(m.body_pos + 3 * b + 2)};
-        float bq[4] = {LDG(m.body_quat + 4 * b), LDG(m.body_quat + 4 * b + 1), LDG(m.body_quat + 4 * b + 2), LDG(m.body_quat + 4 * b + 3)};
+        const int p = TB(body_parent)[b];
+        float bp[3] = {LDG(TB(body_pos) + 3 * b), LDG(TB(body_pos) + 3 * b + 1), LDG(TB(body_pos) + 3 * b + 2)};
+        float bq[4] = {LDG(TB(body_quat) + 4 * b), LDG(TB(body_quat) + 4 * b + 1), LDG(TB(body_quat) + 4 * b + 2), LDG(TB(body_quat) + 4 * b + 3)};
         float r[3]; m3mulv(r, xmat + 9 * p, bp); v3add(xp, xpos + 3 * p, r);
         quat_mul(xq, xquat + 4 * p, bq);
         if (j >= 0) {
-          float jp[3] = {LDG(m.jnt_pos + 3 * j), LDG(m.jnt_pos + 3 * j + 1), LDG(m.jnt_pos + 3 * j + 2)};
-          float ax[3] = {LDG(m.jnt_axis + 3 * j), LDG(m.jnt_axis + 3 * j + 1), LDG(m.jnt_axis + 3 * j + 2)};
+          float jp[3] = {LDG(TB(jnt_pos) + 3 * j), LDG(TB(jnt_pos) + 3 * j + 1), LDG(TB(jnt_pos) + 3 * j + 2)};
+          float ax[3] = {LDG(TB(jnt_axis) + 3 * j), LDG(TB(jnt_axis) + 3 * j + 1), LDG(TB(jnt_axis) + 3 * j + 2)};
           float v[3]; quat_rot(v, xq, jp); v3add(xanchor + 3 * j, xp, v);
           quat_rot(xaxis + 3 * j, xq, ax);
-          const int qa = m.jnt_qposadr[j];
-          float ang = (qpos[qa] - LDG(m.qpos0 + qa)) * 0.5f, s, c;
+          const int qa = TB(jnt_qposadr)[j];
+          float ang = (qpos[qa] - LDG(TB(qpos0) + qa)) * 0.5f, s, c;
           sincosf(ang, &s, &c);
           float ql[4] = {c, ax[0] * s, ax[1] * s, ax[2] * s};
           quat_mul(xq, xq, ql);
@@ -404,16 +423,16 @@ DEV_NOINLINE void kinematics(const ModelDev& m, float* ws, int lane) {
       v3copy(xpos + 3 * b, xp);
       xquat[4 * b] = xq[0]; xquat[4 * b + 1] = xq[1]; xquat[4 * b + 2] = xq[2]; xquat[4 * b + 3] = xq[3];
       quat_to_mat(xmat + 9 * b, xq);
-      float ip[3] = {LDG(m.body_ipos + 3 * b), LDG(m.body_ipos + 3 * b + 1), LDG(m.body_ipos + 3 * b + 2)}, r[3];
+      float ip[3] = {LDG(TB(body_ipos) + 3 * b), LDG(TB(body_ipos) + 3 * b + 1), LDG(TB(body_ipos) + 3 * b + 2)}, r[3];
       m3mulv(r, xmat + 9 * b, ip); v3add(xipos + 3 * b, xp, r);
     }
     SYNC();
   }
   float* gxpos = WS(W_GXPOS); float* gxmat = WS(W_GXMAT);
   FOR_LANE(g, MD(ngeom)) {
-    const int b = m.geom_body[g];
-    float gp[3] = {LDG(m.geom_pos + 3 * g), LDG(m.geom_pos + 3 * g + 1), LDG(m.geom_pos + 3 * g + 2)};
-    float gq[4] = {LDG(m.geom_quat + 4 * g), LDG(m.geom_quat + 4 * g + 1), LDG(m.geom_quat + 4 * g + 2), LDG(m.geom_quat + 4 * g + 3)};
+    const int b = TB(geom_body)[g];
+    float gp[3] = {LDG(TB(geom_pos) + 3 * g), LDG(TB(geom_pos) + 3 * g + 1), LDG(TB(geom_pos) + 3 * g + 2)};
+    float gq[4] = {LDG(TB(geom_quat) + 4 * g), LDG(TB(geom_quat) + 4 * g + 1), LDG(TB(geom_quat) + 4 * g + 2), LDG(TB(geom_quat) + 4 * g + 3)};
     float r[3], q[4]; m3mulv(r, xmat + 9 * b, gp); v3add(gxpos + 3 * g, xpos + 3 * b, r);
     quat_mul(q, xquat + 4 * b, gq); quat_to_mat(gxmat + 9 * g, q);
   }
@@ -433,7 +452,7 @@ DEV_NOINLINE void com_pos(const ModelDev& m, float* ws, int lane) {
   if (lane == 0) { scom[0] = com[0]; scom[1] = com[1]; scom[2] = com[2]; scom[3] = sm; }
   float* cinert = WS(W_CINERT);
   NOUNROLL for (int b = 1 + lane; b < nb; b += LANES) {
-    const float* Ib = m.body_inertia + 6 * b;
+    const float* Ib = TB(body_inertia) + 6 * b;
     const float I[9] = {LDG(Ib), LDG(Ib + 3), LDG(Ib + 4), LDG(Ib + 3), LDG(Ib + 1), LDG(Ib + 5), LDG(Ib + 4), LDG(Ib + 5), LDG(Ib + 2)};
     const float* R = xmat + 9 * b;
     float RI[9], Iw[9];
@@ -454,11 +473,11 @@ DEV_NOINLINE void com_pos(const ModelDev& m, float* ws, int lane) {
   }
   float* cdof = WS(W_CDOF); const float* xanchor = WS(W_XANCHOR); const float* xaxis = WS(W_XAXIS);
   FOR_LANE(k, nv) {
-    const int j = m.dof_jnt[k], b = m.dof_body[k];
+    const int j = TB(dof_jnt)[k], b = TB(dof_body)[k];
     float off[3]; v3sub(off, com, xanchor + 3 * j);
     float* cd = cdof + 6 * k;
-    if (m.jnt_type[j] == 0) {
-      const int r = k - m.jnt_dofadr[j];
+    if (TB(jnt_type)[j] == 0) {
+      const int r = k - TB(jnt_dofadr)[j];
       if (r < 3) { cd[0] = cd[1] = cd[2] = 0.f; cd[3] = (r == 0); cd[4] = (r == 1); cd[5] = (r == 2); }
       else { float ax[3] = {xmat[9 * b + r - 3], xmat[9 * b + 3 + r - 3], xmat[9 * b + 6 + r - 3]}; v3copy(cd, ax); v3cross(cd + 3, ax, off); }
     } else { v3copy(cd, xaxis + 3 * j); v3cross(cd + 3, xaxis + 3 * j, off); }
@@ -474,7 +493,7 @@ DEV_NOINLINE void crb(const ModelDev& m, float* ws, int lane) {
     float acc[10];
 #pragma unroll
     for (int i = 0; i < 10; ++i) acc[i] = cinert[10 * b + i];
-    const int end = b + m.body_subsize[b];
+    const int end = b + TB(body_subsize)[b];
     NOUNROLL for (int c = b + 1; c < end; ++c)
 #pragma unroll
       for (int i = 0; i < 10; ++i) acc[i] += cinert[10 * c + i];
@@ -483,14 +502,14 @@ DEV_NOINLINE void crb(const ModelDev& m, float* ws, int lane) {
   }
   FOR_LANE(i, nv * nv) M[i] = 0.f;
   SYNC();
-  FOR_LANE(i, nv) inert_mul(buf + 6 * i, crbI + 10 * m.dof_body[i], cdof + 6 * i);
+  FOR_LANE(i, nv) inert_mul(buf + 6 * i, crbI + 10 * TB(dof_body)[i], cdof + 6 * i);
   SYNC();
   FOR_LANE(p, m.nmpair) {
-    const int i = m.mpair_i[p], j = m.mpair_j[p];
+    const int i = TB(mpair_i)[p], j = TB(mpair_j)[p];
     float s = 0.f;
 #pragma unroll
     for (int k = 0; k < 6; ++k) s += cdof[6 * j + k] * buf[6 * i + k];
-    if (i == j) s += LDG(m.dof_armature + i);
+    if (i == j) s += LDG(TB(dof_armature) + i);
     M[i * nv + j] = s; M[j * nv + i] = s;
   }
   SYNC();
@@ -500,10 +519,10 @@ DEV_NOINLINE void crb(const ModelDev& m, float* ws, int lane) {
 // [upstream mj_factorM: L^T D L from the leaves of the kinematic tree towards the root].  With dofs numbered parent-before-child
 // the mass matrix -- and every Hessian M + J^T D J whose rows act on single bodies (ground contacts, limits, friction loss) --
 // couples a dof only with its ancestors, and in this elimination order no fill-in appears: column j updates only the pairs
-// (i, k) of ancestors of j (`sparse` = 1: per-column pair lists m.ctab / m.coff; humanoid 1018 pair updates in 48 passes
+// (i, k) of ancestors of j (`sparse` = 1: per-column pair lists m.ctab / TB(coff); humanoid 1018 pair updates in 48 passes
 // instead of 4060 in 141, w4 555 / 29 instead of 1771 / 67, flamingo_p_v3 295 / 17 instead of 455 / 22).  Rows that couple two
 // branches (geom-geom contacts, connect constraints) need the dense variant (`sparse` = 0): all pairs i, k < j, which are the
-// first j (j + 1) / 2 entries of m.tri.  The factor is kept UNSCALED: after the call A[j][i] (i < j) holds U_ij * U_jj and
+// first j (j + 1) / 2 entries of TB(tri).  The factor is kept UNSCALED: after the call A[j][i] (i < j) holds U_ij * U_jj and
 // invd[j] = 1 / U_jj; chol_solve folds the scaling into its pivots (no column-scaling pass, one warp barrier per column).
 // Entries outside the tree pattern are never touched by the sparse variant and must be zero (chol_solve reads whole rows).
 DEV_NOINLINE void chol_factor(const ModelDev& m, float* A, float* invd, int n, int lane, int sparse) {
@@ -511,7 +530,7 @@ DEV_NOINLINE void chol_factor(const ModelDev& m, float* A, float* invd, int n, i
   sparse = 0;        // A / B builds: dense elimination everywhere
 #endif
   // table pointers and the column offsets' base in registers: the stores to A below would otherwise force their re-load per column
-  const int* const tri = m.tri; const int* const coff = m.coff; const int* const ctab = m.ctab; const uint16_t* const t16 = m.ctab16;
+  const int* const tri = TB(tri); const int* const coff = TB(coff); const int* const ctab = m.ctab; const uint16_t* const t16 = m.ctab16 ? SHP(m.ctab16) : nullptr;
   NOUNROLL for (int j = n - 1; j >= 0; --j) {
     const float* row = A + j * n;
     const float d = fmaxf(row[j], 1e-30f);
@@ -588,14 +607,14 @@ DEV_NOINLINE void com_vel(const ModelDev& m, float* ws, int lane) {
   FOR_LANE(i, 6) cvel[i] = 0.f;
   SYNC();
   NOUNROLL for (int l = 1; l < m.nlevels; ++l) {
-    NOUNROLL for (int idx = m.level_start[l] + lane; idx < m.level_start[l + 1]; idx += LANES) {
-      const int b = m.level_body[idx], p = m.body_parent[b], j = m.body_jnt[b];
+    NOUNROLL for (int idx = TB(level_start)[l] + lane; idx < TB(level_start)[l + 1]; idx += LANES) {
+      const int b = TB(level_body)[idx], p = TB(body_parent)[b], j = TB(body_jnt)[b];
       float v[6];
 #pragma unroll
       for (int i = 0; i < 6; ++i) v[i] = cvel[6 * p + i];
       if (j >= 0) {
-        const int da = m.jnt_dofadr[j];
-        if (m.jnt_type[j] == 0) {
+        const int da = TB(jnt_dofadr)[j];
+        if (TB(jnt_type)[j] == 0) {
           for (int k = 0; k < 3; ++k) {
 #pragma unroll
             for (int i = 0; i < 6; ++i) { cdd[6 * (da + k) + i] = 0.f; v[i] += cdof[6 * (da + k) + i] * qvel[da + k]; }
@@ -626,12 +645,12 @@ DEV_NOINLINE void rne_bias(const ModelDev& m, float* ws, float* out, int lane) {
   if (lane == 0) { cacc[0] = cacc[1] = cacc[2] = 0.f; cacc[3] = -MO(gx); cacc[4] = -MO(gy); cacc[5] = -MO(gz); }
   SYNC();
   NOUNROLL for (int l = 1; l < m.nlevels; ++l) {
-    NOUNROLL for (int idx = m.level_start[l] + lane; idx < m.level_start[l + 1]; idx += LANES) {
-      const int b = m.level_body[idx], p = m.body_parent[b];
+    NOUNROLL for (int idx = TB(level_start)[l] + lane; idx < TB(level_start)[l + 1]; idx += LANES) {
+      const int b = TB(level_body)[idx], p = TB(body_parent)[b];
       float a[6];
 #pragma unroll
       for (int i = 0; i < 6; ++i) a[i] = cacc[6 * p + i];
-      const int d0 = m.body_dofadr[b], d1 = d0 + m.body_dofnum[b];
+      const int d0 = TB(body_dofadr)[b], d1 = d0 + TB(body_dofnum)[b];
       NOUNROLL for (int k = d0; k < d1; ++k)
 #pragma unroll
         for (int i = 0; i < 6; ++i) a[i] += cdd[6 * k + i] * qvel[k];
@@ -648,7 +667,7 @@ DEV_NOINLINE void rne_bias(const ModelDev& m, float* ws, float* out, int lane) {
   }
   // subtree sums (deterministic order) folded directly into the dof projection
   FOR_LANE(k, nv) {
-    const int b = m.dof_body[k], end = b + m.body_subsize[b];
+    const int b = TB(dof_body)[k], end = b + TB(body_subsize)[b];
     float f[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     NOUNROLL for (int c = b; c < end; ++c)
 #pragma unroll
@@ -684,11 +703,11 @@ DEV int support_bucket(const float* d) {
 struct GeomW { int type; const float* pos; const float* mat; float size[3]; const float* verts; int nvert; float center[3]; const int* sup_off; const float4* sup_cand; };
 
 DEV GeomW make_geom(const ModelDev& m, const float* ws, int g) {
-  GeomW G; G.type = m.geom_type[g]; G.pos = WS(W_GXPOS) + 3 * g; G.mat = WS(W_GXMAT) + 9 * g;
-  G.size[0] = LDG(m.geom_size + 3 * g); G.size[1] = LDG(m.geom_size + 3 * g + 1); G.size[2] = LDG(m.geom_size + 3 * g + 2);
-  G.verts = m.hull_verts + 3 * m.geom_vadr[g]; G.nvert = m.geom_vnum[g];
-  { const int sa = m.geom_supadr[g]; G.sup_off = sa >= 0 ? m.sup_off + sa : nullptr; G.sup_cand = m.sup_cand; }
-  float c[3] = {LDG(m.geom_center + 3 * g), LDG(m.geom_center + 3 * g + 1), LDG(m.geom_center + 3 * g + 2)}, r[3];
+  GeomW G; G.type = TB(geom_type)[g]; G.pos = WS(W_GXPOS) + 3 * g; G.mat = WS(W_GXMAT) + 9 * g;
+  G.size[0] = LDG(TB(geom_size) + 3 * g); G.size[1] = LDG(TB(geom_size) + 3 * g + 1); G.size[2] = LDG(TB(geom_size) + 3 * g + 2);
+  G.verts = m.hull_verts + 3 * TB(geom_vadr)[g]; G.nvert = TB(geom_vnum)[g];
+  { const int sa = TB(geom_supadr)[g]; G.sup_off = sa >= 0 ? m.sup_off + sa : nullptr; G.sup_cand = m.sup_cand; }
+  float c[3] = {LDG(TB(geom_center) + 3 * g), LDG(TB(geom_center) + 3 * g + 1), LDG(TB(geom_center) + 3 * g + 2)}, r[3];
   m3mulv(r, G.mat, c); v3add(G.center, G.pos, r);
   return G;
 }
@@ -744,7 +763,7 @@ DEV void write_contact(const ModelDev& m, float* ws, int slot, const float* pos,
 // all lanes call with identical arguments; lane 0 writes.  ncon is warp-uniform (register) state
 DEV_NOINLINE void add_contact(const ModelDev& m, float* ws, int& ncon, int& dropped, const float* pos, const float* normal, float dist, int g, int cell, int lane) {
   if (ncon >= MD(ncon_max)) { ++dropped; return; }
-  if (lane == 0) write_contact(m, ws, ncon, pos, normal, dist, fmaxf(WS(W_SCAL)[0], WS(W_GMU)[g]), m.geom_body[g], g, cell);
+  if (lane == 0) write_contact(m, ws, ncon, pos, normal, dist, fmaxf(WS(W_SCAL)[0], WS(W_GMU)[g]), TB(geom_body)[g], g, cell);
   ++ncon;
 }
 
@@ -762,23 +781,23 @@ struct F3 { float x, y, z; };
 // serial scan over all hull vertices.
 DEV_NOINLINE F3 support_lane(const ModelDev& m, const float* ws, int g, int grp, unsigned gmask, float ox, float oy, float dx, float dy, float dz) {
   const float* M = WS(W_GXMAT) + 9 * g; const float* pos = WS(W_GXPOS) + 3 * g;
-  const int type = m.geom_type[g];
+  const int type = TB(geom_type)[g];
   const float l0 = M[0] * dx + M[3] * dy + M[6] * dz, l1 = M[1] * dx + M[4] * dy + M[7] * dz, l2 = M[2] * dx + M[5] * dy + M[8] * dz;
   float px = 0.f, py = 0.f, pz = 0.f;
-  if (type == GEOM_SPHERE) { const float r = LDG(m.geom_size + 3 * g); px = l0 * r; py = l1 * r; pz = l2 * r; }
+  if (type == GEOM_SPHERE) { const float r = LDG(TB(geom_size) + 3 * g); px = l0 * r; py = l1 * r; pz = l2 * r; }
   else if (type == GEOM_CYLINDER) {
-    const float r = LDG(m.geom_size + 3 * g), hh = LDG(m.geom_size + 3 * g + 1);
+    const float r = LDG(TB(geom_size) + 3 * g), hh = LDG(TB(geom_size) + 3 * g + 1);
     const float n = sqrtf(l0 * l0 + l1 * l1);
     if (n > MINVALF) { px = l0 / n * r; py = l1 / n * r; }
     pz = (l2 > 0.f ? 1.f : (l2 < 0.f ? -1.f : 0.f)) * hh;
   } else if (type == GEOM_BOX) {
-    px = (l0 > 0.f ? 1.f : -1.f) * LDG(m.geom_size + 3 * g); py = (l1 > 0.f ? 1.f : -1.f) * LDG(m.geom_size + 3 * g + 1); pz = (l2 > 0.f ? 1.f : -1.f) * LDG(m.geom_size + 3 * g + 2);
-  } else if (m.geom_supadr[g] >= 0) {
-    const int* sup_off = m.sup_off + m.geom_supadr[g];
+    px = (l0 > 0.f ? 1.f : -1.f) * LDG(TB(geom_size) + 3 * g); py = (l1 > 0.f ? 1.f : -1.f) * LDG(TB(geom_size) + 3 * g + 1); pz = (l2 > 0.f ? 1.f : -1.f) * LDG(TB(geom_size) + 3 * g + 2);
+  } else if (TB(geom_supadr)[g] >= 0) {
+    const int* sup_off = m.sup_off + TB(geom_supadr)[g];
     const float ld[3] = {l0, l1, l2};
     const int bucket = support_bucket(ld);
     int o0, o1;
-    if (m.sup_off16) { const uint16_t* t16 = m.sup_off16 + m.geom_supadr[g]; const int b0 = m.geom_supbase[g]; o0 = b0 + t16[bucket]; o1 = b0 + t16[bucket + 1]; }
+    if (m.sup_off16) { const uint16_t* t16 = SHP(m.sup_off16) + TB(geom_supadr)[g]; const int b0 = TB(geom_supbase)[g]; o0 = b0 + t16[bucket]; o1 = b0 + t16[bucket + 1]; }
     else { o0 = LDGB(sup_off + bucket); o1 = LDGB(sup_off + bucket + 1); }
     float bv = -INFINITY; int bk = 0x7fffffff;
     const int gs = grp >> 8, sub = grp & 255;
@@ -808,7 +827,7 @@ DEV_NOINLINE F3 support_lane(const ModelDev& m, const float* ws, int g, int grp,
     }
 #endif
   } else {
-    const float* verts = m.hull_verts + 3 * m.geom_vadr[g]; const int nvert = m.geom_vnum[g];
+    const float* verts = m.hull_verts + 3 * TB(geom_vadr)[g]; const int nvert = TB(geom_vnum)[g];
     float bv = -INFINITY;
     NOUNROLL for (int i = 0; i < nvert; ++i) {
       const float vx = LDGB(verts + 3 * i), vy = LDGB(verts + 3 * i + 1), vz = LDGB(verts + 3 * i + 2);
@@ -1125,11 +1144,11 @@ DEV float bound_support(const GeomBound& B, const float* d) {
   return s;
 }
 DEV void make_bound(const ModelDev& m, const float* ws, int g, float ox, float oy, GeomBound& B) {
-  const float* R = WS(W_GXMAT) + 9 * g; const float* pos = WS(W_GXPOS) + 3 * g; const float* ab = m.geom_aabb + 6 * g; const float* bc = m.geom_bcyl + 8 * g;
+  const float* R = WS(W_GXMAT) + 9 * g; const float* pos = WS(W_GXPOS) + 3 * g; const float* ab = TB(geom_aabb) + 6 * g; const float* bc = TB(geom_bcyl) + 8 * g;
   B.R = R;
   const float o[3] = {pos[0] - ox, pos[1] - oy, pos[2]};
   { const float c[3] = {LDG(ab), LDG(ab + 1), LDG(ab + 2)}; float r[3]; m3mulv(r, R, c); v3add(B.cb, o, r); B.h[0] = LDG(ab + 3); B.h[1] = LDG(ab + 4); B.h[2] = LDG(ab + 5); }
-  { const float c[3] = {LDG(m.geom_center + 3 * g), LDG(m.geom_center + 3 * g + 1), LDG(m.geom_center + 3 * g + 2)}; float r[3]; m3mulv(r, R, c); v3add(B.cs, o, r); B.rb = LDG(m.geom_rbound + g) * 1.0001f + 1e-6f; }
+  { const float c[3] = {LDG(TB(geom_center) + 3 * g), LDG(TB(geom_center) + 3 * g + 1), LDG(TB(geom_center) + 3 * g + 2)}; float r[3]; m3mulv(r, R, c); v3add(B.cs, o, r); B.rb = LDG(TB(geom_rbound) + g) * 1.0001f + 1e-6f; }
   B.cr = LDG(bc + 6); B.chl = LDG(bc + 7);
   { const float c[3] = {LDG(bc), LDG(bc + 1), LDG(bc + 2)}, a[3] = {LDG(bc + 3), LDG(bc + 4), LDG(bc + 5)}; float r[3]; m3mulv(r, R, c); v3add(B.cc, o, r); m3mulv(B.ca, R, a); }
 }
@@ -1192,7 +1211,7 @@ DEV_NOINLINE void mpr_batch(const ModelDev& m, float* ws, int head, int n, int g
 #if defined(COSIM_PHASE_TIMING) && !defined(COSIM_HOST_EMU)
       if (sub == 0) atomicAdd(m.phase + PH_MPR_CALLS, 1ull);
 #endif
-      const float cl[3] = {LDG(m.geom_center + 3 * g), LDG(m.geom_center + 3 * g + 1), LDG(m.geom_center + 3 * g + 2)};
+      const float cl[3] = {LDG(TB(geom_center) + 3 * g), LDG(TB(geom_center) + 3 * g + 1), LDG(TB(geom_center) + 3 * g + 2)};
       const float* gpos = WS(W_GXPOS) + 3 * g;
       float gc[3]; m3mulv(gc, WS(W_GXMAT) + 9 * g, cl);
       gc[0] += gpos[0] - ox; gc[1] += gpos[1] - oy; gc[2] += gpos[2];
@@ -1214,7 +1233,7 @@ DEV_NOINLINE void mpr_batch(const ModelDev& m, float* ws, int head, int n, int g
     const int keep = hit && g == gsrc && (have + rank) < 50;
     const unsigned keepm = wballot(keep);
     const int slot = ncon + popc32(keepm & ((1u << lane) - 1u));
-    if (keep && slot < cap) write_contact(m, ws, slot, cp, nrm, -depth, fmaxf(WS(W_SCAL)[0], WS(W_GMU)[g]), m.geom_body[g], g, cell);
+    if (keep && slot < cap) write_contact(m, ws, slot, cp, nrm, -depth, fmaxf(WS(W_SCAL)[0], WS(W_GMU)[g]), TB(geom_body)[g], g, cell);
     const int nkeep = popc32(keepm), room = imax(0, cap - ncon);
     dropped += imax(0, nkeep - room); ncon += imin(nkeep, room);
     SYNC();
@@ -1245,9 +1264,9 @@ DEV_NOINLINE void collide_hfield_all(const ModelDev& m, float* ws, int lane, int
     int* tk = task + 8 * g;
     if (sub1 == 0) { tk[0] = tk[1] = tk[2] = tk[3] = tk[4] = tk[5] = 0; }
     const int grp1 = sub1 | (gs1 << 8);
-    const float cl[3] = {LDG(m.geom_center + 3 * g), LDG(m.geom_center + 3 * g + 1), LDG(m.geom_center + 3 * g + 2)};
+    const float cl[3] = {LDG(TB(geom_center) + 3 * g), LDG(TB(geom_center) + 3 * g + 1), LDG(TB(geom_center) + 3 * g + 2)};
     float pos[3]; m3mulv(pos, WS(W_GXMAT) + 9 * g, cl); v3add(pos, WS(W_GXPOS) + 3 * g, pos);
-    const float rb = LDG(m.geom_rbound + g);
+    const float rb = LDG(TB(geom_rbound) + g);
     if (pos[0] - rb > sx || pos[0] + rb < -sx || pos[1] - rb > sy || pos[1] + rb < -sy) continue;
     if (pos[2] - rb > sz || pos[2] + rb < -base) continue;
     float hmax = INFINITY;
@@ -1376,7 +1395,7 @@ DEV_NOINLINE void collide_hfield_all(const ModelDev& m, float* ws, int lane, int
 }
 
 // body of the first geom of a contact: 0 (world) for ground contacts; geom-geom contacts carry -2 - geom1 in the record's cell slot
-DEV int contact_body1(const ModelDev& m, const float* ws, int c) { const int cell = CRECI(c)[CR_CELL]; return cell <= -2 ? m.geom_body[-2 - cell] : 0; }
+DEV int contact_body1(const ModelDev& m, const float* ws, int c) { const int cell = CRECI(c)[CR_CELL]; return cell <= -2 ? TB(geom_body)[-2 - cell] : 0; }
 
 // mjc_fixNormal restated (oracle/oracle.hpp fix_normal): for smooth primitives the contact normal is rebuilt from the contact
 // point -- sphere: centre to point; cylinder: radial direction of the wall unless the point sits on / near a cap.  A normal
@@ -1384,12 +1403,12 @@ DEV int contact_body1(const ModelDev& m, const float* ws, int c) { const int cel
 DEV void fix_normal(const ModelDev& m, const float* ws, int g1, int g2, const float* pos, float* normal) {
   float acc[3] = {0.f, 0.f, 0.f}; int n = 0;
   for (int i = 0; i < 2; ++i) {
-    const int g = i ? g2 : g1, type = m.geom_type[g];
+    const int g = i ? g2 : g1, type = TB(geom_type)[g];
     if (type != GEOM_SPHERE && type != GEOM_CYLINDER) continue;
     const float* R = WS(W_GXMAT) + 9 * g; const float* x = WS(W_GXPOS) + 3 * g;
     float rel[3], loc[3]; v3sub(rel, pos, x); m3tmulv(loc, R, rel);
     if (type == GEOM_CYLINDER) {
-      const float rad = LDG(m.geom_size + 3 * g), hl = LDG(m.geom_size + 3 * g + 1);
+      const float rad = LDG(TB(geom_size) + 3 * g), hl = LDG(TB(geom_size) + 3 * g + 1);
       if (fabsf(loc[2]) > 0.95f * hl) continue;
       const float dflat = fabsf(hl - fabsf(loc[2])), dround = fabsf(rad - sqrtf(loc[0] * loc[0] + loc[1] * loc[1]));
       if (!(dround < dflat)) continue;
@@ -1530,10 +1549,10 @@ template <bool BB> DEV_NOINLINE void collide_pairs(const ModelDev& m, float* ws,
     const int p = p0 + lane;
     int cand = 0;
     if (p < npair) {      // separating-axis test on the six face normals of the two geom-frame boxes
-      const int g1 = m.pair_geom[2 * p], g2 = m.pair_geom[2 * p + 1];
+      const int g1 = TB(pair_geom)[2 * p], g2 = TB(pair_geom)[2 * p + 1];
       const float* R1 = WS(W_GXMAT) + 9 * g1; const float* R2 = WS(W_GXMAT) + 9 * g2;
       const float* x1 = WS(W_GXPOS) + 3 * g1; const float* x2 = WS(W_GXPOS) + 3 * g2;
-      const float* a1 = m.geom_aabb + 6 * g1; const float* a2 = m.geom_aabb + 6 * g2;
+      const float* a1 = TB(geom_aabb) + 6 * g1; const float* a2 = TB(geom_aabb) + 6 * g2;
       const float c1[3] = {LDG(a1), LDG(a1 + 1), LDG(a1 + 2)}, c2[3] = {LDG(a2), LDG(a2 + 1), LDG(a2 + 2)};
       const float h1[3] = {LDG(a1 + 3), LDG(a1 + 4), LDG(a1 + 5)}, h2[3] = {LDG(a2 + 3), LDG(a2 + 4), LDG(a2 + 5)};
       float w1[3], w2[3], t[3]; m3mulv(w1, R1, c1); m3mulv(w2, R2, c2);
@@ -1572,22 +1591,22 @@ template <bool BB> DEV_NOINLINE void collide_pairs(const ModelDev& m, float* ws,
       if (k < nc) {
         unsigned mm = cmask; for (int i = 0; i < k; ++i) mm &= mm - 1;
         const int pp = p0 + ctz32(mm);
-        g1 = m.pair_geom[2 * pp]; g2 = m.pair_geom[2 * pp + 1];
-        const float cl1[3] = {LDG(m.geom_center + 3 * g1), LDG(m.geom_center + 3 * g1 + 1), LDG(m.geom_center + 3 * g1 + 2)};
-        const float cl2[3] = {LDG(m.geom_center + 3 * g2), LDG(m.geom_center + 3 * g2 + 1), LDG(m.geom_center + 3 * g2 + 2)};
+        g1 = TB(pair_geom)[2 * pp]; g2 = TB(pair_geom)[2 * pp + 1];
+        const float cl1[3] = {LDG(TB(geom_center) + 3 * g1), LDG(TB(geom_center) + 3 * g1 + 1), LDG(TB(geom_center) + 3 * g1 + 2)};
+        const float cl2[3] = {LDG(TB(geom_center) + 3 * g2), LDG(TB(geom_center) + 3 * g2 + 1), LDG(TB(geom_center) + 3 * g2 + 2)};
         const float* x1 = WS(W_GXPOS) + 3 * g1; const float* x2 = WS(W_GXPOS) + 3 * g2;
         float r1[3], r2[3]; m3mulv(r1, WS(W_GXMAT) + 9 * g1, cl1); m3mulv(r2, WS(W_GXMAT) + 9 * g2, cl2);
         const float ox = x1[0], oy = x1[1];
         GeomA A; A.g1 = g1; A.c[0] = r1[0]; A.c[1] = r1[1]; A.c[2] = x1[2] + r1[2];
         const float gc[3] = {(x2[0] - ox) + r2[0], (x2[1] - oy) + r2[1], x2[2] + r2[2]};
         const float dv[3] = {gc[0] - A.c[0], gc[1] - A.c[1], gc[2] - A.c[2]};
-        const float bound = LDG(m.geom_rbound + g1) + LDG(m.geom_rbound + g2);
-        if (BB && v3dot(dv, dv) <= bound * bound && m.geom_type[g1] == GEOM_BOX && m.geom_type[g2] == GEOM_BOX) {      // mjc_BoxBox: up to 8 contacts, one lane
+        const float bound = LDG(TB(geom_rbound) + g1) + LDG(TB(geom_rbound) + g2);
+        if (BB && v3dot(dv, dv) <= bound * bound && TB(geom_type)[g1] == GEOM_BOX && TB(geom_type)[g2] == GEOM_BOX) {      // mjc_BoxBox: up to 8 contacts, one lane
           if (sub == 0) {
             bbout = *(float* const*)(ws + m.off[W_GPTR]) + m.bb_off + 56 * lane;
             const float q1[3] = {0.f, 0.f, x1[2]}, q2[3] = {x2[0] - ox, x2[1] - oy, x2[2]};      // frame centred on geom 1 in x, y
-            const float sA[3] = {LDG(m.geom_size + 3 * g1), LDG(m.geom_size + 3 * g1 + 1), LDG(m.geom_size + 3 * g1 + 2)};
-            const float sB[3] = {LDG(m.geom_size + 3 * g2), LDG(m.geom_size + 3 * g2 + 1), LDG(m.geom_size + 3 * g2 + 2)};
+            const float sA[3] = {LDG(TB(geom_size) + 3 * g1), LDG(TB(geom_size) + 3 * g1 + 1), LDG(TB(geom_size) + 3 * g1 + 2)};
+            const float sB[3] = {LDG(TB(geom_size) + 3 * g2), LDG(TB(geom_size) + 3 * g2 + 1), LDG(TB(geom_size) + 3 * g2 + 2)};
             hit = box_box(q1, WS(W_GXMAT) + 9 * g1, sA, q2, WS(W_GXMAT) + 9 * g2, sB, bbout);
             bbx = ox; bby = oy;
           }
@@ -1634,10 +1653,10 @@ template <bool BB> DEV_NOINLINE void collide_pairs(const ModelDev& m, float* ws,
         nhit = __popc(hits); slot = ncon + __popc(hits & ((1u << lane) - 1u));
       }
 #endif
-      if (!BB || !bbout) { if (hit && slot < MD(ncon_max)) write_contact(m, ws, slot, cp, nrm, -depth, fmaxf(WS(W_GMU)[g1], WS(W_GMU)[g2]), m.geom_body[g2], g2, -2 - g1); }
+      if (!BB || !bbout) { if (hit && slot < MD(ncon_max)) write_contact(m, ws, slot, cp, nrm, -depth, fmaxf(WS(W_GMU)[g1], WS(W_GMU)[g2]), TB(geom_body)[g2], g2, -2 - g1); }
       else NOUNROLL for (int c = 0; c < hit; ++c) if (slot + c < MD(ncon_max)) {
         const float* o = bbout + 7 * c; const float wp[3] = {o[0] + bbx, o[1] + bby, o[2]};
-        write_contact(m, ws, slot + c, wp, o + 3, o[6], fmaxf(WS(W_GMU)[g1], WS(W_GMU)[g2]), m.geom_body[g2], g2, -2 - g1);
+        write_contact(m, ws, slot + c, wp, o + 3, o[6], fmaxf(WS(W_GMU)[g1], WS(W_GMU)[g2]), TB(geom_body)[g2], g2, -2 - g1);
       }
       const int room = imax(0, MD(ncon_max) - ncon);
       dropped += imax(0, nhit - room); ncon += imin(nhit, room);
@@ -1743,7 +1762,7 @@ DEV void kb_params(const ModelDev& m, const float* solref, const float* solimp, 
 }
 // translational point Jacobian column for dof k at world point (offset from subtree COM), if dof k moves `body`
 DEV void jac_col(const ModelDev& m, const float* ws, int body, int k, const float* off, float* jp) {
-  if ((m.body_dofmask[body] >> k) & 1) {
+  if ((TB(body_dofmask)[body] >> k) & 1) {
     const float* cd = WS(W_CDOF) + 6 * k; float c[3]; v3cross(c, cd, off);
     jp[0] = cd[3] + c[0]; jp[1] = cd[4] + c[1]; jp[2] = cd[5] + c[2];
   } else { jp[0] = jp[1] = jp[2] = 0.f; }
@@ -1770,7 +1789,7 @@ DEV void contact_edge_rows(const ModelDev& m, const float* ws, const float* rec,
   float off[3], vp[3]; v3sub(off, rec + CR_POS, WS(W_SCOM));
   point_vel(bv + 6 * ((const int*)rec)[CR_BODY], off, vp);
   const int cell = ((const int*)rec)[CR_CELL];
-  if (cell <= -2) { const int b1 = m.geom_body[-2 - cell]; if (b1 > 0) { float v1[3]; point_vel(bv + 6 * b1, off, v1); v3sub(vp, vp, v1); } }
+  if (cell <= -2) { const int b1 = TB(geom_body)[-2 - cell]; if (b1 > 0) { float v1[3]; point_vel(bv + 6 * b1, off, v1); v3sub(vp, vp, v1); } }
   const float* fr = rec + CR_FRAME; const float mu = rec[CR_MU];
   const float vn = v3dot(fr, vp), v1 = mu * v3dot(fr + 3, vp), v2 = mu * v3dot(fr + 6, vp);
   r[0] = vn + v1; r[1] = vn - v1; r[2] = vn + v2; r[3] = vn - v2;
@@ -1782,7 +1801,7 @@ DEV_NOINLINE void contact_index(const ModelDev& m, float* ws, int ncon, int lane
   NOUNROLL for (int c = lane; c < ncon; c += LANES) {
     const int* rec = CRECI(c); const int cell = rec[CR_CELL];
     ng_ += cell > -2; mask |= 1u << rec[CR_BODY];
-    if (cell <= -2) mask |= 1u << m.geom_body[-2 - cell];
+    if (cell <= -2) mask |= 1u << TB(geom_body)[-2 - cell];
   }
 #ifndef COSIM_HOST_EMU
   ng_ = __reduce_add_sync(0xffffffffu, ng_); mask = __reduce_or_sync(0xffffffffu, mask);
@@ -1805,7 +1824,7 @@ DEV_NOINLINE void body_vel(const ModelDev& m, float* ws, const float* vec, int l
   NOUNROLL for (int idx = lane; idx < 6 * nb; idx += LANES) {
     const int b = idx / 6, i = idx - 6 * b;
     if (!((cb >> b) & 1u)) continue;
-    unsigned mask = (unsigned)m.body_dofmask[b]; float acc = 0.f;
+    unsigned mask = (unsigned)TB(body_dofmask)[b]; float acc = 0.f;
     NOUNROLL while (mask) { const int k = ctz32(mask); mask &= mask - 1u; acc += cdof[6 * k + i] * vec[k]; }
     bv[idx] = acc;
   }
@@ -1820,9 +1839,9 @@ DEV_NOINLINE void make_constraint(const ModelDev& m, float* ws, int ncon, int la
   const float* qvel = WS(W_QVEL); const float* qpos = WS(W_QPOS); const float* scom = WS(W_SCOM);
   // equality: connect
   NOUNROLL for (int e = 0; e < neq; ++e) {
-    const int b1 = m.eq_body1[e], b2 = m.eq_body2[e];
-    float a1[3] = {LDG(m.eq_anchor1 + 3 * e), LDG(m.eq_anchor1 + 3 * e + 1), LDG(m.eq_anchor1 + 3 * e + 2)};
-    float a2[3] = {LDG(m.eq_anchor2 + 3 * e), LDG(m.eq_anchor2 + 3 * e + 1), LDG(m.eq_anchor2 + 3 * e + 2)};
+    const int b1 = TB(eq_body1)[e], b2 = TB(eq_body2)[e];
+    float a1[3] = {LDG(TB(eq_anchor1) + 3 * e), LDG(TB(eq_anchor1) + 3 * e + 1), LDG(TB(eq_anchor1) + 3 * e + 2)};
+    float a2[3] = {LDG(TB(eq_anchor2) + 3 * e), LDG(TB(eq_anchor2) + 3 * e + 1), LDG(TB(eq_anchor2) + 3 * e + 2)};
     float p1[3], p2[3], r[3], o1[3], o2[3];
     m3mulv(r, WS(W_XMAT) + 9 * b1, a1); v3add(p1, WS(W_XPOS) + 3 * b1, r);
     m3mulv(r, WS(W_XMAT) + 9 * b2, a2); v3add(p2, WS(W_XPOS) + 3 * b2, r);
@@ -1835,8 +1854,8 @@ DEV_NOINLINE void make_constraint(const ModelDev& m, float* ws, int ncon, int la
     }
     vel[0] = wsum(vel[0]); vel[1] = wsum(vel[1]); vel[2] = wsum(vel[2]);
     float pe[3]; v3sub(pe, p1, p2);
-    float si[5]; for (int i = 0; i < 5; ++i) si[i] = LDG(m.eq_solimp + 5 * e + i);
-    float sr[2] = {LDG(m.eq_solref + 2 * e), LDG(m.eq_solref + 2 * e + 1)};
+    float si[5]; for (int i = 0; i < 5; ++i) si[i] = LDG(TB(eq_solimp) + 5 * e + i);
+    float sr[2] = {LDG(TB(eq_solref) + 2 * e), LDG(TB(eq_solref) + 2 * e + 1)};
     float imp = impedance(si, v3norm(pe)), Ke, Be; kb_params(m, sr, si, &Ke, &Be);
     float diag = WS(W_INVWB)[b1] + WS(W_INVWB)[b2];
     float R = fmaxf(MINVALF, (1.f - imp) * diag / imp);
@@ -1854,9 +1873,9 @@ DEV_NOINLINE void make_constraint(const ModelDev& m, float* ws, int ncon, int la
   // joint limits: at most one side active per joint (lo < hi); sign 0 marks "no row"
   FOR_LANE(j, njnt) {
     float sign = 0.f, D = 0.f, aref = 0.f;
-    if (m.jnt_limited[j]) {
-      const float q = qpos[m.jnt_qposadr[j]]; const int k = m.jnt_dofadr[j];
-      float dlo = q - LDG(m.jnt_range + 2 * j), dhi = LDG(m.jnt_range + 2 * j + 1) - q;
+    if (TB(jnt_limited)[j]) {
+      const float q = qpos[TB(jnt_qposadr)[j]]; const int k = TB(jnt_dofadr)[j];
+      float dlo = q - LDG(TB(jnt_range) + 2 * j), dhi = LDG(TB(jnt_range) + 2 * j + 1) - q;
       float dist = 0.f;
       if (dlo < 0.f) { sign = 1.f; dist = dlo; } else if (dhi < 0.f) { sign = -1.f; dist = dhi; }
       if (sign != 0.f) {
@@ -1876,7 +1895,7 @@ DEV_NOINLINE void make_constraint(const ModelDev& m, float* ws, int ncon, int la
       const float* fr = rec + CR_FRAME; float off[3], jp[3];
       v3sub(off, rec + CR_POS, scom);
       jac_col(m, ws, ((const int*)rec)[CR_BODY], k, off, jp);
-      { const int cell = ((const int*)rec)[CR_CELL]; if (cell <= -2) { const int b1 = m.geom_body[-2 - cell]; if (b1 > 0) { float j1[3]; jac_col(m, ws, b1, k, off, j1); v3sub(jp, jp, j1); } } }
+      { const int cell = ((const int*)rec)[CR_CELL]; if (cell <= -2) { const int b1 = TB(geom_body)[-2 - cell]; if (b1 > 0) { float j1[3]; jac_col(m, ws, b1, k, off, j1); v3sub(jp, jp, j1); } } }
       float* J = WS(W_CN_J) + (size_t)3 * c * nv;
       J[k] = v3dot(fr, jp); J[nv + k] = v3dot(fr + 3, jp); J[2 * nv + k] = v3dot(fr + 6, jp);
     }
@@ -1942,7 +1961,7 @@ DEV_NOINLINE RowSum eval_rows(const ModelDev& m, const float* ws, int ncon, floa
   }
   FOR_LANE(j, njnt) {
     const float sg = WS(W_LM_SIGN)[j];
-    if (sg != 0.f) { const int k = m.jnt_dofadr[j]; row_acc(s, sg * WS(W_QACC)[k] - WS(W_LM_AREF)[j], use_v ? sg * WS(W_SEARCH)[k] : 0.f, a, WS(W_LM_D)[j], 2, 0.f, 0.f); }
+    if (sg != 0.f) { const int k = TB(jnt_dofadr)[j]; row_acc(s, sg * WS(W_QACC)[k] - WS(W_LM_AREF)[j], use_v ? sg * WS(W_SEARCH)[k] : 0.f, a, WS(W_LM_D)[j], 2, 0.f, 0.f); }
   }
   if (ncon <= FEW_CONTACTS) { NOUNROLL for (int idx = lane; idx < 4 * ncon; idx += LANES) { const float* rec = CRECS(idx >> 2); const int e = idx & 3; row_acc(s, rec[CR_X + e], use_v ? rec[CR_V + e] : 0.f, a, rec[CR_D], 2, 0.f, 0.f); } }
   else NOUNROLL for (int idx = lane; idx < 4 * ncon; idx += LANES) { const float* rec = CREC(idx >> 2); const int e = idx & 3; row_acc(s, rec[CR_X + e], use_v ? rec[CR_V + e] : 0.f, a, rec[CR_D], 2, 0.f, 0.f); }
@@ -2028,7 +2047,7 @@ DEV_NOINLINE float update_forces(const ModelDev& m, float* ws, int ncon, int lan
       NOUNROLL for (int c = ncg; c < ncon; ++c) {
         const float* rec = CREC(c);
         if (((const int*)rec)[CR_BODY] == b) acc += rec[CR_WF + i];
-        if (m.geom_body[-2 - ((const int*)rec)[CR_CELL]] == b) acc -= rec[CR_WF + i];
+        if (TB(geom_body)[-2 - ((const int*)rec)[CR_CELL]] == b) acc -= rec[CR_WF + i];
       }
       bf[idx] = acc;
     }
@@ -2043,14 +2062,14 @@ DEV_NOINLINE float update_forces(const ModelDev& m, float* ws, int ncon, int lan
       else if (x >= Rf) { q -= f; cost += f * (-0.5f * Rf + x); }
       else { q -= D * x; cost += 0.5f * D * x * x; }
     }
-    const int j = m.dof_jnt[k];
+    const int j = TB(dof_jnt)[k];
     const float sg = WS(W_LM_SIGN)[j];
-    if (sg != 0.f && m.jnt_dofadr[j] == k) {
+    if (sg != 0.f && TB(jnt_dofadr)[j] == k) {
       const float x = sg * WS(W_QACC)[k] - WS(W_LM_AREF)[j], Dl = WS(W_LM_D)[j];
       if (x < 0.f) { q += sg * (-Dl * x); cost += 0.5f * Dl * x * x; }
     }
     if (cb) {      // J^T f: the wrenches of the bodies below dof k, projected on its motion axis
-      const int b0 = m.dof_body[k], b1 = b0 + m.body_subsize[b0];
+      const int b0 = TB(dof_body)[k], b1 = b0 + TB(body_subsize)[b0];
       const float* cd = WS(W_CDOF) + 6 * k; const float* bf = WS(W_BV);
       NOUNROLL for (int b = b0; b < b1; ++b) if ((cb >> b) & 1u) {
         const float* w = bf + 6 * b;
@@ -2182,7 +2201,7 @@ DEV uint32_t active_set_signature(const ModelDev& m, const float* ws, int ncon, 
   }
   FOR_LANE(j, njnt) {
     const float sg = WS(W_LM_SIGN)[j];
-    if (sg != 0.f && (sg * qacc[m.jnt_dofadr[j]] - WS(W_LM_AREF)[j]) < 0.f) h ^= (uint32_t)(j + 2001) * 3266489917u;
+    if (sg != 0.f && (sg * qacc[TB(jnt_dofadr)[j]] - WS(W_LM_AREF)[j]) < 0.f) h ^= (uint32_t)(j + 2001) * 3266489917u;
   }
   return wxor(h) | 1u;       // never 0: 0 means "no factor yet"
 }
@@ -2265,7 +2284,7 @@ DEV_NOINLINE float newton_direction(const ModelDev& m, float* ws, int ncon, int 
     SYNC();
   }
   NOUNROLL for (int idx = lane; idx < npair; idx += LANES) {          // lower triangle only, one (i, j <= i) pair per lane
-    const int t = m.tri[idx], i = t >> 8, j = t & 255;
+    const int t = TB(tri)[idx], i = t >> 8, j = t & 255;
     float h = M[i * nv + j];
     if (few) {
       NOUNROLL for (int c = 0; c < ncon; ++c) {
@@ -2278,9 +2297,9 @@ DEV_NOINLINE float newton_direction(const ModelDev& m, float* ws, int ncon, int 
         h += J[i] * (gnn * jn + gn1 * j1 + gn2 * j2) + J[nv + i] * (gn1 * jn + g11 * j1) + J[2 * nv + i] * (gn2 * jn + g22 * j2);
       }
     } else {
-      const int bi = m.dof_body[i];
-      if (cbg && ((m.body_dofmask[bi] >> j) & 1)) {        // j moves body(i): contact inertias of the subtree of body(i)
-        const int bend = bi + m.body_subsize[bi];
+      const int bi = TB(dof_body)[i];
+      if (cbg && ((TB(body_dofmask)[bi] >> j) & 1)) {        // j moves body(i): contact inertias of the subtree of body(i)
+        const int bend = bi + TB(body_subsize)[bi];
         const float* di = cdof + 6 * i; const float* dj = cdof + 6 * j;
         NOUNROLL for (int b = bi; b < bend; ++b) if ((cbg >> b) & 1u) {
           const float* S = BS + 21 * b;
@@ -2296,7 +2315,7 @@ DEV_NOINLINE float newton_direction(const ModelDev& m, float* ws, int ncon, int 
       NOUNROLL for (int c = ncg; c < ncon; ++c) {        // geom-geom contacts: J = J(body 2) - J(body 1)
         const float* rec = CREC(c); const float* W = rec + CR_WW;
         if (W[0] < 0.f) continue;
-        const int b2 = ((const int*)rec)[CR_BODY], b1 = m.geom_body[-2 - ((const int*)rec)[CR_CELL]];
+        const int b2 = ((const int*)rec)[CR_BODY], b1 = TB(geom_body)[-2 - ((const int*)rec)[CR_CELL]];
         float off[3], ji[3], jj[3], t3[3]; v3sub(off, rec + CR_POS, scom);
         jac_col(m, ws, b2, i, off, ji); jac_col(m, ws, b1, i, off, t3); v3sub(ji, ji, t3);
         jac_col(m, ws, b2, j, off, jj); jac_col(m, ws, b1, j, off, t3); v3sub(jj, jj, t3);
@@ -2307,8 +2326,8 @@ DEV_NOINLINE float newton_direction(const ModelDev& m, float* ws, int ncon, int 
     if (i == j) {
       const float D = WS(W_FR_D)[i];
       if (D > 0.f) { const float x = WS(W_TMPW)[i], Rf = WS(W_FLOSS)[i] / D; if (x > -Rf && x < Rf) h += D; }
-      const int jn_ = m.dof_jnt[i]; const float sg = WS(W_LM_SIGN)[jn_];
-      if (sg != 0.f && m.jnt_dofadr[jn_] == i && (sg * qacc[i] - WS(W_LM_AREF)[jn_]) < 0.f) h += WS(W_LM_D)[jn_];
+      const int jn_ = TB(dof_jnt)[i]; const float sg = WS(W_LM_SIGN)[jn_];
+      if (sg != 0.f && TB(jnt_dofadr)[jn_] == i && (sg * qacc[i] - WS(W_LM_AREF)[jn_]) < 0.f) h += WS(W_LM_D)[jn_];
     }
     H[i * nv + j] = h;
   }
@@ -2469,14 +2488,14 @@ DEV void stage_smooth(const ModelDev& m, float* ws, int lane) {
   // smooth forces: passive damping - bias + actuation (ctrl clamp, gear, actuatorfrcrange clamp)
   rne_bias(m, ws, WS(W_TMPV), lane);
   float* fs = WS(W_FSMOOTH);
-  FOR_LANE(k, nv) fs[k] = -LDG(m.dof_damping + k) * WS(W_QVEL)[k] - WS(W_TMPV)[k];
+  FOR_LANE(k, nv) fs[k] = -LDG(TB(dof_damping) + k) * WS(W_QVEL)[k] - WS(W_TMPV)[k];
   SYNC();
   FOR_LANE(a, nu) {
     float c = WS(W_CTRL)[a];
-    if (m.act_ctrllimited[a]) c = fminf(LDG(m.act_ctrlrange + 2 * a + 1), fmaxf(LDG(m.act_ctrlrange + 2 * a), c));
-    float f = LDG(m.act_gear + a) * c;
-    const int k = m.act_dof[a], j = m.dof_jnt[k];
-    if (m.jnt_actfrclimited[j]) f = fminf(LDG(m.jnt_actfrcrange + 2 * j + 1), fmaxf(LDG(m.jnt_actfrcrange + 2 * j), f));
+    if (TB(act_ctrllimited)[a]) c = fminf(LDG(TB(act_ctrlrange) + 2 * a + 1), fmaxf(LDG(TB(act_ctrlrange) + 2 * a), c));
+    float f = LDG(TB(act_gear) + a) * c;
+    const int k = TB(act_dof)[a], j = TB(dof_jnt)[k];
+    if (TB(jnt_actfrclimited)[j]) f = fminf(LDG(TB(jnt_actfrcrange) + 2 * j + 1), fmaxf(LDG(TB(jnt_actfrcrange) + 2 * j), f));
     fs[k] += f;     // one actuator per joint in all four robots
   }
   SYNC();
@@ -2548,7 +2567,7 @@ DEV_NOINLINE int bad_state(const ModelDev& m, const float* ws, int lane) {
   return wor(bad);
 }
 DEV_NOINLINE void reset_data(const ModelDev& m, float* ws, int lane) {
-  FOR_LANE(i, MD(nq)) WS(W_QPOS)[i] = LDG(m.qpos0 + i);
+  FOR_LANE(i, MD(nq)) WS(W_QPOS)[i] = LDG(TB(qpos0) + i);
   FOR_LANE(i, MD(nv)) { WS(W_QVEL)[i] = 0.f; WS(W_WARM)[i] = 0.f; }
   SYNC();
 }
@@ -2566,7 +2585,7 @@ DEV_NOINLINE int substep_post(const ModelDev& m, float* ws, int lane, int iters)
   PH_DECL;
   const float dt = MO(timestep);
   float* A = WS(W_A); const float* M = WS(W_M);
-  FOR_LANE(i, nv * nv) { const int r = i / nv, c = i - r * nv; A[i] = M[i] + (r == c ? dt * LDG(m.dof_damping + r) : 0.f); }
+  FOR_LANE(i, nv * nv) { const int r = i / nv, c = i - r * nv; A[i] = M[i] + (r == c ? dt * LDG(TB(dof_damping) + r) : 0.f); }
   FOR_LANE(k, nv) WS(W_TMPV)[k] = WS(W_FSMOOTH)[k] + WS(W_FCON)[k];
   SYNC();
   chol_factor(m, A, WS(W_INVD), nv, lane, 1);
@@ -2575,8 +2594,8 @@ DEV_NOINLINE int substep_post(const ModelDev& m, float* ws, int lane, int iters)
   FOR_LANE(k, nv) qvel[k] += dt * WS(W_GRAD)[k];
   SYNC();
   FOR_LANE(j, njnt) {
-    const int qa = m.jnt_qposadr[j], da = m.jnt_dofadr[j];
-    if (m.jnt_type[j] == 0) {
+    const int qa = TB(jnt_qposadr)[j], da = TB(jnt_dofadr)[j];
+    if (TB(jnt_type)[j] == 0) {
       for (int k = 0; k < 3; ++k) qpos[qa + k] += dt * qvel[da + k];
       float w[3] = {qvel[da + 3], qvel[da + 4], qvel[da + 5]};
       float ang = v3norm(w) * dt;
@@ -2620,8 +2639,8 @@ DEV_NOINLINE void cfrc_ext(const ModelDev& m, float* ws, int ncon, int lane) {
       if (b1 > 0) { float* o1 = out + 6 * b1; for (int k = 0; k < 3; ++k) { o1[k] -= tq[k]; o1[3 + k] -= wf[k]; } }
     }
     NOUNROLL for (int e = 0; e < neq; ++e) {
-      const int b1 = m.eq_body1[e], b2 = m.eq_body2[e];
-      float a1[3] = {m.eq_anchor1[3 * e], m.eq_anchor1[3 * e + 1], m.eq_anchor1[3 * e + 2]}, p1[3], r[3], arm[3], tq[3];
+      const int b1 = TB(eq_body1)[e], b2 = TB(eq_body2)[e];
+      float a1[3] = {TB(eq_anchor1)[3 * e], TB(eq_anchor1)[3 * e + 1], TB(eq_anchor1)[3 * e + 2]}, p1[3], r[3], arm[3], tq[3];
       m3mulv(r, WS(W_XMAT) + 9 * b1, a1); v3add(p1, WS(W_XPOS) + 3 * b1, r);
       const float* wf = WS(W_EQ_F) + 3 * e;
       v3sub(arm, p1, scom); v3cross(tq, arm, wf);

@@ -63,19 +63,19 @@ DEV_NOINLINE void init_env(const ModelDev& m, const EnvArrays& E, int env, float
 #pragma unroll
   for (int i = 0; i < 8; ++i) draw[i] = fmaf(uni(m, env, RNG_MODEL, 0, i), m.rnd_span[i], m.rnd_lo[i]);
   const float slide = draw[0], floss = draw[3], delay = draw[4], load = draw[5], kps = draw[6], kds = draw[7];
-  FOR_LANE(b, nb) WS(W_BMASS)[b] = LDG(m.body_mass + b);
+  FOR_LANE(b, nb) WS(W_BMASS)[b] = LDG(TB(body_mass) + b);
   SYNC();
   FOR_LANE(i, MD(n_massnoise)) {
-    const int b = m.massnoise_body[i];
-    const float m0 = LDG(m.body_mass + b), mk = m0 * MO(mass_noise);
+    const int b = TB(massnoise_body)[i];
+    const float m0 = LDG(TB(body_mass) + b), mk = m0 * MO(mass_noise);
     float mass = m0 + fmaf(uni(m, env, RNG_MODEL, 0, 8 + i), 2.f * mk, -mk);
     if (b == MD(base_body)) mass += load;
     WS(W_BMASS)[b] = mass;
   }
-  FOR_LANE(g, ng) WS(W_GMU)[g] = m.geom_fr_random[g] ? slide : LDG(m.geom_friction + 3 * g);
-  FOR_LANE(k, nv) WS(W_FLOSS)[k] = m.dof_fl_random[k] ? floss : LDG(m.dof_frictionloss + k);
-  FOR_LANE(a, nu) { E.kp[(size_t)env * nu + a] = LDG(m.act_kp + a) * kps; E.kd[(size_t)env * nu + a] = LDG(m.act_kd + a) * kds; }
-  FOR_LANE(i, MD(nq)) WS(W_QPOS)[i] = LDG(m.qpos0 + i);
+  FOR_LANE(g, ng) WS(W_GMU)[g] = TB(geom_fr_random)[g] ? slide : LDG(TB(geom_friction) + 3 * g);
+  FOR_LANE(k, nv) WS(W_FLOSS)[k] = TB(dof_fl_random)[k] ? floss : LDG(TB(dof_frictionloss) + k);
+  FOR_LANE(a, nu) { E.kp[(size_t)env * nu + a] = LDG(TB(act_kp) + a) * kps; E.kd[(size_t)env * nu + a] = LDG(TB(act_kd) + a) * kds; }
+  FOR_LANE(i, MD(nq)) WS(W_QPOS)[i] = LDG(TB(qpos0) + i);
   SYNC();
   // mj_setConst at qpos0: M, M^-1, dof / body inverse weights, meaninertia
   kinematics(m, ws, lane); com_pos(m, ws, lane); crb(m, ws, lane);
@@ -94,8 +94,8 @@ DEV_NOINLINE void init_env(const ModelDev& m, const EnvArrays& E, int env, float
     SYNC();
   }
   FOR_LANE(j, njnt) {
-    const int a = m.jnt_dofadr[j];
-    if (m.jnt_type[j] == 0) {
+    const int a = TB(jnt_dofadr)[j];
+    if (TB(jnt_type)[j] == 0) {
       const float t = (M[a * nv + a] + M[(a + 1) * nv + a + 1] + M[(a + 2) * nv + a + 2]) / 3.f;
       const float r = (M[(a + 3) * nv + a + 3] + M[(a + 4) * nv + a + 4] + M[(a + 5) * nv + a + 5]) / 3.f;
       NOUNROLL for (int k = 0; k < 3; ++k) { WS(W_INVWD)[a + k] = t; WS(W_INVWD)[a + 3 + k] = r; }
@@ -132,7 +132,7 @@ DEV_NOINLINE void init_env(const ModelDev& m, const EnvArrays& E, int env, float
 // ------------------------------------------------------------------------------------------ observation build
 DEV_NOINLINE float trunc_noise(const ModelDev& m, int env, uint32_t nobs, int which, uint32_t idx) {
   if (MD(zero_noise)) return 0.f;
-  const float* nz = m.noise + 6 * which;
+  const float* nz = TB(noise) + 6 * which;
   const float u = uni(m, env, RNG_NOISE, nobs, idx);
   const float p = LDG(nz + 4) + u * (LDG(nz + 5) - LDG(nz + 4));
   float x = LDG(nz) + LDG(nz + 1) * ndtri(p);
@@ -147,8 +147,8 @@ DEV int raw_offset(const ModelDev& m, int kind) {
 DEV_NOINLINE void get_obs(const ModelDev& m, const EnvArrays& E, int env, float* ws, uint32_t nobs, int lane) {
   const int np = MD(n_dofpos), nvl = MD(n_dofvel), nu = MD(nu), rx = MD(hm_res_x), ry = MD(hm_res_y), nh = rx * ry;
   float* raw = WS(W_RAW); const float* qpos = WS(W_QPOS); const float* qvel = WS(W_QVEL); const float* S = WS(W_SENS);
-  FOR_LANE(i, np) raw[i] = qpos[m.dofpos_qadr[i]] * LDG(m.dofpos_fac + i) + trunc_noise(m, env, nobs, 0, i);
-  FOR_LANE(i, nvl) raw[np + i] = qvel[m.dofvel_dadr[i]] * LDG(m.dofvel_fac + i) + trunc_noise(m, env, nobs, 1, np + i);
+  FOR_LANE(i, np) raw[i] = qpos[TB(dofpos_qadr)[i]] * LDG(TB(dofpos_fac) + i) + trunc_noise(m, env, nobs, 0, i);
+  FOR_LANE(i, nvl) raw[np + i] = qvel[TB(dofvel_dadr)[i]] * LDG(TB(dofvel_fac) + i) + trunc_noise(m, env, nobs, 1, np + i);
   FOR_LANE(i, 3) {
     const int o = np + nvl;
     raw[o + i] = S[4 + i] + trunc_noise(m, env, nobs, 2, o + i);
@@ -182,9 +182,9 @@ DEV_NOINLINE void get_obs(const ModelDev& m, const EnvArrays& E, int env, float*
 // noise draw index convention: position in [dof_pos | dof_vel | ang_vel | lin_vel | proj_grav | height_map]
 
 DEV_NOINLINE void concat_obs(const ModelDev& m, const EnvArrays& E, int env, const float* ws, int sim_step, bool stacked, const float* cmd, float* out, int lane) {
-  const int* kind = stacked ? m.sobs_kind : m.nobs_kind; const int* dim = stacked ? m.sobs_dim : m.nobs_dim;
-  const float* scale = stacked ? m.sobs_scale : m.nobs_scale; const int* itv = stacked ? m.sobs_interval : m.nobs_interval;
-  const int* off = stacked ? m.sobs_off : m.nobs_off; const int n = stacked ? MD(n_sobs) : MD(n_nobs);
+  const int* kind = stacked ? TB(sobs_kind) : TB(nobs_kind); const int* dim = stacked ? TB(sobs_dim) : TB(nobs_dim);
+  const float* scale = stacked ? TB(sobs_scale) : TB(nobs_scale); const int* itv = stacked ? TB(sobs_interval) : TB(nobs_interval);
+  const int* off = stacked ? TB(sobs_off) : TB(nobs_off); const int n = stacked ? MD(n_sobs) : MD(n_nobs);
   float* cache = E.freq_cache + (size_t)env * imax(1, MD(cache_dim));
   int o = 0;
   NOUNROLL for (int k = 0; k < n; ++k) {
@@ -219,8 +219,8 @@ DEV_NOINLINE void build_state(const ModelDev& m, const EnvArrays& E, int env, fl
   // command slots inside stacked frames carry the current command in every frame
   int o = 0;
   NOUNROLL for (int k = 0; k < MD(n_sobs); ++k) {
-    if (m.sobs_kind[k] == OBS_COMMAND) for (int f = 1; f < ss; ++f) FOR_LANE(i, m.sobs_dim[k]) EST(state + f * sd + o + i, cmd ? cmd[i] : 0.f);
-    o += m.sobs_dim[k];
+    if (TB(sobs_kind)[k] == OBS_COMMAND) for (int f = 1; f < ss; ++f) FOR_LANE(i, TB(sobs_dim)[k]) EST(state + f * sd + o + i, cmd ? cmd[i] : 0.f);
+    o += TB(sobs_dim)[k];
   }
 }
 
@@ -233,7 +233,7 @@ DEV_NOINLINE void reset_env(const ModelDev& m, const EnvArrays& E, int env, floa
   FOR_LANE(i, nq) WS(W_QPOS)[i] = (i == 2) ? MO(z0) : (i == 3 ? 1.f : 0.f);
   SYNC();
   const float lo = -MO(init_noise), hi = MO(init_noise);
-  FOR_LANE(i, MD(n_initnoise)) WS(W_QPOS)[m.initnoise_qadr[i]] += fmaf(uni(m, env, RNG_RESET, nreset, i), hi - lo, lo);
+  FOR_LANE(i, MD(n_initnoise)) WS(W_QPOS)[TB(initnoise_qadr)[i]] += fmaf(uni(m, env, RNG_RESET, nreset, i), hi - lo, lo);
   FOR_LANE(i, nv) { WS(W_QVEL)[i] = 0.f; WS(W_WARM)[i] = 0.f; }
   FOR_LANE(i, nu) { WS(W_CTRL)[i] = 0.f; WS(W_ACT)[i] = 0.f; E.prev_action[(size_t)env * nu + i] = 0.f; E.delay_prev[(size_t)env * nu + i] = 0.f; E.torque[(size_t)env * nu + i] = 0.f; E.last_action[(size_t)env * nu + i] = 0.f; }
   SYNC();
@@ -299,17 +299,17 @@ DEV void step_prologue(const ModelDev& m, const EnvArrays& E, int env, float* ws
     const float f = delay ? E.delay_prev[(size_t)env * nu + k] : ak;
     E.delay_prev[(size_t)env * nu + k] = ak;
     WS(W_ACT)[k] = ak;
-    const float target = f * LDG(m.act_scale + k);
+    const float target = f * LDG(TB(act_scale) + k);
     float tq;
-    if (m.act_mode[k] == 0) {
-      const float pf = LDG(m.act_posfac + k);
-      const float q = WS(W_QPOS)[m.act_qadr[k]] * pf, qd = WS(W_QVEL)[m.act_dof[k]] * pf;
+    if (TB(act_mode)[k] == 0) {
+      const float pf = LDG(TB(act_posfac) + k);
+      const float q = WS(W_QPOS)[TB(act_qadr)[k]] * pf, qd = WS(W_QVEL)[TB(act_dof)[k]] * pf;
       tq = WS(W_KP)[k] * (target - q) + WS(W_KD)[k] * (0.f - qd);
-      tq = tq * LDG(m.act_gamma + k);
+      tq = tq * LDG(TB(act_gamma) + k);
     } else {
-      tq = WS(W_KD)[k] * (target - WS(W_QVEL)[m.act_dof[k]]);
+      tq = WS(W_KD)[k] * (target - WS(W_QVEL)[TB(act_dof)[k]]);
     }
-    const float cl = LDG(m.act_clip + k);
+    const float cl = LDG(TB(act_clip) + k);
     tq = fminf(cl, fmaxf(-cl, tq));
     WS(W_CTRL)[k] = tq;
     E.torque[(size_t)env * nu + k] = tq;
@@ -337,7 +337,7 @@ DEV void step_epilogue(const ModelDev& m, const EnvArrays& E, int env, float* ws
   // termination: signed cfrc_ext component above threshold on the listed bodies
   int term = 0;
   { const float* cf = WS(W_CACC); const float thr = MO(term_threshold);
-    FOR_LANE(i, 6 * MD(n_term_body)) term |= (cf[6 * m.term_body[i / 6] + i % 6] > thr);
+    FOR_LANE(i, 6 * MD(n_term_body)) term |= (cf[6 * TB(term_body)[i / 6] + i % 6] > thr);
     term = wor(term); }
   if (E.dbg_cfrc) FOR_LANE(i, 6 * nb) E.dbg_cfrc[(size_t)env * 6 * nb + i] = WS(W_CACC)[i];
   dump_contacts(m, E, env, ws, ncon, lane);

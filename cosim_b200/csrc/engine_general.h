@@ -34,7 +34,7 @@ DEV float gen_dot(const float* a, const float* b, int n) { float s = 0.f; NOUNRO
 
 // rotational Jacobian column of dof k for `body` (world frame): the motion axis if k moves the body
 DEV void jac_col_rot(const ModelDev& m, const float* ws, int body, int k, float* jr) {
-  if ((m.body_dofmask[body] >> k) & 1) { const float* cd = WS(W_CDOF) + 6 * k; jr[0] = cd[0]; jr[1] = cd[1]; jr[2] = cd[2]; }
+  if ((TB(body_dofmask)[body] >> k) & 1) { const float* cd = WS(W_CDOF) + 6 * k; jr[0] = cd[0]; jr[1] = cd[1]; jr[2] = cd[2]; }
   else { jr[0] = jr[1] = jr[2] = 0.f; }
 }
 
@@ -64,9 +64,9 @@ DEV_NOINLINE int gen_make_rows(const ModelDev& m, float* ws, int ncon, int lane)
   NOUNROLL for (int c = lane; c < ncg; c += LANES) {
     const float* rec = CREC(c); float* cc = G.con + (size_t)c * GC_STRIDE;
     const int g2 = ((const int*)rec)[CR_GEOM], cell = ((const int*)rec)[CR_CELL];
-    float tor = m.geom_fr_random[g2] ? WS(W_SCAL)[4] : LDG(m.geom_friction + 3 * g2 + 1), rol = m.geom_fr_random[g2] ? WS(W_SCAL)[5] : LDG(m.geom_friction + 3 * g2 + 2);
+    float tor = TB(geom_fr_random)[g2] ? WS(W_SCAL)[4] : LDG(TB(geom_friction) + 3 * g2 + 1), rol = TB(geom_fr_random)[g2] ? WS(W_SCAL)[5] : LDG(TB(geom_friction) + 3 * g2 + 2);
     if (cell <= -2) { const int g1 = -2 - cell;
-      tor = fmaxf(tor, m.geom_fr_random[g1] ? WS(W_SCAL)[4] : LDG(m.geom_friction + 3 * g1 + 1)); rol = fmaxf(rol, m.geom_fr_random[g1] ? WS(W_SCAL)[5] : LDG(m.geom_friction + 3 * g1 + 2));
+      tor = fmaxf(tor, TB(geom_fr_random)[g1] ? WS(W_SCAL)[4] : LDG(TB(geom_friction) + 3 * g1 + 1)); rol = fmaxf(rol, TB(geom_fr_random)[g1] ? WS(W_SCAL)[5] : LDG(TB(geom_friction) + 3 * g1 + 2));
     } else { tor = fmaxf(tor, m.ground_friction[3] != 0.f ? WS(W_SCAL)[4] : m.ground_friction[1]); rol = fmaxf(rol, m.ground_friction[3] != 0.f ? WS(W_SCAL)[5] : m.ground_friction[2]); }
     const float sl = fmaxf(rec[CR_MU], 1e-5f);
     cc[GC_FRIC] = cc[GC_FRIC + 1] = sl; cc[GC_FRIC + 2] = fmaxf(tor, 1e-5f); cc[GC_FRIC + 3] = cc[GC_FRIC + 4] = fmaxf(rol, 1e-5f);
@@ -79,11 +79,11 @@ DEV_NOINLINE int gen_make_rows(const ModelDev& m, float* ws, int ncon, int lane)
     float v = 0.f;
     if (type == GT_EQ) v = WS(W_EQ_J)[(size_t)id * nv + k];
     else if (type == GT_FRICTION) v = (k == id) ? 1.f : 0.f;
-    else if (type == GT_LIMIT) v = (k == m.jnt_dofadr[id]) ? WS(W_LM_SIGN)[id] : 0.f;
+    else if (type == GT_LIMIT) v = (k == TB(jnt_dofadr)[id]) ? WS(W_LM_SIGN)[id] : 0.f;
     else {
       const int c = id & 0xffff, sub = id >> 16;
       const float* rec = CREC(c); const float* cc = G.con + (size_t)c * GC_STRIDE; const float* fr = rec + CR_FRAME;
-      const int b2 = ((const int*)rec)[CR_BODY], cell = ((const int*)rec)[CR_CELL], b1 = cell <= -2 ? m.geom_body[-2 - cell] : 0;
+      const int b2 = ((const int*)rec)[CR_BODY], cell = ((const int*)rec)[CR_CELL], b1 = cell <= -2 ? TB(geom_body)[-2 - cell] : 0;
       float off[3], jp[3], jr[3]; v3sub(off, rec + CR_POS, scom);
       jac_col(m, ws, b2, k, off, jp); jac_col_rot(m, ws, b2, k, jr);
       if (b1 > 0) { float t[3]; jac_col(m, ws, b1, k, off, t); v3sub(jp, jp, t); jac_col_rot(m, ws, b1, k, t); v3sub(jr, jr, t); }
@@ -114,7 +114,7 @@ DEV_NOINLINE int gen_make_rows(const ModelDev& m, float* ws, int ncon, int lane)
       const float* rec = CREC(c); const float* cc = G.con + (size_t)c * GC_STRIDE;
       const float vel = gen_dot(G.J + (size_t)r * nv, WS(W_QVEL), nv), dist = rec[CR_DIST], imp = impedance(solimp, dist);
       float tran = WS(W_INVWB)[((const int*)rec)[CR_BODY]];
-      { const int cell = ((const int*)rec)[CR_CELL]; if (cell <= -2) { const int b1 = m.geom_body[-2 - cell]; if (b1 > 0) tran += WS(W_INVWB)[b1]; } }
+      { const int cell = ((const int*)rec)[CR_CELL]; if (cell <= -2) { const int b1 = TB(geom_body)[-2 - cell]; if (b1 > 0) tran += WS(W_INVWB)[b1]; } }
       const float f0 = cc[GC_FRIC], mu = cc[GC_MU];
       float R;
       if (type == GT_CONTACT) {
@@ -255,7 +255,7 @@ DEV_NOINLINE float gen_direction(const ModelDev& m, float* ws, int nefc, int ncg
   SYNC();
   const int npair = (nv * (nv + 1)) >> 1;
   NOUNROLL for (int idx = lane; idx < npair; idx += LANES) {          // lower triangle, one (i, j <= i) pair per lane
-    const int t = m.tri[idx], i = t >> 8, j = t & 255;
+    const int t = TB(tri)[idx], i = t >> 8, j = t & 255;
     float h = M[i * nv + j];
     NOUNROLL for (int r = 0; r < nefc; ++r) {
       const int st = G.state[r];
