@@ -46,7 +46,7 @@ ROBOT, TERRAIN = "flamingo_p_v3", "rocky_hard"
 B_ALG = 1832      # algorithmic HBM bytes per env-step, flamingo_p_v3 with height map
 
 
-def workload_config(name="flamingo_rocky"):
+def workload_config(name="flamingo_rocky", spawn_spread=0.0):
     from cosim_b200.config import make_config, RANDOM_FULL, RANDOM_NONE, RANDOM_DEFAULTS, load_tables
     w = WORKLOADS[name]
     et, _ = load_tables()
@@ -56,7 +56,10 @@ def workload_config(name="flamingo_rocky"):
     if w.get("position"):
         kw["position_command"] = True; kw["command_dim"] = 2
     rnd = {"full": RANDOM_FULL, "none": RANDOM_NONE, "defaults": RANDOM_DEFAULTS}[w["random"]]
-    return make_config(w["robot"], w["terrain"], random=rnd, engine={"auto_reset": True, "seed": 0xC051}, **kw)
+    eng = {"auto_reset": True, "seed": 0xC051}
+    if spawn_spread > 0:
+        eng["spawn_spread"] = float(spawn_spread)
+    return make_config(w["robot"], w["terrain"], random=rnd, engine=eng, **kw)
 
 
 def workload_text(name, N):
@@ -189,7 +192,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cfg = workload_config(args.config)
+    cfg = workload_config(args.config, args.spawn_spread)
     n = args.cpu_envs
     # `--steps K --warmup W` of the driver apply to the GPU arm's step; the CPU arm steps a bounded sample for >= 1 s per "step" budget
     value, cores, dt, steps = cpu_reference(cfg, n, min_seconds=max(1.0, args.cpu_seconds), warmup=2)
@@ -222,6 +225,7 @@ def main():
     ap.add_argument("--steady-steps", type=int, default=200, help="length of the steady-state window (0 = skip)")
     ap.add_argument("--steady-seconds", type=float, default=40.0, help="wall-clock cap of the steady-state warm-up and of its window")
     ap.add_argument("--policy", default="mlp", choices=["mlp", "zero"], help="mlp: synthetic random MLP (headline); zero: PD hold of the reset pose (robots stay on the terrain)")
+    ap.add_argument("--spawn-spread", type=float, default=0.0, help="variant: per-env spawn offsets of up to this many metres over the terrain (0 = the reference's spawn at the origin, the headline)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     # stdout carries exactly one JSON line: libraries that print to fd 1 (NCCL's version banner under torchrun) are sent to
@@ -254,7 +258,7 @@ def main():
         total_envs = size
     else:
         N, offset, total_envs = size, rank * size, world * size
-    cfg = workload_config(args.config)
+    cfg = workload_config(args.config, args.spawn_spread)
     env = BatchedEnv(cfg, N, device=dev, seed=0xC051, env_offset=offset)     # RNG substream = global env id
     pol = MLPPolicy(synthetic_mlp(env.state_dim, env.action_dim), "elu", dev)
     gen = torch.Generator(device=dev); gen.manual_seed(1000 + rank)
@@ -389,7 +393,7 @@ def main():
     out = {"metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps, "warmup": warm,
            "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
            "dtype": "f32 (physics), bf16 x bf16 -> f32 (policy MLP)", "data": "synthetic",
-           "config": {"workload": workload_text(args.config, N), "name": args.config, "envs_per_gpu": N, "total_envs": total_envs, "policy": args.policy,
+           "config": {"workload": workload_text(args.config, N) + (f", spawn offsets up to {args.spawn_spread:g} m over the terrain (variant, not the reference's spawn)" if args.spawn_spread > 0 else ""), "name": args.config, "envs_per_gpu": N, "total_envs": total_envs, "policy": args.policy, "spawn_spread_m": args.spawn_spread,
                       "sub_steps_per_s": value * 4,
                       "l2": "per-env state, parameter and observation arrays total > 126 MB L2 at 65 536 envs (inputs larger than L2); no explicit flush"},
            "clocks": clk, "gpu_launches": launches,

@@ -10,7 +10,7 @@ Extensions (not in the reference, all optional):
   config["random"][knob] may be a 2-list [lo, hi] -> drawn per env ~ U(lo, hi)
   config["random"]["kp_scale"] / ["kd_scale"]: [lo, hi] per-env gain multipliers
   config["random"]["sensor_noise"] == "zero": a true-zero noise level (SURVEY cfg 2)
-  config["engine"]: {"seed", "ncon_max", "auto_reset", "self_collision", "condim", "cone", "solver", "impratio", "iterations"}
+  config["engine"]: {"seed", "ncon_max", "auto_reset", "self_collision", "condim", "cone", "solver", "impratio", "iterations", "spawn_spread", "spawn_radius"}
 """
 import copy
 import os

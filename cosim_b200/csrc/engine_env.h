@@ -234,6 +234,26 @@ DEV_NOINLINE void reset_env(const ModelDev& m, const EnvArrays& E, int env, floa
   SYNC();
   const float lo = -MO(init_noise), hi = MO(init_noise);
   FOR_LANE(i, MD(n_initnoise)) WS(W_QPOS)[TB(initnoise_qadr)[i]] += fmaf(uni(m, env, RNG_RESET, nreset, i), hi - lo, lo);
+  // optional spawn offset (engine.spawn_spread, not in the reference: oracle.hpp reset has the same lines): uniform in
+  // [-spread, spread]^2, lifted by the highest terrain vertex within spawn_radius of the spot
+  const float spread = MO(spawn_spread);
+  if (spread > 0.f) {
+    const float ox = (2.f * uni(m, env, RNG_RESET, nreset, 1000u) - 1.f) * spread, oy = (2.f * uni(m, env, RNG_RESET, nreset, 1001u) - 1.f) * spread;
+    float hmax = 0.f;
+    if (MD(ground_type) == 1) {
+      const int ncol = MD(hf_ncol), nrow = MD(hf_nrow);
+      const float sx = MO(hf_sx), sy = MO(hf_sy), rad = MO(spawn_radius);
+      const float dx = 2.f * sx / (float)(ncol - 1), dy = 2.f * sy / (float)(nrow - 1);
+      const int c0 = imax(0, (int)floorf((ox - rad + sx) / dx)), c1 = imin(ncol - 1, (int)ceilf((ox + rad + sx) / dx));
+      const int r0 = imax(0, (int)floorf((oy - rad + sy) / dy)), r1 = imin(nrow - 1, (int)ceilf((oy + rad + sy) / dy));
+      const int w = c1 - c0 + 1, cnt = w * (r1 - r0 + 1);
+      float h = -INFINITY;
+      FOR_LANE(t, cnt) h = fmaxf(h, LDGB(m.hfield_data + (size_t)(r0 + t / w) * ncol + c0 + t % w));
+      hmax = wmaxf(h) * MO(hf_sz);
+    }
+    SYNC();
+    if (lane == 0) { WS(W_QPOS)[0] += ox; WS(W_QPOS)[1] += oy; WS(W_QPOS)[2] += hmax; }
+  }
   FOR_LANE(i, nv) { WS(W_QVEL)[i] = 0.f; WS(W_WARM)[i] = 0.f; }
   FOR_LANE(i, nu) { WS(W_CTRL)[i] = 0.f; WS(W_ACT)[i] = 0.f; E.prev_action[(size_t)env * nu + i] = 0.f; E.delay_prev[(size_t)env * nu + i] = 0.f; E.torque[(size_t)env * nu + i] = 0.f; E.last_action[(size_t)env * nu + i] = 0.f; }
   SYNC();

@@ -36,7 +36,7 @@ OPTS = ["timestep", "gx", "gy", "gz", "tolerance", "ls_tolerance", "ccd_toleranc
         "solref0", "solref1", "solimp0", "solimp1", "solimp2", "solimp3", "solimp4",
         "slide_lo", "slide_hi", "tors_lo", "tors_hi", "roll_lo", "roll_hi", "floss_lo", "floss_hi",
         "delay_lo", "delay_hi", "mass_noise", "load_lo", "load_hi", "kp_lo", "kp_hi", "kd_lo", "kd_hi",
-        "plane_sx", "plane_sy", "impratio"]
+        "plane_sx", "plane_sy", "impratio", "spawn_spread", "spawn_radius"]
 DIM = {k: i for i, k in enumerate(DIMS)}
 OPT = {k: i for i, k in enumerate(OPTS)}
 
@@ -541,6 +541,14 @@ def build_model(config, ncon_max=None, auto_reset=False):
     impratio = float(eng.get("impratio", 1.0))
     if impratio <= 0:
         raise ValueError("engine.impratio must be positive")
+    # Not in the reference (it spawns every robot at the origin, on the flat centre patch of its rasters): an optional per-env spawn
+    # offset, uniform in [-spawn_spread, spawn_spread]^2 m, lifted by the highest terrain vertex within spawn_radius of the spot
+    # (bench.py --spawn-spread: robots that stand on rough cells from the first step on).  0 = the reference's spawn.
+    spawn_spread, spawn_radius = float(eng.get("spawn_spread", 0.0)), float(eng.get("spawn_radius", 0.6))
+    if spawn_spread < 0 or spawn_radius < 0:
+        raise ValueError("engine.spawn_spread / spawn_radius must not be negative")
+    if ground_type == 1 and spawn_spread + spawn_radius >= min(hf_size[0], hf_size[1]):
+        raise ValueError("engine.spawn_spread reaches beyond the terrain")
     rows_per_contact = 1 if condim == 1 else (condim if cone == 1 else 2 * (condim - 1))
     nefc_max = 3 * neq + nfl_upper + nlimit_max + rows_per_contact * ncon_max
 
@@ -580,7 +588,7 @@ def build_model(config, ncon_max=None, auto_reset=False):
          slide_lo=sl[0], slide_hi=sl[1], tors_lo=tl[0], tors_hi=tl[1], roll_lo=rl[0], roll_hi=rl[1],
          floss_lo=fl[0], floss_hi=fl[1], delay_lo=dl[0], delay_hi=dl[1], mass_noise=float(rnd["mass_noise"]),
          load_lo=ld[0], load_hi=ld[1], kp_lo=kpr[0], kp_hi=kpr[1], kd_lo=kdr[0], kd_hi=kdr[1],
-         plane_sx=100.0, plane_sy=100.0, impratio=impratio)
+         plane_sx=100.0, plane_sy=100.0, impratio=impratio, spawn_spread=spawn_spread, spawn_radius=spawn_radius)
 
     def w0(a, fill=0.0):  # prepend the world body row
         a = np.asarray(a)

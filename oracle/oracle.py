@@ -14,9 +14,18 @@ _LIB = os.path.join(_HERE, "_build", "liboracle.so")
 _lib = None
 
 
+def _stale():
+    if not os.path.exists(_LIB):
+        return True
+    t = os.path.getmtime(_LIB)
+    srcs = [os.path.join(_HERE, f) for f in ("oracle.hpp", "oracle_math.hpp", "oracle_capi.cpp", "Makefile")] + \
+           [os.path.join(_HERE, "..", "include", "cosim_blob.h")]
+    return any(os.path.exists(f) and os.path.getmtime(f) > t for f in srcs)
+
+
 def build(force=False):
-    if force or not os.path.exists(_LIB):
-        subprocess.check_call(["make", "-C", _HERE], stdout=subprocess.DEVNULL)
+    if force or _stale():
+        subprocess.check_call(["make", "-B", "-C", _HERE], stdout=subprocess.DEVNULL)
     return _LIB
 
 

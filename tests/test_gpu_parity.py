@@ -53,6 +53,37 @@ def test_reset_state_bit_exact(robot, terrain):
     env.close()
 
 
+@pytest.mark.parametrize("robot,terrain,spread", [("flamingo_p_v3", "rocky_hard", 30.0), ("w4_p_v2", "stairs_up_hard", 3.0), ("flamingo_light_v1", "flat", 30.0)])
+def test_spawn_spread_reset_and_steps(robot, terrain, spread):
+    """engine.spawn_spread (bench.py --spawn-spread; not in the reference): the CUDA reset draws the same spots and lifts as the
+    oracle, nothing spawns inside the terrain, and teacher-forced steps from those spots agree like the ones from the origin."""
+    N = 256
+    env = _env(robot, terrain, N, hm=(robot == "flamingo_p_v3"), engine={"spawn_spread": spread})
+    orc = _oracle(env, N)
+    s_o = orc.reset(); s_g, _ = env.reset()
+    q_o, q_g = orc.get("qpos"), env.get("qpos").cpu().numpy()
+    np.testing.assert_allclose(q_g, q_o, atol=2e-6)
+    np.testing.assert_allclose(s_g.cpu().numpy(), s_o, atol=3e-5)          # height-map rays up to 30 m from the origin in fp32
+    assert np.abs(q_o[:, :2]).max() <= spread and q_o[:, :2].std() > 0.4 * spread          # uniform in [-spread, spread]: std = 0.58 spread
+    cap = env.model.dim("ncon_max")
+    for e in range(0, N, 16):
+        c = orc.contacts(e, cap)
+        assert len(c) == 0 or c[:, 0].min() > -5e-3          # the reference's own spawn height leaves the wheels 0.7 - 2.8 mm inside the ground
+    same = []
+    a = np.zeros((N, env.action_dim))
+    for i in range(6):                                # PD hold: the robots settle on the rough cells under them
+        for k in ("qpos", "qvel", "qacc_warmstart"):
+            env.set(k, orc.get(k))
+        orc.step(a); s, _, _, _ = env.step(a)
+        assert np.isfinite(s.cpu().numpy()).all()
+        nco, ncg = orc.get("ncon")[:, 0].astype(int), env.get("counters")[:, 7].cpu().numpy()
+        same.append((nco == ncg).mean())
+        assert float(env.get("stats")[:, 13].sum()) == 0.0, "a contact was dropped"
+    print(f"{robot}/{terrain} with spawn offsets: contact counts agree in {min(same):.3f} of the envs, mean contacts {nco.mean():.2f}")
+    assert min(same) >= 0.97
+    env.close()
+
+
 def test_contact_free_window_1e5():
     """flamingo_p_v3 dropped from z0 + 0.5 m: 13 control steps = 52 sub-steps without contact."""
     N = 32

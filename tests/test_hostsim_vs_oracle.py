@@ -243,3 +243,36 @@ def test_tree_sparse_cholesky_against_numpy(robot, terrain):
     b = rng.normal(size=nv)
     x = h.chol_solve(F, b, 0)
     assert np.abs(F @ x - b).max() < 1e-4 * max(1.0, np.abs(b).max()) * nv
+
+
+def test_spawn_spread_reset():
+    """engine.spawn_spread (not in the reference, off by default): per-env spawn spots spread over the terrain, lifted by the highest
+    terrain vertex within spawn_radius.  Engine logic == oracle, spots differ per env and stay inside the spread, nothing spawns inside
+    the terrain, and spread 0 is the reference's spawn at the origin."""
+    et, _ = load_tables()
+    kw = dict(non_stacked_obs_order=list(et["flamingo_p_v3"]["non_stacked_obs_order"]) + ["height_map"])
+    m0 = build_model(make_config("flamingo_p_v3", "rocky_hard", random=RANDOM_NONE, **kw))
+    m = build_model(make_config("flamingo_p_v3", "rocky_hard", random=RANDOM_NONE, engine={"spawn_spread": 25.0}, **kw))
+    N = 16
+    o, h, o0 = Oracle(m, N, seed=7), HostSim(m, N, seed=7), Oracle(m0, N, seed=7)
+    s_o, s_h, s_0 = o.reset(), h.reset(), o0.reset()
+    np.testing.assert_allclose(s_h, s_o, atol=2e-5)          # height-map rays 25 m from the origin: fp32 world coordinates resolve 2e-6 m
+    q, q0 = o.get("qpos"), o0.get("qpos")
+    np.testing.assert_allclose(h.get("qpos"), q, atol=1e-6)
+    assert np.abs(q0[:, :2]).max() == 0.0 and np.abs(q[:, :2]).max() <= 25.0
+    assert len(np.unique(np.round(q[:, 0], 3))) == N and np.abs(q[:, :2]).max() > 5.0
+    assert (q[:, 2] >= q0[:, 2] - 1e-9).all() and (q[:, 2] > q0[:, 2] + 1e-3).any()        # lifted by the local terrain height
+    cap = m.dim("ncon_max")
+    for e in range(N):                                                                         # nothing starts inside the terrain
+        c = o.contacts(e, cap)
+        assert len(c) == 0 or c[:, 0].min() > -5e-3
+    assert not np.allclose(s_o, s_0)                                                           # the height map sees other terrain
+    a = np.zeros((N, m.dim("nu")))
+    for _ in range(3):
+        for k in ("qpos", "qvel", "qacc_warmstart"):
+            h.set(k, o.get(k))
+        so, to, _ = o.step(a); sh, th, _ = h.step(a)
+        assert np.isfinite(sh).all() and (o.get("ncon_dropped") == 0).all()
+    # a second reset of the same env draws a new spot (the draw is keyed by the reset counter)
+    o.reset()
+    assert np.abs(o.get("qpos")[:, :2] - q[:, :2]).max() > 1.0
