@@ -123,7 +123,12 @@ int cosim_create(const void* blob, size_t nbytes, int num_envs, int device, uint
   cudaError_t e2 = cudaFuncSetAttribute(h->k.reset, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 16);
   cudaError_t e3 = cudaFuncSetAttribute(h->k.step, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 16);
   if (e3 == cudaSuccess) e3 = cudaFuncSetAttribute(h->k.substep, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 16);
-  cudaFuncSetAttribute(h->k.step, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  { // shared-memory carve-out of the unified 256 KB: what the CTA needs, rounded up by the driver to one of its configurations -- the
+    // rest is L1, which is all the stack frames / spills of the out-of-line device functions have before L2 (COSIM_CARVEOUT = percent overrides)
+    int carve = (int)((h->smem + 1024 + 2621) / 2622);          // percent of 256 KB, rounded up
+    if (carve > 100) carve = 100;
+    { const char* e = getenv("COSIM_CARVEOUT"); if (e && atoi(e) >= 0 && atoi(e) <= 100) carve = atoi(e); }
+    cudaFuncSetAttribute(h->k.step, cudaFuncAttributePreferredSharedMemoryCarveout, carve); }
   if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) { fprintf(stderr, "cosim_create: cudaFuncSetAttribute failed: %s\n", cudaGetErrorString(e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3))); for (void* p : h->allocs) cudaFree(p); delete h; return COSIM_ERR_CUDA; }
   // grid = the CTAs that are resident at once (persistent CTAs walk over chunks of wpb environments); every resident warp
   // owns one global-memory slot for the contact records that do not fit its shared-memory tier

@@ -51,6 +51,9 @@ struct float4 { float x, y, z, w; };
 #define LDG(p) (*(p))
 #define LDGB(p) (*(p))
 #define SHP(p) (p)
+typedef float* WSP;
+#define WSF(w) (w)
+#define LANE_REFRESH() ((void)0)
 static inline float wsum(float v) { return v; }
 static inline float wmaxf(float v) { return v; }
 static inline int wor(int v) { return v; }
@@ -89,6 +92,16 @@ template <class T> struct ShTab {      // read-only table in shared memory, addr
 };
 template <class T> static __device__ __forceinline__ ShTab<T> shp_(const T* p) { return ShTab<T>{(uint32_t)__cvta_generic_to_shared(p)}; }
 #define SHP(p) shp_(p)
+// The env's workspace travels through the out-of-line functions as its 32-bit shared-window address, not as a 64-bit generic pointer
+// (one register / stack slot instead of two on every call; the loads stay LDS because the address space is known at the conversion).
+struct WSP { uint32_t a; };
+// `lane` is re-read from the special register at the top of every out-of-line function: the parameter then dies (the functions are
+// static, so it is not passed at all) instead of travelling through local memory next to ws: +3 % on flamingo_p_v3 (same-box A / B,
+// profiles/r02_experiments.md).  Same values, but another instruction order: results differ from the previous build in the last bits
+// (tools/lib_check.py), as they do between any two builds.
+static __device__ __forceinline__ int lane_id_() { int l; asm("mov.u32 %0, %%laneid;" : "=r"(l)); return l; }
+#define LANE_REFRESH() lane = lane_id_()
+#define WSF(w) ((float*)__cvta_shared_to_generic((size_t)(w).a))
 #define LDG(p) (*(p))          // small model tables: shared-memory copy of the arena (plain load; __ldg would fault)
 #define LDGB(p) __ldg(p)       // big read-only tables in global memory: hull vertices, support maps, height field
 DEV float wsum(float v) {
@@ -219,6 +232,7 @@ struct ModelDev {
   // conservative culls ahead of the terrain narrow phase: max height per 8 x 8 block of cells, and per-geom bounding
   // cylinders (geom frame: centre, unit axis, radius, half length; radius 0 = none)
   const float* hf_max8; int hf_mrow, hf_mcol; const float* geom_bcyl;
+  int hf_fine;                    // raster cells under 0.2 m: the terrain pass with culls and block-wise sweep (collide_hfield_all<true>)
   // general constraint path (engine_general.h: condim 1 / 4 / 6, elliptic cone, PGS): on / off, row capacity, float offset of its
   // region inside the env's global-memory slot (behind the contact-record overflow)
   int general, gen_rows; unsigned long long gen_off;
@@ -242,11 +256,11 @@ enum WsField {
   W_EQ_J, W_EQ_D, W_EQ_AREF, W_EQ_X, W_EQ_V, W_EQ_F, W_SENS, W_RAW, W_ACT, W_FILT, W_KP, W_KD, W_GTASK, W_CNT, W_PAXIS, W__COUNT   // keep <= 80 (ModelDev::off)
 };
 static_assert(W__COUNT <= 80, "ModelDev::off too small");
-#define WS(f) (ws + m.off[f])
-#define WSI(f) ((int*)(ws + m.off[f]))
+#define WS(f) (WSF(ws) + m.off[f])
+#define WSI(f) ((int*)(WSF(ws) + m.off[f]))
 // record of contact c: shared-memory tier below cn_k, else the warp's global overflow slot (pointer kept in W_GPTR)
 #define CREC(c) cn_rec(m, ws, (c))
-#define CRECS(c) (ws + m.off[W_CN_REC] + (c) * CR_STRIDE)      /* few-contact paths: every record is in the shared-memory tier (cn_k >= FEW_CONTACTS) */
+#define CRECS(c) (WSF(ws) + m.off[W_CN_REC] + (c) * CR_STRIDE)      /* few-contact paths: every record is in the shared-memory tier (cn_k >= FEW_CONTACTS) */
 #define CRECI(c) ((int*)cn_rec(m, ws, (c)))
 // contact record (floats): position, frame (normal, t1, t2 rows), distance, friction, body / geom / cell (ints), the
 // pyramid's shared D, then per edge: reference acceleration, residual X = J a - aref, V = J search (also: the Hessian weights
@@ -340,9 +354,9 @@ DEV void cross_force(float* r, const float* v, const float* f) {
   r[0] = a[0] + b[0]; r[1] = a[1] + b[1]; r[2] = a[2] + b[2]; r[3] = c[0]; r[4] = c[1]; r[5] = c[2];
 }
 
-DEV float* cn_rec(const ModelDev& m, const float* ws, int c) {
-  if (c < m.cn_k) return (float*)ws + m.off[W_CN_REC] + c * CR_STRIDE;
-  float* g = *(float* const*)(ws + m.off[W_GPTR]);
+DEV float* cn_rec(const ModelDev& m, WSP ws, int c) {
+  if (c < m.cn_k) return WSF(ws) + m.off[W_CN_REC] + c * CR_STRIDE;
+  float* g = *(float* const*)(WSF(ws) + m.off[W_GPTR]);
   return g + (size_t)(c - m.cn_k) * CR_STRIDE;
 }
 
@@ -379,7 +393,7 @@ DEV float ndtri(float p) {
 }
 
 // ------------------------------------------------------------------------------------------ kinematics
-DEV_NOINLINE void kinematics(const ModelDev& m, float* ws, int lane) {
+DEV_NOINLINE void kinematics(const ModelDev& m, WSP ws, int lane) { LANE_REFRESH();
   float* qpos = WS(W_QPOS); float* xpos = WS(W_XPOS); float* xquat = WS(W_XQUAT); float* xmat = WS(W_XMAT);
   float* xipos = WS(W_XIPOS); float* xanchor = WS(W_XANCHOR); float* xaxis = WS(W_XAXIS);
   if (lane == 0) {
@@ -440,7 +454,7 @@ DEV_NOINLINE void kinematics(const ModelDev& m, float* ws, int lane) {
 }
 
 // subtree COM of the (single) tree, spatial inertias about it, motion axes
-DEV_NOINLINE void com_pos(const ModelDev& m, float* ws, int lane) {
+DEV_NOINLINE void com_pos(const ModelDev& m, WSP ws, int lane) { LANE_REFRESH();
   const int nb = MD(nbody), nv = MD(nv);
   const float* xipos = WS(W_XIPOS); const float* xmat = WS(W_XMAT); const float* bmass = WS(W_BMASS);
   float sx = 0.f, sy = 0.f, sz = 0.f, sm = 0.f;
@@ -485,7 +499,7 @@ DEV_NOINLINE void com_pos(const ModelDev& m, float* ws, int lane) {
   SYNC();
 }
 
-DEV_NOINLINE void crb(const ModelDev& m, float* ws, int lane) {
+DEV_NOINLINE void crb(const ModelDev& m, WSP ws, int lane) { LANE_REFRESH();
   const int nb = MD(nbody), nv = MD(nv);
   const float* cinert = WS(W_CINERT); float* crbI = WS(W_CRB); const float* cdof = WS(W_CDOF);
   float* buf = WS(W_BUF); float* M = WS(W_M);
@@ -525,7 +539,7 @@ DEV_NOINLINE void crb(const ModelDev& m, float* ws, int lane) {
 // first j (j + 1) / 2 entries of TB(tri).  The factor is kept UNSCALED: after the call A[j][i] (i < j) holds U_ij * U_jj and
 // invd[j] = 1 / U_jj; chol_solve folds the scaling into its pivots (no column-scaling pass, one warp barrier per column).
 // Entries outside the tree pattern are never touched by the sparse variant and must be zero (chol_solve reads whole rows).
-DEV_NOINLINE void chol_factor(const ModelDev& m, float* A, float* invd, int n, int lane, int sparse) {
+DEV_NOINLINE void chol_factor(const ModelDev& m, float* A, float* invd, int n, int lane, int sparse) { LANE_REFRESH();
 #ifdef COSIM_CHOL_ALLDENSE
   sparse = 0;        // A / B builds: dense elimination everywhere
 #endif
@@ -565,7 +579,7 @@ DEV_NOINLINE void chol_factor(const ModelDev& m, float* A, float* invd, int n, i
   }
 }
 // solves U U^T x = b with the unscaled factor of chol_factor (either variant).  b is destroyed, tmp is scratch, result in out
-DEV_NOINLINE void chol_solve(const float* A, const float* invd, float* b, float* tmp, float* out, int n, int lane) {
+DEV_NOINLINE void chol_solve(const float* A, const float* invd, float* b, float* tmp, float* out, int n, int lane) { LANE_REFRESH();
 #ifdef COSIM_HOST_EMU
   for (int j = n - 1; j >= 0; --j) {            // U z = b, column-oriented from the last dof
     const float zj = b[j] * invd[j], s = zj * invd[j];
@@ -601,7 +615,7 @@ DEV_NOINLINE void chol_solve(const float* A, const float* invd, float* b, float*
 }
 
 // ------------------------------------------------------------------------------------------ velocity / bias
-DEV_NOINLINE void com_vel(const ModelDev& m, float* ws, int lane) {
+DEV_NOINLINE void com_vel(const ModelDev& m, WSP ws, int lane) { LANE_REFRESH();
   const int nv = MD(nv);
   const float* cdof = WS(W_CDOF); float* cdd = WS(W_CDOFDOT); float* cvel = WS(W_CVEL); const float* qvel = WS(W_QVEL);
   FOR_LANE(i, 6) cvel[i] = 0.f;
@@ -638,7 +652,7 @@ DEV_NOINLINE void com_vel(const ModelDev& m, float* ws, int lane) {
 }
 
 // qfrc_bias into `out` (length nv)
-DEV_NOINLINE void rne_bias(const ModelDev& m, float* ws, float* out, int lane) {
+DEV_NOINLINE void rne_bias(const ModelDev& m, WSP ws, float* out, int lane) { LANE_REFRESH();
   const int nb = MD(nbody), nv = MD(nv);
   const float* cdof = WS(W_CDOF); const float* cdd = WS(W_CDOFDOT); const float* cvel = WS(W_CVEL);
   float* cacc = WS(W_CACC); float* cfrc = WS(W_CFRC); const float* cinert = WS(W_CINERT); const float* qvel = WS(W_QVEL);
@@ -702,7 +716,7 @@ DEV int support_bucket(const float* d) {
 }
 struct GeomW { int type; const float* pos; const float* mat; float size[3]; const float* verts; int nvert; float center[3]; const int* sup_off; const float4* sup_cand; };
 
-DEV GeomW make_geom(const ModelDev& m, const float* ws, int g) {
+DEV GeomW make_geom(const ModelDev& m, WSP ws, int g) {
   GeomW G; G.type = TB(geom_type)[g]; G.pos = WS(W_GXPOS) + 3 * g; G.mat = WS(W_GXMAT) + 9 * g;
   G.size[0] = LDG(TB(geom_size) + 3 * g); G.size[1] = LDG(TB(geom_size) + 3 * g + 1); G.size[2] = LDG(TB(geom_size) + 3 * g + 2);
   G.verts = m.hull_verts + 3 * TB(geom_vadr)[g]; G.nvert = TB(geom_vnum)[g];
@@ -754,14 +768,14 @@ DEV void make_frame(float* frame) {
   v3cross(t2, n, t1);
 }
 // write the geometric part of contact record `slot` (one lane)
-DEV void write_contact(const ModelDev& m, float* ws, int slot, const float* pos, const float* normal, float dist, float mu, int body, int g, int cell) {
+DEV void write_contact(const ModelDev& m, WSP ws, int slot, const float* pos, const float* normal, float dist, float mu, int body, int g, int cell) {
   float* r = CREC(slot);
   v3copy(r + CR_POS, pos); v3copy(r + CR_FRAME, normal); make_frame(r + CR_FRAME);
   r[CR_DIST] = dist; r[CR_MU] = mu;
   ((int*)r)[CR_BODY] = body; ((int*)r)[CR_GEOM] = g; ((int*)r)[CR_CELL] = cell;
 }
 // all lanes call with identical arguments; lane 0 writes.  ncon is warp-uniform (register) state
-DEV_NOINLINE void add_contact(const ModelDev& m, float* ws, int& ncon, int& dropped, const float* pos, const float* normal, float dist, int g, int cell, int lane) {
+DEV_NOINLINE void add_contact(const ModelDev& m, WSP ws, int& ncon, int& dropped, const float* pos, const float* normal, float dist, int g, int cell, int lane) { LANE_REFRESH();
   if (ncon >= MD(ncon_max)) { ++dropped; return; }
   if (lane == 0) write_contact(m, ws, ncon, pos, normal, dist, fmaxf(WS(W_SCAL)[0], WS(W_GMU)[g]), TB(geom_body)[g], g, cell);
   ++ncon;
@@ -779,7 +793,7 @@ struct F3 { float x, y, z; };
 // grp = sub | (gsize << 8): the lanes [sub = 0 .. gsize) of one group (mask gmask) work on the same query and split the
 // candidate scan.  (ox, oy) = origin of the local frame the query runs in.  Same arithmetic / tie-breaks as the oracle's
 // serial scan over all hull vertices.
-DEV_NOINLINE F3 support_lane(const ModelDev& m, const float* ws, int g, int grp, unsigned gmask, float ox, float oy, float dx, float dy, float dz) {
+DEV_NOINLINE F3 support_lane(const ModelDev& m, WSP ws, int g, int grp, unsigned gmask, float ox, float oy, float dx, float dy, float dz) {
   const float* M = WS(W_GXMAT) + 9 * g; const float* pos = WS(W_GXPOS) + 3 * g;
   const int type = TB(geom_type)[g];
   const float l0 = M[0] * dx + M[3] * dy + M[6] * dz, l1 = M[1] * dx + M[4] * dy + M[7] * dz, l2 = M[2] * dx + M[5] * dy + M[8] * dz;
@@ -849,7 +863,7 @@ DEV void prism_vertex(const PrismL& P, int i, float* v) {
   v[1] = c == 0 ? P.y[0] : (c == 1 ? P.y[1] : P.y[2]);
   v[2] = i >= 3 ? (c == 0 ? P.z[0] : (c == 1 ? P.z[1] : P.z[2])) : -P.base;
 }
-#define GQ_PARAMS const ModelDev& m, const float* ws, int g, int grp, unsigned gmask, float ox, float oy
+#define GQ_PARAMS const ModelDev& m, WSP ws, int g, int grp, unsigned gmask, float ox, float oy
 #define GQ_ARGS m, ws, g, grp, gmask, ox, oy
 // First MPR object ("shape A"): a terrain prism (mjc_ConvexHField) or a convex geom (mjc_Convex).  A shape provides its
 // portal-vertex type PV (Minkowski-difference point x, y, z + what it needs to recover the witness on A), the Minkowski
@@ -1143,7 +1157,7 @@ DEV float bound_support(const GeomBound& B, const float* d) {
   if (B.cr > 0.f) { const float ad = v3dot(d, B.ca); s = fminf(s, v3dot(d, B.cc) + B.chl * fabsf(ad) + B.cr * sqrtf(fmaxf(0.f, 1.f - ad * ad))); }
   return s;
 }
-DEV void make_bound(const ModelDev& m, const float* ws, int g, float ox, float oy, GeomBound& B) {
+DEV void make_bound(const ModelDev& m, WSP ws, int g, float ox, float oy, GeomBound& B) {
   const float* R = WS(W_GXMAT) + 9 * g; const float* pos = WS(W_GXPOS) + 3 * g; const float* ab = TB(geom_aabb) + 6 * g; const float* bc = TB(geom_bcyl) + 8 * g;
   B.R = R;
   const float o[3] = {pos[0] - ox, pos[1] - oy, pos[2]};
@@ -1180,12 +1194,11 @@ DEV bool prism_culled(const GeomBound& B, const float* x, const float* y, const 
 // per-geom task record in W_GTASK: [cmin, rmin, ncols, nrows, unused, contacts so far, zmin (float), unused]
 // one batch of `n` (<= LANES / gs) narrow-phase queries from the ring (entry = geom << 24 | prism index inside the geom's sub-grid),
 // gs lanes per query; hits are appended in ring (= task) order, honouring the 50-per-geom cap and the store's capacity
-DEV_NOINLINE void mpr_batch(const ModelDev& m, float* ws, int head, int n, int gs, int lane) {
+DEV_NOINLINE void mpr_batch(const ModelDev& m, WSP ws, int head, int n, int gs, int lane) { LANE_REFRESH();
   const int ncol = MD(hf_ncol), nrow = MD(hf_nrow);
   const float sx = MO(hf_sx), sy = MO(hf_sy), sz = MO(hf_sz), base = MO(hf_base);
   const float dx = 2.f * sx / (float)(ncol - 1), dy = 2.f * sy / (float)(nrow - 1);
   int* task = WSI(W_GTASK); const int* ring = WSI(W_RING);
-  int ncon = WSI(W_CNT)[CNT_NCON], dropped = WSI(W_CNT)[CNT_DROPPED];
   const int sub = lane & (gs - 1), k = lane / gs;
   const unsigned gmask = ((gs >= 32 ? 0u : (1u << gs)) - 1u) << (lane & ~(gs - 1));
   int hit = 0, g = 0, cell = -1; float depth = 0.f, nrm[3] = {0.f, 0.f, 0.f}, cp[3] = {0.f, 0.f, 0.f};
@@ -1215,13 +1228,16 @@ DEV_NOINLINE void mpr_batch(const ModelDev& m, float* ws, int head, int n, int g
       const float* gpos = WS(W_GXPOS) + 3 * g;
       float gc[3]; m3mulv(gc, WS(W_GXMAT) + 9 * g, cl);
       gc[0] += gpos[0] - ox; gc[1] += gpos[1] - oy; gc[2] += gpos[2];
+      const int cell_ = ((r * ncol + (c - 1)) << 1) | i;               // before the query: one live value instead of four
       if (mpr_lane(PA, m, ws, g, sub | (gs << 8), gmask, ox, oy, gc, &depth, nrm, cp) == 0 && !(nrm[0] == 0.f && nrm[1] == 0.f && nrm[2] == 0.f) && depth == depth) {
-        hit = (sub == 0); cell = ((r * ncol + (c - 1)) << 1) | i;       // one lane per group reports the contact
+        hit = (sub == 0); cell = cell_;       // one lane per group reports the contact
         cp[0] += ox; cp[1] += oy;
       }
     }
   }
   // ---- append the hits of this batch in task order, honouring the per-geom cap (50) and the capacity of the store
+  task = WSI(W_GTASK);          // re-derived: nothing but the outcome of the query needs to survive the narrow phase in registers
+  int ncon = WSI(W_CNT)[CNT_NCON], dropped = WSI(W_CNT)[CNT_DROPPED];
   const int cap = MD(ncon_max);
   unsigned hits = wballot(hit);
   while (hits) {
@@ -1246,7 +1262,9 @@ DEV_NOINLINE void mpr_batch(const ModelDev& m, float* ws, int head, int n, int g
 }
 
 // part 0: the whole pass; 1: stage 1 only (per-geom bounds and sub-grids -> W_GTASK); 2: stage 2 only (prisms, narrow phase)
-DEV_NOINLINE void collide_hfield_all(const ModelDev& m, float* ws, int lane, int part = 0) {
+// FINE = false: the instance for coarse rasters (cells of 0.2 m and more: a geom covers a handful of prisms) carries neither the
+// bounding-shape culls nor the block-wise sweep (both only skip work; same results), which frees ~25 registers in the prism loop
+template <bool FINE> DEV_NOINLINE void collide_hfield_all(const ModelDev& m, WSP ws, int lane, int part = 0) { LANE_REFRESH();
   const int ng = MD(ngeom), nrow = MD(hf_nrow), ncol = MD(hf_ncol);
   const float sx = MO(hf_sx), sy = MO(hf_sy), sz = MO(hf_sz), base = MO(hf_base);
   const float dx = 2.f * sx / (float)(ncol - 1), dy = 2.f * sy / (float)(nrow - 1);
@@ -1283,7 +1301,7 @@ DEV_NOINLINE void collide_hfield_all(const ModelDev& m, float* ws, int lane, int
           hmax = fmaxf(fmaxf(hmax, fmaxf(h0, h1)), fmaxf(h2, h3));
         }
         hmax *= sz;
-      } else if (m.hf_max8 && c1 >= c0 && r1 >= r0) {        // fine rasters: block maxima (8 x 8 cells per block)
+      } else if (FINE && m.hf_max8 && c1 >= c0 && r1 >= r0) {        // fine rasters: block maxima (8 x 8 cells per block)
         hmax = -INFINITY;
         const int bw = (c1 >> 3) - (c0 >> 3) + 1, bcnt = bw * ((r1 >> 3) - (r0 >> 3) + 1);
         NOUNROLL for (int t = 0; t < bcnt; ++t) hmax = fmaxf(hmax, LDGB(m.hf_max8 + (size_t)((r0 >> 3) + t / bw) * m.hf_mcol + (c0 >> 3) + t % bw));
@@ -1327,12 +1345,12 @@ DEV_NOINLINE void collide_hfield_all(const ModelDev& m, float* ws, int lane, int
     const float ox = dx * (float)cmin - sx, oy = dy * (float)rmin - sy;
     // the bounding-shape culls pay off on fine rasters (dozens to thousands of prisms under a hull); a handful of prisms goes
     // straight to the narrow phase after the reference's height test
-    const bool cull = Tg > 16;
+    const bool cull = FINE && Tg > 16;
     GeomBound B;
     if (cull) make_bound(m, ws, g, ox, oy, B);
     const int per_row = 2 * ncols;
     const int cb0 = cmin >> 3, ncb = ((cmin + ncols - 1) >> 3) - cb0 + 1;
-    const bool blocked = m.hf_max8 != nullptr && Tg > 256 && ncb <= 8;
+    const bool blocked = FINE && m.hf_max8 != nullptr && Tg > 256 && ncb <= 8;
     const int band0 = blocked ? (rmin >> 3) : 0, band1 = blocked ? ((rmin + nrows - 1) >> 3) : 0;
     bool full = false;
     NOUNROLL for (int band = band0; band <= band1 && !full; ++band) {
@@ -1395,12 +1413,12 @@ DEV_NOINLINE void collide_hfield_all(const ModelDev& m, float* ws, int lane, int
 }
 
 // body of the first geom of a contact: 0 (world) for ground contacts; geom-geom contacts carry -2 - geom1 in the record's cell slot
-DEV int contact_body1(const ModelDev& m, const float* ws, int c) { const int cell = CRECI(c)[CR_CELL]; return cell <= -2 ? TB(geom_body)[-2 - cell] : 0; }
+DEV int contact_body1(const ModelDev& m, WSP ws, int c) { const int cell = CRECI(c)[CR_CELL]; return cell <= -2 ? TB(geom_body)[-2 - cell] : 0; }
 
 // mjc_fixNormal restated (oracle/oracle.hpp fix_normal): for smooth primitives the contact normal is rebuilt from the contact
 // point -- sphere: centre to point; cylinder: radial direction of the wall unless the point sits on / near a cap.  A normal
 // from geom 2 is flipped, two normals are averaged.  pos is in world coordinates.
-DEV void fix_normal(const ModelDev& m, const float* ws, int g1, int g2, const float* pos, float* normal) {
+DEV void fix_normal(const ModelDev& m, WSP ws, int g1, int g2, const float* pos, float* normal) {
   float acc[3] = {0.f, 0.f, 0.f}; int n = 0;
   for (int i = 0; i < 2; ++i) {
     const int g = i ? g2 : g1, type = TB(geom_type)[g];
@@ -1541,7 +1559,7 @@ DEV_NOINLINE int box_box(const float* p1, const float* R1, const float* A, const
 // Hits are appended after the ground contacts in pair order.
 // BB: the model has box-box pairs (mjc_BoxBox: several contacts per pair, appended by prefix sum); models without them run the
 // instance that carries none of that code (the headline workload lost 2.5 % to it when there was one instance)
-template <bool BB> DEV_NOINLINE void collide_pairs(const ModelDev& m, float* ws, int lane) {
+template <bool BB> DEV_NOINLINE void collide_pairs(const ModelDev& m, WSP ws, int lane) { LANE_REFRESH();
   const int npair = MD(npair);
   int ncon = WSI(W_CNT)[CNT_NCON], dropped = WSI(W_CNT)[CNT_DROPPED];
   SYNC();
@@ -1603,7 +1621,7 @@ template <bool BB> DEV_NOINLINE void collide_pairs(const ModelDev& m, float* ws,
         const float bound = LDG(TB(geom_rbound) + g1) + LDG(TB(geom_rbound) + g2);
         if (BB && v3dot(dv, dv) <= bound * bound && TB(geom_type)[g1] == GEOM_BOX && TB(geom_type)[g2] == GEOM_BOX) {      // mjc_BoxBox: up to 8 contacts, one lane
           if (sub == 0) {
-            bbout = *(float* const*)(ws + m.off[W_GPTR]) + m.bb_off + 56 * lane;
+            bbout = *(float* const*)(WSF(ws) + m.off[W_GPTR]) + m.bb_off + 56 * lane;
             const float q1[3] = {0.f, 0.f, x1[2]}, q2[3] = {x2[0] - ox, x2[1] - oy, x2[2]};      // frame centred on geom 1 in x, y
             const float sA[3] = {LDG(TB(geom_size) + 3 * g1), LDG(TB(geom_size) + 3 * g1 + 1), LDG(TB(geom_size) + 3 * g1 + 2)};
             const float sB[3] = {LDG(TB(geom_size) + 3 * g2), LDG(TB(geom_size) + 3 * g2 + 1), LDG(TB(geom_size) + 3 * g2 + 2)};
@@ -1668,7 +1686,7 @@ template <bool BB> DEV_NOINLINE void collide_pairs(const ModelDev& m, float* ws,
   SYNC();
 }
 
-DEV_NOINLINE void collide_plane(const ModelDev& m, float* ws, int g, int& ncon, int& dropped, int lane) {
+DEV_NOINLINE void collide_plane(const ModelDev& m, WSP ws, int g, int& ncon, int& dropped, int lane) { LANE_REFRESH();
   const GeomW G = make_geom(m, ws, g);
   const float n[3] = {0.f, 0.f, 1.f};
   if (G.type == GEOM_SPHERE) {
@@ -1761,7 +1779,7 @@ DEV void kb_params(const ModelDev& m, const float* solref, const float* solimp, 
   *B = 2.f / fmaxf(MINVALF, dmax * tc);
 }
 // translational point Jacobian column for dof k at world point (offset from subtree COM), if dof k moves `body`
-DEV void jac_col(const ModelDev& m, const float* ws, int body, int k, const float* off, float* jp) {
+DEV void jac_col(const ModelDev& m, WSP ws, int body, int k, const float* off, float* jp) {
   if ((TB(body_dofmask)[body] >> k) & 1) {
     const float* cd = WS(W_CDOF) + 6 * k; float c[3]; v3cross(c, cd, off);
     jp[0] = cd[3] + c[0]; jp[1] = cd[4] + c[1]; jp[2] = cd[5] + c[2];
@@ -1785,7 +1803,7 @@ DEV void point_vel(const float* v6, const float* off, float* vp) { float c[3]; v
 // that the Jacobian-free formulation takes over.  Both evaluate the same rows.
 enum { FEW_CONTACTS = 8 };
 // the four pyramid-edge projections n +- mu t1, n +- mu t2 of the contact-point velocity given the body velocities `bv` [nbody][6]
-DEV void contact_edge_rows(const ModelDev& m, const float* ws, const float* rec, const float* bv, float* r) {
+DEV void contact_edge_rows(const ModelDev& m, WSP ws, const float* rec, const float* bv, float* r) {
   float off[3], vp[3]; v3sub(off, rec + CR_POS, WS(W_SCOM));
   point_vel(bv + 6 * ((const int*)rec)[CR_BODY], off, vp);
   const int cell = ((const int*)rec)[CR_CELL];
@@ -1795,7 +1813,7 @@ DEV void contact_edge_rows(const ModelDev& m, const float* ws, const float* rec,
   r[0] = vn + v1; r[1] = vn - v1; r[2] = vn + v2; r[3] = vn - v2;
 }
 // per-body contact ranges, number of ground contacts, mask of the bodies in contact
-DEV_NOINLINE void contact_index(const ModelDev& m, float* ws, int ncon, int lane) {
+DEV_NOINLINE void contact_index(const ModelDev& m, WSP ws, int ncon, int lane) { LANE_REFRESH();
   const int nb = MD(nbody);
   int ng_ = 0; unsigned mask = 0;
   NOUNROLL for (int c = lane; c < ncon; c += LANES) {
@@ -1818,7 +1836,7 @@ DEV_NOINLINE void contact_index(const ModelDev& m, float* ws, int ncon, int lane
   SYNC();
 }
 // W_BV[b] = spatial velocity (about the subtree COM) of body b under the generalized velocity `vec`, for the bodies in contact
-DEV_NOINLINE void body_vel(const ModelDev& m, float* ws, const float* vec, int lane) {
+DEV_NOINLINE void body_vel(const ModelDev& m, WSP ws, const float* vec, int lane) { LANE_REFRESH();
   const int nb = MD(nbody); const unsigned cb = (unsigned)WSI(W_CNT)[CNT_CBMASK];
   float* bv = WS(W_BV); const float* cdof = WS(W_CDOF);
   NOUNROLL for (int idx = lane; idx < 6 * nb; idx += LANES) {
@@ -1831,7 +1849,7 @@ DEV_NOINLINE void body_vel(const ModelDev& m, float* ws, const float* vec, int l
   SYNC();
 }
 
-DEV_NOINLINE void make_constraint(const ModelDev& m, float* ws, int ncon, int lane) {
+DEV_NOINLINE void make_constraint(const ModelDev& m, WSP ws, int ncon, int lane) { LANE_REFRESH();
   const int nv = MD(nv), njnt = MD(njnt), neq = MD(neq);
   const float solref[2] = {MO(solref0), MO(solref1)};
   const float solimp[5] = {MO(solimp0), MO(solimp1), MO(solimp2), MO(solimp3), MO(solimp4)};
@@ -1951,7 +1969,7 @@ DEV void row_acc(RowSum& s, float x0, float jv, float a, float D, int kind, floa
   }
   s.cost += 0.5f * D * x * x; s.d0 += D * x * jv; s.d1 += D * jv * jv;
 }
-DEV_NOINLINE RowSum eval_rows(const ModelDev& m, const float* ws, int ncon, float a, bool use_v, int lane) {
+DEV_NOINLINE RowSum eval_rows(const ModelDev& m, WSP ws, int ncon, float a, bool use_v, int lane) { LANE_REFRESH();
   const int nv = MD(nv), njnt = MD(njnt), neq3 = 3 * MD(neq);
   RowSum s = {0.f, 0.f, 0.f};
   FOR_LANE(i, neq3) row_acc(s, WS(W_EQ_X)[i], use_v ? WS(W_EQ_V)[i] : 0.f, a, WS(W_EQ_D)[i], 0, 0.f, 0.f);
@@ -1968,7 +1986,7 @@ DEV_NOINLINE RowSum eval_rows(const ModelDev& m, const float* ws, int ncon, floa
   return s;
 }
 // X = J*q - aref for every row class, given q (length nv).  friction rows' X go to W_TMPW.
-DEV_NOINLINE void compute_jaref(const ModelDev& m, float* ws, int ncon, const float* q, int lane) {
+DEV_NOINLINE void compute_jaref(const ModelDev& m, WSP ws, int ncon, const float* q, int lane) { LANE_REFRESH();
   const int nv = MD(nv), neq3 = 3 * MD(neq);
   FOR_LANE(i, neq3) { const float* J = WS(W_EQ_J) + (size_t)i * nv; float s = 0.f; NOUNROLL for (int k = 0; k < nv; ++k) s += J[k] * q[k]; WS(W_EQ_X)[i] = s - WS(W_EQ_AREF)[i]; }
   FOR_LANE(k, nv) WS(W_TMPW)[k] = q[k] - WS(W_FR_AREF)[k];
@@ -1991,7 +2009,7 @@ DEV_NOINLINE void compute_jaref(const ModelDev& m, float* ws, int ncon, const fl
   }
   SYNC();
 }
-DEV_NOINLINE void compute_jv(const ModelDev& m, float* ws, int ncon, const float* v, int lane) {
+DEV_NOINLINE void compute_jv(const ModelDev& m, WSP ws, int ncon, const float* v, int lane) { LANE_REFRESH();
   const int nv = MD(nv), neq3 = 3 * MD(neq);
   FOR_LANE(i, neq3) { const float* J = WS(W_EQ_J) + (size_t)i * nv; float s = 0.f; NOUNROLL for (int k = 0; k < nv; ++k) s += J[k] * v[k]; WS(W_EQ_V)[i] = s; }
   if (ncon > FEW_CONTACTS) {
@@ -2013,12 +2031,12 @@ DEV_NOINLINE void compute_jv(const ModelDev& m, float* ws, int ncon, const float
   }
   SYNC();
 }
-DEV_NOINLINE void mat_vec(const float* M, const float* x, float* y, int n, int lane) {
+DEV_NOINLINE void mat_vec(const float* M, const float* x, float* y, int n, int lane) { LANE_REFRESH();
   FOR_LANE(i, n) { float s = 0.f; NOUNROLL for (int k = 0; k < n; ++k) s += M[i * n + k] * x[k]; y[i] = s; }
   SYNC();
 }
 // constraint forces from current X; qfrc_constraint -> W_FCON; contact frame forces / world wrenches -> the records; returns constraint cost
-DEV_NOINLINE float update_forces(const ModelDev& m, float* ws, int ncon, int lane) {
+DEV_NOINLINE float update_forces(const ModelDev& m, WSP ws, int ncon, int lane) { LANE_REFRESH();
   const int nv = MD(nv), njnt = MD(njnt), neq = MD(neq), nb = MD(nbody);
   float cost = 0.f;
   FOR_LANE(i, 3 * neq) { const float x = WS(W_EQ_X)[i], D = WS(W_EQ_D)[i]; WS(W_EQ_F)[i] = -D * x; cost += 0.5f * D * x * x; }
@@ -2090,7 +2108,7 @@ DEV_NOINLINE float update_forces(const ModelDev& m, float* ws, int ncon, int lan
   return wsum(cost);
 }
 // total cost at q (Gauss + constraints); leaves X / forces for q
-DEV_NOINLINE float total_cost(const ModelDev& m, float* ws, int ncon, const float* q, float* Mq, int lane) {
+DEV_NOINLINE float total_cost(const ModelDev& m, WSP ws, int ncon, const float* q, float* Mq, int lane) { LANE_REFRESH();
   const int nv = MD(nv);
   mat_vec(WS(W_M), q, Mq, nv, lane);
   if (q != WS(W_QACC)) { FOR_LANE(k, nv) WS(W_QACC)[k] = q[k]; SYNC(); }
@@ -2117,9 +2135,9 @@ static long g_emu_ls_evals = 0;      // analysis aid of the host emulation (test
 #endif
 struct LSPoint { float alpha, cost, d0, d1; };
 #if COSIM_GENERAL
-DEV_NOINLINE RowSum gen_eval_rows(const ModelDev& m, const float* ws, int nefc, float a, int lane);      // engine_general.h
+DEV_NOINLINE RowSum gen_eval_rows(const ModelDev& m, WSP ws, int nefc, float a, int lane);      // engine_general.h
 #endif
-DEV_NOINLINE LSPoint ls_eval(const ModelDev& m, const float* ws, int ncon, float a, float q0, float q1, float q2, int lane) {
+DEV_NOINLINE LSPoint ls_eval(const ModelDev& m, WSP ws, int ncon, float a, float q0, float q1, float q2, int lane) { LANE_REFRESH();
 #if COSIM_GENERAL
   RowSum s = m.general ? gen_eval_rows(m, ws, ncon, a, lane) : eval_rows(m, ws, ncon, a, true, lane);       // general path: `ncon` carries the row count
 #else
@@ -2145,7 +2163,7 @@ DEV int ls_update(LSPoint& p, const LSPoint* cand) {
   }
   return flag;
 }
-DEV_NOINLINE float linesearch(const ModelDev& m, const float* ws, int ncon, float gauss, float q1, float q2, float snorm, float absterms, int lane) {
+DEV_NOINLINE float linesearch(const ModelDev& m, WSP ws, int ncon, float gauss, float q1, float q2, float snorm, float absterms, int lane) { LANE_REFRESH();
   if (snorm < MINVALF) return 0.f;
   const float gtol = fmaxf(MO(tolerance) * MO(ls_tolerance) * snorm * WS(W_SCAL)[1] * (float)imax(1, MD(nv)), 1e-6f * absterms);
   const int maxit = MD(ls_iterations);
@@ -2190,7 +2208,7 @@ DEV uint32_t wxor(uint32_t v) {
 #endif
   return v;
 }
-DEV uint32_t active_set_signature(const ModelDev& m, const float* ws, int ncon, int lane) {
+DEV uint32_t active_set_signature(const ModelDev& m, WSP ws, int ncon, int lane) {
   const int nv = MD(nv), njnt = MD(njnt);
   const float* qacc = WS(W_QACC);
   uint32_t h = 0;
@@ -2207,7 +2225,7 @@ DEV uint32_t active_set_signature(const ModelDev& m, const float* ws, int ncon, 
 }
 // `sig` carries the signature of the factor currently held in W_A: when the active set did not change since the previous
 // iteration the Hessian is the same matrix and only the triangular solves are repeated
-DEV_NOINLINE float newton_direction(const ModelDev& m, float* ws, int ncon, int lane, uint32_t& sig, float* termnorm = nullptr) {
+DEV_NOINLINE float newton_direction(const ModelDev& m, WSP ws, int ncon, int lane, uint32_t& sig, float* termnorm = nullptr) { LANE_REFRESH();
   const int nv = MD(nv), neq = MD(neq);
   float* grad = WS(W_GRAD); float* H = WS(W_A); const float* M = WS(W_M); const float* qacc = WS(W_QACC); const float* Ma = WS(W_MA);
   float gn = 0.f, fn = 0.f;
@@ -2354,10 +2372,15 @@ struct NewtonCarry { float cost; uint32_t sig; };
 #else
 #define NEWTON_LS_SYNC() ((void)0)
 #endif
-template <bool LOCK> DEV_NOINLINE int newton_solve(const ModelDev& m, float* ws, int ncon, int has_rows, int lane, int part, NewtonCarry& nc) {
+template <bool LOCK> DEV_NOINLINE int newton_solve(const ModelDev& m, WSP ws, int ncon, int has_rows, int lane, int part, NewtonCarry& nc) { LANE_REFRESH();
   const int nv = MD(nv), neq = MD(neq);
-  float* qacc = WS(W_QACC); float* Ma = WS(W_MA); float* Mv = WS(W_MV); float* search = WS(W_SEARCH);
-  const float* M = WS(W_M);
+  // the field pointers are re-derived at their uses (one LDS + add) instead of being kept alive across the out-of-line calls, where
+  // the 80-register build spilled five of them to local memory (L1 holds < 10 stack lines per warp): +1.1 % on flamingo_p_v3
+#define qacc WS(W_QACC)
+#define Ma WS(W_MA)
+#define Mv WS(W_MV)
+#define search WS(W_SEARCH)
+#define M WS(W_M)
   constexpr bool lock = LOCK;      // two instances: the lock-step one costs the plain one nothing
   if (!has_rows) {
     if (part != 2 && part != 4) { FOR_LANE(k, nv) { qacc[k] = WS(W_ASMOOTH)[k]; WS(W_WARM)[k] = WS(W_ASMOOTH)[k]; WS(W_FCON)[k] = 0.f; } SYNC(); }
@@ -2423,9 +2446,14 @@ template <bool LOCK> DEV_NOINLINE int newton_solve(const ModelDev& m, float* ws,
   SYNC();
   return iter;
 }
+#undef qacc
+#undef Ma
+#undef Mv
+#undef search
+#undef M
 
 // ------------------------------------------------------------------------------------------ sensors
-DEV_NOINLINE void sensors(const ModelDev& m, float* ws, int lane) {
+DEV_NOINLINE void sensors(const ModelDev& m, WSP ws, int lane) { LANE_REFRESH();
   if (lane == 0) {
     const int b = MD(imu_body);
     float sq[4] = {m.imu_quat[0], m.imu_quat[1], m.imu_quat[2], m.imu_quat[3]};
@@ -2451,7 +2479,7 @@ DEV_NOINLINE void sensors(const ModelDev& m, float* ws, int lane) {
 // stage for every environment of a CTA's pool before any environment enters the next one; forward() below strings them
 // together for one environment (with optional CTA-wide barriers in between).
 // stage 1: kinematics, spatial inertias, mass matrix and its Cholesky factor
-DEV void stage_kin(const ModelDev& m, float* ws, int lane, int part = 0) {
+DEV void stage_kin(const ModelDev& m, WSP ws, int lane, int part = 0) {
   const int nv = MD(nv);
   float* A = WS(W_A);
   if (part != 2) {
@@ -2466,8 +2494,8 @@ DEV void stage_kin(const ModelDev& m, float* ws, int lane, int part = 0) {
   chol_factor(m, A, WS(W_INVD), nv, lane, 1);
 }
 // stage 2: collision
-DEV void stage_collide(const ModelDev& m, float* ws, int lane, int part = 0) {
-  if (MD(ground_type) == 1) { collide_hfield_all(m, ws, lane, part); if (part == 1) return; }
+DEV void stage_collide(const ModelDev& m, WSP ws, int lane, int part = 0) {
+  if (MD(ground_type) == 1) { if (m.hf_fine) collide_hfield_all<true>(m, ws, lane, part); else collide_hfield_all<false>(m, ws, lane, part); if (part == 1) return; }
   else if (part == 1) return;
   else {
     int ncon = 0, dropped = 0;
@@ -2478,7 +2506,7 @@ DEV void stage_collide(const ModelDev& m, float* ws, int lane, int part = 0) {
   if (MD(npair) > 0) { if (m.n_boxbox) collide_pairs<true>(m, ws, lane); else collide_pairs<false>(m, ws, lane); }
 }
 // stage 3: sensors, smooth forces and acceleration, constraint rows
-DEV void stage_smooth(const ModelDev& m, float* ws, int lane) {
+DEV void stage_smooth(const ModelDev& m, WSP ws, int lane) {
   const int nv = MD(nv), nu = MD(nu), njnt = MD(njnt);
   PH_DECL;
   float* A = WS(W_A);
@@ -2517,7 +2545,7 @@ DEV void stage_smooth(const ModelDev& m, float* ws, int lane) {
   SYNC();
 }
 // stage 4: constraint solve; returns the solver iterations
-DEV int stage_newton(const ModelDev& m, float* ws, int lane, int part, NewtonCarry& nc) {
+DEV int stage_newton(const ModelDev& m, WSP ws, int lane, int part, NewtonCarry& nc) {
 #if COSIM_GENERAL
   if (m.general) { if (part == 2 || part == 4) return 0; const int it_ = gen_solve(m, ws, WSI(W_CNT)[CNT_NCON], lane); PH_COUNT(PH_NEWTON_ITERS, it_); return it_; }
 #endif
@@ -2526,10 +2554,10 @@ DEV int stage_newton(const ModelDev& m, float* ws, int lane, int part, NewtonCar
   if (part != 1) PH_COUNT(PH_NEWTON_ITERS, iters);
   return iters;
 }
-DEV int stage_newton(const ModelDev& m, float* ws, int lane) { NewtonCarry nc = {0.f, 0u}; return stage_newton(m, ws, lane, 0, nc); }
+DEV int stage_newton(const ModelDev& m, WSP ws, int lane) { NewtonCarry nc = {0.f, 0u}; return stage_newton(m, ws, lane, 0, nc); }
 // returns solver iterations; the contact count of this pass is left in W_CNT
 // `active` = this warp has an env to advance; `bsync` = CTA-wide phase barriers (must then be called by every warp)
-DEV_NOINLINE int forward(const ModelDev& m, float* ws, int lane, int active = 1, int bsync = 0) {
+DEV_NOINLINE int forward(const ModelDev& m, WSP ws, int lane, int active = 1, int bsync = 0) { LANE_REFRESH();
   PH_DECL;
   int iters = 0;
   // extra barriers INSIDE the three big phases (bits 6, 7, 8 of the mask): the narrower the window of code the warps of an SM
@@ -2560,24 +2588,24 @@ DEV_NOINLINE int forward(const ModelDev& m, float* ws, int lane, int active = 1,
   return iters;
 }
 
-DEV_NOINLINE int bad_state(const ModelDev& m, const float* ws, int lane) {
+DEV_NOINLINE int bad_state(const ModelDev& m, WSP ws, int lane) { LANE_REFRESH();
   int bad = 0;
   FOR_LANE(i, MD(nq)) { float x = WS(W_QPOS)[i]; bad |= !(x == x) || fabsf(x) > 1e10f; }
   FOR_LANE(i, MD(nv)) { float x = WS(W_QVEL)[i]; bad |= !(x == x) || fabsf(x) > 1e10f; }
   return wor(bad);
 }
-DEV_NOINLINE void reset_data(const ModelDev& m, float* ws, int lane) {
+DEV_NOINLINE void reset_data(const ModelDev& m, WSP ws, int lane) { LANE_REFRESH();
   FOR_LANE(i, MD(nq)) WS(W_QPOS)[i] = LDG(TB(qpos0) + i);
   FOR_LANE(i, MD(nv)) { WS(W_QVEL)[i] = 0.f; WS(W_WARM)[i] = 0.f; }
   SYNC();
 }
 
 // what mj_step does around the forward pass: the state check in front of it ...
-DEV void substep_pre(const ModelDev& m, float* ws, int lane) {
+DEV void substep_pre(const ModelDev& m, WSP ws, int lane) {
   if (bad_state(m, ws, lane)) { reset_data(m, ws, lane); if (lane == 0) WSI(W_CNT)[CNT_NAN]++; }
 }
 // ... and the acceleration check + implicitfast integration after it (returns the solver iterations that count)
-DEV_NOINLINE int substep_post(const ModelDev& m, float* ws, int lane, int iters) {
+DEV_NOINLINE int substep_post(const ModelDev& m, WSP ws, int lane, int iters) { LANE_REFRESH();
   const int nv = MD(nv), njnt = MD(njnt);
   { int bad = 0; FOR_LANE(i, nv) { float x = WS(W_QACC)[i]; bad |= !(x == x) || fabsf(x) > 1e10f; }
     if (wor(bad)) { reset_data(m, ws, lane); if (lane == 0) WSI(W_CNT)[CNT_NAN]++; iters = forward(m, ws, lane, 1, 0); } }   // rare: no barriers inside
@@ -2613,7 +2641,7 @@ DEV_NOINLINE int substep_post(const ModelDev& m, float* ws, int lane, int iters)
   PH_MARK(PH_INTEGRATE);
   return iters;
 }
-DEV_NOINLINE int substep(const ModelDev& m, float* ws, int lane, int active = 1, int bsync = 0) {
+DEV_NOINLINE int substep(const ModelDev& m, WSP ws, int lane, int active = 1, int bsync = 0) { LANE_REFRESH();
   if (active) substep_pre(m, ws, lane);
   int iters = forward(m, ws, lane, active, bsync);
   if (active) iters = substep_post(m, ws, lane, iters);
@@ -2622,7 +2650,7 @@ DEV_NOINLINE int substep(const ModelDev& m, float* ws, int lane, int active = 1,
 }
 
 // cfrc_ext of the bodies in contact / connected -> W_CACC region reused as [nbody][6]
-DEV_NOINLINE void cfrc_ext(const ModelDev& m, float* ws, int ncon, int lane) {
+DEV_NOINLINE void cfrc_ext(const ModelDev& m, WSP ws, int ncon, int lane) { LANE_REFRESH();
   const int nb = MD(nbody), neq = MD(neq);
   float* out = WS(W_CACC); const float* scom = WS(W_SCOM);
   FOR_LANE(i, 6 * nb) out[i] = 0.f;

@@ -32,7 +32,7 @@ struct StepArgs {
 #define EST(p, v) __stcs((p), (v))
 #endif
 
-DEV_NOINLINE void load_params(const ModelDev& m, const EnvArrays& E, int env, float* ws, int lane) {
+DEV_NOINLINE void load_params(const ModelDev& m, const EnvArrays& E, int env, WSP ws, int lane) { LANE_REFRESH();
   const int nb = MD(nbody), nv = MD(nv), ng = MD(ngeom), nu = MD(nu);
   FOR_LANE(i, nb) { WS(W_BMASS)[i] = ELD(E.body_mass + (size_t)env * nb + i); WS(W_INVWB)[i] = ELD(E.invw_body + (size_t)env * nb + i); }
   FOR_LANE(i, nv) { WS(W_INVWD)[i] = ELD(E.invw_dof + (size_t)env * nv + i); WS(W_FLOSS)[i] = ELD(E.floss + (size_t)env * nv + i); }
@@ -43,13 +43,13 @@ DEV_NOINLINE void load_params(const ModelDev& m, const EnvArrays& E, int env, fl
   // init_env() makes, recomputed from the counter-based RNG -- only the general constraint path reads them
   if (IF_GENERAL(m)) FOR_LANE(i, 2) WS(W_SCAL)[4 + i] = fmaf(uni(m, env, RNG_MODEL, 0, 1 + i), m.rnd_span[1 + i], m.rnd_lo[1 + i]);
 }
-DEV_NOINLINE void load_state(const ModelDev& m, const EnvArrays& E, int env, float* ws, int lane) {
+DEV_NOINLINE void load_state(const ModelDev& m, const EnvArrays& E, int env, WSP ws, int lane) { LANE_REFRESH();
   const int nq = MD(nq), nv = MD(nv);
   FOR_LANE(i, nq) WS(W_QPOS)[i] = ELD(E.qpos + (size_t)env * nq + i);
   FOR_LANE(i, nv) { WS(W_QVEL)[i] = ELD(E.qvel + (size_t)env * nv + i); WS(W_WARM)[i] = ELD(E.warm + (size_t)env * nv + i); }
   if (MD(npair) > 0) FOR_LANE(i, 4 * PAXIS_SLOTS) WS(W_PAXIS)[i] = ELD(E.paxis + (size_t)env * 4 * PAXIS_SLOTS + i);
 }
-DEV_NOINLINE void store_state(const ModelDev& m, const EnvArrays& E, int env, const float* ws, int lane) {
+DEV_NOINLINE void store_state(const ModelDev& m, const EnvArrays& E, int env, WSP ws, int lane) { LANE_REFRESH();
   const int nq = MD(nq), nv = MD(nv);
   FOR_LANE(i, nq) EST(E.qpos + (size_t)env * nq + i, WS(W_QPOS)[i]);
   FOR_LANE(i, nv) { EST(E.qvel + (size_t)env * nv + i, WS(W_QVEL)[i]); EST(E.warm + (size_t)env * nv + i, WS(W_WARM)[i]); }
@@ -57,7 +57,7 @@ DEV_NOINLINE void store_state(const ModelDev& m, const EnvArrays& E, int env, co
 }
 
 // ------------------------------------------------------------------------------------------ init: randomise + setConst
-DEV_NOINLINE void init_env(const ModelDev& m, const EnvArrays& E, int env, float* ws, int lane) {
+DEV_NOINLINE void init_env(const ModelDev& m, const EnvArrays& E, int env, WSP ws, int lane) { LANE_REFRESH();
   const int nb = MD(nbody), nv = MD(nv), ng = MD(ngeom), nu = MD(nu), njnt = MD(njnt);
   float draw[8];
 #pragma unroll
@@ -144,7 +144,7 @@ DEV int raw_offset(const ModelDev& m, int kind) {
   return 0;
 }
 // raw noisy observations -> W_RAW: [dof_pos | dof_vel | ang_vel | lin_vel | projected_gravity | last_action | height_map]
-DEV_NOINLINE void get_obs(const ModelDev& m, const EnvArrays& E, int env, float* ws, uint32_t nobs, int lane) {
+DEV_NOINLINE void get_obs(const ModelDev& m, const EnvArrays& E, int env, WSP ws, uint32_t nobs, int lane) { LANE_REFRESH();
   const int np = MD(n_dofpos), nvl = MD(n_dofvel), nu = MD(nu), rx = MD(hm_res_x), ry = MD(hm_res_y), nh = rx * ry;
   float* raw = WS(W_RAW); const float* qpos = WS(W_QPOS); const float* qvel = WS(W_QVEL); const float* S = WS(W_SENS);
   FOR_LANE(i, np) raw[i] = qpos[TB(dofpos_qadr)[i]] * LDG(TB(dofpos_fac) + i) + trunc_noise(m, env, nobs, 0, i);
@@ -181,7 +181,7 @@ DEV_NOINLINE void get_obs(const ModelDev& m, const EnvArrays& E, int env, float*
 }
 // noise draw index convention: position in [dof_pos | dof_vel | ang_vel | lin_vel | proj_grav | height_map]
 
-DEV_NOINLINE void concat_obs(const ModelDev& m, const EnvArrays& E, int env, const float* ws, int sim_step, bool stacked, const float* cmd, float* out, int lane) {
+DEV_NOINLINE void concat_obs(const ModelDev& m, const EnvArrays& E, int env, WSP ws, int sim_step, bool stacked, const float* cmd, float* out, int lane) { LANE_REFRESH();
   const int* kind = stacked ? TB(sobs_kind) : TB(nobs_kind); const int* dim = stacked ? TB(sobs_dim) : TB(nobs_dim);
   const float* scale = stacked ? TB(sobs_scale) : TB(nobs_scale); const int* itv = stacked ? TB(sobs_interval) : TB(nobs_interval);
   const int* off = stacked ? TB(sobs_off) : TB(nobs_off); const int n = stacked ? MD(n_sobs) : MD(n_nobs);
@@ -201,7 +201,7 @@ DEV_NOINLINE void concat_obs(const ModelDev& m, const EnvArrays& E, int env, con
   }
 }
 // StateBuildWrapper._build_state + CommandWrapper._apply_command_inplace
-DEV_NOINLINE void build_state(const ModelDev& m, const EnvArrays& E, int env, float* ws, int sim_step, bool reset, const float* cmd, float* state, int lane) {
+DEV_NOINLINE void build_state(const ModelDev& m, const EnvArrays& E, int env, WSP ws, int sim_step, bool reset, const float* cmd, float* state, int lane) { LANE_REFRESH();
   const int ss = MD(stack_size), sd = MD(stacked_dim);
   float* buf = E.obs_buffer + (size_t)env * ss * sd;
   // newest frame straight into state[0:sd]; older frames shift by one (or copy on reset)
@@ -225,7 +225,7 @@ DEV_NOINLINE void build_state(const ModelDev& m, const EnvArrays& E, int env, fl
 }
 
 // ------------------------------------------------------------------------------------------ reset
-DEV_NOINLINE void reset_env(const ModelDev& m, const EnvArrays& E, int env, float* ws, const float* cmd, float* state, int lane) {
+DEV_NOINLINE void reset_env(const ModelDev& m, const EnvArrays& E, int env, WSP ws, const float* cmd, float* state, int lane) { LANE_REFRESH();
   const int nq = MD(nq), nv = MD(nv), nu = MD(nu);
   int* ct = E.counters + (size_t)env * 8;
   const uint32_t nreset = (uint32_t)ct[CT_NRESET], nobs = (uint32_t)ct[CT_NOBS];
@@ -273,7 +273,7 @@ DEV_NOINLINE void reset_env(const ModelDev& m, const EnvArrays& E, int env, floa
   SYNC();
 }
 
-DEV_NOINLINE void dump_contacts(const ModelDev& m, const EnvArrays& E, int env, const float* ws, int ncon, int lane) {
+DEV_NOINLINE void dump_contacts(const ModelDev& m, const EnvArrays& E, int env, WSP ws, int ncon, int lane) { LANE_REFRESH();
   if (!E.dbg_contacts) return;
   const int cap = MD(ncon_max);
   float* out = E.dbg_contacts + (size_t)env * cap * 10;
@@ -292,7 +292,7 @@ DEV_NOINLINE void dump_contacts(const ModelDev& m, const EnvArrays& E, int env, 
 struct StepLocals { int active, sim_step; uint32_t nstep, nobs; float rm, tabs, tsq, tmax; };
 // part 1: pending reset (the reference asserts reset-before-step; the batched engine resets the env instead and skips the
 // step), parameters and state -> workspace, delay filter, PD law, clip.  L.active = 0: nothing more to do for this env.
-DEV void step_prologue(const ModelDev& m, const EnvArrays& E, int env, float* ws, const StepArgs& a, int lane, StepLocals& L) {
+DEV void step_prologue(const ModelDev& m, const EnvArrays& E, int env, WSP ws, const StepArgs& a, int lane, StepLocals& L) {
   const int nu = MD(nu), cd = MD(command_dim), sdim = MD(state_dim);
   int* ct = E.counters + (size_t)env * 8;
   const float* cmd = a.command ? a.command + (size_t)env * cd : nullptr;
@@ -344,7 +344,7 @@ DEV void step_prologue(const ModelDev& m, const EnvArrays& E, int env, float* ws
   SYNC();
 }
 // part 2 (after the sub-steps): cfrc_ext, termination, observations, state build, write-back, bookkeeping and statistics
-DEV void step_epilogue(const ModelDev& m, const EnvArrays& E, int env, float* ws, const StepArgs& a, int lane, const StepLocals& L, int iters) {
+DEV void step_epilogue(const ModelDev& m, const EnvArrays& E, int env, WSP ws, const StepArgs& a, int lane, const StepLocals& L, int iters) {
   const int nv = MD(nv), cd = MD(command_dim), sdim = MD(state_dim), nb = MD(nbody);
   int* ct = E.counters + (size_t)env * 8;
   const float* cmd = a.command ? a.command + (size_t)env * cd : nullptr;
@@ -389,7 +389,7 @@ DEV void step_epilogue(const ModelDev& m, const EnvArrays& E, int env, float* ws
 }
 // One control step of one env by one warp, all stages back to back.
 // `have_env` = this warp owns an env (false for the padding warps of the last CTA); `bsync` = CTA-wide phase barriers
-DEV_NOINLINE void step_env(const ModelDev& m, const EnvArrays& E, int env, float* ws, const StepArgs& a, int lane, int have_env = 1, int bsync = 0) {
+DEV_NOINLINE void step_env(const ModelDev& m, const EnvArrays& E, int env, WSP ws, const StepArgs& a, int lane, int have_env = 1, int bsync = 0) { LANE_REFRESH();
   StepLocals L; L.active = 0;
   if (have_env) step_prologue(m, E, env, ws, a, lane, L);
   const int active = L.active;
@@ -403,7 +403,7 @@ DEV_NOINLINE void step_env(const ModelDev& m, const EnvArrays& E, int env, float
 
 // one raw physics sub-step (mj_step) from the stored state with ctrl = the last applied torque; debug / parity aid
 // mirroring the oracle's orc_substep
-DEV_NOINLINE void substep_env(const ModelDev& m, const EnvArrays& E, int env, float* ws, int lane) {
+DEV_NOINLINE void substep_env(const ModelDev& m, const EnvArrays& E, int env, WSP ws, int lane) { LANE_REFRESH();
   const int nv = MD(nv), nu = MD(nu), nb = MD(nbody);
   load_params(m, E, env, ws, lane);
   load_state(m, E, env, ws, lane);

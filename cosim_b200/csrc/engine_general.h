@@ -17,8 +17,8 @@ enum { GS_QUAD = 0, GS_SATISFIED = 1, GS_LINNEG = 2, GS_LINPOS = 3, GS_CONE = 4 
 // per-contact block: friction[5] (slide, slide, torsion, roll, roll), regularised mu, first row, dim, cone Hessian (6 x 6)
 enum { GC_FRIC = 0, GC_MU = 5, GC_FIRST = 6, GC_DIM = 7, GC_HC = 8, GC_STRIDE = GEN_CON_STRIDE };
 struct GenView { float *J, *W, *D, *R, *aref, *X, *V, *F, *B, *floss; int *type, *id, *state; float* con; };
-DEV GenView gen_view(const ModelDev& m, const float* ws) {
-  float* g = *(float* const*)(ws + m.off[W_GPTR]) + m.gen_off;
+DEV GenView gen_view(const ModelDev& m, WSP ws) {
+  float* g = *(float* const*)(WSF(ws) + m.off[W_GPTR]) + m.gen_off;
   const size_t NR = (size_t)m.gen_rows, nv = (size_t)MD(nv);
   GenView v;
   v.J = g; g += NR * nv; v.W = g; g += NR * nv;
@@ -33,14 +33,14 @@ DEV float gen_impratio(const ModelDev& m) { const float r = MO(impratio); return
 DEV float gen_dot(const float* a, const float* b, int n) { float s = 0.f; NOUNROLL for (int k = 0; k < n; ++k) s += a[k] * b[k]; return s; }
 
 // rotational Jacobian column of dof k for `body` (world frame): the motion axis if k moves the body
-DEV void jac_col_rot(const ModelDev& m, const float* ws, int body, int k, float* jr) {
+DEV void jac_col_rot(const ModelDev& m, WSP ws, int body, int k, float* jr) {
   if ((TB(body_dofmask)[body] >> k) & 1) { const float* cd = WS(W_CDOF) + 6 * k; jr[0] = cd[0]; jr[1] = cd[1]; jr[2] = cd[2]; }
   else { jr[0] = jr[1] = jr[2] = 0.f; }
 }
 
 // rows of the env: equality, dof friction, limits (copied from what make_constraint() prepared), then the contacts.
 // Leaves the row count in W_CNT[CNT_ROWS] and returns it.
-DEV_NOINLINE int gen_make_rows(const ModelDev& m, float* ws, int ncon, int lane) {
+DEV_NOINLINE int gen_make_rows(const ModelDev& m, WSP ws, int ncon, int lane) { LANE_REFRESH();
   const int nv = MD(nv), njnt = MD(njnt), neq = MD(neq), cdim = gen_condim(m), ell = MD(cone) == 1, rpc = gen_rows_per_contact(m);
   const GenView G = gen_view(m, ws);
   const int ncg = imin(ncon, GEN_MAX_CON);
@@ -148,13 +148,13 @@ DEV GenCone gen_cone(const float* cc, float D0, const float* x, int dim) {
   return e;
 }
 // X = J q - aref
-DEV_NOINLINE void gen_jaref(const ModelDev& m, float* ws, int nefc, const float* q, int lane) {
+DEV_NOINLINE void gen_jaref(const ModelDev& m, WSP ws, int nefc, const float* q, int lane) { LANE_REFRESH();
   const GenView G = gen_view(m, ws); const int nv = MD(nv);
   NOUNROLL for (int r = lane; r < nefc; r += LANES) G.X[r] = gen_dot(G.J + (size_t)r * nv, q, nv) - G.aref[r];
   SYNC();
 }
 // forces and states from X; qfrc_constraint -> W_FCON; returns the constraint cost (oracle update_constraint)
-DEV_NOINLINE float gen_update(const ModelDev& m, float* ws, int nefc, int lane) {
+DEV_NOINLINE float gen_update(const ModelDev& m, WSP ws, int nefc, int lane) { LANE_REFRESH();
   const GenView G = gen_view(m, ws); const int nv = MD(nv);
   float cost = 0.f;
   NOUNROLL for (int r = lane; r < nefc; r += LANES) {
@@ -191,7 +191,7 @@ DEV_NOINLINE float gen_update(const ModelDev& m, float* ws, int nefc, int lane) 
   return wsum(cost);
 }
 // rows at X + a V for the line search: cost and its first / second derivative along the search direction (oracle ls_eval)
-DEV_NOINLINE RowSum gen_eval_rows(const ModelDev& m, const float* ws, int nefc, float a, int lane) {
+DEV_NOINLINE RowSum gen_eval_rows(const ModelDev& m, WSP ws, int nefc, float a, int lane) { LANE_REFRESH();
   const GenView G = gen_view(m, ws);
   RowSum s = {0.f, 0.f, 0.f};
   NOUNROLL for (int r = lane; r < nefc; r += LANES) {
@@ -221,7 +221,7 @@ DEV_NOINLINE RowSum gen_eval_rows(const ModelDev& m, const float* ws, int nefc, 
   return s;
 }
 // total cost at q (Gauss + constraints); leaves X / forces / W_FCON for q and M q in Mq (oracle solve(): mulM + jaref + update)
-DEV_NOINLINE float gen_total_cost(const ModelDev& m, float* ws, int nefc, const float* q, float* Mq, int lane) {
+DEV_NOINLINE float gen_total_cost(const ModelDev& m, WSP ws, int nefc, const float* q, float* Mq, int lane) { LANE_REFRESH();
   const int nv = MD(nv);
   mat_vec(WS(W_M), q, Mq, nv, lane);
   if (q != WS(W_QACC)) { FOR_LANE(k, nv) WS(W_QACC)[k] = q[k]; SYNC(); }
@@ -232,7 +232,7 @@ DEV_NOINLINE float gen_total_cost(const ModelDev& m, float* ws, int nefc, const 
   return c + 0.5f * wsum(g);
 }
 // grad = Ma - qfrc_smooth - qfrc_constraint; H = M + sum_quad D J'J + sum_cones Jc' Hc Jc; search = -H^-1 grad.  Returns |grad|
-DEV_NOINLINE float gen_direction(const ModelDev& m, float* ws, int nefc, int ncg, int lane, float* termnorm) {
+DEV_NOINLINE float gen_direction(const ModelDev& m, WSP ws, int nefc, int ncg, int lane, float* termnorm) { LANE_REFRESH();
   const GenView G = gen_view(m, ws); const int nv = MD(nv);
   float* grad = WS(W_GRAD); float* H = WS(W_A); const float* M = WS(W_M); const float* Ma = WS(W_MA);
   float gn = 0.f, fn = 0.f;
@@ -274,7 +274,7 @@ DEV_NOINLINE float gen_direction(const ModelDev& m, float* ws, int nefc, int ncg
   return gn;
 }
 // contact forces in the contact frame -> the records (CR_F: normal, t1, t2; CR_WF: torsion, roll1, roll2) for cfrc_ext; connect forces -> W_EQ_F
-DEV_NOINLINE void gen_publish_forces(const ModelDev& m, float* ws, int nefc, int ncon, int lane) {
+DEV_NOINLINE void gen_publish_forces(const ModelDev& m, WSP ws, int nefc, int ncon, int lane) { LANE_REFRESH();
   const GenView G = gen_view(m, ws); const int ncg = imin(ncon, GEN_MAX_CON), ell = MD(cone) == 1;
   NOUNROLL for (int c = lane; c < ncon; c += LANES) {
     float* rec = CREC(c); float lf[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -292,7 +292,7 @@ DEV_NOINLINE void gen_publish_forces(const ModelDev& m, float* ws, int nefc, int
 }
 
 // Newton on the primal cost with the general rows; same control flow as newton_solve() / the oracle's solve()
-DEV_NOINLINE int gen_newton(const ModelDev& m, float* ws, int nefc, int ncon, int lane) {
+DEV_NOINLINE int gen_newton(const ModelDev& m, WSP ws, int nefc, int ncon, int lane) { LANE_REFRESH();
   const GenView G = gen_view(m, ws); const int nv = MD(nv), ncg = imin(ncon, GEN_MAX_CON);
   float* qacc = WS(W_QACC); float* Ma = WS(W_MA); float* Mv = WS(W_MV); float* search = WS(W_SEARCH); const float* M = WS(W_M);
   const float cs = gen_total_cost(m, ws, nefc, WS(W_ASMOOTH), Ma, lane);
@@ -358,7 +358,7 @@ DEV void gen_qcqp(const float* A, const float* b, const float* fri, float r, int
   for (int i = 0; i < n; ++i) x[i] = y[i] * fri[i];
 }
 // PGS on the dual (oracle solve_pgs): W = M^-1 J' row by row, running v = W f in W_SEARCH, Gauss-Seidel over the rows
-DEV_NOINLINE int gen_pgs(const ModelDev& m, float* ws, int nefc, int ncon, int lane) {
+DEV_NOINLINE int gen_pgs(const ModelDev& m, WSP ws, int nefc, int ncon, int lane) { LANE_REFRESH();
 #ifdef COSIM_AB_NO_PGS
   return 0;
 #endif
@@ -459,7 +459,7 @@ DEV_NOINLINE int gen_pgs(const ModelDev& m, float* ws, int nefc, int ncon, int l
 }
 
 // constraint solve of the general path (stage 4); returns the solver iterations
-DEV_NOINLINE int gen_solve(const ModelDev& m, float* ws, int ncon, int lane) {
+DEV_NOINLINE int gen_solve(const ModelDev& m, WSP ws, int ncon, int lane) { LANE_REFRESH();
   const int nv = MD(nv), nefc = WSI(W_CNT)[CNT_ROWS];
   if (nefc == 0) {
     FOR_LANE(k, nv) { WS(W_QACC)[k] = WS(W_ASMOOTH)[k]; WS(W_WARM)[k] = WS(W_ASMOOTH)[k]; WS(W_FCON)[k] = 0.f; }

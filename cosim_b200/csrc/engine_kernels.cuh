@@ -47,9 +47,10 @@ extern __shared__ __align__(16) float g_smem[];
   }                                                                                                      \
   const ModelDev& m = *(const ModelDev*)g_smem;                                                          \
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb_ = blockDim.x >> 5;                    \
-  float* ws = g_smem + m.shared_floats + (size_t)warp * m.ws_floats;                                     \
+  float* const wsf_ = g_smem + m.shared_floats + (size_t)warp * m.ws_floats;                             \
+  const WSP ws = {(uint32_t)__cvta_generic_to_shared(wsf_)};                                             \
   /* global overflow slot of this resident warp (contact records beyond the shared-memory tier) */       \
-  if (lane == 0) *(float**)(ws + m.off[W_GPTR]) = m.gscratch + (size_t)(blockIdx.x * wpb_ + warp) * m.gslot_floats; \
+  if (lane == 0) *(float**)(wsf_ + m.off[W_GPTR]) = m.gscratch + (size_t)(blockIdx.x * wpb_ + warp) * m.gslot_floats; \
   __syncwarp();
 // The grid is sized to what is resident at once (engine.cu cosim_create); each CTA walks over chunks of wpb environments.
 #define FOR_ENV_CHUNKS() for (int env = blockIdx.x * wpb_ + warp; env - warp < E.N; env += gridDim.x * wpb_)
@@ -163,7 +164,7 @@ __global__ void __launch_bounds__(COSIM_LB, 1) KN(k_step_pool)(const __grid_cons
         int* loc = (int*)(img + wsf); float* locf = img + wsf;
         if (pos > 0) {
           if (!__ldcg(loc + LOC_ACTIVE)) continue;        // the env was reset in the prologue: no step
-          ws_load(ws, img, wsf, lane);
+          ws_load(wsf_, img, wsf, lane);
         }
         const long long t0 = clock64();
         int active = 1;
@@ -171,7 +172,7 @@ __global__ void __launch_bounds__(COSIM_LB, 1) KN(k_step_pool)(const __grid_cons
           const int k = stage_kind(st, nst);
           PH_DECL;
           if (k == SG_PRO) {
-            if (lane == 0) *(float**)(ws + m.off[W_GPTR]) = m.gscratch + (size_t)(blockIdx.x * pa.P + i) * m.gslot_floats;
+            if (lane == 0) *(float**)(wsf_ + m.off[W_GPTR]) = m.gscratch + (size_t)(blockIdx.x * pa.P + i) * m.gslot_floats;
             __syncwarp();
             StepLocals L; step_prologue(m, E, env, ws, a, lane, L);
             if (lane == 0) {
@@ -196,7 +197,7 @@ __global__ void __launch_bounds__(COSIM_LB, 1) KN(k_step_pool)(const __grid_cons
           }
         }
         if (k0 >= SG_KIN && k0 <= SG_NEW && lane == 0) { const long long d = (clock64() - t0) >> 8; s_cost[k0 - 1][i] = (unsigned short)(d > 65535 ? 65535 : d); }
-        if (gend < nst - 1 && active) ws_store(img, ws, wsf, lane);
+        if (gend < nst - 1 && active) ws_store(img, wsf_, wsf, lane);
       }
 #if defined(COSIM_PHASE_TIMING)
       { const long long tw1 = clock64(); __syncthreads();

@@ -196,6 +196,9 @@ static inline void build_model(const void* blob, size_t nbytes, uint64_t seed, u
         mx[(size_t)br * mc + bc] = v;
       }
       m.hf_max8 = push(u, mx); m.hf_mrow = mr; m.hf_mcol = mc;
+      const double cellx = 2.0 * opts[CO_hf_sx] / (ncol - 1), celly = 2.0 * opts[CO_hf_sy] / (nrow - 1);
+      m.hf_fine = std::min(cellx, celly) < 0.2 ? 1 : 0;
+      { const char* e = getenv("COSIM_HF_FINE"); if (e) m.hf_fine = atoi(e) ? 1 : 0; }
     }
   }
   { // Cholesky pair tables (engine_core.h chol_factor).  tri: all pairs (i, k <= i), rows in increasing order, so that the first

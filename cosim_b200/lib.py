@@ -10,7 +10,7 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 BUILD_DIR = os.path.join(CSRC, "_build")
-LIB_PATH = os.path.join(BUILD_DIR, "libcosim_b200.so")
+LIB_PATH = os.environ.get("COSIM_LIB_PATH") or os.path.join(BUILD_DIR, "libcosim_b200.so")      # COSIM_LIB_PATH: a library built elsewhere (tools/build_ab.sh, same-box A / B runs)
 SOURCES = ["engine.cu", "engine_gen.cu", "engine_w24.cu", "engine_w12.cu", "policy.cu"]
 HEADERS = ["engine_core.h", "engine_env.h", "engine_setup.h", "engine_general.h", "engine_kernels.cuh", os.path.join("..", "..", "include", "cosim_b200.h"),
            os.path.join("..", "..", "include", "cosim_blob.h")]
@@ -21,6 +21,8 @@ _lib = None
 
 
 def _stale():
+    if os.environ.get("COSIM_LIB_PATH"):
+        return False
     if not os.path.exists(LIB_PATH):
         return True
     t = os.path.getmtime(LIB_PATH)
