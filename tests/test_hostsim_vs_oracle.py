@@ -276,3 +276,38 @@ def test_spawn_spread_reset():
     # a second reset of the same env draws a new spot (the draw is keyed by the reset counter)
     o.reset()
     assert np.abs(o.get("qpos")[:, :2] - q[:, :2]).max() > 1.0
+
+
+@pytest.mark.parametrize("robot,terrain", [("flamingo_p_v3", "rocky_hard"), ("w4_p_v2", "stairs_up_hard")])
+def test_terrain_pass_instances_agree(robot, terrain, monkeypatch):
+    """collide_hfield_all<false> (coarse rasters: no bounding-shape culls, no block-wise sweep) and <true> only differ in the work they
+    skip: forced onto the same model (COSIM_HF_FINE) they must produce the same contact lists and the same states, bit for bit."""
+    m = build_model(make_config(robot, terrain, random=RANDOM_NONE))
+    N = 4
+    sims = []
+    for fine in ("0", "1"):
+        monkeypatch.setenv("COSIM_HF_FINE", fine)
+        sims.append(HostSim(m, N, seed=1))
+    monkeypatch.delenv("COSIM_HF_FINE")
+    o = Oracle(m, N, seed=1)
+    o.reset()
+    for h in sims:
+        h.reset()
+    rng = np.random.default_rng(5)
+    cap = m.dim("ncon_max")
+    ncon_seen = 0
+    for i in range(4):
+        a = rng.uniform(-1, 1, (N, m.dim("nu")))
+        o.step(a)
+        for h in sims:
+            for k in ("qpos", "qvel", "qacc_warmstart", "torque"):
+                h.set(k, o.get(k))
+            h.substep()
+        c0, c1 = sims[0].get("contacts").reshape(N, cap, 10), sims[1].get("contacts").reshape(N, cap, 10)
+        n0, n1 = sims[0].get("counters")[:, 7], sims[1].get("counters")[:, 7]
+        assert (n0 == n1).all()
+        for e in range(N):
+            assert (c0[e, :n0[e]] == c1[e, :n1[e]]).all()
+        assert (sims[0].get("qvel") == sims[1].get("qvel")).all() and (sims[0].get("qpos") == sims[1].get("qpos")).all()
+        ncon_seen += int(n0.sum())
+    assert ncon_seen > 0

@@ -1,6 +1,8 @@
 #!/usr/bin/env python3
-"""Two barrier masks of the lock-step kernel (COSIM_BSYNC_MASK) against each other: barriers only change WHEN code runs, so the
-states, done flags and statistics must be bit-identical.  mask_check.py maskA maskB [N] [steps] [robot terrain]"""
+"""Two settings of a create-time switch against each other in one process; the results must be bit-identical (states, done flags, qpos,
+qvel, counters, statistics).  Default switch: COSIM_BSYNC_MASK (barriers only change WHEN code runs); COSIM_CHECK_VAR names another one,
+e.g. COSIM_CHECK_VAR=COSIM_HF_FINE mask_check.py 0 1 (the two instances of the terrain pass only differ in the work they skip).
+mask_check.py A B [N] [steps] [robot terrain]"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -14,7 +16,7 @@ cfg = bench.workload_config() if len(sys.argv) < 7 else make_config(sys.argv[5],
 os.environ["COSIM_POOL_R"] = "0"
 envs = []
 for r in (ma, mb):
-    os.environ["COSIM_BSYNC_MASK"] = r
+    os.environ[os.environ.get("COSIM_CHECK_VAR", "COSIM_BSYNC_MASK")] = r
     envs.append(BatchedEnv(cfg, N, seed=0xC051))
 torch.manual_seed(1)
 cmd = torch.rand((N, envs[0].command_dim), device="cuda") * 3 - 1.5
@@ -33,4 +35,4 @@ for k in range(steps):
         sys.exit(1)
 for f in ("qpos", "qvel", "counters", "stats"):
     assert torch.equal(envs[0].get(f), envs[1].get(f)), f
-print(f"mask {ma} == mask {mb} over {steps} steps of {N} envs (bit-identical); episodes {envs[0].stats()['episodes']:.0f}")
+print(f"{os.environ.get('COSIM_CHECK_VAR', 'mask')} {ma} == {mb} over {steps} steps of {N} envs (bit-identical); episodes {envs[0].stats()['episodes']:.0f}")
